@@ -1,0 +1,158 @@
+"""ctypes mirror of include/fdb200.h and the loader of the CUDA library.
+
+There is no CPU fallback: :func:`load_library` raises if ``libfdb200.so`` (the hand-written
+sm_100a kernels + C ABI, built in-tree by ``__graft_entry__.build()``) is missing.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libfdb200.so")
+
+FDB_OK = 0
+FDB_STAGE_WVM, FDB_STAGE_OE, FDB_STAGE_SVM, FDB_STAGE_NMS = 1, 2, 3, 4
+FDB_SV_U8, FDB_SV_F32 = 0, 1
+FDB_KERNEL_RBF = 0
+
+
+class Rect4(C.Structure):
+    _fields_ = [("x1", C.c_int32), ("y1", C.c_int32), ("x2", C.c_int32), ("y2", C.c_int32)]
+
+
+class WvmDesc(C.Structure):
+    _fields_ = [
+        ("filter_size_x", C.c_int32), ("filter_size_y", C.c_int32),
+        ("num_lin_filters", C.c_int32), ("num_filters_per_level", C.c_int32),
+        ("num_levels", C.c_int32), ("num_used_filters", C.c_int32),
+        ("basis_param", C.c_float), ("limit_reliability_filter", C.c_float),
+        ("lin_thresholds", C.POINTER(C.c_float)),
+        ("hk_weights", C.POINTER(C.c_float)),
+        ("app_rsv_convol", C.POINTER(C.c_double)),
+        ("hierarchical_thresholds", C.POINTER(C.c_float)),
+        ("area_cntval", C.POINTER(C.c_int32)),
+        ("area_val", C.POINTER(C.c_double)),
+        ("area_cntrec", C.POINTER(C.c_int32)),
+        ("area_rec", C.POINTER(Rect4)),
+        ("logistic_a", C.c_double), ("logistic_b", C.c_double),
+    ]
+
+
+class SvmDesc(C.Structure):
+    _fields_ = [
+        ("kernel", C.c_int32), ("gamma", C.c_double),
+        ("num_sv", C.c_int32), ("dim", C.c_int32), ("sv_type", C.c_int32),
+        ("support_vectors", C.c_void_p),
+        ("coefficients", C.POINTER(C.c_float)),
+        ("bias", C.c_float), ("threshold", C.c_float),
+        ("logistic_a", C.c_double), ("logistic_b", C.c_double),
+    ]
+
+
+class DetectorDesc(C.Structure):
+    _fields_ = [
+        ("incremental_scale_factor", C.c_double),
+        ("min_scale_factor", C.c_double), ("max_scale_factor", C.c_double),
+        ("patch_width", C.c_int32), ("patch_height", C.c_int32),
+        ("step_x", C.c_int32), ("step_y", C.c_int32),
+        ("oe_dist", C.c_float), ("oe_ratio", C.c_float),
+        ("max_positives_per_frame", C.c_int32),
+    ]
+
+
+class WindowScore(C.Structure):
+    _fields_ = [("fout", C.c_float), ("level", C.c_int32)]
+
+
+class LayerInfo(C.Structure):
+    _fields_ = [
+        ("index", C.c_int32), ("scale", C.c_double),
+        ("width", C.c_int32), ("height", C.c_int32),
+        ("orig_patch_width", C.c_int32), ("orig_patch_height", C.c_int32),
+        ("windows_x", C.c_int32), ("windows_y", C.c_int32),
+        ("first_window", C.c_int64),
+    ]
+
+
+class Detection(C.Structure):
+    _fields_ = [
+        ("frame", C.c_int32), ("layer", C.c_int32), ("x", C.c_int32), ("y", C.c_int32),
+        ("center_x", C.c_int32), ("center_y", C.c_int32),
+        ("width", C.c_int32), ("height", C.c_int32),
+        ("window", C.c_int64),
+        ("wvm_level", C.c_int32), ("wvm_fout", C.c_float),
+        ("wvm_probability", C.c_double),
+        ("svm_distance", C.c_double), ("svm_probability", C.c_double),
+        ("probability", C.c_double),
+        ("positive", C.c_int32), ("reserved", C.c_int32),
+    ]
+
+
+# every symbol include/fdb200.h declares: (name, restype, argtypes)
+_P = C.POINTER
+SYMBOLS = [
+    ("fdb_abi_version", C.c_int, []),
+    ("fdb_last_error", C.c_char_p, []),
+    ("fdb_status_string", C.c_char_p, [C.c_int]),
+    ("fdb_ctx_create", C.c_int, [C.c_int, _P(C.c_void_p)]),
+    ("fdb_ctx_destroy", None, [C.c_void_p]),
+    ("fdb_ctx_stream", C.c_void_p, [C.c_void_p]),
+    ("fdb_ctx_synchronize", C.c_int, [C.c_void_p]),
+    ("fdb_ctx_launch_count", C.c_int64, [C.c_void_p]),
+    ("fdb_host_alloc", C.c_int, [C.c_size_t, _P(C.c_void_p)]),
+    ("fdb_host_free", None, [C.c_void_p]),
+    ("fdb_wvm_create", C.c_int, [C.c_void_p, _P(WvmDesc), _P(C.c_void_p)]),
+    ("fdb_wvm_destroy", None, [C.c_void_p]),
+    ("fdb_wvm_set_limit_reliability_filter", C.c_int, [C.c_void_p, C.c_float]),
+    ("fdb_wvm_get_probability", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("fdb_svm_create", C.c_int, [C.c_void_p, _P(SvmDesc), _P(C.c_void_p)]),
+    ("fdb_svm_destroy", None, [C.c_void_p]),
+    ("fdb_svm_set_threshold", C.c_int, [C.c_void_p, C.c_float]),
+    ("fdb_svm_get_probability", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("fdb_detector_create", C.c_int, [C.c_void_p, _P(DetectorDesc), C.c_void_p, C.c_void_p, _P(C.c_void_p)]),
+    ("fdb_detector_destroy", None, [C.c_void_p]),
+    ("fdb_detector_prepare", C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32]),
+    ("fdb_detector_layers", C.c_int, [C.c_void_p, _P(LayerInfo), C.c_int32, _P(C.c_int32)]),
+    ("fdb_detector_windows_per_frame", C.c_int64, [C.c_void_p]),
+    ("fdb_detector_pyramid_bytes", C.c_int64, [C.c_void_p]),
+    ("fdb_detect_batch", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, _P(C.c_int64)]),
+    ("fdb_detect_batch_device", C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, _P(C.c_int64)]),
+    ("fdb_detect_enqueue_device", C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
+    ("fdb_detect_roi", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int64, _P(C.c_int64)]),
+    ("fdb_extract_patches", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, _P(C.c_int64)]),
+    ("fdb_pyramid_layer", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int64]),
+    ("fdb_detector_last_counts", C.c_int, [C.c_void_p, _P(C.c_int64)]),
+]
+
+_lib = None
+
+
+def load_library(path=None):
+    """Load libfdb200.so and bind every declared symbol. Raises if the library is absent."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = path or LIB_PATH
+    if not os.path.exists(p):
+        raise RuntimeError(
+            "featuredetection_b200: CUDA library %s is missing - run `python -c "
+            "'import __graft_entry__ as g; g.build()'` (there is no CPU fallback)" % p)
+    lib = C.CDLL(p)
+    for name, restype, argtypes in SYMBOLS:
+        fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+        fn.restype = restype
+        fn.argtypes = argtypes
+    if path is None:
+        _lib = lib
+    return lib
+
+
+class FdbError(RuntimeError):
+    def __init__(self, status, message):
+        super().__init__("fdb200 status %d: %s" % (status, message))
+        self.status = status
+
+
+def check(lib, status):
+    if status != FDB_OK:
+        msg = lib.fdb_last_error()
+        raise FdbError(status, msg.decode("utf-8", "replace") if msg else "")

@@ -1,0 +1,270 @@
+"""Seeded synthetic frames and WVM/SVM models.
+
+The reference ships no model weights for this path (every ffpDetectApp .cfg points at absent
+MATLAB files, e.g. ffpDetectApp/FaceFrontal.cfg:7-8,15-16), so benchmarks and parity tests run on
+synthetic models whose *shapes* come from the .cfg files and whose numbers are generated here,
+deterministically, with integer / IEEE-exact numpy arithmetic only (no cv2, no libm-dependent
+steps in the frame generator) so that the GPU box regenerates bit-identical inputs.
+"""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+
+from . import capi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+DATA_DIR = os.path.join(_HERE, "data")
+
+# cfg order of SURVEY.md section 8 (ffpDetectApp/*.cfg:17-23; filter counts from classifierFile names)
+# name: (patch_w, patch_h, inc, min, max, filters_per_level, levels, rbf_r)
+LANDMARK_CONFIGS = [
+    ("FaceFrontal", 20, 20, 0.92, 0.05, 0.16, 14, 20, 0.04),
+    ("FaceLeftProfile", 20, 20, 0.9, 0.09, 0.25, 14, 7, 0.09),
+    ("FaceRightProfile", 20, 20, 0.9, 0.09, 0.25, 14, 7, 0.09),
+    ("RightEyeCenter", 32, 16, 0.85, 0.5, 0.7, 20, 8, 0.0325),
+    ("LeftEyeCenter", 32, 16, 0.9, 0.5, 0.7, 20, 8, 0.0325),
+    ("CenterLipUpperOuter", 24, 24, 0.9, 0.5, 0.7, 30, 8, 0.0195),
+    ("LeftEyeOuterCorner", 24, 24, 0.9, 0.5, 0.7, 20, 11, 0.013),
+    ("RightEyeOuterCorner", 24, 24, 0.9, 0.5, 0.7, 20, 11, 0.013),
+    ("LeftLipCorner", 24, 24, 0.9, 0.5, 0.7, 30, 8, 0.0325),
+    ("RightLipCorner", 24, 24, 0.9, 0.5, 0.7, 30, 8, 0.0325),
+    ("LeftNoseCorner", 24, 24, 0.9, 0.5, 0.7, 30, 8, 0.0325),
+    ("RightNoseCorner", 24, 24, 0.9, 0.5, 0.7, 30, 8, 0.0325),
+    ("NoseTip", 32, 24, 0.9, 0.5, 0.7, 30, 7, 0.026),
+    ("LeftEarCenter", 16, 24, 0.9, 0.5, 0.7, 20, 10, 0.0325),
+    ("RightEarCenter", 16, 24, 0.9, 0.5, 0.7, 20, 10, 0.0325),
+]
+
+
+def landmark_config(name):
+    for i, c in enumerate(LANDMARK_CONFIGS):
+        if c[0] == name:
+            return i, c
+    raise KeyError(name)
+
+
+# ------------------------------------------------------------------------------------------------
+# frames
+# ------------------------------------------------------------------------------------------------
+def _box_sum(a, r):
+    """Exact integer box sum of radius r with edge replication (separable, via cumsum)."""
+    for axis in (0, 1):
+        pad = [(0, 0), (0, 0)]
+        pad[axis] = (r + 1, r)
+        p = np.pad(a, pad, mode="edge")
+        c = np.cumsum(p, axis=axis, dtype=np.int64)
+        n = a.shape[axis]
+        hi = np.take(c, np.arange(2 * r + 1, 2 * r + 1 + n), axis=axis)
+        lo = np.take(c, np.arange(0, n), axis=axis)
+        a = hi - lo
+    return a
+
+
+def synthetic_frame(k, width=640, height=480):
+    """8-bit 1-channel frame k: smooth random field (3x box blur, radius 8) stretched to 0..255
+    plus +-12 noise. Integer arithmetic only => identical on every machine."""
+    rng = np.random.default_rng(1234 + int(k))
+    base = rng.integers(0, 256, (height, width), dtype=np.int64)
+    img = base
+    for _ in range(3):
+        img = _box_sum(img, 8)
+    lo, hi = int(img.min()), int(img.max())
+    img = (img - lo) * 255 // max(hi - lo, 1)
+    noise = rng.integers(-12, 13, (height, width), dtype=np.int64)
+    return np.clip(img + noise, 0, 255).astype(np.uint8)
+
+
+def synthetic_frames(first, count, width=640, height=480):
+    return np.stack([synthetic_frame(first + i, width, height) for i in range(count)])
+
+
+# ------------------------------------------------------------------------------------------------
+# hq64 in numpy (used only to draw support vectors; float32 ops are IEEE-exact in numpy)
+# ------------------------------------------------------------------------------------------------
+def _hq64_np(patch):
+    h, w = patch.shape
+    s = np.float32(255.0) / np.float32(w * h)
+    counts = np.bincount((patch.ravel() >> 2), minlength=64).astype(np.float32)
+    pdf = counts * s
+    cdf = np.zeros(64, np.float32)
+    acc = np.float32(0)
+    for i in range(64):
+        acc = np.float32(acc + pdf[i]) if i else pdf[0]
+        cdf[i] = acc
+    eq = np.floor(cdf.astype(np.float64) + 0.5).astype(np.uint8)
+    return eq[patch >> 2]
+
+
+# ------------------------------------------------------------------------------------------------
+# models
+# ------------------------------------------------------------------------------------------------
+class WvmModel:
+    """Host-side state of a WvmClassifier + logistic in evaluator units
+    (WvmClassifier.hpp:77-130, ProbabilisticWvmClassifier.hpp:35)."""
+
+    def __init__(self, w, h, per_level, levels, basis_param, lin_thresholds, hk_weights,
+                 app_rsv_convol, thresholds, cntval, val, cntrec, rec,
+                 limit_reliability_filter=0.0, num_used=0, logistic_a=0.00556, logistic_b=-2.95):
+        self.w, self.h = int(w), int(h)
+        self.per_level, self.levels = int(per_level), int(levels)
+        self.n = self.per_level * self.levels
+        self.basis_param = np.float32(basis_param)
+        self.lin_thresholds = np.ascontiguousarray(lin_thresholds, np.float32)
+        self.hk_weights = np.ascontiguousarray(hk_weights, np.float32)
+        self.app_rsv_convol = np.ascontiguousarray(app_rsv_convol, np.float64)
+        self.thresholds = np.ascontiguousarray(thresholds, np.float32)
+        self.cntval = np.ascontiguousarray(cntval, np.int32)
+        self.val = np.ascontiguousarray(val, np.float64)
+        self.cntrec = np.ascontiguousarray(cntrec, np.int32)
+        self.rec = np.ascontiguousarray(rec, np.int32).reshape(-1, 4)  # x1,y1,x2,y2
+        self.limit_reliability_filter = float(limit_reliability_filter)
+        self.num_used = int(num_used)
+        self.logistic_a, self.logistic_b = float(logistic_a), float(logistic_b)
+
+    def desc(self):
+        d = capi.WvmDesc()
+        d.filter_size_x, d.filter_size_y = self.w, self.h
+        d.num_lin_filters, d.num_filters_per_level, d.num_levels = self.n, self.per_level, self.levels
+        d.num_used_filters = self.num_used
+        d.basis_param = float(self.basis_param)
+        d.limit_reliability_filter = self.limit_reliability_filter
+        d.lin_thresholds = self.lin_thresholds.ctypes.data_as(C.POINTER(C.c_float))
+        d.hk_weights = self.hk_weights.ctypes.data_as(C.POINTER(C.c_float))
+        d.app_rsv_convol = self.app_rsv_convol.ctypes.data_as(C.POINTER(C.c_double))
+        d.hierarchical_thresholds = self.thresholds.ctypes.data_as(C.POINTER(C.c_float))
+        d.area_cntval = self.cntval.ctypes.data_as(C.POINTER(C.c_int32))
+        d.area_val = self.val.ctypes.data_as(C.POINTER(C.c_double))
+        d.area_cntrec = self.cntrec.ctypes.data_as(C.POINTER(C.c_int32))
+        d.area_rec = self.rec.ctypes.data_as(C.POINTER(capi.Rect4))
+        d.logistic_a, d.logistic_b = self.logistic_a, self.logistic_b
+        d._keepalive = self
+        return d
+
+    def with_thresholds(self, thresholds):
+        m = WvmModel.__new__(WvmModel)
+        m.__dict__.update(self.__dict__)
+        m.thresholds = np.ascontiguousarray(thresholds, np.float32)
+        assert m.thresholds.shape == (self.n,)
+        return m
+
+
+class SvmModel:
+    """Host-side state of an SvmClassifier (RBF) + logistic (SvmClassifier.hpp:165-167)."""
+
+    def __init__(self, support_vectors, coefficients, gamma, bias=0.0, threshold=0.0,
+                 logistic_a=0.00556, logistic_b=-2.95):
+        sv = np.ascontiguousarray(support_vectors)
+        assert sv.ndim == 2 and sv.dtype in (np.uint8, np.float32)
+        self.sv = sv
+        self.coef = np.ascontiguousarray(coefficients, np.float32)
+        self.gamma = float(gamma)
+        self.bias, self.threshold = float(np.float32(bias)), float(np.float32(threshold))
+        self.logistic_a, self.logistic_b = float(logistic_a), float(logistic_b)
+
+    def desc(self):
+        d = capi.SvmDesc()
+        d.kernel = capi.FDB_KERNEL_RBF
+        d.gamma = self.gamma
+        d.num_sv, d.dim = self.sv.shape
+        d.sv_type = capi.FDB_SV_U8 if self.sv.dtype == np.uint8 else capi.FDB_SV_F32
+        d.support_vectors = self.sv.ctypes.data
+        d.coefficients = self.coef.ctypes.data_as(C.POINTER(C.c_float))
+        d.bias, d.threshold = self.bias, self.threshold
+        d.logistic_a, d.logistic_b = self.logistic_a, self.logistic_b
+        d._keepalive = self
+        return d
+
+
+def make_wvm(w, h, per_level, levels, rbf_r, seed, cntval=5, rects_per_value=4):
+    """Synthetic WVM: per filter `cntval` grey values and `rects_per_value` inclusive rectangles
+    for v >= 1 (2..w/3 px extents, so overlaps are rare and the
+    rectangle image stays in the 0..255 range). Filters at wavelet level l >= 1 are zero-mean residuals and app_rsv_convol is the
+    exact squared norm of the CUMULATIVE rectangle image (WvmClassifier.cpp:313-314 accumulates
+    x.p across wavelet levels), so norm = |x - P_cum|^2 >= 0. Thresholds are -inf ("no-exit")
+    until calibrated (see load_thresholds)."""
+    rng = np.random.default_rng(int(seed))
+    n = per_level * levels
+    cv = np.full(n, cntval, np.int32)
+    val = np.zeros((n, cntval), np.float64)
+    cntrec = np.zeros((n, cntval), np.int32)
+    cntrec[:, 1:] = rects_per_value
+    rec = np.zeros((n, cntval - 1, rects_per_value, 4), np.int32)
+    cum = np.zeros((per_level, h, w), np.float64)
+    convol = np.zeros(n, np.float64)
+    for f in range(n):
+        lev, k = divmod(f, per_level)
+        if lev == 0:
+            val[f] = rng.uniform(64.0, 192.0, cntval)
+        else:
+            val[f] = rng.normal(0.0, 24.0 * 0.7 ** lev, cntval)
+        img = np.full((h, w), val[f, 0])
+        for v in range(1, cntval):
+            for r in range(rects_per_value):
+                rw = int(rng.integers(2, max(3, w // 3) + 1)); rh = int(rng.integers(2, max(3, h // 3) + 1))
+                x1 = int(rng.integers(0, w - rw + 1)); x2 = x1 + rw - 1
+                y1 = int(rng.integers(0, h - rh + 1)); y2 = y1 + rh - 1
+                rec[f, v - 1, r] = (x1, y1, x2, y2)
+                img[y1:y2 + 1, x1:x2 + 1] += val[f, v] - val[f, 0]
+        cum[k] += img
+        convol[f] = float(np.sum(cum[k] * cum[k]))
+    weights = np.concatenate([rng.normal(0.0, (l + 1) ** -0.5, l + 1) for l in range(n)]).astype(np.float32)
+    return WvmModel(w, h, per_level, levels, np.float32(rbf_r) / np.float32(65025.0),
+                    np.zeros(n, np.float32), weights, convol,
+                    np.full(n, -np.inf, np.float32), cv, val.ravel(), cntrec.ravel(),
+                    rec.reshape(-1, 4))
+
+
+def make_svm(w, h, seed, num_sv=1024, gamma=7.689e-7):
+    """Synthetic u8 RBF-SVM: support vectors are hq64-equalised crops of block-averaged frames
+    1000..1003 (gamma from adaptiveTrackingApp/default.cfg:148)."""
+    rng = np.random.default_rng(int(seed))
+    svs = np.zeros((num_sv, w * h), np.uint8)
+    small = []
+    for k in range(4):
+        f = synthetic_frame(1000 + k).astype(np.int64)
+        H, W = f.shape
+        f = f[: H // 6 * 6, : W // 6 * 6].reshape(H // 6, 6, W // 6, 6).sum(axis=(1, 3)) // 36
+        small.append(f.astype(np.uint8))
+    for i in range(num_sv):
+        img = small[i % 4]
+        y = int(rng.integers(0, img.shape[0] - h)); x = int(rng.integers(0, img.shape[1] - w))
+        svs[i] = _hq64_np(img[y:y + h, x:x + w]).ravel()
+    coef = rng.normal(0.0, 1.0, num_sv).astype(np.float32)
+    return SvmModel(svs, coef, gamma)
+
+
+def thresholds_path(name, profile="realistic"):
+    return os.path.join(DATA_DIR, "thresholds_%s_%s.json" % (name, profile))
+
+
+def load_thresholds(name, profile="realistic"):
+    """Hierarchical thresholds calibrated offline by oracle/tools/calibrate_thresholds.py to the
+    survival profile S(l) = max(0.5^(l+1), 2e-3) (stored as float32 bit patterns)."""
+    with open(thresholds_path(name, profile)) as fh:
+        d = json.load(fh)
+    return np.array(d["thresholds_u32"], dtype=np.uint32).view(np.float32)
+
+
+def landmark_models(name, profile="realistic"):
+    """(detector kwargs, WvmModel, SvmModel) for one ffpDetectApp landmark cfg.
+    profile: "realistic" (calibrated thresholds) or "no-exit" (all thresholds -inf)."""
+    idx, (nm, pw, ph, inc, mn, mx, per_level, levels, r) = landmark_config(name)
+    wvm = make_wvm(pw, ph, per_level, levels, r, seed=100 + idx)
+    svm = make_svm(pw, ph, seed=300 + idx)
+    if profile == "realistic":
+        wvm = wvm.with_thresholds(load_thresholds(name, profile))
+    elif profile != "no-exit":
+        raise ValueError(profile)
+    det = dict(incremental_scale_factor=float(np.float32(inc)), min_scale_factor=float(np.float32(mn)),
+               max_scale_factor=float(np.float32(mx)), patch_width=pw, patch_height=ph,
+               step_x=1, step_y=1, oe_dist=5.0, oe_ratio=0.0)
+    return det, wvm, svm
+
+
+def detector_desc(**kw):
+    d = capi.DetectorDesc()
+    for k, v in kw.items():
+        setattr(d, k, v)
+    return d

@@ -1,0 +1,301 @@
+/*
+ * fdb200.h - C ABI of the B200-native sliding-window landmark detector hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++/torch/OpenCV types.
+ * The reference (elador/FeatureDetection) has no FFI of its own; its seams are the C++
+ * abstract classes
+ *     imageprocessing::FeatureExtractor / PyramidFeatureExtractor
+ *         (libImageProcessing/include/imageprocessing/FeatureExtractor.hpp:32-53,
+ *          PyramidFeatureExtractor.hpp:52-118)
+ *     classification::ProbabilisticClassifier
+ *         (libClassification/include/classification/ProbabilisticClassifier.hpp:33,
+ *          BinaryClassifier.hpp:32,42)
+ *     detection::Detector
+ *         (libDetection/include/detection/Detector.hpp:59-79)
+ * Every entry point below names the reference call it replaces.  The C++ adapters that
+ * implement those three interfaces on top of this ABI live in adapters/ and
+ * INTEGRATION.md shows how a maintainer links them.
+ *
+ * Conventions
+ *  - every function returns an fdb_status (0 = ok), never throws, never takes ownership
+ *    of caller memory; fdb_last_error() returns a thread-local message for the last failure.
+ *  - "host" pointers are ordinary (pageable or pinned) CPU memory; "device" pointers are
+ *    CUDA device memory of the context's device.
+ *  - a context is bound to one CUDA device; objects created from it may be used by one
+ *    host thread at a time (same contract as the reference objects, which are not re-entrant).
+ *  - there is NO CPU fallback: if the CUDA device is missing the create call fails.
+ */
+#ifndef FDB200_H_
+#define FDB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define FDB_API __declspec(dllexport)
+#else
+#define FDB_API __attribute__((visibility("default")))
+#endif
+
+#define FDB_ABI_VERSION 1
+
+typedef enum fdb_status {
+	FDB_OK = 0,
+	FDB_ERR_INVALID_ARGUMENT = 1, /* std::invalid_argument in the reference */
+	FDB_ERR_RUNTIME = 2,          /* std::runtime_error in the reference */
+	FDB_ERR_CUDA = 3,             /* CUDA runtime/driver failure */
+	FDB_ERR_NO_DEVICE = 4,        /* no usable sm_100 device: there is no CPU fallback */
+	FDB_ERR_UNSUPPORTED = 5,      /* model outside the exactness envelope */
+	FDB_ERR_OVERFLOW = 6          /* a fixed-capacity result buffer was too small */
+} fdb_status;
+
+typedef struct fdb_ctx fdb_ctx;
+typedef struct fdb_wvm fdb_wvm;
+typedef struct fdb_svm fdb_svm;
+typedef struct fdb_detector fdb_detector;
+
+/* ------------------------------------------------------------------------------------------
+ * Model descriptors (host memory, copied during create)
+ * ---------------------------------------------------------------------------------------- */
+
+/* One rectangle of a rectangle-approximated reduced set vector; corners are INCLUSIVE.
+ * Mirrors WvmClassifier::TRec {x1,x2,y1,y2} (WvmClassifier.hpp:103-105). */
+typedef struct fdb_rect4 {
+	int32_t x1, y1, x2, y2;
+} fdb_rect4;
+
+/* Wavelet reduced vector machine + logistic.
+ * Replaces the state that WvmClassifier::loadFromMatlab (WvmClassifier.cpp:348-770) and
+ * ProbabilisticWvmClassifier::load (ProbabilisticWvmClassifier.cpp:75-85) build:
+ * numbers are given already in evaluator units (the loader's x255, /65025 conversions applied). */
+typedef struct fdb_wvm_desc {
+	int32_t filter_size_x;         /* WvmClassifier::filter_size_x */
+	int32_t filter_size_y;
+	int32_t num_lin_filters;       /* numLinFilters (e.g. 280) */
+	int32_t num_filters_per_level; /* numFiltersPerLevel (e.g. 14) */
+	int32_t num_levels;            /* numLevels (e.g. 20) */
+	int32_t num_used_filters;      /* 0 or > num_lin_filters: use all (setNumUsedFilters, WvmClassifier.cpp:151) */
+	float basis_param;             /* basisParam */
+	float limit_reliability_filter;/* cfg "threshold"; added to every hierarchical threshold (WvmClassifier.cpp:165) */
+	const float* lin_thresholds;   /* [num_lin_filters] */
+	const float* hk_weights;       /* packed lower triangle: filter l owns l+1 weights at offset l(l+1)/2 */
+	const double* app_rsv_convol;  /* [num_lin_filters] */
+	const float* hierarchical_thresholds; /* [num_lin_filters] hierarchicalThresholdsFromFile */
+	/* Area of filter f: grey values val[0..cntval) and, for v >= 1, cntrec rectangles.
+	 * Flattened: value slot s = val_offset[f] + v. */
+	const int32_t* area_cntval;    /* [num_lin_filters] */
+	const double* area_val;        /* [sum cntval] */
+	const int32_t* area_cntrec;    /* [sum cntval]; entry for v == 0 is ignored */
+	const fdb_rect4* area_rec;     /* [sum cntrec over v >= 1], in (f, v, r) order */
+	double logistic_a;             /* ProbabilisticWvmClassifier::logisticA (default 0.00556) */
+	double logistic_b;             /* ProbabilisticWvmClassifier::logisticB (default -2.95) */
+} fdb_wvm_desc;
+
+typedef enum fdb_kernel_kind {
+	FDB_KERNEL_RBF = 0 /* classification::RbfKernel (RbfKernel.hpp:32-40) */
+} fdb_kernel_kind;
+
+typedef enum fdb_sv_type {
+	FDB_SV_U8 = 0, /* CV_8U support vectors: exact integer SSD (RbfKernel.hpp:78-88) */
+	FDB_SV_F32 = 1 /* CV_32F support vectors: float32 sequential SSD (RbfKernel.hpp:97-108) */
+} fdb_sv_type;
+
+/* Support vector machine + logistic.
+ * Replaces SvmClassifier::setSvmParameters (SvmClassifier.cpp:62-66),
+ * VectorMachineClassifier::setThreshold and ProbabilisticSvmClassifier's logistic
+ * (ProbabilisticSvmClassifier.cpp:50-58). */
+typedef struct fdb_svm_desc {
+	int32_t kernel;          /* fdb_kernel_kind */
+	double gamma;            /* RbfKernel::gamma */
+	int32_t num_sv;
+	int32_t dim;             /* elements per support vector (patch w*h for u8) */
+	int32_t sv_type;         /* fdb_sv_type */
+	const void* support_vectors; /* [num_sv][dim] row-major, u8 or f32 */
+	const float* coefficients;   /* [num_sv] */
+	float bias;              /* VectorMachineClassifier::bias */
+	float threshold;         /* VectorMachineClassifier::threshold */
+	double logistic_a;
+	double logistic_b;
+} fdb_svm_desc;
+
+/* Image pyramid + window extraction parameters.
+ * Replaces ImagePyramid(double inc, double min, double max) (ImagePyramid.cpp:79-92),
+ * DirectPyramidFeatureExtractor(pyramid, w, h) (DirectPyramidFeatureExtractor.cpp:36-37) with
+ * a GrayscaleFilter image filter and a HistEq64Filter patch filter (ffpDetectApp.cpp:407-415),
+ * SlidingWindowDetector(classifier, extractor, stepX, stepY) (SlidingWindowDetector.cpp:27) and
+ * OverlapElimination(dist, ratio) (OverlapElimination.cpp:30). */
+typedef struct fdb_detector_desc {
+	double incremental_scale_factor; /* cfg pyramid.incrementalScaleFactor (float widened, as the app does) */
+	double min_scale_factor;
+	double max_scale_factor;
+	int32_t patch_width;
+	int32_t patch_height;
+	int32_t step_x;   /* SlidingWindowDetector stepSizeX (default 1) */
+	int32_t step_y;
+	float oe_dist;    /* overlapElimination.dist (default 5.0) */
+	float oe_ratio;   /* overlapElimination.ratio (default 0.0) */
+	int32_t max_positives_per_frame; /* capacity of the per-frame stage-1 candidate list; 0 = default 4096 */
+} fdb_detector_desc;
+
+/* ------------------------------------------------------------------------------------------
+ * Result records
+ * ---------------------------------------------------------------------------------------- */
+
+/* Dense stage-1 record, one per window in canonical order (layer index asc, y, x);
+ * = the pair<int,double> of WvmClassifier::computeHyperplaneDistance (WvmClassifier.cpp:100-149),
+ * fout kept in its native float. */
+typedef struct fdb_window_score {
+	float fout;
+	int32_t level; /* index of the last evaluated filter */
+} fdb_window_score;
+
+/* Geometry of one pyramid layer as ImagePyramidLayer / PyramidFeatureExtractor expose it. */
+typedef struct fdb_layer_info {
+	int32_t index;        /* ImagePyramidLayer::getIndex */
+	double scale;         /* theoretical scale factor (getScaleFactor) */
+	int32_t width, height;/* layer image size (getLayerSizes) */
+	int32_t orig_patch_width, orig_patch_height; /* getPatchSizes: cvRound(patch / scale) */
+	int32_t windows_x, windows_y; /* window grid of the full-frame scan */
+	int64_t first_window; /* canonical index of this layer's first window */
+} fdb_layer_info;
+
+/* One classified patch = detection::ClassifiedPatch + imageprocessing::Patch geometry
+ * (ClassifiedPatch.hpp:18-97, Patch.hpp:241-243). */
+typedef struct fdb_detection {
+	int32_t frame;
+	int32_t layer;          /* pyramid layer index */
+	int32_t x, y;           /* top-left corner inside the layer */
+	int32_t center_x, center_y;   /* Patch::getX/getY (original image coordinates) */
+	int32_t width, height;  /* Patch::getWidth/getHeight (original image size) */
+	int64_t window;         /* canonical window index inside the frame */
+	int32_t wvm_level;
+	float wvm_fout;
+	double wvm_probability; /* ProbabilisticWvmClassifier::getProbability */
+	double svm_distance;    /* SvmClassifier::computeHyperplaneDistance (NaN if stage not run) */
+	double svm_probability; /* ProbabilisticSvmClassifier::getProbability */
+	double probability;     /* ClassifiedPatch::getProbability as the reference returns it */
+	int32_t positive;
+	int32_t reserved;
+} fdb_detection;
+
+typedef enum fdb_stage {
+	FDB_STAGE_WVM = 1,      /* SlidingWindowDetector::detect: windows with wvm positive */
+	FDB_STAGE_OE = 2,       /* + OverlapElimination::eliminate */
+	FDB_STAGE_SVM = 3,      /* + SVM classify, positives only, sorted (FiveStage detect(Mat,Rect)) */
+	FDB_STAGE_NMS = 4       /* + grid NMS of FiveStageSlidingWindowDetector::detect(Mat) */
+} fdb_stage;
+
+/* ------------------------------------------------------------------------------------------
+ * Context
+ * ---------------------------------------------------------------------------------------- */
+FDB_API int fdb_abi_version(void);
+FDB_API const char* fdb_last_error(void);
+FDB_API const char* fdb_status_string(int status);
+
+/* device < 0: use the current CUDA device. Fails with FDB_ERR_NO_DEVICE without a GPU. */
+FDB_API int fdb_ctx_create(int device, fdb_ctx** out);
+FDB_API void fdb_ctx_destroy(fdb_ctx* ctx);
+/* The CUDA stream (cudaStream_t) all work of this context is enqueued on. */
+FDB_API void* fdb_ctx_stream(fdb_ctx* ctx);
+FDB_API int fdb_ctx_synchronize(fdb_ctx* ctx);
+/* Number of kernel launches issued by this context so far (for bench accounting). */
+FDB_API int64_t fdb_ctx_launch_count(fdb_ctx* ctx);
+
+/* Pinned host memory for frame/result staging (optional; any host memory is accepted). */
+FDB_API int fdb_host_alloc(size_t bytes, void** out);
+FDB_API void fdb_host_free(void* p);
+
+/* ------------------------------------------------------------------------------------------
+ * Classifiers  (classification::ProbabilisticClassifier surface)
+ * ---------------------------------------------------------------------------------------- */
+FDB_API int fdb_wvm_create(fdb_ctx* ctx, const fdb_wvm_desc* desc, fdb_wvm** out);
+FDB_API void fdb_wvm_destroy(fdb_wvm* wvm);
+/* WvmClassifier::setLimitReliabilityFilter (WvmClassifier.cpp:165-181) */
+FDB_API int fdb_wvm_set_limit_reliability_filter(fdb_wvm* wvm, float value);
+
+/* ProbabilisticWvmClassifier::getProbability (ProbabilisticWvmClassifier.cpp:42-54) over a batch
+ * of n already-extracted feature vectors (u8, filter_size_x*filter_size_y each, continuous).
+ * Any output pointer may be NULL. */
+FDB_API int fdb_wvm_get_probability(fdb_wvm* wvm, const uint8_t* patches_host, int64_t n,
+		int32_t* level_out, float* fout_out, double* probability_out, uint8_t* positive_out);
+
+FDB_API int fdb_svm_create(fdb_ctx* ctx, const fdb_svm_desc* desc, fdb_svm** out);
+FDB_API void fdb_svm_destroy(fdb_svm* svm);
+FDB_API int fdb_svm_set_threshold(fdb_svm* svm, float threshold);
+
+/* ProbabilisticSvmClassifier::getProbability / SvmClassifier::computeHyperplaneDistance
+ * (ProbabilisticSvmClassifier.cpp:50-58, SvmClassifier.cpp:55-60) over n feature vectors
+ * of the SVM's sv_type (u8 or f32), dim elements each. */
+FDB_API int fdb_svm_get_probability(fdb_svm* svm, const void* vectors_host, int64_t n,
+		double* distance_out, double* probability_out, uint8_t* positive_out);
+
+/* ------------------------------------------------------------------------------------------
+ * Detector  (PyramidFeatureExtractor + Detector surface)
+ * ---------------------------------------------------------------------------------------- */
+/* svm may be NULL (plain SlidingWindowDetector, ffpDetectApp "single" with pwvm). */
+FDB_API int fdb_detector_create(fdb_ctx* ctx, const fdb_detector_desc* desc,
+		fdb_wvm* wvm, fdb_svm* svm, fdb_detector** out);
+FDB_API void fdb_detector_destroy(fdb_detector* det);
+
+/* Fix the frame geometry (ImagePyramid::update / createLayers sizing, ImagePyramid.cpp:170-198)
+ * and allocate device buffers for up to max_batch frames. Must be called before detect. */
+FDB_API int fdb_detector_prepare(fdb_detector* det, int32_t width, int32_t height, int32_t max_batch);
+
+/* PyramidFeatureExtractor getters (getLayerScales/getLayerSizes/getPatchSizes,
+ * PyramidFeatureExtractor.hpp:72-118). Returns the number of layers; fills up to cap entries. */
+FDB_API int fdb_detector_layers(fdb_detector* det, fdb_layer_info* out, int32_t cap, int32_t* n_layers);
+FDB_API int64_t fdb_detector_windows_per_frame(fdb_detector* det);
+/* Bytes of all pyramid images of one frame (the materialised pyramid) */
+FDB_API int64_t fdb_detector_pyramid_bytes(fdb_detector* det);
+
+/* Detector::detect over a batch of frames in HOST memory (8-bit, 1 channel, row pitch in bytes).
+ *   stage           how far to run the five-stage cascade (fdb_stage)
+ *   dense_out       NULL or host [n_frames * windows_per_frame] stage-1 records
+ *   detections_out  host array of capacity det_cap; *n_detections receives the count
+ * Copies frames H2D, runs the whole path, copies results D2H and returns after completion.
+ * Replaces FiveStageSlidingWindowDetector::detect(Mat) (FiveStageSlidingWindowDetector.cpp:187-322)
+ * / SlidingWindowDetector::detect(Mat) (SlidingWindowDetector.cpp:40-50). */
+FDB_API int fdb_detect_batch(fdb_detector* det, const uint8_t* frames_host, int64_t pitch,
+		int32_t n_frames, int32_t stage, fdb_window_score* dense_out,
+		fdb_detection* detections_out, int64_t det_cap, int64_t* n_detections);
+
+/* Same, frames already resident in device memory (pitch == width, frames contiguous);
+ * no input copy inside. dense_out_device may be NULL or a DEVICE pointer. */
+FDB_API int fdb_detect_batch_device(fdb_detector* det, const uint8_t* frames_device,
+		int32_t n_frames, int32_t stage, fdb_window_score* dense_out_device,
+		fdb_detection* detections_out, int64_t det_cap, int64_t* n_detections);
+
+/* Stage-1 only on device-resident frames, results stay on the device; returns without
+ * synchronising (used for kernel timing). dense_out_device may be NULL. */
+FDB_API int fdb_detect_enqueue_device(fdb_detector* det, const uint8_t* frames_device,
+		int32_t n_frames, fdb_window_score* dense_out_device);
+
+/* ROI variant: Detector::detect(Mat, Rect) (FiveStageSlidingWindowDetector.cpp:331-380,
+ * SlidingWindowDetector.cpp:53-79): one frame, windows restricted by roi {x,y,w,h}. */
+FDB_API int fdb_detect_roi(fdb_detector* det, const uint8_t* frame_host, int64_t pitch,
+		int32_t roi_x, int32_t roi_y, int32_t roi_w, int32_t roi_h, int32_t stage,
+		fdb_detection* detections_out, int64_t det_cap, int64_t* n_detections);
+
+/* PyramidFeatureExtractor::extract(stepX, stepY) (DirectPyramidFeatureExtractor.cpp:75-123):
+ * writes the HistEq64-filtered patch of every window of one frame, canonical order,
+ * patch_w*patch_h bytes each, to patches_out (host). */
+FDB_API int fdb_extract_patches(fdb_detector* det, const uint8_t* frame_host, int64_t pitch,
+		uint8_t* patches_out, int64_t cap_windows, int64_t* n_windows);
+
+/* ImagePyramid::getLayers image data of one frame: copies layer `layer_index`
+ * (width*height bytes) to out (host). */
+FDB_API int fdb_pyramid_layer(fdb_detector* det, const uint8_t* frame_host, int64_t pitch,
+		int32_t layer_index, uint8_t* out, int64_t cap);
+
+/* Per-stage counters of the last detect call (TOT/TACC-style counters, ffpDetectApp.cpp:650-657):
+ * [0] windows, [1] wvm positives, [2] after OE, [3] svm positives, [4] after NMS. */
+FDB_API int fdb_detector_last_counts(fdb_detector* det, int64_t counts[5]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FDB200_H_ */

@@ -1,0 +1,279 @@
+"""ctypes front-end of the CPU oracle (libfdoracle.so) and of the compiled reference (oracle/_ref).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and the cpu_baseline /
+--impl reference legs of bench.py. The product package never imports this module.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from featuredetection_b200 import capi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+ORACLE_LIB = os.path.join(_HERE, "libfdoracle.so")
+REF_LIB = os.path.join(_HERE, "_ref", "libfdref.so")
+
+
+def build(force=False):
+    """make -C oracle (compiles fd_oracle.c and, when /root/reference exists, oracle/_ref)."""
+    if force or not os.path.exists(ORACLE_LIB) or (os.path.isdir("/root/reference") and not os.path.exists(REF_LIB)):
+        subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
+
+
+class _Pyramid(C.Structure):
+    _fields_ = [
+        ("octave_layer_count", C.c_int), ("incremental_scale_factor", C.c_double),
+        ("min_scale_factor", C.c_double), ("max_scale_factor", C.c_double),
+        ("image_width", C.c_int), ("image_height", C.c_int),
+        ("n_layers", C.c_int), ("layers", C.c_void_p),
+        ("n_resize", C.c_int), ("n_pyrdown", C.c_int),
+        ("px_resize", C.c_int64), ("px_pyrdown", C.c_int64),
+    ]
+
+
+class _Layer(C.Structure):
+    _fields_ = [("index", C.c_int), ("scale", C.c_double), ("width", C.c_int), ("height", C.c_int),
+                ("data", C.POINTER(C.c_uint8))]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(ORACLE_LIB)
+        L.fdo_cvround.restype = C.c_int; L.fdo_cvround.argtypes = [C.c_double]
+        L.fdo_resize_linear_u8.restype = None
+        L.fdo_resize_linear_u8.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int]
+        L.fdo_pyrdown_u8.restype = None
+        L.fdo_pyrdown_u8.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.fdo_pyramid_build.restype = C.POINTER(_Pyramid)
+        L.fdo_pyramid_build.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double]
+        L.fdo_pyramid_free.restype = None; L.fdo_pyramid_free.argtypes = [C.POINTER(_Pyramid)]
+        L.fdo_hq64.restype = None; L.fdo_hq64.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        L.fdo_wvm_create.restype = C.c_void_p; L.fdo_wvm_create.argtypes = [C.POINTER(capi.WvmDesc)]
+        L.fdo_wvm_free.restype = None; L.fdo_wvm_free.argtypes = [C.c_void_p]
+        L.fdo_wvm_eval.restype = None
+        L.fdo_wvm_eval.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_float)]
+        L.fdo_wvm_eval_all_levels.restype = None
+        L.fdo_wvm_eval_all_levels.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.fdo_wvm_classify.restype = C.c_int; L.fdo_wvm_classify.argtypes = [C.c_void_p, C.c_int, C.c_float]
+        L.fdo_wvm_probability.restype = C.c_double; L.fdo_wvm_probability.argtypes = [C.c_void_p, C.c_float]
+        L.fdo_svm_create.restype = C.c_void_p; L.fdo_svm_create.argtypes = [C.POINTER(capi.SvmDesc)]
+        L.fdo_svm_free.restype = None; L.fdo_svm_free.argtypes = [C.c_void_p]
+        L.fdo_svm_distance.restype = C.c_double; L.fdo_svm_distance.argtypes = [C.c_void_p, C.c_void_p]
+        L.fdo_svm_classify.restype = C.c_int; L.fdo_svm_classify.argtypes = [C.c_void_p, C.c_double]
+        L.fdo_svm_probability.restype = C.c_double; L.fdo_svm_probability.argtypes = [C.c_void_p, C.c_double]
+        L.fdo_enumerate.restype = C.c_int64
+        L.fdo_enumerate.argtypes = [C.POINTER(_Pyramid), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                    C.c_int, C.c_int, C.POINTER(capi.LayerInfo), C.c_int]
+        L.fdo_detect_frame.restype = C.c_int64
+        L.fdo_detect_frame.argtypes = [C.POINTER(capi.DetectorDesc), C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                       C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                       C.POINTER(C.c_int64), C.POINTER(C.c_double)]
+        _lib = L
+    return _lib
+
+
+_ref = None
+
+
+def ref_available():
+    return os.path.exists(REF_LIB)
+
+
+def ref():
+    """The compiled, unmodified reference sources (oracle/_ref/libfdref.so)."""
+    global _ref
+    if _ref is None:
+        build()
+        R = C.CDLL(REF_LIB)
+        R.ref_hq64.restype = None; R.ref_hq64.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        R.ref_wvm_create.restype = C.c_void_p; R.ref_wvm_create.argtypes = [C.POINTER(capi.WvmDesc)]
+        R.ref_wvm_free.restype = None; R.ref_wvm_free.argtypes = [C.c_void_p]
+        R.ref_wvm_eval.restype = None
+        R.ref_wvm_eval.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_float),
+                                   C.POINTER(C.c_double), C.POINTER(C.c_int)]
+        R.ref_svm_create.restype = C.c_void_p; R.ref_svm_create.argtypes = [C.POINTER(capi.SvmDesc)]
+        R.ref_svm_free.restype = None; R.ref_svm_free.argtypes = [C.c_void_p]
+        R.ref_svm_eval.restype = None
+        R.ref_svm_eval.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int)]
+        R.ref_overlap_eliminate.restype = C.c_int
+        R.ref_overlap_eliminate.argtypes = [C.c_float, C.c_float, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                            C.c_void_p, C.c_void_p]
+        _ref = R
+    return _ref
+
+
+# ------------------------------------------------------------------------------------------------
+# numpy-level helpers
+# ------------------------------------------------------------------------------------------------
+def resize_linear(img, dw, dh):
+    img = np.ascontiguousarray(img, np.uint8)
+    out = np.empty((dh, dw), np.uint8)
+    lib().fdo_resize_linear_u8(img.ctypes.data, img.shape[1], img.shape[0], img.shape[1], out.ctypes.data, dw, dh)
+    return out
+
+
+def pyrdown(img):
+    img = np.ascontiguousarray(img, np.uint8)
+    out = np.empty(((img.shape[0] + 1) // 2, (img.shape[1] + 1) // 2), np.uint8)
+    lib().fdo_pyrdown_u8(img.ctypes.data, img.shape[1], img.shape[0], out.ctypes.data)
+    return out
+
+
+def hq64(patch, use_ref=False):
+    """HistEq64 of a 2-D u8 array (may be a strided view with contiguous rows)."""
+    assert patch.dtype == np.uint8 and patch.strides[1] == 1
+    h, w = patch.shape
+    out = np.empty((h, w), np.uint8)
+    fn = ref().ref_hq64 if use_ref else lib().fdo_hq64
+    fn(patch.ctypes.data, patch.strides[0], w, h, out.ctypes.data)
+    return out
+
+
+def pyramid(frame, inc, mn, mx):
+    """Returns (octave_layer_count, [(index, scale, image), ...])."""
+    frame = np.ascontiguousarray(frame, np.uint8)
+    p = lib().fdo_pyramid_build(frame.ctypes.data, frame.shape[1], frame.shape[0], frame.shape[1], inc, mn, mx)
+    if not p:
+        raise ValueError("invalid pyramid parameters")
+    try:
+        layers = C.cast(p.contents.layers, C.POINTER(_Layer))
+        out = []
+        for i in range(p.contents.n_layers):
+            L = layers[i]
+            img = np.ctypeslib.as_array(L.data, shape=(L.height, L.width)).copy()
+            out.append((L.index, L.scale, img))
+        return p.contents.octave_layer_count, out
+    finally:
+        lib().fdo_pyramid_free(p)
+
+
+class Wvm:
+    def __init__(self, model, use_ref=False):
+        self.model = model
+        self.use_ref = use_ref
+        self._desc = model.desc()
+        self.h = (ref().ref_wvm_create if use_ref else lib().fdo_wvm_create)(C.byref(self._desc))
+
+    def __del__(self):
+        try:
+            (ref().ref_wvm_free if self.use_ref else lib().fdo_wvm_free)(self.h)
+        except Exception:
+            pass
+
+    def eval(self, patches):
+        """patches: [n, h*w] u8 -> (level int32[n], fout float32[n], prob float64[n], positive uint8[n])"""
+        patches = np.ascontiguousarray(patches, np.uint8).reshape(-1, self.model.w * self.model.h)
+        n = patches.shape[0]
+        level = np.empty(n, np.int32); fout = np.empty(n, np.float32)
+        prob = np.empty(n, np.float64); pos = np.empty(n, np.uint8)
+        lv, fo, pr, po = C.c_int(), C.c_float(), C.c_double(), C.c_int()
+        if self.use_ref:
+            R = ref()
+            for i in range(n):
+                R.ref_wvm_eval(self.h, patches[i].ctypes.data, C.byref(lv), C.byref(fo), C.byref(pr), C.byref(po))
+                level[i], fout[i], prob[i], pos[i] = lv.value, fo.value, pr.value, po.value
+        else:
+            L = lib()
+            for i in range(n):
+                L.fdo_wvm_eval(self.h, patches[i].ctypes.data, C.byref(lv), C.byref(fo))
+                level[i], fout[i] = lv.value, fo.value
+                prob[i] = L.fdo_wvm_probability(self.h, fo)
+                pos[i] = L.fdo_wvm_classify(self.h, lv, fo)
+        return level, fout, prob, pos
+
+    def eval_all_levels(self, patches):
+        assert not self.use_ref
+        patches = np.ascontiguousarray(patches, np.uint8).reshape(-1, self.model.w * self.model.h)
+        out = np.empty((patches.shape[0], self.model.n), np.float32)
+        L = lib()
+        for i in range(patches.shape[0]):
+            L.fdo_wvm_eval_all_levels(self.h, patches[i].ctypes.data, out[i].ctypes.data)
+        return out
+
+
+class Svm:
+    def __init__(self, model, use_ref=False):
+        self.model = model
+        self.use_ref = use_ref
+        self._desc = model.desc()
+        self.h = (ref().ref_svm_create if use_ref else lib().fdo_svm_create)(C.byref(self._desc))
+
+    def __del__(self):
+        try:
+            (ref().ref_svm_free if self.use_ref else lib().fdo_svm_free)(self.h)
+        except Exception:
+            pass
+
+    def eval(self, vectors):
+        """vectors [n, dim] of the SV dtype -> (distance f64[n], probability f64[n], positive u8[n])"""
+        vectors = np.ascontiguousarray(vectors, self.model.sv.dtype).reshape(-1, self.model.sv.shape[1])
+        n = vectors.shape[0]
+        dist = np.empty(n, np.float64); prob = np.empty(n, np.float64); pos = np.empty(n, np.uint8)
+        d, p, q = C.c_double(), C.c_double(), C.c_int()
+        for i in range(n):
+            if self.use_ref:
+                ref().ref_svm_eval(self.h, vectors[i].ctypes.data, C.byref(d), C.byref(p), C.byref(q))
+                dist[i], prob[i], pos[i] = d.value, p.value, q.value
+            else:
+                L = lib()
+                dist[i] = L.fdo_svm_distance(self.h, vectors[i].ctypes.data)
+                prob[i] = L.fdo_svm_probability(self.h, dist[i])
+                pos[i] = L.fdo_svm_classify(self.h, dist[i])
+        return dist, prob, pos
+
+
+def detections_to_array(buf, n):
+    """ctypes Detection array -> numpy structured array copy"""
+    dt = np.dtype([(name, np.ctypeslib.as_ctypes_type(np.dtype(_np_of(ct)))) for name, ct in capi.Detection._fields_], align=True)
+    return np.frombuffer(buf, dtype=dt, count=n).copy()
+
+
+def _np_of(ct):
+    return {C.c_int32: "i4", C.c_int64: "i8", C.c_float: "f4", C.c_double: "f8"}[ct]
+
+
+DETECTION_DTYPE = np.dtype([(name, _np_of(ct)) for name, ct in capi.Detection._fields_], align=True)
+assert DETECTION_DTYPE.itemsize == C.sizeof(capi.Detection)
+SCORE_DTYPE = np.dtype([("fout", "f4"), ("level", "i4")])
+
+
+def detect_frame(det_kwargs, wvm, svm, frame, stage=capi.FDB_STAGE_NMS, roi=(0, 0, 0, 0), frame_index=0,
+                 want_dense=True, want_patches=False, det_cap=1 << 16, timing=False):
+    """Whole reference path on one frame (fdo_detect_frame). Returns a dict."""
+    from featuredetection_b200.synthetic import detector_desc
+    desc = detector_desc(**det_kwargs)
+    frame = np.ascontiguousarray(frame, np.uint8)
+    H, W = frame.shape
+    L = lib()
+    # window count
+    p = L.fdo_pyramid_build(frame.ctypes.data, W, H, W, desc.incremental_scale_factor, desc.min_scale_factor, desc.max_scale_factor)
+    if not p:
+        raise ValueError("invalid pyramid parameters")
+    infos = (capi.LayerInfo * max(p.contents.n_layers, 1))()
+    total = L.fdo_enumerate(p, desc.patch_width, desc.patch_height, max(desc.step_x, 1), max(desc.step_y, 1),
+                            roi[0], roi[1], roi[2], roi[3], infos, p.contents.n_layers)
+    n_layers = p.contents.n_layers
+    L.fdo_pyramid_free(p)
+    dense = np.zeros(total, SCORE_DTYPE) if want_dense else None
+    patches = np.zeros((total, desc.patch_width * desc.patch_height), np.uint8) if want_patches else None
+    dets = np.zeros(det_cap, DETECTION_DTYPE)
+    counts = (C.c_int64 * 5)()
+    tim = (C.c_double * 5)()
+    n = L.fdo_detect_frame(C.byref(desc), wvm.h, svm.h if svm is not None else None, frame.ctypes.data, W, H, W,
+                           frame_index, roi[0], roi[1], roi[2], roi[3], stage,
+                           dense.ctypes.data if dense is not None else None,
+                           patches.ctypes.data if patches is not None else None,
+                           dets.ctypes.data, det_cap, counts, tim if timing else None)
+    if n < 0:
+        raise RuntimeError("fdo_detect_frame failed (%d)" % n)
+    layers = [{f: getattr(infos[i], f) for f, _ in capi.LayerInfo._fields_} for i in range(n_layers)]
+    return dict(windows=int(total), dense=dense, patches=patches, detections=dets[:n].copy(),
+                counts=list(counts), timing=list(tim), layers=layers)
