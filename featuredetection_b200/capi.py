@@ -120,6 +120,9 @@ SYMBOLS = [
     ("fdb_detect_roi", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int64, _P(C.c_int64)]),
     ("fdb_extract_patches", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, _P(C.c_int64)]),
     ("fdb_pyramid_layer", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int64]),
+    ("fdb_plan_layers", C.c_int, [_P(DetectorDesc), C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P(LayerInfo), C.c_int32, _P(C.c_int32), _P(C.c_int64)]),
+    ("fdb_overlap_eliminate", C.c_int, [C.c_void_p, C.c_int64, C.c_float, C.c_float, _P(C.c_int64)]),
+    ("fdb_five_stage_nms", C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, _P(C.c_int64)]),
     ("fdb_detector_last_counts", C.c_int, [C.c_void_p, _P(C.c_int64)]),
 ]
 

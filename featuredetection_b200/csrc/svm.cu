@@ -1,0 +1,147 @@
+/*
+ * svm.cu - stage 3 of the cascade on the GPU: RBF support vector machine (sm_100a).
+ *
+ * One CTA evaluates one feature vector against all support vectors:
+ *   SvmClassifier::computeHyperplaneDistance      libClassification/src/classification/SvmClassifier.cpp:55-60
+ *   RbfKernel::compute / sum of squared differences libClassification/include/classification/RbfKernel.hpp:32-40,78-108
+ * For windows of a frame the HistEq64 patch (HistEq64Filter.cpp:32-125) is rebuilt in shared
+ * memory from the pyramid layer (the stage-1 kernel does not store 400-byte patches per window).
+ *
+ * Exactness: u8 SSD is an exact integer (vabsdiffu4 + dp4a); float SSD keeps the reference's
+ * sequential float32 order; the kernel value exp(-gamma*ssd) and the sum over support vectors
+ * are double precision, accumulated by ONE thread in support-vector order (double addition is
+ * not associative, and classify() compares the sum against a threshold).
+ * Support vectors are stored transposed ([word][sv]) so that the 256 threads of a CTA, each
+ * owning one support vector, read consecutive words.
+ */
+#include <cuda_runtime.h>
+#include <cstdint>
+
+#include "fdb_internal.h"
+#include "wvm_device.h"
+
+namespace fdb {
+
+#define SVM_THREADS 256
+#define SVM_CHUNK 2048
+
+template <int MODE> /* 0: window of a frame (u8, hq64 built here), 1: given u8 vectors, 2: given f32 vectors */
+__global__ void __launch_bounds__(SVM_THREADS) svm_kernel(const DevSvm s, int patch_w, int patch_h,
+		const uint8_t* __restrict__ frames, int W, int H, const uint8_t* __restrict__ arena, int64_t arena_stride,
+		const DevLayer* __restrict__ layers, const SvmItem* __restrict__ items,
+		const void* __restrict__ vectors, double* __restrict__ distance_out) {
+	extern __shared__ __align__(16) unsigned char svm_smem[];
+	double* s_prod = reinterpret_cast<double*>(svm_smem);                    /* [SVM_CHUNK] */
+	uint32_t* s_x = reinterpret_cast<uint32_t*>(svm_smem + sizeof(double) * SVM_CHUNK); /* [nwords] or float[dim] */
+	__shared__ uint32_t s_hist[64];
+	__shared__ uint8_t s_eq[64];
+	const int tid = threadIdx.x;
+	const int item = blockIdx.x;
+
+	if (MODE == 0) {
+		const SvmItem it = items[item];
+		const DevLayer L = layers[it.layer];
+		const uint8_t* img = (L.offset < 0 ? frames + (int64_t)it.frame * W * H
+				: arena + (int64_t)it.frame * arena_stride + L.offset) + (int64_t)it.y * L.width + it.x;
+		const int npix = patch_w * patch_h;
+		if (tid < 64) s_hist[tid] = 0;
+		for (int i = tid; i < s.nwords; i += SVM_THREADS) s_x[i] = 0;
+		__syncthreads();
+		for (int i = tid; i < npix; i += SVM_THREADS) {
+			const int r = i / patch_w, c = i - r * patch_w;
+			atomicAdd(&s_hist[img[(int64_t)r * L.width + c] >> 2], 1u);
+		}
+		__syncthreads();
+		if (tid == 0) { /* sequential float cumsum, HistEq64Filter.cpp:70-87,97 */
+			const float stretch = __fdiv_rn(255.0f, (float)npix);
+			float cdf = 0.f;
+			for (int b = 0; b < 64; ++b) {
+				cdf = __fadd_rn(cdf, __fmul_rn((float)s_hist[b], stretch));
+				const float fl = floorf(cdf);
+				s_eq[b] = (uint8_t)((int)fl + (__fsub_rn(cdf, fl) >= 0.5f ? 1 : 0));
+			}
+		}
+		__syncthreads();
+		for (int i = tid; i < npix; i += SVM_THREADS) {
+			const int r = i / patch_w, c = i - r * patch_w;
+			const uint32_t e = s_eq[img[(int64_t)r * L.width + c] >> 2];
+			atomicOr(&s_x[i >> 2], e << (8 * (i & 3)));
+		}
+	} else if (MODE == 1) {
+		const uint8_t* v = reinterpret_cast<const uint8_t*>(vectors) + (int64_t)item * s.dim;
+		for (int i = tid; i < s.nwords; i += SVM_THREADS) {
+			uint32_t w = 0;
+			for (int k = 0; k < 4; ++k) if (4 * i + k < s.dim) w |= (uint32_t)v[4 * i + k] << (8 * k);
+			s_x[i] = w;
+		}
+	} else {
+		const float* v = reinterpret_cast<const float*>(vectors) + (int64_t)item * s.dim;
+		float* xf = reinterpret_cast<float*>(s_x);
+		for (int i = tid; i < s.dim; i += SVM_THREADS) xf[i] = v[i];
+	}
+	__syncthreads();
+
+	double distance = -(double)s.bias; /* SvmClassifier.cpp:56: double distance = -bias */
+	for (int base = 0; base < s.num_sv; base += SVM_CHUNK) {
+		const int cnt = min(SVM_CHUNK, s.num_sv - base);
+		for (int i = tid; i < cnt; i += SVM_THREADS) {
+			const int sv = base + i;
+			double ssd;
+			if (MODE != 2) {
+				uint32_t acc = 0;
+				for (int j = 0; j < s.nwords; ++j) {
+					const uint32_t d = __vabsdiffu4(s_x[j], s.sv_words[(size_t)j * s.num_sv + sv]);
+					acc = __dp4a(d, d, acc);
+				}
+				ssd = (double)(int)acc;
+			} else {
+				const float* xf = reinterpret_cast<const float*>(s_x);
+				float sum = 0.f;
+				for (int k = 0; k < s.dim; ++k) {
+					const float diff = __fsub_rn(xf[k], s.sv_f32[(size_t)k * s.num_sv + sv]);
+					sum = __fadd_rn(sum, __fmul_rn(diff, diff));
+				}
+				ssd = (double)sum;
+			}
+			const double kv = exp(__dmul_rn(-s.gamma, ssd));                 /* RbfKernel.hpp:39 */
+			s_prod[i] = __dmul_rn((double)s.coef[sv], kv);                   /* SvmClassifier.cpp:58 */
+		}
+		__syncthreads();
+		if (tid == 0)
+			for (int i = 0; i < cnt; ++i) distance = __dadd_rn(distance, s_prod[i]);
+		__syncthreads();
+	}
+	if (tid == 0) distance_out[item] = distance;
+}
+
+static size_t svm_smem_bytes(const DevSvm& s) {
+	size_t xbytes = s.sv_type == FDB_SV_F32 ? sizeof(float) * (size_t)s.dim : sizeof(uint32_t) * (size_t)s.nwords;
+	return sizeof(double) * SVM_CHUNK + ((xbytes + 15) / 16) * 16;
+}
+
+int svm_configure() {
+	cudaError_t e = cudaFuncSetAttribute(svm_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
+	if (e == cudaSuccess) e = cudaFuncSetAttribute(svm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
+	if (e == cudaSuccess) e = cudaFuncSetAttribute(svm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
+	return (int)e;
+}
+
+void launch_svm_windows(cudaStream_t st, const DevSvm& s, int patch_w, int patch_h, const uint8_t* frames, int W, int H,
+		const uint8_t* arena, int64_t arena_stride, const DevLayer* layers, const SvmItem* items, int n_items,
+		double* distance_out) {
+	if (n_items == 0) return;
+	svm_kernel<0><<<(unsigned)n_items, SVM_THREADS, svm_smem_bytes(s), st>>>(s, patch_w, patch_h, frames, W, H, arena,
+			arena_stride, layers, items, nullptr, distance_out);
+}
+
+void launch_svm_vectors(cudaStream_t st, const DevSvm& s, const void* vectors, int n, double* distance_out) {
+	if (n == 0) return;
+	if (s.sv_type == FDB_SV_F32)
+		svm_kernel<2><<<(unsigned)n, SVM_THREADS, svm_smem_bytes(s), st>>>(s, 0, 0, nullptr, 0, 0, nullptr, 0, nullptr,
+				nullptr, vectors, distance_out);
+	else
+		svm_kernel<1><<<(unsigned)n, SVM_THREADS, svm_smem_bytes(s), st>>>(s, 0, 0, nullptr, 0, 0, nullptr, 0, nullptr,
+				nullptr, vectors, distance_out);
+}
+
+} // namespace fdb

@@ -1,0 +1,72 @@
+/*
+ * wvm_device.h - device-side view of the classifiers and launcher prototypes.
+ */
+#ifndef FDB_WVM_DEVICE_H_
+#define FDB_WVM_DEVICE_H_
+
+#include <cuda_runtime.h>
+#include <cstdint>
+
+#include "fdb_internal.h"
+
+namespace fdb {
+
+#define WVM_THREADS 128
+#define FDB_MAX_FILTERS 512   /* hk_kernel_eval capacity per window (e.g. 280 used) */
+#define FDB_MAX_PER_LEVEL 64  /* u_kernel_eval capacity (numFiltersPerLevel, e.g. 14..30) */
+#define FDB_MAX_VALUES 8      /* grey values v >= 1 per filter (cntval - 1) */
+
+/* WvmClassifier state in evaluator form; all pointers are device memory */
+struct DevWvm {
+	int fsx, fsy, nwords;
+	int num_lin, per_level, num_used;
+	int step_x, step_y;             /* window step of the launching detector */
+	float basis_param;
+	const float* lin_thresholds;    /* [num_lin] */
+	const float* hk_weights;        /* packed triangle */
+	const double* app_rsv_convol;   /* [num_lin] */
+	const float* thresholds;        /* hierarchicalThresholds incl. limitReliabilityFilter */
+	const int* cntval;              /* [num_lin] */
+	const int* val_off;             /* [num_lin] */
+	const double* val;              /* grey values */
+	const uint32_t* masks;          /* rectangle coverage counts, 4 pixels per word: filter f at mask_off[f], [nwords][cntval-1] */
+	const int* mask_off;            /* [num_lin] */
+};
+
+/* SvmClassifier (RBF) state; support vectors transposed to [word][sv] for coalesced reads */
+struct DevSvm {
+	int num_sv, dim, nwords, sv_type;
+	double gamma;
+	float bias, threshold;
+	const uint32_t* sv_words;       /* u8: [nwords][num_sv] packed 4 px per word */
+	const float* sv_f32;            /* f32: [dim][num_sv] */
+	const float* coef;              /* [num_sv] */
+};
+
+int wvm_configure();
+size_t wvm_smem_bytes(const DevWvm& m);
+void launch_wvm_windows(cudaStream_t st, const DevWvm& m, const uint8_t* frames, int W, int H, int n_frames,
+		const uint8_t* arena, int64_t arena_stride, const DevLayer* layers, int n_layers, int windows_per_frame,
+		fdb_window_score* dense, uint8_t* patches_out, Candidate* cand, int* cand_count, int cand_cap);
+void launch_wvm_patches(cudaStream_t st, const DevWvm& m, const uint8_t* patches, int n, fdb_window_score* dense);
+
+void launch_resize(cudaStream_t st, const uint8_t* frames, int W, int H, int n_frames, uint8_t* arena,
+		int64_t arena_stride, const ResizeJob* jobs_dev, int n_jobs, int max_quads,
+		const int* ofs_tab, const short2* coef_tab);
+void launch_pyrdown(cudaStream_t st, const uint8_t* frames, int W, int H, int n_frames, uint8_t* arena,
+		int64_t arena_stride, const DownJob* jobs_dev, int n_jobs, int max_pixels);
+
+/* one SVM work item: a window of a frame (geometry resolved on the host) */
+struct SvmItem {
+	int frame;
+	int layer;   /* index into the DevLayer table */
+	int x, y;    /* window corner inside the layer */
+};
+int svm_configure();
+void launch_svm_windows(cudaStream_t st, const DevSvm& s, int patch_w, int patch_h, const uint8_t* frames, int W, int H,
+		const uint8_t* arena, int64_t arena_stride, const DevLayer* layers, const SvmItem* items, int n_items,
+		double* distance_out);
+void launch_svm_vectors(cudaStream_t st, const DevSvm& s, const void* vectors, int n, double* distance_out);
+
+} // namespace fdb
+#endif

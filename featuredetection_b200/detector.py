@@ -1,0 +1,204 @@
+"""Thin Python front-end over the C ABI (include/fdb200.h) for tests, bench.py and smoke().
+
+The product's host side is the C++ inside libfdb200.so (api.cu / plan.cpp / hostpost.cpp) plus the
+C++ adapters in adapters/ that implement the reference's own interfaces; this module only moves
+numpy arrays across the ABI. It mirrors the reference's object graph
+(ffpDetectApp.cpp:391-425): ProbabilisticWvmClassifier, ProbabilisticSvmClassifier and a
+FiveStageSlidingWindowDetector built from them.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+from .synthetic import detector_desc
+
+DETECTION_DTYPE = np.dtype(
+    [(name, {C.c_int32: "i4", C.c_int64: "i8", C.c_float: "f4", C.c_double: "f8"}[ct])
+     for name, ct in capi.Detection._fields_], align=True)
+assert DETECTION_DTYPE.itemsize == C.sizeof(capi.Detection)
+SCORE_DTYPE = np.dtype([("fout", "f4"), ("level", "i4")])
+LAYER_FIELDS = [f for f, _ in capi.LayerInfo._fields_]
+
+
+class Context:
+    """fdb_ctx: one CUDA device + stream. Raises FdbError when no sm_100 GPU is usable."""
+
+    def __init__(self, device=-1):
+        self.lib = capi.load_library()
+        h = C.c_void_p()
+        capi.check(self.lib, self.lib.fdb_ctx_create(device, C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if self.h:
+            self.lib.fdb_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def synchronize(self):
+        capi.check(self.lib, self.lib.fdb_ctx_synchronize(self.h))
+
+    def stream(self):
+        return self.lib.fdb_ctx_stream(self.h)
+
+    def launch_count(self):
+        return int(self.lib.fdb_ctx_launch_count(self.h))
+
+
+class ProbabilisticWvmClassifier:
+    """classification::ProbabilisticWvmClassifier (ProbabilisticWvmClassifier.cpp:42-54) on the GPU."""
+
+    def __init__(self, ctx, model):
+        self.ctx, self.model = ctx, model
+        self._desc = model.desc()
+        h = C.c_void_p()
+        capi.check(ctx.lib, ctx.lib.fdb_wvm_create(ctx.h, C.byref(self._desc), C.byref(h)))
+        self.h = h
+
+    def __del__(self):
+        try:
+            if self.h and self.ctx.h:
+                self.ctx.lib.fdb_wvm_destroy(self.h)
+        except Exception:
+            pass
+
+    def set_limit_reliability_filter(self, value):
+        capi.check(self.ctx.lib, self.ctx.lib.fdb_wvm_set_limit_reliability_filter(self.h, value))
+
+    def get_probability(self, patches):
+        """patches [n, w*h] u8 -> (level, fout, probability, positive)"""
+        p = np.ascontiguousarray(patches, np.uint8).reshape(-1, self.model.w * self.model.h)
+        n = p.shape[0]
+        level = np.empty(n, np.int32); fout = np.empty(n, np.float32)
+        prob = np.empty(n, np.float64); pos = np.empty(n, np.uint8)
+        capi.check(self.ctx.lib, self.ctx.lib.fdb_wvm_get_probability(
+            self.h, p.ctypes.data, n, level.ctypes.data, fout.ctypes.data, prob.ctypes.data, pos.ctypes.data))
+        return level, fout, prob, pos
+
+
+class ProbabilisticSvmClassifier:
+    """classification::ProbabilisticSvmClassifier (ProbabilisticSvmClassifier.cpp:42-58) on the GPU."""
+
+    def __init__(self, ctx, model):
+        self.ctx, self.model = ctx, model
+        self._desc = model.desc()
+        h = C.c_void_p()
+        capi.check(ctx.lib, ctx.lib.fdb_svm_create(ctx.h, C.byref(self._desc), C.byref(h)))
+        self.h = h
+
+    def __del__(self):
+        try:
+            if self.h and self.ctx.h:
+                self.ctx.lib.fdb_svm_destroy(self.h)
+        except Exception:
+            pass
+
+    def set_threshold(self, t):
+        capi.check(self.ctx.lib, self.ctx.lib.fdb_svm_set_threshold(self.h, t))
+
+    def get_probability(self, vectors):
+        v = np.ascontiguousarray(vectors, self.model.sv.dtype).reshape(-1, self.model.sv.shape[1])
+        n = v.shape[0]
+        dist = np.empty(n, np.float64); prob = np.empty(n, np.float64); pos = np.empty(n, np.uint8)
+        capi.check(self.ctx.lib, self.ctx.lib.fdb_svm_get_probability(
+            self.h, v.ctypes.data, n, dist.ctypes.data, prob.ctypes.data, pos.ctypes.data))
+        return dist, prob, pos
+
+
+class SlidingWindowCascade:
+    """detection::FiveStageSlidingWindowDetector / SlidingWindowDetector over frame batches."""
+
+    def __init__(self, ctx, det_kwargs, wvm_model, svm_model=None):
+        self.ctx = ctx
+        self.wvm = ProbabilisticWvmClassifier(ctx, wvm_model)
+        self.svm = ProbabilisticSvmClassifier(ctx, svm_model) if svm_model is not None else None
+        self._desc = detector_desc(**det_kwargs)
+        h = C.c_void_p()
+        capi.check(ctx.lib, ctx.lib.fdb_detector_create(ctx.h, C.byref(self._desc), self.wvm.h,
+                                                        self.svm.h if self.svm else None, C.byref(h)))
+        self.h = h
+        self.width = self.height = None
+        self.patch = (self._desc.patch_width, self._desc.patch_height)
+
+    def __del__(self):
+        try:
+            if self.h and self.ctx.h:
+                self.ctx.lib.fdb_detector_destroy(self.h)
+        except Exception:
+            pass
+
+    def prepare(self, width, height, max_batch):
+        capi.check(self.ctx.lib, self.ctx.lib.fdb_detector_prepare(self.h, width, height, max_batch))
+        self.width, self.height, self.max_batch = width, height, max_batch
+
+    @property
+    def windows_per_frame(self):
+        return int(self.ctx.lib.fdb_detector_windows_per_frame(self.h))
+
+    @property
+    def pyramid_bytes(self):
+        return int(self.ctx.lib.fdb_detector_pyramid_bytes(self.h))
+
+    def layers(self):
+        n = C.c_int32()
+        capi.check(self.ctx.lib, self.ctx.lib.fdb_detector_layers(self.h, None, 0, C.byref(n)))
+        buf = (capi.LayerInfo * max(n.value, 1))()
+        capi.check(self.ctx.lib, self.ctx.lib.fdb_detector_layers(self.h, buf, n.value, C.byref(n)))
+        return [{f: getattr(buf[i], f) for f in LAYER_FIELDS} for i in range(n.value)]
+
+    def detect(self, frames, stage=capi.FDB_STAGE_NMS, want_dense=False, det_cap=None):
+        """frames [n, H, W] u8 (host) -> detections (structured array) [, dense [n, windows]]"""
+        frames = np.ascontiguousarray(frames, np.uint8)
+        if frames.ndim == 2:
+            frames = frames[None]
+        n, H, W = frames.shape
+        assert (W, H) == (self.width, self.height), "prepare() was called for another frame size"
+        det_cap = det_cap or max(1024, n * 4096)
+        dets = np.zeros(det_cap, DETECTION_DTYPE)
+        dense = np.zeros((n, self.windows_per_frame), SCORE_DTYPE) if want_dense else None
+        cnt = C.c_int64()
+        capi.check(self.ctx.lib, self.ctx.lib.fdb_detect_batch(
+            self.h, frames.ctypes.data, W, n, stage, dense.ctypes.data if want_dense else None,
+            dets.ctypes.data, det_cap, C.byref(cnt)))
+        out = dets[:cnt.value].copy()
+        return (out, dense) if want_dense else out
+
+    def detect_roi(self, frame, roi, stage=capi.FDB_STAGE_SVM, det_cap=1 << 16):
+        frame = np.ascontiguousarray(frame, np.uint8)
+        dets = np.zeros(det_cap, DETECTION_DTYPE)
+        cnt = C.c_int64()
+        capi.check(self.ctx.lib, self.ctx.lib.fdb_detect_roi(
+            self.h, frame.ctypes.data, frame.shape[1], roi[0], roi[1], roi[2], roi[3], stage,
+            dets.ctypes.data, det_cap, C.byref(cnt)))
+        return dets[:cnt.value].copy()
+
+    def extract_patches(self, frame):
+        """PyramidFeatureExtractor::extract(1, 1): hq64 patch of every window [windows, w*h]"""
+        frame = np.ascontiguousarray(frame, np.uint8)
+        nw = self.windows_per_frame
+        out = np.zeros((nw, self.patch[0] * self.patch[1]), np.uint8)
+        cnt = C.c_int64()
+        capi.check(self.ctx.lib, self.ctx.lib.fdb_extract_patches(
+            self.h, frame.ctypes.data, frame.shape[1], out.ctypes.data, nw, C.byref(cnt)))
+        return out
+
+    def pyramid_layer(self, frame, layer_index):
+        frame = np.ascontiguousarray(frame, np.uint8)
+        info = [L for L in self.layers() if L["index"] == layer_index]
+        if not info:
+            raise KeyError(layer_index)
+        out = np.zeros((info[0]["height"], info[0]["width"]), np.uint8)
+        capi.check(self.ctx.lib, self.ctx.lib.fdb_pyramid_layer(
+            self.h, frame.ctypes.data, frame.shape[1], layer_index, out.ctypes.data, out.size))
+        return out
+
+    def last_counts(self):
+        c = (C.c_int64 * 5)()
+        capi.check(self.ctx.lib, self.ctx.lib.fdb_detector_last_counts(self.h, c))
+        return list(c)

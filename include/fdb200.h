@@ -291,6 +291,25 @@ FDB_API int fdb_extract_patches(fdb_detector* det, const uint8_t* frame_host, in
 FDB_API int fdb_pyramid_layer(fdb_detector* det, const uint8_t* frame_host, int64_t pitch,
 		int32_t layer_index, uint8_t* out, int64_t cap);
 
+/* ------------------------------------------------------------------------------------------
+ * Host-only entry points (no GPU needed)
+ * ---------------------------------------------------------------------------------------- */
+/* Pyramid geometry and window grid for a width x height frame without touching the device:
+ * ImagePyramid::createLayers sizing (ImagePyramid.cpp:170-198) + the window loops of
+ * DirectPyramidFeatureExtractor::extract(stepX, stepY, roi) (DirectPyramidFeatureExtractor.cpp:75-123).
+ * roi all-zero = whole image. Fills up to cap layer records. */
+FDB_API int fdb_plan_layers(const fdb_detector_desc* desc, int32_t width, int32_t height,
+		int32_t roi_x, int32_t roi_y, int32_t roi_w, int32_t roi_h,
+		fdb_layer_info* out, int32_t cap, int32_t* n_layers, int64_t* n_windows);
+
+/* OverlapElimination::eliminate (OverlapElimination.cpp:44-105) on n classified patches, in place;
+ * *n_out receives the surviving count (survivors first, in the reference's output order). */
+FDB_API int fdb_overlap_eliminate(fdb_detection* dets, int64_t n, float dist, float ratio, int64_t* n_out);
+
+/* Grid NMS + final ordering of FiveStageSlidingWindowDetector::detect(Mat)
+ * (FiveStageSlidingWindowDetector.cpp:143-184,276-311) on the SVM-positive patches of ONE frame. */
+FDB_API int fdb_five_stage_nms(fdb_detection* dets, int64_t n, int32_t width, int32_t height, int64_t* n_out);
+
 /* Per-stage counters of the last detect call (TOT/TACC-style counters, ffpDetectApp.cpp:650-657):
  * [0] windows, [1] wvm positives, [2] after OE, [3] svm positives, [4] after NMS. */
 FDB_API int fdb_detector_last_counts(fdb_detector* det, int64_t counts[5]);

@@ -1,0 +1,186 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI) against the CPU oracle on the same
+seeded inputs. Bit-exact for pyramid pixels, equalised patches, window indices and cascade
+levels; scores within 1e-4 (north_star tolerance)."""
+import numpy as np
+import pytest
+
+from featuredetection_b200 import capi, synthetic as syn
+from featuredetection_b200.detector import SlidingWindowCascade, ProbabilisticWvmClassifier, ProbabilisticSvmClassifier
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4  # north_star: per-patch scores within 1e-4, indices bit-exact
+
+
+def _oracle():
+    from oracle import fdoracle as fo
+    return fo
+
+
+def test_pyramid_layers_bit_exact(ctx, face_models):
+    fo = _oracle()
+    det_kw, wvm, svm = face_models
+    casc = SlidingWindowCascade(ctx, det_kw, wvm, svm)
+    casc.prepare(640, 480, 2)
+    for k in (0, 3):
+        frame = syn.synthetic_frame(k)
+        olc, layers = fo.pyramid(frame, det_kw["incremental_scale_factor"], det_kw["min_scale_factor"], det_kw["max_scale_factor"])
+        infos = casc.layers()
+        assert [L["index"] for L in infos] == [i for i, _, _ in layers]
+        for (idx, scale, img), info in zip(layers, infos):
+            got = casc.pyramid_layer(frame, idx)
+            assert got.shape == img.shape
+            assert np.array_equal(got, img), "layer %d differs" % idx
+            assert info["scale"] == scale
+
+
+@pytest.mark.parametrize("size", [(641, 479), (333, 250), (97, 61)])
+def test_pyramid_odd_sizes(ctx, face_models, size):
+    fo = _oracle()
+    det_kw, wvm, svm = face_models
+    kw = dict(det_kw, min_scale_factor=0.11, max_scale_factor=0.6)
+    W, H = size
+    casc = SlidingWindowCascade(ctx, kw, wvm, svm)
+    casc.prepare(W, H, 1)
+    frame = syn.synthetic_frame(11, W, H)
+    _, layers = fo.pyramid(frame, kw["incremental_scale_factor"], kw["min_scale_factor"], kw["max_scale_factor"])
+    assert len(layers) == len(casc.layers())
+    for idx, scale, img in layers:
+        assert np.array_equal(casc.pyramid_layer(frame, idx), img), "layer %d differs" % idx
+
+
+def test_extract_patches_bit_exact(ctx, face_models):
+    fo = _oracle()
+    det_kw, wvm, svm = face_models
+    casc = SlidingWindowCascade(ctx, det_kw, wvm, svm)
+    casc.prepare(640, 480, 1)
+    frame = syn.synthetic_frame(2)
+    ref = fo.detect_frame(det_kw, fo.Wvm(wvm), fo.Svm(svm), frame, stage=capi.FDB_STAGE_WVM, want_patches=True)
+    got = casc.extract_patches(frame)
+    assert got.shape == ref["patches"].shape == (16185, 400)
+    assert np.array_equal(got, ref["patches"])
+
+
+@pytest.mark.parametrize("profile", ["realistic", "no-exit"])
+def test_dense_scores_and_levels(ctx, face_models, face_models_noexit, profile):
+    fo = _oracle()
+    det_kw, wvm, svm = face_models if profile == "realistic" else face_models_noexit
+    casc = SlidingWindowCascade(ctx, det_kw, wvm, svm)
+    nframes = 3 if profile == "realistic" else 1
+    casc.prepare(640, 480, nframes)
+    frames = syn.synthetic_frames(20, nframes)
+    dets, dense = casc.detect(frames, stage=capi.FDB_STAGE_WVM, want_dense=True, det_cap=1 << 17)
+    wo = fo.Wvm(wvm)
+    for k in range(nframes):
+        ref = fo.detect_frame(det_kw, wo, None, frames[k], stage=capi.FDB_STAGE_WVM, det_cap=1 << 17)
+        assert ref["windows"] == dense.shape[1] == 16185
+        assert np.array_equal(dense[k]["level"], ref["dense"]["level"])
+        assert np.max(np.abs(dense[k]["fout"] - ref["dense"]["fout"])) <= TOL
+        mine = dets[dets["frame"] == k]
+        assert list(mine["window"]) == list(ref["detections"]["window"])
+        for f in ("layer", "x", "y", "center_x", "center_y", "width", "height", "wvm_level"):
+            assert np.array_equal(mine[f], ref["detections"][f]), f
+        assert np.allclose(mine["wvm_probability"], ref["detections"]["wvm_probability"], rtol=0, atol=TOL)
+
+
+@pytest.mark.parametrize("stage", [capi.FDB_STAGE_OE, capi.FDB_STAGE_SVM, capi.FDB_STAGE_NMS])
+def test_five_stage_detections(ctx, face_models, stage):
+    fo = _oracle()
+    det_kw, wvm, svm = face_models
+    casc = SlidingWindowCascade(ctx, det_kw, wvm, svm)
+    casc.prepare(640, 480, 2)  # 5 frames through a 2-frame batch: exercises chunking
+    frames = syn.synthetic_frames(40, 5)
+    dets = casc.detect(frames, stage=stage)
+    wo, so = fo.Wvm(wvm), fo.Svm(svm)
+    total = 0
+    for k in range(5):
+        ref = fo.detect_frame(det_kw, wo, so, frames[k], stage=stage, frame_index=k)["detections"]
+        mine = dets[dets["frame"] == k]
+        assert list(mine["window"]) == list(ref["window"]), "frame %d stage %d" % (k, stage)
+        assert np.array_equal(mine["probability"], ref["probability"])
+        if stage >= capi.FDB_STAGE_SVM:
+            assert np.allclose(mine["svm_distance"], ref["svm_distance"], rtol=0, atol=TOL)
+            assert np.allclose(mine["svm_probability"], ref["svm_probability"], rtol=0, atol=TOL)
+        total += len(ref)
+    assert total == len(dets)
+
+
+def test_roi_detection(ctx, face_models):
+    fo = _oracle()
+    det_kw, wvm, svm = face_models
+    casc = SlidingWindowCascade(ctx, det_kw, wvm, svm)
+    casc.prepare(640, 480, 1)
+    frame = syn.synthetic_frame(7)
+    wo, so = fo.Wvm(wvm), fo.Svm(svm)
+    for roi in [(100, 60, 400, 350), (-20, -10, 700, 300), (0, 0, 640, 480)]:
+        for stage in (capi.FDB_STAGE_WVM, capi.FDB_STAGE_SVM):
+            ref = fo.detect_frame(det_kw, wo, so, frame, stage=stage, roi=roi)["detections"]
+            mine = casc.detect_roi(frame, roi, stage=stage)
+            assert list(mine["window"]) == list(ref["window"]), (roi, stage)
+            assert np.array_equal(mine["center_x"], ref["center_x"]) and np.array_equal(mine["center_y"], ref["center_y"])
+
+
+def test_classifier_entry_points(ctx, face_models):
+    """ProbabilisticClassifier::getProbability over given feature vectors."""
+    fo = _oracle()
+    det_kw, wvm, svm = face_models
+    rng = np.random.default_rng(5)
+    frame = syn.synthetic_frame(9)
+    _, layers = fo.pyramid(frame, det_kw["incremental_scale_factor"], det_kw["min_scale_factor"], det_kw["max_scale_factor"])
+    img = layers[0][2]
+    patches = np.stack([fo.hq64(img[y:y + 20, x:x + 20]).ravel()
+                        for y, x in zip(rng.integers(0, 50, 300), rng.integers(0, 70, 300))])
+    patches[0] = 0; patches[1] = 255; patches[2] = rng.integers(0, 256, 400)  # degenerate inputs
+    gw = ProbabilisticWvmClassifier(ctx, wvm)
+    level, fout, prob, pos = gw.get_probability(patches)
+    rl, rf, rp, rpos = fo.Wvm(wvm).eval(patches)
+    assert np.array_equal(level, rl) and np.array_equal(pos, rpos)
+    assert np.max(np.abs(fout - rf)) <= TOL and np.max(np.abs(prob - rp)) <= TOL
+    gs = ProbabilisticSvmClassifier(ctx, svm)
+    dist, sp, spos = gs.get_probability(patches)
+    rd, rsp, rspos = fo.Svm(svm).eval(patches)
+    assert np.max(np.abs(dist - rd)) <= TOL and np.max(np.abs(sp - rsp)) <= TOL
+    assert np.array_equal(spos, rspos)
+    # float32 support vectors (RbfKernel::computeSumOfSquaredDifferences_any<float>)
+    fsv = rng.normal(0, 1, (64, 144)).astype(np.float32)
+    fmodel = syn.SvmModel(fsv, rng.normal(0, 1, 64).astype(np.float32), gamma=0.2, bias=0.1, threshold=0.05)
+    x = rng.normal(0, 1, (40, 144)).astype(np.float32)
+    d2, p2, q2 = ProbabilisticSvmClassifier(ctx, fmodel).get_probability(x)
+    r2, rp2, rq2 = fo.Svm(fmodel).eval(x)
+    assert np.max(np.abs(d2 - r2)) <= TOL and np.array_equal(q2, rq2)
+
+
+def test_limit_reliability_and_empty(ctx, face_models):
+    fo = _oracle()
+    det_kw, wvm, svm = face_models
+    gw = ProbabilisticWvmClassifier(ctx, wvm)
+    lv, fo_, pr, pos = gw.get_probability(np.zeros((0, 400), np.uint8))
+    assert len(lv) == 0
+    gw.set_limit_reliability_filter(0.05)
+    import copy
+    m2 = copy.copy(wvm); m2.limit_reliability_filter = 0.05
+    rng = np.random.default_rng(3)
+    patches = rng.integers(0, 256, (200, 400), dtype=np.uint8)
+    level, fout, _, _ = gw.get_probability(patches)
+    rl, rf, _, _ = fo.Wvm(m2).eval(patches)
+    assert np.array_equal(level, rl) and np.max(np.abs(fout - rf)) <= TOL
+
+
+def test_batch_invariance_full_size(ctx, face_models):
+    """Full-size (256-frame) property: results do not depend on batch position or chunking,
+    duplicated frames give identical records, and frame k of the batch equals a solo run."""
+    det_kw, wvm, svm = face_models
+    base = syn.synthetic_frames(100, 8)
+    frames = np.concatenate([base] * 32)  # 256 frames
+    casc = SlidingWindowCascade(ctx, det_kw, wvm, svm)
+    casc.prepare(640, 480, 256)
+    dets, dense = casc.detect(frames, stage=capi.FDB_STAGE_NMS, want_dense=True)
+    for r in range(1, 32):
+        assert np.array_equal(dense[r * 8:(r + 1) * 8], dense[:8])
+    casc2 = SlidingWindowCascade(ctx, det_kw, wvm, svm)
+    casc2.prepare(640, 480, 3)
+    dets2, dense2 = casc2.detect(base, stage=capi.FDB_STAGE_NMS, want_dense=True)
+    assert np.array_equal(dense2, dense[:8])
+    first = dets[dets["frame"] < 8]
+    assert np.array_equal(first["window"], dets2["window"]) and np.array_equal(first["frame"], dets2["frame"])
+    counts = casc.last_counts()
+    assert counts[0] == 256 * 16185 and counts[4] == len(dets)
