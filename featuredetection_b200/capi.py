@@ -98,6 +98,8 @@ SYMBOLS = [
     ("fdb_ctx_stream", C.c_void_p, [C.c_void_p]),
     ("fdb_ctx_synchronize", C.c_int, [C.c_void_p]),
     ("fdb_ctx_launch_count", C.c_int64, [C.c_void_p]),
+    ("fdb_ctx_timer_start", C.c_int, [C.c_void_p]),
+    ("fdb_ctx_timer_stop", C.c_int, [C.c_void_p, _P(C.c_double)]),
     ("fdb_host_alloc", C.c_int, [C.c_size_t, _P(C.c_void_p)]),
     ("fdb_host_free", None, [C.c_void_p]),
     ("fdb_wvm_create", C.c_int, [C.c_void_p, _P(WvmDesc), _P(C.c_void_p)]),
@@ -117,6 +119,7 @@ SYMBOLS = [
     ("fdb_detect_batch", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, _P(C.c_int64)]),
     ("fdb_detect_batch_device", C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, _P(C.c_int64)]),
     ("fdb_detect_enqueue_device", C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
+    ("fdb_detect_profile_device", C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, _P(C.c_double)]),
     ("fdb_detect_roi", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int64, _P(C.c_int64)]),
     ("fdb_extract_patches", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, _P(C.c_int64)]),
     ("fdb_pyramid_layer", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int64]),

@@ -51,6 +51,7 @@ struct fdb_ctx {
 	int device = 0;
 	cudaStream_t stream = nullptr;
 	int64_t launches = 0;
+	cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr}; /* stopwatch + per-kernel profile marks */
 };
 
 struct fdb_wvm {
@@ -169,21 +170,24 @@ int upload_layers(fdb_detector* det, const Plan& plan, DevLayer* dst) {
 
 /* enqueue pyramid + stage-1 kernels for n frames resident at d_frames */
 int enqueue_stage1(fdb_detector* det, const uint8_t* d_frames, int n, const Plan& plan, const DevLayer* d_layers,
-		int64_t windows, fdb_window_score* d_dense, uint8_t* d_patches, bool want_candidates) {
+		int64_t windows, fdb_window_score* d_dense, uint8_t* d_patches, bool want_candidates, bool marks = false) {
 	fdb_ctx* c = det->ctx;
 	cudaStream_t st = c->stream;
 	const int W = plan.width, H = plan.height;
 	if (want_candidates) CUDA_TRY(cudaMemsetAsync(det->d_cand_count, 0, sizeof(int), st));
+	if (marks) CUDA_TRY(cudaEventRecord(c->ev[1], st));
 	if (det->n_resize) {
 		launch_resize(st, d_frames, W, H, n, det->d_arena, plan.arena_bytes, det->d_resize, det->n_resize,
 				det->max_quads, det->d_ofs_tab, det->d_coef_tab);
 		c->launches++;
 	}
+	if (marks) CUDA_TRY(cudaEventRecord(c->ev[2], st));
 	for (size_t j = 0; j < det->d_down.size(); ++j) {
 		if (!det->n_down[j]) continue;
 		launch_pyrdown(st, d_frames, W, H, n, det->d_arena, plan.arena_bytes, det->d_down[j], det->n_down[j], det->max_down_px[j]);
 		c->launches++;
 	}
+	if (marks) CUDA_TRY(cudaEventRecord(c->ev[3], st));
 	if (windows > 0) {
 		DevWvm m = det->wvm->dev;
 		m.step_x = det->desc.step_x; m.step_y = det->desc.step_y;
@@ -191,6 +195,7 @@ int enqueue_stage1(fdb_detector* det, const uint8_t* d_frames, int n, const Plan
 				(int)windows, d_dense, d_patches, want_candidates ? det->d_cand : nullptr, det->d_cand_count, det->cand_cap);
 		c->launches++;
 	}
+	if (marks) CUDA_TRY(cudaEventRecord(c->ev[4], st));
 	CUDA_TRY(cudaGetLastError());
 	return FDB_OK;
 }
@@ -338,6 +343,7 @@ int fdb_ctx_create(int device, fdb_ctx** out) {
 	fdb_ctx* c = new fdb_ctx;
 	c->device = device;
 	CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+	for (cudaEvent_t& e : c->ev) CUDA_TRY(cudaEventCreate(&e));
 	if (wvm_configure() != 0 || svm_configure() != 0) {
 		cudaStreamDestroy(c->stream); delete c;
 		return fail(FDB_ERR_CUDA, "cudaFuncSetAttribute failed: libfdb200 kernels not loadable on this device");
@@ -350,6 +356,7 @@ void fdb_ctx_destroy(fdb_ctx* c) {
 	if (!c) return;
 	cudaSetDevice(c->device);
 	cudaStreamSynchronize(c->stream);
+	for (cudaEvent_t e : c->ev) if (e) cudaEventDestroy(e);
 	cudaStreamDestroy(c->stream);
 	delete c;
 }
@@ -359,6 +366,22 @@ void* fdb_ctx_stream(fdb_ctx* c) { return c ? (void*)c->stream : nullptr; }
 int fdb_ctx_synchronize(fdb_ctx* c) {
 	int s = check_ctx(c); if (s) return s;
 	CUDA_TRY(cudaStreamSynchronize(c->stream));
+	return FDB_OK;
+}
+
+int fdb_ctx_timer_start(fdb_ctx* c) {
+	int s = check_ctx(c); if (s) return s;
+	CUDA_TRY(cudaEventRecord(c->ev[0], c->stream));
+	return FDB_OK;
+}
+
+int fdb_ctx_timer_stop(fdb_ctx* c, double* elapsed_ms) {
+	int s = check_ctx(c); if (s) return s;
+	CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));
+	CUDA_TRY(cudaEventSynchronize(c->ev[1]));
+	float ms = 0;
+	CUDA_TRY(cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]));
+	if (elapsed_ms) *elapsed_ms = ms;
 	return FDB_OK;
 }
 
@@ -783,6 +806,23 @@ int fdb_detect_enqueue_device(fdb_detector* det, const uint8_t* frames_device, i
 	int s = check_ctx(det->ctx); if (s) return s;
 	if (n_frames < 0 || n_frames > det->max_batch) return fail(FDB_ERR_INVALID_ARGUMENT, "n_frames exceeds the prepared batch");
 	return enqueue_stage1(det, frames_device, n_frames, det->plan, det->d_layers, det->plan.windows, dense_out_device, nullptr, true);
+}
+
+int fdb_detect_profile_device(fdb_detector* det, const uint8_t* frames_device, int32_t n_frames, double ms_out[4]) {
+	if (!det || !det->prepared) return fail(FDB_ERR_INVALID_ARGUMENT, "detector not prepared (call fdb_detector_prepare)");
+	int s = check_ctx(det->ctx); if (s) return s;
+	if (n_frames < 0 || n_frames > det->max_batch || !ms_out) return fail(FDB_ERR_INVALID_ARGUMENT, "bad arguments");
+	s = enqueue_stage1(det, frames_device, n_frames, det->plan, det->d_layers, det->plan.windows, nullptr, nullptr, true, true);
+	if (s) return s;
+	fdb_ctx* c = det->ctx;
+	CUDA_TRY(cudaEventSynchronize(c->ev[4]));
+	float a = 0, b = 0, w = 0, t = 0;
+	CUDA_TRY(cudaEventElapsedTime(&a, c->ev[1], c->ev[2]));
+	CUDA_TRY(cudaEventElapsedTime(&b, c->ev[2], c->ev[3]));
+	CUDA_TRY(cudaEventElapsedTime(&w, c->ev[3], c->ev[4]));
+	CUDA_TRY(cudaEventElapsedTime(&t, c->ev[1], c->ev[4]));
+	ms_out[0] = a; ms_out[1] = b; ms_out[2] = w; ms_out[3] = t;
+	return FDB_OK;
 }
 
 int fdb_detect_roi(fdb_detector* det, const uint8_t* frame_host, int64_t pitch, int32_t roi_x, int32_t roi_y, int32_t roi_w,

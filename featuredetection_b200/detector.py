@@ -50,6 +50,14 @@ class Context:
     def launch_count(self):
         return int(self.lib.fdb_ctx_launch_count(self.h))
 
+    def timer_start(self):
+        capi.check(self.lib, self.lib.fdb_ctx_timer_start(self.h))
+
+    def timer_stop(self):
+        ms = C.c_double()
+        capi.check(self.lib, self.lib.fdb_ctx_timer_stop(self.h, C.byref(ms)))
+        return ms.value
+
 
 class ProbabilisticWvmClassifier:
     """classification::ProbabilisticWvmClassifier (ProbabilisticWvmClassifier.cpp:42-54) on the GPU."""
@@ -168,6 +176,25 @@ class SlidingWindowCascade:
             dets.ctypes.data, det_cap, C.byref(cnt)))
         out = dets[:cnt.value].copy()
         return (out, dense) if want_dense else out
+
+    def detect_device(self, frames_ptr, n, stage=capi.FDB_STAGE_NMS, dense_ptr=None, det_cap=None):
+        """frames already in device memory ([n, H, W] u8 at frames_ptr); dense_ptr: optional device
+        buffer of n * windows_per_frame records"""
+        det_cap = det_cap or max(1024, n * 4096)
+        dets = np.zeros(det_cap, DETECTION_DTYPE)
+        cnt = C.c_int64()
+        capi.check(self.ctx.lib, self.ctx.lib.fdb_detect_batch_device(
+            self.h, frames_ptr, n, stage, dense_ptr, dets.ctypes.data, det_cap, C.byref(cnt)))
+        return dets[:cnt.value].copy()
+
+    def enqueue_device(self, frames_ptr, n, dense_ptr=None):
+        capi.check(self.ctx.lib, self.ctx.lib.fdb_detect_enqueue_device(self.h, frames_ptr, n, dense_ptr))
+
+    def profile_device(self, frames_ptr, n):
+        """(resize ms, pyrDown ms, window-kernel ms, step ms) from CUDA events between the kernels"""
+        ms = (C.c_double * 4)()
+        capi.check(self.ctx.lib, self.ctx.lib.fdb_detect_profile_device(self.h, frames_ptr, n, ms))
+        return list(ms)
 
     def detect_roi(self, frame, roi, stage=capi.FDB_STAGE_SVM, det_cap=1 << 16):
         frame = np.ascontiguousarray(frame, np.uint8)

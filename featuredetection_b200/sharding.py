@@ -1,0 +1,63 @@
+"""Frame-level data parallelism.
+
+Frames are independent units (every ``update(Mat)`` rebuilds the pyramid, FeatureExtractor.hpp:32-34,
+classifiers are read-only at inference), so a batch is split into contiguous frame ranges, one per
+rank; models are replicated; the only exchange is a gather of fixed-size detection records at the
+end (NCCL over NVLink on GPUs, gloo in the CPU tests). No data-path collective exists.
+"""
+import numpy as np
+
+# columns of the gathered record (float64 keeps every field exactly: ints < 2^53)
+GATHER_FIELDS = ("frame", "window", "layer", "x", "y", "center_x", "center_y", "width", "height",
+                 "wvm_level", "wvm_fout", "wvm_probability", "svm_distance", "svm_probability", "probability", "positive")
+
+
+def shard_range(n_frames, rank, world):
+    """Contiguous range [lo, hi) of rank `rank`: ranges differ by at most one frame."""
+    base, rem = divmod(int(n_frames), int(world))
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def pack_detections(dets, frame_offset, capacity):
+    """structured detections -> [capacity + 1, len(GATHER_FIELDS)] float64 block; row 0 holds the
+    count (and an overflow flag); frame indices become global."""
+    block = np.zeros((capacity + 1, len(GATHER_FIELDS)), np.float64)
+    n = min(len(dets), capacity)
+    block[0, 0] = len(dets)
+    block[0, 1] = 1.0 if len(dets) > capacity else 0.0
+    for j, f in enumerate(GATHER_FIELDS):
+        col = dets[f][:n].astype(np.float64)
+        if f == "frame":
+            col = col + frame_offset
+        block[1:n + 1, j] = col
+    return block
+
+
+def unpack_detections(blocks, dtype):
+    """[world, capacity + 1, F] gathered blocks -> one structured array ordered by rank (= frame order)."""
+    out = []
+    for b in blocks:
+        n = int(b[0, 0])
+        if b[0, 1] != 0.0:
+            raise OverflowError("a rank overflowed its gather block (%d detections)" % n)
+        rec = np.zeros(n, dtype)
+        for j, f in enumerate(GATHER_FIELDS):
+            rec[f] = b[1:n + 1, j].astype(dtype[f])
+        out.append(rec)
+    return np.concatenate(out) if out else np.zeros(0, dtype)
+
+
+def gather_detections(dets, frame_offset, capacity, dist, device=None, dst=0):
+    """Result gather: every rank contributes one fixed-size block; rank `dst` gets them all.
+    `dist` is torch.distributed (initialised); tensors live on `device` (cuda for NCCL)."""
+    import torch
+    block = torch.from_numpy(pack_detections(dets, frame_offset, capacity))
+    if device is not None:
+        block = block.to(device)
+    world = dist.get_world_size()
+    bucket = [torch.empty_like(block) for _ in range(world)]
+    dist.all_gather(bucket, block)
+    if dist.get_rank() != dst:
+        return None
+    return unpack_detections([b.cpu().numpy() for b in bucket], dets.dtype)

@@ -205,6 +205,11 @@ FDB_API int fdb_ctx_synchronize(fdb_ctx* ctx);
 /* Number of kernel launches issued by this context so far (for bench accounting). */
 FDB_API int64_t fdb_ctx_launch_count(fdb_ctx* ctx);
 
+/* CUDA-event stopwatch on the context stream (device time, for bench.py):
+ * start records an event; stop records a second one, waits for it and returns the elapsed ms. */
+FDB_API int fdb_ctx_timer_start(fdb_ctx* ctx);
+FDB_API int fdb_ctx_timer_stop(fdb_ctx* ctx, double* elapsed_ms);
+
 /* Pinned host memory for frame/result staging (optional; any host memory is accepted). */
 FDB_API int fdb_host_alloc(size_t bytes, void** out);
 FDB_API void fdb_host_free(void* p);
@@ -273,6 +278,11 @@ FDB_API int fdb_detect_batch_device(fdb_detector* det, const uint8_t* frames_dev
  * synchronising (used for kernel timing). dense_out_device may be NULL. */
 FDB_API int fdb_detect_enqueue_device(fdb_detector* det, const uint8_t* frames_device,
 		int32_t n_frames, fdb_window_score* dense_out_device);
+
+/* Same enqueue with CUDA events between the kernels of the step; after completion
+ * ms_out[0..3] = resize kernel, pyrDown kernels, fused hq64+WVM window kernel, whole step (ms). */
+FDB_API int fdb_detect_profile_device(fdb_detector* det, const uint8_t* frames_device,
+		int32_t n_frames, double ms_out[4]);
 
 /* ROI variant: Detector::detect(Mat, Rect) (FiveStageSlidingWindowDetector.cpp:331-380,
  * SlidingWindowDetector.cpp:53-79): one frame, windows restricted by roi {x,y,w,h}. */

@@ -595,6 +595,47 @@ static void non_maxima_suppression(const float* src, int M, int N, int sz, uint8
 		}
 }
 
+/* grid NMS + bookkeeping of FiveStageSlidingWindowDetector::detect(Mat)
+ * (FiveStageSlidingWindowDetector.cpp:276-311) on one frame's SVM-positive patches, in place */
+int64_t fdo_five_stage_nms(fdb_detection* det_out, int64_t n, int width, int height) {
+	float* map = (float*)calloc((size_t)width * height, sizeof(float));
+	uint8_t* mask = (uint8_t*)calloc((size_t)width * height, 1);
+	uint8_t* maxima = (uint8_t*)malloc((size_t)width * height);
+	for (int64_t i = 0; i < n; ++i) {
+		int px = det_out[i].center_x, py = det_out[i].center_y;
+		if (px < 0 || py < 0 || px >= width || py >= height) continue; /* UB in the reference */
+		if (map[(size_t)py * width + px] < det_out[i].probability)
+			map[(size_t)py * width + px] = (float)det_out[i].probability;
+	}
+	for (size_t i = 0; i < (size_t)width * height; ++i) mask[i] = map[i] > 0.3f ? 255 : 0;
+	non_maxima_suppression(map, height, width, 35, maxima, mask);
+	int64_t nz = 0;
+	for (size_t i = 0; i < (size_t)width * height; ++i) nz += maxima[i] != 0;
+	int skip = 0;
+	if (nz == 0) {
+		non_maxima_suppression(map, height, width, 35, maxima, NULL);
+		for (size_t i = 0; i < (size_t)width * height; ++i) nz += maxima[i] != 0;
+		if (nz == 0) skip = 1; /* :292-294 returns svmPatchesPositive as is */
+	}
+	if (!skip) {
+		stable_sort_desc(det_out, n);                               /* :298 */
+		fdb_detection* sel = (fdb_detection*)malloc(sizeof(fdb_detection) * (size_t)(nz ? nz : 1));
+		int64_t m = 0;
+		for (int y = 0; y < height; ++y)                            /* findNonZero order: row-major */
+			for (int x = 0; x < width; ++x) {
+				if (!maxima[(size_t)y * width + x]) continue;
+				for (int64_t i = 0; i < n; ++i)
+					if (det_out[i].center_x == x && det_out[i].center_y == y) { sel[m++] = det_out[i]; break; }
+			}
+		memcpy(det_out, sel, sizeof(fdb_detection) * (size_t)m);
+		free(sel);
+		n = m;
+		stable_sort_desc(det_out, n);                               /* :311 */
+	}
+	free(map); free(mask); free(maxima);
+	return n;
+}
+
 static void fill_geometry(fdb_detection* d, const fdb_layer_info* L, int frame, int x, int y, int64_t window) {
 	/* DirectPyramidFeatureExtractor.cpp:115-118 */
 	d->frame = frame; d->layer = L->index; d->x = x; d->y = y;
@@ -684,42 +725,7 @@ int64_t fdo_detect_frame(const fdb_detector_desc* desc, const fdo_wvm* wvm, cons
 		n = k;
 		counts[3] = n;
 		if (stage >= FDB_STAGE_NMS && !is_roi) {
-			/* FiveStageSlidingWindowDetector.cpp:276-305 */
-			float* map = (float*)calloc((size_t)width * height, sizeof(float));
-			uint8_t* mask = (uint8_t*)calloc((size_t)width * height, 1);
-			uint8_t* maxima = (uint8_t*)malloc((size_t)width * height);
-			for (int64_t i = 0; i < n; ++i) {
-				int px = det_out[i].center_x, py = det_out[i].center_y;
-				if (px < 0 || py < 0 || px >= width || py >= height) continue; /* UB in the reference */
-				if (map[(size_t)py * width + px] < det_out[i].probability)
-					map[(size_t)py * width + px] = (float)det_out[i].probability;
-			}
-			for (size_t i = 0; i < (size_t)width * height; ++i) mask[i] = map[i] > 0.3f ? 255 : 0;
-			non_maxima_suppression(map, height, width, 35, maxima, mask);
-			int64_t nz = 0;
-			for (size_t i = 0; i < (size_t)width * height; ++i) nz += maxima[i] != 0;
-			int skip = 0;
-			if (nz == 0) {
-				non_maxima_suppression(map, height, width, 35, maxima, NULL);
-				for (size_t i = 0; i < (size_t)width * height; ++i) nz += maxima[i] != 0;
-				if (nz == 0) skip = 1; /* :292-294 returns svmPatchesPositive as is */
-			}
-			if (!skip) {
-				stable_sort_desc(det_out, n);                               /* :298 */
-				fdb_detection* sel = (fdb_detection*)malloc(sizeof(fdb_detection) * (size_t)(nz ? nz : 1));
-				int64_t m = 0;
-				for (int y = 0; y < height; ++y)                            /* findNonZero order: row-major */
-					for (int x = 0; x < width; ++x) {
-						if (!maxima[(size_t)y * width + x]) continue;
-						for (int64_t i = 0; i < n; ++i)
-							if (det_out[i].center_x == x && det_out[i].center_y == y) { sel[m++] = det_out[i]; break; }
-					}
-				memcpy(det_out, sel, sizeof(fdb_detection) * (size_t)m);
-				free(sel);
-				n = m;
-				stable_sort_desc(det_out, n);                               /* :311 */
-			}
-			free(map); free(mask); free(maxima);
+			n = fdo_five_stage_nms(det_out, n, width, height);
 			counts[4] = n;
 		} else {
 			stable_sort_desc(det_out, n);                                   /* ROI variant :366 */

@@ -106,6 +106,9 @@ def ref():
         R.ref_overlap_eliminate.restype = C.c_int
         R.ref_overlap_eliminate.argtypes = [C.c_float, C.c_float, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                             C.c_void_p, C.c_void_p]
+        R.ref_detect_frame.restype = C.c_int64
+        R.ref_detect_frame.argtypes = [C.POINTER(capi.DetectorDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                       C.c_int, C.c_void_p, C.POINTER(C.c_int64), C.c_void_p, C.c_int64, C.POINTER(C.c_double)]
         _ref = R
     return _ref
 
@@ -277,3 +280,30 @@ def detect_frame(det_kwargs, wvm, svm, frame, stage=capi.FDB_STAGE_NMS, roi=(0, 
     layers = [{f: getattr(infos[i], f) for f, _ in capi.LayerInfo._fields_} for i in range(n_layers)]
     return dict(windows=int(total), dense=dense, patches=patches, detections=dets[:n].copy(),
                 counts=list(counts), timing=list(tim), layers=layers)
+
+
+def ref_detect_frame(det_kwargs, wvm, svm, frame, stage=capi.FDB_STAGE_NMS, want_dense=True, det_cap=1 << 16):
+    """One frame through the reference's own classes (oracle/_ref; see ref_driver.cpp:ref_detect_frame).
+    wvm / svm are Wvm / Svm objects created with use_ref=True. Returns a dict."""
+    from featuredetection_b200.synthetic import detector_desc
+    desc = detector_desc(**det_kwargs)
+    frame = np.ascontiguousarray(frame, np.uint8)
+    H, W = frame.shape
+    nwin = C.c_int64()
+    tim = (C.c_double * 5)()
+    wins = np.zeros(det_cap, np.int64)
+    # first call sizes the dense buffer
+    dense = None
+    if want_dense:
+        from featuredetection_b200 import capi as _c
+        lib_ = _c.load_library() if False else None  # (no product code involved)
+        p = lib().fdo_pyramid_build(frame.ctypes.data, W, H, W, desc.incremental_scale_factor, desc.min_scale_factor, desc.max_scale_factor)
+        infos = (capi.LayerInfo * max(p.contents.n_layers, 1))()
+        total = lib().fdo_enumerate(p, desc.patch_width, desc.patch_height, max(desc.step_x, 1), max(desc.step_y, 1), 0, 0, 0, 0, infos, p.contents.n_layers)
+        lib().fdo_pyramid_free(p)
+        dense = np.zeros(total, SCORE_DTYPE)
+    n = ref().ref_detect_frame(C.byref(desc), wvm.h, svm.h if svm is not None else None, frame.ctypes.data, W, H, stage,
+                               dense.ctypes.data if dense is not None else None, C.byref(nwin), wins.ctypes.data, det_cap, tim)
+    if n < 0:
+        raise RuntimeError("ref_detect_frame failed (%d)" % n)
+    return dict(windows=int(nwin.value), dense=dense, det_windows=wins[:n].copy(), timing=list(tim))

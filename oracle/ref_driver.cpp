@@ -25,7 +25,11 @@
 #include "detection/OverlapElimination.hpp"
 
 #include "fdb200.h"
+#include "fd_oracle.h"
 
+#include <chrono>
+
+#include <algorithm>
 #include <memory>
 #include <vector>
 
@@ -185,6 +189,95 @@ int ref_overlap_eliminate(float dist, float ratio, int n, const int* cx, const i
 	for (size_t i = 0; i < out.size(); ++i)
 		keep_out[i] = out[i]->getPatch()->getData().at<int>(0, 0);
 	return (int)out.size();
+}
+
+/* The reference arm of bench.py: one frame through the reference's OWN classes in the order of
+ * SlidingWindowDetector::detect() (SlidingWindowDetector.cpp:87-98) and
+ * FiveStageSlidingWindowDetector::detect (FiveStageSlidingWindowDetector.cpp:187-322):
+ *   extract: Mat(layer, bounds) -> HistEq64Filter::applyTo -> make_shared<Patch>   (per window heap objects,
+ *            DirectPyramidFeatureExtractor.cpp:113-118)
+ *   classify: ProbabilisticWvmClassifier::getProbability per patch, keep positives
+ *   OverlapElimination::eliminate, ProbabilisticSvmClassifier::classify on the survivors
+ * The OpenCV-owned pyramid (cv::resize / cv::pyrDown) and the cv::minMaxLoc based grid NMS cannot be
+ * compiled without OpenCV; those two steps come from the restatement in fd_oracle.c.
+ * timing_out (NULL or 5 doubles, seconds): pyramid, extract+hq64, wvm, oe, svm+nms. */
+int64_t ref_detect_frame(const fdb_detector_desc* desc, void* wvm_h, void* svm_h, const uint8_t* frame, int width, int height,
+		int stage, fdb_window_score* dense_out, int64_t* windows_out, int64_t* det_windows_out, int64_t det_cap, double* timing_out) {
+	typedef std::chrono::steady_clock clk;
+	auto secs = [](clk::time_point a, clk::time_point b) { return std::chrono::duration<double>(b - a).count(); };
+	RefWvm* rw = (RefWvm*)wvm_h;
+	RefSvm* rs = (RefSvm*)svm_h;
+	static imageprocessing::HistEq64Filter hq64;
+	auto t0 = clk::now();
+	fdo_pyramid* pyr = fdo_pyramid_build(frame, width, height, width, desc->incremental_scale_factor,
+			desc->min_scale_factor, desc->max_scale_factor);
+	if (!pyr) return -2;
+	auto t1 = clk::now();
+	const int pw = desc->patch_width, ph = desc->patch_height;
+	const int sx = desc->step_x > 0 ? desc->step_x : 1, sy = desc->step_y > 0 ? desc->step_y : 1;
+	vector<fdb_layer_info> infos((size_t)std::max(pyr->n_layers, 1));
+	const int64_t total = fdo_enumerate(pyr, pw, ph, sx, sy, 0, 0, 0, 0, infos.data(), pyr->n_layers);
+	if (windows_out) *windows_out = total;
+	vector<shared_ptr<imageprocessing::Patch>> patches;
+	vector<int64_t> window_of;
+	patches.reserve((size_t)total);
+	for (int li = 0; li < pyr->n_layers; ++li) {
+		const fdo_layer& L = pyr->layers[li];
+		const fdb_layer_info& I = infos[(size_t)li];
+		Mat image(L.height, L.width, CV_8U, L.data);
+		for (int iy = 0; iy < I.windows_y; ++iy)
+			for (int ix = 0; ix < I.windows_x; ++ix) {
+				cv::Rect bounds(ix * sx, iy * sy, pw, ph);
+				const int ox = cvRound(bounds.x / L.scale) + I.orig_patch_width / 2;
+				const int oy = cvRound(bounds.y / L.scale) + I.orig_patch_height / 2;
+				Mat data = hq64.applyTo(Mat(image, bounds));
+				patches.push_back(make_shared<imageprocessing::Patch>(ox, oy, I.orig_patch_width, I.orig_patch_height, data));
+			}
+	}
+	auto t2 = clk::now();
+	vector<shared_ptr<detection::ClassifiedPatch>> classified;
+	for (size_t i = 0; i < patches.size(); ++i) {
+		std::pair<int, double> ld = rw->wvm->computeHyperplaneDistance(patches[i]->getData());
+		std::pair<bool, double> res = rw->pwvm->getProbability(ld);
+		if (dense_out) { dense_out[i].fout = (float)ld.second; dense_out[i].level = ld.first; }
+		if (res.first) { classified.push_back(make_shared<detection::ClassifiedPatch>(patches[i], res)); window_of.push_back((int64_t)i); }
+	}
+	auto t3 = clk::now();
+	/* remember the window index of each patch through the stages */
+	std::vector<std::pair<const imageprocessing::Patch*, int64_t>> ids;
+	for (size_t i = 0; i < classified.size(); ++i) ids.push_back({classified[i]->getPatch().get(), window_of[i]});
+	if (stage >= FDB_STAGE_OE) {
+		detection::OverlapElimination oe(desc->oe_dist, desc->oe_ratio);
+		classified = oe.eliminate(classified);
+	}
+	auto t4 = clk::now();
+	vector<shared_ptr<detection::ClassifiedPatch>> positives = classified;
+	if (stage >= FDB_STAGE_SVM && rs) {
+		positives.clear();
+		for (const auto& p : classified) {
+			bool ok = rs->psvm->classify(p->getPatch()->getData());
+			if (ok) positives.push_back(make_shared<detection::ClassifiedPatch>(p->getPatch(), ok));
+		}
+	}
+	int64_t n = 0;
+	vector<fdb_detection> dets;
+	for (const auto& p : positives) {
+		fdb_detection d;
+		std::memset(&d, 0, sizeof(d));
+		d.center_x = p->getPatch()->getX(); d.center_y = p->getPatch()->getY();
+		d.width = p->getPatch()->getWidth(); d.height = p->getPatch()->getHeight();
+		d.probability = p->getProbability();
+		for (const auto& id : ids) if (id.first == p->getPatch().get()) d.window = id.second;
+		dets.push_back(d);
+	}
+	n = (int64_t)dets.size();
+	if (stage >= FDB_STAGE_NMS && rs && n) n = fdo_five_stage_nms(dets.data(), n, width, height);
+	auto t5 = clk::now();
+	if (n > det_cap) n = -1;
+	for (int64_t i = 0; i < n; ++i) det_windows_out[i] = dets[(size_t)i].window;
+	if (timing_out) { timing_out[0] = secs(t0, t1); timing_out[1] = secs(t1, t2); timing_out[2] = secs(t2, t3); timing_out[3] = secs(t3, t4); timing_out[4] = secs(t4, t5); }
+	fdo_pyramid_free(pyr);
+	return n;
 }
 
 } // extern "C"

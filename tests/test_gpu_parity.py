@@ -64,6 +64,8 @@ def test_extract_patches_bit_exact(ctx, face_models):
 def test_dense_scores_and_levels(ctx, face_models, face_models_noexit, profile):
     fo = _oracle()
     det_kw, wvm, svm = face_models if profile == "realistic" else face_models_noexit
+    if profile == "no-exit":  # every window is a stage-1 positive
+        det_kw = dict(det_kw, max_positives_per_frame=20000)
     casc = SlidingWindowCascade(ctx, det_kw, wvm, svm)
     nframes = 3 if profile == "realistic" else 1
     casc.prepare(640, 480, nframes)
@@ -71,7 +73,8 @@ def test_dense_scores_and_levels(ctx, face_models, face_models_noexit, profile):
     dets, dense = casc.detect(frames, stage=capi.FDB_STAGE_WVM, want_dense=True, det_cap=1 << 17)
     wo = fo.Wvm(wvm)
     for k in range(nframes):
-        ref = fo.detect_frame(det_kw, wo, None, frames[k], stage=capi.FDB_STAGE_WVM, det_cap=1 << 17)
+        okw = {k2: v for k2, v in det_kw.items() if k2 != "max_positives_per_frame"}
+        ref = fo.detect_frame(okw, wo, None, frames[k], stage=capi.FDB_STAGE_WVM, det_cap=1 << 17)
         assert ref["windows"] == dense.shape[1] == 16185
         assert np.array_equal(dense[k]["level"], ref["dense"]["level"])
         assert np.max(np.abs(dense[k]["fout"] - ref["dense"]["fout"])) <= TOL
