@@ -88,7 +88,8 @@ struct fdb_detector {
 	fdb_window_score* d_dense = nullptr;
 	uint8_t* d_patches = nullptr; int64_t d_patches_bytes = 0;
 	Candidate* d_cand = nullptr;
-	int* d_cand_count = nullptr;
+	int* d_cand_count = nullptr;      /* [0] candidate counter, [1] deep-queue counter */
+	DeepQueue deep{};
 	DevLayer* d_layers = nullptr;     /* whole-image scan */
 	DevLayer* d_layers_roi = nullptr; /* scratch table for ROI scans */
 	ResizeJob* d_resize = nullptr; int n_resize = 0; int max_quads = 0;
@@ -174,7 +175,7 @@ int enqueue_stage1(fdb_detector* det, const uint8_t* d_frames, int n, const Plan
 	fdb_ctx* c = det->ctx;
 	cudaStream_t st = c->stream;
 	const int W = plan.width, H = plan.height;
-	if (want_candidates) CUDA_TRY(cudaMemsetAsync(det->d_cand_count, 0, sizeof(int), st));
+	CUDA_TRY(cudaMemsetAsync(det->d_cand_count, 0, 2 * sizeof(int), st));
 	if (marks) CUDA_TRY(cudaEventRecord(c->ev[1], st));
 	if (det->n_resize) {
 		launch_resize(st, d_frames, W, H, n, det->d_arena, plan.arena_bytes, det->d_resize, det->n_resize,
@@ -192,8 +193,8 @@ int enqueue_stage1(fdb_detector* det, const uint8_t* d_frames, int n, const Plan
 		DevWvm m = det->wvm->dev;
 		m.step_x = det->desc.step_x; m.step_y = det->desc.step_y;
 		launch_wvm_windows(st, m, d_frames, W, H, n, det->d_arena, plan.arena_bytes, d_layers, (int)plan.layers.size(),
-				(int)windows, d_dense, d_patches, want_candidates ? det->d_cand : nullptr, det->d_cand_count, det->cand_cap);
-		c->launches++;
+				(int)windows, d_dense, d_patches, want_candidates ? det->d_cand : nullptr, det->d_cand_count, det->cand_cap, det->deep);
+		c->launches += det->wvm->dev.num_lin > 0 ? 2 : 1;
 	}
 	if (marks) CUDA_TRY(cudaEventRecord(c->ev[4], st));
 	CUDA_TRY(cudaGetLastError());
@@ -718,6 +719,11 @@ int fdb_detector_prepare(fdb_detector* det, int32_t width, int32_t height, int32
 	s = dev_alloc(&det->d_arena, (size_t)max_batch * (size_t)plan.arena_bytes, det->owned); if (s) return s;
 	s = dev_alloc(&det->d_cand, (size_t)det->cand_cap, det->owned); if (s) return s;
 	s = dev_alloc(&det->d_cand_count, 4, det->owned); if (s) return s;
+	/* deep queue: room for 1/16 of the windows of a full batch (beyond that windows finish inline) */
+	det->deep.count = det->d_cand_count + 1;
+	det->deep.cap = (int)std::max<int64_t>(1024, std::min<int64_t>(plan.windows * max_batch / 16 + 1024, (int64_t)1 << 24));
+	s = dev_alloc(&det->deep.rec, (size_t)det->deep.cap, det->owned); if (s) return s;
+	s = dev_alloc(&det->deep.patch, (size_t)det->deep.cap * (size_t)det->wvm->dev.nwords, det->owned); if (s) return s;
 	s = dev_alloc(&det->d_layers, FDB_MAX_LAYERS, det->owned); if (s) return s;
 	s = dev_alloc(&det->d_layers_roi, FDB_MAX_LAYERS, det->owned); if (s) return s;
 	s = dev_alloc(&det->d_items, (size_t)det->items_cap, det->owned); if (s) return s;

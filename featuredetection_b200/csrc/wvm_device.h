@@ -15,6 +15,22 @@ namespace fdb {
 #define FDB_MAX_FILTERS 512   /* hk_kernel_eval capacity per window (e.g. 280 used) */
 #define FDB_MAX_PER_LEVEL 64  /* u_kernel_eval capacity (numFiltersPerLevel, e.g. 14..30) */
 #define FDB_MAX_VALUES 8      /* grey values v >= 1 per filter (cntval - 1) */
+#define WVM_KA 6              /* filters evaluated by the window kernel before a survivor is queued for wvm_deep_kernel */
+
+/* a window that survived the first WVM_KA filters (state of WvmClassifier::computeHyperplaneDistance so far) */
+struct DeepRec {
+	int frame, window;
+	float total_f, sum_xx;
+	float hk[WVM_KA];
+	float u[WVM_KA];
+};
+
+struct DeepQueue {
+	int* count;        /* device counter (may run past cap) */
+	int cap;
+	DeepRec* rec;      /* [cap]; nullptr disables the queue */
+	uint32_t* patch;   /* [nwords][cap] equalised patch words */
+};
 
 /* WvmClassifier state in evaluator form; all pointers are device memory */
 struct DevWvm {
@@ -47,7 +63,7 @@ int wvm_configure();
 size_t wvm_smem_bytes(const DevWvm& m);
 void launch_wvm_windows(cudaStream_t st, const DevWvm& m, const uint8_t* frames, int W, int H, int n_frames,
 		const uint8_t* arena, int64_t arena_stride, const DevLayer* layers, int n_layers, int windows_per_frame,
-		fdb_window_score* dense, uint8_t* patches_out, Candidate* cand, int* cand_count, int cand_cap);
+		fdb_window_score* dense, uint8_t* patches_out, Candidate* cand, int* cand_count, int cand_cap, const DeepQueue& q);
 void launch_wvm_patches(cudaStream_t st, const DevWvm& m, const uint8_t* patches, int n, fdb_window_score* dense);
 
 void launch_resize(cudaStream_t st, const uint8_t* frames, int W, int H, int n_frames, uint8_t* arena,
