@@ -90,6 +90,8 @@ struct fdb_detector {
 	Candidate* d_cand = nullptr;
 	int* d_cand_count = nullptr;      /* [0] candidate counter, [1] deep-queue counter */
 	DeepQueue deep{};
+	Strip* d_strips = nullptr; int n_strips = 0;
+	bool use_strips = false;          /* fast path usable (and not yet overflowed) */
 	DevLayer* d_layers = nullptr;     /* whole-image scan */
 	DevLayer* d_layers_roi = nullptr; /* scratch table for ROI scans */
 	ResizeJob* d_resize = nullptr; int n_resize = 0; int max_quads = 0;
@@ -192,8 +194,13 @@ int enqueue_stage1(fdb_detector* det, const uint8_t* d_frames, int n, const Plan
 	if (windows > 0) {
 		DevWvm m = det->wvm->dev;
 		m.step_x = det->desc.step_x; m.step_y = det->desc.step_y;
-		launch_wvm_windows(st, m, d_frames, W, H, n, det->d_arena, plan.arena_bytes, d_layers, (int)plan.layers.size(),
-				(int)windows, d_dense, d_patches, want_candidates ? det->d_cand : nullptr, det->d_cand_count, det->cand_cap, det->deep);
+		if (det->use_strips && d_layers == det->d_layers && !d_patches) {
+			launch_wvm_strips(st, m, d_frames, W, H, n, det->d_arena, plan.arena_bytes, d_layers, det->d_strips, det->n_strips,
+					(int)windows, d_dense, want_candidates ? det->d_cand : nullptr, det->d_cand_count, det->cand_cap, det->deep);
+		} else {
+			launch_wvm_windows(st, m, d_frames, W, H, n, det->d_arena, plan.arena_bytes, d_layers, (int)plan.layers.size(),
+					(int)windows, d_dense, d_patches, want_candidates ? det->d_cand : nullptr, det->d_cand_count, det->cand_cap, det->deep);
+		}
 		c->launches += det->wvm->dev.num_lin > 0 ? 2 : 1;
 	}
 	if (marks) CUDA_TRY(cudaEventRecord(c->ev[4], st));
@@ -223,8 +230,14 @@ int finish_chunk(fdb_detector* det, const uint8_t* d_frames, int n, int frame_ba
 		const DevLayer* d_layers, int stage, bool is_roi, std::vector<fdb_detection>& out) {
 	fdb_ctx* c = det->ctx;
 	cudaStream_t st = c->stream;
-	CUDA_TRY(cudaMemcpyAsync(det->h_count, det->d_cand_count, sizeof(int), cudaMemcpyDeviceToHost, st));
+	CUDA_TRY(cudaMemcpyAsync(det->h_count, det->d_cand_count, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
 	CUDA_TRY(cudaStreamSynchronize(st));
+	if (det->use_strips && d_layers == det->d_layers && det->h_count[1] > det->deep.cap) {
+		/* more survivors than the deep queue holds (a model with hardly any early exits): the strip
+		 * kernel cannot finish them inline, so this detector switches to the generic kernels for good */
+		det->use_strips = false;
+		return -1000;
+	}
 	const int ncand = *det->h_count;
 	if (ncand > det->cand_cap)
 		return fail(FDB_ERR_OVERFLOW, "stage-1 candidate list overflow: raise max_positives_per_frame");
@@ -345,7 +358,7 @@ int fdb_ctx_create(int device, fdb_ctx** out) {
 	c->device = device;
 	CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
 	for (cudaEvent_t& e : c->ev) CUDA_TRY(cudaEventCreate(&e));
-	if (wvm_configure() != 0 || svm_configure() != 0) {
+	if (wvm_configure() != 0 || svm_configure() != 0 || strip_configure_all() != 0) {
 		cudaStreamDestroy(c->stream); delete c;
 		return fail(FDB_ERR_CUDA, "cudaFuncSetAttribute failed: libfdb200 kernels not loadable on this device");
 	}
@@ -414,8 +427,10 @@ int fdb_wvm_create(fdb_ctx* ctx, const fdb_wvm_desc* d, fdb_wvm** out) {
 	std::vector<int> val_off(n), mask_off(n);
 	std::vector<uint32_t> masks;
 	int slot = 0; size_t rofs = 0;
+	int max_nv = 0;
 	for (int f = 0; f < n; ++f) {
 		const int cntval = d->area_cntval[f];
+		max_nv = std::max(max_nv, cntval - 1);
 		if (cntval < 1) return fail(FDB_ERR_INVALID_ARGUMENT, "WVM: filter without grey values");
 		if (cntval - 1 > FDB_MAX_VALUES) return fail(FDB_ERR_UNSUPPORTED, "WVM: more than 8 rectangle grey values per filter");
 		val_off[f] = slot;
@@ -467,6 +482,16 @@ int fdb_wvm_create(fdb_ctx* ctx, const fdb_wvm_desc* d, fdb_wvm** out) {
 	UP(d->area_val, slot, val, dp);
 	UP(masks.data(), masks.size(), masks, up);
 	UP(mask_off.data(), n, mask_off, ip);
+	dv.masks4 = nullptr;
+	if (max_nv <= 4) { /* padded copy for the strip / deep-warp kernels: [filter][word][4] */
+		std::vector<uint32_t> m4((size_t)n * nwords * 4, 0u);
+		for (int f = 0; f < n; ++f) {
+			const int nv = d->area_cntval[f] - 1;
+			for (int j = 0; j < nwords; ++j)
+				for (int v = 0; v < nv; ++v) m4[((size_t)f * nwords + j) * 4 + v] = masks[(size_t)mask_off[f] + (size_t)j * nv + v];
+		}
+		UP(m4.data(), m4.size(), masks4, up);
+	}
 #undef UP
 	s = dev_alloc(&m->d_thresholds, (size_t)n, m->owned);
 	if (s) { free_all(m->owned); delete m; return s; }
@@ -733,6 +758,28 @@ int fdb_detector_prepare(fdb_detector* det, int32_t width, int32_t height, int32
 	s = host_alloc(&det->h_items, (size_t)det->items_cap, det->owned_host); if (s) return s;
 	s = host_alloc(&det->h_dist, (size_t)det->items_cap, det->owned_host); if (s) return s;
 	s = upload_layers(det, plan, det->d_layers); if (s) return s;
+	/* strip table of the fast path: whole-image scan, step 1, supported patch size, <= 4 grey values, <= 256 words */
+	det->use_strips = det->desc.step_x == 1 && det->desc.step_y == 1 && det->wvm->dev.masks4 != nullptr
+			&& strip_supported(det->desc.patch_width, det->desc.patch_height) && det->wvm->dev.num_lin > WVM_KA
+			&& det->wvm->dev.num_used > WVM_KA;
+	std::vector<Strip> strips;
+	if (det->use_strips) {
+		for (size_t li = 0; li < plan.layers.size(); ++li) {
+			const PlanLayer& L = plan.layers[li];
+			for (int ix0 = 0; ix0 < L.windows_x; ix0 += 32) {
+				const int cols = std::min(32, L.windows_x - ix0);
+				const int nsub = std::min(WVM_MAXSUB, 32 / cols);
+				for (int iy0 = 0; iy0 < L.windows_y; iy0 += nsub * WVM_RUN) {
+					Strip st{};
+					st.layer = (int)li; st.ix0 = ix0; st.iy0 = iy0; st.cols = cols;
+					st.nsub = std::min(nsub, (L.windows_y - iy0 + WVM_RUN - 1) / WVM_RUN);
+					strips.push_back(st);
+				}
+			}
+		}
+	}
+	det->n_strips = (int)strips.size();
+	s = upload(strips.data(), strips.size(), &det->d_strips, det->owned); if (s) return s;
 	det->prepared = true;
 	return FDB_OK;
 }
@@ -792,6 +839,10 @@ static int detect_impl(fdb_detector* det, const uint8_t* frames, bool frames_on_
 			CUDA_TRY(cudaMemcpyAsync(dense_out + (int64_t)base * plan.windows, det->d_dense,
 					sizeof(fdb_window_score) * (size_t)plan.windows * n, cudaMemcpyDeviceToHost, st));
 		s = finish_chunk(det, d_frames, n, base, plan, det->d_layers, stage, false, dets);
+		if (s == -1000) { /* deep-queue overflow: redo this chunk on the generic path */
+			base -= det->max_batch;
+			continue;
+		}
 		if (s) return s;
 	}
 	return copy_out(dets, dets_out, det_cap, n_dets);

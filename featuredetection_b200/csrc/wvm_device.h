@@ -47,6 +47,17 @@ struct DevWvm {
 	const double* val;              /* grey values */
 	const uint32_t* masks;          /* rectangle coverage counts, 4 pixels per word: filter f at mask_off[f], [nwords][cntval-1] */
 	const int* mask_off;            /* [num_lin] */
+	const uint32_t* masks4;         /* same, padded to 4 values per word: [num_lin][nwords][4]; nullptr if a filter has > 4 */
+};
+
+/* work item of wvm_strip_kernel: `cols` adjacent window columns x `nsub` runs of WVM_RUN window rows */
+#define WVM_RUN 8
+#define WVM_MAXSUB 4
+struct Strip {
+	int layer;      /* index into the DevLayer table */
+	int ix0, iy0;   /* first window column / row of the strip */
+	int cols, nsub; /* cols * nsub <= 32 lanes */
+	int pad[3];
 };
 
 /* SvmClassifier (RBF) state; support vectors transposed to [word][sv] for coalesced reads */
@@ -65,6 +76,13 @@ void launch_wvm_windows(cudaStream_t st, const DevWvm& m, const uint8_t* frames,
 		const uint8_t* arena, int64_t arena_stride, const DevLayer* layers, int n_layers, int windows_per_frame,
 		fdb_window_score* dense, uint8_t* patches_out, Candidate* cand, int* cand_count, int cand_cap, const DeepQueue& q);
 void launch_wvm_patches(cudaStream_t st, const DevWvm& m, const uint8_t* patches, int n, fdb_window_score* dense);
+
+/* fast path (wvm_strip.cu): whole-image scans with step 1 and one of the ffpDetectApp patch sizes */
+int strip_configure_all();
+bool strip_supported(int patch_w, int patch_h);
+void launch_wvm_strips(cudaStream_t st, const DevWvm& m, const uint8_t* frames, int W, int H, int n_frames,
+		const uint8_t* arena, int64_t arena_stride, const DevLayer* layers, const Strip* strips, int n_strips,
+		int windows_per_frame, fdb_window_score* dense, Candidate* cand, int* cand_count, int cand_cap, const DeepQueue& q);
 
 void launch_resize(cudaStream_t st, const uint8_t* frames, int W, int H, int n_frames, uint8_t* arena,
 		int64_t arena_stride, const ResizeJob* jobs_dev, int n_jobs, int max_quads,
