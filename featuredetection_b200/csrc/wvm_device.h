@@ -15,7 +15,7 @@ namespace fdb {
 #define FDB_MAX_FILTERS 512   /* hk_kernel_eval capacity per window (e.g. 280 used) */
 #define FDB_MAX_PER_LEVEL 64  /* u_kernel_eval capacity (numFiltersPerLevel, e.g. 14..30) */
 #define FDB_MAX_VALUES 8      /* grey values v >= 1 per filter (cntval - 1) */
-#define WVM_KA 6              /* filters evaluated by the window kernel before a survivor is queued for wvm_deep_kernel */
+#define WVM_KA 8              /* filters evaluated by the window kernel before a survivor is queued for wvm_deep_kernel */
 
 /* a window that survived the first WVM_KA filters (state of WvmClassifier::computeHyperplaneDistance so far) */
 struct DeepRec {
@@ -27,6 +27,7 @@ struct DeepRec {
 
 struct DeepQueue {
 	int* count;        /* device counter (may run past cap) */
+	int* next;         /* work-distribution cursor of wvm_deep_warp_kernel */
 	int cap;
 	DeepRec* rec;      /* [cap]; nullptr disables the queue */
 	uint32_t* patch;   /* [nwords][cap] equalised patch words */
@@ -51,13 +52,14 @@ struct DevWvm {
 };
 
 /* work item of wvm_strip_kernel: `cols` adjacent window columns x `nsub` runs of WVM_RUN window rows */
-#define WVM_RUN 8
+#define WVM_RUN 12   /* longest run of window rows one lane walks down */
 #define WVM_MAXSUB 4
 struct Strip {
 	int layer;      /* index into the DevLayer table */
 	int ix0, iy0;   /* first window column / row of the strip */
 	int cols, nsub; /* cols * nsub <= 32 lanes */
-	int pad[3];
+	int run;        /* window rows per lane (balanced over the layer, <= WVM_RUN) */
+	int pad[2];
 };
 
 /* SvmClassifier (RBF) state; support vectors transposed to [word][sv] for coalesced reads */

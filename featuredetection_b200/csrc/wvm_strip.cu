@@ -71,17 +71,17 @@ __global__ void __launch_bounds__(STRIP_T, (PW * PH <= 416 ? 3 : (PW * PH <= 600
 	/* --- stage the strip's pixels as histogram bins (v >> 2, HistEq64Filter.cpp:14-25) --- */
 	const int tx0 = L.begin_x + st.ix0, ty0 = L.begin_y + st.iy0;
 	const int tcols = min(st.cols + PW - 1, L.width - tx0);
-	const int trows = min(st.nsub * WVM_RUN + PH - 1, L.height - ty0);
+	const int trows = min(st.nsub * st.run + PH - 1, L.height - ty0);
 	for (int r = 0; r < trows; ++r) {
 		const uint8_t* row = img + (int64_t)(ty0 + r) * L.width + tx0;
 		for (int c = lane; c < tcols; c += 32) s_tile[r * STRIP_TILE_PITCH + c] = row[c] >> 2;
 	}
 	__syncwarp();
 	const int col = lane % st.cols, sub = lane / st.cols;
-	const int iy_first = st.iy0 + sub * WVM_RUN;
+	const int iy_first = st.iy0 + sub * st.run;
 	if (sub >= st.nsub || iy_first >= L.windows_y) return;
-	const int nrows = min(WVM_RUN, L.windows_y - iy_first);
-	const uint8_t* const tcol = s_tile + (sub * WVM_RUN) * STRIP_TILE_PITCH + col;
+	const int nrows = min(st.run, L.windows_y - iy_first);
+	const uint8_t* const tcol = s_tile + (sub * st.run) * STRIP_TILE_PITCH + col;
 	const float stretch = __fdiv_rn(255.0f, (float)(PW * PH)); /* HistEq64Filter.cpp:34 */
 
 	/* histogram of the first window of the run, two 16-bit counts per word */
@@ -223,7 +223,12 @@ __global__ void __launch_bounds__(DEEP_WARPS * 32) wvm_deep_warp_kernel(const De
 	const int n = min(*q.count, q.cap);
 	const int nt = (m.nwords + 31) / 32;
 	const int own = lane >> 1;          /* filter (within the round) owned by the even lanes */
-	for (int slot = blockIdx.x * DEEP_WARPS + warp; slot < n; slot += gridDim.x * DEEP_WARPS) {
+	for (;;) {
+		/* dynamic work distribution: windows differ by 50x in cost (first-round exits vs. full depth) */
+		int slot = 0;
+		if (lane == 0) slot = atomicAdd(q.next, 1);
+		slot = __shfl_sync(0xffffffffu, slot, 0);
+		if (slot >= n) break;
 		const DeepRec rec = q.rec[slot];
 		uint32_t xw[DEEP_MAXT];
 #pragma unroll
@@ -290,7 +295,15 @@ __global__ void __launch_bounds__(DEEP_WARPS * 32) wvm_deep_warp_kernel(const De
 			if (owner) {
 				const float* __restrict__ wgt = m.hk_weights + (size_t)level * (level + 1) / 2;
 				res = -__ldg(m.lin_thresholds + level);
-				for (int p = 0; p <= level; ++p) res = __fadd_rn(res, __fmul_rn(__ldg(wgt + p), hk[p]));
+				int p = 0;
+				for (; p + 8 <= level + 1; p += 8) { /* loads first, then the sequential adds */
+					float wv[8];
+#pragma unroll
+					for (int i = 0; i < 8; ++i) wv[i] = __fmul_rn(__ldg(wgt + p + i), hk[p + i]);
+#pragma unroll
+					for (int i = 0; i < 8; ++i) res = __fadd_rn(res, wv[i]);
+				}
+				for (; p <= level; ++p) res = __fadd_rn(res, __fmul_rn(__ldg(wgt + p), hk[p]));
 				pass = res >= __ldg(m.thresholds + level) && level + 1 < m.num_used;
 			}
 			const unsigned fails = __ballot_sync(0xffffffffu, owner && !pass);
@@ -345,7 +358,7 @@ void launch_wvm_strips(cudaStream_t st, const DevWvm& m, const uint8_t* frames, 
 		layers, strips, n_strips, windows_per_frame, dense, cand, cand_count, cand_cap, q); }
 	FDB_STRIP_CASE(20, 20) else FDB_STRIP_CASE(24, 24) else FDB_STRIP_CASE(32, 16) else FDB_STRIP_CASE(32, 24) else FDB_STRIP_CASE(16, 24)
 #undef FDB_STRIP_CASE
-	const int blocks = std::min((q.cap + DEEP_WARPS - 1) / DEEP_WARPS, 148 * 8);
+	const int blocks = std::min((q.cap + DEEP_WARPS - 1) / DEEP_WARPS, 148 * 4);
 	wvm_deep_warp_kernel<<<blocks, DEEP_WARPS * 32, 0, st>>>(m, q, windows_per_frame, dense, cand, cand_count, cand_cap);
 }
 
