@@ -1,0 +1,23 @@
+/* Compile check of the adapters against the reference's unchanged headers (tests/test_adapters_compile.py):
+ * instantiates every adapter so that a missing pure-virtual override fails the build. */
+#include "fdb200_adapters.hpp"
+
+int main() {
+	std::shared_ptr<fdb200::Context> ctx; /* not created: no GPU needed to type-check */
+	fdb_wvm_desc wd = fdb_wvm_desc();
+	fdb_svm_desc sd = fdb_svm_desc();
+	fdb_detector_desc dd = fdb_detector_desc();
+	if (ctx) {
+		std::shared_ptr<fdb200::B200ProbabilisticWvmClassifier> wvm = std::make_shared<fdb200::B200ProbabilisticWvmClassifier>(ctx, wd);
+		std::shared_ptr<fdb200::B200ProbabilisticSvmClassifier> svm = std::make_shared<fdb200::B200ProbabilisticSvmClassifier>(ctx, sd);
+		std::shared_ptr<classification::ProbabilisticClassifier> c1 = wvm, c2 = svm;
+		std::shared_ptr<fdb200::B200SlidingWindowDetector> det = std::make_shared<fdb200::B200SlidingWindowDetector>(ctx, dd, wvm, svm);
+		std::shared_ptr<detection::Detector> d = det;
+		std::shared_ptr<imageprocessing::PyramidFeatureExtractor> e = det;
+		cv::Mat frame(480, 640, CV_8U);
+		d->detect(frame);
+		e->update(frame);
+		e->extract(1, 1);
+	}
+	return 0;
+}

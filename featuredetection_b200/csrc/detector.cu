@@ -79,7 +79,7 @@ struct fdb_detector {
 	DevLayer* d_layers_roi = nullptr; /* scratch table for ROI scans */
 	ResizeJob* d_resize = nullptr; int n_resize = 0; int max_quads = 0;
 	std::vector<DownJob*> d_down; std::vector<int> n_down; std::vector<int> max_down_px;
-	int* d_ofs_tab = nullptr; short2* d_coef_tab = nullptr;
+	int2* d_xy_tab = nullptr; /* bilinear tables: {source offset, a0 | a1 << 16} */
 	Strip* d_strips = nullptr; int n_strips = 0;
 	bool use_strips = false;          /* fast path usable (and not yet overflowed) */
 	int64_t counts[5] = {0, 0, 0, 0, 0};
@@ -133,7 +133,7 @@ int enqueue_stage1(fdb_detector* det, Slot& sl, cudaStream_t st, const uint8_t* 
 	if (marks) CUDA_TRY(cudaEventRecord(c->ev[1], st));
 	if (det->n_resize) {
 		launch_resize(st, d_frames, W, H, n, sl.d_arena, plan.arena_bytes, det->d_resize, det->n_resize,
-				det->max_quads, det->d_ofs_tab, det->d_coef_tab);
+				det->max_quads, det->d_xy_tab);
 		c->launches++;
 	}
 	if (marks) CUDA_TRY(cudaEventRecord(c->ev[2], st));
@@ -466,7 +466,7 @@ int fdb_detector_prepare(fdb_detector* det, int32_t width, int32_t height, int32
 			j.ytab = (int)ofs.size();
 			linear_tables(height, im.height, false, ofs, coef);
 			rj.push_back(j);
-			det->max_quads = std::max(det->max_quads, ((im.width + 3) / 4) * im.height);
+			det->max_quads = std::max(det->max_quads, resize_tiles(im.width, im.height));
 		} else if (im.kind == IMG_PYRDOWN) {
 			const PyrImage& src = plan.images[(size_t)im.src];
 			DownJob j{};
@@ -477,13 +477,17 @@ int fdb_detector_prepare(fdb_detector* det, int32_t width, int32_t height, int32
 	}
 	det->n_resize = (int)rj.size();
 	s = upload(rj.data(), rj.size(), &det->d_resize, det->owned); if (s) return s;
-	s = upload(ofs.data(), ofs.size(), &det->d_ofs_tab, det->owned); if (s) return s;
-	s = upload(coef.data(), coef.size(), &det->d_coef_tab, det->owned); if (s) return s;
+	std::vector<int2> xy(ofs.size());
+	for (size_t k = 0; k < ofs.size(); ++k) {
+		xy[k].x = ofs[k];
+		xy[k].y = (int)((uint32_t)(uint16_t)coef[k].x | ((uint32_t)(uint16_t)coef[k].y << 16));
+	}
+	s = upload(xy.data(), xy.size(), &det->d_xy_tab, det->owned); if (s) return s;
 	for (size_t j = 1; j < dj.size(); ++j) {
 		DownJob* p = nullptr;
 		s = upload(dj[j].data(), dj[j].size(), &p, det->owned); if (s) return s;
 		int mx = 0;
-		for (const DownJob& q : dj[j]) mx = std::max(mx, q.dst_w * q.dst_h);
+		for (const DownJob& q : dj[j]) mx = std::max(mx, pyrdown_tiles(q.dst_w, q.dst_h));
 		det->d_down.push_back(p); det->n_down.push_back((int)dj[j].size()); det->max_down_px.push_back(mx);
 	}
 	CUDA_TRY(cudaEventCreateWithFlags(&det->ev_begin, cudaEventDisableTiming));

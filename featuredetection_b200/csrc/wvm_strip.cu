@@ -250,16 +250,16 @@ __global__ void __launch_bounds__(DEEP_WARPS * 32) wvm_deep_warp_kernel(const De
 			for (int i = 0; i < DEEP_CH * 4; ++i) a[i] = 0;
 #pragma unroll
 			for (int l = 0; l < DEEP_CH; ++l) {
-				if (l < cnt) {
-					const uint4* __restrict__ mk4 = reinterpret_cast<const uint4*>(m.masks4 + (size_t)(base + l) * m.nwords * 4);
+				/* filters past the end of the cascade are clamped (their sums are never used); patch words past
+				 * the end are zero, so no per-element guards are needed */
+				const int lvl = min(base + l, m.num_used - 1);
+				const uint4* __restrict__ mk4 = reinterpret_cast<const uint4*>(m.masks4) + (size_t)lvl * m.nwords;
 #pragma unroll
-					for (int t = 0; t < DEEP_MAXT; ++t) {
-						const int j = lane + 32 * t;
-						if (t < nt && j < m.nwords) {
-							const uint4 k4 = __ldg(mk4 + j);
-							a[l * 4 + 0] = __dp4a(xw[t], k4.x, a[l * 4 + 0]); a[l * 4 + 1] = __dp4a(xw[t], k4.y, a[l * 4 + 1]);
-							a[l * 4 + 2] = __dp4a(xw[t], k4.z, a[l * 4 + 2]); a[l * 4 + 3] = __dp4a(xw[t], k4.w, a[l * 4 + 3]);
-						}
+				for (int t = 0; t < DEEP_MAXT; ++t) {
+					if (t < nt) { /* warp-uniform */
+						const uint4 k4 = __ldg(mk4 + min(lane + 32 * t, m.nwords - 1));
+						a[l * 4 + 0] = __dp4a(xw[t], k4.x, a[l * 4 + 0]); a[l * 4 + 1] = __dp4a(xw[t], k4.y, a[l * 4 + 1]);
+						a[l * 4 + 2] = __dp4a(xw[t], k4.z, a[l * 4 + 2]); a[l * 4 + 3] = __dp4a(xw[t], k4.w, a[l * 4 + 3]);
 					}
 				}
 			}

@@ -187,3 +187,57 @@ def test_batch_invariance_full_size(ctx, face_models):
     assert np.array_equal(first["window"], dets2["window"]) and np.array_equal(first["frame"], dets2["frame"])
     counts = casc.last_counts()
     assert counts[0] == 256 * 16185 and counts[4] == len(dets)
+
+
+def test_cuda_path_matches_reference_golden(ctx):
+    """The CUDA path against golden vectors produced by the reference's OWN compiled sources
+    (tests/golden/ref_classifiers.npz, made by tests/golden/make_ref_golden.py from oracle/_ref)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_classifiers.npz"))
+    det_kw, wvm, svm = syn.landmark_models("FaceFrontal")
+    _, wvm_ne, _ = syn.landmark_models("FaceFrontal", "no-exit")
+    for tag, model in (("realistic", wvm), ("noexit", wvm_ne)):
+        lv, fout, pr, pos = ProbabilisticWvmClassifier(ctx, model).get_probability(g["patches"])
+        assert np.array_equal(lv, g["wvm_%s_level" % tag]) and np.array_equal(pos, g["wvm_%s_pos" % tag])
+        assert np.max(np.abs(fout - g["wvm_%s_fout" % tag])) <= TOL and np.max(np.abs(pr - g["wvm_%s_prob" % tag])) <= TOL
+    d, p, q = ProbabilisticSvmClassifier(ctx, svm).get_probability(g["patches"])
+    assert np.max(np.abs(d - g["svm_dist"])) <= TOL and np.max(np.abs(p - g["svm_prob"])) <= TOL and np.array_equal(q, g["svm_pos"])
+    casc = SlidingWindowCascade(ctx, det_kw, wvm, svm)
+    casc.prepare(640, 480, 2)
+    frames = syn.synthetic_frames(0, 2)
+    dets, dense = casc.detect(frames, stage=capi.FDB_STAGE_WVM, want_dense=True)
+    for k in (0, 1):
+        assert np.array_equal(dense[k]["level"], g["frame%d_dense_level" % k])
+        assert np.max(np.abs(dense[k]["fout"] - g["frame%d_dense_fout" % k])) <= TOL
+    for stage, name in ((capi.FDB_STAGE_WVM, "wvm"), (capi.FDB_STAGE_OE, "oe"), (capi.FDB_STAGE_SVM, "svm"), (capi.FDB_STAGE_NMS, "nms")):
+        d = casc.detect(frames, stage=stage)
+        for k in (0, 1):
+            assert list(d[d["frame"] == k]["window"]) == list(g["frame%d_%s_windows" % (k, name)]), (k, name)
+    # extraction entry point: hq64 patches of the golden raw crops are covered by test_extract_patches_bit_exact
+
+
+def test_fifteen_landmark_geometries(ctx):
+    """Every ffpDetectApp cfg geometry (5 patch sizes incl. the generic fallbacks) on one frame: no-exit
+    synthetic models with few filters keep it fast; dense records against the oracle."""
+    fo = _oracle()
+    frame = syn.synthetic_frame(33)
+    seen = set()
+    for (nm, pw, ph, inc, mn, mx, per, lev, r) in syn.LANDMARK_CONFIGS:
+        if (pw, ph, inc, mn, mx) in seen:
+            continue
+        seen.add((pw, ph, inc, mn, mx))
+        wvm = syn.make_wvm(pw, ph, 4, 3, r, seed=900 + len(seen))
+        thr = np.full(12, -np.inf, np.float32); thr[::2] = 0.0  # mixed exits
+        wvm = wvm.with_thresholds(thr)
+        kw = dict(incremental_scale_factor=float(np.float32(inc)), min_scale_factor=float(np.float32(mn)),
+                  max_scale_factor=float(np.float32(mx)), patch_width=pw, patch_height=ph, step_x=1, step_y=1,
+                  max_positives_per_frame=400000)
+        casc = SlidingWindowCascade(ctx, kw, wvm, None)
+        casc.prepare(640, 480, 1)
+        dets, dense = casc.detect(frame[None], stage=capi.FDB_STAGE_WVM, want_dense=True, det_cap=400000)
+        okw = {k: v for k, v in kw.items() if k != "max_positives_per_frame"}
+        ref = fo.detect_frame(okw, fo.Wvm(wvm), None, frame, stage=capi.FDB_STAGE_WVM, det_cap=400000)
+        assert ref["windows"] == dense.shape[1], nm
+        assert np.array_equal(dense[0]["level"], ref["dense"]["level"]), nm
+        assert np.max(np.abs(dense[0]["fout"] - ref["dense"]["fout"])) <= TOL, nm
+        assert list(dets["window"]) == list(ref["detections"]["window"]), nm
