@@ -79,7 +79,7 @@ struct fdb_detector {
 	DevLayer* d_layers_roi = nullptr; /* scratch table for ROI scans */
 	ResizeJob* d_resize = nullptr; int n_resize = 0; int max_quads = 0;
 	std::vector<DownJob*> d_down; std::vector<int> n_down; std::vector<int> max_down_px;
-	int2* d_xy_tab = nullptr; /* bilinear tables: {source offset, a0 | a1 << 16} */
+	int4* d_xy_tab = nullptr; /* bilinear tables: {source offset, a0, a1, 0} */
 	Strip* d_strips = nullptr; int n_strips = 0;
 	bool use_strips = false;          /* fast path usable (and not yet overflowed) */
 	int64_t counts[5] = {0, 0, 0, 0, 0};
@@ -477,11 +477,8 @@ int fdb_detector_prepare(fdb_detector* det, int32_t width, int32_t height, int32
 	}
 	det->n_resize = (int)rj.size();
 	s = upload(rj.data(), rj.size(), &det->d_resize, det->owned); if (s) return s;
-	std::vector<int2> xy(ofs.size());
-	for (size_t k = 0; k < ofs.size(); ++k) {
-		xy[k].x = ofs[k];
-		xy[k].y = (int)((uint32_t)(uint16_t)coef[k].x | ((uint32_t)(uint16_t)coef[k].y << 16));
-	}
+	std::vector<int4> xy(ofs.size());
+	for (size_t k = 0; k < ofs.size(); ++k) { xy[k].x = ofs[k]; xy[k].y = coef[k].x; xy[k].z = coef[k].y; xy[k].w = 0; }
 	s = upload(xy.data(), xy.size(), &det->d_xy_tab, det->owned); if (s) return s;
 	for (size_t j = 1; j < dj.size(); ++j) {
 		DownJob* p = nullptr;

@@ -31,14 +31,14 @@ __device__ __forceinline__ int reflect101(int p, int len) {
 /* ---------------------------------------------------------------------------------------------
  * resize: grid = (tiles, job, frame); a CTA of 256 threads = 32 pixel-quads x 8 rows, i.e. a
  * 128 x 8 output tile; each thread produces 4 horizontally adjacent pixels and stores one word.
- * Tables: xy_tab[k] = {source offset, a0 | a1 << 16} (one 8-byte load per output column / row).
+ * Tables: xy_tab[k] = {source offset, a0, a1, 0} (one 16-byte load per output column / row).
  * ------------------------------------------------------------------------------------------- */
 #define RS_QX 32
 #define RS_TY 8
 
 __global__ void __launch_bounds__(RS_QX * RS_TY) resize_kernel(const uint8_t* __restrict__ frames, int W, int H,
 		uint8_t* __restrict__ arena, int64_t arena_stride,
-		const ResizeJob* __restrict__ jobs, const int2* __restrict__ xy_tab) {
+		const ResizeJob* __restrict__ jobs, const int4* __restrict__ xy_tab) {
 	const ResizeJob job = jobs[blockIdx.y];
 	const int quads_per_row = (job.dst_w + 3) >> 2;
 	const int tiles_x = (quads_per_row + RS_QX - 1) / RS_QX, tiles_y = (job.dst_h + RS_TY - 1) / RS_TY;
@@ -61,22 +61,34 @@ __global__ void __launch_bounds__(RS_QX * RS_TY) resize_kernel(const uint8_t* __
 				packed |= (uint32_t)((s0[x] + s0[x + 1] + s1[x] + s1[x + 1] + 2) >> 2) << (8 * k);
 			}
 	} else {
-		const int2 ty = __ldg(xy_tab + job.ytab + dy);
-		const int b0 = (short)(ty.y & 0xffff), b1 = ty.y >> 16;
+		const int4 ty = __ldg(xy_tab + job.ytab + dy);
 		const int y0 = min(max(ty.x, 0), H - 1), y1 = min(max(ty.x + 1, 0), H - 1);
-		const uint8_t* s0 = src + y0 * W;
-		const uint8_t* s1 = src + y1 * W;
-#pragma unroll
-		for (int k = 0; k < 4; ++k)
-			if (k < nvalid) {
-				const int2 tx = __ldg(xy_tab + job.xtab + dx0 + k);
-				const int a0 = (short)(tx.y & 0xffff), a1 = tx.y >> 16;
+		const uint8_t* __restrict__ s0 = src + y0 * W;
+		const uint8_t* __restrict__ s1 = src + y1 * W;
+		const int4* __restrict__ xt = xy_tab + job.xtab + dx0;
+		if (nvalid == 4) {
+			const int4 t0 = __ldg(xt), t1 = __ldg(xt + 1), t2 = __ldg(xt + 2), t3 = __ldg(xt + 3);
+			const int W1 = W - 1;
+			/* 16 independent byte loads first, then the fixed-point arithmetic */
+			const int p00 = s0[t0.x], p01 = s0[min(t0.x + 1, W1)], q00 = s1[t0.x], q01 = s1[min(t0.x + 1, W1)];
+			const int p10 = s0[t1.x], p11 = s0[min(t1.x + 1, W1)], q10 = s1[t1.x], q11 = s1[min(t1.x + 1, W1)];
+			const int p20 = s0[t2.x], p21 = s0[min(t2.x + 1, W1)], q20 = s1[t2.x], q21 = s1[min(t2.x + 1, W1)];
+			const int p30 = s0[t3.x], p31 = s0[min(t3.x + 1, W1)], q30 = s1[t3.x], q31 = s1[min(t3.x + 1, W1)];
+#define FDB_RS_PIX(P0, P1, Q0, Q1, T) ((((ty.y * ((P0 * T.y + P1 * T.z) >> 4)) >> 16) + ((ty.z * ((Q0 * T.y + Q1 * T.z) >> 4)) >> 16) + 2) >> 2)
+			const int v0 = FDB_RS_PIX(p00, p01, q00, q01, t0), v1 = FDB_RS_PIX(p10, p11, q10, q11, t1);
+			const int v2 = FDB_RS_PIX(p20, p21, q20, q21, t2), v3 = FDB_RS_PIX(p30, p31, q30, q31, t3);
+#undef FDB_RS_PIX
+			packed = (uint32_t)(v0 & 255) | ((uint32_t)(v1 & 255) << 8) | ((uint32_t)(v2 & 255) << 16) | ((uint32_t)(v3 & 255) << 24);
+		} else {
+			for (int k = 0; k < nvalid; ++k) {
+				const int4 tx = __ldg(xt + k);
 				const int sx = tx.x, sx1 = min(sx + 1, W - 1);
-				const int h0 = s0[sx] * a0 + s0[sx1] * a1;
-				const int h1 = s1[sx] * a0 + s1[sx1] * a1;
-				const int v = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
+				const int h0 = s0[sx] * tx.y + s0[sx1] * tx.z;
+				const int h1 = s1[sx] * tx.y + s1[sx1] * tx.z;
+				const int v = (((ty.y * (h0 >> 4)) >> 16) + ((ty.z * (h1 >> 4)) >> 16) + 2) >> 2;
 				packed |= (uint32_t)(v & 255) << (8 * k);
 			}
+		}
 	}
 	if (nvalid == 4 && ((job.dst_w & 3) == 0)) {
 		*reinterpret_cast<uint32_t*>(o) = packed;
@@ -86,56 +98,82 @@ __global__ void __launch_bounds__(RS_QX * RS_TY) resize_kernel(const uint8_t* __
 }
 
 /* ---------------------------------------------------------------------------------------------
- * pyrDown: grid = (tiles, job, frame); a CTA of 256 threads produces a 32x8 output tile.
- * The 67x19 input footprint is staged once in shared memory (border pixels resolved with
- * BORDER_REFLECT_101, only on tiles that touch the image border), the separable filter runs as a
- * horizontal pass into shared memory and a vertical pass from it: 5 + 5 shared-memory taps per
- * output instead of 25 global loads.  Integer sums are identical to the 25-tap form (OpenCV's
- * pyrDown has no intermediate rounding).
+ * pyrDown: grid = (tiles, job, frame); a CTA of 256 threads = 32 x 8 threads, each thread
+ * produces a 4 (x) x 2 (y) block of output pixels => a 128 x 16 output tile per CTA.
+ * Interior threads read their 7 x 11 input footprint as aligned 32-bit words straight from global
+ * memory (L1 serves the overlap with the neighbours), realign with funnel shifts and evaluate the
+ * horizontal [1 4 6 4 1] taps with dp4a on packed bytes; the vertical taps run on registers.
+ * Threads whose footprint touches the image border (BORDER_REFLECT_101) take a byte-wise path.
+ * Integer sums are identical to the 25-tap form (OpenCV's pyrDown has no intermediate rounding).
  * ------------------------------------------------------------------------------------------- */
-#define PD_TW 32
-#define PD_TH 8
-#define PD_IW (2 * PD_TW + 3)
-#define PD_IH (2 * PD_TH + 3)
+#define PD_BX 32
+#define PD_BY 8
+#define PD_TW (PD_BX * 4)
+#define PD_TH (PD_BY * 2)
 
-__global__ void __launch_bounds__(PD_TW * PD_TH) pyrdown_kernel(const uint8_t* __restrict__ frames, int W, int H,
+__device__ __forceinline__ void pd_hrow_fast(const uint8_t* __restrict__ rowp, int col, int* h) {
+	/* bytes col .. col+10 of the row as three words b[0..3], b[4..7], b[8..11] */
+	const uintptr_t addr = reinterpret_cast<uintptr_t>(rowp + col);
+	const uint32_t* __restrict__ wp = reinterpret_cast<const uint32_t*>(addr & ~(uintptr_t)3);
+	const unsigned sh = (unsigned)(addr & 3) * 8;
+	const uint32_t a0 = __ldg(wp), a1 = __ldg(wp + 1), a2 = __ldg(wp + 2), a3 = __ldg(wp + 3);
+	const uint32_t w0 = __funnelshift_r(a0, a1, sh), w1 = __funnelshift_r(a1, a2, sh), w2 = __funnelshift_r(a2, a3, sh);
+	h[0] = (int)__dp4a(w0, 0x04060401u, w1 & 0xffu);
+	h[1] = (int)__dp4a(w1, 0x00010406u, __dp4a(w0, 0x04010000u, 0u));
+	h[2] = (int)__dp4a(w1, 0x04060401u, w2 & 0xffu);
+	h[3] = (int)__dp4a(w2, 0x00010406u, __dp4a(w1, 0x04010000u, 0u));
+}
+
+__device__ __forceinline__ void pd_hrow_border(const uint8_t* __restrict__ src, int src_w, int src_h, int row, int col, int* h) {
+	const uint8_t* __restrict__ r = src + reflect101(row, src_h) * src_w;
+	int b[11];
+#pragma unroll
+	for (int i = 0; i < 11; ++i) b[i] = r[reflect101(col + i, src_w)];
+#pragma unroll
+	for (int k = 0; k < 4; ++k) h[k] = b[2 * k] + 4 * b[2 * k + 1] + 6 * b[2 * k + 2] + 4 * b[2 * k + 3] + b[2 * k + 4];
+}
+
+__global__ void __launch_bounds__(PD_BX * PD_BY) pyrdown_kernel(const uint8_t* __restrict__ frames, int W, int H,
 		uint8_t* __restrict__ arena, int64_t arena_stride, const DownJob* __restrict__ jobs) {
-	__shared__ uint8_t s_in[PD_IH][PD_IW + 1];
-	__shared__ uint16_t s_h[PD_IH][PD_TW];
 	const DownJob job = jobs[blockIdx.y];
 	const int tiles_x = (job.dst_w + PD_TW - 1) / PD_TW, tiles_y = (job.dst_h + PD_TH - 1) / PD_TH;
 	if ((int)blockIdx.x >= tiles_x * tiles_y) return;
 	const int tile_y = (int)blockIdx.x / tiles_x;
-	const int ty0 = tile_y * PD_TH, tx0 = ((int)blockIdx.x - tile_y * tiles_x) * PD_TW;
+	const int x0 = (((int)blockIdx.x - tile_y * tiles_x) * PD_BX + ((int)threadIdx.x & 31)) * 4;
+	const int y0 = (tile_y * PD_BY + ((int)threadIdx.x >> 5)) * 2;
+	if (x0 >= job.dst_w || y0 >= job.dst_h) return;
 	const uint8_t* __restrict__ src = job.src_offset < 0
 			? frames + (int64_t)blockIdx.z * W * H
 			: arena + (int64_t)blockIdx.z * arena_stride + job.src_offset;
 	uint8_t* __restrict__ dst = arena + (int64_t)blockIdx.z * arena_stride + job.dst_offset;
-	const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
-	const int ix0 = 2 * tx0 - 2, iy0 = 2 * ty0 - 2;
-	const bool interior = ix0 >= 0 && iy0 >= 0 && ix0 + PD_IW <= job.src_w && iy0 + PD_IH <= job.src_h;
+	const int col = 2 * x0 - 2, row = 2 * y0 - 2;
+	/* fast path: footprint strictly inside the image and not on its last row (aligned word reads may
+	 * run a few bytes past the footprint) */
+	const bool interior = col >= 0 && row >= 0 && col + 16 <= job.src_w && row + 7 < job.src_h;
+	int h[7][4];
 	if (interior) {
-		for (int r = ly; r < PD_IH; r += PD_TH) {
-			const uint8_t* row = src + (iy0 + r) * job.src_w + ix0;
-			s_in[r][lx] = row[lx];
-			s_in[r][lx + 32] = row[lx + 32];
-			if (lx < PD_IW - 64) s_in[r][lx + 64] = row[lx + 64];
-		}
+#pragma unroll
+		for (int r = 0; r < 7; ++r) pd_hrow_fast(src + (row + r) * job.src_w, col, h[r]);
 	} else {
-		for (int r = ly; r < PD_IH; r += PD_TH) {
-			const uint8_t* row = src + reflect101(iy0 + r, job.src_h) * job.src_w;
-			for (int c = lx; c < PD_IW; c += 32) s_in[r][c] = row[reflect101(ix0 + c, job.src_w)];
+#pragma unroll
+		for (int r = 0; r < 7; ++r) pd_hrow_border(src, job.src_w, job.src_h, row + r, col, h[r]);
+	}
+	const int nx = min(4, job.dst_w - x0);
+#pragma unroll
+	for (int oy = 0; oy < 2; ++oy) {
+		if (y0 + oy >= job.dst_h) break;
+		uint32_t packed = 0;
+#pragma unroll
+		for (int k = 0; k < 4; ++k) {
+			const int acc = h[2 * oy][k] + 4 * h[2 * oy + 1][k] + 6 * h[2 * oy + 2][k] + 4 * h[2 * oy + 3][k] + h[2 * oy + 4][k];
+			packed |= (uint32_t)((acc + 128) >> 8) << (8 * k);
 		}
-	}
-	__syncthreads();
-	for (int r = ly; r < PD_IH; r += PD_TH) {
-		const uint8_t* p = &s_in[r][2 * lx];
-		s_h[r][lx] = (uint16_t)(p[0] + 4 * p[1] + 6 * p[2] + 4 * p[3] + p[4]);
-	}
-	__syncthreads();
-	if (tx0 + lx < job.dst_w && ty0 + ly < job.dst_h) {
-		const int acc = s_h[2 * ly][lx] + 4 * s_h[2 * ly + 1][lx] + 6 * s_h[2 * ly + 2][lx] + 4 * s_h[2 * ly + 3][lx] + s_h[2 * ly + 4][lx];
-		dst[(ty0 + ly) * job.dst_w + tx0 + lx] = (uint8_t)((acc + 128) >> 8);
+		uint8_t* o = dst + (y0 + oy) * job.dst_w + x0;
+		if (nx == 4 && (job.dst_w & 3) == 0) {
+			*reinterpret_cast<uint32_t*>(o) = packed;
+		} else {
+			for (int k = 0; k < nx; ++k) o[k] = (uint8_t)(packed >> (8 * k));
+		}
 	}
 }
 
@@ -143,7 +181,7 @@ __global__ void __launch_bounds__(PD_TW * PD_TH) pyrdown_kernel(const uint8_t* _
  * launchers
  * ------------------------------------------------------------------------------------------- */
 void launch_resize(cudaStream_t st, const uint8_t* frames, int W, int H, int n_frames, uint8_t* arena,
-		int64_t arena_stride, const ResizeJob* jobs_dev, int n_jobs, int max_tiles, const int2* xy_tab) {
+		int64_t arena_stride, const ResizeJob* jobs_dev, int n_jobs, int max_tiles, const int4* xy_tab) {
 	if (n_jobs == 0 || n_frames == 0) return;
 	dim3 grid((unsigned)max_tiles, (unsigned)n_jobs, (unsigned)n_frames);
 	resize_kernel<<<grid, RS_QX * RS_TY, 0, st>>>(frames, W, H, arena, arena_stride, jobs_dev, xy_tab);
@@ -158,7 +196,7 @@ void launch_pyrdown(cudaStream_t st, const uint8_t* frames, int W, int H, int n_
 		int64_t arena_stride, const DownJob* jobs_dev, int n_jobs, int max_tiles) {
 	if (n_jobs == 0 || n_frames == 0) return;
 	dim3 grid((unsigned)max_tiles, (unsigned)n_jobs, (unsigned)n_frames);
-	pyrdown_kernel<<<grid, PD_TW * PD_TH, 0, st>>>(frames, W, H, arena, arena_stride, jobs_dev);
+	pyrdown_kernel<<<grid, PD_BX * PD_BY, 0, st>>>(frames, W, H, arena, arena_stride, jobs_dev);
 }
 
 int pyrdown_tiles(int dst_w, int dst_h) {

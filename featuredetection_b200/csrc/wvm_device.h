@@ -87,7 +87,7 @@ void launch_wvm_strips(cudaStream_t st, const DevWvm& m, const uint8_t* frames, 
 		int windows_per_frame, fdb_window_score* dense, Candidate* cand, int* cand_count, int cand_cap, const DeepQueue& q);
 
 void launch_resize(cudaStream_t st, const uint8_t* frames, int W, int H, int n_frames, uint8_t* arena,
-		int64_t arena_stride, const ResizeJob* jobs_dev, int n_jobs, int max_tiles, const int2* xy_tab);
+		int64_t arena_stride, const ResizeJob* jobs_dev, int n_jobs, int max_tiles, const int4* xy_tab);
 int resize_tiles(int dst_w, int dst_h);
 void launch_pyrdown(cudaStream_t st, const uint8_t* frames, int W, int H, int n_frames, uint8_t* arena,
 		int64_t arena_stride, const DownJob* jobs_dev, int n_jobs, int max_tiles);
