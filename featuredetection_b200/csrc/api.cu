@@ -197,6 +197,19 @@ int fdb_wvm_create(fdb_ctx* ctx, const fdb_wvm_desc* d, fdb_wvm** out) {
 	UP(d->area_val, slot, val, dp);
 	UP(masks.data(), masks.size(), masks, up);
 	UP(mask_off.data(), n, mask_off, ip);
+	{ /* weight rows padded to 16 bytes for the deep kernel's float4 loads */
+		std::vector<int> row4(n);
+		std::vector<float> w4;
+		size_t tri = 0;
+		for (int l = 0; l < n; ++l) {
+			row4[l] = (int)w4.size();
+			for (int p = 0; p <= l; ++p) w4.push_back(d->hk_weights[tri + p]);
+			while (w4.size() % 4) w4.push_back(0.f);
+			tri += (size_t)l + 1;
+		}
+		UP(w4.data(), w4.size(), hk_weights4, fp);
+		UP(row4.data(), n, hk_row4, ip);
+	}
 	dv.masks4 = nullptr;
 	if (max_nv <= 4) { /* padded copy for the strip / deep-warp kernels: [filter][word][4] */
 		std::vector<uint32_t> m4((size_t)n * nwords * 4, 0u);

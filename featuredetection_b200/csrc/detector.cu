@@ -21,6 +21,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <string>
@@ -446,6 +447,10 @@ int fdb_detector_prepare(fdb_detector* det, int32_t width, int32_t height, int32
 	det->max_batch = max_batch;
 	/* chunking: big batches flow through the slots in quarters so that copies, kernels and host work overlap */
 	det->chunk = max_batch >= 16 ? (max_batch + 3) / 4 : max_batch;
+	if (const char* e = std::getenv("FDB_CHUNK_FRAMES")) { /* tuning knob: frames per pipeline chunk */
+		const int v = std::atoi(e);
+		if (v > 0) det->chunk = std::min(v, (int)max_batch);
+	}
 	det->n_slots = std::min(PIPE_SLOTS, (max_batch + det->chunk - 1) / det->chunk);
 	const int64_t cap64 = (int64_t)det->desc.max_positives_per_frame * det->chunk;
 	det->cand_cap = (int)std::max<int64_t>(OPT_CAND, std::min<int64_t>(cap64, (int64_t)1 << 26));

@@ -49,6 +49,8 @@ struct DevWvm {
 	const uint32_t* masks;          /* rectangle coverage counts, 4 pixels per word: filter f at mask_off[f], [nwords][cntval-1] */
 	const int* mask_off;            /* [num_lin] */
 	const uint32_t* masks4;         /* same, padded to 4 values per word: [num_lin][nwords][4]; nullptr if a filter has > 4 */
+	const float* hk_weights4;       /* hkWeights rows padded to multiples of 4 floats (16-byte aligned rows) */
+	const int* hk_row4;             /* [num_lin] start of row l in hk_weights4 (floats) */
 };
 
 /* work item of wvm_strip_kernel: `cols` adjacent window columns x `nsub` runs of WVM_RUN window rows */

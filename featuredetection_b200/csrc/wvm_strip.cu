@@ -207,22 +207,59 @@ __global__ void __launch_bounds__(STRIP_T, (PW * PH <= 416 ? 3 : (PW * PH <= 600
 }
 
 /* ---------------------------------------------------------------------------------------------
- * deep kernel: one warp per queued window, 16 filters per round
+ * deep kernel: one warp per queued window, up to 32 filters per round (two 16-filter passes)
  * ------------------------------------------------------------------------------------------- */
 #define DEEP_WARPS 4
-#define DEEP_CH 16       /* filters per round */
+#define DEEP_CH 16       /* filters per reduce-scatter pass */
 #define DEEP_MAXT 8      /* patch words per lane: nwords <= 256 */
+
+/* partial rectangle sums of 16 consecutive filters starting at `first`, reduced over the warp:
+ * on return lane holds, for filter (lane >> 1) of the pass, values 2*(lane&1)+{0,1} in r0, r1 */
+__device__ __forceinline__ void deep_pass(const DevWvm& m, int first, int lane, int nt, const uint32_t* xw,
+		uint32_t* r0, uint32_t* r1) {
+	uint32_t a[DEEP_CH * 4];
+#pragma unroll
+	for (int i = 0; i < DEEP_CH * 4; ++i) a[i] = 0;
+#pragma unroll
+	for (int l = 0; l < DEEP_CH; ++l) {
+		/* filters past the end of the cascade are clamped (their sums are never used); patch words past
+		 * the end are zero, so no per-element guards are needed */
+		const int lvl = min(first + l, m.num_used - 1);
+		const uint4* __restrict__ mk4 = reinterpret_cast<const uint4*>(m.masks4) + (size_t)lvl * m.nwords;
+#pragma unroll
+		for (int t = 0; t < DEEP_MAXT; ++t) {
+			if (t < nt) { /* warp-uniform */
+				const uint4 k4 = __ldg(mk4 + min(lane + 32 * t, m.nwords - 1));
+				a[l * 4 + 0] = __dp4a(xw[t], k4.x, a[l * 4 + 0]); a[l * 4 + 1] = __dp4a(xw[t], k4.y, a[l * 4 + 1]);
+				a[l * 4 + 2] = __dp4a(xw[t], k4.z, a[l * 4 + 2]); a[l * 4 + 3] = __dp4a(xw[t], k4.w, a[l * 4 + 3]);
+			}
+		}
+	}
+	/* recursive-halving reduce-scatter */
+#pragma unroll
+	for (int half = DEEP_CH * 2, mask = 16; mask >= 1; half >>= 1, mask >>= 1) {
+		const bool upper = (lane & mask) != 0;
+#pragma unroll
+		for (int i = 0; i < half; ++i) {
+			const uint32_t send = upper ? a[i] : a[i + half];
+			const uint32_t keep = upper ? a[i + half] : a[i];
+			a[i] = keep + __shfl_xor_sync(0xffffffffu, send, mask);
+		}
+	}
+	*r0 = a[0]; *r1 = a[1];
+}
 
 __global__ void __launch_bounds__(DEEP_WARPS * 32) wvm_deep_warp_kernel(const DevWvm m, const DeepQueue q, int windows_per_frame,
 		fdb_window_score* __restrict__ dense, Candidate* __restrict__ cand, int* __restrict__ cand_count, int cand_cap) {
-	__shared__ float s_hk[DEEP_WARPS][FDB_MAX_FILTERS];
+	__shared__ __align__(16) float s_hk[DEEP_WARPS][FDB_MAX_FILTERS];
 	__shared__ float s_u[DEEP_WARPS][FDB_MAX_PER_LEVEL];
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	float* const hk = s_hk[warp];
 	float* const us = s_u[warp];
 	const int n = min(*q.count, q.cap);
 	const int nt = (m.nwords + 31) / 32;
-	const int own = lane >> 1;          /* filter (within the round) owned by the even lanes */
+	/* ownership inside a round: even lanes own filter lane>>1 of the first pass, odd lanes filter 16 + (lane>>1) of the second */
+	const int own = (lane & 1) * DEEP_CH + (lane >> 1);
 	for (;;) {
 		/* dynamic work distribution: windows differ by 50x in cost (first-round exits vs. full depth) */
 		int slot = 0;
@@ -242,74 +279,58 @@ __global__ void __launch_bounds__(DEEP_WARPS * 32) wvm_deep_warp_kernel(const De
 		__syncwarp();
 		int final_level = -1;
 		float final_fout = 0.f;
-		for (int base = WVM_KA; base < m.num_used && final_level < 0; base += DEEP_CH) {
-			const int cnt = min(DEEP_CH, m.num_used - base);
-			/* per-lane partial rectangle sums of the round's filters */
-			uint32_t a[DEEP_CH * 4];
-#pragma unroll
-			for (int i = 0; i < DEEP_CH * 4; ++i) a[i] = 0;
-#pragma unroll
-			for (int l = 0; l < DEEP_CH; ++l) {
-				/* filters past the end of the cascade are clamped (their sums are never used); patch words past
-				 * the end are zero, so no per-element guards are needed */
-				const int lvl = min(base + l, m.num_used - 1);
-				const uint4* __restrict__ mk4 = reinterpret_cast<const uint4*>(m.masks4) + (size_t)lvl * m.nwords;
-#pragma unroll
-				for (int t = 0; t < DEEP_MAXT; ++t) {
-					if (t < nt) { /* warp-uniform */
-						const uint4 k4 = __ldg(mk4 + min(lane + 32 * t, m.nwords - 1));
-						a[l * 4 + 0] = __dp4a(xw[t], k4.x, a[l * 4 + 0]); a[l * 4 + 1] = __dp4a(xw[t], k4.y, a[l * 4 + 1]);
-						a[l * 4 + 2] = __dp4a(xw[t], k4.z, a[l * 4 + 2]); a[l * 4 + 3] = __dp4a(xw[t], k4.w, a[l * 4 + 3]);
-					}
-				}
-			}
-			/* recursive-halving reduce-scatter: afterwards lane holds the totals of filter lane>>1, values 2*(lane&1)+{0,1} */
-#pragma unroll
-			for (int half = DEEP_CH * 2, mask = 16; mask >= 1; half >>= 1, mask >>= 1) {
-				const bool upper = (lane & mask) != 0;
-#pragma unroll
-				for (int i = 0; i < half; ++i) {
-					const uint32_t send = upper ? a[i] : a[i + half];
-					const uint32_t keep = upper ? a[i + half] : a[i];
-					a[i] = keep + __shfl_xor_sync(0xffffffffu, send, mask);
-				}
-			}
-			const uint32_t o0 = __shfl_xor_sync(0xffffffffu, a[0], 1), o1 = __shfl_xor_sync(0xffffffffu, a[1], 1);
-			/* kernel values on the owner lanes; filters sharing u_kernel_eval go in wavelet-level order */
+		int span = DEEP_CH; /* the first round is short: most queued windows are rejected within a few filters */
+		for (int base = WVM_KA; base < m.num_used && final_level < 0; base += span, span = 2 * DEEP_CH) {
+			const int cnt = min(span, m.num_used - base);
+			uint32_t e0, e1, f0 = 0, f1 = 0;
+			deep_pass(m, base, lane, nt, xw, &e0, &e1);
+			if (cnt > DEEP_CH) deep_pass(m, base + DEEP_CH, lane, nt, xw, &f0, &f1);
+			/* hand the other half of the owner's four sums over from the neighbour lane */
+			const uint32_t pe0 = __shfl_xor_sync(0xffffffffu, e0, 1), pe1 = __shfl_xor_sync(0xffffffffu, e1, 1);
+			const uint32_t pf0 = __shfl_xor_sync(0xffffffffu, f0, 1), pf1 = __shfl_xor_sync(0xffffffffu, f1, 1);
+			const bool odd = (lane & 1) != 0;
+			const uint32_t s0 = odd ? pf0 : e0, s1 = odd ? pf1 : e1, s2 = odd ? f0 : pe0, s3 = odd ? f1 : pe1;
 			const int level = base + own;
-			const bool owner = (lane & 1) == 0 && own < cnt;
+			const bool owner = own < cnt;
 			const int nv = owner ? __ldg(m.cntval + level) - 1 : 0;
-			const int rounds = (DEEP_CH + m.per_level - 1) / m.per_level;
+			/* kernel values; filters sharing u_kernel_eval go in wavelet-level order */
+			const int rounds = (cnt + m.per_level - 1) / m.per_level;
 			for (int r = 0; r < rounds; ++r) {
 				if (owner && own / m.per_level == r) {
 					float un = us[level % m.per_level];
-					const float kv = wvm_kernel_value4(m, level, a[0], a[1], o0, o1, nv, rec.total_f, rec.sum_xx, &un);
+					const float kv = wvm_kernel_value4(m, level, s0, s1, s2, s3, nv, rec.total_f, rec.sum_xx, &un);
 					us[level % m.per_level] = un;
 					hk[level] = kv;
 				}
 				__syncwarp();
 			}
-			/* float weighted sums (WvmClassifier.cpp:340-341): one sequential chain per owner lane */
+			/* float weighted sums (WvmClassifier.cpp:340-341): one sequential chain per owner lane; weights come
+			 * four at a time from the 16-byte aligned row copy, kernel values four at a time from shared memory */
 			float res = 0.f;
 			bool pass = true;
 			if (owner) {
-				const float* __restrict__ wgt = m.hk_weights + (size_t)level * (level + 1) / 2;
+				const float4* __restrict__ w4 = reinterpret_cast<const float4*>(m.hk_weights4 + __ldg(m.hk_row4 + level));
+				const float4* h4 = reinterpret_cast<const float4*>(hk);
 				res = -__ldg(m.lin_thresholds + level);
-				int p = 0;
-				for (; p + 8 <= level + 1; p += 8) { /* loads first, then the sequential adds */
-					float wv[8];
-#pragma unroll
-					for (int i = 0; i < 8; ++i) wv[i] = __fmul_rn(__ldg(wgt + p + i), hk[p + i]);
-#pragma unroll
-					for (int i = 0; i < 8; ++i) res = __fadd_rn(res, wv[i]);
+				const int groups = (level + 1) >> 2;
+				int g = 0;
+				for (; g + 2 <= groups; g += 2) {
+					const float4 wa = __ldg(w4 + g), wb = __ldg(w4 + g + 1);
+					const float4 ha = h4[g], hb = h4[g + 1];
+					res = __fadd_rn(res, __fmul_rn(wa.x, ha.x)); res = __fadd_rn(res, __fmul_rn(wa.y, ha.y));
+					res = __fadd_rn(res, __fmul_rn(wa.z, ha.z)); res = __fadd_rn(res, __fmul_rn(wa.w, ha.w));
+					res = __fadd_rn(res, __fmul_rn(wb.x, hb.x)); res = __fadd_rn(res, __fmul_rn(wb.y, hb.y));
+					res = __fadd_rn(res, __fmul_rn(wb.z, hb.z)); res = __fadd_rn(res, __fmul_rn(wb.w, hb.w));
 				}
-				for (; p <= level; ++p) res = __fadd_rn(res, __fmul_rn(__ldg(wgt + p), hk[p]));
+				for (int p = 4 * g; p <= level; ++p)
+					res = __fadd_rn(res, __fmul_rn(__ldg(m.hk_weights4 + __ldg(m.hk_row4 + level) + p), hk[p]));
 				pass = res >= __ldg(m.thresholds + level) && level + 1 < m.num_used;
 			}
 			const unsigned fails = __ballot_sync(0xffffffffu, owner && !pass);
-			if (fails) { /* the cascade stops at the first rejecting filter; later ones were speculative */
-				const int src = __ffs(fails) - 1;
-				final_level = base + (src >> 1);
+			if (fails) { /* the cascade stops at the first rejecting filter (level order: even lanes, then odd lanes) */
+				const unsigned fe = fails & 0x55555555u, fo = fails & 0xaaaaaaaau;
+				const int src = fe ? __ffs(fe) - 1 : __ffs(fo) - 1;
+				final_level = base + (src & 1) * DEEP_CH + (src >> 1);
 				final_fout = __shfl_sync(0xffffffffu, res, src);
 			}
 			__syncwarp();
