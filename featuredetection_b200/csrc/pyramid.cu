@@ -124,11 +124,11 @@ __device__ __forceinline__ void pd_hrow_fast(const uint8_t* __restrict__ rowp, i
 	h[3] = (int)__dp4a(w2, 0x00010406u, __dp4a(w1, 0x04010000u, 0u));
 }
 
-__device__ __forceinline__ void pd_hrow_border(const uint8_t* __restrict__ src, int src_w, int src_h, int row, int col, int* h) {
-	const uint8_t* __restrict__ r = src + reflect101(row, src_h) * src_w;
+/* border threads: the 11 reflected column indices are resolved once per thread (cx), the row once per call */
+__device__ __forceinline__ void pd_hrow_border(const uint8_t* __restrict__ rowp, const int* cx, int* h) {
 	int b[11];
 #pragma unroll
-	for (int i = 0; i < 11; ++i) b[i] = r[reflect101(col + i, src_w)];
+	for (int i = 0; i < 11; ++i) b[i] = rowp[cx[i]];
 #pragma unroll
 	for (int k = 0; k < 4; ++k) h[k] = b[2 * k] + 4 * b[2 * k + 1] + 6 * b[2 * k + 2] + 4 * b[2 * k + 3] + b[2 * k + 4];
 }
@@ -155,8 +155,11 @@ __global__ void __launch_bounds__(PD_BX * PD_BY) pyrdown_kernel(const uint8_t* _
 #pragma unroll
 		for (int r = 0; r < 7; ++r) pd_hrow_fast(src + (row + r) * job.src_w, col, h[r]);
 	} else {
+		int cx[11];
 #pragma unroll
-		for (int r = 0; r < 7; ++r) pd_hrow_border(src, job.src_w, job.src_h, row + r, col, h[r]);
+		for (int i = 0; i < 11; ++i) cx[i] = reflect101(col + i, job.src_w);
+#pragma unroll
+		for (int r = 0; r < 7; ++r) pd_hrow_border(src + reflect101(row + r, job.src_h) * job.src_w, cx, h[r]);
 	}
 	const int nx = min(4, job.dst_w - x0);
 #pragma unroll
