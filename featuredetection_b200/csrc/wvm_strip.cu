@@ -207,16 +207,15 @@ __global__ void __launch_bounds__(STRIP_T, (PW * PH <= 416 ? 3 : (PW * PH <= 600
 }
 
 /* ---------------------------------------------------------------------------------------------
- * deep kernel: one warp per queued window, up to 32 filters per round (two 16-filter passes)
+ * deep kernel: one warp per queued window, up to 32 filters per round (four 8-filter passes)
  * ------------------------------------------------------------------------------------------- */
 #define DEEP_WARPS 4
-#define DEEP_CH 16       /* filters per reduce-scatter pass */
+#define DEEP_CH 8        /* filters per reduce-scatter pass (32 accumulators per lane) */
 #define DEEP_MAXT 8      /* patch words per lane: nwords <= 256 */
 
-/* partial rectangle sums of 16 consecutive filters starting at `first`, reduced over the warp:
- * on return lane holds, for filter (lane >> 1) of the pass, values 2*(lane&1)+{0,1} in r0, r1 */
-__device__ __forceinline__ void deep_pass(const DevWvm& m, int first, int lane, int nt, const uint32_t* xw,
-		uint32_t* r0, uint32_t* r1) {
+/* partial rectangle sums of 8 consecutive filters starting at `first`, reduced over the warp:
+ * on return lane holds the total of filter (lane >> 2) of the pass, grey value (lane & 3) */
+__device__ __forceinline__ uint32_t deep_pass(const DevWvm& m, int first, int lane, int nt, const uint32_t* xw) {
 	uint32_t a[DEEP_CH * 4];
 #pragma unroll
 	for (int i = 0; i < DEEP_CH * 4; ++i) a[i] = 0;
@@ -235,7 +234,7 @@ __device__ __forceinline__ void deep_pass(const DevWvm& m, int first, int lane, 
 			}
 		}
 	}
-	/* recursive-halving reduce-scatter */
+	/* recursive-halving reduce-scatter: 32 values per lane -> 1 */
 #pragma unroll
 	for (int half = DEEP_CH * 2, mask = 16; mask >= 1; half >>= 1, mask >>= 1) {
 		const bool upper = (lane & mask) != 0;
@@ -246,10 +245,10 @@ __device__ __forceinline__ void deep_pass(const DevWvm& m, int first, int lane, 
 			a[i] = keep + __shfl_xor_sync(0xffffffffu, send, mask);
 		}
 	}
-	*r0 = a[0]; *r1 = a[1];
+	return a[0];
 }
 
-__global__ void __launch_bounds__(DEEP_WARPS * 32) wvm_deep_warp_kernel(const DevWvm m, const DeepQueue q, int windows_per_frame,
+__global__ void __launch_bounds__(DEEP_WARPS * 32, 6) wvm_deep_warp_kernel(const DevWvm m, const DeepQueue q, int windows_per_frame,
 		fdb_window_score* __restrict__ dense, Candidate* __restrict__ cand, int* __restrict__ cand_count, int cand_cap) {
 	__shared__ __align__(16) float s_hk[DEEP_WARPS][FDB_MAX_FILTERS];
 	__shared__ float s_u[DEEP_WARPS][FDB_MAX_PER_LEVEL];
@@ -258,8 +257,10 @@ __global__ void __launch_bounds__(DEEP_WARPS * 32) wvm_deep_warp_kernel(const De
 	float* const us = s_u[warp];
 	const int n = min(*q.count, q.cap);
 	const int nt = (m.nwords + 31) / 32;
-	/* ownership inside a round: even lanes own filter lane>>1 of the first pass, odd lanes filter 16 + (lane>>1) of the second */
-	const int own = (lane & 1) * DEEP_CH + (lane >> 1);
+	/* ownership inside a round: lane owns filter (lane >> 2) of pass (lane & 3) */
+	const int my_pass = lane & 3;
+	const int own = my_pass * DEEP_CH + (lane >> 2);
+	const int quad = lane & ~3;
 	for (;;) {
 		/* dynamic work distribution: windows differ by 50x in cost (first-round exits vs. full depth) */
 		int slot = 0;
@@ -279,17 +280,21 @@ __global__ void __launch_bounds__(DEEP_WARPS * 32) wvm_deep_warp_kernel(const De
 		__syncwarp();
 		int final_level = -1;
 		float final_fout = 0.f;
-		int span = DEEP_CH; /* the first round is short: most queued windows are rejected within a few filters */
-		for (int base = WVM_KA; base < m.num_used && final_level < 0; base += span, span = 2 * DEEP_CH) {
+		int span = 2 * DEEP_CH; /* the first round is short: most queued windows are rejected within a few filters */
+		for (int base = WVM_KA; base < m.num_used && final_level < 0; base += span, span = 4 * DEEP_CH) {
 			const int cnt = min(span, m.num_used - base);
-			uint32_t e0, e1, f0 = 0, f1 = 0;
-			deep_pass(m, base, lane, nt, xw, &e0, &e1);
-			if (cnt > DEEP_CH) deep_pass(m, base + DEEP_CH, lane, nt, xw, &f0, &f1);
-			/* hand the other half of the owner's four sums over from the neighbour lane */
-			const uint32_t pe0 = __shfl_xor_sync(0xffffffffu, e0, 1), pe1 = __shfl_xor_sync(0xffffffffu, e1, 1);
-			const uint32_t pf0 = __shfl_xor_sync(0xffffffffu, f0, 1), pf1 = __shfl_xor_sync(0xffffffffu, f1, 1);
-			const bool odd = (lane & 1) != 0;
-			const uint32_t s0 = odd ? pf0 : e0, s1 = odd ? pf1 : e1, s2 = odd ? f0 : pe0, s3 = odd ? f1 : pe1;
+			const int npass = (cnt + DEEP_CH - 1) / DEEP_CH;
+			/* the four sums of the filter this lane owns: s[k] = total of grey value k+1 */
+			uint32_t s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+#pragma unroll
+			for (int p = 0; p < 4; ++p) {
+				if (p < npass) { /* warp-uniform */
+					const uint32_t r = deep_pass(m, base + p * DEEP_CH, lane, nt, xw);
+					const uint32_t t0 = __shfl_sync(0xffffffffu, r, quad + 0), t1 = __shfl_sync(0xffffffffu, r, quad + 1);
+					const uint32_t t2 = __shfl_sync(0xffffffffu, r, quad + 2), t3 = __shfl_sync(0xffffffffu, r, quad + 3);
+					if (my_pass == p) { s0 = t0; s1 = t1; s2 = t2; s3 = t3; }
+				}
+			}
 			const int level = base + own;
 			const bool owner = own < cnt;
 			const int nv = owner ? __ldg(m.cntval + level) - 1 : 0;
@@ -309,7 +314,8 @@ __global__ void __launch_bounds__(DEEP_WARPS * 32) wvm_deep_warp_kernel(const De
 			float res = 0.f;
 			bool pass = true;
 			if (owner) {
-				const float4* __restrict__ w4 = reinterpret_cast<const float4*>(m.hk_weights4 + __ldg(m.hk_row4 + level));
+				const float* __restrict__ wrow = m.hk_weights4 + __ldg(m.hk_row4 + level);
+				const float4* __restrict__ w4 = reinterpret_cast<const float4*>(wrow);
 				const float4* h4 = reinterpret_cast<const float4*>(hk);
 				res = -__ldg(m.lin_thresholds + level);
 				const int groups = (level + 1) >> 2;
@@ -322,16 +328,15 @@ __global__ void __launch_bounds__(DEEP_WARPS * 32) wvm_deep_warp_kernel(const De
 					res = __fadd_rn(res, __fmul_rn(wb.x, hb.x)); res = __fadd_rn(res, __fmul_rn(wb.y, hb.y));
 					res = __fadd_rn(res, __fmul_rn(wb.z, hb.z)); res = __fadd_rn(res, __fmul_rn(wb.w, hb.w));
 				}
-				for (int p = 4 * g; p <= level; ++p)
-					res = __fadd_rn(res, __fmul_rn(__ldg(m.hk_weights4 + __ldg(m.hk_row4 + level) + p), hk[p]));
+				for (int p = 4 * g; p <= level; ++p) res = __fadd_rn(res, __fmul_rn(__ldg(wrow + p), hk[p]));
 				pass = res >= __ldg(m.thresholds + level) && level + 1 < m.num_used;
 			}
-			const unsigned fails = __ballot_sync(0xffffffffu, owner && !pass);
-			if (fails) { /* the cascade stops at the first rejecting filter (level order: even lanes, then odd lanes) */
-				const unsigned fe = fails & 0x55555555u, fo = fails & 0xaaaaaaaau;
-				const int src = fe ? __ffs(fe) - 1 : __ffs(fo) - 1;
-				final_level = base + (src & 1) * DEEP_CH + (src >> 1);
-				final_fout = __shfl_sync(0xffffffffu, res, src);
+			/* the cascade stops at the first rejecting filter; later ones were speculative */
+			const unsigned first_fail = __reduce_min_sync(0xffffffffu, (owner && !pass) ? (unsigned)level : 0xffffffffu);
+			if (first_fail != 0xffffffffu) {
+				final_level = (int)first_fail;
+				const unsigned who = __ballot_sync(0xffffffffu, owner && level == (int)first_fail);
+				final_fout = __shfl_sync(0xffffffffu, res, __ffs(who) - 1);
 			}
 			__syncwarp();
 		}
@@ -379,7 +384,7 @@ void launch_wvm_strips(cudaStream_t st, const DevWvm& m, const uint8_t* frames, 
 		layers, strips, n_strips, windows_per_frame, dense, cand, cand_count, cand_cap, q); }
 	FDB_STRIP_CASE(20, 20) else FDB_STRIP_CASE(24, 24) else FDB_STRIP_CASE(32, 16) else FDB_STRIP_CASE(32, 24) else FDB_STRIP_CASE(16, 24)
 #undef FDB_STRIP_CASE
-	const int blocks = std::min((q.cap + DEEP_WARPS - 1) / DEEP_WARPS, 148 * 4);
+	const int blocks = std::min((q.cap + DEEP_WARPS - 1) / DEEP_WARPS, 148 * 6);
 	wvm_deep_warp_kernel<<<blocks, DEEP_WARPS * 32, 0, st>>>(m, q, windows_per_frame, dense, cand, cand_count, cand_cap);
 }
 
