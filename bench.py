@@ -168,12 +168,18 @@ def run_reference(args, rank, world):
 
 
 def workload_config(args, world, extra=None):
-    cfg = {"workload": "BASELINE configs[1]: %d-frame batch per GPU, 640x480 1-channel, FaceFrontal WVM->SVM five-stage "
-                       "cascade (hq64 u8 features for both stages, as ffpDetectApp wires it), full pyramid, step 1x1" % args.frames,
-           "frames_per_gpu": args.frames, "global_frames": args.frames * world, "windows_per_frame": 16185,
+    if args.workload == "facefrontal":
+        wl = ("BASELINE configs[1]: %d-frame batch per GPU, 640x480 1-channel, FaceFrontal WVM->SVM five-stage cascade "
+              "(hq64 u8 features for both stages, as ffpDetectApp wires it), full pyramid, step 1x1" % args.frames)
+        wpf, pyr = 16185, 1931000
+    else:
+        wl = ("BASELINE configs[3] shape: %d-frame batch per GPU, 640x480 1-channel, all 15 ffpDetectApp landmark detectors per frame "
+              "(WVM->SVM cascades, hq64 u8 features), one pyramid per detector as the reference builds them" % args.frames)
+        wpf, pyr = 4302040, 15 * 500000
+    cfg = {"workload": wl, "frames_per_gpu": args.frames, "global_frames": args.frames * world, "windows_per_frame": wpf,
            "threshold_profile": args.profile, "parallelism": "frame-sharded dp%d" % world,
-           "l2": "per-step working set (frames + materialised pyramid = %.0f MB) exceeds the 126 MB L2; a 256 MB "
-                 "scratch write also flushes L2 between timed steps" % ((W * H + 1931000) * args.frames / 1e6)}
+           "l2": "per-step working set (frames + materialised pyramids + dense records = %.0f MB) exceeds the 126 MB L2; a 256 MB "
+                 "scratch write also flushes L2 between timed steps" % ((W * H + pyr + 8 * wpf) * args.frames / 1e6)}
     if extra:
         cfg["sample"] = extra
     return cfg
@@ -185,13 +191,17 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--frames", type=int, default=256, help="frames per GPU per step")
+    ap.add_argument("--frames", type=int, default=None, help="frames per GPU per step (default 256; 16 for landmarks15)")
+    ap.add_argument("--workload", default="facefrontal", choices=["facefrontal", "landmarks15"],
+                    help="facefrontal = BASELINE configs[1] (headline); landmarks15 = all 15 ffpDetectApp landmark detectors per frame (configs[3] shape, hq64 features)")
     ap.add_argument("--profile", default="realistic", choices=["realistic", "no-exit"])
     ap.add_argument("--cpu-frames-per-core", type=int, default=4, help="cpu_baseline sample size per host core")
     ap.add_argument("--ref-frames-per-core", type=int, default=2, help="--impl reference: frames per core per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.frames is None:
+        args.frames = 256 if args.workload == "facefrontal" else 16
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -212,24 +222,30 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
 
-    det_kw, wvm, svm = syn.landmark_models(CFG, args.profile)
-    if args.profile == "no-exit":
-        det_kw = dict(det_kw, max_positives_per_frame=17000)
+    names = [CFG] if args.workload == "facefrontal" else [c[0] for c in syn.LANDMARK_CONFIGS]
     ctx = Context(local_rank)
-    casc = SlidingWindowCascade(ctx, det_kw, wvm, svm)
     n = args.frames
-    casc.prepare(W, H, n)
-    nwin = casc.windows_per_frame
+    cascs = []
+    for nm in names:
+        det_kw, wvm, svm = syn.landmark_models(nm, args.profile)
+        if args.profile == "no-exit":
+            det_kw = dict(det_kw, max_positives_per_frame=400000)
+        c = SlidingWindowCascade(ctx, det_kw, wvm, svm)
+        c.prepare(W, H, n)
+        cascs.append(c)
+    nwin = sum(c.windows_per_frame for c in cascs)          # windows per frame over all detectors
+    max_nwin = max(c.windows_per_frame for c in cascs)
     stage = capi.FDB_STAGE_NMS if args.profile == "realistic" else capi.FDB_STAGE_WVM
+    det_cap = 64 * n if args.profile == "realistic" else max_nwin * n
 
     # this rank's shard of the global batch (weak scaling: n frames per rank), 8 distinct frames tiled
     lo, hi = sharding.shard_range(n * world, rank, world)
-    base = syn.synthetic_frames(lo % 97, 8)
-    host_frames = torch.from_numpy(np.concatenate([base] * ((n + 7) // 8))[:n]).pin_memory()
+    base = syn.synthetic_frames(lo % 97, min(8, n))
+    host_frames = torch.from_numpy(np.concatenate([base] * ((n + len(base) - 1) // len(base)))[:n]).pin_memory()
     dev_frames = host_frames.to(device)
-    dev_dense = torch.empty((n, nwin, 2), dtype=torch.int32, device=device)
+    dev_dense = torch.empty((n, max_nwin, 2), dtype=torch.int32, device=device)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
-    gather_cap = max(256, 8 * n)  # fixed-size gather block per rank (2.2 detections per frame on this workload)
+    gather_cap = max(256, 8 * n) * len(cascs)  # fixed-size gather block per rank
     torch.cuda.synchronize()
 
     def barrier():
@@ -243,13 +259,15 @@ def main():
         torch.cuda.synchronize()
 
     def step_resident():
-        dets = casc.detect_device(dev_frames.data_ptr(), n, stage=stage, dense_ptr=dev_dense.data_ptr(), det_cap=max(64 * n, 20000 * n if args.profile == "no-exit" else 0))
+        parts = [c.detect_device(dev_frames.data_ptr(), n, stage=stage, dense_ptr=dev_dense.data_ptr(), det_cap=det_cap) for c in cascs]
+        dets = np.concatenate(parts)
         if world > 1:
             sharding.gather_detections(dets[:gather_cap], lo, gather_cap, dist, device)
         return dets
 
     def step_e2e():
-        dets = casc.detect(host_frames.numpy(), stage=stage, det_cap=max(64 * n, 20000 * n if args.profile == "no-exit" else 0))
+        parts = [c.detect(host_frames.numpy(), stage=stage, det_cap=det_cap) for c in cascs]
+        dets = np.concatenate(parts)
         if world > 1:
             sharding.gather_detections(dets[:gather_cap], lo, gather_cap, dist, device)
         return dets
@@ -279,7 +297,7 @@ def main():
     prof = []
     for _ in range(max(args.steps, 5)):
         flush_l2()
-        prof.append(casc.profile_device(dev_frames.data_ptr(), n))
+        prof.append(np.sum([c.profile_device(dev_frames.data_ptr(), n) for c in cascs], axis=0))
     prof = np.array(prof)
     ms_resize, ms_down, ms_wvm, ms_stage1 = prof.mean(axis=0)
 
@@ -305,7 +323,7 @@ def main():
         value = windows_step * args.steps / (total_ms * 1e-3)
         e2e_value = windows_step * args.steps / (e2e_total * 1e-3)
         peak, peak_src = hbm_peak()
-        algo_bytes = (W * H + WINDOW_BYTES * nwin) * n       # per launch of the window kernel (one GPU)
+        algo_bytes = (W * H + WINDOW_BYTES * nwin) * n       # per step of the window kernels (one GPU): frame read once + dense records
         achieved = algo_bytes / (ms_wvm * 1e-3) / 1e9
         cpu = None
         if not args.no_cpu_baseline:
@@ -323,7 +341,7 @@ def main():
             "config": workload_config(args, world),
             "frames_per_s": value / nwin,
             "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": "patches/s", "h2d_bytes_per_step": int(W * H * n),
+            "e2e": {"value": e2e_value, "unit": "patches/s", "h2d_bytes_per_step": int(W * H * n * len(cascs)),
                     "d2h_bytes_per_step": int(len(dets_e2e) * DETECTION_DTYPE.itemsize + 4),
                     "ms_per_step": e2e_total / args.steps, "frames_per_s": e2e_value / nwin},
             "gpu_launches": int(launches),

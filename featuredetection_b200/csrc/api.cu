@@ -197,6 +197,28 @@ int fdb_wvm_create(fdb_ctx* ctx, const fdb_wvm_desc* d, fdb_wvm** out) {
 	UP(d->area_val, slot, val, dp);
 	UP(masks.data(), masks.size(), masks, up);
 	UP(mask_off.data(), n, mask_off, ip);
+	{ /* rectangle table for the integral-image evaluation of the deep kernel */
+		std::vector<uint2> rc;
+		std::vector<int> roff(n + 1, 0);
+		int sl = 0; size_t ro = 0;
+		for (int f = 0; f < n; ++f) {
+			roff[f] = (int)rc.size();
+			for (int v = 1; v < d->area_cntval[f]; ++v)
+				for (int r = 0; r < d->area_cntrec[sl + v]; ++r) {
+					const fdb_rect4& q = d->area_rec[ro++];
+					uint2 e;
+					e.x = (uint32_t)q.x1 | ((uint32_t)q.y1 << 8) | ((uint32_t)q.x2 << 16) | ((uint32_t)q.y2 << 24);
+					e.y = (uint32_t)(v - 1);
+					rc.push_back(e);
+				}
+			sl += d->area_cntval[f];
+		}
+		roff[n] = (int)rc.size();
+		uint2* rp; 
+		s = upload(rc.data(), rc.size(), &rp, m->owned); if (s) { free_all(m->owned); delete m; return s; }
+		dv.rects = rp;
+		UP(roff.data(), n + 1, rect_off, ip);
+	}
 	{ /* weight rows padded to 16 bytes for the deep kernel's float4 loads */
 		std::vector<int> row4(n);
 		std::vector<float> w4;

@@ -51,6 +51,8 @@ struct DevWvm {
 	const uint32_t* masks4;         /* same, padded to 4 values per word: [num_lin][nwords][4]; nullptr if a filter has > 4 */
 	const float* hk_weights4;       /* hkWeights rows padded to multiples of 4 floats (16-byte aligned rows) */
 	const int* hk_row4;             /* [num_lin] start of row l in hk_weights4 (floats) */
+	const uint2* rects;             /* rectangles of all filters: {x1 | y1 << 8 | x2 << 16 | y2 << 24, grey value index v - 1} */
+	const int* rect_off;            /* [num_lin + 1] first rectangle of filter l */
 };
 
 /* work item of wvm_strip_kernel: `cols` adjacent window columns x `nsub` runs of WVM_RUN window rows */

@@ -207,60 +207,25 @@ __global__ void __launch_bounds__(STRIP_T, (PW * PH <= 416 ? 3 : (PW * PH <= 600
 }
 
 /* ---------------------------------------------------------------------------------------------
- * deep kernel: one warp per queued window, up to 32 filters per round (four 8-filter passes)
+ * deep kernel: one warp per queued window, 32 filters per round, rectangle sums from an integral
+ * image of the equalised patch (the reference's own evaluation scheme, WvmClassifier.cpp:277-306;
+ * every entry is an exact integer < 2^24, so int32 arithmetic reproduces the float sums bit for bit)
  * ------------------------------------------------------------------------------------------- */
 #define DEEP_WARPS 4
-#define DEEP_CH 8        /* filters per reduce-scatter pass (32 accumulators per lane) */
-#define DEEP_MAXT 8      /* patch words per lane: nwords <= 256 */
+#define DEEP_IIMG 1024   /* (w + 1) * (h + 1) <= 1024 ints per warp (32x24 -> 825) */
 
-/* partial rectangle sums of 8 consecutive filters starting at `first`, reduced over the warp:
- * on return lane holds the total of filter (lane >> 2) of the pass, grey value (lane & 3) */
-__device__ __forceinline__ uint32_t deep_pass(const DevWvm& m, int first, int lane, int nt, const uint32_t* xw) {
-	uint32_t a[DEEP_CH * 4];
-#pragma unroll
-	for (int i = 0; i < DEEP_CH * 4; ++i) a[i] = 0;
-#pragma unroll
-	for (int l = 0; l < DEEP_CH; ++l) {
-		/* filters past the end of the cascade are clamped (their sums are never used); patch words past
-		 * the end are zero, so no per-element guards are needed */
-		const int lvl = min(first + l, m.num_used - 1);
-		const uint4* __restrict__ mk4 = reinterpret_cast<const uint4*>(m.masks4) + (size_t)lvl * m.nwords;
-#pragma unroll
-		for (int t = 0; t < DEEP_MAXT; ++t) {
-			if (t < nt) { /* warp-uniform */
-				const uint4 k4 = __ldg(mk4 + min(lane + 32 * t, m.nwords - 1));
-				a[l * 4 + 0] = __dp4a(xw[t], k4.x, a[l * 4 + 0]); a[l * 4 + 1] = __dp4a(xw[t], k4.y, a[l * 4 + 1]);
-				a[l * 4 + 2] = __dp4a(xw[t], k4.z, a[l * 4 + 2]); a[l * 4 + 3] = __dp4a(xw[t], k4.w, a[l * 4 + 3]);
-			}
-		}
-	}
-	/* recursive-halving reduce-scatter: 32 values per lane -> 1 */
-#pragma unroll
-	for (int half = DEEP_CH * 2, mask = 16; mask >= 1; half >>= 1, mask >>= 1) {
-		const bool upper = (lane & mask) != 0;
-#pragma unroll
-		for (int i = 0; i < half; ++i) {
-			const uint32_t send = upper ? a[i] : a[i + half];
-			const uint32_t keep = upper ? a[i + half] : a[i];
-			a[i] = keep + __shfl_xor_sync(0xffffffffu, send, mask);
-		}
-	}
-	return a[0];
-}
-
-__global__ void __launch_bounds__(DEEP_WARPS * 32, 6) wvm_deep_warp_kernel(const DevWvm m, const DeepQueue q, int windows_per_frame,
+__global__ void __launch_bounds__(DEEP_WARPS * 32) wvm_deep_warp_kernel(const DevWvm m, const DeepQueue q, int windows_per_frame,
 		fdb_window_score* __restrict__ dense, Candidate* __restrict__ cand, int* __restrict__ cand_count, int cand_cap) {
 	__shared__ __align__(16) float s_hk[DEEP_WARPS][FDB_MAX_FILTERS];
 	__shared__ float s_u[DEEP_WARPS][FDB_MAX_PER_LEVEL];
+	__shared__ int s_ii[DEEP_WARPS][DEEP_IIMG];
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	float* const hk = s_hk[warp];
 	float* const us = s_u[warp];
+	int* const ii = s_ii[warp];
 	const int n = min(*q.count, q.cap);
-	const int nt = (m.nwords + 31) / 32;
-	/* ownership inside a round: lane owns filter (lane >> 2) of pass (lane & 3) */
-	const int my_pass = lane & 3;
-	const int own = my_pass * DEEP_CH + (lane >> 2);
-	const int quad = lane & ~3;
+	const int pw = m.fsx, ph = m.fsy, pitch = pw + 1;
+	const int wpr = (pw + 3) >> 2; /* patch words per row (pw is a multiple of 4 on this path) */
 	for (;;) {
 		/* dynamic work distribution: windows differ by 50x in cost (first-round exits vs. full depth) */
 		int slot = 0;
@@ -268,11 +233,22 @@ __global__ void __launch_bounds__(DEEP_WARPS * 32, 6) wvm_deep_warp_kernel(const
 		slot = __shfl_sync(0xffffffffu, slot, 0);
 		if (slot >= n) break;
 		const DeepRec rec = q.rec[slot];
-		uint32_t xw[DEEP_MAXT];
+		/* --- integral image with a zero first row and column: ii[(y+1)*pitch + x+1] = sum of x[0..y][0..x] --- */
+		for (int i = lane; i < pitch; i += 32) ii[i] = 0;
+		int colsum = 0; /* lane = column */
+		for (int r = 0; r < ph; ++r) {
+			uint32_t v = 0;
+			if (lane < pw) v = (__ldg(q.patch + (size_t)(r * wpr + (lane >> 2)) * q.cap + slot) >> ((lane & 3) * 8)) & 255u;
+			/* inclusive prefix over the row */
 #pragma unroll
-		for (int t = 0; t < DEEP_MAXT; ++t) {
-			const int j = lane + 32 * t;
-			xw[t] = (t < nt && j < m.nwords) ? __ldg(q.patch + (size_t)j * q.cap + slot) : 0u;
+			for (int d = 1; d < 32; d <<= 1) {
+				const uint32_t t = __shfl_up_sync(0xffffffffu, v, d);
+				if (lane >= d) v += t;
+			}
+			/* column-wise accumulation of the row prefixes: ii[r+1][c+1] = ii[r][c+1] + prefix(r, c) */
+			colsum += (int)v;
+			if (lane < pw) ii[(r + 1) * pitch + lane + 1] = colsum;
+			if (lane == 0) ii[(r + 1) * pitch] = 0;
 		}
 		for (int i = lane; i < m.per_level; i += 32) us[i] = 0.f;
 		__syncwarp();
@@ -280,28 +256,28 @@ __global__ void __launch_bounds__(DEEP_WARPS * 32, 6) wvm_deep_warp_kernel(const
 		__syncwarp();
 		int final_level = -1;
 		float final_fout = 0.f;
-		int span = 2 * DEEP_CH; /* the first round is short: most queued windows are rejected within a few filters */
-		for (int base = WVM_KA; base < m.num_used && final_level < 0; base += span, span = 4 * DEEP_CH) {
-			const int cnt = min(span, m.num_used - base);
-			const int npass = (cnt + DEEP_CH - 1) / DEEP_CH;
-			/* the four sums of the filter this lane owns: s[k] = total of grey value k+1 */
+		for (int base = WVM_KA; base < m.num_used && final_level < 0; base += 32) {
+			const int cnt = min(32, m.num_used - base);
+			const int level = base + lane;
+			const bool owner = lane < cnt;
+			/* rectangle sums of the filter this lane owns */
 			uint32_t s0 = 0, s1 = 0, s2 = 0, s3 = 0;
-#pragma unroll
-			for (int p = 0; p < 4; ++p) {
-				if (p < npass) { /* warp-uniform */
-					const uint32_t r = deep_pass(m, base + p * DEEP_CH, lane, nt, xw);
-					const uint32_t t0 = __shfl_sync(0xffffffffu, r, quad + 0), t1 = __shfl_sync(0xffffffffu, r, quad + 1);
-					const uint32_t t2 = __shfl_sync(0xffffffffu, r, quad + 2), t3 = __shfl_sync(0xffffffffu, r, quad + 3);
-					if (my_pass == p) { s0 = t0; s1 = t1; s2 = t2; s3 = t3; }
+			int nv = 0;
+			if (owner) {
+				nv = __ldg(m.cntval + level) - 1;
+				const int r0 = __ldg(m.rect_off + level), r1 = __ldg(m.rect_off + level + 1);
+				for (int r = r0; r < r1; ++r) {
+					const uint2 rc = __ldg(m.rects + r); /* {x1 | y1 << 8 | x2 << 16 | y2 << 24, grey value index} */
+					const int x1 = rc.x & 255, y1 = (rc.x >> 8) & 255, x2 = (rc.x >> 16) & 255, y2 = rc.x >> 24;
+					const int sum = ii[(y2 + 1) * pitch + x2 + 1] - ii[y1 * pitch + x2 + 1] - ii[(y2 + 1) * pitch + x1] + ii[y1 * pitch + x1];
+					s0 += rc.y == 0 ? (uint32_t)sum : 0u; s1 += rc.y == 1 ? (uint32_t)sum : 0u;
+					s2 += rc.y == 2 ? (uint32_t)sum : 0u; s3 += rc.y == 3 ? (uint32_t)sum : 0u;
 				}
 			}
-			const int level = base + own;
-			const bool owner = own < cnt;
-			const int nv = owner ? __ldg(m.cntval + level) - 1 : 0;
 			/* kernel values; filters sharing u_kernel_eval go in wavelet-level order */
 			const int rounds = (cnt + m.per_level - 1) / m.per_level;
 			for (int r = 0; r < rounds; ++r) {
-				if (owner && own / m.per_level == r) {
+				if (owner && lane / m.per_level == r) {
 					float un = us[level % m.per_level];
 					const float kv = wvm_kernel_value4(m, level, s0, s1, s2, s3, nv, rec.total_f, rec.sum_xx, &un);
 					us[level % m.per_level] = un;
@@ -332,11 +308,11 @@ __global__ void __launch_bounds__(DEEP_WARPS * 32, 6) wvm_deep_warp_kernel(const
 				pass = res >= __ldg(m.thresholds + level) && level + 1 < m.num_used;
 			}
 			/* the cascade stops at the first rejecting filter; later ones were speculative */
-			const unsigned first_fail = __reduce_min_sync(0xffffffffu, (owner && !pass) ? (unsigned)level : 0xffffffffu);
-			if (first_fail != 0xffffffffu) {
-				final_level = (int)first_fail;
-				const unsigned who = __ballot_sync(0xffffffffu, owner && level == (int)first_fail);
-				final_fout = __shfl_sync(0xffffffffu, res, __ffs(who) - 1);
+			const unsigned fails = __ballot_sync(0xffffffffu, owner && !pass);
+			if (fails) {
+				const int src = __ffs(fails) - 1;
+				final_level = base + src;
+				final_fout = __shfl_sync(0xffffffffu, res, src);
 			}
 			__syncwarp();
 		}
@@ -384,7 +360,7 @@ void launch_wvm_strips(cudaStream_t st, const DevWvm& m, const uint8_t* frames, 
 		layers, strips, n_strips, windows_per_frame, dense, cand, cand_count, cand_cap, q); }
 	FDB_STRIP_CASE(20, 20) else FDB_STRIP_CASE(24, 24) else FDB_STRIP_CASE(32, 16) else FDB_STRIP_CASE(32, 24) else FDB_STRIP_CASE(16, 24)
 #undef FDB_STRIP_CASE
-	const int blocks = std::min((q.cap + DEEP_WARPS - 1) / DEEP_WARPS, 148 * 6);
+	const int blocks = std::min((q.cap + DEEP_WARPS - 1) / DEEP_WARPS, 148 * 8);
 	wvm_deep_warp_kernel<<<blocks, DEEP_WARPS * 32, 0, st>>>(m, q, windows_per_frame, dense, cand, cand_count, cand_cap);
 }
 

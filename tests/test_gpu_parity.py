@@ -241,3 +241,21 @@ def test_fifteen_landmark_geometries(ctx):
         assert np.array_equal(dense[0]["level"], ref["dense"]["level"]), nm
         assert np.max(np.abs(dense[0]["fout"] - ref["dense"]["fout"])) <= TOL, nm
         assert list(dets["window"]) == list(ref["detections"]["window"]), nm
+
+
+@pytest.mark.parametrize("name", ["LeftEyeCenter", "NoseTip", "LeftEarCenter", "CenterLipUpperOuter", "FaceLeftProfile"])
+def test_landmark_models_realistic(ctx, name):
+    """Other ffpDetectApp landmark detectors (patch sizes 32x16, 32x24, 16x24, 24x24, 20x20) with their
+    calibrated thresholds, whole five-stage cascade on one frame against the oracle."""
+    fo = _oracle()
+    det_kw, wvm, svm = syn.landmark_models(name)
+    frame = syn.synthetic_frame(51)
+    casc = SlidingWindowCascade(ctx, det_kw, wvm, svm)
+    casc.prepare(640, 480, 1)
+    dets, dense = casc.detect(frame[None], stage=capi.FDB_STAGE_NMS, want_dense=True)
+    ref = fo.detect_frame(det_kw, fo.Wvm(wvm), fo.Svm(svm), frame, stage=capi.FDB_STAGE_NMS)
+    assert ref["windows"] == dense.shape[1]
+    assert np.array_equal(dense[0]["level"], ref["dense"]["level"])
+    assert np.max(np.abs(dense[0]["fout"] - ref["dense"]["fout"])) <= TOL
+    assert list(dets["window"]) == list(ref["detections"]["window"])
+    assert np.allclose(dets["svm_distance"], ref["detections"]["svm_distance"], rtol=0, atol=TOL)
