@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libfdb200.so")
+LIB_PATH = os.environ.get("FDB_LIB") or os.path.join(_HERE, "csrc", "libfdb200.so")  # FDB_LIB: tuning builds only
 
 FDB_OK = 0
 FDB_STAGE_WVM, FDB_STAGE_OE, FDB_STAGE_SVM, FDB_STAGE_NMS = 1, 2, 3, 4

@@ -13,8 +13,8 @@
  *   cumsum -> 64-entry LUT (+ sum(x), sum(x^2) from the histogram), LUT application into PW*PH/4
  *   REGISTERS (4 pixels per register), then up to WVM_KA filters as dp4a dot products against the
  *   rectangle-coverage masks.  Survivors of all WVM_KA filters go to the deep queue.
- *   Shared memory per lane: 32 words histogram + 64 words LUT, column layout [word][lane] so that
- *   every access is bank-conflict free.
+ *   Shared memory per lane: 64 u16 histogram counts + 64 u16 LUT entries, column layout [bin][lane]
+ *   (two lanes per 32-bit word) so that every access is bank-conflict free.
  *
  * wvm_deep_warp_kernel
  *   One WARP per queued window.  The 32 lanes split the patch words; 16 filters are evaluated per
@@ -35,17 +35,20 @@
 namespace fdb {
 
 #define STRIP_T 128          /* threads per CTA (4 warps, one strip each) */
+#ifndef STRIP_MIN_CTAS
+#define STRIP_MIN_CTAS 3
+#endif
 #define STRIP_TILE_PITCH 64  /* bytes per tile row: 32 columns + PW - 1 <= 63 */
 
 template <int PW, int PH>
 struct StripCfg {
 	static constexpr int NW = PW * PH / 4;
 	static constexpr int TILE_ROWS = WVM_MAXSUB * WVM_RUN + PH - 1;
-	static constexpr size_t SMEM = (size_t)(32 + 64) * STRIP_T * 4 + (size_t)4 * TILE_ROWS * STRIP_TILE_PITCH;
+	static constexpr size_t SMEM = (size_t)(64 + 64) * STRIP_T * 2 + (size_t)4 * TILE_ROWS * STRIP_TILE_PITCH;
 };
 
 template <int PW, int PH>
-__global__ void __launch_bounds__(STRIP_T, (PW * PH <= 416 ? 3 : (PW * PH <= 600 ? 2 : 1))) wvm_strip_kernel(const DevWvm m,
+__global__ void __launch_bounds__(STRIP_T, (PW * PH <= 416 ? STRIP_MIN_CTAS : (PW * PH <= 600 ? 2 : 1))) wvm_strip_kernel(const DevWvm m,
 		const uint8_t* __restrict__ frames, int W, int H,
 		const uint8_t* __restrict__ arena, int64_t arena_stride,
 		const DevLayer* __restrict__ layers, const Strip* __restrict__ strips, int n_strips, int windows_per_frame,
@@ -57,9 +60,9 @@ __global__ void __launch_bounds__(STRIP_T, (PW * PH <= 416 ? 3 : (PW * PH <= 600
 	constexpr int T = STRIP_T;
 	extern __shared__ uint32_t smem[];
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-	uint32_t* const s_hist = smem + tid;             /* [32][T] -> element k at s_hist[k*T] */
-	uint32_t* const s_lut = smem + 32 * T + tid;     /* [64][T] */
-	uint8_t* const s_tile = reinterpret_cast<uint8_t*>(smem + 96 * T) + warp * StripCfg<PW, PH>::TILE_ROWS * STRIP_TILE_PITCH;
+	uint16_t* const s_hist = reinterpret_cast<uint16_t*>(smem) + tid;          /* [64][T] u16 counts -> bin b at s_hist[b*T] */
+	uint16_t* const s_lut = reinterpret_cast<uint16_t*>(smem) + 64 * T + tid;  /* [64][T] u16 equalised values */
+	uint8_t* const s_tile = reinterpret_cast<uint8_t*>(smem) + 128 * T * 2 + warp * StripCfg<PW, PH>::TILE_ROWS * STRIP_TILE_PITCH;
 
 	const int strip_id = blockIdx.x * 4 + warp;
 	if (strip_id >= n_strips) return; /* whole warp leaves; only __syncwarp is used below */
@@ -84,15 +87,12 @@ __global__ void __launch_bounds__(STRIP_T, (PW * PH <= 416 ? 3 : (PW * PH <= 600
 	const uint8_t* const tcol = s_tile + (sub * st.run) * STRIP_TILE_PITCH + col;
 	const float stretch = __fdiv_rn(255.0f, (float)(PW * PH)); /* HistEq64Filter.cpp:34 */
 
-	/* histogram of the first window of the run, two 16-bit counts per word */
+	/* histogram of the first window of the run */
 #pragma unroll
-	for (int k = 0; k < 32; ++k) s_hist[k * T] = 0;
+	for (int k = 0; k < 64; ++k) s_hist[k * T] = 0;
 	for (int r = 0; r < PH; ++r) {
 #pragma unroll
-		for (int c = 0; c < PW; ++c) {
-			const uint32_t b = tcol[r * STRIP_TILE_PITCH + c];
-			s_hist[(b >> 1) * T] += 1u << ((b & 1) * 16);
-		}
+		for (int c = 0; c < PW; ++c) s_hist[tcol[r * STRIP_TILE_PITCH + c] * T] += 1;
 	}
 
 	for (int w = 0; w < nrows; ++w) {
@@ -102,27 +102,22 @@ __global__ void __launch_bounds__(STRIP_T, (PW * PH <= 416 ? 3 : (PW * PH <= 600
 			const uint8_t* const r_in = tw + (PH - 1) * STRIP_TILE_PITCH;
 #pragma unroll
 			for (int c = 0; c < PW; ++c) {
-				const uint32_t bo = r_out[c], bi = r_in[c];
-				s_hist[(bo >> 1) * T] -= 1u << ((bo & 1) * 16);
-				s_hist[(bi >> 1) * T] += 1u << ((bi & 1) * 16);
+				s_hist[r_out[c] * T] -= 1;
+				s_hist[r_in[c] * T] += 1;
 			}
 		}
 		/* --- sequential float cumsum -> LUT (HistEq64Filter.cpp:70-87,97); sums from the histogram --- */
 		float cdf = 0.f;
 		uint32_t total = 0, sxx = 0;
-#pragma unroll 8
-		for (int k = 0; k < 32; ++k) {
-			const uint32_t hw = s_hist[k * T];
-#pragma unroll
-			for (int half = 0; half < 2; ++half) {
-				const uint32_t cnt = half ? (hw >> 16) : (hw & 0xffffu);
-				cdf = __fadd_rn(cdf, __fmul_rn((float)cnt, stretch));
-				const float fl = floorf(cdf); /* (uchar)floor((double)cdf + 0.5) == floor(cdf) + (frac >= 0.5) */
-				const uint32_t e = (uint32_t)(int)fl + (__fsub_rn(cdf, fl) >= 0.5f ? 1u : 0u);
-				s_lut[(2 * k + half) * T] = e & 255u;
-				total += cnt * (e & 255u);
-				sxx += cnt * (e & 255u) * (e & 255u);
-			}
+#pragma unroll 16
+		for (int k = 0; k < 64; ++k) {
+			const uint32_t cnt = s_hist[k * T];
+			cdf = __fadd_rn(cdf, __fmul_rn((float)cnt, stretch));
+			const float fl = floorf(cdf); /* (uchar)floor((double)cdf + 0.5) == floor(cdf) + (frac >= 0.5) */
+			const uint32_t e = ((uint32_t)(int)fl + (__fsub_rn(cdf, fl) >= 0.5f ? 1u : 0u)) & 255u;
+			s_lut[k * T] = (uint16_t)e;
+			total += cnt * e;
+			sxx += cnt * e * e;
 		}
 		/* --- equalised patch into registers, 4 pixels per word --- */
 		uint32_t x[NW];
