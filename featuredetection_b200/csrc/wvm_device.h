@@ -15,7 +15,9 @@ namespace fdb {
 #define FDB_MAX_FILTERS 512   /* hk_kernel_eval capacity per window (e.g. 280 used) */
 #define FDB_MAX_PER_LEVEL 64  /* u_kernel_eval capacity (numFiltersPerLevel, e.g. 14..30) */
 #define FDB_MAX_VALUES 8      /* grey values v >= 1 per filter (cntval - 1) */
+#ifndef WVM_KA
 #define WVM_KA 8              /* filters evaluated by the window kernel before a survivor is queued for wvm_deep_kernel */
+#endif
 
 /* a window that survived the first WVM_KA filters (state of WvmClassifier::computeHyperplaneDistance so far) */
 struct DeepRec {
@@ -56,7 +58,9 @@ struct DevWvm {
 };
 
 /* work item of wvm_strip_kernel: `cols` adjacent window columns x `nsub` runs of WVM_RUN window rows */
+#ifndef WVM_RUN
 #define WVM_RUN 12   /* longest run of window rows one lane walks down */
+#endif
 #define WVM_MAXSUB 4
 struct Strip {
 	int layer;      /* index into the DevLayer table */
