@@ -220,6 +220,7 @@ def main():
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=device)
 
     names = [CFG] if args.workload == "facefrontal" else [c[0] for c in syn.LANDMARK_CONFIGS]
@@ -246,6 +247,7 @@ def main():
     dev_dense = torch.empty((n, max_nwin, 2), dtype=torch.int32, device=device)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
     gather_cap = max(256, 8 * n) * len(cascs)  # fixed-size gather block per rank
+    gather = sharding.DetectionGather(gather_cap, dist, device) if world > 1 else None
     torch.cuda.synchronize()
 
     def barrier():
@@ -262,14 +264,14 @@ def main():
         parts = [c.detect_device(dev_frames.data_ptr(), n, stage=stage, dense_ptr=dev_dense.data_ptr(), det_cap=det_cap) for c in cascs]
         dets = np.concatenate(parts)
         if world > 1:
-            sharding.gather_detections(dets[:gather_cap], lo, gather_cap, dist, device)
+            gather(dets[:gather_cap], lo)
         return dets
 
     def step_e2e():
         parts = [c.detect(host_frames.numpy(), stage=stage, det_cap=det_cap) for c in cascs]
         dets = np.concatenate(parts)
         if world > 1:
-            sharding.gather_detections(dets[:gather_cap], lo, gather_cap, dist, device)
+            gather(dets[:gather_cap], lo)
         return dets
 
     # ---- value: HBM-resident ---------------------------------------------------------------
@@ -299,7 +301,7 @@ def main():
         flush_l2()
         prof.append(np.sum([c.profile_device(dev_frames.data_ptr(), n) for c in cascs], axis=0))
     prof = np.array(prof)
-    ms_resize, ms_down, ms_wvm, ms_stage1 = prof.mean(axis=0)
+    ms_resize, ms_down, ms_wvm, ms_deep, ms_stage1, n_launch = prof.mean(axis=0)
 
     # ---- e2e: host frames through the public call ---------------------------------------------
     for _ in range(2):
@@ -323,8 +325,14 @@ def main():
         value = windows_step * args.steps / (total_ms * 1e-3)
         e2e_value = windows_step * args.steps / (e2e_total * 1e-3)
         peak, peak_src = hbm_peak()
-        algo_bytes = (W * H + WINDOW_BYTES * nwin) * n       # per step of the window kernels (one GPU): frame read once + dense records
-        achieved = algo_bytes / (ms_wvm * 1e-3) / 1e9
+        # dominant kernel = wvm_strip_kernel; one launch covers one internal chunk of the batch
+        frames_per_launch = n * len(cascs) / n_launch
+        algo_bytes = (W * H + WINDOW_BYTES * nwin / len(cascs)) * frames_per_launch   # frame read once + dense records
+        kernel_ms = ms_wvm / n_launch
+        achieved = algo_bytes / (kernel_ms * 1e-3) / 1e9
+        # dram__bytes_read.sum + dram__bytes_write.sum of one wvm_strip_kernel launch (64 frames, FaceFrontal) from
+        # profiles/wvm_r1p_raw.txt (ncu --set full); the layers it reads were just written by pyrDown and sit in L2
+        traffic = 2585600 if args.workload == "facefrontal" and n == 256 else None
         cpu = None
         if not args.no_cpu_baseline:
             arm = CpuArm(args.profile)
@@ -345,12 +353,12 @@ def main():
                     "d2h_bytes_per_step": int(len(dets_e2e) * DETECTION_DTYPE.itemsize + 4),
                     "ms_per_step": e2e_total / args.steps, "frames_per_s": e2e_value / nwin},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "wvm_strip_kernel + wvm_deep_warp_kernel (fused HistEq64 + WVM cascade over all windows of the batch)",
-                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "roofline": {"bound": "hbm", "kernel": "wvm_strip_kernel (fused HistEq64 + first 8 WVM filters on every window; one launch per 64-frame chunk)",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": int(algo_bytes),
-                         "kernel_ms": float(ms_wvm),
-                         "note": "instruction/latency bound: ~3e3 scalar ops per window vs 27 B of compulsory traffic (SURVEY.md 8(d))"},
-            "stage1_ms": {"resize": float(ms_resize), "pyrdown": float(ms_down), "window_kernel": float(ms_wvm), "total": float(ms_stage1)},
+                         "kernel_ms": float(kernel_ms), "launches_per_step": int(n_launch),
+                         "note": "instruction/LSU bound by construction: ~5e3 scalar ops per window vs 27 B of compulsory traffic (SURVEY.md 8(d)); issue-slot utilisation 37 %, see profiles/"},
+            "stage1_ms": {"resize": float(ms_resize), "pyrdown": float(ms_down), "window_kernel": float(ms_wvm), "deep_kernel": float(ms_deep), "total": float(ms_stage1)},
             "detections_per_step": int(len(dets)) * world,
             "cpu_baseline": cpu,
         }

@@ -21,7 +21,7 @@ struct fdb_ctx {
 	int device = 0;
 	cudaStream_t stream = nullptr;
 	int64_t launches = 0;
-	cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr}; /* stopwatch + per-kernel profile marks */
+	cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}; /* stopwatch + per-kernel profile marks */
 };
 
 struct fdb_wvm {

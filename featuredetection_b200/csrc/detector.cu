@@ -149,8 +149,10 @@ int enqueue_stage1(fdb_detector* det, Slot& sl, cudaStream_t st, const uint8_t* 
 		m.step_x = det->desc.step_x; m.step_y = det->desc.step_y;
 		if (det->use_strips && d_layers == det->d_layers && !d_patches) {
 			launch_wvm_strips(st, m, d_frames, W, H, n, sl.d_arena, plan.arena_bytes, d_layers, det->d_strips, det->n_strips,
-					(int)windows, d_dense, want_candidates ? sl.d_cand : nullptr, sl.d_counters, det->cand_cap, sl.deep);
+					(int)windows, d_dense, want_candidates ? sl.d_cand : nullptr, sl.d_counters, det->cand_cap, sl.deep,
+					marks ? c->ev[5] : nullptr);
 		} else {
+			if (marks) CUDA_TRY(cudaEventRecord(c->ev[5], st)); /* generic path: no separate deep mark */
 			launch_wvm_windows(st, m, d_frames, W, H, n, sl.d_arena, plan.arena_bytes, d_layers, (int)plan.layers.size(),
 					(int)windows, d_dense, d_patches, want_candidates ? sl.d_cand : nullptr, sl.d_counters, det->cand_cap, sl.deep);
 		}
@@ -598,25 +600,26 @@ int fdb_detect_enqueue_device(fdb_detector* det, const uint8_t* frames_device, i
 	return FDB_OK;
 }
 
-int fdb_detect_profile_device(fdb_detector* det, const uint8_t* frames_device, int32_t n_frames, double ms_out[4]) {
+int fdb_detect_profile_device(fdb_detector* det, const uint8_t* frames_device, int32_t n_frames, double ms_out[6]) {
 	if (!det || !det->prepared) return fail(FDB_ERR_INVALID_ARGUMENT, "detector not prepared (call fdb_detector_prepare)");
 	int s = check_ctx(det->ctx); if (s) return s;
 	if (n_frames < 0 || n_frames > det->max_batch || !ms_out) return fail(FDB_ERR_INVALID_ARGUMENT, "bad arguments");
 	fdb_ctx* c = det->ctx;
 	const Plan& plan = det->plan;
-	ms_out[0] = ms_out[1] = ms_out[2] = ms_out[3] = 0;
+	for (int k = 0; k < 6; ++k) ms_out[k] = 0;
 	for (int base = 0; base < n_frames; base += det->chunk) {
 		const int n = std::min(det->chunk, n_frames - base);
 		s = enqueue_stage1(det, det->slots[0], c->stream, frames_device + (int64_t)base * plan.width * plan.height, n, plan,
 				det->d_layers, plan.windows, nullptr, nullptr, true, true);
 		if (s) return s;
 		CUDA_TRY(cudaEventSynchronize(c->ev[4]));
-		float a = 0, b = 0, w = 0, t = 0;
+		float a = 0, b = 0, w = 0, d = 0, t = 0;
 		CUDA_TRY(cudaEventElapsedTime(&a, c->ev[1], c->ev[2]));
 		CUDA_TRY(cudaEventElapsedTime(&b, c->ev[2], c->ev[3]));
-		CUDA_TRY(cudaEventElapsedTime(&w, c->ev[3], c->ev[4]));
+		CUDA_TRY(cudaEventElapsedTime(&w, c->ev[3], c->ev[5]));
+		CUDA_TRY(cudaEventElapsedTime(&d, c->ev[5], c->ev[4]));
 		CUDA_TRY(cudaEventElapsedTime(&t, c->ev[1], c->ev[4]));
-		ms_out[0] += a; ms_out[1] += b; ms_out[2] += w; ms_out[3] += t;
+		ms_out[0] += a; ms_out[1] += b; ms_out[2] += w; ms_out[3] += d; ms_out[4] += t; ms_out[5] += 1;
 	}
 	return FDB_OK;
 }

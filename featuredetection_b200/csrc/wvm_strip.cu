@@ -349,12 +349,14 @@ static void strip_launch(cudaStream_t st, const DevWvm& m, const uint8_t* frames
 
 void launch_wvm_strips(cudaStream_t st, const DevWvm& m, const uint8_t* frames, int W, int H, int n_frames,
 		const uint8_t* arena, int64_t arena_stride, const DevLayer* layers, const Strip* strips, int n_strips,
-		int windows_per_frame, fdb_window_score* dense, Candidate* cand, int* cand_count, int cand_cap, const DeepQueue& q) {
+		int windows_per_frame, fdb_window_score* dense, Candidate* cand, int* cand_count, int cand_cap, const DeepQueue& q,
+		cudaEvent_t ev_mid) {
 	if (n_strips == 0 || n_frames == 0) return;
 #define FDB_STRIP_CASE(PW, PH) if (m.fsx == PW && m.fsy == PH) { strip_launch<PW, PH>(st, m, frames, W, H, n_frames, arena, arena_stride, \
 		layers, strips, n_strips, windows_per_frame, dense, cand, cand_count, cand_cap, q); }
 	FDB_STRIP_CASE(20, 20) else FDB_STRIP_CASE(24, 24) else FDB_STRIP_CASE(32, 16) else FDB_STRIP_CASE(32, 24) else FDB_STRIP_CASE(16, 24)
 #undef FDB_STRIP_CASE
+	if (ev_mid) cudaEventRecord(ev_mid, st); /* profiling mark between the two kernels */
 	const int blocks = std::min((q.cap + DEEP_WARPS - 1) / DEEP_WARPS, 148 * 8);
 	wvm_deep_warp_kernel<<<blocks, DEEP_WARPS * 32, 0, st>>>(m, q, windows_per_frame, dense, cand, cand_count, cand_cap);
 }

@@ -191,8 +191,9 @@ class SlidingWindowCascade:
         capi.check(self.ctx.lib, self.ctx.lib.fdb_detect_enqueue_device(self.h, frames_ptr, n, dense_ptr))
 
     def profile_device(self, frames_ptr, n):
-        """(resize ms, pyrDown ms, window-kernel ms, step ms) from CUDA events between the kernels"""
-        ms = (C.c_double * 4)()
+        """(resize ms, pyrDown ms, window-kernel ms, deep-kernel ms, stage-1 ms, launches per kernel) from CUDA
+        events between the kernels, summed over the internal chunks"""
+        ms = (C.c_double * 6)()
         capi.check(self.ctx.lib, self.ctx.lib.fdb_detect_profile_device(self.h, frames_ptr, n, ms))
         return list(ms)
 

@@ -61,3 +61,34 @@ def gather_detections(dets, frame_offset, capacity, dist, device=None, dst=0):
     if dist.get_rank() != dst:
         return None
     return unpack_detections([b.cpu().numpy() for b in bucket], dets.dtype)
+
+
+class DetectionGather:
+    """Reusable gather with preallocated buffers (pinned host + device): one H2D, one all_gather_into_tensor,
+    one D2H and a single stream synchronisation per call."""
+
+    def __init__(self, capacity, dist, device=None):
+        import torch
+        self.torch, self.dist, self.device, self.capacity = torch, dist, device, int(capacity)
+        self.world = dist.get_world_size()
+        shape = (self.capacity + 1, len(GATHER_FIELDS))
+        pin = device is not None
+        self.h_in = torch.zeros(shape, dtype=torch.float64, pin_memory=pin)
+        self.h_out = torch.zeros((self.world,) + shape, dtype=torch.float64, pin_memory=pin)
+        if device is not None:
+            self.d_in = torch.zeros(shape, dtype=torch.float64, device=device)
+            self.d_out = torch.zeros((self.world,) + shape, dtype=torch.float64, device=device)
+
+    def __call__(self, dets, frame_offset, dst=0):
+        torch = self.torch
+        self.h_in.numpy()[...] = pack_detections(dets, frame_offset, self.capacity)
+        if self.device is None:
+            self.dist.all_gather_into_tensor(self.h_out.view(-1), self.h_in.view(-1))
+        else:
+            self.d_in.copy_(self.h_in, non_blocking=True)
+            self.dist.all_gather_into_tensor(self.d_out.view(-1), self.d_in.view(-1))
+            self.h_out.copy_(self.d_out, non_blocking=True)
+            torch.cuda.current_stream(self.device).synchronize()
+        if self.dist.get_rank() != dst:
+            return None
+        return unpack_detections(list(self.h_out.numpy()), dets.dtype)

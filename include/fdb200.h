@@ -279,10 +279,11 @@ FDB_API int fdb_detect_batch_device(fdb_detector* det, const uint8_t* frames_dev
 FDB_API int fdb_detect_enqueue_device(fdb_detector* det, const uint8_t* frames_device,
 		int32_t n_frames, fdb_window_score* dense_out_device);
 
-/* Same enqueue with CUDA events between the kernels of the step; after completion
- * ms_out[0..3] = resize kernel, pyrDown kernels, fused hq64+WVM window kernel, whole step (ms). */
+/* Same enqueue with CUDA events between the kernels of the step (summed over the internal chunks);
+ * after completion ms_out[0..4] = resize kernel, pyrDown kernels, fused hq64+WVM window kernel,
+ * deep-cascade kernel, whole stage 1 (ms); ms_out[5] = number of launches of each kernel. */
 FDB_API int fdb_detect_profile_device(fdb_detector* det, const uint8_t* frames_device,
-		int32_t n_frames, double ms_out[4]);
+		int32_t n_frames, double ms_out[6]);
 
 /* ROI variant: Detector::detect(Mat, Rect) (FiveStageSlidingWindowDetector.cpp:331-380,
  * SlidingWindowDetector.cpp:53-79): one frame, windows restricted by roi {x,y,w,h}. */

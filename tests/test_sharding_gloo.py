@@ -55,6 +55,9 @@ def _worker(rank, world, port, n_frames, queue):
                             want_dense=False)["detections"] for k in range(lo, hi)]
     dets = np.concatenate(mine) if mine else np.zeros(0, fo.DETECTION_DTYPE)
     gathered = sharding.gather_detections(dets, lo, 64, dist)
+    again = sharding.DetectionGather(64, dist)(dets, lo)
+    if rank == 0:
+        assert len(again) == len(gathered) and np.array_equal(again["window"], gathered["window"])
     if rank == 0:
         queue.put(gathered)
     dist.barrier()
