@@ -220,7 +220,7 @@ def main():
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line
+        os.environ["NCCL_DEBUG"] = os.environ.get("FDB_NCCL_DEBUG", "WARN")  # NCCL prints its banner to stdout: keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=device)
 
     names = [CFG] if args.workload == "facefrontal" else [c[0] for c in syn.LANDMARK_CONFIGS]

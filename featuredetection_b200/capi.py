@@ -126,6 +126,9 @@ SYMBOLS = [
     ("fdb_plan_layers", C.c_int, [_P(DetectorDesc), C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P(LayerInfo), C.c_int32, _P(C.c_int32), _P(C.c_int64)]),
     ("fdb_overlap_eliminate", C.c_int, [C.c_void_p, C.c_int64, C.c_float, C.c_float, _P(C.c_int64)]),
     ("fdb_five_stage_nms", C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, _P(C.c_int64)]),
+    ("fdb_svm_file_load", C.c_int, [C.c_char_p, _P(C.c_void_p)]),
+    ("fdb_svm_file_desc", _P(SvmDesc), [C.c_void_p]),
+    ("fdb_svm_file_free", None, [C.c_void_p]),
     ("fdb_detector_last_counts", C.c_int, [C.c_void_p, _P(C.c_int64)]),
 ]
 

@@ -321,6 +321,14 @@ FDB_API int fdb_overlap_eliminate(fdb_detection* dets, int64_t n, float dist, fl
  * (FiveStageSlidingWindowDetector.cpp:143-184,276-311) on the SVM-positive patches of ONE frame. */
 FDB_API int fdb_five_stage_nms(fdb_detection* dets, int64_t n, int32_t width, int32_t height, int64_t* n_out);
 
+/* The reference's SVM text container (SvmClassifier::store/load(std::ifstream&), SvmClassifier.cpp:68-158,
+ * followed by ProbabilisticSvmClassifier's "Logistic a b" line, ProbabilisticSvmClassifier.cpp:65-78).
+ * The returned descriptor points into the file object and stays valid until fdb_svm_file_free. */
+typedef struct fdb_svm_file fdb_svm_file;
+FDB_API int fdb_svm_file_load(const char* path, fdb_svm_file** out);
+FDB_API const fdb_svm_desc* fdb_svm_file_desc(const fdb_svm_file* file);
+FDB_API void fdb_svm_file_free(fdb_svm_file* file);
+
 /* Per-stage counters of the last detect call (TOT/TACC-style counters, ffpDetectApp.cpp:650-657):
  * [0] windows, [1] wvm positives, [2] after OE, [3] svm positives, [4] after NMS. */
 FDB_API int fdb_detector_last_counts(fdb_detector* det, int64_t counts[5]);

@@ -106,6 +106,7 @@ def ref():
         R.ref_overlap_eliminate.restype = C.c_int
         R.ref_overlap_eliminate.argtypes = [C.c_float, C.c_float, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                             C.c_void_p, C.c_void_p]
+        R.ref_svm_store.restype = C.c_int; R.ref_svm_store.argtypes = [C.c_void_p, C.c_char_p]
         R.ref_detect_frame.restype = C.c_int64
         R.ref_detect_frame.argtypes = [C.POINTER(capi.DetectorDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                        C.c_int, C.c_void_p, C.POINTER(C.c_int64), C.c_void_p, C.c_int64, C.POINTER(C.c_double)]

@@ -171,6 +171,15 @@ void ref_svm_eval(void* p, const void* x, double* distance, double* probability,
 	if (positive) *positive = pr.first ? 1 : 0;
 }
 
+/* ProbabilisticSvmClassifier::store (-> SvmClassifier::store) into a text file: the reference's own writer */
+int ref_svm_store(void* p, const char* path) {
+	RefSvm* r = (RefSvm*)p;
+	std::ofstream file(path);
+	if (!file) return -1;
+	r->psvm->store(file);
+	return 0;
+}
+
 /* OverlapElimination::eliminate on n candidates {center_x, center_y, width, probability};
  * writes the surviving candidates' input indices (in output order) to keep_out, returns count.
  * NOTE: std::sort is not stable; inputs with equal probabilities may come back in a different

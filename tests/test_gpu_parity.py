@@ -259,3 +259,72 @@ def test_landmark_models_realistic(ctx, name):
     assert np.max(np.abs(dense[0]["fout"] - ref["dense"]["fout"])) <= TOL
     assert list(dets["window"]) == list(ref["detections"]["window"])
     assert np.allclose(dets["svm_distance"], ref["detections"]["svm_distance"], rtol=0, atol=TOL)
+
+
+@pytest.mark.parametrize("steps", [(2, 3), (5, 1)])
+def test_window_steps_generic_path(ctx, face_models, steps):
+    """SlidingWindowDetector(classifier, extractor, stepX, stepY) with steps != 1 (generic kernels)."""
+    fo = _oracle()
+    det_kw, wvm, svm = face_models
+    kw = dict(det_kw, step_x=steps[0], step_y=steps[1])
+    casc = SlidingWindowCascade(ctx, kw, wvm, svm)
+    casc.prepare(640, 480, 2)
+    frames = syn.synthetic_frames(70, 2)
+    dets, dense = casc.detect(frames, stage=capi.FDB_STAGE_NMS, want_dense=True)
+    wo, so = fo.Wvm(wvm), fo.Svm(svm)
+    for k in range(2):
+        ref = fo.detect_frame(kw, wo, so, frames[k], stage=capi.FDB_STAGE_NMS, frame_index=k)
+        assert ref["windows"] == dense.shape[1]
+        assert np.array_equal(dense[k]["level"], ref["dense"]["level"])
+        assert np.max(np.abs(dense[k]["fout"] - ref["dense"]["fout"])) <= TOL
+        assert list(dets[dets["frame"] == k]["window"]) == list(ref["detections"]["window"])
+
+
+def test_pitch_partial_batches_and_empty(ctx, face_models):
+    """Row pitch > width, batch sizes that do not divide the prepared batch, and an empty batch."""
+    import ctypes as C
+    from featuredetection_b200.detector import DETECTION_DTYPE
+    det_kw, wvm, svm = face_models
+    casc = SlidingWindowCascade(ctx, det_kw, wvm, svm)
+    casc.prepare(640, 480, 20)  # chunk = 5 frames, 3 slots
+    frames = syn.synthetic_frames(80, 13)
+    want = casc.detect(frames, stage=capi.FDB_STAGE_NMS)
+    padded = np.zeros((13, 480, 704), np.uint8)
+    padded[:, :, :640] = frames
+    dets = np.zeros(4096, DETECTION_DTYPE)
+    cnt = C.c_int64()
+    capi.check(ctx.lib, ctx.lib.fdb_detect_batch(casc.h, padded.ctypes.data, 704, 13, capi.FDB_STAGE_NMS, None,
+                                                 dets.ctypes.data, 4096, C.byref(cnt)))
+    got = dets[:cnt.value]
+    assert np.array_equal(got["window"], want["window"]) and np.array_equal(got["frame"], want["frame"])
+    assert np.array_equal(got["svm_distance"], want["svm_distance"])
+    for n in (1, 4, 6, 11):
+        part = casc.detect(frames[:n], stage=capi.FDB_STAGE_NMS)
+        ref = want[want["frame"] < n]
+        assert np.array_equal(part["window"], ref["window"]) and np.array_equal(part["frame"], ref["frame"])
+    capi.check(ctx.lib, ctx.lib.fdb_detect_batch(casc.h, padded.ctypes.data, 704, 0, capi.FDB_STAGE_NMS, None,
+                                                 dets.ctypes.data, 4096, C.byref(cnt)))
+    assert cnt.value == 0
+    # error behaviour: too small result buffer, bad stage, pitch < width
+    assert ctx.lib.fdb_detect_batch(casc.h, padded.ctypes.data, 704, 13, capi.FDB_STAGE_NMS, None, dets.ctypes.data, 1, C.byref(cnt)) == 6
+    assert cnt.value == len(want)  # the needed capacity is reported
+    assert ctx.lib.fdb_detect_batch(casc.h, padded.ctypes.data, 704, 1, 9, None, dets.ctypes.data, 4096, C.byref(cnt)) == 1
+    assert ctx.lib.fdb_detect_batch(casc.h, padded.ctypes.data, 600, 1, 1, None, dets.ctypes.data, 4096, C.byref(cnt)) == 1
+
+
+def test_model_validation_errors(ctx, face_models):
+    """Loader-side errors of the reference become status codes (invalid_argument / unsupported)."""
+    import copy
+    import ctypes as C
+    det_kw, wvm, svm = face_models
+    bad = copy.copy(wvm)
+    bad.rec = wvm.rec.copy(); bad.rec[0] = (0, 0, 25, 3)  # rectangle outside the 20x20 filter window
+    d = bad.desc(); h = C.c_void_p()
+    assert ctx.lib.fdb_wvm_create(ctx.h, C.byref(d), C.byref(h)) == 1 and not h.value
+    with pytest.raises(capi.FdbError):  # patch size differs from the WVM filter size
+        SlidingWindowCascade(ctx, dict(det_kw, patch_width=24), wvm, svm)
+    with pytest.raises(capi.FdbError):  # DirectPyramidFeatureExtractor: stepX has to be greater than zero
+        SlidingWindowCascade(ctx, dict(det_kw, step_x=-2), wvm, svm)
+    casc = SlidingWindowCascade(ctx, det_kw, wvm, svm)
+    with pytest.raises(capi.FdbError):  # not prepared
+        casc.detect_roi(syn.synthetic_frame(0), (0, 0, 10, 10))

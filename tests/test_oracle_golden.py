@@ -149,3 +149,30 @@ def test_synthetic_inputs_are_reproducible():
     assert zlib.crc32(w.hk_weights.tobytes()) == 3194455472
     assert zlib.crc32(s.sv.tobytes()) == 1226913186
     assert zlib.crc32(w.thresholds.tobytes()) == 1260564680
+
+
+def test_svm_text_container_roundtrip(fo, tmp_path):
+    """fdb_svm_file_load (product, host only) reads what the reference's own ProbabilisticSvmClassifier::store
+    writes (needs oracle/_ref): float32 support vectors, coefficients, bias, gamma and the logistic line."""
+    import ctypes as C
+    if not fo.ref_available():
+        pytest.skip("oracle/_ref not built here")
+    lib = capi.load_library()
+    rng = np.random.default_rng(4)
+    model = syn.SvmModel(rng.normal(0, 1, (37, 144)).astype(np.float32), rng.normal(0, 1, 37).astype(np.float32),
+                         gamma=0.2, bias=0.125, logistic_a=-0.6663, logistic_b=-1.8201)
+    ref = fo.Svm(model, use_ref=True)
+    path = str(tmp_path / "svm.txt").encode()
+    assert fo.ref().ref_svm_store(ref.h, path) == 0
+    h = C.c_void_p()
+    capi.check(lib, lib.fdb_svm_file_load(path, C.byref(h)))
+    d = lib.fdb_svm_file_desc(h).contents
+    assert (d.num_sv, d.dim, d.sv_type, d.kernel) == (37, 144, capi.FDB_SV_F32, capi.FDB_KERNEL_RBF)
+    # operator<< prints 6 significant digits: compare at that precision
+    assert abs(d.gamma - 0.2) < 1e-6 and abs(d.bias - 0.125) < 1e-6
+    assert abs(d.logistic_a + 0.6663) < 1e-6 and abs(d.logistic_b + 1.8201) < 1e-6
+    coef = np.ctypeslib.as_array(d.coefficients, shape=(37,))
+    sv = np.ctypeslib.as_array(C.cast(d.support_vectors, C.POINTER(C.c_float)), shape=(37, 144))
+    assert np.allclose(coef, model.coef, rtol=1e-5, atol=1e-7) and np.allclose(sv, model.sv, rtol=1e-5, atol=1e-7)
+    lib.fdb_svm_file_free(h)
+    assert lib.fdb_svm_file_load(b"/nonexistent/file", C.byref(h)) == 2
