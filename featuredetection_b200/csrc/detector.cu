@@ -461,7 +461,7 @@ int fdb_detector_prepare(fdb_detector* det, int32_t width, int32_t height, int32
 	/* job tables */
 	std::vector<ResizeJob> rj;
 	std::vector<std::vector<DownJob>> dj((size_t)plan.max_down + 1);
-	std::vector<int> ofs; std::vector<short2> coef;
+	std::vector<int> ofs, winfo; std::vector<short2> coef;
 	det->max_quads = 0;
 	for (const PyrImage& im : plan.images) {
 		if (im.kind == IMG_RESIZE) {
@@ -470,8 +470,20 @@ int fdb_detector_prepare(fdb_detector* det, int32_t width, int32_t height, int32
 			j.area2x = (width == 2 * im.width && height == 2 * im.height) ? 1 : 0;
 			j.xtab = (int)ofs.size();
 			linear_tables(width, im.width, true, ofs, coef);
+			/* word-path info per output column (see resize_kernel) */
+			j.words_ok = (width % 4 == 0) ? 1 : 0;
+			winfo.resize(ofs.size(), 0);
+			for (int dx0 = 0; dx0 < im.width; dx0 += 4) {
+				const int base = ofs[(size_t)j.xtab + dx0] & ~3;
+				for (int k = 0; k < 4 && dx0 + k < im.width; ++k) {
+					const int o = ofs[(size_t)j.xtab + dx0 + k] - base;
+					if (o < 0 || o > 10) j.words_ok = 0;
+					winfo[(size_t)j.xtab + dx0 + k] = (o >> 2) | (((o & 3) * 8) << 8) | ((base >> 2) << 16);
+				}
+			}
 			j.ytab = (int)ofs.size();
 			linear_tables(height, im.height, false, ofs, coef);
+			winfo.resize(ofs.size(), 0);
 			rj.push_back(j);
 			det->max_quads = std::max(det->max_quads, resize_tiles(im.width, im.height));
 		} else if (im.kind == IMG_PYRDOWN) {
@@ -485,7 +497,8 @@ int fdb_detector_prepare(fdb_detector* det, int32_t width, int32_t height, int32
 	det->n_resize = (int)rj.size();
 	s = upload(rj.data(), rj.size(), &det->d_resize, det->owned); if (s) return s;
 	std::vector<int4> xy(ofs.size());
-	for (size_t k = 0; k < ofs.size(); ++k) { xy[k].x = ofs[k]; xy[k].y = coef[k].x; xy[k].z = coef[k].y; xy[k].w = 0; }
+	winfo.resize(ofs.size(), 0);
+	for (size_t k = 0; k < ofs.size(); ++k) { xy[k].x = ofs[k]; xy[k].y = coef[k].x; xy[k].z = coef[k].y; xy[k].w = winfo[k]; }
 	s = upload(xy.data(), xy.size(), &det->d_xy_tab, det->owned); if (s) return s;
 	for (size_t j = 1; j < dj.size(); ++j) {
 		DownJob* p = nullptr;

@@ -72,6 +72,7 @@ struct ResizeJob {       /* one cv::resize target */
 	int64_t dst_offset;  /* arena offset */
 	int xtab, ytab;      /* offsets into the coefficient tables */
 	int area2x;          /* 1: exact 2x decimation (INTER_AREA fast path) */
+	int words_ok;        /* 1: aligned-word source path usable (W % 4 == 0, every quad spans <= 11 source bytes) */
 };
 
 struct DownJob {         /* one cv::pyrDown */

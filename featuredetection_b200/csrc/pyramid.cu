@@ -31,69 +31,91 @@ __device__ __forceinline__ int reflect101(int p, int len) {
 /* ---------------------------------------------------------------------------------------------
  * resize: grid = (tiles, job, frame); a CTA of 256 threads = 32 pixel-quads x 8 rows, i.e. a
  * 128 x 8 output tile; each thread produces 4 horizontally adjacent pixels and stores one word.
- * Tables: xy_tab[k] = {source offset, a0, a1, 0} (one 16-byte load per output column / row).
+ * Tables: xy_tab[k] = {source offset, a0, a1, word-path info} (one 16-byte load per output column / row);
+ * word-path info of column dx = word select | bit shift << 8 | base word of its quad << 16.
  * ------------------------------------------------------------------------------------------- */
 #define RS_QX 32
 #define RS_TY 8
+
+#define RS_ROWS 4   /* output rows per thread: the column tables are loaded once and reused */
 
 __global__ void __launch_bounds__(RS_QX * RS_TY) resize_kernel(const uint8_t* __restrict__ frames, int W, int H,
 		uint8_t* __restrict__ arena, int64_t arena_stride,
 		const ResizeJob* __restrict__ jobs, const int4* __restrict__ xy_tab) {
 	const ResizeJob job = jobs[blockIdx.y];
 	const int quads_per_row = (job.dst_w + 3) >> 2;
-	const int tiles_x = (quads_per_row + RS_QX - 1) / RS_QX, tiles_y = (job.dst_h + RS_TY - 1) / RS_TY;
+	const int tiles_x = (quads_per_row + RS_QX - 1) / RS_QX, tiles_y = (job.dst_h + RS_TY * RS_ROWS - 1) / (RS_TY * RS_ROWS);
 	if ((int)blockIdx.x >= tiles_x * tiles_y) return;
 	const int tile_y = (int)blockIdx.x / tiles_x, tile_x = (int)blockIdx.x - tile_y * tiles_x;
-	const int dy = tile_y * RS_TY + ((int)threadIdx.x >> 5);
 	const int dx0 = (tile_x * RS_QX + ((int)threadIdx.x & 31)) << 2;
-	if (dy >= job.dst_h || dx0 >= job.dst_w) return;
+	if (dx0 >= job.dst_w) return;
 	const uint8_t* __restrict__ src = frames + (int64_t)blockIdx.z * W * H;
-	uint8_t* __restrict__ o = arena + (int64_t)blockIdx.z * arena_stride + job.dst_offset + dy * job.dst_w + dx0;
+	uint8_t* __restrict__ dst = arena + (int64_t)blockIdx.z * arena_stride + job.dst_offset;
 	const int nvalid = min(4, job.dst_w - dx0);
-	uint32_t packed = 0;
-	if (job.area2x) {
-		const uint8_t* s0 = src + (2 * dy) * W;
-		const uint8_t* s1 = s0 + W;
+	const bool word_store = nvalid == 4 && ((job.dst_w & 3) == 0);
+	const int4* __restrict__ xt = xy_tab + job.xtab + dx0;
+	const bool fast = nvalid == 4 && job.words_ok && !job.area2x;
+	int4 t0 = make_int4(0, 0, 0, 0), t1 = t0, t2 = t0, t3 = t0;
+	if (fast) { t0 = __ldg(xt); t1 = __ldg(xt + 1); t2 = __ldg(xt + 2); t3 = __ldg(xt + 3); }
+	const int wlast = (W >> 2) - 1;
+	const int b0 = (int)((uint32_t)t0.w >> 16), b1 = min(b0 + 1, wlast), b2 = min(b0 + 2, wlast);
 #pragma unroll
-		for (int k = 0; k < 4; ++k)
-			if (k < nvalid) {
-				const int x = 2 * (dx0 + k);
-				packed |= (uint32_t)((s0[x] + s0[x + 1] + s1[x] + s1[x + 1] + 2) >> 2) << (8 * k);
-			}
-	} else {
-		const int4 ty = __ldg(xy_tab + job.ytab + dy);
-		const int y0 = min(max(ty.x, 0), H - 1), y1 = min(max(ty.x + 1, 0), H - 1);
-		const uint8_t* __restrict__ s0 = src + y0 * W;
-		const uint8_t* __restrict__ s1 = src + y1 * W;
-		const int4* __restrict__ xt = xy_tab + job.xtab + dx0;
-		if (nvalid == 4) {
-			const int4 t0 = __ldg(xt), t1 = __ldg(xt + 1), t2 = __ldg(xt + 2), t3 = __ldg(xt + 3);
-			const int W1 = W - 1;
-			/* 16 independent byte loads first, then the fixed-point arithmetic */
-			const int p00 = s0[t0.x], p01 = s0[min(t0.x + 1, W1)], q00 = s1[t0.x], q01 = s1[min(t0.x + 1, W1)];
-			const int p10 = s0[t1.x], p11 = s0[min(t1.x + 1, W1)], q10 = s1[t1.x], q11 = s1[min(t1.x + 1, W1)];
-			const int p20 = s0[t2.x], p21 = s0[min(t2.x + 1, W1)], q20 = s1[t2.x], q21 = s1[min(t2.x + 1, W1)];
-			const int p30 = s0[t3.x], p31 = s0[min(t3.x + 1, W1)], q30 = s1[t3.x], q31 = s1[min(t3.x + 1, W1)];
-#define FDB_RS_PIX(P0, P1, Q0, Q1, T) ((((ty.y * ((P0 * T.y + P1 * T.z) >> 4)) >> 16) + ((ty.z * ((Q0 * T.y + Q1 * T.z) >> 4)) >> 16) + 2) >> 2)
-			const int v0 = FDB_RS_PIX(p00, p01, q00, q01, t0), v1 = FDB_RS_PIX(p10, p11, q10, q11, t1);
-			const int v2 = FDB_RS_PIX(p20, p21, q20, q21, t2), v3 = FDB_RS_PIX(p30, p31, q30, q31, t3);
-#undef FDB_RS_PIX
-			packed = (uint32_t)(v0 & 255) | ((uint32_t)(v1 & 255) << 8) | ((uint32_t)(v2 & 255) << 16) | ((uint32_t)(v3 & 255) << 24);
+	for (int i = 0; i < RS_ROWS; ++i) {
+		const int dy = tile_y * (RS_TY * RS_ROWS) + i * RS_TY + ((int)threadIdx.x >> 5);
+		if (dy >= job.dst_h) break;
+		uint32_t packed = 0;
+		if (job.area2x) {
+			const uint8_t* s0 = src + (2 * dy) * W;
+			const uint8_t* s1 = s0 + W;
+#pragma unroll
+			for (int k = 0; k < 4; ++k)
+				if (k < nvalid) {
+					const int x = 2 * (dx0 + k);
+					packed |= (uint32_t)((s0[x] + s0[x + 1] + s1[x] + s1[x + 1] + 2) >> 2) << (8 * k);
+				}
 		} else {
-			for (int k = 0; k < nvalid; ++k) {
-				const int4 tx = __ldg(xt + k);
-				const int sx = tx.x, sx1 = min(sx + 1, W - 1);
-				const int h0 = s0[sx] * tx.y + s0[sx1] * tx.z;
-				const int h1 = s1[sx] * tx.y + s1[sx1] * tx.z;
-				const int v = (((ty.y * (h0 >> 4)) >> 16) + ((ty.z * (h1 >> 4)) >> 16) + 2) >> 2;
-				packed |= (uint32_t)(v & 255) << (8 * k);
+			const int4 ty = __ldg(xy_tab + job.ytab + dy);
+			const int y0 = min(max(ty.x, 0), H - 1), y1 = min(max(ty.x + 1, 0), H - 1);
+			const uint8_t* __restrict__ s0 = src + y0 * W;
+			const uint8_t* __restrict__ s1 = src + y1 * W;
+			if (fast) {
+				/* word path: the 8 source bytes of a row that 4 adjacent outputs need lie within 12 bytes of a
+				 * 4-aligned base (scale < 2); three aligned 32-bit loads per row replace 8 byte gathers and the
+				 * byte pairs (sx, sx+1) are cut out with funnel shifts. t.w = word select | bit shift << 8 | base word << 16 */
+				const uint32_t* __restrict__ r0 = reinterpret_cast<const uint32_t*>(s0);
+				const uint32_t* __restrict__ r1 = reinterpret_cast<const uint32_t*>(s1);
+				const uint32_t p0 = __ldg(r0 + b0), p1 = __ldg(r0 + b1), p2 = __ldg(r0 + b2);
+				const uint32_t q0 = __ldg(r1 + b0), q1 = __ldg(r1 + b1), q2 = __ldg(r1 + b2);
+#define FDB_RS_PAIR(A0, A1, A2, T) __funnelshift_r(((T.w & 255) == 0 ? A0 : ((T.w & 255) == 1 ? A1 : A2)), \
+						((T.w & 255) == 0 ? A1 : A2), (unsigned)((T.w >> 8) & 31))
+#define FDB_RS_PIXW(T) { const uint32_t up = FDB_RS_PAIR(p0, p1, p2, T), lo = FDB_RS_PAIR(q0, q1, q2, T); \
+					const int h0 = (int)(up & 255u) * T.y + (int)((up >> 8) & 255u) * T.z; \
+					const int h1 = (int)(lo & 255u) * T.y + (int)((lo >> 8) & 255u) * T.z; \
+					v = (((ty.y * (h0 >> 4)) >> 16) + ((ty.z * (h1 >> 4)) >> 16) + 2) >> 2; }
+				int v;
+				FDB_RS_PIXW(t0) packed = (uint32_t)(v & 255);
+				FDB_RS_PIXW(t1) packed |= (uint32_t)(v & 255) << 8;
+				FDB_RS_PIXW(t2) packed |= (uint32_t)(v & 255) << 16;
+				FDB_RS_PIXW(t3) packed |= (uint32_t)(v & 255) << 24;
+#undef FDB_RS_PIXW
+#undef FDB_RS_PAIR
+			} else {
+				for (int k = 0; k < nvalid; ++k) {
+					const int4 tx = __ldg(xt + k);
+					const int sx = tx.x, sx1 = min(sx + 1, W - 1);
+					const int h0 = s0[sx] * tx.y + s0[sx1] * tx.z;
+					const int h1 = s1[sx] * tx.y + s1[sx1] * tx.z;
+					const int v = (((ty.y * (h0 >> 4)) >> 16) + ((ty.z * (h1 >> 4)) >> 16) + 2) >> 2;
+					packed |= (uint32_t)(v & 255) << (8 * k);
+				}
 			}
 		}
-	}
-	if (nvalid == 4 && ((job.dst_w & 3) == 0)) {
-		*reinterpret_cast<uint32_t*>(o) = packed;
-	} else {
-		for (int k = 0; k < nvalid; ++k) o[k] = (uint8_t)(packed >> (8 * k));
+		uint8_t* o = dst + dy * job.dst_w + dx0;
+		if (word_store) {
+			*reinterpret_cast<uint32_t*>(o) = packed;
+		} else {
+			for (int k = 0; k < nvalid; ++k) o[k] = (uint8_t)(packed >> (8 * k));
+		}
 	}
 }
 
@@ -192,7 +214,7 @@ void launch_resize(cudaStream_t st, const uint8_t* frames, int W, int H, int n_f
 
 int resize_tiles(int dst_w, int dst_h) {
 	const int quads = (dst_w + 3) / 4;
-	return ((quads + RS_QX - 1) / RS_QX) * ((dst_h + RS_TY - 1) / RS_TY);
+	return ((quads + RS_QX - 1) / RS_QX) * ((dst_h + RS_TY * RS_ROWS - 1) / (RS_TY * RS_ROWS));
 }
 
 void launch_pyrdown(cudaStream_t st, const uint8_t* frames, int W, int H, int n_frames, uint8_t* arena,

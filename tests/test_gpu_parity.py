@@ -328,3 +328,23 @@ def test_model_validation_errors(ctx, face_models):
     casc = SlidingWindowCascade(ctx, det_kw, wvm, svm)
     with pytest.raises(capi.FdbError):  # not prepared
         casc.detect_roi(syn.synthetic_frame(0), (0, 0, 10, 10))
+
+
+def test_full_hd_frame(ctx, face_models):
+    """BASELINE configs[2] geometry: one 1920x1080 frame (190 616 FaceFrontal windows, 21 pyramid layers up
+    to 307 px wide -> many strips per layer), whole cascade against the oracle."""
+    fo = _oracle()
+    det_kw, wvm, svm = face_models
+    frame = syn.synthetic_frame(5, 1920, 1080)
+    casc = SlidingWindowCascade(ctx, det_kw, wvm, svm)
+    casc.prepare(1920, 1080, 1)
+    assert casc.windows_per_frame == 190616
+    dets, dense = casc.detect(frame[None], stage=capi.FDB_STAGE_NMS, want_dense=True)
+    ref = fo.detect_frame(det_kw, fo.Wvm(wvm), fo.Svm(svm), frame, stage=capi.FDB_STAGE_NMS)
+    assert np.array_equal(dense[0]["level"], ref["dense"]["level"])
+    assert np.max(np.abs(dense[0]["fout"] - ref["dense"]["fout"])) <= TOL
+    assert list(dets["window"]) == list(ref["detections"]["window"])
+    for idx in (casc.layers()[0]["index"], casc.layers()[-1]["index"]):
+        _, layers = fo.pyramid(frame, det_kw["incremental_scale_factor"], det_kw["min_scale_factor"], det_kw["max_scale_factor"])
+        img = [im for i, _, im in layers if i == idx][0]
+        assert np.array_equal(casc.pyramid_layer(frame, idx), img)
