@@ -358,8 +358,11 @@ int detect_pipeline(fdb_detector* det, const uint8_t* frames, bool frames_on_dev
 		if (frames_on_device) {
 			sl.frames_dev = frames + (int64_t)sl.base * W * H;
 		} else {
-			CUDA_TRY(cudaMemcpy2DAsync(sl.d_frames, (size_t)W, frames + (int64_t)sl.base * pitch * H, (size_t)pitch, (size_t)W,
-					(size_t)H * sl.n, cudaMemcpyHostToDevice, sl.st));
+			if (pitch == W) /* contiguous frames: one linear copy */
+				CUDA_TRY(cudaMemcpyAsync(sl.d_frames, frames + (int64_t)sl.base * W * H, (size_t)W * H * sl.n, cudaMemcpyHostToDevice, sl.st));
+			else
+				CUDA_TRY(cudaMemcpy2DAsync(sl.d_frames, (size_t)W, frames + (int64_t)sl.base * pitch * H, (size_t)pitch, (size_t)W,
+						(size_t)H * sl.n, cudaMemcpyHostToDevice, sl.st));
 			sl.frames_dev = sl.d_frames;
 		}
 		fdb_window_score* d_dense = nullptr;
