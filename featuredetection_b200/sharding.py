@@ -64,8 +64,9 @@ def gather_detections(dets, frame_offset, capacity, dist, device=None, dst=0):
 
 
 class DetectionGather:
-    """Reusable gather with preallocated buffers (pinned host + device): one H2D, one all_gather_into_tensor,
-    one D2H and a single stream synchronisation per call."""
+    """Reusable gather with preallocated buffers (pinned host + device), double-buffered so that the gather of
+    step k overlaps the computation of step k+1: submit() enqueues H2D + all_gather + D2H on a side stream and
+    returns a ticket, collect(ticket) waits for it and unpacks on the destination rank."""
 
     def __init__(self, capacity, dist, device=None):
         import torch
@@ -73,22 +74,40 @@ class DetectionGather:
         self.world = dist.get_world_size()
         shape = (self.capacity + 1, len(GATHER_FIELDS))
         pin = device is not None
-        self.h_in = torch.zeros(shape, dtype=torch.float64, pin_memory=pin)
-        self.h_out = torch.zeros((self.world,) + shape, dtype=torch.float64, pin_memory=pin)
-        if device is not None:
-            self.d_in = torch.zeros(shape, dtype=torch.float64, device=device)
-            self.d_out = torch.zeros((self.world,) + shape, dtype=torch.float64, device=device)
+        self.bufs = []
+        for _ in range(2):
+            b = {"h_in": torch.zeros(shape, dtype=torch.float64, pin_memory=pin),
+                 "h_out": torch.zeros((self.world,) + shape, dtype=torch.float64, pin_memory=pin), "event": None}
+            if device is not None:
+                b["d_in"] = torch.zeros(shape, dtype=torch.float64, device=device)
+                b["d_out"] = torch.zeros((self.world,) + shape, dtype=torch.float64, device=device)
+            self.bufs.append(b)
+        self.stream = torch.cuda.Stream(device) if device is not None else None
+        self.turn = 0
 
-    def __call__(self, dets, frame_offset, dst=0):
+    def submit(self, dets, frame_offset):
         torch = self.torch
-        self.h_in.numpy()[...] = pack_detections(dets, frame_offset, self.capacity)
+        b = self.bufs[self.turn]
+        self.turn ^= 1
+        b["h_in"].numpy()[...] = pack_detections(dets, frame_offset, self.capacity)
+        b["dtype"] = dets.dtype
         if self.device is None:
-            self.dist.all_gather_into_tensor(self.h_out.view(-1), self.h_in.view(-1))
+            self.dist.all_gather_into_tensor(b["h_out"].view(-1), b["h_in"].view(-1))
         else:
-            self.d_in.copy_(self.h_in, non_blocking=True)
-            self.dist.all_gather_into_tensor(self.d_out.view(-1), self.d_in.view(-1))
-            self.h_out.copy_(self.d_out, non_blocking=True)
-            torch.cuda.current_stream(self.device).synchronize()
+            with torch.cuda.stream(self.stream):
+                b["d_in"].copy_(b["h_in"], non_blocking=True)
+                self.dist.all_gather_into_tensor(b["d_out"].view(-1), b["d_in"].view(-1))
+                b["h_out"].copy_(b["d_out"], non_blocking=True)
+                b["event"] = torch.cuda.Event()
+                b["event"].record(self.stream)
+        return b
+
+    def collect(self, ticket, dst=0):
+        if ticket.get("event") is not None:
+            ticket["event"].synchronize()
         if self.dist.get_rank() != dst:
             return None
-        return unpack_detections(list(self.h_out.numpy()), dets.dtype)
+        return unpack_detections(list(ticket["h_out"].numpy()), ticket["dtype"])
+
+    def __call__(self, dets, frame_offset, dst=0):
+        return self.collect(self.submit(dets, frame_offset), dst)
