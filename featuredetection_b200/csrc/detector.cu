@@ -114,9 +114,10 @@ int upload_layers(fdb_detector* det, const Plan& plan, DevLayer* dst, cudaStream
 		const PlanLayer& p = plan.layers[i];
 		L[i].offset = plan.images[p.image].offset;
 		L[i].width = p.width; L[i].height = p.height;
+		L[i].pitch = plan.images[p.image].pitch;
 		L[i].begin_x = p.begin_x; L[i].begin_y = p.begin_y;
 		L[i].windows_x = p.windows_x; L[i].windows_y = p.windows_y;
-		L[i].first_window = (int)p.first_window; L[i].pad = 0;
+		L[i].first_window = (int)p.first_window;
 	}
 	if (!L.empty())
 		CUDA_TRY(cudaMemcpyAsync(dst, L.data(), sizeof(DevLayer) * L.size(), cudaMemcpyHostToDevice, st));
@@ -469,7 +470,7 @@ int fdb_detector_prepare(fdb_detector* det, int32_t width, int32_t height, int32
 	for (const PyrImage& im : plan.images) {
 		if (im.kind == IMG_RESIZE) {
 			ResizeJob j{};
-			j.dst_w = im.width; j.dst_h = im.height; j.dst_offset = im.offset;
+			j.dst_w = im.width; j.dst_h = im.height; j.dst_pitch = im.pitch; j.dst_offset = im.offset;
 			j.area2x = (width == 2 * im.width && height == 2 * im.height) ? 1 : 0;
 			j.xtab = (int)ofs.size();
 			linear_tables(width, im.width, true, ofs, coef);
@@ -493,6 +494,7 @@ int fdb_detector_prepare(fdb_detector* det, int32_t width, int32_t height, int32
 			const PyrImage& src = plan.images[(size_t)im.src];
 			DownJob j{};
 			j.src_w = src.width; j.src_h = src.height; j.dst_w = im.width; j.dst_h = im.height;
+			j.src_pitch = src.pitch; j.dst_pitch = im.pitch;
 			j.src_offset = src.kind == IMG_FRAME ? -1 : src.offset; j.dst_offset = im.offset;
 			dj[(size_t)im.down].push_back(j);
 		}
@@ -588,7 +590,7 @@ int64_t fdb_detector_windows_per_frame(fdb_detector* det) { return det && det->p
 int64_t fdb_detector_pyramid_bytes(fdb_detector* det) {
 	if (!det || !det->prepared) return -1;
 	int64_t b = 0;
-	for (const PyrImage& im : det->plan.images) if (im.kind != IMG_FRAME) b += (int64_t)im.width * im.height;
+	for (const PyrImage& im : det->plan.images) if (im.kind != IMG_FRAME) b += (int64_t)im.pitch * im.height;
 	return b;
 }
 
@@ -712,7 +714,7 @@ int fdb_pyramid_layer(fdb_detector* det, const uint8_t* frame_host, int64_t pitc
 	if (s) return s;
 	const PyrImage& im = plan.images[(size_t)L->image];
 	const uint8_t* src = im.kind == IMG_FRAME ? sl.d_frames : sl.d_arena + im.offset;
-	CUDA_TRY(cudaMemcpyAsync(out, src, (size_t)L->width * L->height, cudaMemcpyDeviceToHost, st));
+	CUDA_TRY(cudaMemcpy2DAsync(out, (size_t)L->width, src, (size_t)im.pitch, (size_t)L->width, (size_t)L->height, cudaMemcpyDeviceToHost, st));
 	CUDA_TRY(cudaStreamSynchronize(st));
 	return FDB_OK;
 }

@@ -24,6 +24,7 @@ struct PyrImage {
 	int kind;        /* ImageKind */
 	int src;         /* index of the source image in the plan (-1: the input frame) */
 	int width, height;
+	int pitch;       /* row pitch in bytes: a multiple of 16 inside the arena (TMA), the frame width for IMG_FRAME */
 	int64_t offset;  /* byte offset inside the per-frame arena (IMG_FRAME: unused) */
 	int octave, down;/* i and j of ImagePyramid::createLayers */
 	double scale;    /* theoretical scale factor */
@@ -69,6 +70,7 @@ int64_t enumerate_windows(Plan* plan, int patch_w, int patch_h, int step_x, int 
 /* ---- device-side tables ----------------------------------------------------------------- */
 struct ResizeJob {       /* one cv::resize target */
 	int dst_w, dst_h;
+	int dst_pitch;
 	int64_t dst_offset;  /* arena offset */
 	int xtab, ytab;      /* offsets into the coefficient tables */
 	int area2x;          /* 1: exact 2x decimation (INTER_AREA fast path) */
@@ -77,16 +79,17 @@ struct ResizeJob {       /* one cv::resize target */
 
 struct DownJob {         /* one cv::pyrDown */
 	int src_w, src_h, dst_w, dst_h;
+	int src_pitch, dst_pitch;
 	int64_t src_offset, dst_offset; /* arena offsets; src_offset < 0: source is the input frame */
 };
 
 struct DevLayer {        /* per layer, read by the window kernels */
 	int64_t offset;      /* arena offset, or -1 when the layer is the frame itself */
 	int width, height;
+	int pitch;           /* row pitch in bytes */
 	int begin_x, begin_y;
 	int windows_x, windows_y;
 	int first_window;
-	int pad;
 };
 
 #define FDB_MAX_LAYERS 64

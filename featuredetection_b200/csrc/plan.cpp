@@ -71,9 +71,11 @@ int build_plan(const fdb_detector_desc& d, int width, int height, Plan* out) {
 		for (PyrImage& im : chain) {
 			if (im.kind == IMG_PYRDOWN) im.src = prev;
 			if (im.kind != IMG_FRAME) {
+				im.pitch = (int)align_up(im.width, 16); /* 16-byte row pitch: TMA tensor maps need it, word stores like it */
 				im.offset = offset;
-				offset = align_up(offset + (int64_t)im.width * im.height, 16);
+				offset = align_up(offset + (int64_t)im.pitch * im.height, 128);
 			} else {
+				im.pitch = width;
 				im.offset = -1;
 			}
 			p.max_down = std::max(p.max_down, im.down);
@@ -81,7 +83,7 @@ int build_plan(const fdb_detector_desc& d, int width, int height, Plan* out) {
 			prev = (int)p.images.size() - 1;
 		}
 	}
-	p.arena_bytes = std::max<int64_t>(offset, 16);
+	p.arena_bytes = std::max<int64_t>(align_up(offset, 128), 128);
 	for (size_t k = 0; k < p.images.size(); ++k) {
 		const PyrImage& im = p.images[k];
 		if (!im.kept) continue;

@@ -11,7 +11,7 @@
  *   pyrDown 8U: 5x5 [1 4 6 4 1]^2, BORDER_REFLECT_101, (sum + 128) >> 8.
  *
  * Data layout: frames are [n][H][W] u8; every other pyramid image lives at a fixed offset of a
- * per-frame arena (u8, row pitch == width, 16-byte aligned starts).  One launch covers all
+ * per-frame arena (u8, row pitch = width rounded up to 16 bytes, 128-byte aligned starts).  One launch covers all
  * frames of the batch and all images of one dependency level; each thread produces 4 horizontally
  * adjacent output pixels where the width allows and stores them as one 32-bit word.
  */
@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(RS_QX * RS_TY) resize_kernel(const uint8_t* __
 	const uint8_t* __restrict__ src = frames + (int64_t)blockIdx.z * W * H;
 	uint8_t* __restrict__ dst = arena + (int64_t)blockIdx.z * arena_stride + job.dst_offset;
 	const int nvalid = min(4, job.dst_w - dx0);
-	const bool word_store = nvalid == 4 && ((job.dst_w & 3) == 0);
+	const bool word_store = nvalid == 4; /* rows are 16-byte aligned (dst_pitch), dx0 is a multiple of 4 */
 	const int4* __restrict__ xt = xy_tab + job.xtab + dx0;
 	const bool fast = nvalid == 4 && job.words_ok && !job.area2x;
 	int4 t0 = make_int4(0, 0, 0, 0), t1 = t0, t2 = t0, t3 = t0;
@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(RS_QX * RS_TY) resize_kernel(const uint8_t* __
 				}
 			}
 		}
-		uint8_t* o = dst + dy * job.dst_w + dx0;
+		uint8_t* o = dst + dy * job.dst_pitch + dx0;
 		if (word_store) {
 			*reinterpret_cast<uint32_t*>(o) = packed;
 		} else {
@@ -175,13 +175,13 @@ __global__ void __launch_bounds__(PD_BX * PD_BY) pyrdown_kernel(const uint8_t* _
 	int h[7][4];
 	if (interior) {
 #pragma unroll
-		for (int r = 0; r < 7; ++r) pd_hrow_fast(src + (row + r) * job.src_w, col, h[r]);
+		for (int r = 0; r < 7; ++r) pd_hrow_fast(src + (row + r) * job.src_pitch, col, h[r]);
 	} else {
 		int cx[11];
 #pragma unroll
 		for (int i = 0; i < 11; ++i) cx[i] = reflect101(col + i, job.src_w);
 #pragma unroll
-		for (int r = 0; r < 7; ++r) pd_hrow_border(src + reflect101(row + r, job.src_h) * job.src_w, cx, h[r]);
+		for (int r = 0; r < 7; ++r) pd_hrow_border(src + reflect101(row + r, job.src_h) * job.src_pitch, cx, h[r]);
 	}
 	const int nx = min(4, job.dst_w - x0);
 #pragma unroll
@@ -193,8 +193,8 @@ __global__ void __launch_bounds__(PD_BX * PD_BY) pyrdown_kernel(const uint8_t* _
 			const int acc = h[2 * oy][k] + 4 * h[2 * oy + 1][k] + 6 * h[2 * oy + 2][k] + 4 * h[2 * oy + 3][k] + h[2 * oy + 4][k];
 			packed |= (uint32_t)((acc + 128) >> 8) << (8 * k);
 		}
-		uint8_t* o = dst + (y0 + oy) * job.dst_w + x0;
-		if (nx == 4 && (job.dst_w & 3) == 0) {
+		uint8_t* o = dst + (y0 + oy) * job.dst_pitch + x0;
+		if (nx == 4) { /* 16-byte aligned rows, x0 is a multiple of 4 */
 			*reinterpret_cast<uint32_t*>(o) = packed;
 		} else {
 			for (int k = 0; k < nx; ++k) o[k] = (uint8_t)(packed >> (8 * k));

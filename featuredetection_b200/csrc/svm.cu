@@ -42,14 +42,14 @@ __global__ void __launch_bounds__(SVM_THREADS) svm_kernel(const DevSvm s, int pa
 		const SvmItem it = items[item];
 		const DevLayer L = layers[it.layer];
 		const uint8_t* img = (L.offset < 0 ? frames + (int64_t)it.frame * W * H
-				: arena + (int64_t)it.frame * arena_stride + L.offset) + (int64_t)it.y * L.width + it.x;
+				: arena + (int64_t)it.frame * arena_stride + L.offset) + (int64_t)it.y * L.pitch + it.x;
 		const int npix = patch_w * patch_h;
 		if (tid < 64) s_hist[tid] = 0;
 		for (int i = tid; i < s.nwords; i += SVM_THREADS) s_x[i] = 0;
 		__syncthreads();
 		for (int i = tid; i < npix; i += SVM_THREADS) {
 			const int r = i / patch_w, c = i - r * patch_w;
-			atomicAdd(&s_hist[img[(int64_t)r * L.width + c] >> 2], 1u);
+			atomicAdd(&s_hist[img[(int64_t)r * L.pitch + c] >> 2], 1u);
 		}
 		__syncthreads();
 		if (tid == 0) { /* sequential float cumsum, HistEq64Filter.cpp:70-87,97 */
@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(SVM_THREADS) svm_kernel(const DevSvm s, int pa
 		__syncthreads();
 		for (int i = tid; i < npix; i += SVM_THREADS) {
 			const int r = i / patch_w, c = i - r * patch_w;
-			const uint32_t e = s_eq[img[(int64_t)r * L.width + c] >> 2];
+			const uint32_t e = s_eq[img[(int64_t)r * L.pitch + c] >> 2];
 			atomicOr(&s_x[i >> 2], e << (8 * (i & 3)));
 		}
 	} else if (MODE == 1) {

@@ -172,13 +172,13 @@ __global__ void __launch_bounds__(WVM_THREADS) wvm_window_kernel(const DevWvm m,
 		const int iy = local / L.windows_x, ix = local - iy * L.windows_x;
 		const int x = L.begin_x + ix * m.step_x, y = L.begin_y + iy * m.step_y;
 		const uint8_t* __restrict__ img = (L.offset < 0 ? frames + (int64_t)frame * W * H
-				: arena + (int64_t)frame * arena_stride + L.offset) + (int64_t)y * L.width + x;
+				: arena + (int64_t)frame * arena_stride + L.offset) + (int64_t)y * L.pitch + x;
 
 		/* --- HistEq64: 64-bin histogram (HistEq64Filter.cpp:59-67) --- */
 #pragma unroll
 		for (int k = 0; k < 32; ++k) s_hist[k * T + tid] = 0;
 		for (int r = 0; r < ph; ++r) {
-			const uint8_t* row = img + (int64_t)r * L.width;
+			const uint8_t* row = img + (int64_t)r * L.pitch;
 			for (int c = 0; c < pw; ++c) {
 				const int b = row[c] >> 2;
 				s_hist[(b >> 1) * T + tid] += 1u << ((b & 1) * 16);
@@ -205,7 +205,7 @@ __global__ void __launch_bounds__(WVM_THREADS) wvm_window_kernel(const DevWvm m,
 		/* --- apply the LUT, pack 4 pixels per word, accumulate the two integral-image totals --- */
 		uint32_t word = 0; int i = 0;
 		for (int r = 0; r < ph; ++r) {
-			const uint8_t* row = img + (int64_t)r * L.width;
+			const uint8_t* row = img + (int64_t)r * L.pitch;
 			int rowsq = 0;
 			for (int c = 0; c < pw; ++c, ++i) {
 				const int b = row[c] >> 2;

@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(STRIP_T, (PW * PH <= 416 ? STRIP_MIN_CTAS : (P
 	const int tcols = min(st.cols + PW - 1, L.width - tx0);
 	const int trows = min(st.nsub * st.run + PH - 1, L.height - ty0);
 	for (int r = 0; r < trows; ++r) {
-		const uint8_t* row = img + (int64_t)(ty0 + r) * L.width + tx0;
+		const uint8_t* row = img + (int64_t)(ty0 + r) * L.pitch + tx0;
 		for (int c = lane; c < tcols; c += 32) s_tile[r * STRIP_TILE_PITCH + c] = row[c] >> 2;
 	}
 	__syncwarp();
