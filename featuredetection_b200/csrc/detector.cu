@@ -17,6 +17,7 @@
  *                 deep/SVM kernels and the host post-processing of neighbouring chunks overlap.
  * Results are appended in chunk order, i.e. in frame order, exactly as the serial path would.
  */
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -43,6 +44,7 @@ struct Slot {
 	cudaEvent_t ev_stage1 = nullptr, ev_svm = nullptr;
 	uint8_t* d_frames = nullptr;
 	uint8_t* d_arena = nullptr;
+	CUtensorMap* d_tmaps = nullptr; /* one TMA descriptor per pyramid layer of this slot's arena (strip kernel) */
 	fdb_window_score* d_dense = nullptr;
 	int* d_counters = nullptr;     /* [0] candidates, [1] deep queue, [2] deep cursor; followed by the candidate list */
 	Candidate* d_cand = nullptr;   /* = (Candidate*)(d_counters + 4) */
@@ -82,6 +84,7 @@ struct fdb_detector {
 	std::vector<DownJob*> d_down; std::vector<int> n_down; std::vector<int> max_down_px;
 	int4* d_xy_tab = nullptr; /* bilinear tables: {source offset, a0, a1, 0} */
 	Strip* d_strips = nullptr; int n_strips = 0;
+	bool use_tma = false;             /* strip tiles staged by TMA (tensor maps encoded) */
 	bool use_strips = false;          /* fast path usable (and not yet overflowed) */
 	int64_t counts[5] = {0, 0, 0, 0, 0};
 };
@@ -118,6 +121,7 @@ int upload_layers(fdb_detector* det, const Plan& plan, DevLayer* dst, cudaStream
 		L[i].begin_x = p.begin_x; L[i].begin_y = p.begin_y;
 		L[i].windows_x = p.windows_x; L[i].windows_y = p.windows_y;
 		L[i].first_window = (int)p.first_window;
+		L[i].tma_ok = det->use_tma && L[i].offset >= 0 ? 1 : 0;
 	}
 	if (!L.empty())
 		CUDA_TRY(cudaMemcpyAsync(dst, L.data(), sizeof(DevLayer) * L.size(), cudaMemcpyHostToDevice, st));
@@ -151,7 +155,7 @@ int enqueue_stage1(fdb_detector* det, Slot& sl, cudaStream_t st, const uint8_t* 
 		if (det->use_strips && d_layers == det->d_layers && !d_patches) {
 			launch_wvm_strips(st, m, d_frames, W, H, n, sl.d_arena, plan.arena_bytes, d_layers, det->d_strips, det->n_strips,
 					(int)windows, d_dense, want_candidates ? sl.d_cand : nullptr, sl.d_counters, det->cand_cap, sl.deep,
-					marks ? c->ev[5] : nullptr);
+					marks ? c->ev[5] : nullptr, det->use_tma ? sl.d_tmaps : nullptr);
 		} else {
 			if (marks) CUDA_TRY(cudaEventRecord(c->ev[5], st)); /* generic path: no separate deep mark */
 			launch_wvm_windows(st, m, d_frames, W, H, n, sl.d_arena, plan.arena_bytes, d_layers, (int)plan.layers.size(),
@@ -538,6 +542,41 @@ int fdb_detector_prepare(fdb_detector* det, int32_t width, int32_t height, int32
 		s = host_alloc(&sl.h_cand_big, (size_t)det->cand_cap, det->owned_host); if (s) return s;
 		s = host_alloc(&sl.h_items, (size_t)det->items_cap, det->owned_host); if (s) return s;
 		s = host_alloc(&sl.h_dist, (size_t)det->items_cap, det->owned_host); if (s) return s;
+	}
+	/* TMA descriptors for the strip kernel's tiles: layer li of slot i is a 3-D u8 tensor {width, height, chunk}
+	 * with strides {pitch, arena_bytes}; the box is one warp tile. Encoded through the driver entry point
+	 * (no link-time libcuda dependency); when it is missing the kernel stages tiles with plain loads. */
+	det->use_tma = false;
+	{
+		typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+				const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+				CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+		void* fn = nullptr;
+		cudaDriverEntryPointQueryResult qres = cudaDriverEntryPointSymbolNotFound;
+		const char* env = std::getenv("FDB_NO_TMA");
+		if (!(env && env[0] == '1') && strip_supported(det->desc.patch_width, det->desc.patch_height)
+				&& cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess
+				&& qres == cudaDriverEntryPointSuccess && fn) {
+			bool ok = true;
+			for (int i = 0; i < det->n_slots && ok; ++i) {
+				Slot& sl = det->slots[i];
+				std::vector<CUtensorMap> maps(plan.layers.size());
+				std::memset(maps.data(), 0, sizeof(CUtensorMap) * maps.size());
+				for (size_t li = 0; li < plan.layers.size() && ok; ++li) {
+					const PyrImage& im = plan.images[plan.layers[li].image];
+					if (im.offset < 0) continue; /* the frame itself: plain loads */
+					const cuuint64_t dims[3] = {(cuuint64_t)im.width, (cuuint64_t)im.height, (cuuint64_t)det->chunk};
+					const cuuint64_t strides[2] = {(cuuint64_t)im.pitch, (cuuint64_t)plan.arena_bytes};
+					const cuuint32_t box[3] = {(cuuint32_t)strip_tile_pitch(), (cuuint32_t)strip_tile_rows(det->desc.patch_height), 1};
+					const cuuint32_t estr[3] = {1, 1, 1};
+					ok = reinterpret_cast<EncodeFn>(fn)(&maps[li], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, sl.d_arena + im.offset,
+							dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+							CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+				}
+				if (ok) { s = upload(maps.data(), maps.size(), &sl.d_tmaps, det->owned); if (s) return s; }
+			}
+			det->use_tma = ok;
+		}
 	}
 	s = dev_alloc(&det->d_layers, FDB_MAX_LAYERS, det->owned); if (s) return s;
 	s = dev_alloc(&det->d_layers_roi, FDB_MAX_LAYERS, det->owned); if (s) return s;

@@ -90,6 +90,7 @@ struct DevLayer {        /* per layer, read by the window kernels */
 	int begin_x, begin_y;
 	int windows_x, windows_y;
 	int first_window;
+	int tma_ok;          /* a TMA tensor map exists for this layer (arena image, 16-byte pitch) */
 };
 
 #define FDB_MAX_LAYERS 64

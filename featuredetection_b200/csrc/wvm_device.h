@@ -93,7 +93,9 @@ bool strip_supported(int patch_w, int patch_h);
 void launch_wvm_strips(cudaStream_t st, const DevWvm& m, const uint8_t* frames, int W, int H, int n_frames,
 		const uint8_t* arena, int64_t arena_stride, const DevLayer* layers, const Strip* strips, int n_strips,
 		int windows_per_frame, fdb_window_score* dense, Candidate* cand, int* cand_count, int cand_cap, const DeepQueue& q,
-		cudaEvent_t ev_mid = nullptr);
+		cudaEvent_t ev_mid = nullptr, const void* tmaps = nullptr /* CUtensorMap[layer] of the slot's arena, or null */);
+int strip_tile_rows(int patch_h);
+int strip_tile_pitch();
 
 void launch_resize(cudaStream_t st, const uint8_t* frames, int W, int H, int n_frames, uint8_t* arena,
 		int64_t arena_stride, const ResizeJob* jobs_dev, int n_jobs, int max_tiles, const int4* xy_tab);

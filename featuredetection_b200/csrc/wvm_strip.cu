@@ -24,6 +24,7 @@
  *   chains, then a ballot finds the first filter that rejects.  Filters past the rejecting one are
  *   computed speculatively and discarded, so results equal the sequential cascade exactly.
  */
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <algorithm>
 #include <cstdint>
@@ -43,7 +44,7 @@ namespace fdb {
 template <int PW, int PH>
 struct StripCfg {
 	static constexpr int NW = PW * PH / 4;
-	static constexpr int TILE_ROWS = WVM_MAXSUB * WVM_RUN + PH - 1;
+	static constexpr int TILE_ROWS = (WVM_MAXSUB * WVM_RUN + PH - 1 + 1) & ~1; /* even: each warp's tile is a multiple of 128 bytes (TMA destination) */
 	static constexpr size_t SMEM = (size_t)(64 + 64) * STRIP_T * 2 + (size_t)4 * TILE_ROWS * STRIP_TILE_PITCH;
 };
 
@@ -53,12 +54,14 @@ __global__ void __launch_bounds__(STRIP_T, (PW * PH <= 416 ? STRIP_MIN_CTAS : (P
 		const uint8_t* __restrict__ arena, int64_t arena_stride,
 		const DevLayer* __restrict__ layers, const Strip* __restrict__ strips, int n_strips, int windows_per_frame,
 		fdb_window_score* __restrict__ dense,
-		Candidate* __restrict__ cand, int* __restrict__ cand_count, int cand_cap, const DeepQueue q) {
+		Candidate* __restrict__ cand, int* __restrict__ cand_count, int cand_cap, const DeepQueue q,
+		const CUtensorMap* __restrict__ tmaps) {
 	static_assert(PW % 4 == 0 && PW <= 32, "patch width must be a multiple of 4, at most 32");
 	constexpr int NW = StripCfg<PW, PH>::NW;
 	constexpr int WPR = PW / 4; /* words per patch row */
 	constexpr int T = STRIP_T;
-	extern __shared__ uint32_t smem[];
+	extern __shared__ __align__(1024) uint32_t smem[];
+	__shared__ __align__(8) uint64_t s_mbar[4];
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	uint16_t* const s_hist = reinterpret_cast<uint16_t*>(smem) + tid;          /* [64][T] u16 counts -> bin b at s_hist[b*T] */
 	uint16_t* const s_lut = reinterpret_cast<uint16_t*>(smem) + 64 * T + tid;  /* [64][T] u16 equalised values */
@@ -75,9 +78,32 @@ __global__ void __launch_bounds__(STRIP_T, (PW * PH <= 416 ? STRIP_MIN_CTAS : (P
 	const int tx0 = L.begin_x + st.ix0, ty0 = L.begin_y + st.iy0;
 	const int tcols = min(st.cols + PW - 1, L.width - tx0);
 	const int trows = min(st.nsub * st.run + PH - 1, L.height - ty0);
-	for (int r = 0; r < trows; ++r) {
-		const uint8_t* row = img + (int64_t)(ty0 + r) * L.pitch + tx0;
-		for (int c = lane; c < tcols; c += 32) s_tile[r * STRIP_TILE_PITCH + c] = row[c] >> 2;
+	if (tmaps != nullptr && L.tma_ok) {
+		/* TMA: one bulk tensor copy (64 bytes x TILE_ROWS rows of the layer, zero-filled outside the image)
+		 * lands the tile in shared memory and signals the warp's mbarrier */
+		const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s_mbar[warp]);
+		const uint32_t dst = (uint32_t)__cvta_generic_to_shared(s_tile);
+		if (lane == 0) {
+			asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar));
+			asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+			asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(StripCfg<PW, PH>::TILE_ROWS * STRIP_TILE_PITCH) : "memory");
+			asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+					:: "r"(dst), "l"(reinterpret_cast<uint64_t>(tmaps + st.layer)), "r"(tx0), "r"(ty0), "r"(frame), "r"(bar) : "memory");
+		}
+		__syncwarp();
+		uint32_t done = 0;
+		while (!done) {
+			asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+					: "=r"(done) : "r"(bar) : "memory");
+		}
+		/* pixels -> bins, in place, 4 per word */
+		uint32_t* const tw32 = reinterpret_cast<uint32_t*>(s_tile);
+		for (int i = lane; i < trows * (STRIP_TILE_PITCH / 4); i += 32) tw32[i] = (tw32[i] >> 2) & 0x3f3f3f3fu;
+	} else {
+		for (int r = 0; r < trows; ++r) {
+			const uint8_t* row = img + (int64_t)(ty0 + r) * L.pitch + tx0;
+			for (int c = lane; c < tcols; c += 32) s_tile[r * STRIP_TILE_PITCH + c] = row[c] >> 2;
+		}
 	}
 	__syncwarp();
 	const int col = lane % st.cols, sub = lane / st.cols;
@@ -341,19 +367,21 @@ bool strip_supported(int pw, int ph) {
 template <int PW, int PH>
 static void strip_launch(cudaStream_t st, const DevWvm& m, const uint8_t* frames, int W, int H, int n_frames,
 		const uint8_t* arena, int64_t arena_stride, const DevLayer* layers, const Strip* strips, int n_strips,
-		int windows_per_frame, fdb_window_score* dense, Candidate* cand, int* cand_count, int cand_cap, const DeepQueue& q) {
+		int windows_per_frame, fdb_window_score* dense, Candidate* cand, int* cand_count, int cand_cap, const DeepQueue& q,
+		const CUtensorMap* tmaps) {
 	dim3 grid((unsigned)((n_strips + 3) / 4), (unsigned)n_frames);
 	wvm_strip_kernel<PW, PH><<<grid, STRIP_T, StripCfg<PW, PH>::SMEM, st>>>(m, frames, W, H, arena, arena_stride, layers, strips,
-			n_strips, windows_per_frame, dense, cand, cand_count, cand_cap, q);
+			n_strips, windows_per_frame, dense, cand, cand_count, cand_cap, q, tmaps);
 }
 
 void launch_wvm_strips(cudaStream_t st, const DevWvm& m, const uint8_t* frames, int W, int H, int n_frames,
 		const uint8_t* arena, int64_t arena_stride, const DevLayer* layers, const Strip* strips, int n_strips,
 		int windows_per_frame, fdb_window_score* dense, Candidate* cand, int* cand_count, int cand_cap, const DeepQueue& q,
-		cudaEvent_t ev_mid) {
+		cudaEvent_t ev_mid, const void* tmaps_v) {
 	if (n_strips == 0 || n_frames == 0) return;
+	const CUtensorMap* tmaps = reinterpret_cast<const CUtensorMap*>(tmaps_v);
 #define FDB_STRIP_CASE(PW, PH) if (m.fsx == PW && m.fsy == PH) { strip_launch<PW, PH>(st, m, frames, W, H, n_frames, arena, arena_stride, \
-		layers, strips, n_strips, windows_per_frame, dense, cand, cand_count, cand_cap, q); }
+		layers, strips, n_strips, windows_per_frame, dense, cand, cand_count, cand_cap, q, tmaps); }
 	FDB_STRIP_CASE(20, 20) else FDB_STRIP_CASE(24, 24) else FDB_STRIP_CASE(32, 16) else FDB_STRIP_CASE(32, 24) else FDB_STRIP_CASE(16, 24)
 #undef FDB_STRIP_CASE
 	if (ev_mid) cudaEventRecord(ev_mid, st); /* profiling mark between the two kernels */
@@ -362,3 +390,8 @@ void launch_wvm_strips(cudaStream_t st, const DevWvm& m, const uint8_t* frames, 
 }
 
 } // namespace fdb
+
+namespace fdb {
+int strip_tile_rows(int patch_h) { return (WVM_MAXSUB * WVM_RUN + patch_h - 1 + 1) & ~1; }
+int strip_tile_pitch() { return STRIP_TILE_PITCH; }
+}
