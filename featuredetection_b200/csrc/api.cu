@@ -73,7 +73,7 @@ int fdb_ctx_create(int device, fdb_ctx** out) {
 	c->device = device;
 	CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
 	for (cudaEvent_t& e : c->ev) CUDA_TRY(cudaEventCreate(&e));
-	if (wvm_configure() != 0 || svm_configure() != 0 || strip_configure_all() != 0) {
+	if (wvm_configure() != 0 || svm_configure() != 0 || strip_configure_all() != 0 || strip_mma_configure_all() != 0) {
 		cudaStreamDestroy(c->stream); delete c;
 		return fail(FDB_ERR_CUDA, "cudaFuncSetAttribute failed: libfdb200 kernels not loadable on this device");
 	}
@@ -233,6 +233,7 @@ int fdb_wvm_create(fdb_ctx* ctx, const fdb_wvm_desc* d, fdb_wvm** out) {
 		UP(row4.data(), n, hk_row4, ip);
 	}
 	dv.masks4 = nullptr;
+	dv.bfrag = nullptr;
 	if (max_nv <= 4) { /* padded copy for the strip / deep-warp kernels: [filter][word][4] */
 		std::vector<uint32_t> m4((size_t)n * nwords * 4, 0u);
 		for (int f = 0; f < n; ++f) {
@@ -241,6 +242,24 @@ int fdb_wvm_create(fdb_ctx* ctx, const fdb_wvm_desc* d, fdb_wvm** out) {
 				for (int v = 0; v < nv; ++v) m4[((size_t)f * nwords + j) * 4 + v] = masks[(size_t)mask_off[f] + (size_t)j * nv + v];
 		}
 		UP(m4.data(), m4.size(), masks4, up);
+		/* the same masks of the first WVM_KA filters in mma.m16n8k32 B-fragment order (wvm_strip_mma.cu): lane (g, t)
+		 * of k-step s holds, for n-tile nt, the words j = 8 s + t and j + 4 of filter 2 nt + (g >> 2), value g & 3 */
+		dv.bfrag = nullptr;
+		if (n >= WVM_KA) {
+			const int ks = (nwords + 7) / 8;
+			std::vector<uint32_t> bf((size_t)ks * 32 * 8, 0u);
+			for (int s2 = 0; s2 < ks; ++s2)
+				for (int lane = 0; lane < 32; ++lane)
+					for (int nt = 0; nt < 4; ++nt)
+						for (int h = 0; h < 2; ++h) {
+							const int g = lane >> 2, t = lane & 3;
+							const int f = 2 * nt + (g >> 2), v = g & 3, j = 8 * s2 + 4 * h + t;
+							if (j < nwords) bf[((size_t)s2 * 32 + lane) * 8 + nt * 2 + h] = m4[((size_t)f * nwords + j) * 4 + v];
+						}
+			uint32_t* bp;
+			s = upload(bf.data(), bf.size(), &bp, m->owned); if (s) { free_all(m->owned); delete m; return s; }
+			dv.bfrag = reinterpret_cast<const uint4*>(bp);
+		}
 	}
 #undef UP
 	s = dev_alloc(&m->d_thresholds, (size_t)n, m->owned);

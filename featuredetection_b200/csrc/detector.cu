@@ -590,12 +590,15 @@ int fdb_detector_prepare(fdb_detector* det, int32_t width, int32_t height, int32
 		for (size_t li = 0; li < plan.layers.size(); ++li) {
 			const PlanLayer& L = plan.layers[li];
 			if (L.windows_x == 0) continue;
-			/* balanced run length: the same number of window rows for every lane of the layer */
-			const int nruns = (L.windows_y + WVM_RUN - 1) / WVM_RUN;
-			const int run = (L.windows_y + nruns - 1) / nruns;
+			const int budget = strip_tile_rows(det->desc.patch_height) - (det->desc.patch_height - 1); /* window rows per tile */
 			for (int ix0 = 0; ix0 < L.windows_x; ix0 += 32) {
 				const int cols = std::min(32, L.windows_x - ix0);
+				/* narrow layers pack several row runs side by side (all 32 lanes busy); the runs share the tile's rows.
+				 * Balanced run length: the same number of window rows for every lane of the layer */
 				const int nsub = std::min(WVM_MAXSUB, 32 / cols);
+				const int run_cap = std::max(1, std::min(WVM_RUN, budget / nsub));
+				const int nruns = (L.windows_y + run_cap - 1) / run_cap;
+				const int run = (L.windows_y + nruns - 1) / nruns;
 				for (int iy0 = 0; iy0 < L.windows_y; iy0 += nsub * run) {
 					Strip st{};
 					st.layer = (int)li; st.ix0 = ix0; st.iy0 = iy0; st.cols = cols; st.run = run;

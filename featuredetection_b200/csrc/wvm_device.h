@@ -50,6 +50,7 @@ struct DevWvm {
 	const double* val;              /* grey values */
 	const uint32_t* masks;          /* rectangle coverage counts, 4 pixels per word: filter f at mask_off[f], [nwords][cntval-1] */
 	const int* mask_off;            /* [num_lin] */
+	const uint4* bfrag;             /* masks of the first WVM_KA filters as mma.m16n8k32 B fragments: [k-step][lane][2] (wvm_strip_mma.cu); nullptr if unavailable */
 	const uint32_t* masks4;         /* same, padded to 4 values per word: [num_lin][nwords][4]; nullptr if a filter has > 4 */
 	const float* hk_weights4;       /* hkWeights rows padded to multiples of 4 floats (16-byte aligned rows) */
 	const int* hk_row4;             /* [num_lin] start of row l in hk_weights4 (floats) */
@@ -62,6 +63,7 @@ struct DevWvm {
 #define WVM_RUN 12   /* longest run of window rows one lane walks down */
 #endif
 #define WVM_MAXSUB 4
+#define STRIP_TILE_ROWS 42 /* rows of a warp's bin tile: nsub * run + patch_h - 1 <= 42 (3 CTAs of 4 warps per SM) */
 struct Strip {
 	int layer;      /* index into the DevLayer table */
 	int ix0, iy0;   /* first window column / row of the strip */
@@ -89,6 +91,12 @@ void launch_wvm_patches(cudaStream_t st, const DevWvm& m, const uint8_t* patches
 
 /* fast path (wvm_strip.cu): whole-image scans with step 1 and one of the ffpDetectApp patch sizes */
 int strip_configure_all();
+int strip_mma_configure_all();
+int strip_mma_ksteps(int patch_w, int patch_h);
+bool launch_strip_mma(cudaStream_t st, const DevWvm& m, const uint8_t* frames, int W, int H, int n_frames,
+		const uint8_t* arena, int64_t arena_stride, const DevLayer* layers, const Strip* strips, int n_strips,
+		int windows_per_frame, fdb_window_score* dense, Candidate* cand, int* cand_count, int cand_cap, const DeepQueue& q,
+		const void* tmaps);
 bool strip_supported(int patch_w, int patch_h);
 void launch_wvm_strips(cudaStream_t st, const DevWvm& m, const uint8_t* frames, int W, int H, int n_frames,
 		const uint8_t* arena, int64_t arena_stride, const DevLayer* layers, const Strip* strips, int n_strips,

@@ -28,6 +28,7 @@
 #include <cuda_runtime.h>
 #include <algorithm>
 #include <cstdint>
+#include <cstdlib>
 
 #include "fdb_internal.h"
 #include "wvm_device.h"
@@ -44,7 +45,7 @@ namespace fdb {
 template <int PW, int PH>
 struct StripCfg {
 	static constexpr int NW = PW * PH / 4;
-	static constexpr int TILE_ROWS = (WVM_MAXSUB * WVM_RUN + PH - 1 + 1) & ~1; /* even: each warp's tile is a multiple of 128 bytes (TMA destination) */
+	static constexpr int TILE_ROWS = STRIP_TILE_ROWS; /* even: each warp's tile is a multiple of 128 bytes (TMA destination) */
 	static constexpr size_t SMEM = (size_t)(64 + 64) * STRIP_T * 2 + (size_t)4 * TILE_ROWS * STRIP_TILE_PITCH;
 };
 
@@ -380,10 +381,14 @@ void launch_wvm_strips(cudaStream_t st, const DevWvm& m, const uint8_t* frames, 
 		cudaEvent_t ev_mid, const void* tmaps_v) {
 	if (n_strips == 0 || n_frames == 0) return;
 	const CUtensorMap* tmaps = reinterpret_cast<const CUtensorMap*>(tmaps_v);
+	static const bool use_mma = []{ const char* e = std::getenv("FDB_STRIP_V1"); return !(e && e[0] == '1'); }();
+	if (!(use_mma && launch_strip_mma(st, m, frames, W, H, n_frames, arena, arena_stride, layers, strips, n_strips,
+			windows_per_frame, dense, cand, cand_count, cand_cap, q, tmaps_v))) {
 #define FDB_STRIP_CASE(PW, PH) if (m.fsx == PW && m.fsy == PH) { strip_launch<PW, PH>(st, m, frames, W, H, n_frames, arena, arena_stride, \
 		layers, strips, n_strips, windows_per_frame, dense, cand, cand_count, cand_cap, q, tmaps); }
 	FDB_STRIP_CASE(20, 20) else FDB_STRIP_CASE(24, 24) else FDB_STRIP_CASE(32, 16) else FDB_STRIP_CASE(32, 24) else FDB_STRIP_CASE(16, 24)
 #undef FDB_STRIP_CASE
+	}
 	if (ev_mid) cudaEventRecord(ev_mid, st); /* profiling mark between the two kernels */
 	const int blocks = std::min((q.cap + DEEP_WARPS - 1) / DEEP_WARPS, 148 * 8);
 	wvm_deep_warp_kernel<<<blocks, DEEP_WARPS * 32, 0, st>>>(m, q, windows_per_frame, dense, cand, cand_count, cand_cap);
@@ -392,6 +397,6 @@ void launch_wvm_strips(cudaStream_t st, const DevWvm& m, const uint8_t* frames, 
 } // namespace fdb
 
 namespace fdb {
-int strip_tile_rows(int patch_h) { return (WVM_MAXSUB * WVM_RUN + patch_h - 1 + 1) & ~1; }
+int strip_tile_rows(int patch_h) { (void)patch_h; return STRIP_TILE_ROWS; }
 int strip_tile_pitch() { return STRIP_TILE_PITCH; }
 }
