@@ -13,6 +13,10 @@ FDB_OK = 0
 FDB_STAGE_WVM, FDB_STAGE_OE, FDB_STAGE_SVM, FDB_STAGE_NMS = 1, 2, 3, 4
 FDB_SV_U8, FDB_SV_F32 = 0, 1
 FDB_KERNEL_RBF = 0
+(FDB_FEATURE_HQ64, FDB_FEATURE_GRAY, FDB_FEATURE_HISTEQ, FDB_FEATURE_WHI, FDB_FEATURE_HOG, FDB_FEATURE_EHOG,
+ FDB_FEATURE_LBP) = range(7)
+FDB_NORM_NONE, FDB_NORM_L2NORM, FDB_NORM_L2HYS, FDB_NORM_L1NORM, FDB_NORM_L1SQRT = range(5)
+FDB_LBP8, FDB_LBP8_UNIFORM, FDB_LBP4, FDB_LBP4_ROTATED = range(4)
 
 
 class Rect4(C.Structure):
@@ -56,6 +60,16 @@ class DetectorDesc(C.Structure):
         ("step_x", C.c_int32), ("step_y", C.c_int32),
         ("oe_dist", C.c_float), ("oe_ratio", C.c_float),
         ("max_positives_per_frame", C.c_int32),
+    ]
+
+
+class FeatureDesc(C.Structure):
+    _fields_ = [
+        ("kind", C.c_int32), ("gradient_kernel", C.c_int32), ("blur_kernel", C.c_int32), ("bins", C.c_int32),
+        ("signed_gradients", C.c_int32), ("interpolate_bins", C.c_int32), ("cell_size", C.c_int32),
+        ("block_size", C.c_int32), ("interpolate_cells", C.c_int32), ("concatenate", C.c_int32),
+        ("signed_and_unsigned", C.c_int32), ("normalization", C.c_int32), ("lbp_type", C.c_int32),
+        ("ehog_alpha", C.c_float), ("whi_alpha", C.c_float), ("whi_cutoff", C.c_float),
     ]
 
 

@@ -268,3 +268,48 @@ def detector_desc(**kw):
     for k, v in kw.items():
         setattr(d, k, v)
     return d
+
+
+# ------------------------------------------------------------------------------------------------
+# feature spaces (parameters of adaptiveTrackingApp/default.cfg:105-129,148-155)
+# ------------------------------------------------------------------------------------------------
+FEATURE_KINDS = {"hq64": capi.FDB_FEATURE_HQ64, "gray": capi.FDB_FEATURE_GRAY, "histeq": capi.FDB_FEATURE_HISTEQ,
+                 "whi": capi.FDB_FEATURE_WHI, "hog": capi.FDB_FEATURE_HOG, "ehog": capi.FDB_FEATURE_EHOG,
+                 "lbp": capi.FDB_FEATURE_LBP}
+NORMALIZATIONS = {"none": capi.FDB_NORM_NONE, "l2norm": capi.FDB_NORM_L2NORM, "l2hys": capi.FDB_NORM_L2HYS,
+                  "l1norm": capi.FDB_NORM_L1NORM, "l1sqrt": capi.FDB_NORM_L1SQRT}
+LBP_TYPES = {"lbp8": capi.FDB_LBP8, "lbp8uniform": capi.FDB_LBP8_UNIFORM, "lbp4": capi.FDB_LBP4,
+             "lbp4rotated": capi.FDB_LBP4_ROTATED}
+# rbf gamma per feature space (adaptiveTrackingApp/default.cfg:148-155)
+FEATURE_GAMMA = {"hq64": 7.689e-7, "gray": 7.689e-7, "histeq": 7.689e-7, "whi": 0.002, "hog": 0.2, "ehog": 0.2, "lbp": 0.6}
+
+
+def feature_desc(kind="hq64", gradient_kernel=1, blur_kernel=0, bins=9, signed_gradients=False, interpolate_bins=True,
+                 cell_size=5, block_size=1, interpolate_cells=False, concatenate=False, signed_and_unsigned=False,
+                 normalization="l2norm", lbp_type="lbp8uniform", ehog_alpha=0.2, whi_alpha=1.0, whi_cutoff=0.390625):
+    """fdb_feature_desc with the canonical parameters of the reference's cfg files as defaults."""
+    d = capi.FeatureDesc()
+    d.kind = FEATURE_KINDS[kind] if isinstance(kind, str) else kind
+    d.gradient_kernel, d.blur_kernel, d.bins = gradient_kernel, blur_kernel, bins
+    d.signed_gradients, d.interpolate_bins = int(signed_gradients), int(interpolate_bins)
+    d.cell_size, d.block_size = cell_size, block_size
+    d.interpolate_cells, d.concatenate, d.signed_and_unsigned = int(interpolate_cells), int(concatenate), int(signed_and_unsigned)
+    d.normalization = NORMALIZATIONS[normalization] if isinstance(normalization, str) else normalization
+    d.lbp_type = LBP_TYPES[lbp_type] if isinstance(lbp_type, str) else lbp_type
+    d.ehog_alpha, d.whi_alpha, d.whi_cutoff = ehog_alpha, whi_alpha, whi_cutoff
+    return d
+
+
+def make_feature_svm(vectors, seed, num_sv=1024, gamma=0.2):
+    """RBF SVM whose support vectors are drawn (seeded) from the given feature vectors [n, dim] (u8 or f32):
+    SURVEY.md 8(d) - coefficients ~ N(0,1) float32, bias 0, threshold 0, logistic defaults."""
+    rng = np.random.default_rng(seed)
+    vectors = np.ascontiguousarray(vectors)
+    idx = rng.integers(0, vectors.shape[0], num_sv)
+    sv = vectors[idx].copy()
+    if sv.dtype != np.uint8:
+        # decorrelate: blend pairs so support vectors are not exact copies of scanned windows
+        idx2 = rng.integers(0, vectors.shape[0], num_sv)
+        sv = (np.float32(0.5) * (sv.astype(np.float32) + vectors[idx2].astype(np.float32))).astype(np.float32)
+    coef = rng.standard_normal(num_sv).astype(np.float32)
+    return SvmModel(sv, coef, gamma=gamma)

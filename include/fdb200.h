@@ -141,6 +141,55 @@ typedef struct fdb_detector_desc {
 	int32_t max_positives_per_frame; /* capacity of the per-frame stage-1 candidate list; 0 = default 4096 */
 } fdb_detector_desc;
 
+/* Feature space of a classifier = the patch-filter chain (and pyramid layer filters) the reference
+ * attaches to its feature extractor:
+ *   hq64 / gray / histeq / whi   ffpDetectApp.cpp:446-461 ("feature" node of a `single` detector) and
+ *                                patchConverter.cpp:218-227
+ *   hog / ehog / lbp             adaptiveTrackingApp/AdaptiveTracking.cpp:183-204,222-227 (+ createHogFilter
+ *                                :241-253, createLbpFilter :255-268, createHistogramFilter :270-292), parameters as
+ *                                in adaptiveTrackingApp/default.cfg:105-129 */
+typedef enum fdb_feature_kind {
+	FDB_FEATURE_HQ64 = 0,   /* HistEq64Filter (HistEq64Filter.cpp:32-125); u8, w*h */
+	FDB_FEATURE_GRAY = 1,   /* no patch filter; u8, w*h */
+	FDB_FEATURE_HISTEQ = 2, /* HistogramEqualizationFilter = cv::equalizeHist (HistogramEqualizationFilter.cpp:17-20); u8, w*h */
+	FDB_FEATURE_WHI = 3,    /* WhiteningFilter (WhiteningFilter.cpp:20-81) + HistogramEqualizationFilter +
+	                         * ConversionFilter(CV_32F, 1/127.5, -1) + UnitNormFilter(NORM_L2); f32, w*h */
+	FDB_FEATURE_HOG = 4,    /* layer filters GradientFilter (GradientFilter.cpp:38-59) + GradientBinningFilter
+	                         * (GradientBinningFilter.cpp:18-92); patch filter SpatialHistogramFilter
+	                         * (SpatialHistogramFilter.cpp:56-94) when block_size == 1 and !signed_and_unsigned,
+	                         * else HogFilter (HogFilter.cpp:58-122); f32 */
+	FDB_FEATURE_EHOG = 5,   /* same layer filters; patch filter ExtendedHogFilter (ExtendedHogFilter.cpp:54-209); f32 */
+	FDB_FEATURE_LBP = 6     /* layer filter LbpFilter (LbpFilter.cpp:56-85, LbpFilter.hpp:88-178); patch filter
+	                         * SpatialHistogramFilter; f32 */
+} fdb_feature_kind;
+
+typedef enum fdb_normalization { /* HistogramFilter::Normalization (HistogramFilter.hpp:26, HistogramFilter.cpp:222-252) */
+	FDB_NORM_NONE = 0, FDB_NORM_L2NORM = 1, FDB_NORM_L2HYS = 2, FDB_NORM_L1NORM = 3, FDB_NORM_L1SQRT = 4
+} fdb_normalization;
+
+typedef enum fdb_lbp_type { /* LbpFilter::Type */
+	FDB_LBP8 = 0, FDB_LBP8_UNIFORM = 1, FDB_LBP4 = 2, FDB_LBP4_ROTATED = 3
+} fdb_lbp_type;
+
+typedef struct fdb_feature_desc {
+	int32_t kind;                /* fdb_feature_kind */
+	int32_t gradient_kernel;     /* hog/ehog: GradientFilter kernelSize, 1 or 3 (cfg gradientKernel) */
+	int32_t blur_kernel;         /* hog/ehog: GradientFilter blurKernelSize; only 0 is supported */
+	int32_t bins;                /* hog/ehog: GradientBinningFilter bins */
+	int32_t signed_gradients;    /* hog/ehog: cfg "signed" */
+	int32_t interpolate_bins;    /* hog/ehog: cfg "interpolate" (two bins per pixel) */
+	int32_t cell_size;           /* histogram.cellSize */
+	int32_t block_size;          /* histogram.blockSize */
+	int32_t interpolate_cells;   /* histogram.interpolate (bilinear between cells) */
+	int32_t concatenate;         /* histogram.concatenate (SpatialHistogramFilter blocks) */
+	int32_t signed_and_unsigned; /* histogram.signedAndUnsigned */
+	int32_t normalization;       /* fdb_normalization (SpatialHistogramFilter) */
+	int32_t lbp_type;            /* fdb_lbp_type */
+	float ehog_alpha;            /* histogram.alpha (ExtendedHogFilter clamp) */
+	float whi_alpha;             /* WhiteningFilter alpha (default 1) */
+	float whi_cutoff;            /* WhiteningFilter cutoffFrequency (default 0.390625) */
+} fdb_feature_desc;
+
 /* ------------------------------------------------------------------------------------------
  * Result records
  * ---------------------------------------------------------------------------------------- */

@@ -650,6 +650,53 @@ int64_t fdo_detect_frame(const fdb_detector_desc* desc, const fdo_wvm* wvm, cons
 		int roi_x, int roi_y, int roi_w, int roi_h, int stage,
 		fdb_window_score* dense_out, uint8_t* patches_out,
 		fdb_detection* det_out, int64_t det_cap, int64_t counts_out[5], double* timing_out) {
+	return fdo_detect_frame_ex(desc, wvm, svm, NULL, frame, width, height, pitch, frame_index, roi_x, roi_y, roi_w, roi_h,
+			stage, dense_out, patches_out, NULL, det_out, det_cap, counts_out, timing_out);
+}
+
+/* filtered copies of all pyramid layers (layer filters of the feature space), or NULL when it has none */
+static uint8_t** filter_layers(const fdo_pyramid* pyr, const fdo_features* f) {
+	if (!f || fdo_features_layer_channels(f) == 0) return NULL;
+	uint8_t** out = (uint8_t**)calloc((size_t)pyr->n_layers, sizeof(uint8_t*));
+	for (int li = 0; li < pyr->n_layers; ++li) {
+		const fdo_layer* L = &pyr->layers[li];
+		out[li] = (uint8_t*)malloc((size_t)L->width * L->height * fdo_features_layer_channels(f));
+		fdo_features_filter_layer(f, L->data, L->width, L->height, out[li]);
+	}
+	return out;
+}
+
+static void free_layers(uint8_t** fl, int n) {
+	if (!fl) return;
+	for (int i = 0; i < n; ++i) free(fl[i]);
+	free(fl);
+}
+
+int fdo_extract_features(const fdb_detector_desc* desc, const fdo_features* f, const uint8_t* frame, int width, int height,
+		int pitch, const int32_t* layer_x_y, int64_t n, void* out) {
+	fdo_pyramid* pyr = fdo_pyramid_build(frame, width, height, pitch, desc->incremental_scale_factor,
+			desc->min_scale_factor, desc->max_scale_factor);
+	if (!pyr) return -2;
+	uint8_t** fl = filter_layers(pyr, f);
+	const size_t es = fdo_features_is_float(f) ? 4 : 1;
+	int rc = 0;
+	for (int64_t i = 0; i < n && rc == 0; ++i) {
+		int li = -1;
+		for (int k = 0; k < pyr->n_layers; ++k) if (pyr->layers[k].index == layer_x_y[3 * i]) li = k;
+		if (li < 0) { rc = -1; break; }
+		fdo_features_patch(f, fl ? fl[li] : pyr->layers[li].data, pyr->layers[li].width, layer_x_y[3 * i + 1], layer_x_y[3 * i + 2],
+				(uint8_t*)out + (size_t)i * fdo_features_dim(f) * es);
+	}
+	free_layers(fl, pyr->n_layers);
+	fdo_pyramid_free(pyr);
+	return rc;
+}
+
+int64_t fdo_detect_frame_ex(const fdb_detector_desc* desc, const fdo_wvm* wvm, const fdo_svm* svm, const fdo_features* svm_features,
+		const uint8_t* frame, int width, int height, int pitch, int frame_index,
+		int roi_x, int roi_y, int roi_w, int roi_h, int stage,
+		fdb_window_score* dense_out, uint8_t* patches_out, double* svm_dense_out,
+		fdb_detection* det_out, int64_t det_cap, int64_t counts_out[5], double* timing_out) {
 	double t0 = now_s();
 	int is_roi = !(roi_x == 0 && roi_y == 0 && roi_w == 0 && roi_h == 0);
 	fdo_pyramid* pyr = fdo_pyramid_build(frame, width, height, pitch, desc->incremental_scale_factor,
@@ -666,6 +713,8 @@ int64_t fdo_detect_frame(const fdb_detector_desc* desc, const fdo_wvm* wvm, cons
 	double t_hq = 0, t_wvm = 0;
 	uint8_t* patch = (uint8_t*)malloc((size_t)pw * ph);
 	int overflow = 0;
+	uint8_t** flayers = filter_layers(pyr, svm_features);
+	void* fvec = svm_features ? malloc((size_t)fdo_features_dim(svm_features) * 4) : NULL;
 	/* stage 1: SlidingWindowDetector::detect() (SlidingWindowDetector.cpp:87-98) */
 	for (int li = 0; li < pyr->n_layers; ++li) {
 		const fdo_layer* L = &pyr->layers[li];
@@ -675,6 +724,25 @@ int64_t fdo_detect_frame(const fdb_detector_desc* desc, const fdo_wvm* wvm, cons
 			for (int ix = 0; ix < I->windows_x; ++ix) {
 				int x = bx + ix * sx, y = by + iy * sy;
 				int64_t w = I->first_window + (int64_t)iy * I->windows_x + ix;
+				if (!wvm) {
+					/* `single` detector with a psvm classifier (ffpDetectApp.cpp:427-500): feature chain, then
+					 * ProbabilisticSvmClassifier::getProbability (ProbabilisticSvmClassifier.cpp:50-58) */
+					if (svm_features) fdo_features_patch(svm_features, flayers ? flayers[li] : L->data, L->width, x, y, fvec);
+					else fdo_hq64(L->data + (size_t)y * L->width + x, L->width, pw, ph, patch);
+					const double dist = fdo_svm_distance(svm, svm_features ? fvec : (void*)patch);
+					if (svm_dense_out) svm_dense_out[w] = dist;
+					if (fdo_svm_classify(svm, dist)) {
+						if (n >= det_cap) { overflow = 1; continue; }
+						fdb_detection* d = &det_out[n++];
+						memset(d, 0, sizeof(*d));
+						fill_geometry(d, I, frame_index, x, y, w);
+						d->wvm_level = -1; d->wvm_fout = NAN; d->wvm_probability = NAN;
+						d->svm_distance = dist; d->svm_probability = fdo_svm_probability(svm, dist);
+						d->probability = d->svm_probability;
+						d->positive = 1;
+					}
+					continue;
+				}
 				double a = timing_out ? now_s() : 0;
 				fdo_hq64(L->data + (size_t)y * L->width + x, L->width, pw, ph, patch);
 				double b = timing_out ? now_s() : 0;
@@ -700,6 +768,7 @@ int64_t fdo_detect_frame(const fdb_detector_desc* desc, const fdo_wvm* wvm, cons
 	counts[1] = n;
 	double t2 = now_s();
 	double t_oe = 0, t_svm = 0;
+	if (!wvm) { counts[2] = counts[3] = counts[4] = n; stage = 0; }
 	if (!overflow && stage >= FDB_STAGE_OE) {
 		n = overlap_eliminate(det_out, n, desc->oe_dist, desc->oe_ratio);
 		counts[2] = n;
@@ -714,8 +783,10 @@ int64_t fdo_detect_frame(const fdb_detector_desc* desc, const fdo_wvm* wvm, cons
 			fdb_detection d = det_out[i];
 			const fdo_layer* L = NULL;
 			for (int li = 0; li < pyr->n_layers; ++li) if (pyr->layers[li].index == d.layer) L = &pyr->layers[li];
-			fdo_hq64(L->data + (size_t)d.y * L->width + d.x, L->width, pw, ph, p2);
-			d.svm_distance = fdo_svm_distance(svm, p2);
+			int lidx = (int)(L - pyr->layers);
+			if (svm_features) fdo_features_patch(svm_features, flayers ? flayers[lidx] : L->data, L->width, d.x, d.y, fvec);
+			else fdo_hq64(L->data + (size_t)d.y * L->width + d.x, L->width, pw, ph, p2);
+			d.svm_distance = fdo_svm_distance(svm, svm_features ? fvec : (void*)p2);
 			d.svm_probability = fdo_svm_probability(svm, d.svm_distance);
 			d.positive = fdo_svm_classify(svm, d.svm_distance);
 			d.probability = 0.5;
@@ -739,6 +810,8 @@ int64_t fdo_detect_frame(const fdb_detector_desc* desc, const fdo_wvm* wvm, cons
 		timing_out[3] = t_oe; timing_out[4] = t_svm;
 	}
 	free(infos);
+	free(fvec);
+	free_layers(flayers, pyr->n_layers);
 	fdo_pyramid_free(pyr);
 	return overflow ? -1 : n;
 }

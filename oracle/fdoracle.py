@@ -76,6 +76,35 @@ def lib():
                                        C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                        C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                        C.POINTER(C.c_int64), C.POINTER(C.c_double)]
+        L.fdo_gradient_u8.restype = None
+        L.fdo_gradient_u8.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        L.fdo_gradient_bin_luts.restype = None
+        L.fdo_gradient_bin_luts.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.fdo_lbp_u8.restype = None
+        L.fdo_lbp_u8.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        L.fdo_equalize_hist_u8.restype = None
+        L.fdo_equalize_hist_u8.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        L.fdo_whitening_filter.restype = None
+        L.fdo_whitening_filter.argtypes = [C.c_int, C.c_int, C.c_float, C.c_float, C.c_void_p]
+        L.fdo_whitening_u8.restype = None
+        L.fdo_whitening_u8.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.fdo_features_create.restype = C.c_void_p
+        L.fdo_features_create.argtypes = [C.POINTER(capi.FeatureDesc), C.c_int, C.c_int]
+        L.fdo_features_free.restype = None; L.fdo_features_free.argtypes = [C.c_void_p]
+        for nm in ("fdo_features_dim", "fdo_features_is_float", "fdo_features_layer_channels"):
+            getattr(L, nm).restype = C.c_int; getattr(L, nm).argtypes = [C.c_void_p]
+        L.fdo_features_filter_layer.restype = None
+        L.fdo_features_filter_layer.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.fdo_features_patch.restype = None
+        L.fdo_features_patch.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        L.fdo_extract_features.restype = C.c_int
+        L.fdo_extract_features.argtypes = [C.POINTER(capi.DetectorDesc), C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                           C.c_void_p, C.c_int64, C.c_void_p]
+        L.fdo_detect_frame_ex.restype = C.c_int64
+        L.fdo_detect_frame_ex.argtypes = [C.POINTER(capi.DetectorDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                          C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                          C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                          C.POINTER(C.c_int64), C.POINTER(C.c_double)]
         _lib = L
     return _lib
 
@@ -110,8 +139,42 @@ def ref():
         R.ref_detect_frame.restype = C.c_int64
         R.ref_detect_frame.argtypes = [C.POINTER(capi.DetectorDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                        C.c_int, C.c_void_p, C.POINTER(C.c_int64), C.c_void_p, C.c_int64, C.POINTER(C.c_double)]
+        R.ref_gradient_bin_luts.restype = None
+        R.ref_gradient_bin_luts.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        R.ref_lbp.restype = None; R.ref_lbp.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        R.ref_patch_histogram.restype = C.c_int
+        R.ref_patch_histogram.argtypes = [C.POINTER(capi.FeatureDesc), C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                          C.c_void_p, C.c_int]
         _ref = R
     return _ref
+
+
+def ref_gradient_bin_luts(bins, signed):
+    one = np.empty((65536, 2), np.uint8); two = np.empty((65536, 4), np.uint8)
+    ref().ref_gradient_bin_luts(bins, int(signed), one.ctypes.data, two.ctypes.data)
+    return one, two
+
+
+def ref_lbp(gray, lbp_type):
+    gray = np.ascontiguousarray(gray, np.uint8)
+    out = np.empty(gray.shape, np.uint8)
+    ref().ref_lbp(gray.ctypes.data, gray.shape[1], gray.shape[0], lbp_type, out.ctypes.data)
+    return out
+
+
+def ref_patch_histogram(feature_desc, bins, filtered_layer, x, y, pw, ph):
+    """The reference's own SpatialHistogramFilter / HogFilter / ExtendedHogFilter on the window (x, y, pw, ph) of a
+    binned layer [H, W, channels] u8."""
+    fl = np.ascontiguousarray(filtered_layer, np.uint8)
+    if fl.ndim == 2:
+        fl = fl[:, :, None]
+    ch = fl.shape[2]
+    roi = fl[y:y + ph, x:x + pw]
+    out = np.empty(1 << 16, np.float32)
+    n = ref().ref_patch_histogram(C.byref(feature_desc), bins, roi.ctypes.data, fl.strides[0], ph, pw, ch, out.ctypes.data, out.size)
+    if n < 0:
+        raise RuntimeError("ref_patch_histogram: buffer too small")
+    return out[:n].copy()
 
 
 # ------------------------------------------------------------------------------------------------
@@ -234,6 +297,98 @@ class Svm:
         return dist, prob, pos
 
 
+class Features:
+    """A prepared feature space (fdo_features): layer filters + patch filter chain."""
+
+    def __init__(self, feature_desc, patch_w, patch_h):
+        self._desc = feature_desc
+        self.pw, self.ph = patch_w, patch_h
+        self.h = lib().fdo_features_create(C.byref(feature_desc), patch_w, patch_h)
+        if not self.h:
+            raise ValueError("unsupported feature descriptor")
+        self.dim = lib().fdo_features_dim(self.h)
+        self.is_float = bool(lib().fdo_features_is_float(self.h))
+        self.layer_channels = lib().fdo_features_layer_channels(self.h)
+        self.dtype = np.float32 if self.is_float else np.uint8
+
+    def __del__(self):
+        try:
+            lib().fdo_features_free(self.h)
+        except Exception:
+            pass
+
+    def filter_layer(self, gray):
+        gray = np.ascontiguousarray(gray, np.uint8)
+        h, w = gray.shape
+        ch = max(self.layer_channels, 1)
+        out = np.empty((h, w, ch), np.uint8)
+        lib().fdo_features_filter_layer(self.h, gray.ctypes.data, w, h, out.ctypes.data)
+        return out
+
+    def patch(self, filtered_layer, x, y):
+        fl = np.ascontiguousarray(filtered_layer, np.uint8)
+        out = np.empty(self.dim, self.dtype)
+        lib().fdo_features_patch(self.h, fl.ctypes.data, fl.shape[1], x, y, out.ctypes.data)
+        return out
+
+    def extract(self, det_kwargs, frame, layer_x_y):
+        """feature vectors of the windows [(layer index, x, y), ...] of one frame -> [n, dim]"""
+        from featuredetection_b200.synthetic import detector_desc
+        desc = detector_desc(**det_kwargs)
+        frame = np.ascontiguousarray(frame, np.uint8)
+        lxy = np.ascontiguousarray(layer_x_y, np.int32).reshape(-1, 3)
+        out = np.empty((lxy.shape[0], self.dim), self.dtype)
+        rc = lib().fdo_extract_features(C.byref(desc), self.h, frame.ctypes.data, frame.shape[1], frame.shape[0],
+                                        frame.shape[1], lxy.ctypes.data, lxy.shape[0], out.ctypes.data)
+        if rc != 0:
+            raise RuntimeError("fdo_extract_features failed (%d)" % rc)
+        return out
+
+
+def gradient(gray, ksize=1):
+    gray = np.ascontiguousarray(gray, np.uint8)
+    out = np.empty(gray.shape + (2,), np.uint8)
+    lib().fdo_gradient_u8(gray.ctypes.data, gray.shape[1], gray.shape[0], gray.shape[1], ksize, out.ctypes.data)
+    return out
+
+
+def gradient_bin_luts(bins, signed):
+    one = np.empty((65536, 2), np.uint8); two = np.empty((65536, 4), np.uint8)
+    lib().fdo_gradient_bin_luts(bins, int(signed), one.ctypes.data, two.ctypes.data)
+    return one, two
+
+
+def lbp(gray, lbp_type):
+    gray = np.ascontiguousarray(gray, np.uint8)
+    out = np.empty(gray.shape, np.uint8)
+    lib().fdo_lbp_u8(gray.ctypes.data, gray.shape[1], gray.shape[0], gray.shape[1], lbp_type, out.ctypes.data)
+    return out
+
+
+def equalize_hist(patch):
+    assert patch.dtype == np.uint8 and patch.strides[1] == 1
+    h, w = patch.shape
+    out = np.empty((h, w), np.uint8)
+    lib().fdo_equalize_hist_u8(patch.ctypes.data, patch.strides[0], w, h, out.ctypes.data)
+    return out
+
+
+def whitening_filter(w, h, alpha=1.0, cutoff=0.390625):
+    out = np.empty((h, w), np.float32)
+    lib().fdo_whitening_filter(w, h, alpha, cutoff, out.ctypes.data)
+    return out
+
+
+def whitening(patch, alpha=1.0, cutoff=0.390625):
+    """-> (u8 whitened patch, float32 image before convertTo)"""
+    assert patch.dtype == np.uint8 and patch.strides[1] == 1
+    h, w = patch.shape
+    filt = whitening_filter(w, h, alpha, cutoff)
+    out = np.empty((h, w), np.uint8); real = np.empty((h, w), np.float32)
+    lib().fdo_whitening_u8(patch.ctypes.data, patch.strides[0], w, h, filt.ctypes.data, out.ctypes.data, real.ctypes.data)
+    return out, real
+
+
 def detections_to_array(buf, n):
     """ctypes Detection array -> numpy structured array copy"""
     dt = np.dtype([(name, np.ctypeslib.as_ctypes_type(np.dtype(_np_of(ct)))) for name, ct in capi.Detection._fields_], align=True)
@@ -250,7 +405,7 @@ SCORE_DTYPE = np.dtype([("fout", "f4"), ("level", "i4")])
 
 
 def detect_frame(det_kwargs, wvm, svm, frame, stage=capi.FDB_STAGE_NMS, roi=(0, 0, 0, 0), frame_index=0,
-                 want_dense=True, want_patches=False, det_cap=1 << 16, timing=False):
+                 want_dense=True, want_patches=False, det_cap=1 << 16, timing=False, svm_features=None):
     """Whole reference path on one frame (fdo_detect_frame). Returns a dict."""
     from featuredetection_b200.synthetic import detector_desc
     desc = detector_desc(**det_kwargs)
@@ -271,16 +426,19 @@ def detect_frame(det_kwargs, wvm, svm, frame, stage=capi.FDB_STAGE_NMS, roi=(0, 
     dets = np.zeros(det_cap, DETECTION_DTYPE)
     counts = (C.c_int64 * 5)()
     tim = (C.c_double * 5)()
-    n = L.fdo_detect_frame(C.byref(desc), wvm.h, svm.h if svm is not None else None, frame.ctypes.data, W, H, W,
-                           frame_index, roi[0], roi[1], roi[2], roi[3], stage,
-                           dense.ctypes.data if dense is not None else None,
-                           patches.ctypes.data if patches is not None else None,
-                           dets.ctypes.data, det_cap, counts, tim if timing else None)
+    svm_dense = np.zeros(total, np.float64) if (wvm is None and want_dense) else None
+    n = L.fdo_detect_frame_ex(C.byref(desc), wvm.h if wvm is not None else None, svm.h if svm is not None else None,
+                              svm_features.h if svm_features is not None else None, frame.ctypes.data, W, H, W,
+                              frame_index, roi[0], roi[1], roi[2], roi[3], stage,
+                              dense.ctypes.data if (dense is not None and wvm is not None) else None,
+                              patches.ctypes.data if (patches is not None and wvm is not None) else None,
+                              svm_dense.ctypes.data if svm_dense is not None else None,
+                              dets.ctypes.data, det_cap, counts, tim if timing else None)
     if n < 0:
         raise RuntimeError("fdo_detect_frame failed (%d)" % n)
     layers = [{f: getattr(infos[i], f) for f, _ in capi.LayerInfo._fields_} for i in range(n_layers)]
     return dict(windows=int(total), dense=dense, patches=patches, detections=dets[:n].copy(),
-                counts=list(counts), timing=list(tim), layers=layers)
+                counts=list(counts), timing=list(tim), layers=layers, svm_dense=svm_dense)
 
 
 def ref_detect_frame(det_kwargs, wvm, svm, frame, stage=capi.FDB_STAGE_NMS, want_dense=True, det_cap=1 << 16):

@@ -10,6 +10,8 @@
 #include <algorithm>
 #include <functional>
 #include <cmath>
+#include <math.h> /* as the real opencv2/core/types_c.h does: with it, unqualified sqrt/pow/exp on float arguments
+                   * resolve to the float overloads (libstdc++'s <math.h> and MSVC both export them globally) */
 #include <cstddef>
 #include <cstdio>
 #include <cstring>
@@ -40,6 +42,12 @@ typedef unsigned short ushort;
 #define CV_32FC1 CV_MAKETYPE(CV_32F, 1)
 #define CV_32SC1 CV_MAKETYPE(CV_32S, 1)
 #define CV_64FC1 CV_MAKETYPE(CV_64F, 1)
+#define CV_8UC(n) CV_MAKETYPE(CV_8U, (n))
+#define CV_8UC2 CV_MAKETYPE(CV_8U, 2)
+#define CV_8UC4 CV_MAKETYPE(CV_8U, 4)
+#define CV_32FC(n) CV_MAKETYPE(CV_32F, (n))
+#define CV_PI 3.1415926535897932384626433832795
+#define CV_SCHARR -1
 
 inline int cvRound(double v) { return (int)std::nearbyint(v); }
 inline int cvFloor(double v) { return (int)std::floor(v); }
@@ -70,6 +78,36 @@ template<class T> struct Rect_ {
 	Size_<T> size() const { return Size_<T>(width, height); }
 };
 typedef Rect_<int> Rect;
+
+template<class T, int N> struct Vec {
+	T val[N];
+	Vec() { for (int i = 0; i < N; ++i) val[i] = T(); }
+	T& operator[](int i) { return val[i]; }
+	const T& operator[](int i) const { return val[i]; }
+};
+typedef Vec<uchar, 2> Vec2b;
+typedef Vec<uchar, 4> Vec4b;
+typedef Vec<float, 2> Vec2f;
+
+/* saturate_cast<uchar>: cvRound (half to even) then clamp, as OpenCV defines it */
+template<class T> inline T saturate_cast(double v);
+template<> inline uchar saturate_cast<uchar>(double v) { int i = cvRound(v); return (uchar)(i < 0 ? 0 : (i > 255 ? 255 : i)); }
+template<class T> inline T saturate_cast(float v);
+template<> inline uchar saturate_cast<uchar>(float v) { int i = cvRound(v); return (uchar)(i < 0 ? 0 : (i > 255 ? 255 : i)); }
+template<class T> inline T saturate_cast(int v);
+template<> inline uchar saturate_cast<uchar>(int v) { return (uchar)(v < 0 ? 0 : (v > 255 ? 255 : v)); }
+
+enum { NORM_INF = 1, NORM_L1 = 2, NORM_L2 = 4 };
+
+class Mat;
+/* the two matrix expressions the histogram filters use: m / s (evaluated as convertTo(type, 1/s), i.e. a
+ * multiplication by (float)(1/s)) and min(m, s); assigned INTO the destination's existing buffer when it has
+ * the right size and type, as cv::MatExpr does */
+struct MatExpr {
+	const Mat* a;
+	int op; /* 0: scale, 1: min */
+	double s;
+};
 
 class Mat {
 public:
@@ -113,6 +151,10 @@ public:
 	template<class T> const T* ptr(int y = 0) const { return (const T*)(data + (size_t)y * step); }
 	uchar* ptr(int y = 0) { return data + (size_t)y * step; }
 	const uchar* ptr(int y = 0) const { return data + (size_t)y * step; }
+	template<class T> T* ptr(int y, int x) { return (T*)(data + (size_t)y * step + (size_t)x * elemSize()); }
+	template<class T> const T* ptr(int y, int x) const { return (const T*)(data + (size_t)y * step + (size_t)x * elemSize()); }
+	static Mat zeros(int r, int c, int type) { Mat m(r, c, type); std::memset(m.data, 0, (size_t)r * m.step); return m; }
+	inline Mat& operator=(const MatExpr& e);
 	template<class T> T& at(int y, int x) { return ((T*)(data + (size_t)y * step))[x]; }
 	template<class T> const T& at(int y, int x) const { return ((const T*)(data + (size_t)y * step))[x]; }
 
@@ -148,6 +190,45 @@ public:
 private:
 	std::shared_ptr<std::vector<uchar>> buffer;
 };
+
+inline Mat& Mat::operator=(const MatExpr& e) {
+	const Mat src = *e.a; /* header copy keeps the source buffer alive if *this is the source */
+	if (src.depth() != CV_32F) throw std::runtime_error("shim MatExpr: only CV_32F");
+	create(src.rows, src.cols, src.type());
+	const int n = src.cols * src.channels();
+	const float fs = e.op == 0 ? (float)(1.0 / e.s) : (float)e.s;
+	for (int y = 0; y < src.rows; ++y) {
+		const float* a = src.ptr<float>(y);
+		float* d = ptr<float>(y);
+		if (e.op == 0) for (int i = 0; i < n; ++i) d[i] = a[i] * fs;
+		else for (int i = 0; i < n; ++i) d[i] = a[i] < fs ? a[i] : fs;
+	}
+	return *this;
+}
+
+inline MatExpr operator/(const Mat& a, double s) { MatExpr e; e.a = &a; e.op = 0; e.s = s; return e; }
+inline MatExpr min(const Mat& a, double s) { MatExpr e; e.a = &a; e.op = 1; e.s = s; return e; }
+
+/* cv::norm for CV_32F arrays: double accumulation */
+inline double norm(const Mat& m, int normType) {
+	if (m.depth() != CV_32F) throw std::runtime_error("shim norm: only CV_32F");
+	const int n = m.cols * m.channels();
+	double s = 0;
+	for (int y = 0; y < m.rows; ++y) {
+		const float* a = m.ptr<float>(y);
+		if (normType == NORM_L2) for (int i = 0; i < n; ++i) s += (double)a[i] * (double)a[i];
+		else if (normType == NORM_L1) for (int i = 0; i < n; ++i) s += std::fabs((double)a[i]);
+		else throw std::runtime_error("shim norm: unsupported type");
+	}
+	return normType == NORM_L2 ? std::sqrt(s) : s;
+}
+
+inline void sqrt(const Mat& src, Mat& dst) {
+	const Mat a = src;
+	dst.create(a.rows, a.cols, a.type());
+	const int n = a.cols * a.channels();
+	for (int y = 0; y < a.rows; ++y) for (int i = 0; i < n; ++i) dst.ptr<float>(y)[i] = std::sqrt(a.ptr<float>(y)[i]);
+}
 
 } // namespace cv
 
