@@ -43,13 +43,30 @@ CFG = "FaceFrontal"
 _worker_state = {}
 
 
-def _cpu_worker_init(kind, profile):
+def feature_svm_model(syn, feature, det_kw, layers, extract):
+    """The SVM of a feature-space cascade: 1024 support vectors blended from feature vectors of seeded
+    windows of frames 1000..1003; extract(frame, layer_x_y) -> [n, dim] is the product's extractor (b200 arm) or the
+    oracle's (CPU arms) - the two agree bit for bit for the histogram features (tests/test_gpu_features.py)."""
+    pw, ph = det_kw["patch_width"], det_kw["patch_height"]
+    vecs = []
+    for k in range(4):
+        lxy = syn.feature_sample_windows(layers, pw, ph, 24, seed=9000 + k)
+        vecs.append(extract(syn.synthetic_frame(1000 + k), lxy))
+    return syn.make_feature_svm(np.concatenate(vecs), seed=300, num_sv=1024, gamma=syn.FEATURE_GAMMA[feature], center=True)
+
+
+def _cpu_worker_init(kind, profile, feature="hq64"):
     from featuredetection_b200 import synthetic as syn
     from oracle import fdoracle as fo
     det_kw, wvm, svm = syn.landmark_models(CFG, profile)
     use_ref = kind == "reference"
+    feat = None
+    if feature != "hq64":
+        feat = fo.Features(syn.feature_desc(kind=feature), det_kw["patch_width"], det_kw["patch_height"])
+        r = fo.detect_frame(det_kw, fo.Wvm(wvm), None, syn.synthetic_frame(0), stage=1, want_dense=False)
+        svm = feature_svm_model(syn, feature, det_kw, r["layers"], lambda fr, lxy: feat.extract(det_kw, fr, lxy))
     _worker_state.update(det_kw=det_kw, wvm=fo.Wvm(wvm, use_ref=use_ref), svm=fo.Svm(svm, use_ref=use_ref),
-                         use_ref=use_ref, fo=fo, syn=syn)
+                         use_ref=use_ref, fo=fo, syn=syn, feat=feat)
 
 
 def _cpu_worker_run(frame_ids):
@@ -60,9 +77,9 @@ def _cpu_worker_run(frame_ids):
     for k in frame_ids:
         frame = syn.synthetic_frame(k)
         if st["use_ref"]:
-            r = fo.ref_detect_frame(st["det_kw"], st["wvm"], st["svm"], frame, want_dense=False)
+            r = fo.ref_detect_frame(st["det_kw"], st["wvm"], st["svm"], frame, want_dense=False, svm_features=st["feat"])
         else:
-            r = fo.detect_frame(st["det_kw"], st["wvm"], st["svm"], frame, want_dense=False)
+            r = fo.detect_frame(st["det_kw"], st["wvm"], st["svm"], frame, want_dense=False, svm_features=st["feat"])
         windows += r["windows"]
     return windows, time.perf_counter() - t0
 
@@ -71,12 +88,12 @@ class CpuArm:
     """The reference CPU path on all host cores (one process per core: the reference objects are
     not thread-safe)."""
 
-    def __init__(self, profile):
+    def __init__(self, profile, feature="hq64"):
         from oracle import fdoracle as fo
         fo.build()
         self.kind = "reference" if fo.ref_available() else "port"
         self.cores = os.cpu_count() or 1
-        self.pool = mp.get_context("spawn").Pool(self.cores, initializer=_cpu_worker_init, initargs=(self.kind, profile))
+        self.pool = mp.get_context("spawn").Pool(self.cores, initializer=_cpu_worker_init, initargs=(self.kind, profile, feature))
 
     def run(self, frames_per_core, first_frame=0):
         chunks = [list(range(first_frame + c * frames_per_core, first_frame + (c + 1) * frames_per_core))
@@ -142,7 +159,7 @@ def hbm_peak():
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    arm = CpuArm(args.profile)
+    arm = CpuArm(args.profile, args.feature)
     per_core = args.ref_frames_per_core
     for _ in range(args.warmup):
         arm.run(1)
@@ -169,8 +186,12 @@ def run_reference(args, rank, world):
 
 def workload_config(args, world, extra=None):
     if args.workload == "facefrontal":
+        fdesc = ("hq64 u8 features for both stages, as ffpDetectApp wires it" if args.feature == "hq64" else
+                 "WVM on hq64 patches, RBF-SVM on %s features (adaptiveTrackingApp/default.cfg parameters: 9 unsigned bins, "
+                 "interpolated binning, cell 5, block 1, l2norm -> 144-d float32)" % args.feature.upper() if args.feature == "hog" else
+                 "WVM on hq64 patches, RBF-SVM on %s features" % args.feature.upper())
         wl = ("BASELINE configs[1]: %d-frame batch per GPU, 640x480 1-channel, FaceFrontal WVM->SVM five-stage cascade "
-              "(hq64 u8 features for both stages, as ffpDetectApp wires it), full pyramid, step 1x1" % args.frames)
+              "(%s), full pyramid, step 1x1" % (args.frames, fdesc))
         wpf, pyr = 16185, 1931000
     else:
         wl = ("BASELINE configs[3] shape: %d-frame batch per GPU, 640x480 1-channel, all 15 ffpDetectApp landmark detectors per frame "
@@ -195,13 +216,19 @@ def main():
     ap.add_argument("--workload", default="facefrontal", choices=["facefrontal", "landmarks15"],
                     help="facefrontal = BASELINE configs[1] (headline); landmarks15 = all 15 ffpDetectApp landmark detectors per frame (configs[3] shape, hq64 features)")
     ap.add_argument("--profile", default="realistic", choices=["realistic", "no-exit"])
-    ap.add_argument("--cpu-frames-per-core", type=int, default=4, help="cpu_baseline sample size per host core")
+    ap.add_argument("--feature", default=None, choices=["hq64", "hog", "whi", "lbp", "histeq", "ehog"],
+                    help="feature space of the second-stage SVM (default: hog for facefrontal = BASELINE configs[1]; hq64 for landmarks15)")
+    ap.add_argument("--cpu-frames-per-core", type=int, default=32, help="cpu_baseline sample size per host core")
     ap.add_argument("--ref-frames-per-core", type=int, default=2, help="--impl reference: frames per core per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.frames is None:
         args.frames = 256 if args.workload == "facefrontal" else 16
+    if args.feature is None:
+        args.feature = "hog" if args.workload == "facefrontal" else "hq64"
+    if args.workload != "facefrontal" and args.feature != "hq64":
+        raise SystemExit("bench.py: --feature applies to the facefrontal workload")
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -231,7 +258,14 @@ def main():
         det_kw, wvm, svm = syn.landmark_models(nm, args.profile)
         if args.profile == "no-exit":
             det_kw = dict(det_kw, max_positives_per_frame=400000)
-        c = SlidingWindowCascade(ctx, det_kw, wvm, svm)
+        fdesc = None
+        if args.feature != "hq64":
+            fdesc = syn.feature_desc(kind=args.feature)
+            probe = SlidingWindowCascade(ctx, det_kw, wvm, None, feature=fdesc)  # the product's own extractor builds the SVM's support vectors
+            probe.prepare(W, H, 1)
+            svm = feature_svm_model(syn, args.feature, det_kw, probe.layers(), probe.extract_features)
+            del probe
+        c = SlidingWindowCascade(ctx, det_kw, wvm, svm, feature=fdesc)
         c.prepare(W, H, n)
         cascs.append(c)
     nwin = sum(c.windows_per_frame for c in cascs)          # windows per frame over all detectors
@@ -353,7 +387,7 @@ def main():
         traffic = 2585600 if args.workload == "facefrontal" and n == 256 else None
         cpu = None
         if not args.no_cpu_baseline:
-            arm = CpuArm(args.profile)
+            arm = CpuArm(args.profile, args.feature)
             arm.run(1)
             wcpu, wall = arm.run(args.cpu_frames_per_core)
             arm.close()

@@ -22,6 +22,7 @@
 #include "fdb_internal.h"
 #include "wvm_device.h"
 #include "api_types.h"
+#include "features_device.h"
 
 namespace fdb {
 
@@ -73,7 +74,7 @@ int fdb_ctx_create(int device, fdb_ctx** out) {
 	c->device = device;
 	CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
 	for (cudaEvent_t& e : c->ev) CUDA_TRY(cudaEventCreate(&e));
-	if (wvm_configure() != 0 || svm_configure() != 0 || strip_configure_all() != 0 || strip_mma_configure_all() != 0) {
+	if (wvm_configure() != 0 || svm_configure() != 0 || strip_configure_all() != 0 || strip_mma_configure_all() != 0 || feature_configure() != 0) {
 		cudaStreamDestroy(c->stream); delete c;
 		return fail(FDB_ERR_CUDA, "cudaFuncSetAttribute failed: libfdb200 kernels not loadable on this device");
 	}

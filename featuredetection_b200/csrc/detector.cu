@@ -31,11 +31,13 @@
 #include "fdb_internal.h"
 #include "wvm_device.h"
 #include "api_types.h"
+#include "features_device.h"
 
 using namespace fdb;
 
 #define PIPE_SLOTS 3
 #define OPT_CAND 4096 /* candidates fetched together with the counters (one D2H); more need a second copy */
+#define FEAT_BATCH 8192 /* feature vectors materialised at a time (feature-space SVM stage) */
 
 namespace {
 
@@ -51,6 +53,8 @@ struct Slot {
 	DeepQueue deep{};
 	SvmItem* d_items = nullptr;
 	double* d_dist = nullptr;
+	uint8_t* d_farena = nullptr;   /* filtered pyramid layers of the chunk (feature spaces with layer filters) */
+	void* d_feat = nullptr;        /* FEAT_BATCH feature vectors */
 	int* h_counters = nullptr;     /* pinned mirror: 4 ints + OPT_CAND candidates */
 	Candidate* h_cand_big = nullptr; /* pinned, cand_cap entries (second copy when > OPT_CAND) */
 	SvmItem* h_items = nullptr;
@@ -86,6 +90,12 @@ struct fdb_detector {
 	Strip* d_strips = nullptr; int n_strips = 0;
 	bool use_tma = false;             /* strip tiles staged by TMA (tensor maps encoded) */
 	bool use_strips = false;          /* fast path usable (and not yet overflowed) */
+	bool has_feature = false;         /* the SVM works in its own feature space (fdb_detector_set_feature) */
+	fdb_feature_desc fdesc{};
+	DevFeature feat{};
+	int64_t farena_bytes = 0;         /* per frame */
+	SvmItem* d_all_items = nullptr;   /* every window of a frame as an SVM item (`single` detector without a WVM) */
+	double* d_all_dist = nullptr; double* h_all_dist = nullptr;
 	int64_t counts[5] = {0, 0, 0, 0, 0};
 };
 
@@ -149,7 +159,7 @@ int enqueue_stage1(fdb_detector* det, Slot& sl, cudaStream_t st, const uint8_t* 
 		c->launches++;
 	}
 	if (marks) CUDA_TRY(cudaEventRecord(c->ev[3], st));
-	if (windows > 0) {
+	if (windows > 0 && det->wvm) {
 		DevWvm m = det->wvm->dev;
 		m.step_x = det->desc.step_x; m.step_y = det->desc.step_y;
 		if (det->use_strips && d_layers == det->d_layers && !d_patches) {
@@ -193,6 +203,31 @@ int enqueue_fetch(fdb_detector* det, Slot& sl, cudaStream_t st) {
 }
 
 const int STATUS_REDO = -1000;
+
+/* the second classifier on n work items of the slot's chunk: hq64 patches are rebuilt inside the SVM kernel;
+ * any other feature space runs its layer filters once per chunk, then feature kernel + SVM in batches */
+void svm_stage(fdb_detector* det, Slot& sl, cudaStream_t st, const Plan& plan, const DevLayer* d_layers, const SvmItem* d_items,
+		int n, double* d_dist, bool filter_layers) {
+	fdb_ctx* c = det->ctx;
+	if (!det->has_feature || det->feat.kind == FDB_FEATURE_HQ64) {
+		launch_svm_windows(st, det->svm->dev, det->desc.patch_width, det->desc.patch_height, sl.frames_dev, plan.width, plan.height,
+				sl.d_arena, plan.arena_bytes, d_layers, d_items, n, d_dist);
+		c->launches++;
+		return;
+	}
+	if (filter_layers && det->feat.layer_channels) {
+		launch_feature_layers(st, det->feat, sl.frames_dev, plan.width, plan.height, sl.n, sl.d_arena, plan.arena_bytes, d_layers,
+				sl.d_farena, det->farena_bytes);
+		c->launches++;
+	}
+	for (int off = 0; off < n; off += FEAT_BATCH) {
+		const int m = std::min(FEAT_BATCH, n - off);
+		launch_feature_patches(st, det->feat, sl.frames_dev, plan.width, plan.height, sl.d_arena, plan.arena_bytes, d_layers,
+				sl.d_farena, det->farena_bytes, d_items + off, m, sl.d_feat);
+		launch_svm_vectors(st, det->svm->dev, sl.d_feat, m, d_dist + off);
+		c->launches += 2;
+	}
+}
 
 /* phase A of the host post-processing: wait for stage 1 of the slot's chunk, build the per-frame
  * candidate lists, overlap elimination, launch the SVM on the survivors (async) */
@@ -248,9 +283,7 @@ int phase_a(fdb_detector* det, Slot& sl, cudaStream_t st, const Plan& plan, cons
 		sl.svm_items = total;
 		if (total) {
 			CUDA_TRY(cudaMemcpyAsync(sl.d_items, sl.h_items, sizeof(SvmItem) * total, cudaMemcpyHostToDevice, st));
-			launch_svm_windows(st, det->svm->dev, det->desc.patch_width, det->desc.patch_height, sl.frames_dev, plan.width, plan.height,
-					sl.d_arena, plan.arena_bytes, d_layers, sl.d_items, (int)total, sl.d_dist);
-			c->launches++;
+			svm_stage(det, sl, st, plan, d_layers, sl.d_items, (int)total, sl.d_dist, true);
 			CUDA_TRY(cudaGetLastError());
 			CUDA_TRY(cudaMemcpyAsync(sl.h_dist, sl.d_dist, sizeof(double) * total, cudaMemcpyDeviceToHost, st));
 		}
@@ -319,6 +352,57 @@ void release(fdb_detector* det) {
 	det->d_down.clear(); det->n_down.clear(); det->max_down_px.clear();
 }
 
+/* `single` detector of ffpDetectApp.cpp:427-500 with a psvm classifier: SlidingWindowDetector::detect
+ * (SlidingWindowDetector.cpp:40-98) where the extractor is a FilteringPyramidFeatureExtractor (the feature space)
+ * and the classifier a ProbabilisticSvmClassifier - every window is classified, positives are returned in
+ * canonical order with the SVM probability. distance_out: NULL or host [n_frames * windows] distances. */
+int detect_single(fdb_detector* det, const uint8_t* frames, bool frames_on_device, int64_t pitch, int32_t n_frames,
+		double* distance_out, fdb_detection* dets_out, int64_t det_cap, int64_t* n_dets) {
+	const Plan& plan = det->plan;
+	const int W = plan.width, H = plan.height;
+	cudaStream_t st = det->ctx->stream;
+	Slot& sl = det->slots[0];
+	std::fill(det->counts, det->counts + 5, 0);
+	det->counts[0] = plan.windows * n_frames;
+	std::vector<fdb_detection> dets;
+	const int nwin = (int)plan.windows;
+	for (int k = 0; k < n_frames; ++k) {
+		if (frames_on_device) sl.frames_dev = frames + (int64_t)k * W * H;
+		else {
+			CUDA_TRY(cudaMemcpy2DAsync(sl.d_frames, (size_t)W, frames + (int64_t)k * pitch * H, (size_t)pitch, (size_t)W, (size_t)H,
+					cudaMemcpyHostToDevice, st));
+			sl.frames_dev = sl.d_frames;
+		}
+		sl.base = k; sl.n = 1;
+		int s = enqueue_stage1(det, sl, st, sl.frames_dev, 1, plan, det->d_layers, 0, nullptr, nullptr, false);
+		if (s) return s;
+		if (nwin > 0) {
+			svm_stage(det, sl, st, plan, det->d_layers, det->d_all_items, nwin, det->d_all_dist, true);
+			CUDA_TRY(cudaGetLastError());
+			CUDA_TRY(cudaMemcpyAsync(det->h_all_dist, det->d_all_dist, sizeof(double) * (size_t)nwin, cudaMemcpyDeviceToHost, st));
+		}
+		CUDA_TRY(cudaStreamSynchronize(st));
+		if (distance_out && nwin) std::memcpy(distance_out + (int64_t)k * nwin, det->h_all_dist, sizeof(double) * (size_t)nwin);
+		for (int w = 0; w < nwin; ++w) {
+			const double dist = det->h_all_dist[w];
+			if (!(dist >= det->svm->dev.threshold)) continue; /* SvmClassifier::classify (SvmClassifier.cpp:44-46) */
+			fdb_detection d;
+			fill_detection(&d, plan, det->desc, k, w);
+			d.reserved = 0;
+			d.wvm_level = -1;
+			d.wvm_fout = std::numeric_limits<float>::quiet_NaN();
+			d.wvm_probability = std::numeric_limits<double>::quiet_NaN();
+			d.svm_distance = dist;
+			d.svm_probability = svm_probability(det->svm->logistic_a, det->svm->logistic_b, dist);
+			d.probability = d.svm_probability;
+			d.positive = 1;
+			dets.push_back(d);
+		}
+	}
+	det->counts[1] = det->counts[2] = det->counts[3] = det->counts[4] = (int64_t)dets.size();
+	return copy_out(dets, dets_out, det_cap, n_dets);
+}
+
 int detect_pipeline(fdb_detector* det, const uint8_t* frames, bool frames_on_device, int64_t pitch, int32_t n_frames,
 		int32_t stage, fdb_window_score* dense_out, bool dense_on_device, fdb_detection* dets_out, int64_t det_cap,
 		int64_t* n_dets) {
@@ -329,6 +413,10 @@ int detect_pipeline(fdb_detector* det, const uint8_t* frames, bool frames_on_dev
 	const Plan& plan = det->plan;
 	const int W = plan.width, H = plan.height;
 	if (!frames_on_device && pitch < W) return fail(FDB_ERR_INVALID_ARGUMENT, "pitch smaller than the frame width");
+	if (!det->wvm) {
+		if (dense_out) return fail(FDB_ERR_INVALID_ARGUMENT, "a detector without a WVM has no stage-1 records (use fdb_detect_single)");
+		return detect_single(det, frames, frames_on_device, pitch, n_frames, nullptr, dets_out, det_cap, n_dets);
+	}
 	std::fill(det->counts, det->counts + 5, 0);
 	det->counts[0] = plan.windows * n_frames;
 	std::vector<fdb_detection> dets;
@@ -415,17 +503,16 @@ int fdb_detector_create(fdb_ctx* ctx, const fdb_detector_desc* desc, fdb_wvm* wv
 	int s = check_ctx(ctx); if (s) return s;
 	if (!desc || !out) return fail(FDB_ERR_INVALID_ARGUMENT, "null argument");
 	*out = nullptr;
-	if (!wvm) return fail(FDB_ERR_INVALID_ARGUMENT, "detector needs a first-stage classifier");
+	if (!wvm && !svm) return fail(FDB_ERR_INVALID_ARGUMENT, "detector needs a classifier");
 	fdb_detector_desc d = *desc;
 	if (d.step_x == 0) d.step_x = 1;
 	if (d.step_y == 0) d.step_y = 1;
 	/* DirectPyramidFeatureExtractor.cpp:77-80 */
 	if (d.step_x < 1) return fail(FDB_ERR_INVALID_ARGUMENT, "DirectPyramidFeatureExtractor: stepX has to be greater than zero");
 	if (d.step_y < 1) return fail(FDB_ERR_INVALID_ARGUMENT, "DirectPyramidFeatureExtractor: stepY has to be greater than zero");
-	if (d.patch_width != wvm->dev.fsx || d.patch_height != wvm->dev.fsy)
+	if (wvm && (d.patch_width != wvm->dev.fsx || d.patch_height != wvm->dev.fsy))
 		return fail(FDB_ERR_INVALID_ARGUMENT, "patch size differs from the WVM filter size");
-	if (svm && (svm->dev.sv_type != FDB_SV_U8 || svm->dev.dim != d.patch_width * d.patch_height))
-		return fail(FDB_ERR_INVALID_ARGUMENT, "second-stage SVM must take the u8 patch as its feature vector");
+	if (d.patch_width < 1 || d.patch_height < 1) return fail(FDB_ERR_INVALID_ARGUMENT, "bad patch size");
 	if (d.max_positives_per_frame <= 0) d.max_positives_per_frame = 4096;
 	Plan probe;
 	s = build_plan(d, 64, 64, &probe); /* validates the pyramid parameters (ImagePyramid.cpp:84-89) */
@@ -455,6 +542,18 @@ int fdb_detector_prepare(fdb_detector* det, int32_t width, int32_t height, int32
 	const Plan& plan = det->plan;
 	if (plan.windows >= (int64_t)1 << 31) return fail(FDB_ERR_UNSUPPORTED, "too many windows per frame");
 	det->max_batch = max_batch;
+	{
+		/* the SVM's input must be what its feature space produces (RbfKernel.hpp:33-38 throws on a mismatch) */
+		fdb_feature_desc fd{};
+		fd.kind = FDB_FEATURE_HQ64;
+		if (det->has_feature) fd = det->fdesc;
+		FeatureShape sh;
+		s = feature_shape(fd, det->desc.patch_width, det->desc.patch_height, &sh); if (s) return s;
+		if (det->svm && (det->svm->dev.dim != sh.dim || (det->svm->dev.sv_type == FDB_SV_F32) != (sh.is_float != 0)))
+			return fail(FDB_ERR_INVALID_ARGUMENT, "RbfKernel: the SVM's support vectors do not match the feature space (type or dimension)");
+		det->farena_bytes = 0;
+		if (det->has_feature) { s = feature_build(fd, det->desc.patch_width, det->desc.patch_height, plan, &det->feat, &det->farena_bytes, det->owned); if (s) return s; }
+	}
 	/* chunking: big batches flow through the slots in quarters so that copies, kernels and host work overlap */
 	det->chunk = max_batch >= 16 ? (max_batch + 3) / 4 : max_batch;
 	if (const char* e = std::getenv("FDB_CHUNK_FRAMES")) { /* tuning knob: frames per pipeline chunk */
@@ -533,9 +632,15 @@ int fdb_detector_prepare(fdb_detector* det, int32_t width, int32_t height, int32
 		sl.deep.next = sl.d_counters + 2;
 		sl.deep.cap = (int)std::max<int64_t>(1024, std::min<int64_t>(plan.windows * det->chunk / 16 + 1024, (int64_t)1 << 24));
 		s = dev_alloc(&sl.deep.rec, (size_t)sl.deep.cap, det->owned); if (s) return s;
-		s = dev_alloc(&sl.deep.patch, (size_t)sl.deep.cap * (size_t)det->wvm->dev.nwords, det->owned); if (s) return s;
+		s = dev_alloc(&sl.deep.patch, (size_t)sl.deep.cap * (size_t)(det->wvm ? det->wvm->dev.nwords : 1), det->owned); if (s) return s;
 		s = dev_alloc(&sl.d_items, (size_t)det->items_cap, det->owned); if (s) return s;
 		s = dev_alloc(&sl.d_dist, (size_t)det->items_cap, det->owned); if (s) return s;
+		if (det->has_feature && det->feat.kind != FDB_FEATURE_HQ64) {
+			if (det->farena_bytes) { s = dev_alloc(&sl.d_farena, (size_t)det->chunk * (size_t)det->farena_bytes, det->owned); if (s) return s; }
+			uint8_t* fb = nullptr;
+			s = dev_alloc(&fb, (size_t)FEAT_BATCH * (size_t)det->feat.dim * 4, det->owned); if (s) return s;
+			sl.d_feat = fb;
+		}
 		uint8_t* hbuf = nullptr;
 		s = host_alloc(&hbuf, 4 * sizeof(int) + OPT_CAND * sizeof(Candidate), det->owned_host); if (s) return s;
 		sl.h_counters = reinterpret_cast<int*>(hbuf);
@@ -582,7 +687,7 @@ int fdb_detector_prepare(fdb_detector* det, int32_t width, int32_t height, int32
 	s = dev_alloc(&det->d_layers_roi, FDB_MAX_LAYERS, det->owned); if (s) return s;
 	s = upload_layers(det, plan, det->d_layers, det->ctx->stream); if (s) return s;
 	/* strip table of the fast path: whole-image scan, step 1, supported patch size, <= 4 grey values, <= 256 words */
-	det->use_strips = det->desc.step_x == 1 && det->desc.step_y == 1 && det->wvm->dev.masks4 != nullptr
+	det->use_strips = det->wvm && det->desc.step_x == 1 && det->desc.step_y == 1 && det->wvm->dev.masks4 != nullptr
 			&& strip_supported(det->desc.patch_width, det->desc.patch_height) && det->wvm->dev.num_lin > WVM_KA
 			&& det->wvm->dev.num_used > WVM_KA;
 	std::vector<Strip> strips;
@@ -610,6 +715,24 @@ int fdb_detector_prepare(fdb_detector* det, int32_t width, int32_t height, int32
 	}
 	det->n_strips = (int)strips.size();
 	s = upload(strips.data(), strips.size(), &det->d_strips, det->owned); if (s) return s;
+	det->d_all_items = nullptr; det->d_all_dist = nullptr; det->h_all_dist = nullptr;
+	if (!det->wvm) {
+		/* `single` detector: every window of a frame is an SVM work item, canonical order */
+		std::vector<SvmItem> all((size_t)plan.windows);
+		size_t k = 0;
+		for (size_t li = 0; li < plan.layers.size(); ++li) {
+			const PlanLayer& L = plan.layers[li];
+			for (int iy = 0; iy < L.windows_y; ++iy)
+				for (int ix = 0; ix < L.windows_x; ++ix) {
+					SvmItem it; it.frame = 0; it.layer = (int)li;
+					it.x = L.begin_x + ix * det->desc.step_x; it.y = L.begin_y + iy * det->desc.step_y;
+					all[k++] = it;
+				}
+		}
+		s = upload(all.data(), all.size(), &det->d_all_items, det->owned); if (s) return s;
+		s = dev_alloc(&det->d_all_dist, (size_t)std::max<int64_t>(plan.windows, 1), det->owned); if (s) return s;
+		s = host_alloc(&det->h_all_dist, (size_t)std::max<int64_t>(plan.windows, 1), det->owned_host); if (s) return s;
+	}
 	det->prepared = true;
 	return FDB_OK;
 }
@@ -649,6 +772,7 @@ int fdb_detect_batch_device(fdb_detector* det, const uint8_t* frames_device, int
 int fdb_detect_enqueue_device(fdb_detector* det, const uint8_t* frames_device, int32_t n_frames, fdb_window_score* dense_out_device) {
 	if (!det || !det->prepared) return fail(FDB_ERR_INVALID_ARGUMENT, "detector not prepared (call fdb_detector_prepare)");
 	int s = check_ctx(det->ctx); if (s) return s;
+	if (!det->wvm) return fail(FDB_ERR_INVALID_ARGUMENT, "this entry point needs a detector with a WVM first stage");
 	if (n_frames < 0 || n_frames > det->max_batch) return fail(FDB_ERR_INVALID_ARGUMENT, "n_frames exceeds the prepared batch");
 	const Plan& plan = det->plan;
 	for (int base = 0; base < n_frames; base += det->chunk) {
@@ -663,6 +787,7 @@ int fdb_detect_enqueue_device(fdb_detector* det, const uint8_t* frames_device, i
 int fdb_detect_profile_device(fdb_detector* det, const uint8_t* frames_device, int32_t n_frames, double ms_out[6]) {
 	if (!det || !det->prepared) return fail(FDB_ERR_INVALID_ARGUMENT, "detector not prepared (call fdb_detector_prepare)");
 	int s = check_ctx(det->ctx); if (s) return s;
+	if (!det->wvm) return fail(FDB_ERR_INVALID_ARGUMENT, "this entry point needs a detector with a WVM first stage");
 	if (n_frames < 0 || n_frames > det->max_batch || !ms_out) return fail(FDB_ERR_INVALID_ARGUMENT, "bad arguments");
 	fdb_ctx* c = det->ctx;
 	const Plan& plan = det->plan;
@@ -688,6 +813,7 @@ int fdb_detect_roi(fdb_detector* det, const uint8_t* frame_host, int64_t pitch, 
 		int32_t roi_h, int32_t stage, fdb_detection* detections_out, int64_t det_cap, int64_t* n_detections) {
 	if (!det || !det->prepared) return fail(FDB_ERR_INVALID_ARGUMENT, "detector not prepared (call fdb_detector_prepare)");
 	int s = check_ctx(det->ctx); if (s) return s;
+	if (!det->wvm) return fail(FDB_ERR_INVALID_ARGUMENT, "this entry point needs a detector with a WVM first stage");
 	if (!frame_host) return fail(FDB_ERR_INVALID_ARGUMENT, "null frame");
 	if (stage < FDB_STAGE_WVM || stage > FDB_STAGE_NMS) return fail(FDB_ERR_INVALID_ARGUMENT, "bad stage");
 	Plan plan = det->plan;
@@ -717,6 +843,7 @@ int fdb_extract_patches(fdb_detector* det, const uint8_t* frame_host, int64_t pi
 		int64_t* n_windows) {
 	if (!det || !det->prepared) return fail(FDB_ERR_INVALID_ARGUMENT, "detector not prepared (call fdb_detector_prepare)");
 	int s = check_ctx(det->ctx); if (s) return s;
+	if (!det->wvm) return fail(FDB_ERR_INVALID_ARGUMENT, "this entry point needs a detector with a WVM first stage");
 	const Plan& plan = det->plan;
 	if (n_windows) *n_windows = plan.windows;
 	if (!frame_host || !patches_out) return fail(FDB_ERR_INVALID_ARGUMENT, "null buffer");
@@ -759,6 +886,85 @@ int fdb_pyramid_layer(fdb_detector* det, const uint8_t* frame_host, int64_t pitc
 	CUDA_TRY(cudaMemcpy2DAsync(out, (size_t)L->width, src, (size_t)im.pitch, (size_t)L->width, (size_t)L->height, cudaMemcpyDeviceToHost, st));
 	CUDA_TRY(cudaStreamSynchronize(st));
 	return FDB_OK;
+}
+
+int fdb_feature_shape(const fdb_feature_desc* desc, int32_t patch_width, int32_t patch_height, int32_t* dim, int32_t* is_float) {
+	if (!desc) return fail(FDB_ERR_INVALID_ARGUMENT, "null feature descriptor");
+	FeatureShape sh;
+	int s = feature_shape(*desc, patch_width, patch_height, &sh); if (s) return s;
+	if (dim) *dim = sh.dim;
+	if (is_float) *is_float = sh.is_float;
+	return FDB_OK;
+}
+
+int fdb_detector_set_feature(fdb_detector* det, const fdb_feature_desc* desc) {
+	if (!det || !desc) return fail(FDB_ERR_INVALID_ARGUMENT, "null argument");
+	int s = check_ctx(det->ctx); if (s) return s;
+	FeatureShape sh;
+	s = feature_shape(*desc, det->desc.patch_width, det->desc.patch_height, &sh); if (s) return s;
+	CUDA_TRY(cudaStreamSynchronize(det->ctx->stream));
+	release(det); /* buffers depend on the feature space: prepare again */
+	det->fdesc = *desc;
+	det->has_feature = true;
+	return FDB_OK;
+}
+
+int fdb_extract_features(fdb_detector* det, const uint8_t* frame_host, int64_t pitch, const int32_t* layer_x_y, int64_t n, void* out) {
+	if (!det || !det->prepared) return fail(FDB_ERR_INVALID_ARGUMENT, "detector not prepared (call fdb_detector_prepare)");
+	int s = check_ctx(det->ctx); if (s) return s;
+	if (!frame_host || (n > 0 && (!layer_x_y || !out))) return fail(FDB_ERR_INVALID_ARGUMENT, "null buffer");
+	if (!det->has_feature || det->feat.kind == FDB_FEATURE_HQ64)
+		return fail(FDB_ERR_INVALID_ARGUMENT, "no feature space set (hq64 patches: fdb_extract_patches)");
+	const Plan& plan = det->plan;
+	if (pitch < plan.width) return fail(FDB_ERR_INVALID_ARGUMENT, "pitch smaller than the frame width");
+	cudaStream_t st = det->ctx->stream;
+	Slot& sl = det->slots[0];
+	const int pw = det->desc.patch_width, ph = det->desc.patch_height;
+	std::vector<SvmItem> items((size_t)n);
+	for (int64_t i = 0; i < n; ++i) {
+		int li = -1;
+		for (size_t k = 0; k < plan.layers.size(); ++k) if (plan.layers[k].index == layer_x_y[3 * i]) li = (int)k;
+		/* DirectPyramidFeatureExtractor.cpp:133-136: out-of-bounds windows yield no patch */
+		if (li < 0) return fail(FDB_ERR_INVALID_ARGUMENT, "no such pyramid layer");
+		const int x = layer_x_y[3 * i + 1], y = layer_x_y[3 * i + 2];
+		if (x < 0 || y < 0 || x + pw > plan.layers[(size_t)li].width || y + ph > plan.layers[(size_t)li].height)
+			return fail(FDB_ERR_INVALID_ARGUMENT, "window outside the pyramid layer");
+		SvmItem it; it.frame = 0; it.layer = li; it.x = x; it.y = y;
+		items[(size_t)i] = it;
+	}
+	CUDA_TRY(cudaMemcpy2DAsync(sl.d_frames, (size_t)plan.width, frame_host, (size_t)pitch, (size_t)plan.width, (size_t)plan.height,
+			cudaMemcpyHostToDevice, st));
+	sl.frames_dev = sl.d_frames; sl.base = 0; sl.n = 1;
+	s = enqueue_stage1(det, sl, st, sl.d_frames, 1, plan, det->d_layers, 0, nullptr, nullptr, false);
+	if (s) return s;
+	if (det->feat.layer_channels) {
+		launch_feature_layers(st, det->feat, sl.d_frames, plan.width, plan.height, 1, sl.d_arena, plan.arena_bytes, det->d_layers,
+				sl.d_farena, det->farena_bytes);
+		det->ctx->launches++;
+	}
+	const size_t vec_bytes = (size_t)det->feat.dim * (det->feat.is_float ? 4 : 1);
+	const int batch = std::min<int>(FEAT_BATCH, det->items_cap);
+	for (int64_t off = 0; off < n; off += batch) {
+		const int m = (int)std::min<int64_t>(batch, n - off);
+		CUDA_TRY(cudaMemcpyAsync(sl.d_items, items.data() + off, sizeof(SvmItem) * (size_t)m, cudaMemcpyHostToDevice, st));
+		launch_feature_patches(st, det->feat, sl.d_frames, plan.width, plan.height, sl.d_arena, plan.arena_bytes, det->d_layers,
+				sl.d_farena, det->farena_bytes, sl.d_items, m, sl.d_feat);
+		det->ctx->launches++;
+		CUDA_TRY(cudaGetLastError());
+		CUDA_TRY(cudaMemcpyAsync((uint8_t*)out + (size_t)off * vec_bytes, sl.d_feat, vec_bytes * (size_t)m, cudaMemcpyDeviceToHost, st));
+		CUDA_TRY(cudaStreamSynchronize(st));
+	}
+	return FDB_OK;
+}
+
+int fdb_detect_single(fdb_detector* det, const uint8_t* frames_host, int64_t pitch, int32_t n_frames, double* distance_out,
+		fdb_detection* detections_out, int64_t det_cap, int64_t* n_detections) {
+	if (!det || !det->prepared) return fail(FDB_ERR_INVALID_ARGUMENT, "detector not prepared (call fdb_detector_prepare)");
+	int s = check_ctx(det->ctx); if (s) return s;
+	if (det->wvm || !det->svm) return fail(FDB_ERR_INVALID_ARGUMENT, "fdb_detect_single needs a detector created with an SVM only");
+	if (n_frames < 0 || (n_frames > 0 && !frames_host)) return fail(FDB_ERR_INVALID_ARGUMENT, "bad frame batch");
+	if (pitch < det->plan.width) return fail(FDB_ERR_INVALID_ARGUMENT, "pitch smaller than the frame width");
+	return detect_single(det, frames_host, false, pitch, n_frames, distance_out, detections_out, det_cap, n_detections);
 }
 
 int fdb_detector_last_counts(fdb_detector* det, int64_t counts[5]) {

@@ -21,6 +21,14 @@ SCORE_DTYPE = np.dtype([("fout", "f4"), ("level", "i4")])
 LAYER_FIELDS = [f for f, _ in capi.LayerInfo._fields_]
 
 
+def feature_shape(feature, patch_w, patch_h):
+    """(dim, numpy dtype) of a feature space for a patch size (fdb_feature_shape, host only)"""
+    lib = capi.load_library()
+    dim, is_float = C.c_int32(), C.c_int32()
+    capi.check(lib, lib.fdb_feature_shape(C.byref(feature), patch_w, patch_h, C.byref(dim), C.byref(is_float)))
+    return dim.value, (np.float32 if is_float.value else np.uint8)
+
+
 class Context:
     """fdb_ctx: one CUDA device + stream. Raises FdbError when no sm_100 GPU is usable."""
 
@@ -122,17 +130,24 @@ class ProbabilisticSvmClassifier:
 class SlidingWindowCascade:
     """detection::FiveStageSlidingWindowDetector / SlidingWindowDetector over frame batches."""
 
-    def __init__(self, ctx, det_kwargs, wvm_model, svm_model=None):
+    def __init__(self, ctx, det_kwargs, wvm_model, svm_model=None, feature=None):
+        """wvm_model None + svm_model: the `single` psvm detector (every window through the SVM).
+        feature: capi.FeatureDesc - feature space of the SVM (default: the HistEq64 patch)."""
         self.ctx = ctx
-        self.wvm = ProbabilisticWvmClassifier(ctx, wvm_model)
+        self.wvm = ProbabilisticWvmClassifier(ctx, wvm_model) if wvm_model is not None else None
         self.svm = ProbabilisticSvmClassifier(ctx, svm_model) if svm_model is not None else None
         self._desc = detector_desc(**det_kwargs)
         h = C.c_void_p()
-        capi.check(ctx.lib, ctx.lib.fdb_detector_create(ctx.h, C.byref(self._desc), self.wvm.h,
+        capi.check(ctx.lib, ctx.lib.fdb_detector_create(ctx.h, C.byref(self._desc), self.wvm.h if self.wvm else None,
                                                         self.svm.h if self.svm else None, C.byref(h)))
         self.h = h
         self.width = self.height = None
         self.patch = (self._desc.patch_width, self._desc.patch_height)
+        self.feature = feature
+        self.feature_dim, self.feature_dtype = self.patch[0] * self.patch[1], np.uint8
+        if feature is not None:
+            capi.check(ctx.lib, ctx.lib.fdb_detector_set_feature(self.h, C.byref(feature)))
+            self.feature_dim, self.feature_dtype = feature_shape(feature, *self.patch)
 
     def __del__(self):
         try:
@@ -225,6 +240,30 @@ class SlidingWindowCascade:
         capi.check(self.ctx.lib, self.ctx.lib.fdb_pyramid_layer(
             self.h, frame.ctypes.data, frame.shape[1], layer_index, out.ctypes.data, out.size))
         return out
+
+    def extract_features(self, frame, layer_x_y):
+        """PyramidFeatureExtractor::extract(layer, x, y) in the SVM's feature space: [n, dim]"""
+        frame = np.ascontiguousarray(frame, np.uint8)
+        lxy = np.ascontiguousarray(layer_x_y, np.int32).reshape(-1, 3)
+        out = np.zeros((lxy.shape[0], self.feature_dim), self.feature_dtype)
+        capi.check(self.ctx.lib, self.ctx.lib.fdb_extract_features(
+            self.h, frame.ctypes.data, frame.shape[1], lxy.ctypes.data, lxy.shape[0], out.ctypes.data))
+        return out
+
+    def detect_single(self, frames, want_distances=True, det_cap=None):
+        """`single` psvm detector: (detections, distances [n, windows] or None)"""
+        frames = np.ascontiguousarray(frames, np.uint8)
+        if frames.ndim == 2:
+            frames = frames[None]
+        n, H, W = frames.shape
+        det_cap = det_cap or max(1024, n * self.windows_per_frame)
+        dets = np.zeros(det_cap, DETECTION_DTYPE)
+        dist = np.zeros((n, self.windows_per_frame), np.float64) if want_distances else None
+        cnt = C.c_int64()
+        capi.check(self.ctx.lib, self.ctx.lib.fdb_detect_single(
+            self.h, frames.ctypes.data, W, n, dist.ctypes.data if want_distances else None,
+            dets.ctypes.data, det_cap, C.byref(cnt)))
+        return dets[:cnt.value].copy(), dist
 
     def last_counts(self):
         c = (C.c_int64 * 5)()

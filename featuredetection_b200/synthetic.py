@@ -300,9 +300,20 @@ def feature_desc(kind="hq64", gradient_kernel=1, blur_kernel=0, bins=9, signed_g
     return d
 
 
-def make_feature_svm(vectors, seed, num_sv=1024, gamma=0.2):
+def feature_sample_windows(layers, patch_w, patch_h, per_layer, seed):
+    """seeded window corners {layer index, x, y} inside every pyramid layer (layers: dicts with index/width/height)"""
+    rng = np.random.default_rng(seed)
+    out = []
+    for L in layers:
+        for _ in range(per_layer):
+            out.append((L["index"], int(rng.integers(0, L["width"] - patch_w + 1)), int(rng.integers(0, L["height"] - patch_h + 1))))
+    return np.array(out, np.int32)
+
+
+def make_feature_svm(vectors, seed, num_sv=1024, gamma=0.2, center=False):
     """RBF SVM whose support vectors are drawn (seeded) from the given feature vectors [n, dim] (u8 or f32):
-    SURVEY.md 8(d) - coefficients ~ N(0,1) float32, bias 0, threshold 0, logistic defaults."""
+    SURVEY.md 8(d) - coefficients ~ N(0,1) float32, bias 0, threshold 0, logistic defaults.
+    center: subtract the mean coefficient so that distances scatter around the threshold 0."""
     rng = np.random.default_rng(seed)
     vectors = np.ascontiguousarray(vectors)
     idx = rng.integers(0, vectors.shape[0], num_sv)
@@ -312,4 +323,6 @@ def make_feature_svm(vectors, seed, num_sv=1024, gamma=0.2):
         idx2 = rng.integers(0, vectors.shape[0], num_sv)
         sv = (np.float32(0.5) * (sv.astype(np.float32) + vectors[idx2].astype(np.float32))).astype(np.float32)
     coef = rng.standard_normal(num_sv).astype(np.float32)
+    if center:
+        coef = (coef - np.float32(coef.astype(np.float64).mean())).astype(np.float32)
     return SvmModel(sv, coef, gamma=gamma)

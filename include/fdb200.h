@@ -290,7 +290,8 @@ FDB_API int fdb_svm_get_probability(fdb_svm* svm, const void* vectors_host, int6
 /* ------------------------------------------------------------------------------------------
  * Detector  (PyramidFeatureExtractor + Detector surface)
  * ---------------------------------------------------------------------------------------- */
-/* svm may be NULL (plain SlidingWindowDetector, ffpDetectApp "single" with pwvm). */
+/* svm may be NULL (plain SlidingWindowDetector, ffpDetectApp "single" with pwvm); wvm may be NULL when svm is
+ * given ("single" with psvm: see fdb_detect_single). */
 FDB_API int fdb_detector_create(fdb_ctx* ctx, const fdb_detector_desc* desc,
 		fdb_wvm* wvm, fdb_svm* svm, fdb_detector** out);
 FDB_API void fdb_detector_destroy(fdb_detector* det);
@@ -377,6 +378,34 @@ typedef struct fdb_svm_file fdb_svm_file;
 FDB_API int fdb_svm_file_load(const char* path, fdb_svm_file** out);
 FDB_API const fdb_svm_desc* fdb_svm_file_desc(const fdb_svm_file* file);
 FDB_API void fdb_svm_file_free(fdb_svm_file* file);
+
+/* ------------------------------------------------------------------------------------------
+ * Feature spaces
+ * ---------------------------------------------------------------------------------------- */
+/* Length and element type (0: u8, 1: float32) of the feature vector a patch of patch_width x patch_height
+ * becomes in this feature space (host only). */
+FDB_API int fdb_feature_shape(const fdb_feature_desc* desc, int32_t patch_width, int32_t patch_height,
+		int32_t* dim, int32_t* is_float);
+
+/* Gives the detector's SVM (the secondClassifier of a fiveStageCascade, or the classifier of a `single`
+ * detector) its own feature space: FilteringPyramidFeatureExtractor::addPatchFilter / DirectPyramidFeatureExtractor::
+ * addLayerFilter (ffpDetectApp.cpp:445-461, AdaptiveTracking.cpp:183-227). The WVM stage always sees HistEq64
+ * patches. Call before fdb_detector_prepare; the SVM's support vectors must have the feature's type and length. */
+FDB_API int fdb_detector_set_feature(fdb_detector* det, const fdb_feature_desc* desc);
+
+/* PyramidFeatureExtractor::extract(layer, x, y) (DirectPyramidFeatureExtractor.cpp:125-143 +
+ * FilteringPyramidFeatureExtractor.hpp:61-66) for n windows {layer index, x, y} of one frame: writes n feature
+ * vectors (fdb_feature_shape elements each) to out (host). Windows must lie inside their layer. */
+FDB_API int fdb_extract_features(fdb_detector* det, const uint8_t* frame_host, int64_t pitch,
+		const int32_t* layer_x_y, int64_t n, void* out);
+
+/* `single` detector of ffpDetectApp.cpp:427-500 with classifier psvm: a detector created with wvm == NULL
+ * classifies EVERY window with the SVM in its feature space (SlidingWindowDetector.cpp:87-98) and returns the
+ * positives in canonical order, probability = ProbabilisticSvmClassifier::getProbability.
+ * distance_out: NULL or host [n_frames * windows_per_frame] hyperplane distances.
+ * (fdb_detect_batch on such a detector does the same without distance_out.) */
+FDB_API int fdb_detect_single(fdb_detector* det, const uint8_t* frames_host, int64_t pitch, int32_t n_frames,
+		double* distance_out, fdb_detection* detections_out, int64_t det_cap, int64_t* n_detections);
 
 /* Per-stage counters of the last detect call (TOT/TACC-style counters, ffpDetectApp.cpp:650-657):
  * [0] windows, [1] wvm positives, [2] after OE, [3] svm positives, [4] after NMS. */

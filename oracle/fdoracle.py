@@ -139,6 +139,9 @@ def ref():
         R.ref_detect_frame.restype = C.c_int64
         R.ref_detect_frame.argtypes = [C.POINTER(capi.DetectorDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                        C.c_int, C.c_void_p, C.POINTER(C.c_int64), C.c_void_p, C.c_int64, C.POINTER(C.c_double)]
+        R.ref_detect_frame_ex.restype = C.c_int64
+        R.ref_detect_frame_ex.argtypes = [C.POINTER(capi.DetectorDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                          C.c_int, C.c_void_p, C.POINTER(C.c_int64), C.c_void_p, C.c_int64, C.POINTER(C.c_double)]
         R.ref_gradient_bin_luts.restype = None
         R.ref_gradient_bin_luts.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         R.ref_lbp.restype = None; R.ref_lbp.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
@@ -441,7 +444,7 @@ def detect_frame(det_kwargs, wvm, svm, frame, stage=capi.FDB_STAGE_NMS, roi=(0, 
                 counts=list(counts), timing=list(tim), layers=layers, svm_dense=svm_dense)
 
 
-def ref_detect_frame(det_kwargs, wvm, svm, frame, stage=capi.FDB_STAGE_NMS, want_dense=True, det_cap=1 << 16):
+def ref_detect_frame(det_kwargs, wvm, svm, frame, stage=capi.FDB_STAGE_NMS, want_dense=True, det_cap=1 << 16, svm_features=None):
     """One frame through the reference's own classes (oracle/_ref; see ref_driver.cpp:ref_detect_frame).
     wvm / svm are Wvm / Svm objects created with use_ref=True. Returns a dict."""
     from featuredetection_b200.synthetic import detector_desc
@@ -461,8 +464,9 @@ def ref_detect_frame(det_kwargs, wvm, svm, frame, stage=capi.FDB_STAGE_NMS, want
         total = lib().fdo_enumerate(p, desc.patch_width, desc.patch_height, max(desc.step_x, 1), max(desc.step_y, 1), 0, 0, 0, 0, infos, p.contents.n_layers)
         lib().fdo_pyramid_free(p)
         dense = np.zeros(total, SCORE_DTYPE)
-    n = ref().ref_detect_frame(C.byref(desc), wvm.h, svm.h if svm is not None else None, frame.ctypes.data, W, H, stage,
-                               dense.ctypes.data if dense is not None else None, C.byref(nwin), wins.ctypes.data, det_cap, tim)
+    n = ref().ref_detect_frame_ex(C.byref(desc), wvm.h, svm.h if svm is not None else None,
+                                  svm_features.h if svm_features is not None else None, frame.ctypes.data, W, H, stage,
+                                  dense.ctypes.data if dense is not None else None, C.byref(nwin), wins.ctypes.data, det_cap, tim)
     if n < 0:
         raise RuntimeError("ref_detect_frame failed (%d)" % n)
     return dict(windows=int(nwin.value), dense=dense, det_windows=wins[:n].copy(), timing=list(tim))

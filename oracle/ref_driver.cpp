@@ -210,8 +210,22 @@ int ref_overlap_eliminate(float dist, float ratio, int n, const int* cx, const i
  * The OpenCV-owned pyramid (cv::resize / cv::pyrDown) and the cv::minMaxLoc based grid NMS cannot be
  * compiled without OpenCV; those two steps come from the restatement in fd_oracle.c.
  * timing_out (NULL or 5 doubles, seconds): pyramid, extract+hq64, wvm, oe, svm+nms. */
+int64_t ref_detect_frame_ex(const fdb_detector_desc* desc, void* wvm_h, void* svm_h, const fdo_features* feat, const uint8_t* frame,
+		int width, int height, int stage, fdb_window_score* dense_out, int64_t* windows_out, int64_t* det_windows_out,
+		int64_t det_cap, double* timing_out);
+
 int64_t ref_detect_frame(const fdb_detector_desc* desc, void* wvm_h, void* svm_h, const uint8_t* frame, int width, int height,
 		int stage, fdb_window_score* dense_out, int64_t* windows_out, int64_t* det_windows_out, int64_t det_cap, double* timing_out) {
+	return ref_detect_frame_ex(desc, wvm_h, svm_h, nullptr, frame, width, height, stage, dense_out, windows_out, det_windows_out,
+			det_cap, timing_out);
+}
+
+/* feat != NULL: the SVM stage classifies the window's vector in that feature space (the second extractor of a
+ * two-feature cascade; its layer filters and patch filter come from fd_features.c, which is pinned bit for bit
+ * against the reference's own filter classes - see ref_features.cpp) with the reference's own SvmClassifier. */
+int64_t ref_detect_frame_ex(const fdb_detector_desc* desc, void* wvm_h, void* svm_h, const fdo_features* feat, const uint8_t* frame,
+		int width, int height, int stage, fdb_window_score* dense_out, int64_t* windows_out, int64_t* det_windows_out,
+		int64_t det_cap, double* timing_out) {
 	typedef std::chrono::steady_clock clk;
 	auto secs = [](clk::time_point a, clk::time_point b) { return std::chrono::duration<double>(b - a).count(); };
 	RefWvm* rw = (RefWvm*)wvm_h;
@@ -263,8 +277,28 @@ int64_t ref_detect_frame(const fdb_detector_desc* desc, void* wvm_h, void* svm_h
 	vector<shared_ptr<detection::ClassifiedPatch>> positives = classified;
 	if (stage >= FDB_STAGE_SVM && rs) {
 		positives.clear();
+		vector<vector<uint8_t>> filtered; /* filtered pyramid layers, built on first use */
 		for (const auto& p : classified) {
-			bool ok = rs->psvm->classify(p->getPatch()->getData());
+			Mat data = p->getPatch()->getData();
+			if (feat) {
+				int64_t win = -1;
+				for (const auto& id : ids) if (id.first == p->getPatch().get()) win = id.second;
+				int li = 0;
+				while (li + 1 < pyr->n_layers && win >= infos[(size_t)li + 1].first_window) ++li;
+				const int64_t local = win - infos[(size_t)li].first_window;
+				const int wy = (int)(local / infos[(size_t)li].windows_x), wx = (int)(local % infos[(size_t)li].windows_x);
+				const fdo_layer& L = pyr->layers[li];
+				const int chn = fdo_features_layer_channels(feat);
+				if (chn && filtered.empty()) filtered.resize((size_t)pyr->n_layers);
+				if (chn && filtered[(size_t)li].empty()) {
+					filtered[(size_t)li].resize((size_t)L.width * L.height * chn);
+					fdo_features_filter_layer(feat, L.data, L.width, L.height, filtered[(size_t)li].data());
+				}
+				const bool is_float = fdo_features_is_float(feat) != 0;
+				data = Mat(1, fdo_features_dim(feat), is_float ? CV_32F : CV_8U);
+				fdo_features_patch(feat, chn ? filtered[(size_t)li].data() : L.data, L.width, wx * sx, wy * sy, data.data);
+			}
+			bool ok = rs->psvm->classify(data);
 			if (ok) positives.push_back(make_shared<detection::ClassifiedPatch>(p->getPatch(), ok));
 		}
 	}
