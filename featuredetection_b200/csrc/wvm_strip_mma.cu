@@ -43,7 +43,9 @@ namespace fdb {
 #define STRIP2_MIN_CTAS 3
 #endif
 #define STRIP2_PITCH 64      /* bytes per tile row */
-#define STRIP2_STAGE 36      /* ints per window row of the D staging area (16-byte aligned rows, conflict-free reads) */
+#define STRIP2_STAGE 40      /* ints per window row of the D staging area: 16-byte aligned rows; the 16 int2 fragment stores per
+                              * window are conflict-free (half-warp rows 8 banks apart), the rarer uint4 reads 2-way */
+#define STRIP2_HKU (32 * STRIP2_STAGE) /* float offset of the cascade state behind the staging area: hk[8][32], u[8][32] */
 
 static_assert(WVM_KA == 8, "the fragment table holds 8 filters x 4 grey values = 32 columns");
 
@@ -79,6 +81,7 @@ __global__ void __launch_bounds__(STRIP2_WARPS * 32, STRIP2_MIN_CTAS) wvm_strip_
 		Candidate* __restrict__ cand, int* __restrict__ cand_count, int cand_cap, const DeepQueue q,
 		const CUtensorMap* __restrict__ tmaps) {
 	static_assert(PW % 4 == 0 && PW <= 32, "patch width must be a multiple of 4, at most 32");
+	static_assert((STRIP2_HKU + 2 * WVM_KA * 32) * 4 <= MmaCfg<PW, PH>::LUT_BYTES, "cascade state must fit behind the staging area");
 	using Cfg = MmaCfg<PW, PH>;
 	constexpr int NW = Cfg::NW, WPR = PW / 4, KS = Cfg::KS, TR = Cfg::TILE_ROWS;
 	extern __shared__ __align__(128) uint8_t smem8[];
@@ -139,15 +142,8 @@ __global__ void __launch_bounds__(STRIP2_WARPS * 32, STRIP2_MIN_CTAS) wvm_strip_
 	int org_i[4];
 #pragma unroll
 	for (int i = 0; i < 4; ++i) org_i[i] = __shfl_sync(0xffffffffu, org, g + 8 * i);
-	/* tile offsets of the two patch words this lane feeds per k-step: j0 = 8 s + t, j1 = j0 + 4 */
-	uint32_t offp[KS];
-#pragma unroll
-	for (int s = 0; s < KS; ++s) {
-		const int j0 = 8 * s + t, j1 = j0 + 4;
-		const uint32_t o0 = j0 < NW ? (uint32_t)((j0 / WPR) * STRIP2_PITCH + (j0 % WPR) * 4) : 0u;
-		const uint32_t o1 = j1 < NW ? (uint32_t)((j1 / WPR) * STRIP2_PITCH + (j1 % WPR) * 4) : 0u;
-		offp[s] = o0 | (o1 << 16);
-	}
+	float* const s_hk = reinterpret_cast<float*>(s_lut) + STRIP2_HKU + lane; /* hk_kernel_eval[i]: s_hk[i * 32] */
+	float* const s_u = s_hk + WVM_KA * 32;                                   /* u_kernel_eval[i]: s_u[i * 32] */
 	/* LUT sharing: after a 4x4 byte transpose over the lanes gw, gw+8, gw+16, gw+24 this lane holds the word of
 	 * bin 4 q + iw; it stores it for the 4 reader lanes 4 gw + t' with one 16-byte store */
 	const uint32_t sel1 = (iw & 1) ? 0x3715u : 0x6240u, sel2 = (iw & 2) ? 0x3276u : 0x5410u;
@@ -160,10 +156,7 @@ __global__ void __launch_bounds__(STRIP2_WARPS * 32, STRIP2_MIN_CTAS) wvm_strip_
 		__syncwarp();
 		const bool active = w < nrows;
 		const uint8_t* const tw = s_tile + org + w * STRIP2_PITCH; /* top-left bin of this lane's window */
-		uint32_t wq[16];
 		uint32_t total = 0, sxx = 0;
-#pragma unroll
-		for (int k = 0; k < 16; ++k) wq[k] = 0;
 		if (active) {
 			if (w == 0) { /* histogram of the first window of the run */
 #pragma unroll
@@ -181,27 +174,30 @@ __global__ void __launch_bounds__(STRIP2_WARPS * 32, STRIP2_MIN_CTAS) wvm_strip_
 					atomicAdd(s_hist + r_in[c] * 32, 1u);
 				}
 			}
-			float cdf = 0.f;
-#pragma unroll
-			for (int k = 0; k < 16; ++k) {
-#pragma unroll
-				for (int b = 0; b < 4; ++b) {
-					const uint32_t cnt = s_hist[(4 * k + b) * 32];
-					const uint32_t e = hq_step(cdf, cnt, stretch);
-					wq[k] |= e << (8 * b);
-					total += cnt * e;
-					sxx += cnt * e * e;
-				}
-			}
 		}
-		/* --- share the LUTs --- */
+		/* --- equalisation LUT (sequential float cumsum) of 4 bins at a time, shared with the 4 reader lanes at once.
+		 * Rolled on purpose: the fully unrolled form made the kernel 100 KB of code and instruction-fetch bound --- */
+		{
+			float cdf = 0.f;
+#pragma unroll 2
+			for (int k = 0; k < 16; ++k) {
+				uint32_t wq = 0;
+				if (active) {
 #pragma unroll
-		for (int k = 0; k < 16; ++k) {
-			const uint32_t x1 = __shfl_xor_sync(0xffffffffu, wq[k], 8);
-			const uint32_t v1 = __byte_perm(wq[k], x1, sel1);
-			const uint32_t x2 = __shfl_xor_sync(0xffffffffu, v1, 16);
-			const uint32_t v2 = __byte_perm(v1, x2, sel2);
-			*reinterpret_cast<uint4*>(s_lut + (4 * k) * 128 + woff) = make_uint4(v2, v2, v2, v2);
+					for (int b = 0; b < 4; ++b) {
+						const uint32_t cnt = s_hist[(4 * k + b) * 32];
+						const uint32_t e = hq_step(cdf, cnt, stretch);
+						wq |= e << (8 * b);
+						total += cnt * e;
+						sxx += cnt * e * e;
+					}
+				}
+				const uint32_t x1 = __shfl_xor_sync(0xffffffffu, wq, 8);
+				const uint32_t v1 = __byte_perm(wq, x1, sel1);
+				const uint32_t x2 = __shfl_xor_sync(0xffffffffu, v1, 16);
+				const uint32_t v2 = __byte_perm(v1, x2, sel2);
+				*reinterpret_cast<uint4*>(s_lut + (4 * k) * 128 + woff) = make_uint4(v2, v2, v2, v2);
+			}
 		}
 		__syncwarp();
 		/* iimg_xx->data[dr]: float32 accumulation in row order (IImg.cpp:33-47); exact unless >= 2^24 */
@@ -229,15 +225,19 @@ __global__ void __launch_bounds__(STRIP2_WARPS * 32, STRIP2_MIN_CTAS) wvm_strip_
 #pragma unroll
 				for (int c = 0; c < 4; ++c) acc[a][b][c] = 0;
 		const uint8_t* const trow = s_tile + w * STRIP2_PITCH;
-#pragma unroll
+#pragma unroll 2
 		for (int s = 0; s < KS; ++s) {
 			const uint4 bA = __ldg(m.bfrag + (s * 32 + lane) * 2), bB = __ldg(m.bfrag + (s * 32 + lane) * 2 + 1);
+			/* tile offsets of the two patch words this lane feeds in this k-step: j0 = 8 s + t, j1 = j0 + 4 (0 past the patch:
+			 * the B fragment is zero there) */
+			const int j0 = 8 * s + t, j1 = j0 + 4;
+			const int off2[2] = {j0 < NW ? (j0 / WPR) * STRIP2_PITCH + (j0 % WPR) * 4 : 0, j1 < NW ? (j1 / WPR) * STRIP2_PITCH + (j1 % WPR) * 4 : 0};
 			uint32_t a[4][2];
 #pragma unroll
 			for (int i = 0; i < 4; ++i)
 #pragma unroll
 				for (int h = 0; h < 2; ++h) {
-					const uint8_t* p = trow + org_i[i] + ((offp[s] >> (16 * h)) & 0xffffu);
+					const uint8_t* p = trow + org_i[i] + off2[h];
 					const uint32_t e0 = lut_r[p[0] * 128 + i], e1 = lut_r[p[1] * 128 + i];
 					const uint32_t e2 = lut_r[p[2] * 128 + i], e3 = lut_r[p[3] * 128 + i];
 					a[i][h] = e0 | (e1 << 8) | (e2 << 16) | (e3 << 24);
@@ -262,51 +262,29 @@ __global__ void __launch_bounds__(STRIP2_WARPS * 32, STRIP2_MIN_CTAS) wvm_strip_
 							make_int2(acc[mt][nt][2 * h], acc[mt][nt][2 * h + 1]);
 		__syncwarp();
 
-		/* --- scalar cascade over the first WVM_KA filters (WvmClassifier.cpp:129-138, 191-346) --- */
-		float hk[WVM_KA], u[WVM_KA];
+		/* --- scalar cascade over the first WVM_KA filters (WvmClassifier.cpp:129-138, 191-346); hk_kernel_eval and
+		 * u_kernel_eval live in shared memory (one column per lane) so that the level loop stays rolled --- */
 #pragma unroll
-		for (int i = 0; i < WVM_KA; ++i) { hk[i] = 0.f; u[i] = 0.f; }
+		for (int i = 0; i < WVM_KA; ++i) s_u[i * 32] = 0.f;                          /* :129-131 */
 		int level = -1;
 		float fout = 0.f;
 		bool alive = active;
-		if (m.per_level >= WVM_KA) {
-			/* usual shape (a wavelet level holds at least WVM_KA filters): u_kernel_eval[lv % per_level] = u[lv] = 0 on
-			 * entry, every index is static and the loop unrolls into straight-line code with one exit test per filter */
-#pragma unroll
-			for (int lv = 0; lv < WVM_KA; ++lv) {
-				if (alive) {
-					level = lv;
-					const int nv = __ldg(m.cntval + lv) - 1;
-					const uint4 d4 = *reinterpret_cast<const uint4*>(s_stage + lane * STRIP2_STAGE + 4 * lv);
-					float un = 0.f;
-					hk[lv] = wvm_kernel_value4(m, lv, d4.x, d4.y, d4.z, d4.w, nv, total_f, sum_xx, &un);
-					u[lv] = un;
-					const float* __restrict__ wgt = m.hk_weights + lv * (lv + 1) / 2;
-					float res = -__ldg(m.lin_thresholds + lv);                      /* :201 */
-#pragma unroll
-					for (int p = 0; p <= lv; ++p) res = __fadd_rn(res, __fmul_rn(__ldg(wgt + p), hk[p])); /* :340-341 */
-					fout = res;
-					alive = fout >= __ldg(m.thresholds + lv) && lv + 1 < m.num_used;
-				}
-			}
-		} else {
 #pragma unroll 1
-			for (int lv = 0; lv < WVM_KA && alive; ++lv) {
+		for (int lv = 0; lv < WVM_KA; ++lv) {
+			if (!__any_sync(0xffffffffu, alive)) break;
+			if (alive) {
 				level = lv;
 				const int nv = __ldg(m.cntval + lv) - 1;
 				const uint4 d4 = *reinterpret_cast<const uint4*>(s_stage + lane * STRIP2_STAGE + 4 * lv);
 				const int n = lv % m.per_level;
-				float un = 0.f;
-#pragma unroll
-				for (int i = 0; i < WVM_KA; ++i) if (i == n) un = u[i];
+				float un = s_u[n * 32];
 				const float kv = wvm_kernel_value4(m, lv, d4.x, d4.y, d4.z, d4.w, nv, total_f, sum_xx, &un);
-#pragma unroll
-				for (int i = 0; i < WVM_KA; ++i) { if (i == n) u[i] = un; if (i == lv) hk[i] = kv; }
+				s_u[n * 32] = un;
+				s_hk[lv * 32] = kv;
 				const float* __restrict__ wgt = m.hk_weights + lv * (lv + 1) / 2;
 				float res = -__ldg(m.lin_thresholds + lv);                      /* :201 */
-#pragma unroll
-				for (int p = 0; p < WVM_KA; ++p)                                /* :340-341 */
-					if (p <= lv) res = __fadd_rn(res, __fmul_rn(__ldg(wgt + p), hk[p]));
+#pragma unroll 1
+				for (int p = 0; p <= lv; ++p) res = __fadd_rn(res, __fmul_rn(__ldg(wgt + p), s_hk[p * 32])); /* :340-341 */
 				fout = res;
 				alive = fout >= __ldg(m.thresholds + lv) && lv + 1 < m.num_used;
 			}
@@ -315,17 +293,20 @@ __global__ void __launch_bounds__(STRIP2_WARPS * 32, STRIP2_MIN_CTAS) wvm_strip_
 		if (active) {
 			const int win = L.first_window + (iy_first + w) * L.windows_x + st.ix0 + col;
 			if (alive) { /* survived every filter of this kernel: rebuild the LUT (own column) and hand the patch over */
-				uint32_t* const mylut = reinterpret_cast<uint32_t*>(s_lut) + lane; /* bin b: mylut[b * 32] */
-				float cdf = 0.f;
-#pragma unroll 8
-				for (int k = 0; k < 64; ++k) mylut[k * 32] = hq_step(cdf, s_hist[k * 32], stretch);
 				const int slot = atomicAdd(q.count, 1);
 				if (slot < q.cap) {
 					DeepRec r;
 					r.frame = frame; r.window = win; r.total_f = total_f; r.sum_xx = sum_xx;
 #pragma unroll
-					for (int i = 0; i < WVM_KA; ++i) { r.hk[i] = hk[i]; r.u[i] = u[i]; }
+					for (int i = 0; i < WVM_KA; ++i) { r.hk[i] = s_hk[i * 32]; r.u[i] = s_u[i * 32]; }
 					q.rec[slot] = r;
+				}
+				/* the LUT area (staging + cascade state) is free again: rebuild this window's own LUT column */
+				uint32_t* const mylut = reinterpret_cast<uint32_t*>(s_lut) + lane; /* bin b: mylut[b * 32] */
+				float cdf = 0.f;
+#pragma unroll 4
+				for (int k = 0; k < 64; ++k) mylut[k * 32] = hq_step(cdf, s_hist[k * 32], stretch);
+				if (slot < q.cap) {
 					for (int rr = 0; rr < PH; ++rr) {
 #pragma unroll
 						for (int k = 0; k < WPR; ++k) {
