@@ -73,6 +73,11 @@ class FeatureDesc(C.Structure):
     ]
 
 
+class SdmDesc(C.Structure):
+    _fields_ = [("num_landmarks", C.c_int32), ("num_cascade_steps", C.c_int32),
+                ("mean_landmarks", C.POINTER(C.c_float)), ("regressors", C.POINTER(C.c_void_p))]
+
+
 class WindowScore(C.Structure):
     _fields_ = [("fout", C.c_float), ("level", C.c_int32)]
 
@@ -148,6 +153,22 @@ SYMBOLS = [
     ("fdb_detector_set_feature", C.c_int, [C.c_void_p, _P(FeatureDesc)]),
     ("fdb_extract_features", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]),
     ("fdb_detect_single", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, _P(C.c_int64)]),
+    ("fdb_sdm_create", C.c_int, [C.c_void_p, _P(SdmDesc), _P(C.c_void_p)]),
+    ("fdb_sdm_destroy", None, [C.c_void_p]),
+    ("fdb_sdm_num_landmarks", C.c_int32, [C.c_void_p]),
+    ("fdb_sdm_num_cascade_steps", C.c_int32, [C.c_void_p]),
+    ("fdb_sdm_file_load", C.c_int, [C.c_char_p, _P(C.c_void_p)]),
+    ("fdb_sdm_file_desc", _P(SdmDesc), [C.c_void_p]),
+    ("fdb_sdm_file_free", None, [C.c_void_p]),
+    ("fdb_sdm_align_rigid", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    ("fdb_sdm_optimize_batch", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int64,
+                                         C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("fdb_sdm_optimize_batch_device", C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int64,
+                                                C.c_void_p, C.c_void_p]),
+    ("fdb_sdm_profile_device", C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int64,
+                                         C.c_void_p, C.c_void_p, _P(C.c_double)]),
+    ("fdb_sdm_descriptors", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32,
+                                      C.c_void_p]),
 ]
 
 _lib = None

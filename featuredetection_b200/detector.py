@@ -269,3 +269,77 @@ class SlidingWindowCascade:
         c = (C.c_int64 * 5)()
         capi.check(self.ctx.lib, self.ctx.lib.fdb_detector_last_counts(self.h, c))
         return list(c)
+
+
+class SdmLandmarkModel:
+    """fdb_sdm: superviseddescent::SdmLandmarkModel + SdmLandmarkModelFitting (SdmLandmarkModel.hpp:44-256) for batches of
+    faces. `model` is a featuredetection_b200.synthetic.SdmModel; `path` a reference text model (SdmLandmarkModel::load)."""
+
+    def __init__(self, ctx, model=None, path=None):
+        self.ctx, self.lib = ctx, ctx.lib
+        self.h = None
+        h = C.c_void_p()
+        if path is not None:
+            f = C.c_void_p()
+            capi.check(self.lib, self.lib.fdb_sdm_file_load(str(path).encode(), C.byref(f)))
+            try:
+                capi.check(self.lib, self.lib.fdb_sdm_create(ctx.h, self.lib.fdb_sdm_file_desc(f), C.byref(h)))
+            finally:
+                self.lib.fdb_sdm_file_free(f)
+        else:
+            regs = (C.c_void_p * len(model.regressors))(*[r.ctypes.data for r in model.regressors])
+            desc = capi.SdmDesc(model.num_landmarks, len(model.regressors), model.mean.ctypes.data_as(C.POINTER(C.c_float)), regs)
+            capi.check(self.lib, self.lib.fdb_sdm_create(ctx.h, C.byref(desc), C.byref(h)))
+        self.h = h
+        self.num_landmarks = int(self.lib.fdb_sdm_num_landmarks(h))
+        self.num_cascade_steps = int(self.lib.fdb_sdm_num_cascade_steps(h))
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.lib.fdb_sdm_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def align_rigid(self, boxes_xywh):
+        """alignRigid(mean, faceBox) for [n][4] integer boxes -> [n][2L] float32 start shapes"""
+        boxes = np.ascontiguousarray(boxes_xywh, np.int32).reshape(-1, 4)
+        out = np.empty((boxes.shape[0], 2 * self.num_landmarks), np.float32)
+        capi.check(self.lib, self.lib.fdb_sdm_align_rigid(self.h, boxes.ctypes.data, boxes.shape[0], out.ctypes.data))
+        return out
+
+    def optimize(self, frames, shapes, face_frame=None, want_features=False):
+        """optimize(modelShape, image) for every face: frames [n][H][W] u8, shapes [faces][2L] -> (shapes, status[, features])"""
+        frames = np.ascontiguousarray(frames, np.uint8)
+        if frames.ndim == 2:
+            frames = frames[None]
+        shapes = np.ascontiguousarray(shapes, np.float32).reshape(-1, 2 * self.num_landmarks).copy()
+        n_faces = shapes.shape[0]
+        ff = None if face_frame is None else np.ascontiguousarray(face_frame, np.int32)
+        status = np.zeros(n_faces, np.int32)
+        feats = np.zeros((self.num_cascade_steps, n_faces, 279 * self.num_landmarks), np.float32) if want_features else None
+        capi.check(self.lib, self.lib.fdb_sdm_optimize_batch(
+            self.h, frames.ctypes.data, frames.shape[2], frames.shape[2], frames.shape[1], frames.shape[0],
+            None if ff is None else ff.ctypes.data, n_faces, shapes.ctypes.data, status.ctypes.data,
+            None if feats is None else feats.ctypes.data))
+        return (shapes, status, feats) if want_features else (shapes, status)
+
+    def optimize_device(self, frames_ptr, width, height, n_frames, face_frame_ptr, n_faces, shapes_ptr, status_ptr=None):
+        capi.check(self.lib, self.lib.fdb_sdm_optimize_batch_device(self.h, frames_ptr, width, height, n_frames, face_frame_ptr, n_faces,
+                                                                    shapes_ptr, status_ptr))
+
+    def profile_device(self, frames_ptr, width, height, n_frames, face_frame_ptr, n_faces, shapes_ptr, status_ptr=None):
+        ms = (C.c_double * 4)()
+        capi.check(self.lib, self.lib.fdb_sdm_profile_device(self.h, frames_ptr, width, height, n_frames, face_frame_ptr, n_faces,
+                                                             shapes_ptr, status_ptr, ms))
+        return dict(hog=ms[0], gemm=ms[1], update=ms[2], total=ms[3])
+
+    def descriptors(self, frame, points_xy, window_size_half):
+        """VlHogDescriptorExtractor::getDescriptors -> [n][279] float32"""
+        frame = np.ascontiguousarray(frame, np.uint8)
+        pts = np.ascontiguousarray(points_xy, np.float32).reshape(-1, 2)
+        out = np.zeros((pts.shape[0], 279), np.float32)
+        capi.check(self.lib, self.lib.fdb_sdm_descriptors(self.h, frame.ctypes.data, frame.shape[1], frame.shape[1], frame.shape[0],
+                                                          pts.ctypes.data, pts.shape[0], window_size_half, out.ctypes.data))
+        return out

@@ -326,3 +326,39 @@ def make_feature_svm(vectors, seed, num_sv=1024, gamma=0.2, center=False):
     if center:
         coef = (coef - np.float32(coef.astype(np.float64).mean())).astype(np.float32)
     return SvmModel(sv, coef, gamma=gamma)
+
+
+# ------------------------------------------------------------------------------------------------
+# supervised-descent regressor (BASELINE configs[4])
+# ------------------------------------------------------------------------------------------------
+SDM_DESC = 279  # 3 x 3 cells x (3 * 9 + 4) UoCTTI dimensions (DescriptorExtractor.hpp:140-144)
+
+
+class SdmModel:
+    """SdmLandmarkModel state (SdmLandmarkModel.hpp:123-131): mean shape (all x, then all y, in [-0.5, 0.5]) and one
+    (L * 279 + 1) x 2L regressor per cascade step (last row = bias)."""
+
+    def __init__(self, mean, regressors):
+        self.mean = np.ascontiguousarray(mean, np.float32)
+        self.num_landmarks = self.mean.size // 2
+        self.regressors = [np.ascontiguousarray(r, np.float32) for r in regressors]
+        for r in self.regressors:
+            assert r.shape == (self.num_landmarks * SDM_DESC + 1, 2 * self.num_landmarks)
+
+
+def make_sdm(num_landmarks=68, num_steps=5, seed=500, sigma=1e-3):
+    """Synthetic model: mean shape = a grid in [-0.4, 0.4]^2 with landmarks 8, 9 (inner eye corners) and 11, 12 (mouth
+    corners) placed where SdmLandmarkModelFitting::optimize expects them (SdmLandmarkModel.hpp:212-216);
+    regressors ~ N(0, sigma) seeded 500 + step."""
+    L = num_landmarks
+    assert L >= 13
+    side = int(np.ceil(np.sqrt(L)))
+    gx, gy = np.meshgrid(np.linspace(-0.4, 0.4, side), np.linspace(-0.4, 0.4, side))
+    mean = np.concatenate([gx.ravel()[:L], gy.ravel()[:L]]).astype(np.float32)
+    for idx, (x, y) in {8: (-0.08, -0.15), 9: (0.08, -0.15), 11: (-0.15, 0.25), 12: (0.15, 0.25)}.items():
+        mean[idx], mean[L + idx] = x, y
+    regs = []
+    for s in range(num_steps):
+        rng = np.random.default_rng(seed + s)
+        regs.append((rng.standard_normal((L * SDM_DESC + 1, 2 * L)) * sigma).astype(np.float32))
+    return SdmModel(mean, regs)

@@ -411,6 +411,63 @@ FDB_API int fdb_detect_single(fdb_detector* det, const uint8_t* frames_host, int
  * [0] windows, [1] wvm positives, [2] after OE, [3] svm positives, [4] after NMS. */
 FDB_API int fdb_detector_last_counts(fdb_detector* det, int64_t counts[5]);
 
+/* ------------------------------------------------------------------------------------------
+ * Supervised-descent landmark regressor (libSupervisedDescent; BASELINE configs[4])
+ * ---------------------------------------------------------------------------------------- */
+typedef struct fdb_sdm fdb_sdm;
+
+/* SdmLandmarkModel state (SdmLandmarkModel.hpp:123-131). Every cascade step uses the "vlhog-uoctti" descriptor with
+ * adaptive parameters (SdmLandmarkModel.cpp:181-215 with empty descriptorParameters; DescriptorExtractor.hpp:140-144:
+ * 3 x 3 cells, 9 orientations, patch resized to 30 x 30 -> 279 values per landmark). */
+typedef struct fdb_sdm_desc {
+	int32_t num_landmarks;          /* L >= 13: optimize() reads landmarks 8, 9, 11, 12 (SdmLandmarkModel.hpp:212-216) */
+	int32_t num_cascade_steps;      /* <= 8 */
+	const float* mean_landmarks;    /* 2 L: all x, then all y */
+	const float* const* regressors; /* [steps] -> (279 L + 1) x 2 L row-major float32, last row = bias */
+} fdb_sdm_desc;
+
+/* SdmLandmarkModel::SdmLandmarkModel(meanLandmarks, ..., regressorData, ...) (SdmLandmarkModel.cpp:34-41): uploads the model. */
+FDB_API int fdb_sdm_create(fdb_ctx* ctx, const fdb_sdm_desc* desc, fdb_sdm** out);
+FDB_API void fdb_sdm_destroy(fdb_sdm* sdm);
+/* getNumLandmarks / getNumCascadeSteps (SdmLandmarkModel.cpp:43-51) */
+FDB_API int32_t fdb_sdm_num_landmarks(const fdb_sdm* sdm);
+FDB_API int32_t fdb_sdm_num_cascade_steps(const fdb_sdm* sdm);
+
+/* SdmLandmarkModel::load (SdmLandmarkModel.cpp:130-232), text format with a "descriptorType vlhog-uoctti" line per step.
+ * The descriptor points into the file object and stays valid until fdb_sdm_file_free. */
+typedef struct fdb_sdm_file fdb_sdm_file;
+FDB_API int fdb_sdm_file_load(const char* path, fdb_sdm_file** out);
+FDB_API const fdb_sdm_desc* fdb_sdm_file_desc(const fdb_sdm_file* file);
+FDB_API void fdb_sdm_file_free(fdb_sdm_file* file);
+
+/* SdmLandmarkModelFitting::alignRigid(modelShape = mean, faceBox) (SdmLandmarkModel.hpp:156-192) for n_faces boxes
+ * {x, y, width, height}: shapes_out[n_faces][2 L] (host; a handful of float operations per landmark, done on the host). */
+FDB_API int fdb_sdm_align_rigid(const fdb_sdm* sdm, const int32_t* boxes_xywh, int64_t n_faces, float* shapes_out);
+
+/* SdmLandmarkModelFitting::optimize(modelShape, image) (SdmLandmarkModel.hpp:199-256) for a batch of faces.
+ *  frames_host   n_frames 8-bit 1-channel images of width x height, row pitch `pitch` bytes, frame k at k * pitch * height
+ *  face_frame    [n_faces] index of the frame each face lies in (NULL: face i lies in frame i)
+ *  shapes        [n_faces][2 L] in: start shapes (alignRigid), out: fitted shapes
+ *  status_out    NULL or [n_faces]: 0 = ok, s + 1 = a HOG window of cascade step s left the (extended) image, where the
+ *                reference's Mat::operator()(Rect) throws (DescriptorExtractor.hpp:173); that face's shape is what it was
+ *                before step s
+ *  features_out  NULL or [steps][n_faces][279 L]: the descriptor rows (for stage-wise checks) */
+FDB_API int fdb_sdm_optimize_batch(fdb_sdm* sdm, const uint8_t* frames_host, int64_t pitch, int32_t width, int32_t height,
+		int32_t n_frames, const int32_t* face_frame, int64_t n_faces, float* shapes, int32_t* status_out, float* features_out);
+/* Same with everything resident on the device (frames contiguous, pitch == width); asynchronous on the context's stream. */
+FDB_API int fdb_sdm_optimize_batch_device(fdb_sdm* sdm, const uint8_t* frames_device, int32_t width, int32_t height,
+		int32_t n_frames, const int32_t* face_frame_device, int64_t n_faces, float* shapes_device, int32_t* status_device);
+/* Same as the device call, synchronous, with CUDA-event times per kernel family summed over the cascade steps:
+ * ms_out = {HOG descriptors, regressor product, shape update, total}. */
+FDB_API int fdb_sdm_profile_device(fdb_sdm* sdm, const uint8_t* frames_device, int32_t width, int32_t height,
+		int32_t n_frames, const int32_t* face_frame_device, int64_t n_faces, float* shapes_device, int32_t* status_device,
+		double ms_out[4]);
+
+/* VlHogDescriptorExtractor::getDescriptors(image, locations, windowSizeHalf) (DescriptorExtractor.hpp:106-219), adaptive
+ * parameters: n_points x 279 float32 to out (host). Returns FDB_ERR_RUNTIME when a window leaves the extended image. */
+FDB_API int fdb_sdm_descriptors(fdb_sdm* sdm, const uint8_t* frame_host, int64_t pitch, int32_t width, int32_t height,
+		const float* points_xy, int32_t n_points, int32_t window_size_half, float* out);
+
 #ifdef __cplusplus
 }
 #endif

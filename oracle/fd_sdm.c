@@ -27,6 +27,14 @@
  * tables, horizontal pass S[sx]*a0 + S[sx+1]*a1, vertical pass S0*b0 + S1*b1, all float32 */
 void fdo_resize_linear_f32(const float* src, int sw, int sh, float* dst, int dw, int dh) {
 	if (sw == dw && sh == dh) { memcpy(dst, src, sizeof(float) * (size_t)sw * sh); return; }
+	if (sw == 2 * dw && sh == 2 * dh) { /* exact 2x decimation: cv::resize switches INTER_LINEAR to the INTER_AREA fast path */
+		for (int dy = 0; dy < dh; ++dy)
+			for (int dx = 0; dx < dw; ++dx) {
+				const float* S = src + (size_t)(2 * dy) * sw + 2 * dx;
+				dst[(size_t)dy * dw + dx] = (((S[0] + S[1]) + S[sw]) + S[sw + 1]) * 0.25f;
+			}
+		return;
+	}
 	const double scale_x = (double)sw / dw, scale_y = (double)sh / dh;
 	int* xofs = (int*)malloc(sizeof(int) * (size_t)(dw + dh));
 	int* yofs = xofs + dw;
@@ -158,6 +166,10 @@ void fdo_vlhog_uoctti(const float* image, int width, int height, int cellSize, i
 	free(hog); free(hogNorm); free(ox);
 }
 
+#ifdef FDO_USE_REF_HOG
+int ref_vlhog_uoctti(const float* image, int width, int height, int cell_size, int num_orientations, float* features, int* hw_out, int* hh_out);
+#endif
+
 #define SDM_PATCH 30 /* adaptive: 3 cells of 10 px (DescriptorExtractor.hpp:140-144) */
 #define SDM_CELL 10
 #define SDM_BINS 9
@@ -193,7 +205,11 @@ int fdo_sdm_descriptors(const uint8_t* image, int cols, int rows, int pitch, con
 			}
 		fdo_resize_linear_f32(roi, side, side, patch, SDM_PATCH, SDM_PATCH); /* :181-183 */
 		int hw, hh;
+#ifdef FDO_USE_REF_HOG /* oracle/_ref build: the reference's own hog.c (through ref_sdm.c) computes the descriptor */
+		ref_vlhog_uoctti(patch, SDM_PATCH, SDM_PATCH, SDM_CELL, SDM_BINS, feat, &hw, &hh);
+#else
 		fdo_vlhog_uoctti(patch, SDM_PATCH, SDM_PATCH, SDM_CELL, SDM_BINS, feat, &hw, &hh);
+#endif
 		/* :196-204: per dimension the hh x ww plane is transposed and flattened -> index j*ww*hh + x*hh + y */
 		float* o = out + (size_t)i * SDM_DESC;
 		for (int j = 0; j < 3 * SDM_BINS + 4; ++j)

@@ -41,6 +41,30 @@ class _Layer(C.Structure):
 _lib = None
 
 
+def _bind_sdm(L):
+    """fd_sdm.c entry points (present in libfdoracle.so and, with the reference's own hog.c inside, in oracle/_ref)"""
+    L.fdo_resize_linear_f32.restype = None
+    L.fdo_resize_linear_f32.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int]
+    L.fdo_vlhog_uoctti.restype = None
+    L.fdo_vlhog_uoctti.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.fdo_sdm_descriptors.restype = C.c_int
+    L.fdo_sdm_descriptors.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    L.fdo_sdm_create.restype = C.c_void_p
+    L.fdo_sdm_create.argtypes = [C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]
+    L.fdo_sdm_load.restype = C.c_void_p; L.fdo_sdm_load.argtypes = [C.c_char_p]
+    L.fdo_sdm_free.restype = None; L.fdo_sdm_free.argtypes = [C.c_void_p]
+    L.fdo_sdm_num_landmarks.restype = C.c_int; L.fdo_sdm_num_landmarks.argtypes = [C.c_void_p]
+    L.fdo_sdm_num_steps.restype = C.c_int; L.fdo_sdm_num_steps.argtypes = [C.c_void_p]
+    L.fdo_sdm_mean.restype = C.POINTER(C.c_float); L.fdo_sdm_mean.argtypes = [C.c_void_p]
+    L.fdo_sdm_regressor.restype = C.POINTER(C.c_float); L.fdo_sdm_regressor.argtypes = [C.c_void_p, C.c_int]
+    L.fdo_sdm_align_rigid.restype = None
+    L.fdo_sdm_align_rigid.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    L.fdo_sdm_window.restype = None
+    L.fdo_sdm_window.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_int)]
+    L.fdo_sdm_optimize.restype = C.c_int
+    L.fdo_sdm_optimize.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+
+
 def lib():
     global _lib
     if _lib is None:
@@ -105,6 +129,7 @@ def lib():
                                           C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                           C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                           C.POINTER(C.c_int64), C.POINTER(C.c_double)]
+        _bind_sdm(L)
         _lib = L
     return _lib
 
@@ -142,6 +167,9 @@ def ref():
         R.ref_detect_frame_ex.restype = C.c_int64
         R.ref_detect_frame_ex.argtypes = [C.POINTER(capi.DetectorDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                           C.c_int, C.c_void_p, C.POINTER(C.c_int64), C.c_void_p, C.c_int64, C.POINTER(C.c_double)]
+        _bind_sdm(R)
+        R.ref_vlhog_uoctti.restype = C.c_int
+        R.ref_vlhog_uoctti.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
         R.ref_gradient_bin_luts.restype = None
         R.ref_gradient_bin_luts.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         R.ref_lbp.restype = None; R.ref_lbp.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
@@ -390,6 +418,87 @@ def whitening(patch, alpha=1.0, cutoff=0.390625):
     out = np.empty((h, w), np.uint8); real = np.empty((h, w), np.float32)
     lib().fdo_whitening_u8(patch.ctypes.data, patch.strides[0], w, h, filt.ctypes.data, out.ctypes.data, real.ctypes.data)
     return out, real
+
+
+def resize_linear_f32(img, dw, dh):
+    img = np.ascontiguousarray(img, np.float32)
+    out = np.empty((dh, dw), np.float32)
+    lib().fdo_resize_linear_f32(img.ctypes.data, img.shape[1], img.shape[0], out.ctypes.data, dw, dh)
+    return out
+
+
+def vlhog_uoctti(img, cell_size=10, num_orientations=9, use_ref=False):
+    """VLFeat HOG (UoCTTI variant) of a float32 image -> [3 no + 4, hogHeight, hogWidth]"""
+    img = np.ascontiguousarray(img, np.float32)
+    h, w = img.shape
+    hw, hh = (w + cell_size // 2) // cell_size, (h + cell_size // 2) // cell_size
+    out = np.zeros((3 * num_orientations + 4, hh, hw), np.float32)
+    a, b = C.c_int(), C.c_int()
+    fn = ref().ref_vlhog_uoctti if use_ref else lib().fdo_vlhog_uoctti
+    fn(img.ctypes.data, w, h, cell_size, num_orientations, out.ctypes.data, C.byref(a), C.byref(b))
+    assert (a.value, b.value) == (hw, hh)
+    return out
+
+
+class Sdm:
+    """SdmLandmarkModel + SdmLandmarkModelFitting (fd_sdm.c)."""
+
+    def __init__(self, model=None, path=None, use_ref=False):
+        """model: featuredetection_b200.synthetic.SdmModel; or path of a reference text model.
+        use_ref: descriptors come from the reference's own hog.c (oracle/_ref) instead of the restatement."""
+        L_ = self._L = ref() if use_ref else lib()
+        if path is not None:
+            self.h = L_.fdo_sdm_load(path.encode())
+            if not self.h:
+                raise ValueError("cannot load SDM model %s" % path)
+        else:
+            regs = (C.c_void_p * len(model.regressors))(*[r.ctypes.data for r in model.regressors])
+            self.h = L_.fdo_sdm_create(model.num_landmarks, len(model.regressors), model.mean.ctypes.data, regs)
+        self.L = L_.fdo_sdm_num_landmarks(self.h)
+        self.steps = L_.fdo_sdm_num_steps(self.h)
+
+    def __del__(self):
+        try:
+            self._L.fdo_sdm_free(self.h)
+        except Exception:
+            pass
+
+    def to_model(self):
+        from featuredetection_b200.synthetic import SdmModel
+        L_ = self._L
+        mean = np.ctypeslib.as_array(L_.fdo_sdm_mean(self.h), shape=(2 * self.L,)).copy()
+        rows = self.L * 279 + 1
+        regs = [np.ctypeslib.as_array(L_.fdo_sdm_regressor(self.h, s), shape=(rows, 2 * self.L)).copy() for s in range(self.steps)]
+        return SdmModel(mean, regs)
+
+    def align_rigid(self, box):
+        shape = np.empty(2 * self.L, np.float32)
+        self._L.fdo_sdm_align_rigid(self.h, int(box[0]), int(box[1]), int(box[2]), int(box[3]), shape.ctypes.data)
+        return shape
+
+    def optimize(self, image, shape, want_features=False):
+        image = np.ascontiguousarray(image, np.uint8)
+        shape = np.ascontiguousarray(shape, np.float32).copy()
+        feats = np.zeros((self.steps, self.L * 279), np.float32) if want_features else None
+        rc = self._L.fdo_sdm_optimize(self.h, image.ctypes.data, image.shape[1], image.shape[0], image.shape[1], shape.ctypes.data,
+                                    feats.ctypes.data if want_features else None)
+        if rc != 0:
+            raise RuntimeError("fdo_sdm_optimize: region of interest outside the image (%d)" % rc)
+        return (shape, feats) if want_features else shape
+
+    def fit(self, image, box):
+        return self.optimize(image, self.align_rigid(box))
+
+
+def sdm_descriptors(image, pts_xy, window_half):
+    image = np.ascontiguousarray(image, np.uint8)
+    pts = np.ascontiguousarray(pts_xy, np.float32).reshape(-1, 2)
+    out = np.zeros((pts.shape[0], 279), np.float32)
+    rc = lib().fdo_sdm_descriptors(image.ctypes.data, image.shape[1], image.shape[0], image.shape[1], pts.ctypes.data, pts.shape[0],
+                                   window_half, out.ctypes.data)
+    if rc != 0:
+        raise RuntimeError("fdo_sdm_descriptors: region of interest outside the image")
+    return out
 
 
 def detections_to_array(buf, n):
