@@ -24,6 +24,7 @@
 
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -258,7 +259,160 @@ __global__ void __launch_bounds__(SDM_THREADS) sdm_hog_kernel(const DevSdm m, co
 	}
 }
 
-/* delta = F * R[0:K] + R[K]; BM faces per CTA, thread (tx, ty) owns faces ty*4..+3 and columns tx + 16 j */
+/* ------------------------------------------------------------------------------------------------
+ * delta = F * R[0:K] + R[K] on the FP64 tensor cores (DMMA).
+ *
+ * cv::gemm on CV_32F accumulates float x float products in double (SdmLandmarkModel.hpp:241 is a MatExpr -> cv::gemm);
+ * a float x float product is exact in double, so a double-accumulating GEMM in any summation order agrees with the
+ * sequential reference sum to ~1e-16 relative - below one float32 ulp of the result except with probability ~1e-9.
+ * mma.sync ... f64 keeps that: operands are converted float -> double once while they are staged into shared memory.
+ *
+ * CTA tile: 32 faces x (8 NT8) columns, 4 warps: warp w owns rows 16 (w & 1) .. +15 and the k16 block (w >> 1) of every
+ * 32-wide k stage; the two k halves are added in a fixed order at the end (deterministic).  Global loads of the next stage
+ * are issued into registers before the current stage is multiplied (register double buffering).
+ * Shared layout (doubles): A [32][36], B [32][8 NT8 + 12]: both strides = 4 mod 16, so the 16 lanes of a half warp
+ * (g = 0..3, t = 0..3 -> g * stride + t) hit 16 distinct 8-byte banks.
+ * ---------------------------------------------------------------------------------------------- */
+#define GM_BM 32
+#define GM_BK 32
+#define GM_AS 36 /* A row stride in doubles */
+
+__device__ __forceinline__ void dmma_m16n8k16(double (&c)[4], const double (&a)[8], const double (&b)[4]) {
+	asm volatile("mma.sync.aligned.m16n8k16.row.col.f64.f64.f64.f64 {%0,%1,%2,%3}, {%4,%5,%6,%7,%8,%9,%10,%11}, {%12,%13,%14,%15}, {%0,%1,%2,%3};"
+			: "+d"(c[0]), "+d"(c[1]), "+d"(c[2]), "+d"(c[3])
+			: "d"(a[0]), "d"(a[1]), "d"(a[2]), "d"(a[3]), "d"(a[4]), "d"(a[5]), "d"(a[6]), "d"(a[7]), "d"(b[0]), "d"(b[1]), "d"(b[2]), "d"(b[3]));
+}
+__device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, double b) {
+	asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+/* VEC: rows of F and R are 16-byte aligned (K % 4 == 0 and N % 4 == 0); K16: use the m16n8k16 shape (else m8n8k4) */
+template <int NT8, bool VEC, bool K16>
+__global__ void __launch_bounds__(128) sdm_gemm_dmma_kernel(const float* __restrict__ F, const float* __restrict__ R, int n_faces, int K, int N,
+		float* __restrict__ delta) {
+	constexpr int BN = 8 * NT8, BS = BN + 12;
+	constexpr int A_V4 = GM_BM * GM_BK / 4 / 128;                /* float4 loads of A per thread and stage (2) */
+	constexpr int B_V4 = (GM_BK * BN / 4 + 127) / 128;           /* float4 loads of B per thread and stage */
+	extern __shared__ __align__(16) double gm_smem[];
+	double* sA = gm_smem;                 /* [32][GM_AS] */
+	double* sB = gm_smem + GM_BM * GM_AS; /* [32][BS] */
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+	const int mh = warp & 1, kh = warp >> 1;
+	const int face0 = blockIdx.x * GM_BM, col0 = blockIdx.y * BN;
+	double acc[NT8][4];
+#pragma unroll
+	for (int j = 0; j < NT8; ++j) { acc[j][0] = 0; acc[j][1] = 0; acc[j][2] = 0; acc[j][3] = 0; }
+	float4 ra[A_V4], rb[B_V4];
+
+	auto load_stage = [&](int k0) {
+#pragma unroll
+		for (int i = 0; i < A_V4; ++i) { /* A: 32 rows x 8 float4 */
+			const int idx = tid + i * 128, row = idx >> 3, c4 = (idx & 7) * 4;
+			const int f = face0 + row, k = k0 + c4;
+			float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+			if (f < n_faces) {
+				const float* src = F + (int64_t)f * K + k;
+				if (VEC && k + 3 < K) v = __ldg(reinterpret_cast<const float4*>(src));
+				else { if (k < K) v.x = __ldg(src); if (k + 1 < K) v.y = __ldg(src + 1); if (k + 2 < K) v.z = __ldg(src + 2); if (k + 3 < K) v.w = __ldg(src + 3); }
+			}
+			ra[i] = v;
+		}
+#pragma unroll
+		for (int i = 0; i < B_V4; ++i) { /* B: 32 k rows x BN / 4 float4 */
+			const int idx = tid + i * 128, row = idx / (BN / 4), c4 = (idx - row * (BN / 4)) * 4;
+			const int k = k0 + row, c = col0 + c4;
+			float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+			if (row < GM_BK && k < K) {
+				const float* src = R + (int64_t)k * N + c;
+				if (VEC && c + 3 < N) v = __ldg(reinterpret_cast<const float4*>(src));
+				else { if (c < N) v.x = __ldg(src); if (c + 1 < N) v.y = __ldg(src + 1); if (c + 2 < N) v.z = __ldg(src + 2); if (c + 3 < N) v.w = __ldg(src + 3); }
+			}
+			rb[i] = v;
+		}
+	};
+	auto store_stage = [&]() {
+#pragma unroll
+		for (int i = 0; i < A_V4; ++i) {
+			const int idx = tid + i * 128, row = idx >> 3, c4 = (idx & 7) * 4;
+			double2* d = reinterpret_cast<double2*>(sA + row * GM_AS + c4);
+			d[0] = make_double2((double)ra[i].x, (double)ra[i].y);
+			d[1] = make_double2((double)ra[i].z, (double)ra[i].w);
+		}
+#pragma unroll
+		for (int i = 0; i < B_V4; ++i) {
+			const int idx = tid + i * 128, row = idx / (BN / 4), c4 = (idx - row * (BN / 4)) * 4;
+			if (row < GM_BK) {
+				double2* d = reinterpret_cast<double2*>(sB + row * BS + c4);
+				d[0] = make_double2((double)rb[i].x, (double)rb[i].y);
+				d[1] = make_double2((double)rb[i].z, (double)rb[i].w);
+			}
+		}
+	};
+
+	load_stage(0);
+	for (int k0 = 0; k0 < K; k0 += GM_BK) {
+		store_stage();
+		__syncthreads();
+		if (k0 + GM_BK < K) load_stage(k0 + GM_BK);
+		const double* A0 = sA + (mh * 16 + g) * GM_AS + kh * 16 + t;
+		const double* B0 = sB + (kh * 16 + t) * BS + g;
+		if (K16) {
+			double a[8];
+#pragma unroll
+			for (int i = 0; i < 8; ++i) a[i] = A0[(i & 1) * 8 * GM_AS + (i >> 1) * 4];
+#pragma unroll
+			for (int j = 0; j < NT8; ++j) {
+				double b[4];
+#pragma unroll
+				for (int i = 0; i < 4; ++i) b[i] = B0[i * 4 * BS + 8 * j];
+				dmma_m16n8k16(acc[j], a, b);
+			}
+		} else {
+#pragma unroll
+			for (int q = 0; q < 4; ++q) { /* four k4 steps of this warp's k16 block */
+				const double a_lo = A0[q * 4], a_hi = A0[8 * GM_AS + q * 4];
+#pragma unroll
+				for (int j = 0; j < NT8; ++j) {
+					const double b = B0[q * 4 * BS + 8 * j];
+					dmma_m8n8k4(acc[j][0], acc[j][1], a_lo, b);
+					dmma_m8n8k4(acc[j][2], acc[j][3], a_hi, b);
+				}
+			}
+		}
+		__syncthreads();
+	}
+	/* add the two k halves in a fixed order (kh = 0 first), then the bias row, round to float32 once */
+	double* red = gm_smem; /* [2 m halves][NT8][4][32 lanes] */
+	if (kh == 1) {
+#pragma unroll
+		for (int j = 0; j < NT8; ++j)
+#pragma unroll
+			for (int i = 0; i < 4; ++i) red[((mh * NT8 + j) * 4 + i) * 32 + lane] = acc[j][i];
+	}
+	__syncthreads();
+	if (kh == 0) {
+#pragma unroll
+		for (int j = 0; j < NT8; ++j)
+#pragma unroll
+			for (int i = 0; i < 4; ++i) {
+				const int f = face0 + mh * 16 + g + (i >> 1) * 8, c = col0 + 8 * j + 2 * t + (i & 1);
+				if (f < n_faces && c < N) {
+					const double sum = __dadd_rn(acc[j][i], red[((mh * NT8 + j) * 4 + i) * 32 + lane]);
+					delta[(int64_t)f * N + c] = (float)__dadd_rn(sum, (double)R[(int64_t)K * N + c]);
+				}
+			}
+	}
+}
+
+template <int NT8>
+static size_t gemm_smem_bytes() {
+	const size_t stage = sizeof(double) * (GM_BM * GM_AS + GM_BK * (8 * NT8 + 12));
+	const size_t red = sizeof(double) * 2 * NT8 * 4 * 32;
+	return stage > red ? stage : red;
+}
+
+/* scalar FP64 FMA version (reference for the tensor-core kernel; FDB_SDM_GEMM=scalar): BM faces per CTA, thread (tx, ty)
+ * owns faces ty*4..+3 and columns tx + 16 j */
 #define GEMM_BM 32
 #define GEMM_BK 16
 template <int NC>
@@ -347,13 +501,46 @@ void launch_sdm_hog(cudaStream_t st, const DevSdm& m, const uint8_t* frames, int
 	sdm_hog_kernel<<<grid, SDM_THREADS, 0, st>>>(m, frames, W, H, face_frame, shapes, step, pts_xy, window_half, features, status);
 }
 
+static int gemm_mode() { /* FDB_SDM_GEMM = scalar | m8 | m16 (default): tuning / cross-check hook */
+	static int mode = -1;
+	if (mode < 0) {
+		const char* e = getenv("FDB_SDM_GEMM");
+		mode = !e ? 2 : (!strcmp(e, "scalar") ? 0 : (!strcmp(e, "m8") ? 1 : 2));
+	}
+	return mode;
+}
+
+template <int NT8, bool VEC, bool K16>
+static void launch_dmma(cudaStream_t st, const DevSdm& m, int step, const float* features, int n_faces, float* delta) {
+	static bool configured = false;
+	const size_t smem = gemm_smem_bytes<NT8>();
+	if (!configured) { cudaFuncSetAttribute(sdm_gemm_dmma_kernel<NT8, VEC, K16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); configured = true; }
+	dim3 grid((unsigned)((n_faces + GM_BM - 1) / GM_BM), (unsigned)((m.N + 8 * NT8 - 1) / (8 * NT8)));
+	sdm_gemm_dmma_kernel<NT8, VEC, K16><<<grid, 128, smem, st>>>(features, m.R[step], n_faces, m.K, m.N, delta);
+}
+
+template <int NT8>
+static void launch_dmma_nt(cudaStream_t st, const DevSdm& m, int step, const float* features, int n_faces, float* delta, bool k16) {
+	const bool vec = (m.K % 4 == 0) && (m.N % 4 == 0);
+	if (vec) { if (k16) launch_dmma<NT8, true, true>(st, m, step, features, n_faces, delta); else launch_dmma<NT8, true, false>(st, m, step, features, n_faces, delta); }
+	else { if (k16) launch_dmma<NT8, false, true>(st, m, step, features, n_faces, delta); else launch_dmma<NT8, false, false>(st, m, step, features, n_faces, delta); }
+}
+
 void launch_sdm_gemm(cudaStream_t st, const DevSdm& m, int step, const float* features, int n_faces, float* delta) {
 	if (n_faces == 0) return;
-	const unsigned grid = (unsigned)((n_faces + GEMM_BM - 1) / GEMM_BM);
-	const int nc = (m.N + 15) / 16;
-	if (nc <= 2) sdm_gemm_kernel<2><<<grid, 128, 0, st>>>(features, m.R[step], n_faces, m.K, m.N, delta);
-	else if (nc <= 5) sdm_gemm_kernel<5><<<grid, 128, 0, st>>>(features, m.R[step], n_faces, m.K, m.N, delta);
-	else sdm_gemm_kernel<9><<<grid, 128, 0, st>>>(features, m.R[step], n_faces, m.K, m.N, delta);
+	const int mode = gemm_mode();
+	if (mode == 0) {
+		const unsigned grid = (unsigned)((n_faces + GEMM_BM - 1) / GEMM_BM);
+		const int nc = (m.N + 15) / 16;
+		if (nc <= 2) sdm_gemm_kernel<2><<<grid, 128, 0, st>>>(features, m.R[step], n_faces, m.K, m.N, delta);
+		else if (nc <= 5) sdm_gemm_kernel<5><<<grid, 128, 0, st>>>(features, m.R[step], n_faces, m.K, m.N, delta);
+		else if (nc <= 9) sdm_gemm_kernel<9><<<grid, 128, 0, st>>>(features, m.R[step], n_faces, m.K, m.N, delta);
+		else launch_dmma_nt<9>(st, m, step, features, n_faces, delta, true);
+		return;
+	}
+	/* column tile: 72 (two tiles cover the 136 columns of a 68-landmark model), 32 for small models */
+	if (m.N <= 32) launch_dmma_nt<4>(st, m, step, features, n_faces, delta, mode == 2);
+	else launch_dmma_nt<9>(st, m, step, features, n_faces, delta, mode == 2);
 }
 
 void launch_sdm_update(cudaStream_t st, const DevSdm& m, int step, const float* delta, float* shapes, const int* status, int n_faces) {
