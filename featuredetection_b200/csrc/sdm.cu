@@ -5,7 +5,7 @@
  *   vl_hog_put_image / vl_hog_extract (UoCTTI)       libSupervisedDescent/src/superviseddescent/hog.c:595-727,857-1063
  *
  * One cascade step over a batch of faces is three launches:
- *   sdm_hog_kernel     one CTA per (landmark, face): crop (black canvas outside the image, with the reference's
+ *   sdm_hog_kernel     one WARP per (landmark, face): crop (black canvas outside the image, with the reference's
  *                      row-offset quirk), float32 bilinear resize to 30x30, VLFeat HOG (3x3 cells x 31) written
  *                      straight into the face's feature row [face][landmark * 279 + ...]
  *   sdm_gemm_kernel    delta[faces x 2L] = features[faces x 279 L] * R[0:-1] + R[-1]: float32 inputs, FLOAT64
@@ -59,26 +59,59 @@ __device__ __forceinline__ float sdm_px(const uint8_t* __restrict__ img, int W, 
 	return (x >= 0 && y >= 0 && x < W && y < H) ? (float)img[(int64_t)y * W + x] : 0.f;
 }
 
-/* mode 0: points come from the face's current shape, window from sdm_window; mode 1: explicit points + window */
-__global__ void __launch_bounds__(SDM_THREADS) sdm_hog_kernel(const DevSdm m, const uint8_t* __restrict__ frames, int W, int H,
-		const int* __restrict__ face_frame, const float* __restrict__ shapes, int step, const float* __restrict__ pts_xy,
-		int window_half, float* __restrict__ features, int* __restrict__ status) {
-	__shared__ float s_img[SDM_P * SDM_P];
-	__shared__ float s_grad[SDM_P * SDM_P];
-	__shared__ uint8_t s_bin[SDM_P * SDM_P];
-	__shared__ uint32_t s_mask[SDM_P][2 * SDM_NO];         /* per row: pixels (bit x) whose orientation bin is o */
-	__shared__ float s_hog[SDM_CELLS * SDM_CELLS * 2 * SDM_NO]; /* [o][cy][cx] */
-	__shared__ float s_norm[SDM_CELLS * SDM_CELLS];
-	__shared__ double s_fac[SDM_CELLS * SDM_CELLS][4];
-	__shared__ double s_hc[SDM_CELLS * SDM_CELLS][SDM_NO][4];
-	__shared__ int s_geo[8];
-	const int tid = threadIdx.x, lm = blockIdx.x, face = blockIdx.y, L = m.L;
-	const uint8_t* __restrict__ img = frames + (int64_t)(face_frame ? face_frame[face] : 0) * W * H;
-	float* __restrict__ out = features + ((int64_t)face * L + lm) * SDM_DESC;
+/* One WARP per descriptor (landmark of a face); HW_WARPS descriptors per CTA, no CTA-wide barrier after the table load.
+ *   pass 1  lane = patch column: rows stream through three registers (resized rows r-1, r, r+1), so the resized patch is
+ *           never stored; gradient, dominant orientation (hog.c:617-682); every contributing pixel gets its rank inside
+ *           the raster-ordered list of its orientation (__match_any_sync + running counts)
+ *   pass 2  scatter pixel ids into the 18 orientation lists (stable: raster order is kept)
+ *   pass 3  bilinear cell accumulation (hog.c:697-722): lane = (orientation, cell row); it walks the contiguous list
+ *           segment of the rows that touch its cell row and feeds the three cells of that row; columns outside a cell have
+ *           weight 0, and acc + 0 == acc exactly, so every cell sees its own pixels in raster order like the reference
+ *   pass 4  block normalisation + UoCTTI features (hog.c:879-1060), staged in shared memory and written as one 279-float row
+ * mode 0: points come from the face's current shape, window from sdm_window; mode 1: explicit points + window */
+#define HW_WARPS 4
+#define HW_RS 32 /* row stride of the per-pixel arrays */
 
-	if (tid == 0) {
+struct HogWarpSmem {
+	float grad[SDM_P * HW_RS];     /* gradient magnitude per pixel; reused as the output staging row */
+	uint16_t bp[SDM_P * HW_RS];    /* (orientation << 10) | rank in the orientation's list; 0xffff: pixel contributes nothing */
+	uint16_t list[SDM_P * SDM_P];  /* pixel ids (y * 32 + x), the 18 orientation lists back to back */
+	float hog[SDM_CELLS * SDM_CELLS * 2 * SDM_NO]; /* [o][cy][cx] */
+	float norm[12];
+	double fac[SDM_CELLS * SDM_CELLS][4];
+	int cnt[2 * SDM_NO];
+	int seg[3][2 * SDM_NO];        /* list fill at the start of rows 5, 15, 25 */
+	int base[2 * SDM_NO + 2];
+};
+
+__global__ void __launch_bounds__(HW_WARPS * 32) sdm_hog_kernel(const DevSdm m, const uint8_t* __restrict__ frames, int W, int H,
+		const int* __restrict__ face_frame, const float* __restrict__ shapes, int step, const float* __restrict__ pts_xy,
+		int window_half, int n_desc, float* __restrict__ features, int* __restrict__ status) {
+	__shared__ HogWarpSmem s_all[HW_WARPS];
+	__shared__ float4 s_wx[SDM_P];            /* column weight for cell columns 0, 1, 2 */
+	__shared__ float s_wy[SDM_CELLS][SDM_P];
+	const unsigned FULL = 0xffffffffu;
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, L = m.L;
+	if (threadIdx.x < SDM_P) {
+		const int x = threadIdx.x, b = m.bin_of[x];
+		const float w1 = m.w1_of[x], w2 = m.w2_of[x];
+		s_wx[x] = make_float4(b == 0 ? w1 : (b + 1 == 0 ? w2 : 0.f), b == 1 ? w1 : (b + 1 == 1 ? w2 : 0.f), b == 2 ? w1 : (b + 1 == 2 ? w2 : 0.f), 0.f);
+		for (int c = 0; c < SDM_CELLS; ++c) s_wy[c][x] = b == c ? w1 : (b + 1 == c ? w2 : 0.f);
+	}
+	__syncthreads();
+	const int desc = blockIdx.x * HW_WARPS + warp;
+	if (desc >= n_desc) return;
+	const int face = desc / L, lm = desc - face * L;
+	if (status && status[face] != 0) return; /* the reference threw at an earlier cascade step of this face */
+	HogWarpSmem& s = s_all[warp];
+	const uint8_t* __restrict__ img = frames + (int64_t)(face_frame ? face_frame[face] : 0) * W * H;
+	float* __restrict__ out = features + (int64_t)desc * SDM_DESC;
+
+	/* ---- window geometry (DescriptorExtractor.hpp:157-173), computed by every lane ---- */
+	int x0, y0, side;
+	{
 		float px, py; int wsh;
-		if (pts_xy) { px = pts_xy[2 * ((int64_t)face * L + lm)]; py = pts_xy[2 * ((int64_t)face * L + lm) + 1]; wsh = window_half; }
+		if (pts_xy) { px = pts_xy[2 * (int64_t)desc]; py = pts_xy[2 * (int64_t)desc + 1]; wsh = window_half; }
 		else {
 			const float* shape = shapes + (int64_t)face * 2 * L;
 			float d;
@@ -87,7 +120,7 @@ __global__ void __launch_bounds__(SDM_THREADS) sdm_hog_kernel(const DevSdm m, co
 		}
 		const int x = __float2int_rn(px), y = __float2int_rn(py); /* cvRound */
 		int rx = x - wsh, ry = y - wsh, bl = 0, bt = 0, br = 0, bb = 0;
-		if (x - wsh < 0 || y - wsh < 0 || x + wsh >= W || y + wsh >= H) { /* DescriptorExtractor.hpp:161-169 */
+		if (x - wsh < 0 || y - wsh < 0 || x + wsh >= W || y + wsh >= H) {
 			bl = (x - wsh) < 0 ? abs(x - wsh) : 0;
 			bt = (y - wsh) < 0 ? abs(y - wsh) : 0;
 			br = (x + wsh) >= W ? abs(W - (x + wsh)) : 0;
@@ -95,168 +128,213 @@ __global__ void __launch_bounds__(SDM_THREADS) sdm_hog_kernel(const DevSdm m, co
 			rx = (x - wsh) + bl;
 			ry = (y - wsh) + br; /* sic (:169) */
 		}
-		const int side = 2 * wsh;
+		side = 2 * wsh;
 		const bool ok = side >= 4 && rx >= 0 && ry >= 0 && rx + side <= W + bl + br && ry + side <= H + bt + bb;
-		s_geo[0] = rx - bl; s_geo[1] = ry - bt; s_geo[2] = side; s_geo[3] = ok ? 1 : 0;
-	}
-	__syncthreads();
-	const int x0 = s_geo[0], y0 = s_geo[1], side = s_geo[2];
-	if (!s_geo[3]) { /* the reference's Mat::operator()(roi) would throw: flag the face with step + 1, emit zeros */
-		if (tid == 0 && status) atomicCAS(status + face, 0, step + 1);
-		for (int i = tid; i < SDM_DESC; i += SDM_THREADS) out[i] = 0.f;
-		return;
-	}
-
-	/* ---- crop + convertTo(CV_32F) + cv::resize(30x30, INTER_LINEAR) ---- */
-	if (side == SDM_P) {
-		for (int i = tid; i < SDM_P * SDM_P; i += SDM_THREADS) { const int r = i / SDM_P, c = i - r * SDM_P; s_img[i] = sdm_px(img, W, H, x0 + c, y0 + r); }
-	} else if (side == 2 * SDM_P) { /* exact 2x decimation: INTER_AREA fast path, ((a + b) + c) + d) * 0.25 */
-		for (int i = tid; i < SDM_P * SDM_P; i += SDM_THREADS) {
-			const int r = i / SDM_P, c = i - r * SDM_P;
-			const float a = sdm_px(img, W, H, x0 + 2 * c, y0 + 2 * r), b = sdm_px(img, W, H, x0 + 2 * c + 1, y0 + 2 * r);
-			const float cc = sdm_px(img, W, H, x0 + 2 * c, y0 + 2 * r + 1), d = sdm_px(img, W, H, x0 + 2 * c + 1, y0 + 2 * r + 1);
-			s_img[i] = __fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(a, b), cc), d), 0.25f);
-		}
-	} else {
-		const double scale = __ddiv_rn((double)side, (double)SDM_P);
-		for (int i = tid; i < SDM_P * SDM_P; i += SDM_THREADS) {
-			const int dy = i / SDM_P, dx = i - dy * SDM_P;
-			float fx = (float)__dsub_rn(__dmul_rn((double)dx + 0.5, scale), 0.5);
-			int sx = (int)floorf(fx);
-			fx = __fsub_rn(fx, (float)sx);
-			if (sx < 0) { fx = 0.f; sx = 0; }
-			if (sx >= side - 1) { fx = 0.f; sx = side - 1; }
-			float fy = (float)__dsub_rn(__dmul_rn((double)dy + 0.5, scale), 0.5);
-			const int sy = (int)floorf(fy);
-			fy = __fsub_rn(fy, (float)sy);
-			const float a0 = __fsub_rn(1.f, fx), a1 = fx, b0 = __fsub_rn(1.f, fy), b1 = fy;
-			const int sx1 = min(sx + 1, side - 1);
-			const int sy0 = min(max(sy, 0), side - 1), sy1 = min(max(sy + 1, 0), side - 1);
-			const float r0 = __fadd_rn(__fmul_rn(sdm_px(img, W, H, x0 + sx, y0 + sy0), a0), __fmul_rn(sdm_px(img, W, H, x0 + sx1, y0 + sy0), a1));
-			const float r1 = __fadd_rn(__fmul_rn(sdm_px(img, W, H, x0 + sx, y0 + sy1), a0), __fmul_rn(sdm_px(img, W, H, x0 + sx1, y0 + sy1), a1));
-			s_img[i] = __fadd_rn(__fmul_rn(r0, b0), __fmul_rn(r1, b1));
+		x0 = rx - bl; y0 = ry - bt;
+		if (!ok) { /* the reference's Mat::operator()(roi) would throw: flag the face with step + 1, emit zeros */
+			if (lane == 0 && status) atomicCAS(status + face, 0, step + 1);
+			for (int i = lane; i < SDM_DESC; i += 32) out[i] = 0.f;
+			return;
 		}
 	}
-	for (int i = tid; i < SDM_CELLS * SDM_CELLS * 2 * SDM_NO; i += SDM_THREADS) s_hog[i] = 0.f;
-	__syncthreads();
+	const bool inside = x0 >= 0 && y0 >= 0 && x0 + side <= W && y0 + side <= H;
+	const int mode = side == SDM_P ? 0 : (side == 2 * SDM_P ? 1 : 2);
+	const int x = lane;
+	const bool xin = x < SDM_P;
 
-	/* ---- vl_hog_put_image: gradient, dominant directed orientation (hog.c:617-682) ---- */
-	for (int i = tid; i < SDM_P * SDM_P; i += SDM_THREADS) {
-		const int y = i / SDM_P, x = i - y * SDM_P;
-		int bin = 255;
+	/* ---- cv::resize(CV_32F, INTER_LINEAR): column coefficients per lane, row coefficients per (warp-uniform) row ---- */
+	const double scale = __ddiv_rn((double)side, (double)SDM_P);
+	int sx = 0, sx1 = 0;
+	float a0 = 1.f, a1 = 0.f;
+	if (mode == 2 && xin) {
+		float f = (float)__dsub_rn(__dmul_rn((double)x + 0.5, scale), 0.5);
+		int si = (int)floorf(f);
+		f = __fsub_rn(f, (float)si);
+		if (si < 0) { f = 0.f; si = 0; }                 /* columns: coefficient and index clamped */
+		if (si >= side - 1) { f = 0.f; si = side - 1; }
+		sx = si; sx1 = min(si + 1, side - 1);
+		a0 = __fsub_rn(1.f, f); a1 = f;
+	}
+	/* source columns / rows of the (up to) four pixels behind one resized pixel */
+	const int cA = x0 + (mode == 0 ? x : (mode == 1 ? 2 * x : sx)), cB = x0 + (mode == 0 ? x : (mode == 1 ? 2 * x + 1 : sx1));
+	struct Row { int y0, y1; float b0, b1; };
+	auto row_of = [&](int r) -> Row { /* rows: the coefficient is kept, only the row index is clamped */
+		Row q;
+		if (mode == 0) { q.y0 = q.y1 = y0 + r; q.b0 = 1.f; q.b1 = 0.f; return q; }
+		if (mode == 1) { q.y0 = y0 + 2 * r; q.y1 = q.y0 + 1; q.b0 = 1.f; q.b1 = 0.f; return q; }
+		float f = (float)__dsub_rn(__dmul_rn((double)r + 0.5, scale), 0.5);
+		const int si = (int)floorf(f);
+		f = __fsub_rn(f, (float)si);
+		q.y0 = y0 + min(max(si, 0), side - 1); q.y1 = y0 + min(max(si + 1, 0), side - 1);
+		q.b0 = __fsub_rn(1.f, f); q.b1 = f;
+		return q;
+	};
+	auto px = [&](int xx, int yy) -> uint32_t { /* black canvas outside the image (copyMakeBorder) */
+		return (xx >= 0 && yy >= 0 && xx < W && yy < H) ? (uint32_t)__ldg(img + (int64_t)yy * W + xx) : 0u;
+	};
+	auto load_raw = [&](const Row& q) -> uint32_t { /* the four source pixels, packed; issued one row ahead of their use */
+		if (!xin) return 0u;
+		if (inside) {
+			const uint8_t* r0 = img + (int64_t)q.y0 * W;
+			if (mode == 0) return (uint32_t)__ldg(r0 + cA);
+			const uint8_t* r1 = img + (int64_t)q.y1 * W;
+			return (uint32_t)__ldg(r0 + cA) | ((uint32_t)__ldg(r0 + cB) << 8) | ((uint32_t)__ldg(r1 + cA) << 16) | ((uint32_t)__ldg(r1 + cB) << 24);
+		}
+		if (mode == 0) return px(cA, q.y0);
+		return px(cA, q.y0) | (px(cB, q.y0) << 8) | (px(cA, q.y1) << 16) | (px(cB, q.y1) << 24);
+	};
+	auto finish = [&](uint32_t raw, const Row& q) -> float { /* resized pixel from its packed sources */
+		const float p00 = (float)(raw & 255u), p01 = (float)((raw >> 8) & 255u), p10 = (float)((raw >> 16) & 255u), p11 = (float)(raw >> 24);
+		if (mode == 0) return p00;
+		if (mode == 1) return __fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(p00, p01), p10), p11), 0.25f); /* INTER_AREA fast path of an exact 2x decimation */
+		const float r0 = __fadd_rn(__fmul_rn(p00, a0), __fmul_rn(p01, a1));
+		const float r1 = __fadd_rn(__fmul_rn(p10, a0), __fmul_rn(p11, a1));
+		return __fadd_rn(__fmul_rn(r0, q.b0), __fmul_rn(r1, q.b1));
+	};
+
+	/* ---- pass 1: gradient + dominant directed orientation per pixel, ranks inside the orientation lists ---- */
+	if (lane < 2 * SDM_NO) s.cnt[lane] = 0;
+	__syncwarp();
+	const bool xvalid = x >= 1 && x < SDM_P - 1;
+	float rowA, rowB;
+	{ const Row q0 = row_of(0), q1 = row_of(1); const uint32_t w0 = load_raw(q0), w1 = load_raw(q1); rowA = finish(w0, q0); rowB = finish(w1, q1); }
+	Row qn = row_of(2);
+	uint32_t pending = load_raw(qn);
+	for (int r = 1; r < SDM_P - 1; ++r) {
+		const Row qc = qn;
+		const uint32_t rawc = pending;
+		if (r + 2 < SDM_P) { qn = row_of(r + 2); pending = load_raw(qn); } /* prefetch: consumed in the next iteration */
+		const float rowC = finish(rawc, qc);
+		const float left = __shfl_up_sync(FULL, rowB, 1), right = __shfl_down_sync(FULL, rowB, 1);
+		int key = 31;
 		float grad = 0.f;
-		if (x >= 1 && x < SDM_P - 1 && y >= 1 && y < SDM_P - 1) {
-			float gx = __fsub_rn(s_img[i + 1], s_img[i - 1]), gy = __fsub_rn(s_img[i + SDM_P], s_img[i - SDM_P]);
+		if (xvalid) {
+			float gx = __fsub_rn(right, left), gy = __fsub_rn(rowC, rowA);
 			float g2 = __fadd_rn(__fmul_rn(gx, gx), __fmul_rn(gy, gy));
-			if (!(g2 > 0.f)) { gx = 0.f; gy = 0.f; g2 = 0.f; }
-			grad = __fsqrt_rn(g2);
-			const double den = (double)grad > 1e-10 ? (double)grad : 1e-10;
-			gx = (float)__ddiv_rn((double)gx, den);
-			gy = (float)__ddiv_rn((double)gy, den);
-			float w0 = 0.f, w1 = 0.f;
-			int b0 = -1;
+			if (g2 > 0.f) {
+				grad = __fsqrt_rn(g2);
+				if (grad > 1e-10f) { /* float / double rounded to float == float / float (53 >= 2 * 24 + 2: no double rounding) */
+					gx = __fdiv_rn(gx, grad); gy = __fdiv_rn(gy, grad);
+				} else {
+					const double den = (double)grad > 1e-10 ? (double)grad : 1e-10;
+					gx = (float)__ddiv_rn((double)gx, den); gy = (float)__ddiv_rn((double)gy, den);
+				}
+				float best = 0.f;
+				int bk = -1;
 #pragma unroll
-			for (int k = 0; k < SDM_NO; ++k) {
-				float score = __fadd_rn(__fmul_rn(gx, m.ox[k]), __fmul_rn(gy, m.oy[k]));
-				int b = k;
-				if (score < 0.f) { score = -score; b += SDM_NO; }
-				if (score > w0) { w1 = w0; b0 = b; w0 = score; }
-				else if (score > w1) { w1 = score; }
+				for (int k = 0; k < SDM_NO; ++k) { /* first strict maximum of |score| (hog.c:656-672) */
+					const float score = __fadd_rn(__fmul_rn(gx, m.ox[k]), __fmul_rn(gy, m.oy[k]));
+					if (fabsf(score) > fabsf(best)) { best = score; bk = k; }
+				}
+				if (bk >= 0) key = best < 0.f ? bk + SDM_NO : bk;
 			}
-			if (b0 >= 0) bin = b0;
 		}
-		s_bin[i] = (uint8_t)bin;
-		s_grad[i] = grad;
+		if (r == 5 || r == 15 || r == 25) { if (lane < 2 * SDM_NO) s.seg[r / 10][lane] = s.cnt[lane]; }
+		const unsigned grp = __match_any_sync(FULL, key);
+		const int rank = __popc(grp & ((1u << lane) - 1u));
+		const int fill = key < 2 * SDM_NO ? s.cnt[key] : 0;
+		__syncwarp();
+		if (key < 2 * SDM_NO) {
+			s.bp[r * HW_RS + x] = (uint16_t)((key << 10) | (fill + rank));
+			s.grad[r * HW_RS + x] = grad;
+			if (rank == 0) s.cnt[key] = fill + __popc(grp);
+		} else if (xin) s.bp[r * HW_RS + x] = 0xffffu;
+		__syncwarp();
+		rowA = rowB; rowB = rowC;
 	}
-	__syncthreads();
-	{ /* per row and orientation: which columns hold that bin */
-		const int lane = tid & 31, warp = tid >> 5;
-		for (int y = warp; y < SDM_P; y += SDM_THREADS / 32) {
-			const int b = lane < SDM_P ? s_bin[y * SDM_P + lane] : 255;
+	/* ---- pass 2: exclusive prefix over the 18 list lengths, scatter the pixel ids ---- */
+	{
+		const int c = lane < 2 * SDM_NO ? s.cnt[lane] : 0;
+		int incl = c;
 #pragma unroll
-			for (int o = 0; o < 2 * SDM_NO; ++o) {
-				const uint32_t msk = __ballot_sync(0xffffffffu, b == o);
-				if (lane == 0) s_mask[y][o] = msk;
+		for (int d = 1; d < 32; d <<= 1) { const int v = __shfl_up_sync(FULL, incl, d); if (lane >= d) incl += v; }
+		if (lane < 2 * SDM_NO) s.base[lane] = incl - c;
+		__syncwarp();
+		if (xvalid)
+			for (int r = 1; r < SDM_P - 1; ++r) {
+				const unsigned v = s.bp[r * HW_RS + x];
+				if (v != 0xffffu) s.list[s.base[v >> 10] + (v & 1023u)] = (uint16_t)(r * HW_RS + x);
 			}
-		}
+		__syncwarp();
 	}
-	__syncthreads();
-	/* bilinear cell accumulation (hog.c:697-722): entry (o, cy, cx) visits its pixels in raster order */
-	for (int e = tid; e < SDM_CELLS * SDM_CELLS * 2 * SDM_NO; e += SDM_THREADS) {
-		const int o = e / (SDM_CELLS * SDM_CELLS), c = e - o * (SDM_CELLS * SDM_CELLS), cy = c / SDM_CELLS, cx = c - cy * SDM_CELLS;
-		float acc = 0.f;
-		for (int y = 1; y < SDM_P - 1; ++y) {
-			const int by = m.bin_of[y];
-			float wy;
-			if (by == cy) wy = m.w1_of[y];
-			else if (by + 1 == cy) wy = m.w2_of[y];
-			else continue;
-			uint32_t msk = s_mask[y][o];
-			while (msk) {
-				const int x = __ffs(msk) - 1;
-				msk &= msk - 1;
-				const int bx = m.bin_of[x];
-				float wx;
-				if (bx == cx) wx = m.w1_of[x];
-				else if (bx + 1 == cx) wx = m.w2_of[x];
-				else continue;
-				acc = __fadd_rn(acc, __fmul_rn(__fmul_rn(s_grad[y * SDM_P + x], wx), wy));
-			}
+	/* ---- pass 3: cell accumulation; pair p = (orientation o, cell row cy) ---- */
+	for (int p = lane; p < 2 * SDM_NO * SDM_CELLS; p += 32) {
+		const int o = p / SDM_CELLS, cy = p - o * SDM_CELLS;
+		const int b = s.base[o];
+		const int beg = b + (cy == 0 ? 0 : s.seg[cy - 1][o]);            /* rows 1.., 5.., 15.. */
+		const int end = b + (cy == 2 ? s.cnt[o] : s.seg[cy + 1][o]);     /* ..14, ..24, ..28 */
+		float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f;
+		for (int i = beg; i < end; ++i) {
+			const int id = s.list[i];
+			const float g = s.grad[id];
+			const float4 wx = s_wx[id & 31];
+			const float wy = s_wy[cy][id >> 5];
+			acc0 = __fadd_rn(acc0, __fmul_rn(__fmul_rn(g, wx.x), wy));
+			acc1 = __fadd_rn(acc1, __fmul_rn(__fmul_rn(g, wx.y), wy));
+			acc2 = __fadd_rn(acc2, __fmul_rn(__fmul_rn(g, wx.z), wy));
 		}
-		s_hog[e] = acc;
+		float* h = s.hog + o * 9 + cy * 3;
+		h[0] = acc0; h[1] = acc1; h[2] = acc2;
 	}
-	__syncthreads();
-	/* ---- vl_hog_extract (hog.c:879-1060) ---- */
-	if (tid < SDM_CELLS * SDM_CELLS) {
+	__syncwarp();
+	/* ---- pass 4: vl_hog_extract (hog.c:879-1060) ---- */
+	if (lane < SDM_CELLS * SDM_CELLS) {
 		float nrm = 0.f;
 		for (int k = 0; k < SDM_NO; ++k) {
-			const float h = __fadd_rn(s_hog[k * 9 + tid], s_hog[(k + SDM_NO) * 9 + tid]);
+			const float h = __fadd_rn(s.hog[k * 9 + lane], s.hog[(k + SDM_NO) * 9 + lane]);
 			nrm = __fadd_rn(nrm, __fmul_rn(h, h));
 		}
-		s_norm[tid] = nrm;
+		s.norm[lane] = nrm;
 	}
-	__syncthreads();
-	if (tid < SDM_CELLS * SDM_CELLS) {
-		const int y = tid / SDM_CELLS, x = tid - y * SDM_CELLS;
-		const int xm = max(x - 1, 0), xp = min(x + 1, SDM_CELLS - 1), ym = max(y - 1, 0), yp = min(y + 1, SDM_CELLS - 1);
-#define NRM(xx, yy) ((double)s_norm[(yy) * SDM_CELLS + (xx)])
-		const double n1 = NRM(xm, ym), n2 = NRM(x, ym), n3 = NRM(xp, ym), n4 = NRM(xm, y), n5 = NRM(x, y), n6 = NRM(xp, y);
-		const double n7 = NRM(xm, yp), n8 = NRM(x, yp), n9 = NRM(xp, yp);
-#undef NRM
-		s_fac[tid][0] = __ddiv_rn(1.0, sqrt(__dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(n1, n2), n4), n5), 1e-4)));
-		s_fac[tid][1] = __ddiv_rn(1.0, sqrt(__dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(n2, n3), n5), n6), 1e-4)));
-		s_fac[tid][2] = __ddiv_rn(1.0, sqrt(__dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(n4, n5), n7), n8), 1e-4)));
-		s_fac[tid][3] = __ddiv_rn(1.0, sqrt(__dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(n5, n6), n8), n9), 1e-4)));
+	__syncwarp();
+	if (lane < SDM_CELLS * SDM_CELLS * 4) { /* (cell, block) -> 1 / sqrt(sum of the block's four cell norms + 1e-4) */
+		const int c = lane >> 2, q = lane & 3, y = c / SDM_CELLS, xx = c - y * SDM_CELLS;
+		const int xa = q & 1 ? xx : max(xx - 1, 0), xb = q & 1 ? min(xx + 1, SDM_CELLS - 1) : xx;   /* block columns, left to right */
+		const int ya = q & 2 ? y : max(y - 1, 0), yb = q & 2 ? min(y + 1, SDM_CELLS - 1) : y;
+		const double n_aa = s.norm[ya * SDM_CELLS + xa], n_ab = s.norm[ya * SDM_CELLS + xb];
+		const double n_ba = s.norm[yb * SDM_CELLS + xa], n_bb = s.norm[yb * SDM_CELLS + xb];
+		s.fac[c][q] = __ddiv_rn(1.0, sqrt(__dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(n_aa, n_ab), n_ba), n_bb), 1e-4)));
 	}
-	__syncthreads();
-	/* descriptor layout (DescriptorExtractor.hpp:196-204): dimension j, then cell column x, then cell row y */
-	if (tid < SDM_CELLS * SDM_CELLS * SDM_NO) {
-		const int c = tid / SDM_NO, k = tid - c * SDM_NO, cy = c / SDM_CELLS, cx = c - cy * SDM_CELLS;
-		const double ha = s_hog[k * 9 + c], hb = s_hog[(k + SDM_NO) * 9 + c];
+	if (lane + 32 < SDM_CELLS * SDM_CELLS * 4) {
+		const int e = lane + 32, c = e >> 2, q = e & 3, y = c / SDM_CELLS, xx = c - y * SDM_CELLS;
+		const int xa = q & 1 ? xx : max(xx - 1, 0), xb = q & 1 ? min(xx + 1, SDM_CELLS - 1) : xx;
+		const int ya = q & 2 ? y : max(y - 1, 0), yb = q & 2 ? min(y + 1, SDM_CELLS - 1) : y;
+		const double n_aa = s.norm[ya * SDM_CELLS + xa], n_ab = s.norm[ya * SDM_CELLS + xb];
+		const double n_ba = s.norm[yb * SDM_CELLS + xa], n_bb = s.norm[yb * SDM_CELLS + xb];
+		s.fac[c][q] = __ddiv_rn(1.0, sqrt(__dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(n_aa, n_ab), n_ba), n_bb), 1e-4)));
+	}
+	__syncwarp();
+	float* stage = s.grad; /* descriptor layout (DescriptorExtractor.hpp:196-204): dimension j, then cell column, then cell row */
+	for (int e = lane; e < SDM_CELLS * SDM_CELLS * SDM_NO; e += 32) {
+		const int c = e / SDM_NO, k = e - c * SDM_NO, cy = c / SDM_CELLS, cx = c - cy * SDM_CELLS;
+		const double ha = s.hog[k * 9 + c], hb = s.hog[(k + SDM_NO) * 9 + c];
 		double sa = 0, sb = 0, sc = 0;
 #pragma unroll
 		for (int q = 0; q < 4; ++q) {
-			const double f = s_fac[c][q];
+			const double f = s.fac[c][q];
 			const double haq = __dmul_rn(f, ha), hbq = __dmul_rn(f, hb);
-			const double hcq = __dadd_rn(haq, hbq);
-			const double hcm = fmin(0.2, hcq);
-			s_hc[c][k][q] = hcm;
+			const double hcm = fmin(0.2, __dadd_rn(haq, hbq));
 			sa = q == 0 ? fmin(0.2, haq) : __dadd_rn(sa, fmin(0.2, haq));
 			sb = q == 0 ? fmin(0.2, hbq) : __dadd_rn(sb, fmin(0.2, hbq));
 			sc = q == 0 ? hcm : __dadd_rn(sc, hcm);
 		}
 		const int pos = cx * SDM_CELLS + cy;
-		out[k * 9 + pos] = (float)__dmul_rn(0.5, sa);
-		out[(k + SDM_NO) * 9 + pos] = (float)__dmul_rn(0.5, sb);
-		out[(k + 2 * SDM_NO) * 9 + pos] = (float)__dmul_rn(0.5, sc);
+		stage[k * 9 + pos] = (float)__dmul_rn(0.5, sa);
+		stage[(k + SDM_NO) * 9 + pos] = (float)__dmul_rn(0.5, sb);
+		stage[(k + 2 * SDM_NO) * 9 + pos] = (float)__dmul_rn(0.5, sc);
 	}
-	__syncthreads();
-	if (tid < SDM_CELLS * SDM_CELLS * 4) { /* texture features: t_q = sum over k of the clamped hc (hog.c:1012-1015,1046-1049) */
-		const int c = tid >> 2, q = tid & 3, cy = c / SDM_CELLS, cx = c - cy * SDM_CELLS;
+	for (int e = lane; e < SDM_CELLS * SDM_CELLS * 4; e += 32) { /* texture features: t_q = sum over k of the clamped hc (hog.c:1012-1015,1046-1049) */
+		const int c = e >> 2, q = e & 3, cy = c / SDM_CELLS, cx = c - cy * SDM_CELLS;
+		const double f = s.fac[c][q];
 		double t = 0;
-		for (int k = 0; k < SDM_NO; ++k) t = __dadd_rn(t, s_hc[c][k][q]);
-		out[(3 * SDM_NO + q) * 9 + cx * SDM_CELLS + cy] = (float)__dmul_rn((double)m.tex, t);
+		for (int k = 0; k < SDM_NO; ++k) {
+			const double ha = s.hog[k * 9 + c], hb = s.hog[(k + SDM_NO) * 9 + c];
+			t = __dadd_rn(t, fmin(0.2, __dadd_rn(__dmul_rn(f, ha), __dmul_rn(f, hb))));
+		}
+		stage[(3 * SDM_NO + q) * 9 + cx * SDM_CELLS + cy] = (float)__dmul_rn((double)m.tex, t);
 	}
+	__syncwarp();
+	for (int i = lane; i < SDM_DESC; i += 32) out[i] = stage[i];
 }
 
 /* ------------------------------------------------------------------------------------------------
@@ -497,8 +575,9 @@ void sdm_fill_tables(DevSdm* m, int L, int steps) {
 void launch_sdm_hog(cudaStream_t st, const DevSdm& m, const uint8_t* frames, int W, int H, const int* face_frame, const float* shapes,
 		int step, const float* pts_xy, int window_half, int n_faces, float* features, int* status) {
 	if (n_faces == 0) return;
-	dim3 grid((unsigned)m.L, (unsigned)n_faces);
-	sdm_hog_kernel<<<grid, SDM_THREADS, 0, st>>>(m, frames, W, H, face_frame, shapes, step, pts_xy, window_half, features, status);
+	const int n_desc = n_faces * m.L;
+	sdm_hog_kernel<<<(unsigned)((n_desc + HW_WARPS - 1) / HW_WARPS), HW_WARPS * 32, 0, st>>>(m, frames, W, H, face_frame, shapes, step, pts_xy,
+			window_half, n_desc, features, status);
 }
 
 static int gemm_mode() { /* FDB_SDM_GEMM = scalar | m8 | m16 (default): tuning / cross-check hook */
