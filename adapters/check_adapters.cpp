@@ -1,6 +1,17 @@
 /* Compile check of the adapters against the reference's unchanged headers (tests/test_adapters_compile.py):
  * instantiates every adapter so that a missing pure-virtual override fails the build. */
 #include "fdb200_adapters.hpp"
+#include "fdb200_sdm_adapter.hpp"
+
+/* stand-in with the getters of superviseddescent::SdmLandmarkModel (SdmLandmarkModel.hpp:74-87; that header itself needs
+ * OpenCV nonfree, Boost and libImageIO, which the compile check does not have) */
+struct MockSdmModel {
+	int getNumLandmarks() const { return 13; }
+	int getNumCascadeSteps() const { return 1; }
+	cv::Mat getMeanShape() const { return cv::Mat::zeros(26, 1, CV_32FC1); }
+	cv::Mat getRegressorData(int) { return cv::Mat::zeros(13 * 279 + 1, 26, CV_32FC1); }
+	std::string getDescriptorType(int) { return "vlhog-uoctti"; }
+};
 
 int main() {
 	std::shared_ptr<fdb200::Context> ctx; /* not created: no GPU needed to type-check */
@@ -18,6 +29,10 @@ int main() {
 		d->detect(frame);
 		e->update(frame);
 		e->extract(1, 1);
+		fdb200::B200SdmLandmarkModelFitting fit(ctx->get(), MockSdmModel());
+		cv::Mat shape = fit.alignRigid(MockSdmModel().getMeanShape(), cv::Rect(10, 10, 100, 100));
+		shape = fit.optimize(shape, frame);
+		fdb200::B200SdmLandmarkModelFitting fromFile(ctx->get(), std::string("model.txt"));
 	}
 	return 0;
 }

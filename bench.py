@@ -316,9 +316,9 @@ def run_sdm(args, rank, world, local_rank):
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": int(algo_bytes), "kernel_ms": hog_ms,
                          "launches_per_step": SDM_STEPS,
-                         "note": "instruction bound (~900 pixels x 9 orientation scores + exact-order histogram per landmark); the regressor "
+                         "note": "instruction bound (~11.7e3 warp instructions per descriptor: 900 pixels x 9 orientation scores + exact-order cell sums); the regressor "
                                  "product is reported under `gemm`"},
-            "gemm": {"kernel": "sdm_gemm_kernel (float32 operands, float64 accumulation like cv::gemm on CV_32F)", "m": n, "n": N, "k": K,
+            "gemm": {"kernel": "sdm_gemm_dmma_kernel (FP64 tensor cores: float32 operands, float64 accumulation like cv::gemm on CV_32F)", "m": n, "n": N, "k": K,
                      "ms": prof["gemm"] / SDM_STEPS, "tflops_fp64": gemm_flops / (prof["gemm"] / SDM_STEPS * 1e-3) / 1e12},
             "kernel_ms_per_fit": prof, "faces_out_of_image": int((status_e2e != 0).sum()),
             "cpu_baseline": cpu}), flush=True)

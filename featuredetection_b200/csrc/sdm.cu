@@ -8,14 +8,14 @@
  *   sdm_hog_kernel     one WARP per (landmark, face): crop (black canvas outside the image, with the reference's
  *                      row-offset quirk), float32 bilinear resize to 30x30, VLFeat HOG (3x3 cells x 31) written
  *                      straight into the face's feature row [face][landmark * 279 + ...]
- *   sdm_gemm_kernel    delta[faces x 2L] = features[faces x 279 L] * R[0:-1] + R[-1]: float32 inputs, FLOAT64
- *                      accumulation in k order, exactly what cv::gemm does for CV_32F - the products of two floats
- *                      are exact in double, so the tiled kernel is bit-identical to the sequential reference sum
+ *   sdm_gemm_dmma_kernel  delta[faces x 2L] = features[faces x 279 L] * R[0:-1] + R[-1] on the FP64 tensor cores: float32 inputs,
+ *                      FLOAT64 accumulation, which is what cv::gemm does for CV_32F - the product of two floats is exact in
+ *                      double, so the result agrees with the sequential reference sum to ~1e-16 relative
  *   sdm_update_kernel  shape += delta^T * eye-mouth distance
- * Why not the tensor cores: the fit is a feedback loop through cvRound(landmark) - a 1e-5 px difference in a shape
- * moves a HOG window by a whole pixel with probability ~1e-5 per coordinate, and 2L x steps coordinates per face
- * turn that into visibly different fits for ~1 % of the faces.  bf16/tf32 products cannot stay below that; the
- * float64-accumulated product can, and at [4096 x 18972] x [18972 x 136] it costs ~1 ms per step against ~3 ms of HOG.
+ * Why FP64 and not bf16/tf32 tensor cores: the fit is a feedback loop through cvRound(landmark) - a 1e-5 px difference in a
+ * shape moves a HOG window by a whole pixel with probability ~1e-5 per coordinate, and 2L x steps coordinates per face turn
+ * that into visibly different fits for ~1 % of the faces.  The float64-accumulated product stays below that, and on the DMMA
+ * pipe [4096 x 18972] x [18972 x 136] costs ~1 ms per step against ~3.8 ms of HOG.
  *
  * Exactness: every float32/float64 operation of the reference is issued in its order with _rn intrinsics (no FMA
  * contraction); histogram cells are accumulated by one thread per (cell, orientation) in pixel raster order.
@@ -748,14 +748,17 @@ int32_t fdb_sdm_num_cascade_steps(const fdb_sdm* m) { return m ? m->dev.steps : 
 int fdb_sdm_align_rigid(const fdb_sdm* m, const int32_t* boxes, int64_t n_faces, float* shapes_out) {
 	if (!m || !boxes || !shapes_out) return fail(FDB_ERR_INVALID_ARGUMENT, "null argument");
 	const int L = m->dev.L;
-	for (int64_t f = 0; f < n_faces; ++f) { /* SdmLandmarkModel.hpp:156-192 with modelShape = mean: (mean + 0.5) * size + corner, float32 */
-		const float x = (float)boxes[4 * f], y = (float)boxes[4 * f + 1], w = (float)boxes[4 * f + 2], h = (float)boxes[4 * f + 3];
+	/* SdmLandmarkModel.hpp:156-192 with modelShape = mean. The source line `(xCoords + 0.5f) * faceBox.width + faceBox.x` is a
+	 * cv::MatExpr that OpenCV folds into convertTo(CV_32F, alpha = w, beta = 0.5 w + x): one float32 multiply, one float32 add
+	 * (core/src/matop.cpp MatOp_AddEx, core/src/convert.cpp cvtScale_<float, float, float>). */
+	for (int64_t f = 0; f < n_faces; ++f) {
+		const float ax = (float)boxes[4 * f + 2], bx = (float)(0.5 * boxes[4 * f + 2] + boxes[4 * f]);
+		const float ay = (float)boxes[4 * f + 3], by = (float)(0.5 * boxes[4 * f + 3] + boxes[4 * f + 1]);
 		float* shape = shapes_out + f * 2 * L;
 		for (int i = 0; i < L; ++i) {
-			volatile float tx = m->mean[i] + 0.5f, ty = m->mean[L + i] + 0.5f; /* volatile: one rounding per operation */
-			volatile float sx = tx * w, sy = ty * h;
-			shape[i] = sx + x;
-			shape[L + i] = sy + y;
+			volatile float tx = m->mean[i] * ax, ty = m->mean[L + i] * ay; /* volatile: one rounding per operation, no contraction */
+			shape[i] = tx + bx;
+			shape[L + i] = ty + by;
 		}
 	}
 	return FDB_OK;

@@ -290,11 +290,17 @@ fail:
 	return NULL;
 }
 
-/* SdmLandmarkModelFitting::alignRigid (SdmLandmarkModel.hpp:156-192): shape = (mean + 0.5) * box size + box corner */
+/* SdmLandmarkModelFitting::alignRigid (SdmLandmarkModel.hpp:156-192) with modelShape = mean:
+ * `xCoords = (xCoords + 0.5f) * faceBox.width + faceBox.x` is a cv::MatExpr. OpenCV folds it (core/src/matop.cpp, MatOp_AddEx:
+ * operator+(Mat, Scalar) -> {alpha 1, s 0.5}; multiply(w) -> {alpha w, s 0.5 w}; add(x) -> {alpha w, s 0.5 w + x}, all in double)
+ * and assigns through Mat::convertTo(CV_32F, alpha, s), whose CV_32F kernel (core/src/convert.cpp cvtScale_<float, float, float>)
+ * computes saturate_cast<float>(src * (float)alpha + (float)s): ONE multiply and ONE add in float32, not the three operations
+ * the source line suggests. 0.5 w + x is a half-integer, exact in float. */
 void fdo_sdm_align_rigid(const fdo_sdm* m, int fx, int fy, int fw, int fh, float* shape) {
+	const float ax = (float)fw, bx = (float)(0.5 * fw + fx), ay = (float)fh, by = (float)(0.5 * fh + fy);
 	for (int i = 0; i < m->L; ++i) {
-		shape[i] = (m->mean[i] + 0.5f) * (float)fw + (float)fx;
-		shape[m->L + i] = (m->mean[m->L + i] + 0.5f) * (float)fh + (float)fy;
+		shape[i] = m->mean[i] * ax + bx;
+		shape[m->L + i] = m->mean[m->L + i] * ay + by;
 	}
 }
 
