@@ -632,6 +632,9 @@ void launch_sdm_update(cudaStream_t st, const DevSdm& m, int step, const float* 
 /* ------------------------------------------------------------------------------------------------
  * C ABI (include/fdb200.h, "Supervised-descent landmark regressor")
  * ---------------------------------------------------------------------------------------------- */
+#define SDM_CHUNKS 4
+#define SDM_CHUNK_MIN_BYTES (64ll << 20) /* pipeline the upload only when the frames are big enough to matter */
+
 struct fdb_sdm {
 	fdb_ctx* ctx = nullptr;
 	fdb::DevSdm dev{};
@@ -646,6 +649,8 @@ struct fdb_sdm {
 	int* d_face_frame = nullptr;  /* [faces] */
 	uint8_t* d_frames = nullptr;  /* host-call staging */
 	cudaEvent_t ev[2 * SDM_MAX_STEPS * 3 + 2] = {};
+	cudaStream_t chunk_stream[SDM_CHUNKS] = {};  /* host-call pipeline: upload of frame chunk c + 1 overlaps the fit of chunk c */
+	cudaEvent_t chunk_ev[SDM_CHUNKS + 1] = {};
 };
 
 using namespace fdb;
@@ -676,21 +681,23 @@ int sdm_reserve(fdb_sdm* m, int64_t n_faces, int64_t frame_bytes) {
 /* the cascade (SdmLandmarkModel.hpp:231-249) on device-resident data; features_host: NULL or [steps][faces][K];
  * ev: NULL or 6 * steps + 2 events recorded around each kernel family */
 int sdm_run(fdb_sdm* m, const uint8_t* d_frames, int W, int H, const int* d_face_frame, int64_t n_faces, float* d_shapes, int* d_status,
-		float* features_host, cudaEvent_t* ev) {
-	cudaStream_t st = m->ctx->stream;
-	int* status = d_status ? d_status : m->d_status;
+		float* features_host, cudaEvent_t* ev, cudaStream_t st = nullptr, int64_t first_face = 0) {
+	if (!st) st = m->ctx->stream;
+	int* status = d_status ? d_status : m->d_status + first_face;
+	float* const features = m->d_features + first_face * m->dev.K; /* workspace rows of this face range */
+	float* const delta = m->d_delta + first_face * m->dev.N;
 	CUDA_TRY(cudaMemsetAsync(status, 0, sizeof(int) * (size_t)n_faces, st));
 	if (ev) CUDA_TRY(cudaEventRecord(ev[0], st));
 	for (int s = 0; s < m->dev.steps; ++s) {
-		launch_sdm_hog(st, m->dev, d_frames, W, H, d_face_frame, d_shapes, s, nullptr, 0, (int)n_faces, m->d_features, status);
+		launch_sdm_hog(st, m->dev, d_frames, W, H, d_face_frame, d_shapes, s, nullptr, 0, (int)n_faces, features, status);
 		if (ev) CUDA_TRY(cudaEventRecord(ev[1 + 3 * s], st));
-		launch_sdm_gemm(st, m->dev, s, m->d_features, (int)n_faces, m->d_delta);
+		launch_sdm_gemm(st, m->dev, s, features, (int)n_faces, delta);
 		if (ev) CUDA_TRY(cudaEventRecord(ev[2 + 3 * s], st));
-		launch_sdm_update(st, m->dev, s, m->d_delta, d_shapes, status, (int)n_faces);
+		launch_sdm_update(st, m->dev, s, delta, d_shapes, status, (int)n_faces);
 		if (ev) CUDA_TRY(cudaEventRecord(ev[3 + 3 * s], st));
 		m->ctx->launches += 3;
 		if (features_host)
-			CUDA_TRY(cudaMemcpyAsync(features_host + (size_t)s * n_faces * m->dev.K, m->d_features, sizeof(float) * (size_t)n_faces * m->dev.K,
+			CUDA_TRY(cudaMemcpyAsync(features_host + (size_t)s * n_faces * m->dev.K, features, sizeof(float) * (size_t)n_faces * m->dev.K,
 					cudaMemcpyDeviceToHost, st));
 	}
 	CUDA_TRY(cudaGetLastError());
@@ -728,6 +735,8 @@ int fdb_sdm_create(fdb_ctx* ctx, const fdb_sdm_desc* d, fdb_sdm** out) {
 		m->dev.R[k] = p;
 	}
 	for (cudaEvent_t& e : m->ev) if (cudaEventCreate(&e) != cudaSuccess) { fdb_sdm_destroy(m); return fail(FDB_ERR_CUDA, "cudaEventCreate"); }
+	for (cudaEvent_t& e : m->chunk_ev) if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { fdb_sdm_destroy(m); return fail(FDB_ERR_CUDA, "cudaEventCreate"); }
+	for (cudaStream_t& t : m->chunk_stream) if (cudaStreamCreateWithFlags(&t, cudaStreamNonBlocking) != cudaSuccess) { fdb_sdm_destroy(m); return fail(FDB_ERR_CUDA, "cudaStreamCreate"); }
 	*out = m;
 	return FDB_OK;
 }
@@ -739,6 +748,8 @@ void fdb_sdm_destroy(fdb_sdm* m) {
 	free_all(m->owned);
 	for (void* p : {(void*)m->d_features, (void*)m->d_delta, (void*)m->d_shapes, (void*)m->d_status, (void*)m->d_face_frame, (void*)m->d_frames}) if (p) cudaFree(p);
 	for (cudaEvent_t e : m->ev) if (e) cudaEventDestroy(e);
+	for (cudaEvent_t e : m->chunk_ev) if (e) cudaEventDestroy(e);
+	for (cudaStream_t t : m->chunk_stream) if (t) cudaStreamDestroy(t);
 	delete m;
 }
 
@@ -811,17 +822,69 @@ int fdb_sdm_optimize_batch(fdb_sdm* m, const uint8_t* frames, int64_t pitch, int
 	if (n_faces == 0) return FDB_OK;
 	s = sdm_reserve(m, n_faces, (int64_t)n_frames * W * H); if (s) return s;
 	cudaStream_t st = m->ctx->stream;
-	if (pitch == W) CUDA_TRY(cudaMemcpyAsync(m->d_frames, frames, (size_t)n_frames * W * H, cudaMemcpyHostToDevice, st));
-	else CUDA_TRY(cudaMemcpy2DAsync(m->d_frames, (size_t)W, frames, (size_t)pitch, (size_t)W, (size_t)n_frames * H, cudaMemcpyHostToDevice, st));
+	const int N = m->dev.N;
+	const size_t frame_bytes = (size_t)W * H;
+	auto upload_frames = [&](int f0, int f1, cudaStream_t t) -> cudaError_t {
+		if (pitch == W) return cudaMemcpyAsync(m->d_frames + f0 * frame_bytes, frames + f0 * frame_bytes, (size_t)(f1 - f0) * frame_bytes, cudaMemcpyHostToDevice, t);
+		return cudaMemcpy2DAsync(m->d_frames + f0 * frame_bytes, (size_t)W, frames + (size_t)f0 * pitch * H, (size_t)pitch, (size_t)W, (size_t)(f1 - f0) * H,
+				cudaMemcpyHostToDevice, t);
+	};
 	std::vector<int> ident;
 	if (!face_frame) { ident.resize((size_t)n_faces); for (int64_t i = 0; i < n_faces; ++i) ident[i] = (int)i; face_frame = ident.data(); }
-	CUDA_TRY(cudaMemcpyAsync(m->d_face_frame, face_frame, sizeof(int) * (size_t)n_faces, cudaMemcpyHostToDevice, st));
-	CUDA_TRY(cudaMemcpyAsync(m->d_shapes, shapes, sizeof(float) * (size_t)n_faces * m->dev.N, cudaMemcpyHostToDevice, st));
-	s = sdm_run(m, m->d_frames, W, H, m->d_face_frame, n_faces, m->d_shapes, nullptr, features_out, nullptr);
-	if (s) { cudaStreamSynchronize(st); return s; }
-	CUDA_TRY(cudaMemcpyAsync(shapes, m->d_shapes, sizeof(float) * (size_t)n_faces * m->dev.N, cudaMemcpyDeviceToHost, st));
-	if (status_out) CUDA_TRY(cudaMemcpyAsync(status_out, m->d_status, sizeof(int) * (size_t)n_faces, cudaMemcpyDeviceToHost, st));
+	const bool pipelined = !features_out && n_frames >= SDM_CHUNKS && (int64_t)n_frames * (int64_t)frame_bytes >= SDM_CHUNK_MIN_BYTES && n_faces >= 64 * SDM_CHUNKS;
+	if (!pipelined) {
+		CUDA_TRY(upload_frames(0, n_frames, st));
+		CUDA_TRY(cudaMemcpyAsync(m->d_face_frame, face_frame, sizeof(int) * (size_t)n_faces, cudaMemcpyHostToDevice, st));
+		CUDA_TRY(cudaMemcpyAsync(m->d_shapes, shapes, sizeof(float) * (size_t)n_faces * N, cudaMemcpyHostToDevice, st));
+		s = sdm_run(m, m->d_frames, W, H, m->d_face_frame, n_faces, m->d_shapes, nullptr, features_out, nullptr);
+		if (s) { cudaStreamSynchronize(st); return s; }
+		CUDA_TRY(cudaMemcpyAsync(shapes, m->d_shapes, sizeof(float) * (size_t)n_faces * N, cudaMemcpyDeviceToHost, st));
+		if (status_out) CUDA_TRY(cudaMemcpyAsync(status_out, m->d_status, sizeof(int) * (size_t)n_faces, cudaMemcpyDeviceToHost, st));
+		CUDA_TRY(cudaStreamSynchronize(st));
+		return FDB_OK;
+	}
+	/* Pipelined host call: the frames go up in SDM_CHUNKS pieces, each on its own stream followed by the whole cascade of the
+	 * faces that lie in that piece, so the copy engine works on piece c + 1 while the SMs fit the faces of piece c (faces are
+	 * independent: SURVEY.md 8(e)).  Faces are grouped by piece with a stable counting sort and scattered back at the end. */
+	auto chunk_of = [&](int frame) { return (int)((int64_t)frame * SDM_CHUNKS / n_frames); };
+	int64_t begin[SDM_CHUNKS + 1] = {0};
+	for (int64_t i = 0; i < n_faces; ++i) ++begin[chunk_of(face_frame[i]) + 1];
+	for (int c = 0; c < SDM_CHUNKS; ++c) begin[c + 1] += begin[c];
+	std::vector<int64_t> order((size_t)n_faces);
+	{
+		int64_t fill[SDM_CHUNKS];
+		for (int c = 0; c < SDM_CHUNKS; ++c) fill[c] = begin[c];
+		for (int64_t i = 0; i < n_faces; ++i) order[(size_t)fill[chunk_of(face_frame[i])]++] = i;
+	}
+	std::vector<float> hshapes((size_t)n_faces * N);
+	std::vector<int> hframe((size_t)n_faces), hstatus((size_t)n_faces);
+	for (int64_t k = 0; k < n_faces; ++k) {
+		std::memcpy(&hshapes[(size_t)k * N], shapes + order[(size_t)k] * N, sizeof(float) * N);
+		hframe[(size_t)k] = face_frame[order[(size_t)k]];
+	}
+	CUDA_TRY(cudaMemcpyAsync(m->d_face_frame, hframe.data(), sizeof(int) * (size_t)n_faces, cudaMemcpyHostToDevice, st));
+	CUDA_TRY(cudaMemcpyAsync(m->d_shapes, hshapes.data(), sizeof(float) * (size_t)n_faces * N, cudaMemcpyHostToDevice, st));
+	CUDA_TRY(cudaEventRecord(m->chunk_ev[SDM_CHUNKS], st));
+	for (int c = 0; c < SDM_CHUNKS; ++c) {
+		cudaStream_t t = m->chunk_stream[c];
+		const int f0 = (int)(((int64_t)c * n_frames + SDM_CHUNKS - 1) / SDM_CHUNKS), f1 = (int)(((int64_t)(c + 1) * n_frames + SDM_CHUNKS - 1) / SDM_CHUNKS);
+		CUDA_TRY(cudaStreamWaitEvent(t, m->chunk_ev[SDM_CHUNKS], 0));
+		if (f1 > f0) CUDA_TRY(upload_frames(f0, f1, t));
+		const int64_t nf = begin[c + 1] - begin[c];
+		if (nf > 0) {
+			s = sdm_run(m, m->d_frames, W, H, m->d_face_frame + begin[c], nf, m->d_shapes + begin[c] * N, nullptr, nullptr, nullptr, t, begin[c]);
+			if (s) { cudaDeviceSynchronize(); return s; }
+		}
+		CUDA_TRY(cudaEventRecord(m->chunk_ev[c], t));
+		CUDA_TRY(cudaStreamWaitEvent(st, m->chunk_ev[c], 0));
+	}
+	CUDA_TRY(cudaMemcpyAsync(hshapes.data(), m->d_shapes, sizeof(float) * (size_t)n_faces * N, cudaMemcpyDeviceToHost, st));
+	CUDA_TRY(cudaMemcpyAsync(hstatus.data(), m->d_status, sizeof(int) * (size_t)n_faces, cudaMemcpyDeviceToHost, st));
 	CUDA_TRY(cudaStreamSynchronize(st));
+	for (int64_t k = 0; k < n_faces; ++k) {
+		std::memcpy(shapes + order[(size_t)k] * N, &hshapes[(size_t)k * N], sizeof(float) * N);
+		if (status_out) status_out[order[(size_t)k]] = hstatus[(size_t)k];
+	}
 	return FDB_OK;
 }
 

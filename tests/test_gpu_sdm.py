@@ -114,3 +114,22 @@ def test_batch_is_order_independent(ctx, models):
     perm = rng.permutation(n)
     b, sb = sdm.optimize(frames, start[perm], ff[perm])
     assert np.array_equal(sa[perm], sb) and np.array_equal(a[perm], b)
+
+
+def test_pipelined_upload_matches_plain_call(ctx, models):
+    """>= 64 MiB of frames: the host call uploads the frames in chunks, each followed by the fit of its faces on its own
+    stream (sdm.cu, SDM_CHUNKS); the result must be what the plain call gives for the same faces"""
+    sdm = SdmLandmarkModel(ctx, models[68])
+    base = syn.synthetic_frames(0, 8)
+    frames = np.concatenate([base] * 28)            # 224 frames, 68.8 MB
+    rng = np.random.default_rng(11)
+    n = 700
+    boxes = np.stack([rng.integers(60, 300, n), rng.integers(40, 180, n), rng.integers(120, 260, n), rng.integers(120, 260, n)], axis=1).astype(np.int32)
+    boxes[:, 2] = np.minimum(boxes[:, 2], 600 - boxes[:, 0]); boxes[:, 3] = np.minimum(boxes[:, 3], 450 - boxes[:, 1])
+    boxes[::97] = [5, 5, 200, 200]                  # some faces leave the image: status must travel through the permutation
+    ff = rng.integers(0, 224, n).astype(np.int32)
+    start = sdm.align_rigid(boxes)
+    a, sa = sdm.optimize(frames, start, ff)         # pipelined
+    b, sb = sdm.optimize(base, start, ff % 8)       # plain
+    assert np.array_equal(sa, sb) and np.array_equal(a, b)
+    assert (sa != 0).any() and (sa == 0).any()
