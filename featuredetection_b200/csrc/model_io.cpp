@@ -12,6 +12,7 @@
  */
 #include <cstdlib>
 #include <fstream>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -193,5 +194,203 @@ int fdb_sdm_file_load(const char* path, fdb_sdm_file** out) {
 
 const fdb_sdm_desc* fdb_sdm_file_desc(const fdb_sdm_file* f) { return f ? &f->desc : nullptr; }
 void fdb_sdm_file_free(fdb_sdm_file* f) { delete f; }
+
+} // extern "C"
+
+/* ------------------------------------------------------------------------------------------------
+ * MATLAB classifier files (the format every ffpDetectApp .cfg points at: classifierFile / thresholdsFile)
+ *   WvmClassifier::loadFromMatlab                            libClassification/src/classification/WvmClassifier.cpp:348-770
+ *   ProbabilisticWvmClassifier::loadSigmoidParamsFromMatlab  ProbabilisticWvmClassifier.cpp:95-137
+ *   SvmClassifier::loadFromMatlab                            SvmClassifier.cpp:240-335
+ *   ProbabilisticSvmClassifier::loadSigmoidParamsFromMatlab  ProbabilisticSvmClassifier.cpp:114-162
+ * restated over matfile.cpp (the reference goes through MATLAB's libmat). The unit conversions are the loader's:
+ * grey values x 255 (:644), app_rsv_convol x 65025 (:696), basisParam / 65025 (:555), support vectors (uchar)(255 v)
+ * (SvmClassifier.cpp:308), posterior vectors are {B, A} (ProbabilisticWvmClassifier.cpp:123-124).
+ * Where the reference would run on with uninitialised memory (a missing weight_hk%d or param_nonlin1) this loader fails.
+ * ---------------------------------------------------------------------------------------------- */
+#include "matfile.h"
+
+struct fdb_wvm_file {
+	fdb_wvm_desc desc;
+	std::vector<float> lin_thresholds, hk_weights, hierarchical_thresholds;
+	std::vector<double> app_rsv_convol, area_val;
+	std::vector<int32_t> area_cntval, area_cntrec;
+	std::vector<fdb_rect4> area_rec;
+};
+
+namespace {
+
+const MatArray* mat_var(const MatFile& f, const std::string& name) { return f.get(name); }
+
+/* the two dimensions the loaders read (mxGetDimensions()[0], [1]) */
+int dim0(const MatArray& a) { return a.dims.size() > 0 ? a.dims[0] : 0; }
+int dim1(const MatArray& a) { return a.dims.size() > 1 ? a.dims[1] : 0; }
+
+int load_posterior(const char* path, const char* var, bool required, double* A, double* B) {
+	MatFile f; std::string err;
+	if (!mat_read(path, &f, &err)) return fail(required ? FDB_ERR_INVALID_ARGUMENT : FDB_ERR_RUNTIME, "Unable to open the thresholds/logistic file: " + err);
+	const MatArray* p = mat_var(f, var);
+	*A = 0; *B = 0;
+	if (!p || dim1(*p) != 2 || p->real.size() < 2) {
+		if (required) return fail(FDB_ERR_RUNTIME, std::string("Unable to find the vector ") + var + " (of size 2). If you don't want probabilistic output, don't use a probabilistic classifier.");
+		return FDB_OK; /* ProbabilisticSvmClassifier.cpp:139-151: warning, A = B = 0 */
+	}
+	*B = p->real[0]; *A = p->real[1];
+	return FDB_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+int fdb_wvm_file_load(const char* classifier_path, const char* thresholds_path, fdb_wvm_file** out) {
+	if (!classifier_path || !thresholds_path || !out) return fail(FDB_ERR_INVALID_ARGUMENT, "null argument");
+	*out = nullptr;
+	MatFile mf; std::string err;
+	if (!mat_read(classifier_path, &mf, &err)) return fail(FDB_ERR_INVALID_ARGUMENT, "WvmClassifier: Could not open the provided classifier filename: " + err);
+	const MatArray* a = mat_var(mf, "num_hk");
+	if (!a || a->real.empty()) return fail(FDB_ERR_RUNTIME, "WvmClassifier: There is a no num_hk in the classifier file.");
+	const int nfilter = (int)a->real[0];
+	if (nfilter < 1 || nfilter > 4096) return fail(FDB_ERR_RUNTIME, "WvmClassifier: bad num_hk");
+	if (mat_var(mf, "wrvm")) return fail(FDB_ERR_RUNTIME, "WvmClassifier: Reading all wvm filters at once using the structure 'wrvm' is not (yet) supported.");
+	a = mat_var(mf, "support_hk1");
+	if (!a) return fail(FDB_ERR_RUNTIME, "WvmClassifier: Unable to find the matrix 'support_hk1' in the classifier file.");
+	if (a->dims.size() != 2) return fail(FDB_ERR_RUNTIME, "WvmClassifier: The matrix 'support_hk' in the classifier file should have 2 dimensions.");
+	std::unique_ptr<fdb_wvm_file> f(new fdb_wvm_file);
+	fdb_wvm_desc& d = f->desc;
+	d = fdb_wvm_desc();
+	d.filter_size_y = dim0(*a); d.filter_size_x = dim1(*a); /* :500-505 */
+	d.num_lin_filters = nfilter;
+	f->hk_weights.assign((size_t)nfilter * (nfilter + 1) / 2, 0.f);
+	for (int i = 0; i < nfilter; ++i) {
+		const std::string idx = std::to_string(i + 1);
+		a = mat_var(mf, "support_hk" + idx); /* the vectors themselves are not used by the rectangle evaluator */
+		if (!a) return fail(FDB_ERR_RUNTIME, "WvmClassifier: Unable to find the matrix 'support_hk" + idx + "' in the classifier file.");
+		if (a->dims.size() != 2) return fail(FDB_ERR_RUNTIME, "WvmClassifier: The matrix 'filter" + idx + "' in the classifier file should have 2 dimensions.");
+		a = mat_var(mf, "weight_hk" + idx);
+		if (!a) return fail(FDB_ERR_RUNTIME, "WvmClassifier: Unable to find the matrix 'weight_hk" + idx + "' (the reference would continue with uninitialised weights)");
+		if (dim1(*a) != i + 1 && dim0(*a) != i + 1)
+			return fail(FDB_ERR_RUNTIME, "WvmClassifier: The matrix weight_hk" + idx + " in the classifier file should have a dimensions 1x" + idx + " or " + idx + "x1");
+		for (int j = 0; j <= i; ++j) f->hk_weights[(size_t)i * (i + 1) / 2 + j] = (float)a->real[j];
+	}
+	a = mat_var(mf, "param_nonlin1_rvm");
+	if (!a) a = mat_var(mf, "param_nonlin1");
+	if (!a || a->real.size() < 3) return fail(FDB_ERR_RUNTIME, "WvmClassifier: neither 'param_nonlin1_rvm' nor 'param_nonlin1' found (the reference would continue with an uninitialised bias)");
+	const float bias = (float)a->real[0];
+	d.basis_param = (float)(a->real[2] / 65025.0);
+	f->lin_thresholds.assign((size_t)nfilter, bias);
+	a = mat_var(mf, "num_hk_wvm");
+	if (!a || a->real.empty()) return fail(FDB_ERR_RUNTIME, "WvmClassifier: Variable 'num_hk_wvm' not found in classifier file.");
+	d.num_filters_per_level = (int)a->real[0];
+	a = mat_var(mf, "num_lev_wvm");
+	if (!a || a->real.empty()) return fail(FDB_ERR_RUNTIME, "WvmClassifier: Variable 'num_lev_wvm' not found in classifier file.");
+	d.num_levels = (int)a->real[0];
+	a = mat_var(mf, "area");
+	if (!a || !a->is_struct()) return fail(FDB_ERR_RUNTIME, "WvmClassifier: 'area' not found (right *.mat/kernel?)");
+	const int nHK = dim1(*a);
+	if (nHK != nfilter || d.num_filters_per_level * d.num_levels != nHK)
+		return fail(FDB_ERR_RUNTIME, "WvmClassifier: Variable 'area' in the classifier file has wrong dimensions:" + std::to_string(nHK) + "(==" + std::to_string(nfilter) + ")");
+	for (int h = 0; h < nHK; ++h) {
+		const MatArray* mval = a->field(h, "val_u");
+		if (!mval) return fail(FDB_ERR_RUNTIME, "WvmClassifier: 'val_u' not found (WVM: 'val_u', else: 'val', right *.mat/kernel?)");
+		const int cntval = dim1(*mval);
+		const MatArray* mcnt = a->field(h, "cntrec_u");
+		const MatArray* mrec = a->field(h, "crec");
+		if (!mcnt || (int)mcnt->real.size() < cntval || (int)mval->real.size() < cntval) return fail(FDB_ERR_RUNTIME, "WvmClassifier: 'cntrec_u' missing or shorter than 'val_u'");
+		f->area_cntval.push_back(cntval);
+		for (int v = 0; v < cntval; ++v) {
+			f->area_val.push_back(mval->real[v] * 255.0F); /* :644 */
+			f->area_cntrec.push_back((int)mcnt->real[v]);
+		}
+		for (int v = 1; v < cntval; ++v) /* descriptor order (f, v, r), v >= 1: the evaluator never reads the rectangles of v == 0 (:277) */
+			for (int r = 0; r < (int)mcnt->real[v]; ++r) {
+				if (!mrec || !mrec->is_struct()) return fail(FDB_ERR_RUNTIME, "WvmClassifier: 'crec' not found in 'area'");
+				const int64_t e = (int64_t)r * cntval + v; /* :653 */
+				const MatArray* x1 = mrec->field(e, "x1"); const MatArray* y1 = mrec->field(e, "y1");
+				const MatArray* x2 = mrec->field(e, "x2"); const MatArray* y2 = mrec->field(e, "y2");
+				if (!x1 || !y1 || !x2 || !y2 || x1->real.empty() || y1->real.empty() || x2->real.empty() || y2->real.empty())
+					return fail(FDB_ERR_RUNTIME, "WvmClassifier: rectangle " + std::to_string(r) + " of grey value " + std::to_string(v) + " of filter " + std::to_string(h + 1) + " is missing in 'crec'");
+				fdb_rect4 rc;
+				rc.x1 = (int)x1->real[0]; rc.y1 = (int)y1->real[0]; rc.x2 = (int)x2->real[0]; rc.y2 = (int)y2->real[0];
+				f->area_rec.push_back(rc);
+			}
+	}
+	a = mat_var(mf, "app_rsv_convol");
+	if (!a) return fail(FDB_ERR_RUNTIME, "WvmClassifier: 'app_rsv_convol' not found.");
+	if (dim1(*a) != nfilter || (int)a->real.size() < nfilter) return fail(FDB_ERR_RUNTIME, "WvmClassifier: 'app_rsv_convol' not right dim:" + std::to_string(dim1(*a)) + " (==" + std::to_string(nfilter) + ")");
+	for (int h = 0; h < nfilter; ++h) f->app_rsv_convol.push_back(a->real[h] * 65025.0);
+
+	MatFile tf;
+	if (!mat_read(thresholds_path, &tf, &err)) return fail(FDB_ERR_RUNTIME, "WvmClassifier: Unable to open the thresholds file (wrong format?):" + err);
+	a = mat_var(tf, "hierar_thresh");
+	if (!a) return fail(FDB_ERR_RUNTIME, "WvmClassifier: Unable to find the matrix hierar_thresh in the thresholds file.");
+	for (int o = 0; o < dim1(*a) && o < (int)a->real.size(); ++o) f->hierarchical_thresholds.push_back((float)a->real[o]);
+	if ((int)f->hierarchical_thresholds.size() != nfilter)
+		return fail(FDB_ERR_RUNTIME, "WvmClassifier: Something seems to be wrong, hierarchicalThresholdsFromFile.size() != numLinFilters; " +
+				std::to_string(f->hierarchical_thresholds.size()) + "!=" + std::to_string(nfilter));
+	a = mat_var(tf, "posterior_wrvm");
+	if (!a) return fail(FDB_ERR_RUNTIME, "ProbabilisticWvmClassifier: Unable to find the vector posterior_wrvm. If you don't want probabilistic output, don't use a probabilistic classifier.");
+	if (dim1(*a) != 2 || a->real.size() < 2) return fail(FDB_ERR_RUNTIME, "ProbabilisticWvmClassifier: Size of vector posterior_wrvm !=2. If you don't want probabilistic output, don't use a probabilistic classifier.");
+	d.logistic_b = a->real[0]; d.logistic_a = a->real[1];
+
+	d.num_used_filters = 280;          /* :358; clamped to num_lin_filters by setNumUsedFilters (:151-158) */
+	d.limit_reliability_filter = 0.f;  /* :363; the cfg's "threshold" is applied by the caller (ProbabilisticWvmClassifier.cpp:82) */
+	d.lin_thresholds = f->lin_thresholds.data();
+	d.hk_weights = f->hk_weights.data();
+	d.app_rsv_convol = f->app_rsv_convol.data();
+	d.hierarchical_thresholds = f->hierarchical_thresholds.data();
+	d.area_cntval = f->area_cntval.data();
+	d.area_val = f->area_val.data();
+	d.area_cntrec = f->area_cntrec.data();
+	d.area_rec = f->area_rec.data();
+	*out = f.release();
+	return FDB_OK;
+}
+
+const fdb_wvm_desc* fdb_wvm_file_desc(const fdb_wvm_file* f) { return f ? &f->desc : nullptr; }
+void fdb_wvm_file_free(fdb_wvm_file* f) { delete f; }
+
+int fdb_svm_mat_load(const char* classifier_path, const char* logistic_path, fdb_svm_file** out) {
+	if (!classifier_path || !out) return fail(FDB_ERR_INVALID_ARGUMENT, "null argument");
+	*out = nullptr;
+	MatFile mf; std::string err;
+	if (!mat_read(classifier_path, &mf, &err)) return fail(FDB_ERR_INVALID_ARGUMENT, "SvmClassifier: Could not open the provided classifier filename: " + err);
+	const MatArray* a = mat_var(mf, "param_nonlin1");
+	if (!a || a->real.size() < 5) return fail(FDB_ERR_RUNTIME, "SvmClassifier: There is a no param_nonlin1 in the classifier file.");
+	std::unique_ptr<fdb_svm_file> f(new fdb_svm_file);
+	fdb_svm_desc& d = f->desc;
+	d = fdb_svm_desc();
+	d.bias = (float)a->real[0];
+	const int nonLinType = (int)a->real[1];
+	const float basisParam = (float)(a->real[2] / 65025.0);
+	if (nonLinType == 1) return fail(FDB_ERR_UNSUPPORTED, "SvmClassifier: the polynomial kernel is not evaluated on the GPU (RBF only)");
+	if (nonLinType != 2) return fail(FDB_ERR_RUNTIME, "SvmClassifier: Unsupported kernel type. Currently, only polynomial and RBF kernels are supported.");
+	d.kernel = FDB_KERNEL_RBF;
+	d.gamma = basisParam; /* RbfKernel(double gamma) receives the float */
+	a = mat_var(mf, "support_nonlin1");
+	if (!a) return fail(FDB_ERR_RUNTIME, "SvmClassifier: There is a nonlinear SVM in the file, but the matrix support_nonlin1 is lacking.");
+	if (a->dims.size() != 3) return fail(FDB_ERR_RUNTIME, "SvmClassifier: The matrix support_nonlin1 in the file should have 3 dimensions.");
+	const int h = a->dims[0], w = a->dims[1], nsv = a->dims[2];
+	f->sv_u8.resize((size_t)nsv * w * h);
+	size_t k = 0;
+	for (int sv = 0; sv < nsv; ++sv)
+		for (int x = 0; x < w; ++x)      /* column-major order (ML-convention), SvmClassifier.cpp:303-309 */
+			for (int y = 0; y < h; ++y)
+				f->sv_u8[(size_t)sv * w * h + (size_t)y * w + x] = static_cast<uint8_t>(255.0 * a->real[k++]);
+	a = mat_var(mf, "weight_nonlin1");
+	if (!a || (int)a->real.size() < nsv) return fail(FDB_ERR_RUNTIME, "SvmClassifier: There is a nonlinear SVM in the file but the matrix threshold_nonlin is lacking.");
+	for (int sv = 0; sv < nsv; ++sv) f->coefficients.push_back(static_cast<float>(a->real[sv]));
+	f->rows = h; f->cols = w; f->channels = 1; f->depth = 0;
+	d.num_sv = nsv; d.dim = w * h; d.sv_type = FDB_SV_U8;
+	d.support_vectors = f->sv_u8.data();
+	d.coefficients = f->coefficients.data();
+	d.threshold = 0.f; /* the cfg's "threshold" is applied by the caller (ProbabilisticSvmClassifier.cpp:100) */
+	if (logistic_path) {
+		const int s = load_posterior(logistic_path, "posterior_svm", false, &d.logistic_a, &d.logistic_b);
+		if (s) return s;
+	}
+	*out = f.release();
+	return FDB_OK;
+}
 
 } // extern "C"

@@ -343,3 +343,44 @@ class SdmLandmarkModel:
         capi.check(self.lib, self.lib.fdb_sdm_descriptors(self.h, frame.ctypes.data, frame.shape[1], frame.shape[1], frame.shape[0],
                                                           pts.ctypes.data, pts.shape[0], window_size_half, out.ctypes.data))
         return out
+
+
+def load_wvm_mat(classifier_path, thresholds_path):
+    """WvmClassifier::loadFromMatlab + the posterior_wrvm logistic through the library's MAT-file reader (fdb_wvm_file_load, host
+    only) -> synthetic.WvmModel holding copies of the descriptor arrays (evaluator units)."""
+    from .synthetic import WvmModel
+    lib = capi.load_library()
+    f = C.c_void_p()
+    capi.check(lib, lib.fdb_wvm_file_load(str(classifier_path).encode(), str(thresholds_path).encode(), C.byref(f)))
+    try:
+        d = lib.fdb_wvm_file_desc(f).contents
+        n = d.num_lin_filters
+        arr = lambda p, k, t: np.ctypeslib.as_array(p, shape=(k,)).astype(t, copy=True) if k else np.zeros(0, t)
+        cntval = arr(d.area_cntval, n, np.int32)
+        nv = int(cntval.sum())
+        cntrec = arr(d.area_cntrec, nv, np.int32)
+        first = np.concatenate([[0], np.cumsum(cntval)[:-1]]).astype(np.int64)
+        nrec = int(cntrec.sum() - cntrec[first].sum())
+        rec = np.ctypeslib.as_array(C.cast(d.area_rec, C.POINTER(C.c_int32)), shape=(nrec, 4)).copy() if nrec else np.zeros((0, 4), np.int32)
+        return WvmModel(d.filter_size_x, d.filter_size_y, d.num_filters_per_level, d.num_levels, d.basis_param,
+                        arr(d.lin_thresholds, n, np.float32), arr(d.hk_weights, n * (n + 1) // 2, np.float32),
+                        arr(d.app_rsv_convol, n, np.float64), arr(d.hierarchical_thresholds, n, np.float32), cntval,
+                        arr(d.area_val, nv, np.float64), cntrec, rec, limit_reliability_filter=d.limit_reliability_filter,
+                        num_used=d.num_used_filters, logistic_a=d.logistic_a, logistic_b=d.logistic_b)
+    finally:
+        lib.fdb_wvm_file_free(f)
+
+
+def load_svm_mat(classifier_path, logistic_path=None):
+    """SvmClassifier::loadFromMatlab + posterior_svm (fdb_svm_mat_load, host only) -> synthetic.SvmModel"""
+    from .synthetic import SvmModel
+    lib = capi.load_library()
+    f = C.c_void_p()
+    capi.check(lib, lib.fdb_svm_mat_load(str(classifier_path).encode(), None if logistic_path is None else str(logistic_path).encode(), C.byref(f)))
+    try:
+        d = lib.fdb_svm_file_desc(f).contents
+        sv = np.ctypeslib.as_array(C.cast(d.support_vectors, C.POINTER(C.c_uint8)), shape=(d.num_sv, d.dim)).copy()
+        coef = np.ctypeslib.as_array(d.coefficients, shape=(d.num_sv,)).copy()
+        return SvmModel(sv, coef, d.gamma, bias=d.bias, threshold=d.threshold, logistic_a=d.logistic_a, logistic_b=d.logistic_b)
+    finally:
+        lib.fdb_svm_file_free(f)

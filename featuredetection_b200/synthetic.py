@@ -362,3 +362,61 @@ def make_sdm(num_landmarks=68, num_steps=5, seed=500, sigma=1e-3):
         rng = np.random.default_rng(seed + s)
         regs.append((rng.standard_normal((L * SDM_DESC + 1, 2 * L)) * sigma).astype(np.float32))
     return SdmModel(mean, regs)
+
+
+# ------------------------------------------------------------------------------------------------
+# MATLAB model files (test support): the variable layout WvmClassifier::loadFromMatlab / SvmClassifier::loadFromMatlab read
+# ------------------------------------------------------------------------------------------------
+def _sio():
+    import scipy.io
+    return scipy.io
+
+
+def _cell(v):
+    return np.array([[float(v)]])
+
+
+def write_wvm_mat(m, classifier_path, thresholds_path, compress, rvm_param=True):
+    """inverse of the loader's conversions: grey values / 255, app_rsv_convol / 65025, basisParam * 65025"""
+    n = m.n
+    out = {"num_hk": _cell(n), "num_hk_wvm": _cell(m.per_level), "num_lev_wvm": _cell(m.levels)}
+    for i in range(n):
+        out["support_hk%d" % (i + 1)] = np.zeros((m.h, m.w))
+        w = m.hk_weights[i * (i + 1) // 2: i * (i + 1) // 2 + i + 1].astype(np.float64)
+        out["weight_hk%d" % (i + 1)] = w.reshape(1, -1) if i % 2 == 0 else w.reshape(-1, 1)   # both orientations are legal (:528)
+    out["param_nonlin1_rvm" if rvm_param else "param_nonlin1"] = np.array([[float(m.lin_thresholds[0]), 2.0, float(m.basis_param) * 65025.0, 0.0, 1.0]])
+    area = np.empty((1, n), dtype=[("val_u", "O"), ("cntrec_u", "O"), ("crec", "O")])
+    vo = ro = 0
+    for f in range(n):
+        cv = int(m.cntval[f])
+        cnt = m.cntrec[vo:vo + cv].astype(np.float64).copy()
+        cnt[0] = 0
+        maxrec = max(1, int(cnt.max()))
+        crec = np.empty((cv, maxrec), dtype=[("x1", "O"), ("y1", "O"), ("x2", "O"), ("y2", "O")])
+        for v in range(cv):
+            for r in range(maxrec):
+                crec[v, r] = (_cell(0), _cell(0), _cell(0), _cell(0))
+        for v in range(1, cv):
+            for r in range(int(cnt[v])):
+                x1, y1, x2, y2 = m.rec[ro]
+                crec[v, r] = (_cell(x1), _cell(y1), _cell(x2), _cell(y2))
+                ro += 1
+        area[0, f] = ((m.val[vo:vo + cv] / 255.0).reshape(1, -1), cnt.reshape(1, -1), crec)
+        vo += cv
+    out["area"] = area
+    out["app_rsv_convol"] = (m.app_rsv_convol / 65025.0).reshape(1, -1)
+    _sio().savemat(classifier_path, out, format="5", do_compression=compress, oned_as="row")
+    _sio().savemat(thresholds_path, {"hierar_thresh": m.thresholds.astype(np.float64).reshape(1, -1),
+                                  "posterior_wrvm": np.array([[m.logistic_b, m.logistic_a]]),
+                                  "posterior_svm": np.array([[-1.25, 0.5]])}, format="5", do_compression=compress)
+    return out
+
+
+def write_svm_mat(m, w, h, classifier_path, logistic_path=None, compress=True):
+    """u8 SvmModel -> support_nonlin1 [h][w][numSV] in grey / 255 units ((v + 0.5) / 255 survives the loader's truncation),
+    weight_nonlin1, param_nonlin1 = [bias, 2 (rbf), gamma * 65025, 0, 1]; logistic file: posterior_svm = [B, A]"""
+    sv = ((m.sv.astype(np.float64) + 0.5) / 255.0).reshape(-1, h, w).transpose(1, 2, 0)
+    _sio().savemat(classifier_path, {"param_nonlin1": np.array([[m.bias, 2.0, m.gamma * 65025.0, 0.0, 1.0]]), "support_nonlin1": sv,
+                                     "weight_nonlin1": m.coef.astype(np.float64).reshape(1, -1)}, format="5", do_compression=compress)
+    if logistic_path is not None:
+        _sio().savemat(logistic_path, {"posterior_svm": np.array([[m.logistic_b, m.logistic_a]])}, format="5", do_compression=compress)

@@ -379,6 +379,24 @@ FDB_API int fdb_svm_file_load(const char* path, fdb_svm_file** out);
 FDB_API const fdb_svm_desc* fdb_svm_file_desc(const fdb_svm_file* file);
 FDB_API void fdb_svm_file_free(fdb_svm_file* file);
 
+/* The MATLAB classifier files every ffpDetectApp .cfg names (classifierFile + thresholdsFile): Level-5 MAT-files read with
+ * the library's own reader (the reference uses MATLAB's libmat).
+ *   fdb_wvm_file_load  WvmClassifier::loadFromMatlab (WvmClassifier.cpp:348-770) + ProbabilisticWvmClassifier::
+ *                      loadSigmoidParamsFromMatlab (ProbabilisticWvmClassifier.cpp:95-137): variables num_hk, support_hk%d,
+ *                      weight_hk%d, param_nonlin1[_rvm], num_hk_wvm, num_lev_wvm, area{val_u, cntrec_u, crec{x1,y1,x2,y2}},
+ *                      app_rsv_convol; thresholds file: hierar_thresh, posterior_wrvm. Units converted as the loader does.
+ *   fdb_svm_mat_load   SvmClassifier::loadFromMatlab (SvmClassifier.cpp:240-335) + ProbabilisticSvmClassifier::
+ *                      loadSigmoidParamsFromMatlab (ProbabilisticSvmClassifier.cpp:114-162): param_nonlin1, support_nonlin1,
+ *                      weight_nonlin1; logistic file (may be NULL): posterior_svm. Returns the same object type as
+ *                      fdb_svm_file_load (use fdb_svm_file_desc / fdb_svm_file_free).
+ * The cfg's "threshold" values are applied afterwards with fdb_wvm_set_limit_reliability_filter / fdb_svm_set_threshold,
+ * as ProbabilisticWvmClassifier::load / ProbabilisticSvmClassifier::load do. */
+typedef struct fdb_wvm_file fdb_wvm_file;
+FDB_API int fdb_wvm_file_load(const char* classifier_path, const char* thresholds_path, fdb_wvm_file** out);
+FDB_API const fdb_wvm_desc* fdb_wvm_file_desc(const fdb_wvm_file* file);
+FDB_API void fdb_wvm_file_free(fdb_wvm_file* file);
+FDB_API int fdb_svm_mat_load(const char* classifier_path, const char* logistic_path, fdb_svm_file** out);
+
 /* ------------------------------------------------------------------------------------------
  * Feature spaces
  * ---------------------------------------------------------------------------------------- */

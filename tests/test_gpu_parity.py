@@ -348,3 +348,27 @@ def test_full_hd_frame(ctx, face_models):
         _, layers = fo.pyramid(frame, det_kw["incremental_scale_factor"], det_kw["min_scale_factor"], det_kw["max_scale_factor"])
         img = [im for i, _, im in layers if i == idx][0]
         assert np.array_equal(casc.pyramid_layer(frame, idx), img)
+
+
+def test_models_from_matlab_files(ctx, face_models, tmp_path):
+    """the whole cascade with both classifiers read from MATLAB files (fdb_wvm_file_load / fdb_svm_mat_load): detections
+    equal the oracle's for the same loaded numbers, and the cfg "threshold" applied afterwards behaves like the descriptor's"""
+    pytest.importorskip("scipy.io")
+    from featuredetection_b200.detector import load_wvm_mat, load_svm_mat
+    from oracle import fdoracle as fo
+    det_kw, wvm, svm = face_models
+    c, t, sp, lg = str(tmp_path / "wvm.mat"), str(tmp_path / "thr.mat"), str(tmp_path / "svm.mat"), str(tmp_path / "log.mat")
+    syn.write_wvm_mat(wvm, c, t, True)
+    syn.write_svm_mat(svm, 20, 20, sp, lg)
+    wl, sl = load_wvm_mat(c, t), load_svm_mat(sp, lg)
+    assert np.array_equal(sl.sv, svm.sv) and np.array_equal(sl.coef, svm.coef)
+    assert np.array_equal(wl.rec, wvm.rec) and np.array_equal(wl.hk_weights, wvm.hk_weights) and np.array_equal(wl.thresholds, wvm.thresholds)
+    casc = SlidingWindowCascade(ctx, det_kw, wl, sl)
+    casc.prepare(640, 480, 1)
+    frame = syn.synthetic_frame(3)
+    dets, dense = casc.detect(frame[None], stage=capi.FDB_STAGE_NMS, want_dense=True)
+    ref = fo.detect_frame(det_kw, fo.Wvm(wl), fo.Svm(sl), frame, stage=capi.FDB_STAGE_NMS)
+    assert np.array_equal(dense[0]["level"], ref["dense"]["level"])
+    assert np.allclose(dense[0]["fout"], ref["dense"]["fout"], rtol=0, atol=TOL)
+    assert list(dets["window"]) == list(ref["detections"]["window"])
+    assert np.allclose(dets["svm_distance"], ref["detections"]["svm_distance"], rtol=0, atol=TOL)
