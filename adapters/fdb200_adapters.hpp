@@ -53,11 +53,15 @@ private:
 	fdb_ctx* handle;
 };
 
-/* a 1-channel 8-bit view of the frame (GrayscaleFilter's copy branch, GrayscaleFilter.cpp:21-22) */
-inline const cv::Mat& requireGray(const cv::Mat& image) {
-	if (image.depth() != CV_8U || image.channels() != 1)
-		throw std::invalid_argument("fdb200: frames must be 8-bit 1-channel (convert BGR with cv::cvtColor first)");
-	return image;
+/* GrayscaleFilter::applyTo (GrayscaleFilter.cpp:18-24): 1-channel frames are taken as they are (copy branch), 3-channel frames go
+ * through cvtColor(CV_BGR2GRAY) - on the device (fdb_gray_from_bgr) */
+inline cv::Mat grayOf(fdb_ctx* ctx, const cv::Mat& image) {
+	if (image.depth() != CV_8U || (image.channels() != 1 && image.channels() != 3))
+		throw std::invalid_argument("fdb200: frames must be 8-bit with 1 (gray) or 3 (BGR) channels");
+	if (image.channels() == 1) return image;
+	cv::Mat gray(image.rows, image.cols, CV_8UC1);
+	check(fdb_gray_from_bgr(ctx, image.ptr<unsigned char>(0), (int64_t)image.step, image.cols, image.rows, 1, gray.ptr<unsigned char>(0)));
+	return gray;
 }
 
 /* classification::ProbabilisticWvmClassifier replacement (ProbabilisticWvmClassifier.cpp:42-54) */
@@ -155,12 +159,14 @@ public:
 
 	/* ---- detection::Detector ---- */
 	std::vector<std::shared_ptr<detection::ClassifiedPatch>> detect(const cv::Mat& image) {
-		prepareFor(requireGray(image));
-		return run(image, cv::Rect(), false);
+		const cv::Mat gray = grayOf(context->get(), image);
+		prepareFor(gray);
+		return run(gray, cv::Rect(), false);
 	}
 	std::vector<std::shared_ptr<detection::ClassifiedPatch>> detect(const cv::Mat& image, const cv::Rect& roi) {
-		prepareFor(requireGray(image));
-		return run(image, roi, true);
+		const cv::Mat gray = grayOf(context->get(), image);
+		prepareFor(gray);
+		return run(gray, roi, true);
 	}
 	std::vector<std::shared_ptr<detection::ClassifiedPatch>> detect(std::shared_ptr<imageprocessing::VersionedImage> image) {
 		return detect(image->getData());
@@ -169,8 +175,9 @@ public:
 	/* ---- imageprocessing::FeatureExtractor / PyramidFeatureExtractor ---- */
 	using imageprocessing::FeatureExtractor::update;
 	void update(std::shared_ptr<imageprocessing::VersionedImage> image) {
-		prepareFor(requireGray(image->getData()));
-		current = image->getData().clone();
+		const cv::Mat gray = grayOf(context->get(), image->getData());
+		prepareFor(gray);
+		current = gray.clone();
 		patches.clear();
 	}
 	std::shared_ptr<imageprocessing::Patch> extract(int x, int y, int w, int h) const {

@@ -76,6 +76,9 @@ struct fdb_detector {
 	fdb_svm* svm = nullptr;
 	Plan plan;
 	bool prepared = false;
+	uint8_t* d_bgr = nullptr;      /* fdb_detect_batch_bgr staging: interleaved frames and their gray conversion */
+	uint8_t* d_gray = nullptr;
+	int64_t bgr_cap_px = 0;
 	int max_batch = 0, chunk = 0, n_slots = 0;
 	int cand_cap = 0, items_cap = 0;
 	std::vector<void*> owned, owned_host;
@@ -528,6 +531,8 @@ void fdb_detector_destroy(fdb_detector* det) {
 	cudaSetDevice(det->ctx->device);
 	cudaStreamSynchronize(det->ctx->stream);
 	release(det);
+	if (det->d_bgr) cudaFree(det->d_bgr);
+	if (det->d_gray) cudaFree(det->d_gray);
 	delete det;
 }
 
@@ -767,6 +772,56 @@ int fdb_detect_batch(fdb_detector* det, const uint8_t* frames_host, int64_t pitc
 int fdb_detect_batch_device(fdb_detector* det, const uint8_t* frames_device, int32_t n_frames, int32_t stage,
 		fdb_window_score* dense_out_device, fdb_detection* detections_out, int64_t det_cap, int64_t* n_detections) {
 	return detect_impl(det, frames_device, true, 0, n_frames, stage, dense_out_device, true, detections_out, det_cap, n_detections);
+}
+
+/* GrayscaleFilter::applyTo on the device for n frames of interleaved 8-bit BGR in host memory -> d_gray (contiguous) */
+static int upload_bgr_as_gray(cudaStream_t st, const uint8_t* bgr_host, int64_t pitch, int W, int H, int n, uint8_t* d_bgr, uint8_t* d_gray) {
+	if (pitch == 3ll * W) CUDA_TRY(cudaMemcpyAsync(d_bgr, bgr_host, (size_t)3 * W * H * n, cudaMemcpyHostToDevice, st));
+	else CUDA_TRY(cudaMemcpy2DAsync(d_bgr, (size_t)3 * W, bgr_host, (size_t)pitch, (size_t)3 * W, (size_t)H * n, cudaMemcpyHostToDevice, st));
+	launch_bgr2gray(st, d_bgr, d_gray, (int64_t)W * H * n);
+	CUDA_TRY(cudaGetLastError());
+	return FDB_OK;
+}
+
+int fdb_gray_from_bgr(fdb_ctx* ctx, const uint8_t* bgr_host, int64_t pitch, int32_t W, int32_t H, int32_t n_frames, uint8_t* gray_host) {
+	int s = check_ctx(ctx); if (s) return s;
+	if (!bgr_host || !gray_host || W < 1 || H < 1 || n_frames < 0 || pitch < 3ll * W) return fail(FDB_ERR_INVALID_ARGUMENT, "bad BGR frame batch");
+	if (n_frames == 0) return FDB_OK;
+	const size_t px = (size_t)W * H * n_frames;
+	uint8_t* d = nullptr;
+	CUDA_TRY(cudaMalloc((void**)&d, 4 * px + 16));
+	s = upload_bgr_as_gray(ctx->stream, bgr_host, pitch, W, H, n_frames, d + ((px + 15) & ~(size_t)15), d);
+	ctx->launches += 1;
+	cudaError_t e = s ? cudaSuccess : cudaMemcpyAsync(gray_host, d, px, cudaMemcpyDeviceToHost, ctx->stream);
+	if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+	cudaFree(d);
+	if (s) return s;
+	if (e != cudaSuccess) return fail(FDB_ERR_CUDA, std::string("fdb_gray_from_bgr: ") + cudaGetErrorString(e));
+	return FDB_OK;
+}
+
+int fdb_detect_batch_bgr(fdb_detector* det, const uint8_t* bgr_host, int64_t pitch, int32_t n_frames, int32_t stage,
+		fdb_window_score* dense_out, fdb_detection* detections_out, int64_t det_cap, int64_t* n_detections) {
+	if (!det || !det->prepared) return fail(FDB_ERR_INVALID_ARGUMENT, "detector not prepared (call fdb_detector_prepare)");
+	int s = check_ctx(det->ctx); if (s) return s;
+	const int W = det->plan.width, H = det->plan.height;
+	if (n_frames < 0 || (n_frames > 0 && !bgr_host) || pitch < 3ll * W) return fail(FDB_ERR_INVALID_ARGUMENT, "bad BGR frame batch");
+	const int64_t px = (int64_t)W * H * n_frames;
+	if (px > det->bgr_cap_px) {
+		cudaStreamSynchronize(det->ctx->stream);
+		if (det->d_bgr) cudaFree(det->d_bgr);
+		if (det->d_gray) cudaFree(det->d_gray);
+		det->d_bgr = det->d_gray = nullptr; det->bgr_cap_px = 0;
+		CUDA_TRY(cudaMalloc((void**)&det->d_bgr, (size_t)3 * px));
+		CUDA_TRY(cudaMalloc((void**)&det->d_gray, (size_t)px));
+		det->bgr_cap_px = px;
+	}
+	if (n_frames > 0) {
+		s = upload_bgr_as_gray(det->ctx->stream, bgr_host, pitch, W, H, n_frames, det->d_bgr, det->d_gray); if (s) return s;
+		det->ctx->launches += 1;
+		CUDA_TRY(cudaStreamSynchronize(det->ctx->stream)); /* the pipeline slots run on their own streams */
+	}
+	return detect_impl(det, det->d_gray, true, 0, n_frames, stage, dense_out, false, detections_out, det_cap, n_detections);
 }
 
 int fdb_detect_enqueue_device(fdb_detector* det, const uint8_t* frames_device, int32_t n_frames, fdb_window_score* dense_out_device) {

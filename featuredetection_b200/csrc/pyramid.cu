@@ -203,6 +203,47 @@ __global__ void __launch_bounds__(PD_BX * PD_BY) pyrdown_kernel(const uint8_t* _
 }
 
 /* ---------------------------------------------------------------------------------------------
+ * GrayscaleFilter::applyTo (GrayscaleFilter.cpp:18-24): cv::cvtColor(CV_BGR2GRAY) on 8-bit frames. OpenCV 2.4.3 (the pinned
+ * version; imgproc/src/color.cpp RGB2Gray<uchar>, yuv_shift = 14, B2Y = 1868, G2Y = 9617, R2Y = 4899):
+ *     gray = (1868 B + 9617 G + 4899 R + 8192) >> 14
+ * Pure streaming: 3 bytes read + 1 byte written per pixel, so this is the one kernel of the path that sits on the HBM roofline.
+ * A thread converts 16 pixels: three 16-byte loads (48 interleaved bytes), one 16-byte store; rows are handled as a flat
+ * array when pitch == 3 W (always inside the library), with a scalar tail.
+ * ------------------------------------------------------------------------------------------- */
+__device__ __forceinline__ uint32_t gray_of(uint32_t b, uint32_t g, uint32_t r) { return (1868u * b + 9617u * g + 4899u * r + 8192u) >> 14; }
+
+__global__ void __launch_bounds__(256) bgr2gray_kernel(const uint8_t* __restrict__ bgr, uint8_t* __restrict__ gray, int64_t n_px) {
+	const int64_t groups = n_px >> 4;
+	const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+	for (int64_t gidx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; gidx < groups; gidx += stride) {
+		const uint4* src = reinterpret_cast<const uint4*>(bgr) + 3 * gidx;
+		const uint4 a = __ldcs(src), b = __ldcs(src + 1), c = __ldcs(src + 2);
+		const uint32_t w[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
+		uint32_t out[4];
+#pragma unroll
+		for (int q = 0; q < 4; ++q) { /* 4 pixels = 12 bytes = words 3q .. 3q + 2 */
+			const uint32_t w0 = w[3 * q], w1 = w[3 * q + 1], w2 = w[3 * q + 2];
+			const uint32_t p0 = gray_of(w0 & 255u, (w0 >> 8) & 255u, (w0 >> 16) & 255u);
+			const uint32_t p1 = gray_of(w0 >> 24, w1 & 255u, (w1 >> 8) & 255u);
+			const uint32_t p2 = gray_of((w1 >> 16) & 255u, w1 >> 24, w2 & 255u);
+			const uint32_t p3 = gray_of((w2 >> 8) & 255u, (w2 >> 16) & 255u, w2 >> 24);
+			out[q] = p0 | (p1 << 8) | (p2 << 16) | (p3 << 24);
+		}
+		__stcs(reinterpret_cast<uint4*>(gray) + gidx, make_uint4(out[0], out[1], out[2], out[3]));
+	}
+	if (blockIdx.x == 0) /* tail: fewer than 16 pixels */
+		for (int64_t i = (groups << 4) + threadIdx.x; i < n_px; i += blockDim.x) gray[i] = (uint8_t)gray_of(bgr[3 * i], bgr[3 * i + 1], bgr[3 * i + 2]);
+}
+
+void launch_bgr2gray(cudaStream_t st, const uint8_t* bgr, uint8_t* gray, int64_t n_px) {
+	if (n_px <= 0) return;
+	const int64_t groups = n_px >> 4;
+	const int64_t want = (groups + 255) / 256;
+	const unsigned grid = (unsigned)(want < 1 ? 1 : (want > 148 * 16 ? 148 * 16 : want)); /* grid-stride over 148 SMs x 16 resident CTAs */
+	bgr2gray_kernel<<<grid, 256, 0, st>>>(bgr, gray, n_px);
+}
+
+/* ---------------------------------------------------------------------------------------------
  * launchers
  * ------------------------------------------------------------------------------------------- */
 void launch_resize(cudaStream_t st, const uint8_t* frames, int W, int H, int n_frames, uint8_t* arena,

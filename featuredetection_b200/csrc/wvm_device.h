@@ -111,6 +111,7 @@ int resize_tiles(int dst_w, int dst_h);
 void launch_pyrdown(cudaStream_t st, const uint8_t* frames, int W, int H, int n_frames, uint8_t* arena,
 		int64_t arena_stride, const DownJob* jobs_dev, int n_jobs, int max_tiles);
 int pyrdown_tiles(int dst_w, int dst_h);
+void launch_bgr2gray(cudaStream_t st, const uint8_t* bgr, uint8_t* gray, int64_t n_px);
 
 /* one SVM work item: a window of a frame (geometry resolved on the host) */
 struct SvmItem {

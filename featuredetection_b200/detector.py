@@ -67,6 +67,18 @@ class Context:
         return ms.value
 
 
+def gray_from_bgr(ctx, frames_bgr, pitch=None):
+    """GrayscaleFilter::applyTo on [n, H, W, 3] interleaved BGR frames (fdb_gray_from_bgr) -> [n, H, W] u8"""
+    frames = np.ascontiguousarray(frames_bgr, np.uint8)
+    if frames.ndim == 3:
+        frames = frames[None]
+    n, H, W, ch = frames.shape
+    assert ch == 3
+    out = np.empty((n, H, W), np.uint8)
+    capi.check(ctx.lib, ctx.lib.fdb_gray_from_bgr(ctx.h, frames.ctypes.data, pitch or 3 * W, W, H, n, out.ctypes.data))
+    return out
+
+
 class ProbabilisticWvmClassifier:
     """classification::ProbabilisticWvmClassifier (ProbabilisticWvmClassifier.cpp:42-54) on the GPU."""
 
@@ -188,6 +200,23 @@ class SlidingWindowCascade:
         cnt = C.c_int64()
         capi.check(self.ctx.lib, self.ctx.lib.fdb_detect_batch(
             self.h, frames.ctypes.data, W, n, stage, dense.ctypes.data if want_dense else None,
+            dets.ctypes.data, det_cap, C.byref(cnt)))
+        out = dets[:cnt.value].copy()
+        return (out, dense) if want_dense else out
+
+    def detect_bgr(self, frames_bgr, stage=capi.FDB_STAGE_NMS, want_dense=False, det_cap=None):
+        """frames [n, H, W, 3] u8 interleaved BGR (host): GrayscaleFilter's cvtColor branch runs on the device first"""
+        frames = np.ascontiguousarray(frames_bgr, np.uint8)
+        if frames.ndim == 3:
+            frames = frames[None]
+        n, H, W, ch = frames.shape
+        assert ch == 3 and (W, H) == (self.width, self.height)
+        det_cap = det_cap or max(1024, n * 4096)
+        dets = np.zeros(det_cap, DETECTION_DTYPE)
+        dense = np.zeros((n, self.windows_per_frame), SCORE_DTYPE) if want_dense else None
+        cnt = C.c_int64()
+        capi.check(self.ctx.lib, self.ctx.lib.fdb_detect_batch_bgr(
+            self.h, frames.ctypes.data, 3 * W, n, stage, dense.ctypes.data if want_dense else None,
             dets.ctypes.data, det_cap, C.byref(cnt)))
         out = dets[:cnt.value].copy()
         return (out, dense) if want_dense else out

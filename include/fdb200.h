@@ -429,6 +429,16 @@ FDB_API int fdb_detect_single(fdb_detector* det, const uint8_t* frames_host, int
  * [0] windows, [1] wvm positives, [2] after OE, [3] svm positives, [4] after NMS. */
 FDB_API int fdb_detector_last_counts(fdb_detector* det, int64_t counts[5]);
 
+/* GrayscaleFilter::applyTo (GrayscaleFilter.cpp:18-24) for colour input: cv::cvtColor(CV_BGR2GRAY) of n_frames interleaved
+ * 8-bit BGR frames (row pitch >= 3 * width bytes, frame k at k * pitch * height), OpenCV 2.4.3 arithmetic
+ * (1868 B + 9617 G + 4899 R + 8192) >> 14. fdb_gray_from_bgr returns the gray frames (host, width * height bytes each);
+ * fdb_detect_batch_bgr is fdb_detect_batch on such frames (the conversion runs on the device in front of the pyramid).
+ * 1-channel frames take the filter's copy branch: pass them to fdb_detect_batch directly. */
+FDB_API int fdb_gray_from_bgr(fdb_ctx* ctx, const uint8_t* bgr_host, int64_t pitch, int32_t width, int32_t height,
+		int32_t n_frames, uint8_t* gray_host);
+FDB_API int fdb_detect_batch_bgr(fdb_detector* det, const uint8_t* bgr_host, int64_t pitch, int32_t n_frames, int32_t stage,
+		fdb_window_score* dense_out, fdb_detection* detections_out, int64_t det_cap, int64_t* n_detections);
+
 /* ------------------------------------------------------------------------------------------
  * Supervised-descent landmark regressor (libSupervisedDescent; BASELINE configs[4])
  * ---------------------------------------------------------------------------------------- */

@@ -815,3 +815,16 @@ int64_t fdo_detect_frame_ex(const fdb_detector_desc* desc, const fdo_wvm* wvm, c
 	fdo_pyramid_free(pyr);
 	return overflow ? -1 : n;
 }
+
+/* GrayscaleFilter::applyTo (GrayscaleFilter.cpp:18-24), 3-channel branch: cv::cvtColor(image, filtered, CV_BGR2GRAY).
+ * OpenCV 2.4.3 (pinned by the reference's CMake; imgproc/src/color.cpp, RGB2Gray<uchar>: yuv_shift 14, B2Y 1868, G2Y 9617,
+ * R2Y 4899, rounding offset 1 << 13 folded into the R table). PARITY UNPINNED: OpenCV 2.4.3 is not installable here and
+ * cv2 4.13 uses 15-bit coefficients (differs by 1 in ~0.3 % of the pixels); tests/test_oracle_golden.py checks the formula
+ * against that bound only. */
+void fdo_bgr_to_gray(const uint8_t* bgr, int width, int height, int pitch, uint8_t* gray) {
+	for (int y = 0; y < height; ++y) {
+		const uint8_t* s = bgr + (size_t)y * pitch;
+		uint8_t* d = gray + (size_t)y * width;
+		for (int x = 0; x < width; ++x, s += 3) d[x] = (uint8_t)((s[0] * 1868 + s[1] * 9617 + s[2] * 4899 + (1 << 13)) >> 14);
+	}
+}

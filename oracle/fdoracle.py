@@ -420,6 +420,18 @@ def whitening(patch, alpha=1.0, cutoff=0.390625):
     return out, real
 
 
+def bgr_to_gray(bgr):
+    """GrayscaleFilter::applyTo on one [H, W, 3] BGR frame (OpenCV 2.4.3 cvtColor arithmetic)"""
+    bgr = np.ascontiguousarray(bgr, np.uint8)
+    h, w, _ = bgr.shape
+    out = np.empty((h, w), np.uint8)
+    L = lib()
+    L.fdo_bgr_to_gray.restype = None
+    L.fdo_bgr_to_gray.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    L.fdo_bgr_to_gray(bgr.ctypes.data, w, h, 3 * w, out.ctypes.data)
+    return out
+
+
 def resize_linear_f32(img, dw, dh):
     img = np.ascontiguousarray(img, np.float32)
     out = np.empty((dh, dw), np.float32)

@@ -372,3 +372,32 @@ def test_models_from_matlab_files(ctx, face_models, tmp_path):
     assert np.allclose(dense[0]["fout"], ref["dense"]["fout"], rtol=0, atol=TOL)
     assert list(dets["window"]) == list(ref["detections"]["window"])
     assert np.allclose(dets["svm_distance"], ref["detections"]["svm_distance"], rtol=0, atol=TOL)
+
+
+def test_bgr_frames(ctx, face_models):
+    """GrayscaleFilter's cvtColor branch on the device: gray frames bit-exact to the oracle's 2.4.3 formula (odd sizes, pitch,
+    tails), and the cascade on BGR frames equals the cascade on the converted frames"""
+    from featuredetection_b200.detector import gray_from_bgr
+    from oracle import fdoracle as fo
+    rng = np.random.default_rng(21)
+    for (h, w, n) in ((480, 640, 3), (61, 97, 2), (5, 3, 1), (33, 1, 1)):
+        bgr = rng.integers(0, 256, (n, h, w, 3), dtype=np.uint8)
+        got = gray_from_bgr(ctx, bgr)
+        for k in range(n):
+            assert np.array_equal(got[k], fo.bgr_to_gray(bgr[k])), (h, w, k)
+    padded = rng.integers(0, 256, (2, 50, 3 * 70 + 10), dtype=np.uint8)          # row pitch > 3 W
+    view = np.stack([padded[k][:, :210].reshape(50, 70, 3) for k in range(2)])
+    lib = ctx.lib
+    out = np.empty((2, 50, 70), np.uint8)
+    capi.check(lib, lib.fdb_gray_from_bgr(ctx.h, padded.ctypes.data, padded.shape[2], 70, 50, 2, out.ctypes.data))
+    assert np.array_equal(out, np.stack([fo.bgr_to_gray(v) for v in view]))
+    det_kw, wvm, svm = face_models
+    casc = SlidingWindowCascade(ctx, det_kw, wvm, svm)
+    casc.prepare(640, 480, 2)
+    gray = syn.synthetic_frames(4, 2)
+    colour = np.stack([np.clip(gray.astype(int) + d, 0, 255).astype(np.uint8) for d in (-9, 3, 5)], axis=-1)  # B, G, R
+    conv = gray_from_bgr(ctx, colour)
+    d1, dense1 = casc.detect_bgr(colour, want_dense=True)
+    d2, dense2 = casc.detect(conv, want_dense=True)
+    assert np.array_equal(dense1["level"], dense2["level"]) and np.array_equal(dense1["fout"], dense2["fout"])
+    assert np.array_equal(d1["window"], d2["window"]) and np.array_equal(d1["svm_distance"], d2["svm_distance"])

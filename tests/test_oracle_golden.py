@@ -176,3 +176,20 @@ def test_svm_text_container_roundtrip(fo, tmp_path):
     assert np.allclose(coef, model.coef, rtol=1e-5, atol=1e-7) and np.allclose(sv, model.sv, rtol=1e-5, atol=1e-7)
     lib.fdb_svm_file_free(h)
     assert lib.fdb_svm_file_load(b"/nonexistent/file", C.byref(h)) == 2
+
+
+def test_bgr_to_gray_formula(built):
+    """GrayscaleFilter's cvtColor branch: the OpenCV 2.4.3 fixed-point formula; cv2 4.13 (15-bit coefficients) may differ by 1
+    in a fraction of a percent of the pixels - the only executable check available for this primitive (parity unpinned)"""
+    from oracle import fdoracle as fo
+    rng = np.random.default_rng(77)
+    bgr = rng.integers(0, 256, (97, 131, 3), dtype=np.uint8)
+    got = fo.bgr_to_gray(bgr)
+    b, g, r = (bgr[..., i].astype(np.int64) for i in range(3))
+    assert np.array_equal(got, ((1868 * b + 9617 * g + 4899 * r + 8192) >> 14).astype(np.uint8))
+    for v in (0, 255):  # the coefficients sum to 2^14: grey stays grey
+        assert np.all(fo.bgr_to_gray(np.full((4, 5, 3), v, np.uint8)) == v)
+    cv2 = pytest.importorskip("cv2")
+    ref = cv2.cvtColor(bgr, cv2.COLOR_BGR2GRAY)
+    diff = np.abs(got.astype(int) - ref.astype(int))
+    assert diff.max() <= 1 and (diff != 0).mean() < 0.01
