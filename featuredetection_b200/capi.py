@@ -129,6 +129,7 @@ SYMBOLS = [
     ("fdb_svm_destroy", None, [C.c_void_p]),
     ("fdb_svm_set_threshold", C.c_int, [C.c_void_p, C.c_float]),
     ("fdb_svm_get_probability", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("fdb_svm_has_dense", C.c_int, [C.c_void_p]),
     ("fdb_detector_create", C.c_int, [C.c_void_p, _P(DetectorDesc), C.c_void_p, C.c_void_p, _P(C.c_void_p)]),
     ("fdb_detector_destroy", None, [C.c_void_p]),
     ("fdb_detector_prepare", C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32]),
@@ -159,6 +160,8 @@ SYMBOLS = [
     ("fdb_detector_set_feature", C.c_int, [C.c_void_p, _P(FeatureDesc)]),
     ("fdb_extract_features", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]),
     ("fdb_detect_single", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, _P(C.c_int64)]),
+    ("fdb_detect_single_device", C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, _P(C.c_int64)]),
+    ("fdb_detector_single_dense", C.c_int, [C.c_void_p]),
     ("fdb_sdm_create", C.c_int, [C.c_void_p, _P(SdmDesc), _P(C.c_void_p)]),
     ("fdb_sdm_destroy", None, [C.c_void_p]),
     ("fdb_sdm_num_landmarks", C.c_int32, [C.c_void_p]),

@@ -74,7 +74,7 @@ int fdb_ctx_create(int device, fdb_ctx** out) {
 	c->device = device;
 	CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
 	for (cudaEvent_t& e : c->ev) CUDA_TRY(cudaEventCreate(&e));
-	if (wvm_configure() != 0 || svm_configure() != 0 || strip_configure_all() != 0 || strip_mma_configure_all() != 0 || feature_configure() != 0) {
+	if (wvm_configure() != 0 || svm_configure() != 0 || svm_dense_configure() != 0 || strip_configure_all() != 0 || strip_mma_configure_all() != 0 || feature_configure() != 0) {
 		cudaStreamDestroy(c->stream); delete c;
 		return fail(FDB_ERR_CUDA, "cudaFuncSetAttribute failed: libfdb200 kernels not loadable on this device");
 	}
@@ -359,6 +359,20 @@ int fdb_svm_create(fdb_ctx* ctx, const fdb_svm_desc* d, fdb_svm** out) {
 			uint32_t* up;
 			s = upload(tr.data(), tr.size(), &up, m->owned);
 			dv.sv_words = up;
+			/* tensor-core form for whole-batch evaluation (svm_dense.cu) */
+			SvmDenseHost dh;
+			if (!s && svm_dense_build(sv, d->coefficients, d->num_sv, d->dim, d->gamma, d->bias, d->threshold, &dh)) {
+				uint8_t* bb; int* sq; double* cf; double* tb;
+				s = upload(dh.b_blocks.data(), dh.b_blocks.size(), &bb, m->owned);
+				if (!s) s = upload(dh.ssq.data(), dh.ssq.size(), &sq, m->owned);
+				if (!s) s = upload(dh.coef.data(), dh.coef.size(), &cf, m->owned);
+				if (!s) s = upload(dh.tab.data(), dh.tab.size(), &tb, m->owned);
+				if (!s) {
+					m->dense = dh.dev;
+					m->dense.b_blocks = bb; m->dense.ssq = sq; m->dense.coef = cf; m->dense.exp_tab = tb;
+					m->has_dense = true;
+				}
+			}
 		} else {
 			const float* sv = (const float*)d->support_vectors;
 			std::vector<float> tr((size_t)d->dim * d->num_sv);
@@ -385,8 +399,11 @@ void fdb_svm_destroy(fdb_svm* m) {
 int fdb_svm_set_threshold(fdb_svm* m, float t) {
 	if (!m) return fail(FDB_ERR_INVALID_ARGUMENT, "null svm");
 	m->dev.threshold = t;
+	m->dense.threshold = t;
 	return FDB_OK;
 }
+
+int fdb_svm_has_dense(const fdb_svm* m) { return m && m->has_dense && fdb::svm_dense_enabled() ? 1 : 0; }
 
 int fdb_svm_get_probability(fdb_svm* m, const void* vectors, int64_t n, double* dist_out, double* prob_out, uint8_t* pos_out) {
 	if (!m) return fail(FDB_ERR_INVALID_ARGUMENT, "null svm");
@@ -404,7 +421,10 @@ int fdb_svm_get_probability(fdb_svm* m, const void* vectors, int64_t n, double* 
 	std::vector<double> host((size_t)n);
 	cudaError_t e = cudaMemcpyAsync(d_v, vectors, bytes, cudaMemcpyHostToDevice, st);
 	if (e == cudaSuccess) {
-		launch_svm_vectors(st, m->dev, d_v, (int)n, d_d);
+		if (m->has_dense && svm_dense_enabled() && n >= FDB_SVM_DENSE_MIN_VECTORS)
+			launch_svm_dense_vectors(st, m->dense, d_v, n, d_d);
+		else
+			launch_svm_vectors(st, m->dev, d_v, (int)n, d_d);
 		m->ctx->launches++;
 		e = cudaGetLastError();
 	}

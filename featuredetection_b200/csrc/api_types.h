@@ -38,6 +38,8 @@ struct fdb_wvm {
 struct fdb_svm {
 	fdb_ctx* ctx = nullptr;
 	fdb::DevSvm dev{};
+	bool has_dense = false;     /* tensor-core form available (u8 support vectors, see svm_dense.cu) */
+	fdb::DevSvmDense dense{};
 	std::vector<void*> owned;
 	double logistic_a = 0, logistic_b = 0;
 };

@@ -99,6 +99,9 @@ struct fdb_detector {
 	int64_t farena_bytes = 0;         /* per frame */
 	SvmItem* d_all_items = nullptr;   /* every window of a frame as an SVM item (`single` detector without a WVM) */
 	double* d_all_dist = nullptr; double* h_all_dist = nullptr;
+	/* `single` detector on the tensor cores (svm_dense.cu): distances of a chunk, positives list */
+	double* d_sd_dist = nullptr; int* d_sd_count = nullptr; DensePositive* d_sd_pos = nullptr;
+	int* h_sd_count = nullptr; DensePositive* h_sd_pos = nullptr; int sd_pos_cap = 0;
 	int64_t counts[5] = {0, 0, 0, 0, 0};
 };
 
@@ -355,12 +358,18 @@ void release(fdb_detector* det) {
 	det->d_down.clear(); det->n_down.clear(); det->max_down_px.clear();
 }
 
+bool single_dense_usable(const fdb_detector* det);
+int detect_single_dense(fdb_detector* det, const uint8_t* frames, bool frames_on_device, int64_t pitch, int32_t n_frames,
+		double* distance_out, bool distance_on_device, fdb_detection* dets_out, int64_t det_cap, int64_t* n_dets);
+
 /* `single` detector of ffpDetectApp.cpp:427-500 with a psvm classifier: SlidingWindowDetector::detect
  * (SlidingWindowDetector.cpp:40-98) where the extractor is a FilteringPyramidFeatureExtractor (the feature space)
  * and the classifier a ProbabilisticSvmClassifier - every window is classified, positives are returned in
  * canonical order with the SVM probability. distance_out: NULL or host [n_frames * windows] distances. */
 int detect_single(fdb_detector* det, const uint8_t* frames, bool frames_on_device, int64_t pitch, int32_t n_frames,
 		double* distance_out, fdb_detection* dets_out, int64_t det_cap, int64_t* n_dets) {
+	if (single_dense_usable(det))
+		return detect_single_dense(det, frames, frames_on_device, pitch, n_frames, distance_out, false, dets_out, det_cap, n_dets);
 	const Plan& plan = det->plan;
 	const int W = plan.width, H = plan.height;
 	cudaStream_t st = det->ctx->stream;
@@ -397,6 +406,75 @@ int detect_single(fdb_detector* det, const uint8_t* frames, bool frames_on_devic
 			d.wvm_probability = std::numeric_limits<double>::quiet_NaN();
 			d.svm_distance = dist;
 			d.svm_probability = svm_probability(det->svm->logistic_a, det->svm->logistic_b, dist);
+			d.probability = d.svm_probability;
+			d.positive = 1;
+			dets.push_back(d);
+		}
+	}
+	det->counts[1] = det->counts[2] = det->counts[3] = det->counts[4] = (int64_t)dets.size();
+	return copy_out(dets, dets_out, det_cap, n_dets);
+}
+
+/* the same detector when the SVM has a tensor-core form and works on HistEq64 patches: whole chunks of frames go
+ * through pyramid kernels + ONE svm_dense_kernel launch (every window x every support vector as an u8 matrix product);
+ * only the positives (and, if asked for, the distances) come back.
+ * distance_out: NULL, host [n_frames * windows] or - distance_on_device - device memory of that size. */
+bool single_dense_usable(const fdb_detector* det) {
+	return !det->wvm && det->svm && det->svm->has_dense && svm_dense_enabled() && det->d_sd_dist
+			&& (!det->has_feature || det->feat.kind == FDB_FEATURE_HQ64)
+			&& det->svm->dense.dim == det->desc.patch_width * det->desc.patch_height;
+}
+
+int detect_single_dense(fdb_detector* det, const uint8_t* frames, bool frames_on_device, int64_t pitch, int32_t n_frames,
+		double* distance_out, bool distance_on_device, fdb_detection* dets_out, int64_t det_cap, int64_t* n_dets) {
+	const Plan& plan = det->plan;
+	const int W = plan.width, H = plan.height;
+	fdb_ctx* c = det->ctx;
+	cudaStream_t st = c->stream;
+	Slot& sl = det->slots[0];
+	std::fill(det->counts, det->counts + 5, 0);
+	det->counts[0] = plan.windows * n_frames;
+	std::vector<fdb_detection> dets;
+	const int64_t nwin = plan.windows;
+	for (int base = 0; base < n_frames; base += det->chunk) {
+		const int n = std::min(det->chunk, n_frames - base);
+		if (frames_on_device) sl.frames_dev = frames + (int64_t)base * W * H;
+		else {
+			CUDA_TRY(cudaMemcpy2DAsync(sl.d_frames, (size_t)W, frames + (int64_t)base * pitch * H, (size_t)pitch, (size_t)W,
+					(size_t)H * n, cudaMemcpyHostToDevice, st));
+			sl.frames_dev = sl.d_frames;
+		}
+		sl.base = base; sl.n = n;
+		CUDA_TRY(cudaMemsetAsync(det->d_sd_count, 0, sizeof(int), st));
+		int s = enqueue_stage1(det, sl, st, sl.frames_dev, n, plan, det->d_layers, 0, nullptr, nullptr, false);
+		if (s) return s;
+		double* d_out = distance_out && distance_on_device ? distance_out + (int64_t)base * nwin : det->d_sd_dist;
+		launch_svm_dense_windows(st, det->svm->dense, det->desc.patch_width, det->desc.patch_height, det->desc.step_x,
+				det->desc.step_y, sl.frames_dev, W, H, n, sl.d_arena, plan.arena_bytes, det->d_layers, (int)plan.layers.size(),
+				nwin, d_out, det->d_sd_count, det->d_sd_pos, det->sd_pos_cap);
+		c->launches++;
+		CUDA_TRY(cudaGetLastError());
+		CUDA_TRY(cudaMemcpyAsync(det->h_sd_count, det->d_sd_count, sizeof(int), cudaMemcpyDeviceToHost, st));
+		if (distance_out && !distance_on_device)
+			CUDA_TRY(cudaMemcpyAsync(distance_out + (int64_t)base * nwin, d_out, sizeof(double) * (size_t)(nwin * n), cudaMemcpyDeviceToHost, st));
+		CUDA_TRY(cudaStreamSynchronize(st));
+		const int npos = det->h_sd_count[0];
+		if (npos > det->sd_pos_cap) return fail(FDB_ERR_OVERFLOW, "positives list overflow: raise max_positives_per_frame");
+		if (npos > 0) {
+			CUDA_TRY(cudaMemcpyAsync(det->h_sd_pos, det->d_sd_pos, sizeof(DensePositive) * (size_t)npos, cudaMemcpyDeviceToHost, st));
+			CUDA_TRY(cudaStreamSynchronize(st));
+			std::sort(det->h_sd_pos, det->h_sd_pos + npos, [](const DensePositive& a, const DensePositive& b) { return a.row < b.row; });
+		}
+		for (int i = 0; i < npos; ++i) { /* canonical order: SlidingWindowDetector::detect pushes in extract order */
+			const DensePositive& p = det->h_sd_pos[i];
+			fdb_detection d;
+			fill_detection(&d, plan, det->desc, base + (int)(p.row / nwin), p.row % nwin);
+			d.reserved = 0;
+			d.wvm_level = -1;
+			d.wvm_fout = std::numeric_limits<float>::quiet_NaN();
+			d.wvm_probability = std::numeric_limits<double>::quiet_NaN();
+			d.svm_distance = p.distance;
+			d.svm_probability = svm_probability(det->svm->logistic_a, det->svm->logistic_b, p.distance);
 			d.probability = d.svm_probability;
 			d.positive = 1;
 			dets.push_back(d);
@@ -737,6 +815,15 @@ int fdb_detector_prepare(fdb_detector* det, int32_t width, int32_t height, int32
 		s = upload(all.data(), all.size(), &det->d_all_items, det->owned); if (s) return s;
 		s = dev_alloc(&det->d_all_dist, (size_t)std::max<int64_t>(plan.windows, 1), det->owned); if (s) return s;
 		s = host_alloc(&det->h_all_dist, (size_t)std::max<int64_t>(plan.windows, 1), det->owned_host); if (s) return s;
+		det->d_sd_dist = nullptr;
+		if (det->svm->has_dense && plan.windows > 0) {
+			det->sd_pos_cap = (int)std::min<int64_t>(plan.windows * det->chunk, (int64_t)1 << 26); /* every window may be positive */
+			s = dev_alloc(&det->d_sd_dist, (size_t)plan.windows * det->chunk, det->owned); if (s) return s;
+			s = dev_alloc(&det->d_sd_count, 4, det->owned); if (s) return s;
+			s = dev_alloc(&det->d_sd_pos, (size_t)det->sd_pos_cap, det->owned); if (s) return s;
+			s = host_alloc(&det->h_sd_count, 4, det->owned_host); if (s) return s;
+			s = host_alloc(&det->h_sd_pos, (size_t)det->sd_pos_cap, det->owned_host); if (s) return s;
+		}
 	}
 	det->prepared = true;
 	return FDB_OK;
@@ -1021,6 +1108,19 @@ int fdb_detect_single(fdb_detector* det, const uint8_t* frames_host, int64_t pit
 	if (pitch < det->plan.width) return fail(FDB_ERR_INVALID_ARGUMENT, "pitch smaller than the frame width");
 	return detect_single(det, frames_host, false, pitch, n_frames, distance_out, detections_out, det_cap, n_detections);
 }
+
+int fdb_detect_single_device(fdb_detector* det, const uint8_t* frames_device, int32_t n_frames, double* distance_device,
+		fdb_detection* detections_out, int64_t det_cap, int64_t* n_detections) {
+	if (!det || !det->prepared) return fail(FDB_ERR_INVALID_ARGUMENT, "detector not prepared (call fdb_detector_prepare)");
+	int s = check_ctx(det->ctx); if (s) return s;
+	if (det->wvm || !det->svm) return fail(FDB_ERR_INVALID_ARGUMENT, "fdb_detect_single_device needs a detector created with an SVM only");
+	if (n_frames < 0 || (n_frames > 0 && !frames_device)) return fail(FDB_ERR_INVALID_ARGUMENT, "bad frame batch");
+	if (!single_dense_usable(det))
+		return fail(FDB_ERR_UNSUPPORTED, "fdb_detect_single_device: this SVM has no tensor-core form (u8 RBF on HistEq64 patches only)");
+	return detect_single_dense(det, frames_device, true, det->plan.width, n_frames, distance_device, true, detections_out, det_cap, n_detections);
+}
+
+int fdb_detector_single_dense(fdb_detector* det) { return det && det->prepared && single_dense_usable(det) ? 1 : 0; }
 
 int fdb_detector_last_counts(fdb_detector* det, int64_t counts[5]) {
 	if (!det || !counts) return fail(FDB_ERR_INVALID_ARGUMENT, "null argument");

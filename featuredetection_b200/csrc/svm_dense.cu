@@ -1,0 +1,517 @@
+/*
+ * svm_dense.cu - the RBF support vector machine over EVERY window of a batch as one integer matrix product on the
+ * 5th-generation tensor cores (tcgen05.mma kind::i8, accumulators in tensor memory), sm_100a only.
+ *
+ * What it replaces: the `single` detector of ffpDetectApp with a psvm classifier (ffpDetectApp.cpp:427-500) -
+ * SlidingWindowDetector::detect (SlidingWindowDetector.cpp:40-98) calls, for every window of every pyramid layer,
+ *   HistEq64Filter::applyTo                         HistEq64Filter.cpp:32-125
+ *   SvmClassifier::computeHyperplaneDistance        SvmClassifier.cpp:55-60      distance = -bias + sum_i coef_i k(x, sv_i)
+ *   RbfKernel::compute                              RbfKernel.hpp:32-40,78-108   k = exp(-gamma * sum (x - sv)^2), u8 -> int
+ * i.e. windows x support vectors x pixels multiply-adds (16 185 x 1024 x 400 per 640x480 FaceFrontal frame).
+ *
+ * The sum of squared differences of two u8 vectors is an exact integer: |x|^2 + |sv|^2 - 2 x.sv, and x.sv for all
+ * (window, support vector) pairs is the matrix product [windows x pixels] . [pixels x support vectors] of u8 operands
+ * with s32 accumulation - exact on the integer tensor cores (400 * 255 * 255 < 2^31).
+ *
+ * One persistent CTA per SM, 14 warps with fixed roles:
+ *   warp 0      streams the support-vector blocks (pre-arranged on the host as UMMA core matrices) from L2 into a
+ *               4-stage shared-memory ring with cp.async.bulk + mbarrier complete_tx
+ *   warp 1      owns tensor memory (512 columns) and issues tcgen05.mma (one lane): 2 window tiles of 128 rows share
+ *               every support-vector block; two accumulator buffers of 2 x 128 columns alternate between MMA and epilogue
+ *   warps 2-5   producers of the A operand: thread = window; HistEq64 of the window straight from the pyramid layer
+ *               (float32 cdf in the reference's order, like the other kernels), equalised pixels written to shared
+ *               memory as 8x16-byte core matrices, |x|^2 from the histogram; no equalised patch ever touches HBM
+ *   warps 6-13  epilogue: thread = window row (tcgen05.ld 32 lanes x 32 columns), ssd = |x|^2 + |sv|^2 - 2 dot,
+ *               k = exp(-gamma ssd) in float64, distance accumulated in float64 IN SUPPORT-VECTOR ORDER (one thread
+ *               owns one window for all support vectors, so the order of the reference's loop is kept)
+ *
+ * exp(-gamma * ssd) for an integer ssd: ssd = hi * 2^s + lo, exp(-gamma hi 2^s) from a table of glibc-computed doubles
+ * in shared memory, exp(-gamma lo) by its degree-5 Taylor polynomial (gamma * 2^s <= 2^-7, truncation < 3e-16 relative).
+ * The kernel value therefore differs from glibc's exp by a few 1e-16 relative - far inside the 1e-4 score tolerance
+ * (tests compare distances at 1e-9) - while the integer part of the computation is exact.
+ *
+ * Shared-memory operand layout (no swizzle, K-major): a core matrix is 8 rows x 16 bytes stored as 128 contiguous
+ * bytes; core matrices adjacent in K are 128 bytes apart (descriptor LBO), groups of 8 rows SBO bytes apart.
+ */
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include "fdb_internal.h"
+#include "wvm_device.h"
+
+namespace fdb {
+
+namespace {
+
+constexpr int SD_ROWS = 128;      /* window rows per MMA (UMMA M) */
+constexpr int SD_MT = 2;          /* window tiles per pass */
+constexpr int SD_N = 128;         /* support vectors per accumulator block (UMMA N) */
+constexpr int SD_KCH = 8;         /* 16-byte k chunks per streamed support-vector block */
+constexpr int SD_STAGES = 4;
+constexpr int SD_B_STAGE_BYTES = (SD_N / 8) * SD_KCH * 128;
+constexpr int SD_PROD_WARPS = 4, SD_EPI_WARPS = 8;
+constexpr int SD_THREADS = 32 * (2 + SD_PROD_WARPS + SD_EPI_WARPS);
+constexpr int SD_TMEM_COLS = 512;
+constexpr int SD_PASS_ROWS = SD_ROWS * SD_MT;
+constexpr int SD_SPIN_LIMIT = 1 << 26;
+
+/* barrier slots */
+enum { BAR_B_FULL = 0, BAR_B_EMPTY = SD_STAGES, BAR_A_FULL = 2 * SD_STAGES, BAR_A_EMPTY = 2 * SD_STAGES + 2,
+	BAR_T_FULL = 2 * SD_STAGES + 3, BAR_T_EMPTY = 2 * SD_STAGES + 5, BAR_COUNT = 2 * SD_STAGES + 7 };
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, int count) {
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+/* bounded wait: a protocol error traps instead of hanging the device */
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+	uint32_t done;
+	int spins = 0;
+	do {
+		asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+				: "=r"(done) : "r"(bar), "r"(parity) : "memory");
+		if (!done && ++spins > SD_SPIN_LIMIT) {
+			printf("svm_dense_kernel: barrier %u timed out (block %d thread %d)\n", bar, blockIdx.x, threadIdx.x);
+			__trap();
+		}
+	} while (!done);
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+	asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
+}
+/* D[tmem] (+)= A[smem] . B[smem]^T, u8 x u8 -> s32 */
+__device__ __forceinline__ void tc_mma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+	asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+			:: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+/* shared-memory matrix descriptor: K-major, no swizzle, version 1 (sm_100) */
+__device__ __forceinline__ uint64_t tc_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
+	return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo >> 4) & 0x3FFF) << 32)
+			| ((uint64_t)1 << 46);
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+	asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+			"{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+			"%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+			: "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+			  "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+			  "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+			  "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+			: "r"(taddr) : "memory");
+	asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+struct SvmDenseArgs {
+	DevSvmDense s;
+	int patch_w, patch_h, step_x, step_y;
+	const uint8_t* frames; int W, H;
+	const uint8_t* arena; int64_t arena_stride;
+	const DevLayer* layers; int n_layers;
+	int64_t windows_per_frame;
+	const uint8_t* vectors;       /* MODE 1: [total][dim] u8 */
+	int64_t total;                /* rows = windows of the batch (or vectors) */
+	double* distance_out;         /* [total] */
+	int* pos_count;               /* positives appended (may run past pos_cap), or nullptr */
+	DensePositive* pos;
+	int pos_cap;
+	uint32_t desc_swap;           /* debugging: exchange LBO and SBO in the matrix descriptors */
+};
+
+/* A row of one window: HistEq64 (HistEq64Filter.cpp:32-125) from the layer image into the core-matrix layout */
+__device__ __forceinline__ int produce_window(const SvmDenseArgs& a, const DevLayer* sLayers, uint16_t* hist /* column of this thread */,
+		uint8_t* arow /* A tile + row offset */, int64_t g) {
+	const int pw = a.patch_w, ph = a.patch_h, npix = pw * ph;
+	const int frame = (int)(g / a.windows_per_frame);
+	const int w = (int)(g - (int64_t)frame * a.windows_per_frame);
+	int li = 0;
+	while (li + 1 < a.n_layers && w >= sLayers[li + 1].first_window) ++li;
+	const DevLayer& L = sLayers[li];
+	const int local = w - L.first_window;
+	const int iy = local / L.windows_x, ix = local - iy * L.windows_x;
+	const int pitch = L.pitch;
+	const uint8_t* src = (L.offset < 0 ? a.frames + (int64_t)frame * a.W * a.H : a.arena + (int64_t)frame * a.arena_stride + L.offset)
+			+ (int64_t)(L.begin_y + iy * a.step_y) * pitch + (L.begin_x + ix * a.step_x);
+#pragma unroll 8
+	for (int b = 0; b < 64; ++b) hist[b * SD_ROWS] = 0;
+	for (int r = 0; r < ph; ++r) {
+		const uint8_t* row = src + (int64_t)r * pitch;
+		for (int c = 0; c < pw; ++c) hist[(row[c] >> 2) * SD_ROWS] += 1;
+	}
+	/* sequential float32 cdf, rounded: HistEq64Filter.cpp:70-87,97 */
+	const float stretch = __fdiv_rn(255.0f, (float)npix);
+	float cdf = 0.f;
+	int xx = 0;
+	for (int b = 0; b < 64; ++b) {
+		const int cnt = hist[b * SD_ROWS];
+		cdf = __fadd_rn(cdf, __fmul_rn((float)cnt, stretch));
+		const float fl = floorf(cdf);
+		const int eq = ((int)fl + (__fsub_rn(cdf, fl) >= 0.5f ? 1 : 0)) & 255; /* saturate_cast never triggers: cdf <= 255 */
+		hist[b * SD_ROWS] = (uint16_t)eq;
+		xx += cnt * eq * eq;
+	}
+	int r = 0, c = 0;
+	const uint8_t* row = src;
+	for (int ch = 0; ch < a.s.chunks; ++ch) {
+		uint32_t wd[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+		for (int k = 0; k < 16; ++k) {
+			if (ch * 16 + k < npix) {
+				const uint32_t e = hist[(row[c] >> 2) * SD_ROWS];
+				wd[k >> 2] |= e << (8 * (k & 3));
+				if (++c == pw) { c = 0; ++r; row += pitch; }
+			}
+		}
+		*reinterpret_cast<uint4*>(arow + ch * 128) = make_uint4(wd[0], wd[1], wd[2], wd[3]);
+	}
+	return xx;
+}
+
+__device__ __forceinline__ int produce_vector(const SvmDenseArgs& a, uint8_t* arow, int64_t g) {
+	const int dim = a.s.dim;
+	const uint8_t* v = a.vectors + g * dim;
+	int xx = 0;
+	for (int ch = 0; ch < a.s.chunks; ++ch) {
+		uint32_t wd[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+		for (int k = 0; k < 16; ++k) {
+			const int i = ch * 16 + k;
+			if (i < dim) wd[k >> 2] |= (uint32_t)v[i] << (8 * (k & 3));
+		}
+#pragma unroll
+		for (int k = 0; k < 4; ++k) xx = __dp4a(wd[k], wd[k], (unsigned)xx);
+		*reinterpret_cast<uint4*>(arow + ch * 128) = make_uint4(wd[0], wd[1], wd[2], wd[3]);
+	}
+	return xx;
+}
+
+template <int MODE> /* 0: windows of frames (HistEq64 built by the producers), 1: given u8 vectors */
+__global__ void __launch_bounds__(SD_THREADS, 1) svm_dense_kernel(const __grid_constant__ SvmDenseArgs a) {
+	extern __shared__ __align__(128) unsigned char sd_smem[];
+	const int chunks = a.s.chunks;
+	const int a_tile = (SD_ROWS / 8) * chunks * 128;
+	uint8_t* sA = sd_smem;
+	uint8_t* sB = sA + SD_MT * a_tile;
+	uint16_t* sHist = reinterpret_cast<uint16_t*>(sB + SD_STAGES * SD_B_STAGE_BYTES);   /* [64][SD_ROWS] */
+	double* sTab = reinterpret_cast<double*>(sHist + 64 * SD_ROWS);                    /* [tab_n] */
+	int* sXX = reinterpret_cast<int*>(sTab + a.s.tab_n);                               /* [2][SD_PASS_ROWS] */
+	DevLayer* sLayers = reinterpret_cast<DevLayer*>(sXX + 2 * SD_PASS_ROWS);
+	uint64_t* bars = reinterpret_cast<uint64_t*>(sLayers + FDB_MAX_LAYERS);
+	uint32_t* sTmem = reinterpret_cast<uint32_t*>(bars + BAR_COUNT);
+
+	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+	const uint32_t bar0 = smem_u32(bars);
+	auto bar = [bar0](int i) { return bar0 + 8u * (uint32_t)i; };
+
+	if (tid == 0) {
+		for (int i = 0; i < SD_STAGES; ++i) { mbar_init(bar(BAR_B_FULL + i), 1); mbar_init(bar(BAR_B_EMPTY + i), 1); }
+		mbar_init(bar(BAR_A_FULL), SD_ROWS); mbar_init(bar(BAR_A_FULL + 1), SD_ROWS);
+		mbar_init(bar(BAR_A_EMPTY), 1);
+		for (int i = 0; i < 2; ++i) { mbar_init(bar(BAR_T_FULL + i), 1); mbar_init(bar(BAR_T_EMPTY + i), SD_EPI_WARPS); }
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	if (warp == 1) {
+		asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(sTmem)), "n"(SD_TMEM_COLS) : "memory");
+		asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+	}
+	for (int i = tid; i < a.s.tab_n; i += SD_THREADS) sTab[i] = a.s.exp_tab[i];
+	if (MODE == 0) for (int i = tid; i < a.n_layers; i += SD_THREADS) sLayers[i] = a.layers[i];
+	tc_fence_before();
+	__syncthreads();
+	tc_fence_after();
+	const uint32_t tmem = *sTmem;
+
+	const int64_t npass = (a.total + SD_PASS_ROWS - 1) / SD_PASS_ROWS;
+	const int NT = a.s.num_sv_pad / SD_N;
+	const int KB = (chunks + SD_KCH - 1) / SD_KCH;
+
+	if (warp == 0) {
+		/* ===== support-vector block stream ===== */
+		if (lane == 0) {
+			uint32_t it = 0;
+			const size_t nblock_bytes = (size_t)(SD_N / 8) * chunks * 128;
+			for (int64_t pass = blockIdx.x; pass < npass; pass += gridDim.x) {
+				for (int nt = 0; nt < NT; ++nt) {
+					const uint8_t* src = a.s.b_blocks + (size_t)nt * nblock_bytes;
+					for (int kb = 0; kb < KB; ++kb, ++it) {
+						const int cb = min(SD_KCH, chunks - kb * SD_KCH);
+						const uint32_t bytes = (uint32_t)(SD_N / 8) * cb * 128;
+						const int stage = it % SD_STAGES;
+						mbar_wait(bar(BAR_B_EMPTY + stage), ((it / SD_STAGES) & 1) ^ 1);
+						mbar_expect_tx(bar(BAR_B_FULL + stage), bytes);
+						asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+								:: "r"(smem_u32(sB + stage * SD_B_STAGE_BYTES)), "l"(src), "r"(bytes), "r"(bar(BAR_B_FULL + stage)) : "memory");
+						src += bytes;
+					}
+				}
+			}
+		}
+	} else if (warp == 1) {
+		/* ===== MMA issue ===== */
+		if (lane == 0) {
+			/* instruction descriptor: D = s32, A = B = u8, both K-major, N = 128, M = 128 */
+			const uint32_t idesc = (2u << 4) | ((uint32_t)(SD_N >> 3) << 17) | ((uint32_t)(SD_ROWS >> 4) << 24);
+			const uint32_t a_addr = smem_u32(sA), b_addr = smem_u32(sB);
+			const uint32_t a_sbo = (uint32_t)chunks * 128;
+			uint32_t it = 0, acc_it = 0, pass_it = 0;
+			for (int64_t pass = blockIdx.x; pass < npass; pass += gridDim.x, ++pass_it) {
+				mbar_wait(bar(BAR_A_FULL + (pass_it & 1)), (pass_it >> 1) & 1);
+				tc_fence_after();
+				for (int nt = 0; nt < NT; ++nt, ++acc_it) {
+					const uint32_t buf = acc_it & 1;
+					mbar_wait(bar(BAR_T_EMPTY + buf), ((acc_it >> 1) & 1) ^ 1);
+					tc_fence_after();
+					for (int kb = 0; kb < KB; ++kb, ++it) {
+						const int cb = min(SD_KCH, chunks - kb * SD_KCH);
+						const int stage = it % SD_STAGES;
+						mbar_wait(bar(BAR_B_FULL + stage), (it / SD_STAGES) & 1);
+						tc_fence_after();
+						const uint32_t b_sbo = (uint32_t)cb * 128;
+						for (int ks = 0; ks < cb / 2; ++ks) {
+							const uint32_t bstart = b_addr + stage * SD_B_STAGE_BYTES + ks * 256;
+							const uint64_t bdesc = a.desc_swap ? tc_desc(bstart, b_sbo, 128) : tc_desc(bstart, 128, b_sbo);
+#pragma unroll
+							for (int m = 0; m < SD_MT; ++m) {
+								const uint32_t astart = a_addr + m * a_tile + (kb * SD_KCH + 2 * ks) * 128;
+								const uint64_t adesc = a.desc_swap ? tc_desc(astart, a_sbo, 128) : tc_desc(astart, 128, a_sbo);
+								tc_mma_i8(tmem + buf * (SD_MT * SD_N) + m * SD_N, adesc, bdesc, idesc, (kb | ks) != 0 ? 1u : 0u);
+							}
+						}
+						tc_commit(bar(BAR_B_EMPTY + stage)); /* the ring slot is free once these MMAs have read it */
+					}
+					tc_commit(bar(BAR_T_FULL + buf));
+				}
+				tc_commit(bar(BAR_A_EMPTY));
+			}
+		}
+	} else if (warp < 2 + SD_PROD_WARPS) {
+		/* ===== A operand producers: thread = window row ===== */
+		const int t = tid - 64;
+		uint16_t* hist = sHist + t;
+		uint32_t pass_it = 0;
+		for (int64_t pass = blockIdx.x; pass < npass; pass += gridDim.x, ++pass_it) {
+			mbar_wait(bar(BAR_A_EMPTY), (pass_it & 1) ^ 1);
+#pragma unroll 1
+			for (int m = 0; m < SD_MT; ++m) {
+				const int64_t g = pass * SD_PASS_ROWS + m * SD_ROWS + t;
+				uint8_t* arow = sA + m * a_tile + (t >> 3) * (chunks * 128) + (t & 7) * 16;
+				int xx = 0;
+				if (g < a.total) {
+					xx = MODE == 0 ? produce_window(a, sLayers, hist, arow, g) : produce_vector(a, arow, g);
+				} else {
+					for (int ch = 0; ch < chunks; ++ch) *reinterpret_cast<uint4*>(arow + ch * 128) = make_uint4(0u, 0u, 0u, 0u);
+				}
+				sXX[(pass_it & 1) * SD_PASS_ROWS + m * SD_ROWS + t] = xx;
+			}
+			asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); /* generic-proxy stores -> visible to the tensor core */
+			mbar_arrive(bar(BAR_A_FULL + (pass_it & 1)));
+		}
+	} else {
+		/* ===== epilogue: thread = window row of tile m ===== */
+		const int e = warp - (2 + SD_PROD_WARPS);
+		const int m = e >> 2, q = warp & 3;       /* a warp reads the tensor-memory lanes 32 * (warp id % 4) .. + 31 */
+		const int row = q * 32 + lane;
+		const int s_shift = a.s.shift;
+		const uint32_t lo_mask = (1u << s_shift) - 1u;
+		const int tab_last = a.s.tab_n - 1;
+		const double c1 = a.s.poly[0], c2 = a.s.poly[1], c3 = a.s.poly[2], c4 = a.s.poly[3], c5 = a.s.poly[4];
+		const int* __restrict__ ssq = a.s.ssq;
+		const double* __restrict__ coef = a.s.coef;
+		uint32_t acc_it = 0, pass_it = 0;
+		for (int64_t pass = blockIdx.x; pass < npass; pass += gridDim.x, ++pass_it) {
+			mbar_wait(bar(BAR_A_FULL + (pass_it & 1)), (pass_it >> 1) & 1);
+			const int xx = sXX[(pass_it & 1) * SD_PASS_ROWS + m * SD_ROWS + row];
+			double dist = a.s.neg_bias; /* SvmClassifier.cpp:56: double distance = -bias */
+			for (int nt = 0; nt < NT; ++nt, ++acc_it) {
+				const uint32_t buf = acc_it & 1;
+				mbar_wait(bar(BAR_T_FULL + buf), (acc_it >> 1) & 1);
+				tc_fence_after();
+				const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + buf * (SD_MT * SD_N) + m * SD_N;
+#pragma unroll 1
+				for (int cq = 0; cq < SD_N / 32; ++cq) {
+					uint32_t v[32];
+					tc_ld32(taddr + cq * 32, v);
+					if (cq == SD_N / 32 - 1) { /* accumulators are in registers: hand the buffer back to the MMA warp */
+						tc_fence_before();
+						__syncwarp();
+						if (lane == 0) mbar_arrive(bar(BAR_T_EMPTY + buf));
+					}
+					const int sv0 = nt * SD_N + cq * 32;
+					const int4* __restrict__ s4p = reinterpret_cast<const int4*>(ssq + sv0);       /* warp-uniform vector loads */
+					const double2* __restrict__ c2p = reinterpret_cast<const double2*>(coef + sv0);
+#pragma unroll
+					for (int j4 = 0; j4 < 8; ++j4) {
+						const int4 s4 = __ldg(s4p + j4);
+						const double2 ca = __ldg(c2p + 2 * j4), cb = __ldg(c2p + 2 * j4 + 1);
+						const int ss[4] = {s4.x, s4.y, s4.z, s4.w};
+						const double cc[4] = {ca.x, ca.y, cb.x, cb.y};
+#pragma unroll
+						for (int k = 0; k < 4; ++k) {
+							const int ssd = xx + ss[k] - 2 * (int)v[4 * j4 + k];
+							const double l = (double)(int)(ssd & lo_mask);
+							const int hi = min(ssd >> s_shift, tab_last);
+							double p = fma(l, c5, c4);
+							p = fma(l, p, c3);
+							p = fma(l, p, c2);
+							p = fma(l, p, c1);
+							p = fma(l, p, 1.0);
+							const double kv = __dmul_rn(sTab[hi], p);         /* RbfKernel.hpp:39 */
+							dist = fma(cc[k], kv, dist);                      /* SvmClassifier.cpp:58, in support-vector order */
+						}
+					}
+				}
+			}
+			const int64_t g = pass * SD_PASS_ROWS + m * SD_ROWS + row;
+			if (g < a.total) {
+				a.distance_out[g] = dist;
+				if (a.pos_count && dist >= (double)a.s.threshold) { /* SvmClassifier::classify (SvmClassifier.cpp:44-46) */
+					const int slot = atomicAdd(a.pos_count, 1);
+					if (slot < a.pos_cap) {
+						DensePositive dp;
+						dp.row = g; dp.distance = dist;
+						a.pos[slot] = dp;
+					}
+				}
+			}
+		}
+	}
+
+	tc_fence_before();
+	__syncthreads();
+	if (warp == 1) {
+		tc_fence_after();
+		asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "n"(SD_TMEM_COLS) : "memory");
+	}
+}
+
+size_t sd_smem_bytes(const DevSvmDense& s) {
+	const size_t a_tile = (size_t)(SD_ROWS / 8) * s.chunks * 128;
+	return SD_MT * a_tile + (size_t)SD_STAGES * SD_B_STAGE_BYTES + 64 * SD_ROWS * sizeof(uint16_t) + (size_t)s.tab_n * 8
+			+ 2 * SD_PASS_ROWS * sizeof(int) + FDB_MAX_LAYERS * sizeof(DevLayer) + BAR_COUNT * 8 + 16;
+}
+
+int g_sd_sms = 0;
+size_t g_sd_smem_max = 0;
+
+} // namespace
+
+int svm_dense_configure() {
+	int dev = 0;
+	cudaError_t e = cudaGetDevice(&dev);
+	int v = 0;
+	if (e == cudaSuccess) e = cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+	g_sd_sms = v;
+	if (e == cudaSuccess) e = cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+	g_sd_smem_max = (size_t)v;
+	if (e == cudaSuccess) e = cudaFuncSetAttribute(svm_dense_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, v);
+	if (e == cudaSuccess) e = cudaFuncSetAttribute(svm_dense_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, v);
+	return (int)e;
+}
+
+/* host-side preparation of the tensor-core form of an u8 RBF SVM; returns false when the model does not fit
+ * (shared memory for the window tiles / the exp table) - callers then keep the per-window kernel of svm.cu */
+bool svm_dense_build(const uint8_t* sv, const float* coef, int num_sv, int dim, double gamma, float bias, float threshold,
+		SvmDenseHost* out) {
+	if (!(gamma > 0.0) || num_sv < 1 || dim < 1 || (int64_t)dim * 65025 >= ((int64_t)1 << 31)) return false;
+	SvmDenseHost& h = *out;
+	DevSvmDense& d = h.dev;
+	d.dim = dim;
+	d.chunks = 2 * ((dim + 31) / 32);
+	d.num_sv_pad = ((num_sv + 2 * SD_N - 1) / (2 * SD_N)) * (2 * SD_N); /* an even number of accumulator blocks */
+	d.threshold = threshold;
+	d.neg_bias = -(double)bias;
+	/* exp table: ssd = hi * 2^shift + lo with gamma * 2^shift <= 2^-7 */
+	int shift = 0;
+	while (shift < 24 && gamma * (double)((int64_t)2 << shift) <= 0.0078125) ++shift;
+	if (gamma > 0.0078125) shift = 0;
+	const int64_t max_ssd = (int64_t)dim * 65025;
+	const double under = 746.0 / gamma; /* exp(-746) == 0 in float64 */
+	const int64_t top = under < (double)max_ssd ? (int64_t)under + 1 : max_ssd;
+	const int64_t entries = (top >> shift) + 2;
+	if (gamma > 0.0078125 || entries > 4096) return false; /* TODO(large gamma): needs a finer table than shared memory holds */
+	d.shift = shift;
+	d.tab_n = (int)entries;
+	h.tab.resize((size_t)entries);
+	for (int64_t i = 0; i < entries; ++i) h.tab[(size_t)i] = std::exp(-gamma * (double)(i << shift));
+	if (top < max_ssd) h.tab[(size_t)entries - 1] = 0.0; /* everything past the underflow point */
+	long double f = 1.0L, gk = 1.0L;
+	for (int k = 1; k <= 5; ++k) { f *= k; gk *= -(long double)gamma; d.poly[k - 1] = (double)(gk / f); }
+	if (sd_smem_bytes(d) > (g_sd_smem_max ? g_sd_smem_max : (size_t)232448)) return false;
+	/* support vectors as core matrices: [n block][k block][group of 8 rows][k chunk][row][16 bytes] */
+	const int NT = d.num_sv_pad / SD_N, KB = (d.chunks + SD_KCH - 1) / SD_KCH;
+	h.b_blocks.assign((size_t)d.num_sv_pad * d.chunks * 16, 0);
+	size_t o = 0;
+	for (int nt = 0; nt < NT; ++nt)
+		for (int kb = 0; kb < KB; ++kb) {
+			const int cb = std::min(SD_KCH, d.chunks - kb * SD_KCH);
+			for (int grp = 0; grp < SD_N / 8; ++grp)
+				for (int c = 0; c < cb; ++c)
+					for (int r = 0; r < 8; ++r, o += 16) {
+						const int i = nt * SD_N + grp * 8 + r;
+						if (i >= num_sv) continue;
+						const int k0 = (kb * SD_KCH + c) * 16;
+						for (int k = 0; k < 16 && k0 + k < dim; ++k) h.b_blocks[o + k] = sv[(size_t)i * dim + k0 + k];
+					}
+		}
+	h.ssq.assign((size_t)d.num_sv_pad, 0);
+	h.coef.assign((size_t)d.num_sv_pad, 0.0);
+	for (int i = 0; i < num_sv; ++i) {
+		int s = 0;
+		for (int k = 0; k < dim; ++k) { const int v = sv[(size_t)i * dim + k]; s += v * v; }
+		h.ssq[(size_t)i] = s;
+		h.coef[(size_t)i] = (double)coef[i];
+	}
+	return true;
+}
+
+bool svm_dense_enabled() {
+	const char* e = std::getenv("FDB_SVM_DENSE");
+	return !(e && e[0] == '0');
+}
+
+static int dense_grid(int64_t total) {
+	const int64_t npass = (total + SD_PASS_ROWS - 1) / SD_PASS_ROWS;
+	return (int)std::min<int64_t>(npass, g_sd_sms > 0 ? g_sd_sms : 148);
+}
+
+static uint32_t dense_desc_swap() {
+	const char* e = std::getenv("FDB_SVMD_SWAP");
+	return e && e[0] == '1' ? 1u : 0u;
+}
+
+void launch_svm_dense_windows(cudaStream_t st, const DevSvmDense& s, int patch_w, int patch_h, int step_x, int step_y,
+		const uint8_t* frames, int W, int H, int n_frames, const uint8_t* arena, int64_t arena_stride, const DevLayer* layers,
+		int n_layers, int64_t windows_per_frame, double* distance_out, int* pos_count, DensePositive* pos, int pos_cap) {
+	const int64_t total = windows_per_frame * n_frames;
+	if (total <= 0) return;
+	SvmDenseArgs a{};
+	a.s = s; a.patch_w = patch_w; a.patch_h = patch_h; a.step_x = step_x; a.step_y = step_y;
+	a.frames = frames; a.W = W; a.H = H; a.arena = arena; a.arena_stride = arena_stride;
+	a.layers = layers; a.n_layers = n_layers; a.windows_per_frame = windows_per_frame;
+	a.total = total; a.distance_out = distance_out; a.pos_count = pos_count; a.pos = pos; a.pos_cap = pos_cap;
+	a.desc_swap = dense_desc_swap();
+	svm_dense_kernel<0><<<dense_grid(total), SD_THREADS, sd_smem_bytes(s), st>>>(a);
+}
+
+void launch_svm_dense_vectors(cudaStream_t st, const DevSvmDense& s, const uint8_t* vectors, int64_t n, double* distance_out) {
+	if (n <= 0) return;
+	SvmDenseArgs a{};
+	a.s = s; a.vectors = vectors; a.total = n; a.distance_out = distance_out; a.windows_per_frame = n;
+	a.desc_swap = dense_desc_swap();
+	svm_dense_kernel<1><<<dense_grid(n), SD_THREADS, sd_smem_bytes(s), st>>>(a);
+}
+
+} // namespace fdb

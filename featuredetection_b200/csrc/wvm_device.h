@@ -82,6 +82,43 @@ struct DevSvm {
 	const float* coef;              /* [num_sv] */
 };
 
+/* tensor-core form of an u8 RBF SVM (svm_dense.cu): support vectors as UMMA core matrices, |sv|^2, float64
+ * coefficients, the exp table; all pointers device memory */
+struct DevSvmDense {
+	int num_sv_pad;            /* support vectors padded to a multiple of 256 (zero vectors with coefficient 0) */
+	int dim, chunks;           /* elements per vector; 16-byte k chunks per row (2 * ceil(dim / 32), zero padded) */
+	int shift, tab_n;          /* ssd = hi << shift | lo; exp_tab[hi] = exp(-gamma * (hi << shift)), tab_n entries */
+	float threshold;
+	double neg_bias;
+	double poly[5];            /* (-gamma)^k / k!, k = 1..5: exp(-gamma * lo) */
+	const uint8_t* b_blocks;   /* [n block of 128][k block]{[16 row groups][chunks in block][8 rows][16 bytes]} */
+	const int* ssq;            /* [num_sv_pad] */
+	const double* coef;        /* [num_sv_pad] */
+	const double* exp_tab;     /* [tab_n] */
+};
+struct DensePositive {        /* a row (window of the batch) at or above the threshold */
+	int64_t row;
+	double distance;
+};
+}
+#include <vector>
+namespace fdb {
+struct SvmDenseHost {
+	DevSvmDense dev{};
+	std::vector<uint8_t> b_blocks;
+	std::vector<int> ssq;
+	std::vector<double> coef, tab;
+};
+#define FDB_SVM_DENSE_MIN_VECTORS 128 /* fdb_svm_get_probability: batches from this size use the tensor-core kernel */
+int svm_dense_configure();
+bool svm_dense_enabled(); /* false when FDB_SVM_DENSE=0 (debugging: forces the per-window kernel) */
+bool svm_dense_build(const uint8_t* sv, const float* coef, int num_sv, int dim, double gamma, float bias, float threshold,
+		SvmDenseHost* out);
+void launch_svm_dense_windows(cudaStream_t st, const DevSvmDense& s, int patch_w, int patch_h, int step_x, int step_y,
+		const uint8_t* frames, int W, int H, int n_frames, const uint8_t* arena, int64_t arena_stride, const DevLayer* layers,
+		int n_layers, int64_t windows_per_frame, double* distance_out, int* pos_count, DensePositive* pos, int pos_cap);
+void launch_svm_dense_vectors(cudaStream_t st, const DevSvmDense& s, const uint8_t* vectors, int64_t n, double* distance_out);
+
 int wvm_configure();
 size_t wvm_smem_bytes(const DevWvm& m);
 void launch_wvm_windows(cudaStream_t st, const DevWvm& m, const uint8_t* frames, int W, int H, int n_frames,

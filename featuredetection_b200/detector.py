@@ -130,6 +130,11 @@ class ProbabilisticSvmClassifier:
     def set_threshold(self, t):
         capi.check(self.ctx.lib, self.ctx.lib.fdb_svm_set_threshold(self.h, t))
 
+    @property
+    def has_dense(self):
+        """True when batches run on the tensor cores (csrc/svm_dense.cu)"""
+        return bool(self.ctx.lib.fdb_svm_has_dense(self.h))
+
     def get_probability(self, vectors):
         v = np.ascontiguousarray(vectors, self.model.sv.dtype).reshape(-1, self.model.sv.shape[1])
         n = v.shape[0]
@@ -293,6 +298,20 @@ class SlidingWindowCascade:
             self.h, frames.ctypes.data, W, n, dist.ctypes.data if want_distances else None,
             dets.ctypes.data, det_cap, C.byref(cnt)))
         return dets[:cnt.value].copy(), dist
+
+    @property
+    def single_dense(self):
+        """True when detect_single runs as one tensor-core launch per chunk of frames (csrc/svm_dense.cu)"""
+        return bool(self.ctx.lib.fdb_detector_single_dense(self.h))
+
+    def detect_single_device(self, frames_ptr, n, distance_ptr=None, det_cap=None):
+        """detect_single for frames resident in device memory; distances (if wanted) stay on the device"""
+        det_cap = det_cap or max(1024, 64 * n)
+        dets = np.zeros(det_cap, DETECTION_DTYPE)
+        cnt = C.c_int64()
+        capi.check(self.ctx.lib, self.ctx.lib.fdb_detect_single_device(
+            self.h, frames_ptr, n, distance_ptr, dets.ctypes.data, det_cap, C.byref(cnt)))
+        return dets[:cnt.value].copy()
 
     def last_counts(self):
         c = (C.c_int64 * 5)()

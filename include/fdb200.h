@@ -287,6 +287,12 @@ FDB_API int fdb_svm_set_threshold(fdb_svm* svm, float threshold);
 FDB_API int fdb_svm_get_probability(fdb_svm* svm, const void* vectors_host, int64_t n,
 		double* distance_out, double* probability_out, uint8_t* positive_out);
 
+/* 1 when the SVM has a tensor-core form (csrc/svm_dense.cu: u8 support vectors, RBF kernel, gamma and dimension within
+ * the shared-memory budget): batches of >= 128 vectors in fdb_svm_get_probability and the `single` detector then
+ * evaluate windows x support vectors as one exact u8 matrix product (tcgen05.mma kind::i8) with a float64 epilogue.
+ * Same loop as above (SvmClassifier.cpp:55-60, RbfKernel.hpp:32-40); distances agree with it to ~1e-13. */
+FDB_API int fdb_svm_has_dense(const fdb_svm* svm);
+
 /* ------------------------------------------------------------------------------------------
  * Detector  (PyramidFeatureExtractor + Detector surface)
  * ---------------------------------------------------------------------------------------- */
@@ -424,6 +430,13 @@ FDB_API int fdb_extract_features(fdb_detector* det, const uint8_t* frame_host, i
  * (fdb_detect_batch on such a detector does the same without distance_out.) */
 FDB_API int fdb_detect_single(fdb_detector* det, const uint8_t* frames_host, int64_t pitch, int32_t n_frames,
 		double* distance_out, fdb_detection* detections_out, int64_t det_cap, int64_t* n_detections);
+
+/* The same call for frames resident in device memory ([n_frames][height][width], tight pitch); distance_device: NULL
+ * or device memory for n_frames * windows_per_frame doubles. Only for detectors whose SVM runs on the tensor cores
+ * (fdb_detector_single_dense() == 1), FDB_ERR_UNSUPPORTED otherwise. */
+FDB_API int fdb_detect_single_device(fdb_detector* det, const uint8_t* frames_device, int32_t n_frames,
+		double* distance_device, fdb_detection* detections_out, int64_t det_cap, int64_t* n_detections);
+FDB_API int fdb_detector_single_dense(fdb_detector* det);
 
 /* Per-stage counters of the last detect call (TOT/TACC-style counters, ffpDetectApp.cpp:650-657):
  * [0] windows, [1] wvm positives, [2] after OE, [3] svm positives, [4] after NMS. */
