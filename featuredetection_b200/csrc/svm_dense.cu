@@ -15,7 +15,7 @@
  *
  * One persistent CTA per SM, 14 warps with fixed roles:
  *   warp 0      streams the support-vector blocks (pre-arranged on the host as UMMA core matrices) from L2 into a
- *               4-stage shared-memory ring with cp.async.bulk + mbarrier complete_tx
+ *               3-stage shared-memory ring with cp.async.bulk + mbarrier complete_tx
  *   warp 1      owns tensor memory (512 columns) and issues tcgen05.mma (one lane): 2 window tiles of 128 rows share
  *               every support-vector block; two accumulator buffers of 2 x 128 columns alternate between MMA and epilogue
  *   warps 2-5   producers of the A operand: thread = window; HistEq64 of the window straight from the pyramid layer
@@ -26,9 +26,9 @@
  *               owns one window for all support vectors, so the order of the reference's loop is kept)
  *
  * exp(-gamma * ssd) for an integer ssd: ssd = hi * 2^s + lo, exp(-gamma hi 2^s) from a table of glibc-computed doubles
- * in shared memory, exp(-gamma lo) by its degree-5 Taylor polynomial (gamma * 2^s <= 2^-7, truncation < 3e-16 relative).
- * The kernel value therefore differs from glibc's exp by a few 1e-16 relative - far inside the 1e-4 score tolerance
- * (tests compare distances at 1e-9) - while the integer part of the computation is exact.
+ * in shared memory, exp(-gamma lo) by its degree-4 Taylor polynomial (gamma * 2^s <= 2^-7, truncation < 2.4e-13 relative).
+ * The kernel value therefore differs from glibc's exp by at most 2.4e-13 relative - far inside the 1e-4 score
+ * tolerance (tests compare distances at 1e-9) - while the integer part of the computation is exact.
  *
  * Shared-memory operand layout (no swizzle, K-major): a core matrix is 8 rows x 16 bytes stored as 128 contiguous
  * bytes; core matrices adjacent in K are 128 bytes apart (descriptor LBO), groups of 8 rows SBO bytes apart.
@@ -52,7 +52,7 @@ constexpr int SD_ROWS = 128;      /* window rows per MMA (UMMA M) */
 constexpr int SD_MT = 2;          /* window tiles per pass */
 constexpr int SD_N = 128;         /* support vectors per accumulator block (UMMA N) */
 constexpr int SD_KCH = 8;         /* 16-byte k chunks per streamed support-vector block */
-constexpr int SD_STAGES = 4;
+constexpr int SD_STAGES = 3;
 constexpr int SD_B_STAGE_BYTES = (SD_N / 8) * SD_KCH * 128;
 constexpr int SD_PROD_WARPS = 4, SD_EPI_WARPS = 8;
 constexpr int SD_THREADS = 32 * (2 + SD_PROD_WARPS + SD_EPI_WARPS);
@@ -132,7 +132,7 @@ struct SvmDenseArgs {
 };
 
 /* A row of one window: HistEq64 (HistEq64Filter.cpp:32-125) from the layer image into the core-matrix layout */
-__device__ __forceinline__ int produce_window(const SvmDenseArgs& a, const DevLayer* sLayers, uint16_t* hist /* column of this thread */,
+__device__ __forceinline__ int produce_window(const SvmDenseArgs& a, const DevLayer* sLayers, uint32_t* hist /* column of this thread */,
 		uint8_t* arow /* A tile + row offset */, int64_t g) {
 	const int pw = a.patch_w, ph = a.patch_h, npix = pw * ph;
 	const int frame = (int)(g / a.windows_per_frame);
@@ -160,7 +160,7 @@ __device__ __forceinline__ int produce_window(const SvmDenseArgs& a, const DevLa
 		cdf = __fadd_rn(cdf, __fmul_rn((float)cnt, stretch));
 		const float fl = floorf(cdf);
 		const int eq = ((int)fl + (__fsub_rn(cdf, fl) >= 0.5f ? 1 : 0)) & 255; /* saturate_cast never triggers: cdf <= 255 */
-		hist[b * SD_ROWS] = (uint16_t)eq;
+		hist[b * SD_ROWS] = (uint32_t)eq;
 		xx += cnt * eq * eq;
 	}
 	int r = 0, c = 0;
@@ -177,6 +177,85 @@ __device__ __forceinline__ int produce_window(const SvmDenseArgs& a, const DevLa
 		}
 		*reinterpret_cast<uint4*>(arow + ch * 128) = make_uint4(wd[0], wd[1], wd[2], wd[3]);
 	}
+	return xx;
+}
+
+/* 4-pixel words of one patch row from an arbitrarily aligned address: aligned word loads + funnel shifts */
+template <int WPR>
+__device__ __forceinline__ void load_row_words(const uint8_t* p, uint32_t (&x)[WPR]) {
+	const uintptr_t ad = reinterpret_cast<uintptr_t>(p);
+	const uint32_t* wp = reinterpret_cast<const uint32_t*>(ad & ~(uintptr_t)3);
+	const uint32_t sh = (uint32_t)(ad & 3) * 8;
+	uint32_t w[WPR + 1];
+#pragma unroll
+	for (int i = 0; i < WPR; ++i) w[i] = __ldg(wp + i);
+	w[WPR] = sh ? __ldg(wp + WPR) : 0u; /* an aligned row ends inside word WPR - 1 */
+#pragma unroll
+	for (int i = 0; i < WPR; ++i) x[i] = __funnelshift_r(w[i], w[i + 1], sh);
+}
+
+/* the same for the patch sizes of ffpDetectApp (width and height multiples of 4): word loads, fire-and-forget
+ * shared-memory atomics for the histogram (no read-modify-write chains), 4 rows = PW / 4 whole 16-byte chunks */
+template <int PW, int PH>
+__device__ __forceinline__ int produce_window_fast(const SvmDenseArgs& a, const DevLayer* sLayers, uint32_t* hist,
+		uint8_t* arow, int64_t g) {
+	static_assert(PW % 4 == 0 && PH % 4 == 0, "patch sides must be multiples of 4");
+	constexpr int WPR = PW / 4, NPIX = PW * PH;
+	const int frame = (int)(g / a.windows_per_frame);
+	const int w = (int)(g - (int64_t)frame * a.windows_per_frame);
+	int li = 0;
+	while (li + 1 < a.n_layers && w >= sLayers[li + 1].first_window) ++li;
+	const DevLayer& L = sLayers[li];
+	const int local = w - L.first_window;
+	const int iy = local / L.windows_x, ix = local - iy * L.windows_x;
+	const int pitch = L.pitch;
+	const uint8_t* src = (L.offset < 0 ? a.frames + (int64_t)frame * a.W * a.H : a.arena + (int64_t)frame * a.arena_stride + L.offset)
+			+ (int64_t)(L.begin_y + iy * a.step_y) * pitch + (L.begin_x + ix * a.step_x);
+#pragma unroll 16
+	for (int b = 0; b < 64; ++b) hist[b * SD_ROWS] = 0u;
+#pragma unroll 2
+	for (int r = 0; r < PH; ++r) {
+		uint32_t x[WPR];
+		load_row_words<WPR>(src + (int64_t)r * pitch, x);
+#pragma unroll
+		for (int i = 0; i < WPR; ++i)
+#pragma unroll
+			for (int k = 0; k < 4; ++k) atomicAdd(&hist[((x[i] >> (8 * k + 2)) & 63u) * SD_ROWS], 1u);
+	}
+	/* sequential float32 cdf, rounded: HistEq64Filter.cpp:70-87,97 */
+	const float stretch = __fdiv_rn(255.0f, (float)NPIX);
+	float cdf = 0.f;
+	int xx = 0;
+#pragma unroll 8
+	for (int b = 0; b < 64; ++b) {
+		const int cnt = (int)hist[b * SD_ROWS];
+		cdf = __fadd_rn(cdf, __fmul_rn((float)cnt, stretch));
+		const float fl = floorf(cdf);
+		const int eq = ((int)fl + (__fsub_rn(cdf, fl) >= 0.5f ? 1 : 0)) & 255;
+		hist[b * SD_ROWS] = (uint32_t)eq;
+		xx += cnt * eq * eq;
+	}
+#pragma unroll 1
+	for (int r4 = 0; r4 < PH; r4 += 4) {
+		uint32_t o[4 * WPR];
+#pragma unroll
+		for (int rr = 0; rr < 4; ++rr) {
+			uint32_t x[WPR];
+			load_row_words<WPR>(src + (int64_t)(r4 + rr) * pitch, x);
+#pragma unroll
+			for (int i = 0; i < WPR; ++i) {
+				uint32_t e = hist[((x[i] >> 2) & 63u) * SD_ROWS];
+				e |= hist[((x[i] >> 10) & 63u) * SD_ROWS] << 8;
+				e |= hist[((x[i] >> 18) & 63u) * SD_ROWS] << 16;
+				e |= hist[(x[i] >> 26) * SD_ROWS] << 24;
+				o[rr * WPR + i] = e;
+			}
+		}
+#pragma unroll
+		for (int c = 0; c < WPR; ++c)
+			*reinterpret_cast<uint4*>(arow + ((r4 >> 2) * WPR + c) * 128) = make_uint4(o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]);
+	}
+	for (int ch = NPIX / 16; ch < a.s.chunks; ++ch) *reinterpret_cast<uint4*>(arow + ch * 128) = make_uint4(0u, 0u, 0u, 0u);
 	return xx;
 }
 
@@ -198,14 +277,15 @@ __device__ __forceinline__ int produce_vector(const SvmDenseArgs& a, uint8_t* ar
 	return xx;
 }
 
-template <int MODE> /* 0: windows of frames (HistEq64 built by the producers), 1: given u8 vectors */
+template <int MODE, bool CLAMP> /* MODE 0: windows of frames (HistEq64 built by the producers), 1: given u8 vectors;
+                                   CLAMP: the exp table ends at the underflow point instead of the largest possible ssd */
 __global__ void __launch_bounds__(SD_THREADS, 1) svm_dense_kernel(const __grid_constant__ SvmDenseArgs a) {
 	extern __shared__ __align__(128) unsigned char sd_smem[];
 	const int chunks = a.s.chunks;
 	const int a_tile = (SD_ROWS / 8) * chunks * 128;
 	uint8_t* sA = sd_smem;
 	uint8_t* sB = sA + SD_MT * a_tile;
-	uint16_t* sHist = reinterpret_cast<uint16_t*>(sB + SD_STAGES * SD_B_STAGE_BYTES);   /* [64][SD_ROWS] */
+	uint32_t* sHist = reinterpret_cast<uint32_t*>(sB + SD_STAGES * SD_B_STAGE_BYTES);   /* [64][SD_ROWS] */
 	double* sTab = reinterpret_cast<double*>(sHist + 64 * SD_ROWS);                    /* [tab_n] */
 	int* sXX = reinterpret_cast<int*>(sTab + a.s.tab_n);                               /* [2][SD_PASS_ROWS] */
 	DevLayer* sLayers = reinterpret_cast<DevLayer*>(sXX + 2 * SD_PASS_ROWS);
@@ -300,7 +380,8 @@ __global__ void __launch_bounds__(SD_THREADS, 1) svm_dense_kernel(const __grid_c
 	} else if (warp < 2 + SD_PROD_WARPS) {
 		/* ===== A operand producers: thread = window row ===== */
 		const int t = tid - 64;
-		uint16_t* hist = sHist + t;
+		uint32_t* hist = sHist + t;
+		const bool fast20 = a.patch_w == 20 && a.patch_h == 20;
 		uint32_t pass_it = 0;
 		for (int64_t pass = blockIdx.x; pass < npass; pass += gridDim.x, ++pass_it) {
 			mbar_wait(bar(BAR_A_EMPTY), (pass_it & 1) ^ 1);
@@ -310,7 +391,9 @@ __global__ void __launch_bounds__(SD_THREADS, 1) svm_dense_kernel(const __grid_c
 				uint8_t* arow = sA + m * a_tile + (t >> 3) * (chunks * 128) + (t & 7) * 16;
 				int xx = 0;
 				if (g < a.total) {
-					xx = MODE == 0 ? produce_window(a, sLayers, hist, arow, g) : produce_vector(a, arow, g);
+					if (MODE == 1) xx = produce_vector(a, arow, g);
+					else if (fast20) xx = produce_window_fast<20, 20>(a, sLayers, hist, arow, g);
+					else xx = produce_window(a, sLayers, hist, arow, g);
 				} else {
 					for (int ch = 0; ch < chunks; ++ch) *reinterpret_cast<uint4*>(arow + ch * 128) = make_uint4(0u, 0u, 0u, 0u);
 				}
@@ -327,7 +410,7 @@ __global__ void __launch_bounds__(SD_THREADS, 1) svm_dense_kernel(const __grid_c
 		const int s_shift = a.s.shift;
 		const uint32_t lo_mask = (1u << s_shift) - 1u;
 		const int tab_last = a.s.tab_n - 1;
-		const double c1 = a.s.poly[0], c2 = a.s.poly[1], c3 = a.s.poly[2], c4 = a.s.poly[3], c5 = a.s.poly[4];
+		const double c1 = a.s.poly[0], c2 = a.s.poly[1], c3 = a.s.poly[2], c4 = a.s.poly[3];
 		const int* __restrict__ ssq = a.s.ssq;
 		const double* __restrict__ coef = a.s.coef;
 		uint32_t acc_it = 0, pass_it = 0;
@@ -362,9 +445,9 @@ __global__ void __launch_bounds__(SD_THREADS, 1) svm_dense_kernel(const __grid_c
 						for (int k = 0; k < 4; ++k) {
 							const int ssd = xx + ss[k] - 2 * (int)v[4 * j4 + k];
 							const double l = (double)(int)(ssd & lo_mask);
-							const int hi = min(ssd >> s_shift, tab_last);
-							double p = fma(l, c5, c4);
-							p = fma(l, p, c3);
+							int hi = ssd >> s_shift;
+							if (CLAMP) hi = min(hi, tab_last);
+							double p = fma(l, c4, c3);
 							p = fma(l, p, c2);
 							p = fma(l, p, c1);
 							p = fma(l, p, 1.0);
@@ -399,7 +482,7 @@ __global__ void __launch_bounds__(SD_THREADS, 1) svm_dense_kernel(const __grid_c
 
 size_t sd_smem_bytes(const DevSvmDense& s) {
 	const size_t a_tile = (size_t)(SD_ROWS / 8) * s.chunks * 128;
-	return SD_MT * a_tile + (size_t)SD_STAGES * SD_B_STAGE_BYTES + 64 * SD_ROWS * sizeof(uint16_t) + (size_t)s.tab_n * 8
+	return SD_MT * a_tile + (size_t)SD_STAGES * SD_B_STAGE_BYTES + 64 * SD_ROWS * sizeof(uint32_t) + (size_t)s.tab_n * 8
 			+ 2 * SD_PASS_ROWS * sizeof(int) + FDB_MAX_LAYERS * sizeof(DevLayer) + BAR_COUNT * 8 + 16;
 }
 
@@ -416,8 +499,10 @@ int svm_dense_configure() {
 	g_sd_sms = v;
 	if (e == cudaSuccess) e = cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
 	g_sd_smem_max = (size_t)v;
-	if (e == cudaSuccess) e = cudaFuncSetAttribute(svm_dense_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, v);
-	if (e == cudaSuccess) e = cudaFuncSetAttribute(svm_dense_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, v);
+	if (e == cudaSuccess) e = cudaFuncSetAttribute(svm_dense_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, v);
+	if (e == cudaSuccess) e = cudaFuncSetAttribute(svm_dense_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, v);
+	if (e == cudaSuccess) e = cudaFuncSetAttribute(svm_dense_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, v);
+	if (e == cudaSuccess) e = cudaFuncSetAttribute(svm_dense_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, v);
 	return (int)e;
 }
 
@@ -446,9 +531,10 @@ bool svm_dense_build(const uint8_t* sv, const float* coef, int num_sv, int dim, 
 	d.tab_n = (int)entries;
 	h.tab.resize((size_t)entries);
 	for (int64_t i = 0; i < entries; ++i) h.tab[(size_t)i] = std::exp(-gamma * (double)(i << shift));
-	if (top < max_ssd) h.tab[(size_t)entries - 1] = 0.0; /* everything past the underflow point */
+	d.clamp = top < max_ssd ? 1 : 0;
+	if (d.clamp) h.tab[(size_t)entries - 1] = 0.0; /* everything past the underflow point */
 	long double f = 1.0L, gk = 1.0L;
-	for (int k = 1; k <= 5; ++k) { f *= k; gk *= -(long double)gamma; d.poly[k - 1] = (double)(gk / f); }
+	for (int k = 1; k <= 4; ++k) { f *= k; gk *= -(long double)gamma; d.poly[k - 1] = (double)(gk / f); }
 	if (sd_smem_bytes(d) > (g_sd_smem_max ? g_sd_smem_max : (size_t)232448)) return false;
 	/* support vectors as core matrices: [n block][k block][group of 8 rows][k chunk][row][16 bytes] */
 	const int NT = d.num_sv_pad / SD_N, KB = (d.chunks + SD_KCH - 1) / SD_KCH;
@@ -503,7 +589,8 @@ void launch_svm_dense_windows(cudaStream_t st, const DevSvmDense& s, int patch_w
 	a.layers = layers; a.n_layers = n_layers; a.windows_per_frame = windows_per_frame;
 	a.total = total; a.distance_out = distance_out; a.pos_count = pos_count; a.pos = pos; a.pos_cap = pos_cap;
 	a.desc_swap = dense_desc_swap();
-	svm_dense_kernel<0><<<dense_grid(total), SD_THREADS, sd_smem_bytes(s), st>>>(a);
+	if (s.clamp) svm_dense_kernel<0, true><<<dense_grid(total), SD_THREADS, sd_smem_bytes(s), st>>>(a);
+	else svm_dense_kernel<0, false><<<dense_grid(total), SD_THREADS, sd_smem_bytes(s), st>>>(a);
 }
 
 void launch_svm_dense_vectors(cudaStream_t st, const DevSvmDense& s, const uint8_t* vectors, int64_t n, double* distance_out) {
@@ -511,7 +598,8 @@ void launch_svm_dense_vectors(cudaStream_t st, const DevSvmDense& s, const uint8
 	SvmDenseArgs a{};
 	a.s = s; a.vectors = vectors; a.total = n; a.distance_out = distance_out; a.windows_per_frame = n;
 	a.desc_swap = dense_desc_swap();
-	svm_dense_kernel<1><<<dense_grid(n), SD_THREADS, sd_smem_bytes(s), st>>>(a);
+	if (s.clamp) svm_dense_kernel<1, true><<<dense_grid(n), SD_THREADS, sd_smem_bytes(s), st>>>(a);
+	else svm_dense_kernel<1, false><<<dense_grid(n), SD_THREADS, sd_smem_bytes(s), st>>>(a);
 }
 
 } // namespace fdb

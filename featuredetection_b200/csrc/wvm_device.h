@@ -88,9 +88,10 @@ struct DevSvmDense {
 	int num_sv_pad;            /* support vectors padded to a multiple of 256 (zero vectors with coefficient 0) */
 	int dim, chunks;           /* elements per vector; 16-byte k chunks per row (2 * ceil(dim / 32), zero padded) */
 	int shift, tab_n;          /* ssd = hi << shift | lo; exp_tab[hi] = exp(-gamma * (hi << shift)), tab_n entries */
+	int clamp;                 /* 1: the table ends at the underflow point (hi is clamped to the last, zero, entry) */
 	float threshold;
 	double neg_bias;
-	double poly[5];            /* (-gamma)^k / k!, k = 1..5: exp(-gamma * lo) */
+	double poly[4];            /* (-gamma)^k / k!, k = 1..4: exp(-gamma * lo) */
 	const uint8_t* b_blocks;   /* [n block of 128][k block]{[16 row groups][chunks in block][8 rows][16 bytes]} */
 	const int* ssq;            /* [num_sv_pad] */
 	const double* coef;        /* [num_sv_pad] */

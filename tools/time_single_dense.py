@@ -8,6 +8,11 @@ from featuredetection_b200.detector import Context, SlidingWindowCascade
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 ctx = Context(0)
 det_kw, _, svm = syn.landmark_models("FaceFrontal")
+probe = SlidingWindowCascade(ctx, det_kw, None, svm)
+probe.prepare(640, 480, 1)
+_, d0 = probe.detect_single(syn.synthetic_frames(0, 1))
+svm.threshold = float(np.float32(np.quantile(d0, 0.999)))  # ~0.1 % of the windows positive
+del probe
 c = SlidingWindowCascade(ctx, det_kw, None, svm)
 c.prepare(640, 480, n)
 assert c.single_dense
