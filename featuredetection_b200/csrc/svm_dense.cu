@@ -49,20 +49,22 @@ namespace fdb {
 namespace {
 
 constexpr int SD_ROWS = 128;      /* window rows per MMA (UMMA M) */
-constexpr int SD_MT = 2;          /* window tiles per pass */
+constexpr int SD_ABUF = 2;        /* window tiles in shared memory: one being multiplied, one being produced */
+constexpr int SD_ACC = 4;         /* accumulator blocks in tensor memory (4 x 128 columns) */
+constexpr int SD_EPI_SPLIT = 4;   /* epilogue threads per window row */
+constexpr int SD_XX_RING = 8;     /* |x|^2 slots (tiles the producers may be ahead of the epilogue) */
 constexpr int SD_N = 128;         /* support vectors per accumulator block (UMMA N) */
 constexpr int SD_KCH = 8;         /* 16-byte k chunks per streamed support-vector block */
 constexpr int SD_STAGES = 3;
 constexpr int SD_B_STAGE_BYTES = (SD_N / 8) * SD_KCH * 128;
-constexpr int SD_PROD_WARPS = 4, SD_EPI_WARPS = 8;
+constexpr int SD_PROD_WARPS = 4, SD_EPI_WARPS = 4 * SD_EPI_SPLIT;
 constexpr int SD_THREADS = 32 * (2 + SD_PROD_WARPS + SD_EPI_WARPS);
 constexpr int SD_TMEM_COLS = 512;
-constexpr int SD_PASS_ROWS = SD_ROWS * SD_MT;
-constexpr int SD_SPIN_LIMIT = 1 << 26;
+constexpr int SD_SPIN_LIMIT = 1 << 24;
 
 /* barrier slots */
-enum { BAR_B_FULL = 0, BAR_B_EMPTY = SD_STAGES, BAR_A_FULL = 2 * SD_STAGES, BAR_A_EMPTY = 2 * SD_STAGES + 2,
-	BAR_T_FULL = 2 * SD_STAGES + 3, BAR_T_EMPTY = 2 * SD_STAGES + 5, BAR_COUNT = 2 * SD_STAGES + 7 };
+enum { BAR_B_FULL = 0, BAR_B_EMPTY = SD_STAGES, BAR_A_FULL = 2 * SD_STAGES, BAR_A_EMPTY = BAR_A_FULL + SD_ABUF,
+	BAR_T_FULL = BAR_A_EMPTY + SD_ABUF, BAR_T_EMPTY = BAR_T_FULL + SD_ACC, BAR_COUNT = BAR_T_EMPTY + SD_ACC };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -75,16 +77,21 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
 }
-/* bounded wait: a protocol error traps instead of hanging the device */
+/* bounded wait: a protocol error traps instead of hanging the device. SLEEP_NS > 0 backs off between polls so that
+ * waiting warps leave the issue slots to the warps that have work (try_wait returns at once on this part). */
+template <int SLEEP_NS>
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 	uint32_t done;
 	int spins = 0;
 	do {
 		asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
 				: "=r"(done) : "r"(bar), "r"(parity) : "memory");
-		if (!done && ++spins > SD_SPIN_LIMIT) {
-			printf("svm_dense_kernel: barrier %u timed out (block %d thread %d)\n", bar, blockIdx.x, threadIdx.x);
-			__trap();
+		if (!done) {
+			if (SLEEP_NS > 0) __nanosleep(SLEEP_NS);
+			if (++spins > SD_SPIN_LIMIT) {
+				printf("svm_dense_kernel: barrier %u timed out (block %d thread %d)\n", bar, blockIdx.x, threadIdx.x);
+				__trap();
+			}
 		}
 	} while (!done);
 }
@@ -283,12 +290,13 @@ __global__ void __launch_bounds__(SD_THREADS, 1) svm_dense_kernel(const __grid_c
 	extern __shared__ __align__(128) unsigned char sd_smem[];
 	const int chunks = a.s.chunks;
 	const int a_tile = (SD_ROWS / 8) * chunks * 128;
-	uint8_t* sA = sd_smem;
-	uint8_t* sB = sA + SD_MT * a_tile;
+	uint8_t* sA = sd_smem;                                                             /* [SD_ABUF] window tiles */
+	uint8_t* sB = sA + SD_ABUF * a_tile;                                               /* [SD_STAGES] support-vector blocks */
 	uint32_t* sHist = reinterpret_cast<uint32_t*>(sB + SD_STAGES * SD_B_STAGE_BYTES);   /* [64][SD_ROWS] */
 	double* sTab = reinterpret_cast<double*>(sHist + 64 * SD_ROWS);                    /* [tab_n] */
-	int* sXX = reinterpret_cast<int*>(sTab + a.s.tab_n);                               /* [2][SD_PASS_ROWS] */
-	DevLayer* sLayers = reinterpret_cast<DevLayer*>(sXX + 2 * SD_PASS_ROWS);
+	double* sPart = sTab + a.s.tab_n;                                                  /* [2][SD_EPI_SPLIT][SD_ROWS] */
+	int* sXX = reinterpret_cast<int*>(sPart + 2 * SD_EPI_SPLIT * SD_ROWS);             /* [SD_XX_RING][SD_ROWS] */
+	DevLayer* sLayers = reinterpret_cast<DevLayer*>(sXX + SD_XX_RING * SD_ROWS);
 	uint64_t* bars = reinterpret_cast<uint64_t*>(sLayers + FDB_MAX_LAYERS);
 	uint32_t* sTmem = reinterpret_cast<uint32_t*>(bars + BAR_COUNT);
 
@@ -298,9 +306,8 @@ __global__ void __launch_bounds__(SD_THREADS, 1) svm_dense_kernel(const __grid_c
 
 	if (tid == 0) {
 		for (int i = 0; i < SD_STAGES; ++i) { mbar_init(bar(BAR_B_FULL + i), 1); mbar_init(bar(BAR_B_EMPTY + i), 1); }
-		mbar_init(bar(BAR_A_FULL), SD_ROWS); mbar_init(bar(BAR_A_FULL + 1), SD_ROWS);
-		mbar_init(bar(BAR_A_EMPTY), 1);
-		for (int i = 0; i < 2; ++i) { mbar_init(bar(BAR_T_FULL + i), 1); mbar_init(bar(BAR_T_EMPTY + i), SD_EPI_WARPS); }
+		for (int i = 0; i < SD_ABUF; ++i) { mbar_init(bar(BAR_A_FULL + i), SD_ROWS); mbar_init(bar(BAR_A_EMPTY + i), 1); }
+		for (int i = 0; i < SD_ACC; ++i) { mbar_init(bar(BAR_T_FULL + i), 1); mbar_init(bar(BAR_T_EMPTY + i), SD_EPI_WARPS); }
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	}
 	if (warp == 1) {
@@ -314,23 +321,23 @@ __global__ void __launch_bounds__(SD_THREADS, 1) svm_dense_kernel(const __grid_c
 	tc_fence_after();
 	const uint32_t tmem = *sTmem;
 
-	const int64_t npass = (a.total + SD_PASS_ROWS - 1) / SD_PASS_ROWS;
+	const int64_t ntiles = (a.total + SD_ROWS - 1) / SD_ROWS;
 	const int NT = a.s.num_sv_pad / SD_N;
 	const int KB = (chunks + SD_KCH - 1) / SD_KCH;
 
 	if (warp == 0) {
-		/* ===== support-vector block stream ===== */
+		/* ===== support-vector block stream: the whole model once per window tile, from L2 ===== */
 		if (lane == 0) {
 			uint32_t it = 0;
 			const size_t nblock_bytes = (size_t)(SD_N / 8) * chunks * 128;
-			for (int64_t pass = blockIdx.x; pass < npass; pass += gridDim.x) {
+			for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
 				for (int nt = 0; nt < NT; ++nt) {
 					const uint8_t* src = a.s.b_blocks + (size_t)nt * nblock_bytes;
 					for (int kb = 0; kb < KB; ++kb, ++it) {
 						const int cb = min(SD_KCH, chunks - kb * SD_KCH);
 						const uint32_t bytes = (uint32_t)(SD_N / 8) * cb * 128;
 						const int stage = it % SD_STAGES;
-						mbar_wait(bar(BAR_B_EMPTY + stage), ((it / SD_STAGES) & 1) ^ 1);
+						mbar_wait<32>(bar(BAR_B_EMPTY + stage), ((it / SD_STAGES) & 1) ^ 1);
 						mbar_expect_tx(bar(BAR_B_FULL + stage), bytes);
 						asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
 								:: "r"(smem_u32(sB + stage * SD_B_STAGE_BYTES)), "l"(src), "r"(bytes), "r"(bar(BAR_B_FULL + stage)) : "memory");
@@ -346,66 +353,63 @@ __global__ void __launch_bounds__(SD_THREADS, 1) svm_dense_kernel(const __grid_c
 			const uint32_t idesc = (2u << 4) | ((uint32_t)(SD_N >> 3) << 17) | ((uint32_t)(SD_ROWS >> 4) << 24);
 			const uint32_t a_addr = smem_u32(sA), b_addr = smem_u32(sB);
 			const uint32_t a_sbo = (uint32_t)chunks * 128;
-			uint32_t it = 0, acc_it = 0, pass_it = 0;
-			for (int64_t pass = blockIdx.x; pass < npass; pass += gridDim.x, ++pass_it) {
-				mbar_wait(bar(BAR_A_FULL + (pass_it & 1)), (pass_it >> 1) & 1);
+			uint32_t it = 0, acc_it = 0, tile_it = 0;
+			for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tile_it) {
+				const uint32_t abuf = tile_it % SD_ABUF;
+				mbar_wait<32>(bar(BAR_A_FULL + abuf), (tile_it / SD_ABUF) & 1);
 				tc_fence_after();
 				for (int nt = 0; nt < NT; ++nt, ++acc_it) {
-					const uint32_t buf = acc_it & 1;
-					mbar_wait(bar(BAR_T_EMPTY + buf), ((acc_it >> 1) & 1) ^ 1);
+					const uint32_t acc = acc_it % SD_ACC;
+					mbar_wait<32>(bar(BAR_T_EMPTY + acc), ((acc_it / SD_ACC) & 1) ^ 1);
 					tc_fence_after();
 					for (int kb = 0; kb < KB; ++kb, ++it) {
 						const int cb = min(SD_KCH, chunks - kb * SD_KCH);
 						const int stage = it % SD_STAGES;
-						mbar_wait(bar(BAR_B_FULL + stage), (it / SD_STAGES) & 1);
+						mbar_wait<0>(bar(BAR_B_FULL + stage), (it / SD_STAGES) & 1);
 						tc_fence_after();
 						const uint32_t b_sbo = (uint32_t)cb * 128;
 						for (int ks = 0; ks < cb / 2; ++ks) {
 							const uint32_t bstart = b_addr + stage * SD_B_STAGE_BYTES + ks * 256;
+							const uint32_t astart = a_addr + abuf * a_tile + (kb * SD_KCH + 2 * ks) * 128;
 							const uint64_t bdesc = a.desc_swap ? tc_desc(bstart, b_sbo, 128) : tc_desc(bstart, 128, b_sbo);
-#pragma unroll
-							for (int m = 0; m < SD_MT; ++m) {
-								const uint32_t astart = a_addr + m * a_tile + (kb * SD_KCH + 2 * ks) * 128;
-								const uint64_t adesc = a.desc_swap ? tc_desc(astart, a_sbo, 128) : tc_desc(astart, 128, a_sbo);
-								tc_mma_i8(tmem + buf * (SD_MT * SD_N) + m * SD_N, adesc, bdesc, idesc, (kb | ks) != 0 ? 1u : 0u);
-							}
+							const uint64_t adesc = a.desc_swap ? tc_desc(astart, a_sbo, 128) : tc_desc(astart, 128, a_sbo);
+							tc_mma_i8(tmem + acc * SD_N, adesc, bdesc, idesc, (kb | ks) != 0 ? 1u : 0u);
 						}
 						tc_commit(bar(BAR_B_EMPTY + stage)); /* the ring slot is free once these MMAs have read it */
 					}
-					tc_commit(bar(BAR_T_FULL + buf));
+					tc_commit(bar(BAR_T_FULL + acc));
 				}
-				tc_commit(bar(BAR_A_EMPTY));
+				tc_commit(bar(BAR_A_EMPTY + abuf));
 			}
 		}
 	} else if (warp < 2 + SD_PROD_WARPS) {
-		/* ===== A operand producers: thread = window row ===== */
+		/* ===== A operand producers: thread = window row; tile i + 1 is built while tile i is multiplied and summed ===== */
 		const int t = tid - 64;
 		uint32_t* hist = sHist + t;
 		const bool fast20 = a.patch_w == 20 && a.patch_h == 20;
-		uint32_t pass_it = 0;
-		for (int64_t pass = blockIdx.x; pass < npass; pass += gridDim.x, ++pass_it) {
-			mbar_wait(bar(BAR_A_EMPTY), (pass_it & 1) ^ 1);
-#pragma unroll 1
-			for (int m = 0; m < SD_MT; ++m) {
-				const int64_t g = pass * SD_PASS_ROWS + m * SD_ROWS + t;
-				uint8_t* arow = sA + m * a_tile + (t >> 3) * (chunks * 128) + (t & 7) * 16;
-				int xx = 0;
-				if (g < a.total) {
-					if (MODE == 1) xx = produce_vector(a, arow, g);
-					else if (fast20) xx = produce_window_fast<20, 20>(a, sLayers, hist, arow, g);
-					else xx = produce_window(a, sLayers, hist, arow, g);
-				} else {
-					for (int ch = 0; ch < chunks; ++ch) *reinterpret_cast<uint4*>(arow + ch * 128) = make_uint4(0u, 0u, 0u, 0u);
-				}
-				sXX[(pass_it & 1) * SD_PASS_ROWS + m * SD_ROWS + t] = xx;
+		uint32_t tile_it = 0;
+		for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tile_it) {
+			const uint32_t abuf = tile_it % SD_ABUF;
+			mbar_wait<128>(bar(BAR_A_EMPTY + abuf), ((tile_it / SD_ABUF) & 1) ^ 1);
+			const int64_t g = tile * SD_ROWS + t;
+			uint8_t* arow = sA + abuf * a_tile + (t >> 3) * (chunks * 128) + (t & 7) * 16;
+			int xx = 0;
+			if (g < a.total) {
+				if (MODE == 1) xx = produce_vector(a, arow, g);
+				else if (fast20) xx = produce_window_fast<20, 20>(a, sLayers, hist, arow, g);
+				else xx = produce_window(a, sLayers, hist, arow, g);
+			} else {
+				for (int ch = 0; ch < chunks; ++ch) *reinterpret_cast<uint4*>(arow + ch * 128) = make_uint4(0u, 0u, 0u, 0u);
 			}
+			/* the ring is deeper than the producers can run ahead of the epilogue (SD_ABUF tiles + SD_ACC blocks) */
+			sXX[(tile_it % SD_XX_RING) * SD_ROWS + t] = xx;
 			asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); /* generic-proxy stores -> visible to the tensor core */
-			mbar_arrive(bar(BAR_A_FULL + (pass_it & 1)));
+			mbar_arrive(bar(BAR_A_FULL + abuf));
 		}
 	} else {
-		/* ===== epilogue: thread = window row of tile m ===== */
+		/* ===== epilogue: SD_EPI_SPLIT threads per window row, each owning every SD_EPI_SPLIT-th group of 32 support vectors ===== */
 		const int e = warp - (2 + SD_PROD_WARPS);
-		const int m = e >> 2, q = warp & 3;       /* a warp reads the tensor-memory lanes 32 * (warp id % 4) .. + 31 */
+		const int part = e >> 2, q = warp & 3;    /* a warp reads the tensor-memory lanes 32 * (warp id % 4) .. + 31 */
 		const int row = q * 32 + lane;
 		const int s_shift = a.s.shift;
 		const uint32_t lo_mask = (1u << s_shift) - 1u;
@@ -413,58 +417,61 @@ __global__ void __launch_bounds__(SD_THREADS, 1) svm_dense_kernel(const __grid_c
 		const double c1 = a.s.poly[0], c2 = a.s.poly[1], c3 = a.s.poly[2], c4 = a.s.poly[3];
 		const int* __restrict__ ssq = a.s.ssq;
 		const double* __restrict__ coef = a.s.coef;
-		uint32_t acc_it = 0, pass_it = 0;
-		for (int64_t pass = blockIdx.x; pass < npass; pass += gridDim.x, ++pass_it) {
-			mbar_wait(bar(BAR_A_FULL + (pass_it & 1)), (pass_it >> 1) & 1);
-			const int xx = sXX[(pass_it & 1) * SD_PASS_ROWS + m * SD_ROWS + row];
-			double dist = a.s.neg_bias; /* SvmClassifier.cpp:56: double distance = -bias */
+		uint32_t acc_it = 0, tile_it = 0;
+		for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tile_it) {
+			int xx = 0;
+			double dist = 0.0;
 			for (int nt = 0; nt < NT; ++nt, ++acc_it) {
-				const uint32_t buf = acc_it & 1;
-				mbar_wait(bar(BAR_T_FULL + buf), (acc_it >> 1) & 1);
+				const uint32_t acc = acc_it % SD_ACC;
+				mbar_wait<64>(bar(BAR_T_FULL + acc), (acc_it / SD_ACC) & 1);
 				tc_fence_after();
-				const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + buf * (SD_MT * SD_N) + m * SD_N;
-#pragma unroll 1
-				for (int cq = 0; cq < SD_N / 32; ++cq) {
-					uint32_t v[32];
-					tc_ld32(taddr + cq * 32, v);
-					if (cq == SD_N / 32 - 1) { /* accumulators are in registers: hand the buffer back to the MMA warp */
-						tc_fence_before();
-						__syncwarp();
-						if (lane == 0) mbar_arrive(bar(BAR_T_EMPTY + buf));
-					}
-					const int sv0 = nt * SD_N + cq * 32;
-					const int4* __restrict__ s4p = reinterpret_cast<const int4*>(ssq + sv0);       /* warp-uniform vector loads */
-					const double2* __restrict__ c2p = reinterpret_cast<const double2*>(coef + sv0);
+				if (nt == 0) xx = sXX[(tile_it % SD_XX_RING) * SD_ROWS + row]; /* written before the tile's first MMA was issued */
+				uint32_t v[32];
+				tc_ld32(tmem + ((uint32_t)(q * 32) << 16) + acc * SD_N + part * 32, v);
+				/* accumulators are in registers: hand the buffer back to the MMA warp */
+				tc_fence_before();
+				__syncwarp();
+				if (lane == 0) mbar_arrive(bar(BAR_T_EMPTY + acc));
+				const int sv0 = nt * SD_N + part * 32;
+				const int4* __restrict__ s4p = reinterpret_cast<const int4*>(ssq + sv0);       /* warp-uniform vector loads */
+				const double2* __restrict__ c2p = reinterpret_cast<const double2*>(coef + sv0);
 #pragma unroll
-					for (int j4 = 0; j4 < 8; ++j4) {
-						const int4 s4 = __ldg(s4p + j4);
-						const double2 ca = __ldg(c2p + 2 * j4), cb = __ldg(c2p + 2 * j4 + 1);
-						const int ss[4] = {s4.x, s4.y, s4.z, s4.w};
-						const double cc[4] = {ca.x, ca.y, cb.x, cb.y};
+				for (int j4 = 0; j4 < 8; ++j4) {
+					const int4 s4 = __ldg(s4p + j4);
+					const double2 ca = __ldg(c2p + 2 * j4), cb = __ldg(c2p + 2 * j4 + 1);
+					const int ss[4] = {s4.x, s4.y, s4.z, s4.w};
+					const double cc[4] = {ca.x, ca.y, cb.x, cb.y};
 #pragma unroll
-						for (int k = 0; k < 4; ++k) {
-							const int ssd = xx + ss[k] - 2 * (int)v[4 * j4 + k];
-							const double l = (double)(int)(ssd & lo_mask);
-							int hi = ssd >> s_shift;
-							if (CLAMP) hi = min(hi, tab_last);
-							double p = fma(l, c4, c3);
-							p = fma(l, p, c2);
-							p = fma(l, p, c1);
-							p = fma(l, p, 1.0);
-							const double kv = __dmul_rn(sTab[hi], p);         /* RbfKernel.hpp:39 */
-							dist = fma(cc[k], kv, dist);                      /* SvmClassifier.cpp:58, in support-vector order */
-						}
+					for (int k = 0; k < 4; ++k) {
+						const int ssd = xx + ss[k] - 2 * (int)v[4 * j4 + k];
+						/* exact int -> double without the conversion unit: 2^52 + lo as raw bits, minus 2^52 */
+						const double l = __dsub_rn(__hiloint2double(0x43300000, (int)(ssd & lo_mask)), 4503599627370496.0);
+						int hi = ssd >> s_shift;
+						if (CLAMP) hi = min(hi, tab_last);
+						double p = fma(l, c4, c3);
+						p = fma(l, p, c2);
+						p = fma(l, p, c1);
+						p = fma(l, p, 1.0);
+						const double kv = __dmul_rn(sTab[hi], p);         /* RbfKernel.hpp:39 */
+						dist = fma(cc[k], kv, dist);                      /* SvmClassifier.cpp:58 */
 					}
 				}
 			}
-			const int64_t g = pass * SD_PASS_ROWS + m * SD_ROWS + row;
-			if (g < a.total) {
-				a.distance_out[g] = dist;
-				if (a.pos_count && dist >= (double)a.s.threshold) { /* SvmClassifier::classify (SvmClassifier.cpp:44-46) */
+			/* the SD_EPI_SPLIT partial sums of a row, added in a fixed order */
+			double* pbuf = sPart + (tile_it & 1) * (SD_EPI_SPLIT * SD_ROWS);
+			pbuf[part * SD_ROWS + row] = dist;
+			asm volatile("bar.sync 1, %0;" :: "n"(SD_EPI_WARPS * 32) : "memory");
+			const int64_t g = tile * SD_ROWS + row;
+			if (part == 0 && g < a.total) {
+				double d = a.s.neg_bias; /* SvmClassifier.cpp:56: double distance = -bias */
+#pragma unroll
+				for (int i = 0; i < SD_EPI_SPLIT; ++i) d = __dadd_rn(d, pbuf[i * SD_ROWS + row]);
+				a.distance_out[g] = d;
+				if (a.pos_count && d >= (double)a.s.threshold) { /* SvmClassifier::classify (SvmClassifier.cpp:44-46) */
 					const int slot = atomicAdd(a.pos_count, 1);
 					if (slot < a.pos_cap) {
 						DensePositive dp;
-						dp.row = g; dp.distance = dist;
+						dp.row = g; dp.distance = d;
 						a.pos[slot] = dp;
 					}
 				}
@@ -482,8 +489,9 @@ __global__ void __launch_bounds__(SD_THREADS, 1) svm_dense_kernel(const __grid_c
 
 size_t sd_smem_bytes(const DevSvmDense& s) {
 	const size_t a_tile = (size_t)(SD_ROWS / 8) * s.chunks * 128;
-	return SD_MT * a_tile + (size_t)SD_STAGES * SD_B_STAGE_BYTES + 64 * SD_ROWS * sizeof(uint32_t) + (size_t)s.tab_n * 8
-			+ 2 * SD_PASS_ROWS * sizeof(int) + FDB_MAX_LAYERS * sizeof(DevLayer) + BAR_COUNT * 8 + 16;
+	return SD_ABUF * a_tile + (size_t)SD_STAGES * SD_B_STAGE_BYTES + 64 * SD_ROWS * sizeof(uint32_t) + (size_t)s.tab_n * 8
+			+ 2 * SD_EPI_SPLIT * SD_ROWS * sizeof(double) + SD_XX_RING * SD_ROWS * sizeof(int) + FDB_MAX_LAYERS * sizeof(DevLayer)
+			+ BAR_COUNT * 8 + 16;
 }
 
 int g_sd_sms = 0;
@@ -569,8 +577,8 @@ bool svm_dense_enabled() {
 }
 
 static int dense_grid(int64_t total) {
-	const int64_t npass = (total + SD_PASS_ROWS - 1) / SD_PASS_ROWS;
-	return (int)std::min<int64_t>(npass, g_sd_sms > 0 ? g_sd_sms : 148);
+	const int64_t ntiles = (total + SD_ROWS - 1) / SD_ROWS;
+	return (int)std::min<int64_t>(ntiles, g_sd_sms > 0 ? g_sd_sms : 148);
 }
 
 static uint32_t dense_desc_swap() {
