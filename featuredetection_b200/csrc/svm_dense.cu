@@ -13,15 +13,15 @@
  * (window, support vector) pairs is the matrix product [windows x pixels] . [pixels x support vectors] of u8 operands
  * with s32 accumulation - exact on the integer tensor cores (400 * 255 * 255 < 2^31).
  *
- * One persistent CTA per SM, 14 warps with fixed roles:
+ * One persistent CTA per SM, 18 warps with fixed roles:
  *   warp 0      streams the support-vector blocks (pre-arranged on the host as UMMA core matrices) from L2 into a
- *               3-stage shared-memory ring with cp.async.bulk + mbarrier complete_tx
+ *               4-stage shared-memory ring with cp.async.bulk + mbarrier complete_tx
  *   warp 1      owns tensor memory (512 columns) and issues tcgen05.mma (one lane): 2 window tiles of 128 rows share
  *               every support-vector block; two accumulator buffers of 2 x 128 columns alternate between MMA and epilogue
- *   warps 2-5   producers of the A operand: thread = window; HistEq64 of the window straight from the pyramid layer
+ *   warps 2-9   producers of the A operand (two sets of 4 warps, one per A buffer): thread = window; HistEq64 of the window straight from the pyramid layer
  *               (float32 cdf in the reference's order, like the other kernels), equalised pixels written to shared
  *               memory as 8x16-byte core matrices, |x|^2 from the histogram; no equalised patch ever touches HBM
- *   warps 6-13  epilogue: thread = window row (tcgen05.ld 32 lanes x 32 columns), ssd = |x|^2 + |sv|^2 - 2 dot,
+ *   warps 10-17 epilogue: thread = window row (tcgen05.ld 32 lanes x 32 columns), ssd = |x|^2 + |sv|^2 - 2 dot,
  *               k = exp(-gamma ssd) in float64, distance accumulated in float64 IN SUPPORT-VECTOR ORDER (one thread
  *               owns one window for all support vectors, so the order of the reference's loop is kept)
  *
@@ -51,13 +51,15 @@ namespace {
 constexpr int SD_ROWS = 128;      /* window rows per MMA (UMMA M) */
 constexpr int SD_ABUF = 2;        /* window tiles in shared memory: one being multiplied, one being produced */
 constexpr int SD_ACC = 4;         /* accumulator blocks in tensor memory (4 x 128 columns) */
-constexpr int SD_EPI_SPLIT = 4;   /* epilogue threads per window row */
+constexpr int SD_EPI_SPLIT = 2;   /* epilogue threads per window row */
 constexpr int SD_XX_RING = 8;     /* |x|^2 slots (tiles the producers may be ahead of the epilogue) */
 constexpr int SD_N = 128;         /* support vectors per accumulator block (UMMA N) */
+constexpr int SD_EPI_COLS = SD_N / SD_EPI_SPLIT; /* accumulator columns (support vectors) per epilogue thread and block */
 constexpr int SD_KCH = 8;         /* 16-byte k chunks per streamed support-vector block */
-constexpr int SD_STAGES = 3;
+constexpr int SD_STAGES = 4;
 constexpr int SD_B_STAGE_BYTES = (SD_N / 8) * SD_KCH * 128;
-constexpr int SD_PROD_WARPS = 4, SD_EPI_WARPS = 4 * SD_EPI_SPLIT;
+constexpr int SD_PROD_SETS = 1;    /* sets of 4 producer warps (set s builds the tiles s, s + SD_PROD_SETS, ... of its CTA) */
+constexpr int SD_PROD_WARPS = 4 * SD_PROD_SETS, SD_EPI_WARPS = 4 * SD_EPI_SPLIT;
 constexpr int SD_THREADS = 32 * (2 + SD_PROD_WARPS + SD_EPI_WARPS);
 constexpr int SD_TMEM_COLS = 512;
 constexpr int SD_SPIN_LIMIT = 1 << 24;
@@ -110,14 +112,11 @@ __device__ __forceinline__ uint64_t tc_desc(uint32_t addr, uint32_t lbo, uint32_
 	return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo >> 4) & 0x3FFF) << 32)
 			| ((uint64_t)1 << 46);
 }
-__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
-	asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-			"{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-			"%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+	asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+			"{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
 			: "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-			  "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-			  "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-			  "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+			  "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
 			: "r"(taddr) : "memory");
 	asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
@@ -135,11 +134,10 @@ struct SvmDenseArgs {
 	int* pos_count;               /* positives appended (may run past pos_cap), or nullptr */
 	DensePositive* pos;
 	int pos_cap;
-	uint32_t desc_swap;           /* debugging: exchange LBO and SBO in the matrix descriptors */
 };
 
 /* A row of one window: HistEq64 (HistEq64Filter.cpp:32-125) from the layer image into the core-matrix layout */
-__device__ __forceinline__ int produce_window(const SvmDenseArgs& a, const DevLayer* sLayers, uint32_t* hist /* column of this thread */,
+__device__ __forceinline__ int produce_window(const SvmDenseArgs& a, const DevLayer* sLayers, uint16_t* hist /* column of this thread */,
 		uint8_t* arow /* A tile + row offset */, int64_t g) {
 	const int pw = a.patch_w, ph = a.patch_h, npix = pw * ph;
 	const int frame = (int)(g / a.windows_per_frame);
@@ -167,7 +165,7 @@ __device__ __forceinline__ int produce_window(const SvmDenseArgs& a, const DevLa
 		cdf = __fadd_rn(cdf, __fmul_rn((float)cnt, stretch));
 		const float fl = floorf(cdf);
 		const int eq = ((int)fl + (__fsub_rn(cdf, fl) >= 0.5f ? 1 : 0)) & 255; /* saturate_cast never triggers: cdf <= 255 */
-		hist[b * SD_ROWS] = (uint32_t)eq;
+		hist[b * SD_ROWS] = (uint16_t)eq;
 		xx += cnt * eq * eq;
 	}
 	int r = 0, c = 0;
@@ -204,8 +202,8 @@ __device__ __forceinline__ void load_row_words(const uint8_t* p, uint32_t (&x)[W
 /* the same for the patch sizes of ffpDetectApp (width and height multiples of 4): word loads, fire-and-forget
  * shared-memory atomics for the histogram (no read-modify-write chains), 4 rows = PW / 4 whole 16-byte chunks */
 template <int PW, int PH>
-__device__ __forceinline__ int produce_window_fast(const SvmDenseArgs& a, const DevLayer* sLayers, uint32_t* hist,
-		uint8_t* arow, int64_t g) {
+__device__ __forceinline__ int produce_window_fast(const SvmDenseArgs& a, const DevLayer* sLayers, uint16_t* hist /* column of this thread */,
+		uint32_t* hist_word /* the 32-bit word holding it (shared with the neighbouring thread) */, uint32_t hist_inc, uint8_t* arow, int64_t g) {
 	static_assert(PW % 4 == 0 && PH % 4 == 0, "patch sides must be multiples of 4");
 	constexpr int WPR = PW / 4, NPIX = PW * PH;
 	const int frame = (int)(g / a.windows_per_frame);
@@ -219,7 +217,7 @@ __device__ __forceinline__ int produce_window_fast(const SvmDenseArgs& a, const 
 	const uint8_t* src = (L.offset < 0 ? a.frames + (int64_t)frame * a.W * a.H : a.arena + (int64_t)frame * a.arena_stride + L.offset)
 			+ (int64_t)(L.begin_y + iy * a.step_y) * pitch + (L.begin_x + ix * a.step_x);
 #pragma unroll 16
-	for (int b = 0; b < 64; ++b) hist[b * SD_ROWS] = 0u;
+	for (int b = 0; b < 64; ++b) hist[b * SD_ROWS] = 0;
 #pragma unroll 2
 	for (int r = 0; r < PH; ++r) {
 		uint32_t x[WPR];
@@ -227,7 +225,7 @@ __device__ __forceinline__ int produce_window_fast(const SvmDenseArgs& a, const 
 #pragma unroll
 		for (int i = 0; i < WPR; ++i)
 #pragma unroll
-			for (int k = 0; k < 4; ++k) atomicAdd(&hist[((x[i] >> (8 * k + 2)) & 63u) * SD_ROWS], 1u);
+			for (int k = 0; k < 4; ++k) atomicAdd(&hist_word[((x[i] >> (8 * k + 2)) & 63u) * (SD_ROWS / 2)], hist_inc); /* counts <= 400: no carry */
 	}
 	/* sequential float32 cdf, rounded: HistEq64Filter.cpp:70-87,97 */
 	const float stretch = __fdiv_rn(255.0f, (float)NPIX);
@@ -239,7 +237,7 @@ __device__ __forceinline__ int produce_window_fast(const SvmDenseArgs& a, const 
 		cdf = __fadd_rn(cdf, __fmul_rn((float)cnt, stretch));
 		const float fl = floorf(cdf);
 		const int eq = ((int)fl + (__fsub_rn(cdf, fl) >= 0.5f ? 1 : 0)) & 255;
-		hist[b * SD_ROWS] = (uint32_t)eq;
+		hist[b * SD_ROWS] = (uint16_t)eq;
 		xx += cnt * eq * eq;
 	}
 #pragma unroll 1
@@ -252,9 +250,9 @@ __device__ __forceinline__ int produce_window_fast(const SvmDenseArgs& a, const 
 #pragma unroll
 			for (int i = 0; i < WPR; ++i) {
 				uint32_t e = hist[((x[i] >> 2) & 63u) * SD_ROWS];
-				e |= hist[((x[i] >> 10) & 63u) * SD_ROWS] << 8;
-				e |= hist[((x[i] >> 18) & 63u) * SD_ROWS] << 16;
-				e |= hist[(x[i] >> 26) * SD_ROWS] << 24;
+				e |= (uint32_t)hist[((x[i] >> 10) & 63u) * SD_ROWS] << 8;
+				e |= (uint32_t)hist[((x[i] >> 18) & 63u) * SD_ROWS] << 16;
+				e |= (uint32_t)hist[(x[i] >> 26) * SD_ROWS] << 24;
 				o[rr * WPR + i] = e;
 			}
 		}
@@ -292,8 +290,8 @@ __global__ void __launch_bounds__(SD_THREADS, 1) svm_dense_kernel(const __grid_c
 	const int a_tile = (SD_ROWS / 8) * chunks * 128;
 	uint8_t* sA = sd_smem;                                                             /* [SD_ABUF] window tiles */
 	uint8_t* sB = sA + SD_ABUF * a_tile;                                               /* [SD_STAGES] support-vector blocks */
-	uint32_t* sHist = reinterpret_cast<uint32_t*>(sB + SD_STAGES * SD_B_STAGE_BYTES);   /* [64][SD_ROWS] */
-	double* sTab = reinterpret_cast<double*>(sHist + 64 * SD_ROWS);                    /* [tab_n] */
+	uint16_t* sHist = reinterpret_cast<uint16_t*>(sB + SD_STAGES * SD_B_STAGE_BYTES);   /* [SD_PROD_SETS][64][SD_ROWS] */
+	double* sTab = reinterpret_cast<double*>(sHist + SD_PROD_SETS * 64 * SD_ROWS);     /* [tab_n] */
 	double* sPart = sTab + a.s.tab_n;                                                  /* [2][SD_EPI_SPLIT][SD_ROWS] */
 	int* sXX = reinterpret_cast<int*>(sPart + 2 * SD_EPI_SPLIT * SD_ROWS);             /* [SD_XX_RING][SD_ROWS] */
 	DevLayer* sLayers = reinterpret_cast<DevLayer*>(sXX + SD_XX_RING * SD_ROWS);
@@ -324,6 +322,7 @@ __global__ void __launch_bounds__(SD_THREADS, 1) svm_dense_kernel(const __grid_c
 	const int64_t ntiles = (a.total + SD_ROWS - 1) / SD_ROWS;
 	const int NT = a.s.num_sv_pad / SD_N;
 	const int KB = (chunks + SD_KCH - 1) / SD_KCH;
+	const int nt_rot = (int)(blockIdx.x % (unsigned)NT);
 
 	if (warp == 0) {
 		/* ===== support-vector block stream: the whole model once per window tile, from L2 ===== */
@@ -331,7 +330,8 @@ __global__ void __launch_bounds__(SD_THREADS, 1) svm_dense_kernel(const __grid_c
 			uint32_t it = 0;
 			const size_t nblock_bytes = (size_t)(SD_N / 8) * chunks * 128;
 			for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-				for (int nt = 0; nt < NT; ++nt) {
+				for (int n0 = 0; n0 < NT; ++n0) {
+					const int nt = (n0 + nt_rot) % NT; /* CTAs walk the model in different phases: spreads the L2 reads */
 					const uint8_t* src = a.s.b_blocks + (size_t)nt * nblock_bytes;
 					for (int kb = 0; kb < KB; ++kb, ++it) {
 						const int cb = min(SD_KCH, chunks - kb * SD_KCH);
@@ -371,8 +371,7 @@ __global__ void __launch_bounds__(SD_THREADS, 1) svm_dense_kernel(const __grid_c
 						for (int ks = 0; ks < cb / 2; ++ks) {
 							const uint32_t bstart = b_addr + stage * SD_B_STAGE_BYTES + ks * 256;
 							const uint32_t astart = a_addr + abuf * a_tile + (kb * SD_KCH + 2 * ks) * 128;
-							const uint64_t bdesc = a.desc_swap ? tc_desc(bstart, b_sbo, 128) : tc_desc(bstart, 128, b_sbo);
-							const uint64_t adesc = a.desc_swap ? tc_desc(astart, a_sbo, 128) : tc_desc(astart, 128, a_sbo);
+							const uint64_t bdesc = tc_desc(bstart, 128, b_sbo), adesc = tc_desc(astart, 128, a_sbo);
 							tc_mma_i8(tmem + acc * SD_N, adesc, bdesc, idesc, (kb | ks) != 0 ? 1u : 0u);
 						}
 						tc_commit(bar(BAR_B_EMPTY + stage)); /* the ring slot is free once these MMAs have read it */
@@ -384,11 +383,14 @@ __global__ void __launch_bounds__(SD_THREADS, 1) svm_dense_kernel(const __grid_c
 		}
 	} else if (warp < 2 + SD_PROD_WARPS) {
 		/* ===== A operand producers: thread = window row; tile i + 1 is built while tile i is multiplied and summed ===== */
-		const int t = tid - 64;
-		uint32_t* hist = sHist + t;
+		const int set = (warp - 2) >> 2;
+		const int t = (tid - 64) & (SD_ROWS - 1);
+		uint16_t* hist = sHist + set * (64 * SD_ROWS) + t;
+		uint32_t* hist_word = reinterpret_cast<uint32_t*>(sHist + set * (64 * SD_ROWS)) + (t >> 1);
+		const uint32_t hist_inc = 1u << (16 * (t & 1));
 		const bool fast20 = a.patch_w == 20 && a.patch_h == 20;
-		uint32_t tile_it = 0;
-		for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tile_it) {
+		uint32_t tile_it = (uint32_t)set;
+		for (int64_t tile = blockIdx.x + (int64_t)set * gridDim.x; tile < ntiles; tile += (int64_t)SD_PROD_SETS * gridDim.x, tile_it += SD_PROD_SETS) {
 			const uint32_t abuf = tile_it % SD_ABUF;
 			mbar_wait<128>(bar(BAR_A_EMPTY + abuf), ((tile_it / SD_ABUF) & 1) ^ 1);
 			const int64_t g = tile * SD_ROWS + t;
@@ -396,7 +398,7 @@ __global__ void __launch_bounds__(SD_THREADS, 1) svm_dense_kernel(const __grid_c
 			int xx = 0;
 			if (g < a.total) {
 				if (MODE == 1) xx = produce_vector(a, arow, g);
-				else if (fast20) xx = produce_window_fast<20, 20>(a, sLayers, hist, arow, g);
+				else if (fast20) xx = produce_window_fast<20, 20>(a, sLayers, hist, hist_word, hist_inc, arow, g);
 				else xx = produce_window(a, sLayers, hist, arow, g);
 			} else {
 				for (int ch = 0; ch < chunks; ++ch) *reinterpret_cast<uint4*>(arow + ch * 128) = make_uint4(0u, 0u, 0u, 0u);
@@ -420,43 +422,64 @@ __global__ void __launch_bounds__(SD_THREADS, 1) svm_dense_kernel(const __grid_c
 		uint32_t acc_it = 0, tile_it = 0;
 		for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tile_it) {
 			int xx = 0;
-			double dist = 0.0;
+			double dacc[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
 			for (int nt = 0; nt < NT; ++nt, ++acc_it) {
 				const uint32_t acc = acc_it % SD_ACC;
 				mbar_wait<64>(bar(BAR_T_FULL + acc), (acc_it / SD_ACC) & 1);
 				tc_fence_after();
 				if (nt == 0) xx = sXX[(tile_it % SD_XX_RING) * SD_ROWS + row]; /* written before the tile's first MMA was issued */
-				uint32_t v[32];
-				tc_ld32(tmem + ((uint32_t)(q * 32) << 16) + acc * SD_N + part * 32, v);
-				/* accumulators are in registers: hand the buffer back to the MMA warp */
-				tc_fence_before();
-				__syncwarp();
-				if (lane == 0) mbar_arrive(bar(BAR_T_EMPTY + acc));
-				const int sv0 = nt * SD_N + part * 32;
+				const int sv0 = ((nt + nt_rot) % NT) * SD_N + part * SD_EPI_COLS;
 				const int4* __restrict__ s4p = reinterpret_cast<const int4*>(ssq + sv0);       /* warp-uniform vector loads */
 				const double2* __restrict__ c2p = reinterpret_cast<const double2*>(coef + sv0);
+#pragma unroll 1
+				for (int h16 = 0; h16 < SD_EPI_COLS / 16; ++h16) {
+					uint32_t v[16];
+					tc_ld16(tmem + ((uint32_t)(q * 32) << 16) + acc * SD_N + part * SD_EPI_COLS + h16 * 16, v);
+					if (h16 == SD_EPI_COLS / 16 - 1) { /* accumulators are in registers: hand the buffer back to the MMA warp */
+						tc_fence_before();
+						__syncwarp();
+						if (lane == 0) mbar_arrive(bar(BAR_T_EMPTY + acc));
+					}
+					/* 8 support vectors in lockstep: the float64 pipe has a long latency, so the eight Horner chains, the
+					 * table loads and the eight partial sums are kept independent of each other */
 #pragma unroll
-				for (int j4 = 0; j4 < 8; ++j4) {
-					const int4 s4 = __ldg(s4p + j4);
-					const double2 ca = __ldg(c2p + 2 * j4), cb = __ldg(c2p + 2 * j4 + 1);
-					const int ss[4] = {s4.x, s4.y, s4.z, s4.w};
-					const double cc[4] = {ca.x, ca.y, cb.x, cb.y};
+					for (int j8 = 0; j8 < 2; ++j8) {
+						const int4 sa = __ldg(s4p + h16 * 4 + 2 * j8), sb = __ldg(s4p + h16 * 4 + 2 * j8 + 1);
+						const int ss[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
+						double cc[8];
 #pragma unroll
-					for (int k = 0; k < 4; ++k) {
-						const int ssd = xx + ss[k] - 2 * (int)v[4 * j4 + k];
-						/* exact int -> double without the conversion unit: 2^52 + lo as raw bits, minus 2^52 */
-						const double l = __dsub_rn(__hiloint2double(0x43300000, (int)(ssd & lo_mask)), 4503599627370496.0);
-						int hi = ssd >> s_shift;
-						if (CLAMP) hi = min(hi, tab_last);
-						double p = fma(l, c4, c3);
-						p = fma(l, p, c2);
-						p = fma(l, p, c1);
-						p = fma(l, p, 1.0);
-						const double kv = __dmul_rn(sTab[hi], p);         /* RbfKernel.hpp:39 */
-						dist = fma(cc[k], kv, dist);                      /* SvmClassifier.cpp:58 */
+						for (int k = 0; k < 4; ++k) {
+							const double2 c = __ldg(c2p + h16 * 8 + 4 * j8 + k);
+							cc[2 * k] = c.x; cc[2 * k + 1] = c.y;
+						}
+						int ssd[8];
+						double tv[8], l[8], p[8];
+#pragma unroll
+						for (int k = 0; k < 8; ++k) ssd[k] = xx + ss[k] - 2 * (int)v[8 * j8 + k];
+#pragma unroll
+						for (int k = 0; k < 8; ++k) {
+							int hi = ssd[k] >> s_shift;
+							if (CLAMP) hi = min(hi, tab_last);
+							tv[k] = sTab[hi];
+						}
+#pragma unroll
+						for (int k = 0; k < 8; ++k) /* exact int -> double without the conversion unit: 2^52 + lo as raw bits, minus 2^52 */
+							l[k] = __dsub_rn(__hiloint2double(0x43300000, (int)(ssd[k] & lo_mask)), 4503599627370496.0);
+#pragma unroll
+						for (int k = 0; k < 8; ++k) p[k] = fma(l[k], c4, c3);
+#pragma unroll
+						for (int k = 0; k < 8; ++k) p[k] = fma(l[k], p[k], c2);
+#pragma unroll
+						for (int k = 0; k < 8; ++k) p[k] = fma(l[k], p[k], c1);
+#pragma unroll
+						for (int k = 0; k < 8; ++k) p[k] = fma(l[k], p[k], 1.0);
+#pragma unroll
+						for (int k = 0; k < 8; ++k) dacc[k] = fma(cc[k], __dmul_rn(tv[k], p[k]), dacc[k]); /* RbfKernel.hpp:39, SvmClassifier.cpp:58 */
 					}
 				}
 			}
+			const double dist = __dadd_rn(__dadd_rn(__dadd_rn(dacc[0], dacc[1]), __dadd_rn(dacc[2], dacc[3])),
+					__dadd_rn(__dadd_rn(dacc[4], dacc[5]), __dadd_rn(dacc[6], dacc[7])));
 			/* the SD_EPI_SPLIT partial sums of a row, added in a fixed order */
 			double* pbuf = sPart + (tile_it & 1) * (SD_EPI_SPLIT * SD_ROWS);
 			pbuf[part * SD_ROWS + row] = dist;
@@ -489,7 +512,7 @@ __global__ void __launch_bounds__(SD_THREADS, 1) svm_dense_kernel(const __grid_c
 
 size_t sd_smem_bytes(const DevSvmDense& s) {
 	const size_t a_tile = (size_t)(SD_ROWS / 8) * s.chunks * 128;
-	return SD_ABUF * a_tile + (size_t)SD_STAGES * SD_B_STAGE_BYTES + 64 * SD_ROWS * sizeof(uint32_t) + (size_t)s.tab_n * 8
+	return SD_ABUF * a_tile + (size_t)SD_STAGES * SD_B_STAGE_BYTES + SD_PROD_SETS * 64 * SD_ROWS * sizeof(uint16_t) + (size_t)s.tab_n * 8
 			+ 2 * SD_EPI_SPLIT * SD_ROWS * sizeof(double) + SD_XX_RING * SD_ROWS * sizeof(int) + FDB_MAX_LAYERS * sizeof(DevLayer)
 			+ BAR_COUNT * 8 + 16;
 }
@@ -581,11 +604,6 @@ static int dense_grid(int64_t total) {
 	return (int)std::min<int64_t>(ntiles, g_sd_sms > 0 ? g_sd_sms : 148);
 }
 
-static uint32_t dense_desc_swap() {
-	const char* e = std::getenv("FDB_SVMD_SWAP");
-	return e && e[0] == '1' ? 1u : 0u;
-}
-
 void launch_svm_dense_windows(cudaStream_t st, const DevSvmDense& s, int patch_w, int patch_h, int step_x, int step_y,
 		const uint8_t* frames, int W, int H, int n_frames, const uint8_t* arena, int64_t arena_stride, const DevLayer* layers,
 		int n_layers, int64_t windows_per_frame, double* distance_out, int* pos_count, DensePositive* pos, int pos_cap) {
@@ -596,7 +614,6 @@ void launch_svm_dense_windows(cudaStream_t st, const DevSvmDense& s, int patch_w
 	a.frames = frames; a.W = W; a.H = H; a.arena = arena; a.arena_stride = arena_stride;
 	a.layers = layers; a.n_layers = n_layers; a.windows_per_frame = windows_per_frame;
 	a.total = total; a.distance_out = distance_out; a.pos_count = pos_count; a.pos = pos; a.pos_cap = pos_cap;
-	a.desc_swap = dense_desc_swap();
 	if (s.clamp) svm_dense_kernel<0, true><<<dense_grid(total), SD_THREADS, sd_smem_bytes(s), st>>>(a);
 	else svm_dense_kernel<0, false><<<dense_grid(total), SD_THREADS, sd_smem_bytes(s), st>>>(a);
 }
@@ -605,7 +622,6 @@ void launch_svm_dense_vectors(cudaStream_t st, const DevSvmDense& s, const uint8
 	if (n <= 0) return;
 	SvmDenseArgs a{};
 	a.s = s; a.vectors = vectors; a.total = n; a.distance_out = distance_out; a.windows_per_frame = n;
-	a.desc_swap = dense_desc_swap();
 	if (s.clamp) svm_dense_kernel<1, true><<<dense_grid(n), SD_THREADS, sd_smem_bytes(s), st>>>(a);
 	else svm_dense_kernel<1, false><<<dense_grid(n), SD_THREADS, sd_smem_bytes(s), st>>>(a);
 }

@@ -13,6 +13,8 @@ probe.prepare(640, 480, 1)
 _, d0 = probe.detect_single(syn.synthetic_frames(0, 1))
 svm.threshold = float(np.float32(np.quantile(d0, 0.999)))  # ~0.1 % of the windows positive
 del probe
+if len(sys.argv) > 2:
+    os.environ['FDB_SVMD_DBG'] = sys.argv[2]  # ablation timing (see svm_dense.cu); results are then meaningless
 c = SlidingWindowCascade(ctx, det_kw, None, svm)
 c.prepare(640, 480, n)
 assert c.single_dense
@@ -20,10 +22,10 @@ base = syn.synthetic_frames(0, 8)
 frames = torch.from_numpy(np.concatenate([base] * ((n + 7) // 8))[:n]).cuda()
 dist = torch.empty((n, c.windows_per_frame), dtype=torch.float64, device="cuda")
 for _ in range(2):
-    d = c.detect_single_device(frames.data_ptr(), n, dist.data_ptr())
+    d = c.detect_single_device(frames.data_ptr(), n, dist.data_ptr(), det_cap=n * c.windows_per_frame)
 ts = []
 for _ in range(5):
-    ctx.timer_start(); d = c.detect_single_device(frames.data_ptr(), n, dist.data_ptr()); ts.append(ctx.timer_stop())
+    ctx.timer_start(); d = c.detect_single_device(frames.data_ptr(), n, dist.data_ptr(), det_cap=n * c.windows_per_frame); ts.append(ctx.timer_stop())
 ms = float(np.median(ts))
 w = n * c.windows_per_frame
 print("single psvm dense: %d frames, %d windows, %.3f ms, %.3e windows/s, %.1f TOP/s (u8), %d positives" % (
