@@ -183,12 +183,12 @@ def run_reference_sdm(args, rank, world):
     arm.close()
     value = faces / total
     sample = "%d faces per step (%d per core x %d processes), %d steps" % (per_core * arm.cores, per_core, arm.cores, args.steps)
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": "sdm_fitted_faces_per_s", "value": value, "unit": "faces/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32/f64", "data": "synthetic", "config": sdm_config(args, world, sample),
         "cpu_baseline": {"value": value, "unit": "faces/s", "cores": arm.cores, "kind": arm.kind, "sample": sample},
-        "e2e": {"value": value, "unit": "faces/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
+        "e2e": {"value": value, "unit": "faces/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
 
 
 def run_sdm(args, rank, world, local_rank):
@@ -303,7 +303,7 @@ def run_sdm(args, rank, world, local_rank):
             arm.close()
             cpu = {"value": f / wall, "unit": "faces/s", "cores": arm.cores, "kind": arm.kind,
                    "sample": "%d faces of the same workload (%d per core x %d processes), %.1f s wall" % (f, per_core, arm.cores, wall)}
-        print(json.dumps({
+        emit({
             "metric": "sdm_fitted_faces_per_s", "value": value, "unit": "faces/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32/f64", "data": "synthetic", "config": sdm_config(args, world), "clocks": clocks,
@@ -321,7 +321,7 @@ def run_sdm(args, rank, world, local_rank):
             "gemm": {"kernel": "sdm_gemm_dmma_kernel (FP64 tensor cores: float32 operands, float64 accumulation like cv::gemm on CV_32F)", "m": n, "n": N, "k": K,
                      "ms": prof["gemm"] / SDM_STEPS, "tflops_fp64": gemm_flops / (prof["gemm"] / SDM_STEPS * 1e-3) / 1e12},
             "kernel_ms_per_fit": prof, "faces_out_of_image": int((status_e2e != 0).sum()),
-            "cpu_baseline": cpu}), flush=True)
+            "cpu_baseline": cpu})
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -409,7 +409,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": value, "unit": "patches/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "frames_per_s": value / 16185.0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(args, world, extra=None):
@@ -434,14 +434,272 @@ def workload_config(args, world, extra=None):
     return cfg
 
 
+# ------------------------------------------------------------------------------------------------
+# `single` psvm detector (ffpDetectApp.cpp:427-500; SURVEY 8(d) "every window goes to the SVM"): --workload single-psvm
+# ------------------------------------------------------------------------------------------------
+SINGLE_STRIDE = 16  # the CPU arm classifies every 16th window of its frames (215 us per window and core)
+
+
+def _single_models():
+    """FaceFrontal geometry + its 1024-support-vector u8 RBF SVM; threshold = the 99.9 % quantile of the oracle-independent
+    distances of frame 0 (fixed: computed once from the model and committed here), so that ~0.1 % of the windows are positive"""
+    from featuredetection_b200 import synthetic as syn
+    det_kw, _, svm = syn.landmark_models(CFG)
+    return det_kw, svm
+
+
+def _single_worker_init(kind):
+    from featuredetection_b200 import synthetic as syn
+    from oracle import fdoracle as fo
+    det_kw, svm = _single_models()
+    _worker_state.update(fo=fo, syn=syn, kw=det_kw, svm=fo.Svm(svm, use_ref=(kind == "reference")))
+
+
+def _single_worker_run(frame_ids):
+    """timed: HistEq64 + SVM distance of the sampled windows (the per-window work of SlidingWindowDetector::detect);
+    untimed: the pyramid and slicing the sampled windows out of it (python)"""
+    st = _worker_state
+    fo, syn, kw = st["fo"], st["syn"], st["kw"]
+    n, t = 0, 0.0
+    for k in frame_ids:
+        frame = syn.synthetic_frame(k % 8)
+        _, layers = fo.pyramid(frame, kw["incremental_scale_factor"], kw["min_scale_factor"], kw["max_scale_factor"])
+        raw, w0 = [], 0
+        for _, _, img in layers:
+            wx, wy = img.shape[1] - 19, img.shape[0] - 19
+            for w in range((-w0) % SINGLE_STRIDE, wx * wy, SINGLE_STRIDE):
+                y, x = divmod(w, wx)
+                raw.append(img[y:y + 20, x:x + 20])
+            w0 += wx * wy
+        t0 = time.perf_counter()
+        eq = np.stack([fo.hq64(p).ravel() for p in raw])
+        st["svm"].eval(eq)
+        t += time.perf_counter() - t0
+        n += len(raw)
+    return n, t
+
+
+class SingleCpuArm:
+    """HistEq64 + SvmClassifier::computeHyperplaneDistance per window on all host cores (kind "reference": the compiled
+    reference classes of oracle/_ref), on every SINGLE_STRIDE-th window of the frames"""
+
+    def __init__(self):
+        from oracle import fdoracle as fo
+        fo.build()
+        self.kind = "reference" if fo.ref_available() else "port"
+        self.cores = os.cpu_count() or 1
+        self.pool = mp.get_context("spawn").Pool(self.cores, initializer=_single_worker_init, initargs=(self.kind,))
+
+    def run(self, frames_per_core, first=0):
+        chunks = [list(range(first + c * frames_per_core, first + (c + 1) * frames_per_core)) for c in range(self.cores)]
+        res = self.pool.map(_single_worker_run, chunks)
+        return sum(r[0] for r in res), max(r[1] for r in res)  # the slowest core's classification time
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+
+
+def single_config(args, world, wpf, extra=None):
+    cfg = {"workload": "ffpDetectApp `single` detector with a psvm classifier (SURVEY 8(d) no-exit case of BASELINE configs[3]: every window "
+                       "goes to the RBF-SVM): %d-frame batch per GPU, 640x480 1-channel, FaceFrontal pyramid (13 layers), HistEq64 20x20 "
+                       "patches, 1024 u8 support vectors" % args.frames,
+           "frames_per_gpu": args.frames, "global_frames": args.frames * world, "windows_per_frame": wpf, "support_vectors": 1024,
+           "parallelism": "frame-sharded dp%d" % world,
+           "l2": "a 256 MB scratch write flushes L2 between timed steps"}
+    if extra:
+        cfg["sample"] = extra
+    return cfg
+
+
+def run_reference_single(args, rank, world):
+    if rank != 0:
+        return
+    arm = SingleCpuArm()
+    for _ in range(args.warmup):
+        arm.run(1)
+    windows, total = 0, 0.0
+    for s in range(args.steps):
+        w, wall = arm.run(1, first=s * arm.cores)
+        windows += w
+        total += wall
+    arm.close()
+    value = windows / total
+    sample = "every %dth window of %d frames per step (1 per core x %d processes), %d steps" % (SINGLE_STRIDE, arm.cores, arm.cores, args.steps)
+    emit({"impl": "reference", "metric": "classified_patches_per_s", "value": value, "unit": "patches/s", "n_gpus": args.gpus,
+          "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True,
+          "scaling": "weak", "vs_baseline": None, "dtype": "u8/s32/f64", "data": "synthetic",
+          "config": single_config(args, world, 16185, sample),
+          "cpu_baseline": {"value": value, "unit": "patches/s", "cores": arm.cores, "kind": arm.kind, "sample": sample},
+          "e2e": {"value": value, "unit": "patches/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+
+
+def run_single(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from featuredetection_b200 import synthetic as syn, sharding
+    from featuredetection_b200.detector import Context, SlidingWindowCascade, DETECTION_DTYPE
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - the B200 path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        dist.init_process_group("nccl", device_id=device)
+    ctx = Context(local_rank)
+    det_kw, svm = _single_models()
+    n = args.frames
+    probe = SlidingWindowCascade(ctx, det_kw, None, svm)
+    probe.prepare(W, H, 1)
+    _, d0 = probe.detect_single(syn.synthetic_frames(0, 1))
+    svm.threshold = float(np.float32(np.quantile(d0, 0.999)))   # ~0.1 % of the windows positive
+    del probe
+    casc = SlidingWindowCascade(ctx, det_kw, None, svm)
+    casc.prepare(W, H, n)
+    if not casc.single_dense:
+        raise SystemExit("bench.py: the tensor-core SVM path is not available for this model")
+    wpf = casc.windows_per_frame
+    lo, hi = sharding.shard_range(n * world, rank, world)
+    base = syn.synthetic_frames(lo % 97, min(8, n))
+    host_frames = torch.from_numpy(np.concatenate([base] * ((n + len(base) - 1) // len(base)))[:n]).pin_memory()
+    dev_frames = host_frames.to(device)
+    dev_dist = torch.empty((n, wpf), dtype=torch.float64, device=device)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
+    det_cap = 64 * n
+    gather_cap = max(256, 32 * n)
+    gather = sharding.DetectionGather(gather_cap, dist, device) if world > 1 else None
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ctx.synchronize()
+
+    def flush_l2():
+        flush.fill_(1)
+        torch.cuda.synchronize()
+
+    def exchange(dets):
+        if world > 1:  # the only exchange: fixed-size blocks of positives (the path itself has no collective)
+            gather.collect(gather.submit(dets[:gather_cap], lo))
+
+    def step_resident():
+        dets = casc.detect_single_device(dev_frames.data_ptr(), n, dev_dist.data_ptr(), det_cap=det_cap)
+        exchange(dets)
+        return dets
+
+    def step_e2e():
+        dets, _ = casc.detect_single(host_frames.numpy(), want_distances=False, det_cap=det_cap)
+        exchange(dets)
+        return dets
+
+    for _ in range(args.warmup):
+        step_resident()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    launches0 = ctx.launch_count()
+    if rank == 0:
+        sampler.start()
+    step_ms, kern_ms, kern_n = [], 0.0, 0
+    for _ in range(args.steps):
+        flush_l2()
+        ctx.timer_start()
+        dets = step_resident()
+        step_ms.append(ctx.timer_stop())
+        ms, k = casc.single_dense_profile()
+        kern_ms += ms
+        kern_n += k
+    barrier()
+    launches = ctx.launch_count() - launches0
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    e2e_ms = []
+    for _ in range(args.steps):
+        flush_l2()
+        ctx.timer_start()
+        dets_e2e = step_e2e()
+        e2e_ms.append(ctx.timer_stop())
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    tot = torch.tensor([sum(step_ms), sum(e2e_ms)], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(tot, op=dist.ReduceOp.MAX)
+    total_ms, e2e_total = float(tot[0].item()), float(tot[1].item())
+    same = bool(np.array_equal(dets["window"], dets_e2e["window"]) and np.array_equal(dets["svm_distance"], dets_e2e["svm_distance"]))
+
+    if rank == 0:
+        windows_step = wpf * n * world
+        value = windows_step * args.steps / (total_ms * 1e-3)
+        e2e_value = windows_step * args.steps / (e2e_total * 1e-3)
+        # dominant kernel: svm_dense_kernel, one launch per chunk of frames. Algorithmic work per launch (DESIGN.md 5):
+        # 2 * windows * support vectors * patch pixels integer operations of the u8 matrix product.
+        kernel_ms = kern_ms / kern_n
+        ops = 2.0 * wpf * (n * args.steps / kern_n) * svm.sv.shape[0] * svm.sv.shape[1]
+        achieved = ops / (kernel_ms * 1e-3) / 1e12
+        mp_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        bf16 = json.load(open(mp_path))["bf16_tflops"] if os.path.exists(mp_path) else 1638.6  # burst: the kernel is timed alone
+        peak = 2.0 * bf16  # kind::i8 runs at twice the bf16 rate on sm_100a; no measured int8 figure exists on this pool
+        cpu = None
+        if not args.no_cpu_baseline:
+            arm = SingleCpuArm()
+            arm.run(1)
+            wcpu, wall = arm.run(8)
+            arm.close()
+            cpu = {"value": wcpu / wall, "unit": "patches/s", "cores": arm.cores, "kind": arm.kind,
+                   "sample": "every %dth window of %d frames (8 per core x %d processes), %.1f s on the slowest core" % (SINGLE_STRIDE, 8 * arm.cores, arm.cores, wall)}
+        emit({
+            "metric": "classified_patches_per_s", "value": value, "unit": "patches/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8/s32/f64", "data": "synthetic", "config": single_config(args, world, wpf),
+            "frames_per_s": value / wpf, "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "patches/s", "h2d_bytes_per_step": int(W * H * n),
+                    "d2h_bytes_per_step": int(len(dets_e2e) * 16 + 4 * kern_n // args.steps), "ms_per_step": e2e_total / args.steps,
+                    "identical_to_resident": same},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "tensor", "kernel": "svm_dense_kernel (HistEq64 producers + tcgen05.mma kind::i8 [windows x 400] . [400 x 1024] + float64 "
+                                                      "RBF epilogue; one launch per %d-frame chunk)" % (n * args.steps // kern_n),
+                         "achieved": achieved, "peak": peak, "unit": "TOP/s", "frac": achieved / peak, "traffic": None,
+                         "peak_source": "2 x bf16_tflops (burst) of MEASURED_PEAKS.json: kind::i8 runs at twice the bf16 rate; no int8 figure is measured on this pool (ncu: tensor pipe 13 % active)",
+                         "algorithmic_ops_per_launch": ops, "kernel_ms": kernel_ms, "launches_per_step": kern_n / args.steps,
+                         "note": "the tensor pipe is ~13 % busy (profiles/svmd_*): the launch is bound by the float64 exp epilogue "
+                                 "(7 float64 operations per window x support vector) and by streaming the support vectors from L2 "
+                                 "(426 KB per 128-window tile)"},
+            "detections_per_step": int(len(dets)) * world, "cpu_baseline": cpu})
+    if world > 1:
+        dist.destroy_process_group()
+
+
+_JSON_OUT = None
+
+
+def _claim_stdout():
+    """stdout carries exactly ONE JSON line: keep a private copy of fd 1 for it and point fd 1 at stderr, so that whatever a
+    library prints (NCCL's version banner goes to stdout whatever NCCL_DEBUG_FILE says) cannot end up in front of it"""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    _claim_stdout()
+    _JSON_OUT.write(json.dumps(line) + "\n")
+    _JSON_OUT.flush()
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--frames", type=int, default=None, help="frames per GPU per step (default 256; 16 for landmarks15)")
-    ap.add_argument("--workload", default="facefrontal", choices=["facefrontal", "landmarks15", "sdm"],
+    ap.add_argument("--workload", default="facefrontal", choices=["facefrontal", "landmarks15", "sdm", "single-psvm"],
                     help="sdm = BASELINE configs[4] (supervised-descent fit, 68 landmarks, 4096 faces per GPU); facefrontal = BASELINE configs[1] (headline); landmarks15 = all 15 ffpDetectApp landmark detectors per frame (configs[3] shape, hq64 features)")
     ap.add_argument("--profile", default="realistic", choices=["realistic", "no-exit"])
     ap.add_argument("--feature", default=None, choices=["hq64", "hog", "whi", "lbp", "histeq", "ehog"],
@@ -452,7 +710,7 @@ def main():
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.frames is None:
-        args.frames = {"facefrontal": 256, "landmarks15": 16, "sdm": 4096}[args.workload]
+        args.frames = {"facefrontal": 256, "landmarks15": 16, "sdm": 4096, "single-psvm": 256}[args.workload]
     if args.feature is None:
         args.feature = "hog" if args.workload == "facefrontal" else "hq64"
     if args.workload == "landmarks15" and args.feature != "hq64":
@@ -461,6 +719,12 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.workload == "single-psvm":
+        if args.impl == "reference":
+            run_reference_single(args, rank, world)
+        else:
+            run_single(args, rank, world, local_rank)
+        return
     if args.workload == "sdm":
         if args.impl == "reference":
             run_reference_sdm(args, rank, world)
@@ -648,7 +912,7 @@ def main():
             "detections_per_step": int(len(dets)) * world,
             "cpu_baseline": cpu,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -102,6 +102,7 @@ struct fdb_detector {
 	/* `single` detector on the tensor cores (svm_dense.cu): distances of a chunk, positives list */
 	double* d_sd_dist = nullptr; int* d_sd_count = nullptr; DensePositive* d_sd_pos = nullptr;
 	int* h_sd_count = nullptr; DensePositive* h_sd_pos = nullptr; int sd_pos_cap = 0;
+	double sd_kernel_ms = 0; int sd_kernel_launches = 0; /* svm_dense_kernel time of the last call (CUDA events) */
 	int64_t counts[5] = {0, 0, 0, 0, 0};
 };
 
@@ -436,28 +437,46 @@ int detect_single_dense(fdb_detector* det, const uint8_t* frames, bool frames_on
 	det->counts[0] = plan.windows * n_frames;
 	std::vector<fdb_detection> dets;
 	const int64_t nwin = plan.windows;
+	det->sd_kernel_ms = 0; det->sd_kernel_launches = 0;
+	/* host frames: the upload of chunk k + 1 (copy stream, the other slot's staging buffer) overlaps the kernels of chunk k */
+	const bool overlap = !frames_on_device && det->n_slots >= 2;
+	cudaStream_t cs = overlap ? det->slots[1].st : st;
+	auto upload = [&](int base) -> cudaError_t {
+		const int n = std::min(det->chunk, n_frames - base);
+		Slot& dst = det->slots[overlap ? (base / det->chunk) & 1 : 0];
+		cudaError_t e = cudaMemcpy2DAsync(dst.d_frames, (size_t)W, frames + (int64_t)base * pitch * H, (size_t)pitch, (size_t)W,
+				(size_t)H * n, cudaMemcpyHostToDevice, cs);
+		if (e == cudaSuccess && overlap) e = cudaEventRecord(dst.ev_stage1, cs);
+		return e;
+	};
+	if (overlap && n_frames > 0) CUDA_TRY(upload(0));
 	for (int base = 0; base < n_frames; base += det->chunk) {
 		const int n = std::min(det->chunk, n_frames - base);
 		if (frames_on_device) sl.frames_dev = frames + (int64_t)base * W * H;
 		else {
-			CUDA_TRY(cudaMemcpy2DAsync(sl.d_frames, (size_t)W, frames + (int64_t)base * pitch * H, (size_t)pitch, (size_t)W,
-					(size_t)H * n, cudaMemcpyHostToDevice, st));
-			sl.frames_dev = sl.d_frames;
+			Slot& src = det->slots[overlap ? (base / det->chunk) & 1 : 0];
+			if (overlap) CUDA_TRY(cudaStreamWaitEvent(st, src.ev_stage1, 0));
+			else CUDA_TRY(upload(base));
+			sl.frames_dev = src.d_frames;
 		}
 		sl.base = base; sl.n = n;
 		CUDA_TRY(cudaMemsetAsync(det->d_sd_count, 0, sizeof(int), st));
 		int s = enqueue_stage1(det, sl, st, sl.frames_dev, n, plan, det->d_layers, 0, nullptr, nullptr, false);
 		if (s) return s;
 		double* d_out = distance_out && distance_on_device ? distance_out + (int64_t)base * nwin : det->d_sd_dist;
+		CUDA_TRY(cudaEventRecord(c->ev[1], st));
 		launch_svm_dense_windows(st, det->svm->dense, det->desc.patch_width, det->desc.patch_height, det->desc.step_x,
 				det->desc.step_y, sl.frames_dev, W, H, n, sl.d_arena, plan.arena_bytes, det->d_layers, (int)plan.layers.size(),
 				nwin, d_out, det->d_sd_count, det->d_sd_pos, det->sd_pos_cap);
 		c->launches++;
 		CUDA_TRY(cudaGetLastError());
+		CUDA_TRY(cudaEventRecord(c->ev[2], st));
 		CUDA_TRY(cudaMemcpyAsync(det->h_sd_count, det->d_sd_count, sizeof(int), cudaMemcpyDeviceToHost, st));
+		if (overlap && base + det->chunk < n_frames) CUDA_TRY(upload(base + det->chunk)); /* its buffer was last read by chunk k - 1 (finished) */
 		if (distance_out && !distance_on_device)
 			CUDA_TRY(cudaMemcpyAsync(distance_out + (int64_t)base * nwin, d_out, sizeof(double) * (size_t)(nwin * n), cudaMemcpyDeviceToHost, st));
 		CUDA_TRY(cudaStreamSynchronize(st));
+		{ float ms = 0.f; CUDA_TRY(cudaEventElapsedTime(&ms, c->ev[1], c->ev[2])); det->sd_kernel_ms += ms; det->sd_kernel_launches++; }
 		const int npos = det->h_sd_count[0];
 		if (npos > det->sd_pos_cap) return fail(FDB_ERR_OVERFLOW, "positives list overflow: raise max_positives_per_frame");
 		if (npos > 0) {
@@ -1121,6 +1140,12 @@ int fdb_detect_single_device(fdb_detector* det, const uint8_t* frames_device, in
 }
 
 int fdb_detector_single_dense(fdb_detector* det) { return det && det->prepared && single_dense_usable(det) ? 1 : 0; }
+
+int fdb_detector_single_dense_profile(fdb_detector* det, double* kernel_ms, int32_t* launches) {
+	if (!det || !kernel_ms || !launches) return fail(FDB_ERR_INVALID_ARGUMENT, "null argument");
+	*kernel_ms = det->sd_kernel_ms; *launches = det->sd_kernel_launches;
+	return FDB_OK;
+}
 
 int fdb_detector_last_counts(fdb_detector* det, int64_t counts[5]) {
 	if (!det || !counts) return fail(FDB_ERR_INVALID_ARGUMENT, "null argument");

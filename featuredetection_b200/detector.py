@@ -304,6 +304,12 @@ class SlidingWindowCascade:
         """True when detect_single runs as one tensor-core launch per chunk of frames (csrc/svm_dense.cu)"""
         return bool(self.ctx.lib.fdb_detector_single_dense(self.h))
 
+    def single_dense_profile(self):
+        """(svm_dense_kernel milliseconds, launches) of the last detect_single / detect_single_device call"""
+        ms, n = C.c_double(), C.c_int32()
+        capi.check(self.ctx.lib, self.ctx.lib.fdb_detector_single_dense_profile(self.h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
     def detect_single_device(self, frames_ptr, n, distance_ptr=None, det_cap=None):
         """detect_single for frames resident in device memory; distances (if wanted) stay on the device"""
         det_cap = det_cap or max(1024, 64 * n)

@@ -437,6 +437,9 @@ FDB_API int fdb_detect_single(fdb_detector* det, const uint8_t* frames_host, int
 FDB_API int fdb_detect_single_device(fdb_detector* det, const uint8_t* frames_device, int32_t n_frames,
 		double* distance_device, fdb_detection* detections_out, int64_t det_cap, int64_t* n_detections);
 FDB_API int fdb_detector_single_dense(fdb_detector* det);
+/* time spent in svm_dense_kernel during the last fdb_detect_single[_device] call (CUDA events on the library stream)
+ * and the number of launches (one per chunk of frames): the roofline numerator of bench.py --workload single-psvm */
+FDB_API int fdb_detector_single_dense_profile(fdb_detector* det, double* kernel_ms, int32_t* launches);
 
 /* Per-stage counters of the last detect call (TOT/TACC-style counters, ffpDetectApp.cpp:650-657):
  * [0] windows, [1] wvm positives, [2] after OE, [3] svm positives, [4] after NMS. */
