@@ -13,17 +13,18 @@
  * (window, support vector) pairs is the matrix product [windows x pixels] . [pixels x support vectors] of u8 operands
  * with s32 accumulation - exact on the integer tensor cores (400 * 255 * 255 < 2^31).
  *
- * One persistent CTA per SM, 18 warps with fixed roles:
+ * One persistent CTA per SM, 14 warps with fixed roles; a tile is 128 windows:
  *   warp 0      streams the support-vector blocks (pre-arranged on the host as UMMA core matrices) from L2 into a
- *               4-stage shared-memory ring with cp.async.bulk + mbarrier complete_tx
- *   warp 1      owns tensor memory (512 columns) and issues tcgen05.mma (one lane): 2 window tiles of 128 rows share
- *               every support-vector block; two accumulator buffers of 2 x 128 columns alternate between MMA and epilogue
- *   warps 2-9   producers of the A operand (two sets of 4 warps, one per A buffer): thread = window; HistEq64 of the window straight from the pyramid layer
+ *               4-stage shared-memory ring with cp.async.bulk + mbarrier complete_tx; the whole model passes once per tile
+ *   warp 1      owns tensor memory (512 columns) and issues tcgen05.mma (one lane): M128 N128 K32, 13 k-steps per block of
+ *               128 support vectors; 4 accumulator blocks of 128 columns alternate between MMA and epilogue
+ *   warps 2-5   producers of the A operand: thread = window; HistEq64 of the window straight from the pyramid layer
  *               (float32 cdf in the reference's order, like the other kernels), equalised pixels written to shared
- *               memory as 8x16-byte core matrices, |x|^2 from the histogram; no equalised patch ever touches HBM
- *   warps 10-17 epilogue: thread = window row (tcgen05.ld 32 lanes x 32 columns), ssd = |x|^2 + |sv|^2 - 2 dot,
- *               k = exp(-gamma ssd) in float64, distance accumulated in float64 IN SUPPORT-VECTOR ORDER (one thread
- *               owns one window for all support vectors, so the order of the reference's loop is kept)
+ *               memory as 8x16-byte core matrices, |x|^2 from the histogram; two A buffers, so tile i + 1 is produced while
+ *               tile i is multiplied and summed; no equalised patch ever touches HBM
+ *   warps 6-13  epilogue: two threads per window row (tcgen05.ld 32 lanes x 16 columns), ssd = |x|^2 + |sv|^2 - 2 dot,
+ *               k = exp(-gamma ssd) in float64, 8 independent float64 partial sums per thread (the float64 pipe has a
+ *               long latency), added in a fixed order - deterministic, but not the reference's left-to-right order
  *
  * exp(-gamma * ssd) for an integer ssd: ssd = hi * 2^s + lo, exp(-gamma hi 2^s) from a table of glibc-computed doubles
  * in shared memory, exp(-gamma lo) by its degree-4 Taylor polynomial (gamma * 2^s <= 2^-7, truncation < 2.4e-13 relative).
