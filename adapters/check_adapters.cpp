@@ -2,6 +2,7 @@
  * instantiates every adapter so that a missing pure-virtual override fails the build. */
 #include "fdb200_adapters.hpp"
 #include "fdb200_sdm_adapter.hpp"
+#include "fdb200_condensation_adapter.hpp"
 
 /* stand-in with the getters of superviseddescent::SdmLandmarkModel (SdmLandmarkModel.hpp:74-87; that header itself needs
  * OpenCV nonfree, Boost and libImageIO, which the compile check does not have) */
@@ -29,6 +30,10 @@ int main() {
 		d->detect(frame);
 		e->update(frame);
 		e->extract(1, 1);
+		std::shared_ptr<condensation::MeasurementModel> mm = std::make_shared<fdb200::B200WvmSvmModel>(det);
+		std::vector<std::shared_ptr<condensation::Sample>> particles(1, std::make_shared<condensation::Sample>(320, 240, 200));
+		mm->evaluate(std::make_shared<imageprocessing::VersionedImage>(frame), particles);
+		mm->evaluate(*particles[0]);
 		fdb200::B200SdmLandmarkModelFitting fit(ctx->get(), MockSdmModel());
 		cv::Mat shape = fit.alignRigid(MockSdmModel().getMeanShape(), cv::Rect(10, 10, 100, 100));
 		shape = fit.optimize(shape, frame);

@@ -156,6 +156,8 @@ public:
 		check(fdb_detector_create(context->get(), &desc, wvm->get(), svm ? svm->get() : nullptr, &handle));
 	}
 	~B200SlidingWindowDetector() { fdb_detector_destroy(handle); }
+	fdb_detector* get() const { return handle; }
+	const cv::Mat& currentFrame() const { return current; } /* gray frame of the last update() */
 
 	/* ---- detection::Detector ---- */
 	std::vector<std::shared_ptr<detection::ClassifiedPatch>> detect(const cv::Mat& image) {
@@ -183,7 +185,7 @@ public:
 	std::shared_ptr<imageprocessing::Patch> extract(int x, int y, int w, int h) const {
 		/* DirectPyramidFeatureExtractor.cpp:67-73: the layer whose patch width is closest to w */
 		const double power = std::log((double)desc.patch_width / (double)w) / std::log(incrementalScale());
-		const int index = (int)std::floor(power + 0.5);
+		const int index = (int)std::round(power); /* ImagePyramid.cpp:307-310 */
 		const fdb_layer_info* L = findLayer(index);
 		if (!L) return std::shared_ptr<imageprocessing::Patch>();
 		return extractAt(*L, cvRound((x - w / 2) * L->scale), cvRound((y - h / 2) * L->scale));
@@ -216,7 +218,7 @@ public:
 	}
 	int getLayerIndex(int w, int /*h*/) const {
 		const double power = std::log((double)desc.patch_width / (double)w) / std::log(incrementalScale());
-		const fdb_layer_info* L = findLayer((int)std::floor(power + 0.5));
+		const fdb_layer_info* L = findLayer((int)std::round(power));
 		return L ? L->index : -1;
 	}
 	double getMinScaleFactor() const { return desc.min_scale_factor; }

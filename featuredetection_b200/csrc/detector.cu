@@ -503,6 +503,120 @@ int detect_single_dense(fdb_detector* det, const uint8_t* frames, bool frames_on
 	return copy_out(dets, dets_out, det_cap, n_dets);
 }
 
+/* condensation::WvmSvmModel::evaluate(image, samples) (WvmSvmModel.cpp:74-119) on one frame: the tracker's sparse use of the
+ * same two classifiers. Sample i = {centre x, centre y, width, height} in image pixels:
+ *   patch  = DirectPyramidFeatureExtractor::extract(x, y, w, h) (DirectPyramidFeatureExtractor.cpp:67-73,133-147): layer index
+ *            round(log(patchWidth / w) / log(incrementalScaleFactor)) (ImagePyramid.cpp:307-310), corner
+ *            cvRound((x - w / 2) * scale), cvRound((y - h / 2) * scale); no such layer / outside the layer -> weight 0
+ *   equal (layer, corner) = one patch, classified once (CachingPyramidFeatureExtractor + the model's result cache)
+ *   weight = 0.5 * P_wvm; the max_svm_patches (reference: 8) WVM-positive patches of highest probability also get the SVM:
+ *   target = SVM positive, weight = 2 * weight * P_svm. max_svm_patches <= 0: no cut (= evaluate(Sample&) per sample).
+ * std::sort in the reference leaves the order of equal probabilities open; ties keep first-seen order here. */
+int evaluate_samples(fdb_detector* det, const uint8_t* frame_host, int64_t pitch, const int32_t* xywh, int64_t n,
+		int32_t max_svm_patches, uint8_t* target_out, double* weight_out) {
+	const Plan& plan = det->plan;
+	fdb_ctx* c = det->ctx;
+	cudaStream_t st = c->stream;
+	Slot& sl = det->slots[0];
+	const int pw = det->desc.patch_width, ph = det->desc.patch_height, npix = pw * ph;
+	std::vector<int> sample_patch((size_t)n, -1);
+	std::vector<SvmItem> items;
+	std::vector<std::pair<int64_t, int>> seen; /* (key, patch index), sorted insert */
+	for (int64_t i = 0; i < n; ++i) {
+		const int x = xywh[4 * i], y = xywh[4 * i + 1], w = xywh[4 * i + 2], h = xywh[4 * i + 3];
+		target_out[i] = 0; weight_out[i] = 0.0;
+		if (w <= 0) continue;
+		const double power = std::log((double)pw / (double)w) / std::log(plan.incremental_scale_factor);
+		const int index = (int)std::round(power);
+		int li = -1;
+		for (size_t k = 0; k < plan.layers.size(); ++k) if (plan.layers[k].index == index) li = (int)k;
+		if (li < 0) continue;
+		const PlanLayer& L = plan.layers[(size_t)li];
+		const int px = cv_round((x - w / 2) * L.scale), py = cv_round((y - h / 2) * L.scale);
+		if (px < 0 || py < 0 || px + pw > L.width || py + ph > L.height) continue; /* DirectPyramidFeatureExtractor.cpp:135-136 */
+		const int64_t key = ((int64_t)li << 48) | ((int64_t)py << 24) | (int64_t)px;
+		auto pos = std::lower_bound(seen.begin(), seen.end(), std::make_pair(key, -1));
+		if (pos == seen.end() || pos->first != key) {
+			SvmItem it; it.frame = 0; it.layer = li; it.x = px; it.y = py;
+			pos = seen.insert(pos, std::make_pair(key, (int)items.size()));
+			items.push_back(it);
+		}
+		sample_patch[(size_t)i] = pos->second;
+	}
+	const int m = (int)items.size();
+	if (m == 0) return FDB_OK;
+	std::vector<void*> tmp;
+	SvmItem* d_items; uint8_t* d_patches; fdb_window_score* d_scores; double* d_dist;
+	int s = dev_alloc(&d_items, (size_t)m, tmp);
+	if (!s) s = dev_alloc(&d_patches, (size_t)m * npix, tmp);
+	if (!s) s = dev_alloc(&d_scores, (size_t)m, tmp);
+	if (!s) s = dev_alloc(&d_dist, (size_t)m, tmp);
+	if (s) { free_all(tmp); return s; }
+	std::vector<fdb_window_score> scores((size_t)m);
+	auto run = [&]() -> int {
+		CUDA_TRY(cudaMemcpy2DAsync(sl.d_frames, (size_t)plan.width, frame_host, (size_t)pitch, (size_t)plan.width, (size_t)plan.height,
+				cudaMemcpyHostToDevice, st));
+		sl.frames_dev = sl.d_frames; sl.base = 0; sl.n = 1;
+		int r = enqueue_stage1(det, sl, st, sl.d_frames, 1, plan, det->d_layers, 0, nullptr, nullptr, false);
+		if (r) return r;
+		CUDA_TRY(cudaMemcpyAsync(d_items, items.data(), sizeof(SvmItem) * (size_t)m, cudaMemcpyHostToDevice, st));
+		launch_hq64_items(st, pw, ph, sl.d_frames, plan.width, plan.height, sl.d_arena, plan.arena_bytes, det->d_layers, d_items, m, d_patches);
+		DevWvm wm = det->wvm->dev;
+		launch_wvm_patches(st, wm, d_patches, m, d_scores);
+		c->launches += 2;
+		CUDA_TRY(cudaGetLastError());
+		CUDA_TRY(cudaMemcpyAsync(scores.data(), d_scores, sizeof(fdb_window_score) * (size_t)m, cudaMemcpyDeviceToHost, st));
+		CUDA_TRY(cudaStreamSynchronize(st));
+		return FDB_OK;
+	};
+	s = run();
+	if (s) { free_all(tmp); return s; }
+	/* WVM results per patch (ProbabilisticWvmClassifier::getProbability) */
+	std::vector<double> pwvm((size_t)m);
+	std::vector<int> remaining; /* WVM-positive patches in first-seen order */
+	const fdb_wvm* wv = det->wvm;
+	for (int k = 0; k < m; ++k) {
+		const fdb_window_score& r = scores[(size_t)k];
+		pwvm[(size_t)k] = wvm_probability(wv->logistic_a, wv->logistic_b, r.fout);
+		if (r.level + 1 == wv->dev.num_lin && r.fout >= wv->thresholds[(size_t)r.level]) remaining.push_back(k);
+	}
+	for (int64_t i = 0; i < n; ++i) if (sample_patch[(size_t)i] >= 0) weight_out[i] = 0.5 * pwvm[(size_t)sample_patch[(size_t)i]];
+	if (remaining.empty() || !det->svm) { free_all(tmp); return FDB_OK; }
+	if (max_svm_patches > 0 && (int)remaining.size() > max_svm_patches) {
+		std::stable_sort(remaining.begin(), remaining.end(), [&](int a, int b) { return pwvm[(size_t)a] > pwvm[(size_t)b]; });
+		remaining.resize((size_t)max_svm_patches);
+	}
+	/* SVM on the chosen patches: gather their equalised patches on the device side by re-running the item kernel on the subset */
+	const int q = (int)remaining.size();
+	std::vector<SvmItem> sub((size_t)q);
+	for (int k = 0; k < q; ++k) sub[(size_t)k] = items[(size_t)remaining[(size_t)k]];
+	std::vector<double> dist((size_t)q);
+	auto run2 = [&]() -> int {
+		CUDA_TRY(cudaMemcpyAsync(d_items, sub.data(), sizeof(SvmItem) * (size_t)q, cudaMemcpyHostToDevice, st));
+		launch_svm_windows(st, det->svm->dev, pw, ph, sl.d_frames, plan.width, plan.height, sl.d_arena, plan.arena_bytes, det->d_layers,
+				d_items, q, d_dist);
+		c->launches++;
+		CUDA_TRY(cudaGetLastError());
+		CUDA_TRY(cudaMemcpyAsync(dist.data(), d_dist, sizeof(double) * (size_t)q, cudaMemcpyDeviceToHost, st));
+		CUDA_TRY(cudaStreamSynchronize(st));
+		return FDB_OK;
+	};
+	s = run2();
+	free_all(tmp);
+	if (s) return s;
+	std::vector<int> patch_rank((size_t)m, -1);
+	for (int k = 0; k < q; ++k) patch_rank[(size_t)remaining[(size_t)k]] = k;
+	for (int64_t i = 0; i < n; ++i) {
+		const int pidx = sample_patch[(size_t)i];
+		if (pidx < 0 || patch_rank[(size_t)pidx] < 0) continue;
+		const double d = dist[(size_t)patch_rank[(size_t)pidx]];
+		target_out[i] = d >= det->svm->dev.threshold ? 1 : 0;
+		weight_out[i] = 2 * weight_out[i] * svm_probability(det->svm->logistic_a, det->svm->logistic_b, d);
+	}
+	return FDB_OK;
+}
+
+
 int detect_pipeline(fdb_detector* det, const uint8_t* frames, bool frames_on_device, int64_t pitch, int32_t n_frames,
 		int32_t stage, fdb_window_score* dense_out, bool dense_on_device, fdb_detection* dets_out, int64_t det_cap,
 		int64_t* n_dets) {
@@ -1116,6 +1230,18 @@ int fdb_extract_features(fdb_detector* det, const uint8_t* frame_host, int64_t p
 		CUDA_TRY(cudaStreamSynchronize(st));
 	}
 	return FDB_OK;
+}
+
+int fdb_evaluate_samples(fdb_detector* det, const uint8_t* frame_host, int64_t pitch, const int32_t* samples_xywh, int64_t n,
+		int32_t max_svm_patches, uint8_t* target_out, double* weight_out) {
+	if (!det || !det->prepared) return fail(FDB_ERR_INVALID_ARGUMENT, "detector not prepared (call fdb_detector_prepare)");
+	int s = check_ctx(det->ctx); if (s) return s;
+	if (!det->wvm) return fail(FDB_ERR_INVALID_ARGUMENT, "fdb_evaluate_samples needs a detector with a WVM");
+	if (det->has_feature && det->feat.kind != FDB_FEATURE_HQ64)
+		return fail(FDB_ERR_UNSUPPORTED, "fdb_evaluate_samples: both classifiers work on the HistEq64 patch (WvmSvmModel.cpp:53-59)");
+	if (n < 0 || !frame_host || (n > 0 && (!samples_xywh || !target_out || !weight_out))) return fail(FDB_ERR_INVALID_ARGUMENT, "null buffer");
+	if (pitch < det->plan.width) return fail(FDB_ERR_INVALID_ARGUMENT, "pitch smaller than the frame width");
+	return evaluate_samples(det, frame_host, pitch, samples_xywh, n, max_svm_patches, target_out, weight_out);
 }
 
 int fdb_detect_single(fdb_detector* det, const uint8_t* frames_host, int64_t pitch, int32_t n_frames, double* distance_out,

@@ -114,6 +114,50 @@ __global__ void __launch_bounds__(SVM_THREADS) svm_kernel(const DevSvm s, int pa
 	if (tid == 0) distance_out[item] = distance;
 }
 
+/* HistEq64 patches (HistEq64Filter.cpp:32-125) of a list of windows -> [n][patch_w * patch_h] u8: the patch data of
+ * DirectPyramidFeatureExtractor::extract(x, y, width, height) (DirectPyramidFeatureExtractor.cpp:67-73,133-147) for
+ * sparse callers (condensation::WvmSvmModel). One CTA of 128 threads per window. */
+__global__ void __launch_bounds__(128) hq64_items_kernel(int patch_w, int patch_h, const uint8_t* __restrict__ frames, int W, int H,
+		const uint8_t* __restrict__ arena, int64_t arena_stride, const DevLayer* __restrict__ layers,
+		const SvmItem* __restrict__ items, uint8_t* __restrict__ out) {
+	__shared__ uint32_t s_hist[64];
+	__shared__ uint8_t s_eq[64];
+	const int tid = threadIdx.x;
+	const SvmItem it = items[blockIdx.x];
+	const DevLayer L = layers[it.layer];
+	const uint8_t* img = (L.offset < 0 ? frames + (int64_t)it.frame * W * H
+			: arena + (int64_t)it.frame * arena_stride + L.offset) + (int64_t)it.y * L.pitch + it.x;
+	const int npix = patch_w * patch_h;
+	if (tid < 64) s_hist[tid] = 0;
+	__syncthreads();
+	for (int i = tid; i < npix; i += 128) {
+		const int r = i / patch_w, c = i - r * patch_w;
+		atomicAdd(&s_hist[img[(int64_t)r * L.pitch + c] >> 2], 1u);
+	}
+	__syncthreads();
+	if (tid == 0) { /* sequential float cumsum, HistEq64Filter.cpp:70-87,97 */
+		const float stretch = __fdiv_rn(255.0f, (float)npix);
+		float cdf = 0.f;
+		for (int b = 0; b < 64; ++b) {
+			cdf = __fadd_rn(cdf, __fmul_rn((float)s_hist[b], stretch));
+			const float fl = floorf(cdf);
+			s_eq[b] = (uint8_t)((int)fl + (__fsub_rn(cdf, fl) >= 0.5f ? 1 : 0));
+		}
+	}
+	__syncthreads();
+	uint8_t* dst = out + (int64_t)blockIdx.x * npix;
+	for (int i = tid; i < npix; i += 128) {
+		const int r = i / patch_w, c = i - r * patch_w;
+		dst[i] = s_eq[img[(int64_t)r * L.pitch + c] >> 2];
+	}
+}
+
+void launch_hq64_items(cudaStream_t st, int patch_w, int patch_h, const uint8_t* frames, int W, int H, const uint8_t* arena,
+		int64_t arena_stride, const DevLayer* layers, const SvmItem* items, int n_items, uint8_t* out) {
+	if (n_items == 0) return;
+	hq64_items_kernel<<<(unsigned)n_items, 128, 0, st>>>(patch_w, patch_h, frames, W, H, arena, arena_stride, layers, items, out);
+}
+
 static size_t svm_smem_bytes(const DevSvm& s) {
 	size_t xbytes = s.sv_type == FDB_SV_F32 ? sizeof(float) * (size_t)s.dim : sizeof(uint32_t) * (size_t)s.nwords;
 	return sizeof(double) * SVM_CHUNK + ((xbytes + 15) / 16) * 16;

@@ -162,6 +162,8 @@ void launch_svm_windows(cudaStream_t st, const DevSvm& s, int patch_w, int patch
 		const uint8_t* arena, int64_t arena_stride, const DevLayer* layers, const SvmItem* items, int n_items,
 		double* distance_out);
 void launch_svm_vectors(cudaStream_t st, const DevSvm& s, const void* vectors, int n, double* distance_out);
+void launch_hq64_items(cudaStream_t st, int patch_w, int patch_h, const uint8_t* frames, int W, int H, const uint8_t* arena,
+		int64_t arena_stride, const DevLayer* layers, const SvmItem* items, int n_items, uint8_t* out);
 
 } // namespace fdb
 #endif

@@ -299,6 +299,16 @@ class SlidingWindowCascade:
             dets.ctypes.data, det_cap, C.byref(cnt)))
         return dets[:cnt.value].copy(), dist
 
+    def evaluate_samples(self, frame, samples_xywh, max_svm_patches=8):
+        """condensation::WvmSvmModel::evaluate(image, samples): samples [n, 4] = centre x, centre y, width, height ->
+        (target [n] bool, weight [n] float64)"""
+        frame = np.ascontiguousarray(frame, np.uint8)
+        smp = np.ascontiguousarray(samples_xywh, np.int32).reshape(-1, 4)
+        target = np.zeros(len(smp), np.uint8); weight = np.zeros(len(smp), np.float64)
+        capi.check(self.ctx.lib, self.ctx.lib.fdb_evaluate_samples(
+            self.h, frame.ctypes.data, frame.shape[1], smp.ctypes.data, len(smp), max_svm_patches, target.ctypes.data, weight.ctypes.data))
+        return target.astype(bool), weight
+
     @property
     def single_dense(self):
         """True when detect_single runs as one tensor-core launch per chunk of frames (csrc/svm_dense.cu)"""

@@ -441,6 +441,17 @@ FDB_API int fdb_detector_single_dense(fdb_detector* det);
  * and the number of launches (one per chunk of frames): the roofline numerator of bench.py --workload single-psvm */
 FDB_API int fdb_detector_single_dense_profile(fdb_detector* det, double* kernel_ms, int32_t* launches);
 
+/* condensation::WvmSvmModel::evaluate(image, samples) (libCondensation/src/condensation/WvmSvmModel.cpp:74-119): the
+ * tracker's sparse use of the two classifiers on one frame. samples_xywh[i] = {centre x, centre y, width, height} (Sample.hpp);
+ * each sample's patch is DirectPyramidFeatureExtractor::extract(x, y, w, h) (DirectPyramidFeatureExtractor.cpp:67-73,133-147;
+ * layer choice ImagePyramid.cpp:307-310); equal patches are classified once (CachingPyramidFeatureExtractor + the model's
+ * cache). target_out[i] / weight_out[i] = Sample::isTarget / getWeight afterwards: no patch -> (0, 0); WVM-negative or not
+ * among the max_svm_patches (reference: 8) most probable WVM positives -> (0, 0.5 P_wvm); else (SVM positive, P_wvm P_svm).
+ * max_svm_patches <= 0 disables the cut (= MeasurementModel::evaluate(Sample&) for every sample). Needs a detector with a WVM
+ * (the SVM may be NULL: no second stage) working on HistEq64 patches. */
+FDB_API int fdb_evaluate_samples(fdb_detector* det, const uint8_t* frame_host, int64_t pitch, const int32_t* samples_xywh,
+		int64_t n, int32_t max_svm_patches, uint8_t* target_out, double* weight_out);
+
 /* Per-stage counters of the last detect call (TOT/TACC-style counters, ffpDetectApp.cpp:650-657):
  * [0] windows, [1] wvm positives, [2] after OE, [3] svm positives, [4] after NMS. */
 FDB_API int fdb_detector_last_counts(fdb_detector* det, int64_t counts[5]);

@@ -591,3 +591,53 @@ def ref_detect_frame(det_kwargs, wvm, svm, frame, stage=capi.FDB_STAGE_NMS, want
     if n < 0:
         raise RuntimeError("ref_detect_frame failed (%d)" % n)
     return dict(windows=int(nwin.value), dense=dense, det_windows=wins[:n].copy(), timing=list(tim))
+
+
+def evaluate_samples(det_kwargs, wvm, svm, frame, samples_xywh, max_svm_patches=8):
+    """condensation::WvmSvmModel::evaluate(image, samples) restated (libCondensation/src/condensation/WvmSvmModel.cpp:74-119)
+    over a caching extractor: DirectPyramidFeatureExtractor::extract(x, y, w, h) (DirectPyramidFeatureExtractor.cpp:67-73,
+    133-147), ImagePyramid::getLayer(double) (ImagePyramid.cpp:307-310), ImagePyramidLayer::getScaled
+    (ImagePyramidLayer.hpp:65-67). wvm / svm: Wvm / Svm oracle objects (svm may be None). Small inputs only (python loop).
+    Ties of equal WVM probability in the top-k cut keep first-seen order (std::sort leaves them open)."""
+    import math
+    pw, ph = det_kwargs["patch_width"], det_kwargs["patch_height"]
+    olc, layers = pyramid(frame, float(det_kwargs["incremental_scale_factor"]), det_kwargs["min_scale_factor"], det_kwargs["max_scale_factor"])
+    inc = math.pow(0.5, 1.0 / olc)  # ImagePyramid.cpp:90-91: the pyramid keeps the factor recomputed from the octave layer count
+    by_index = {idx: (scale, img) for idx, scale, img in layers}
+    n = len(samples_xywh)
+    target = np.zeros(n, bool); weight = np.zeros(n, np.float64)
+    cache, order, sample_key = {}, [], [None] * n
+    L = lib()
+    for i, (x, y, w, h) in enumerate(np.asarray(samples_xywh, np.int64).tolist()):
+        if w <= 0:
+            continue
+        power = math.log(float(pw) / float(w)) / math.log(inc)
+        index = int(math.floor(abs(power) + 0.5)) * (1 if power >= 0 else -1)  # std::round: half away from zero
+        if index not in by_index:
+            continue
+        scale, img = by_index[index]
+        half_w, half_h = int(w / 2), int(h / 2)  # C++ integer division truncates
+        px, py = L.fdo_cvround((x - half_w) * scale), L.fdo_cvround((y - half_h) * scale)
+        if px < 0 or py < 0 or px + pw > img.shape[1] or py + ph > img.shape[0]:
+            continue
+        key = (index, px, py)
+        if key not in cache:
+            patch = hq64(img[py:py + ph, px:px + pw]).ravel()
+            level, fout, prob, pos = wvm.eval(patch[None])
+            cache[key] = (bool(pos[0]), float(prob[0]), patch)
+            if pos[0]:
+                order.append(key)
+        sample_key[i] = key
+        weight[i] = 0.5 * cache[key][1]
+    if order and svm is not None:
+        if max_svm_patches > 0 and len(order) > max_svm_patches:
+            order = sorted(order, key=lambda k: -cache[k][1])[:max_svm_patches]  # sorted() is stable
+        res = {}
+        for key in order:
+            d, p, q = svm.eval(cache[key][2][None])
+            res[key] = (bool(q[0]), float(p[0]))
+        for i in range(n):
+            if sample_key[i] in res:
+                target[i] = res[sample_key[i]][0]
+                weight[i] = 2 * weight[i] * res[sample_key[i]][1]
+    return target, weight

@@ -1,5 +1,5 @@
 """The C++ adapters (adapters/fdb200_adapters.hpp) must compile against the reference's UNCHANGED
-interface headers: PyramidFeatureExtractor, ProbabilisticClassifier, Detector. Needs /root/reference
+interface headers: PyramidFeatureExtractor, ProbabilisticClassifier, Detector, condensation::MeasurementModel. Needs /root/reference
 (present where the driver runs the CPU suite, absent on the GPU box -> skipped there)."""
 import os
 import subprocess
@@ -15,7 +15,8 @@ def test_adapters_compile_against_reference_headers(tmp_path):
     cmd = ["g++", "-std=c++11", "-c", "-o", str(tmp_path / "check.o"),
            "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(ROOT, "adapters"), "-I" + os.path.join(ROOT, "oracle", "shim"),
            "-I" + os.path.join(REF, "libClassification", "include"), "-I" + os.path.join(REF, "libImageProcessing", "include"),
-           "-I" + os.path.join(REF, "libDetection", "include"), "-Wno-deprecated-declarations",
+           "-I" + os.path.join(REF, "libDetection", "include"), "-I" + os.path.join(REF, "libCondensation", "include"),
+           "-Wno-deprecated-declarations",
            os.path.join(ROOT, "adapters", "check_adapters.cpp")]
     r = subprocess.run(cmd, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-3000:]
