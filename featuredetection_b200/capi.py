@@ -12,7 +12,7 @@ LIB_PATH = os.environ.get("FDB_LIB") or os.path.join(_HERE, "csrc", "libfdb200.s
 FDB_OK = 0
 FDB_STAGE_WVM, FDB_STAGE_OE, FDB_STAGE_SVM, FDB_STAGE_NMS = 1, 2, 3, 4
 FDB_SV_U8, FDB_SV_F32 = 0, 1
-FDB_KERNEL_RBF = 0
+FDB_KERNEL_RBF, FDB_KERNEL_POLYNOMIAL, FDB_KERNEL_HIK, FDB_KERNEL_LINEAR = range(4)
 (FDB_FEATURE_HQ64, FDB_FEATURE_GRAY, FDB_FEATURE_HISTEQ, FDB_FEATURE_WHI, FDB_FEATURE_HOG, FDB_FEATURE_EHOG,
  FDB_FEATURE_LBP) = range(7)
 FDB_NORM_NONE, FDB_NORM_L2NORM, FDB_NORM_L2HYS, FDB_NORM_L1NORM, FDB_NORM_L1SQRT = range(5)
@@ -49,6 +49,7 @@ class SvmDesc(C.Structure):
         ("coefficients", C.POINTER(C.c_float)),
         ("bias", C.c_float), ("threshold", C.c_float),
         ("logistic_a", C.c_double), ("logistic_b", C.c_double),
+        ("poly_alpha", C.c_double), ("poly_constant", C.c_double), ("poly_degree", C.c_int32),
     ]
 
 

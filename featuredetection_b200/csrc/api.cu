@@ -334,7 +334,8 @@ int fdb_svm_create(fdb_ctx* ctx, const fdb_svm_desc* d, fdb_svm** out) {
 	int s = check_ctx(ctx); if (s) return s;
 	if (!d || !out) return fail(FDB_ERR_INVALID_ARGUMENT, "null argument");
 	*out = nullptr;
-	if (d->kernel != FDB_KERNEL_RBF) return fail(FDB_ERR_UNSUPPORTED, "SVM: only the RBF kernel is implemented");
+	if (d->kernel < FDB_KERNEL_RBF || d->kernel > FDB_KERNEL_LINEAR) return fail(FDB_ERR_INVALID_ARGUMENT, "SVM: unknown kernel kind");
+	if (d->kernel == FDB_KERNEL_POLYNOMIAL && d->poly_degree < 0) return fail(FDB_ERR_INVALID_ARGUMENT, "SVM: negative polynomial degree");
 	if (d->num_sv < 1 || d->dim < 1) return fail(FDB_ERR_INVALID_ARGUMENT, "SVM: empty model");
 	if (d->sv_type != FDB_SV_U8 && d->sv_type != FDB_SV_F32) return fail(FDB_ERR_INVALID_ARGUMENT, "SVM: bad sv_type");
 	if ((size_t)d->dim * 4 > 96 * 1024) return fail(FDB_ERR_UNSUPPORTED, "SVM: feature vector too long");
@@ -344,7 +345,8 @@ int fdb_svm_create(fdb_ctx* ctx, const fdb_svm_desc* d, fdb_svm** out) {
 	DevSvm& dv = m->dev;
 	dv.num_sv = d->num_sv; dv.dim = d->dim; dv.sv_type = d->sv_type;
 	dv.nwords = (d->dim + 3) / 4;
-	dv.gamma = d->gamma; dv.bias = d->bias; dv.threshold = d->threshold;
+	dv.kernel = d->kernel; dv.gamma = d->gamma; dv.bias = d->bias; dv.threshold = d->threshold;
+	dv.poly_alpha = d->poly_alpha; dv.poly_constant = d->poly_constant; dv.poly_degree = d->poly_degree;
 	dv.sv_words = nullptr; dv.sv_f32 = nullptr;
 	float* fp;
 	s = upload(d->coefficients, (size_t)d->num_sv, &fp, m->owned);
@@ -361,7 +363,7 @@ int fdb_svm_create(fdb_ctx* ctx, const fdb_svm_desc* d, fdb_svm** out) {
 			dv.sv_words = up;
 			/* tensor-core form for whole-batch evaluation (svm_dense.cu) */
 			SvmDenseHost dh;
-			if (!s && svm_dense_build(sv, d->coefficients, d->num_sv, d->dim, d->gamma, d->bias, d->threshold, &dh)) {
+			if (!s && d->kernel == FDB_KERNEL_RBF && svm_dense_build(sv, d->coefficients, d->num_sv, d->dim, d->gamma, d->bias, d->threshold, &dh)) {
 				uint8_t* bb; int* sq; double* cf; double* tb;
 				s = upload(dh.b_blocks.data(), dh.b_blocks.size(), &bb, m->owned);
 				if (!s) s = upload(dh.ssq.data(), dh.ssq.size(), &sq, m->owned);

@@ -45,10 +45,17 @@ int fdb_svm_file_load(const char* path, fdb_svm_file** out) {
 		file >> d.gamma;
 		d.kernel = FDB_KERNEL_RBF;
 		supported = true;
-	} else if (kernelType == "Polynomial") {
-		int degree; double constant, scale;
-		file >> degree >> constant >> scale;
-	} else if (kernelType != "Linear" && kernelType != "HIK") {
+	} else if (kernelType == "Polynomial") { /* SvmClassifier.cpp:76-77: degree, constant, alpha */
+		file >> d.poly_degree >> d.poly_constant >> d.poly_alpha;
+		d.kernel = FDB_KERNEL_POLYNOMIAL;
+		supported = true;
+	} else if (kernelType == "Linear") {
+		d.kernel = FDB_KERNEL_LINEAR;
+		supported = true;
+	} else if (kernelType == "HIK") {
+		d.kernel = FDB_KERNEL_HIK;
+		supported = true;
+	} else {
 		delete f;
 		return fail(FDB_ERR_RUNTIME, "SvmClassifier: Invalid kernel type: " + kernelType);
 	}
@@ -81,7 +88,7 @@ int fdb_svm_file_load(const char* path, fdb_svm_file** out) {
 	d.threshold = 0.0f;                        /* VectorMachineClassifier default */
 	d.logistic_a = 0.00556; d.logistic_b = -2.95; /* ProbabilisticSvmClassifier.hpp:36 defaults */
 	if (file >> tmp && tmp == "Logistic") file >> d.logistic_a >> d.logistic_b;
-	if (!supported) { delete f; return fail(FDB_ERR_UNSUPPORTED, "SvmClassifier: kernel " + kernelType + " is not evaluated on the GPU (RBF only)"); }
+	if (!supported) { delete f; return fail(FDB_ERR_UNSUPPORTED, "SvmClassifier: kernel " + kernelType + " is not supported"); }
 	*out = f;
 	return FDB_OK;
 }
@@ -363,10 +370,15 @@ int fdb_svm_mat_load(const char* classifier_path, const char* logistic_path, fdb
 	d.bias = (float)a->real[0];
 	const int nonLinType = (int)a->real[1];
 	const float basisParam = (float)(a->real[2] / 65025.0);
-	if (nonLinType == 1) return fail(FDB_ERR_UNSUPPORTED, "SvmClassifier: the polynomial kernel is not evaluated on the GPU (RBF only)");
-	if (nonLinType != 2) return fail(FDB_ERR_RUNTIME, "SvmClassifier: Unsupported kernel type. Currently, only polynomial and RBF kernels are supported.");
-	d.kernel = FDB_KERNEL_RBF;
-	d.gamma = basisParam; /* RbfKernel(double gamma) receives the float */
+	if (nonLinType == 1) { /* SvmClassifier.cpp:270-272: PolynomialKernel(1 / divisor, basisParam / divisor, polyPower), float arithmetic */
+		const int polyPower = (int)a->real[3];
+		const float divisor = (float)a->real[4];
+		d.kernel = FDB_KERNEL_POLYNOMIAL;
+		d.poly_alpha = 1 / divisor; d.poly_constant = basisParam / divisor; d.poly_degree = polyPower;
+	} else if (nonLinType == 2) {
+		d.kernel = FDB_KERNEL_RBF;
+		d.gamma = basisParam; /* RbfKernel(double gamma) receives the float */
+	} else return fail(FDB_ERR_RUNTIME, "SvmClassifier: Unsupported kernel type. Currently, only polynomial and RBF kernels are supported.");
 	a = mat_var(mf, "support_nonlin1");
 	if (!a) return fail(FDB_ERR_RUNTIME, "SvmClassifier: There is a nonlinear SVM in the file, but the matrix support_nonlin1 is lacking.");
 	if (a->dims.size() != 3) return fail(FDB_ERR_RUNTIME, "SvmClassifier: The matrix support_nonlin1 in the file should have 3 dimensions.");

@@ -86,24 +86,62 @@ __global__ void __launch_bounds__(SVM_THREADS) svm_kernel(const DevSvm s, int pa
 		const int cnt = min(SVM_CHUNK, s.num_sv - base);
 		for (int i = tid; i < cnt; i += SVM_THREADS) {
 			const int sv = base + i;
-			double ssd;
+			double kv;
 			if (MODE != 2) {
-				uint32_t acc = 0;
-				for (int j = 0; j < s.nwords; ++j) {
-					const uint32_t d = __vabsdiffu4(s_x[j], s.sv_words[(size_t)j * s.num_sv + sv]);
-					acc = __dp4a(d, d, acc);
+				const uint32_t* __restrict__ col = s.sv_words + sv;
+				if (s.kernel == FDB_KERNEL_RBF) {                             /* RbfKernel.hpp:39,78-88 */
+					uint32_t acc = 0;
+					for (int j = 0; j < s.nwords; ++j) {
+						const uint32_t d = __vabsdiffu4(s_x[j], col[(size_t)j * s.num_sv]);
+						acc = __dp4a(d, d, acc);
+					}
+					kv = exp(__dmul_rn(-s.gamma, (double)(int)acc));
+				} else if (s.kernel == FDB_KERNEL_HIK) {                      /* HistogramIntersectionKernel.hpp:59-67: int sum */
+					uint32_t acc = 0;
+					for (int j = 0; j < s.nwords; ++j) acc = __dp4a(__vminu4(s_x[j], col[(size_t)j * s.num_sv]), 0x01010101u, acc);
+					kv = (double)(int)acc;
+				} else {                                                      /* cv::Mat::dot on CV_8U: an exact integer */
+					uint32_t acc = 0;
+					for (int j = 0; j < s.nwords; ++j) acc = __dp4a(s_x[j], col[(size_t)j * s.num_sv], acc);
+					kv = (double)(int)acc;
 				}
-				ssd = (double)(int)acc;
 			} else {
 				const float* xf = reinterpret_cast<const float*>(s_x);
-				float sum = 0.f;
-				for (int k = 0; k < s.dim; ++k) {
-					const float diff = __fsub_rn(xf[k], s.sv_f32[(size_t)k * s.num_sv + sv]);
-					sum = __fadd_rn(sum, __fmul_rn(diff, diff));
+				const float* __restrict__ col = s.sv_f32 + sv;
+				if (s.kernel == FDB_KERNEL_RBF) {                             /* RbfKernel.hpp:97-108: float32, sequential */
+					float sum = 0.f;
+					for (int k = 0; k < s.dim; ++k) {
+						const float diff = __fsub_rn(xf[k], col[(size_t)k * s.num_sv]);
+						sum = __fadd_rn(sum, __fmul_rn(diff, diff));
+					}
+					kv = exp(__dmul_rn(-s.gamma, (double)sum));
+				} else if (s.kernel == FDB_KERNEL_HIK) {                      /* HistogramIntersectionKernel.hpp:72-80: float32 sum */
+					float sum = 0.f;
+					for (int k = 0; k < s.dim; ++k) sum = __fadd_rn(sum, fminf(xf[k], col[(size_t)k * s.num_sv]));
+					kv = (double)sum;
+				} else {
+					/* cv::Mat::dot on CV_32F (OpenCV 2.4.3 dotProd_<float, double>): float64 products, four at a time */
+					double r = 0.0;
+					int k = 0;
+					for (; k <= s.dim - 4; k += 4) {
+						double q = __dmul_rn((double)xf[k], (double)col[(size_t)k * s.num_sv]);
+						q = __dadd_rn(q, __dmul_rn((double)xf[k + 1], (double)col[(size_t)(k + 1) * s.num_sv]));
+						q = __dadd_rn(q, __dmul_rn((double)xf[k + 2], (double)col[(size_t)(k + 2) * s.num_sv]));
+						q = __dadd_rn(q, __dmul_rn((double)xf[k + 3], (double)col[(size_t)(k + 3) * s.num_sv]));
+						r = __dadd_rn(r, q);
+					}
+					for (; k < s.dim; ++k) r = __dadd_rn(r, __dmul_rn((double)xf[k], (double)col[(size_t)k * s.num_sv]));
+					kv = r;
 				}
-				ssd = (double)sum;
 			}
-			const double kv = exp(__dmul_rn(-s.gamma, ssd));                 /* RbfKernel.hpp:39 */
+			if (s.kernel == FDB_KERNEL_POLYNOMIAL) {                          /* PolynomialKernel.hpp:38-40,62-70 */
+				double tmp = __dadd_rn(__dmul_rn(s.poly_alpha, kv), s.poly_constant), ret = 1.0;
+				for (int t = s.poly_degree; t > 0; t /= 2) {
+					if (t % 2 == 1) ret = __dmul_rn(ret, tmp);
+					tmp = __dmul_rn(tmp, tmp);
+				}
+				kv = ret;
+			}
 			s_prod[i] = __dmul_rn((double)s.coef[sv], kv);                   /* SvmClassifier.cpp:58 */
 		}
 		__syncthreads();

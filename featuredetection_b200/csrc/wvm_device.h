@@ -75,7 +75,9 @@ struct Strip {
 /* SvmClassifier (RBF) state; support vectors transposed to [word][sv] for coalesced reads */
 struct DevSvm {
 	int num_sv, dim, nwords, sv_type;
+	int kernel;                     /* fdb_kernel_kind */
 	double gamma;
+	double poly_alpha, poly_constant; int poly_degree;
 	float bias, threshold;
 	const uint32_t* sv_words;       /* u8: [nwords][num_sv] packed 4 px per word */
 	const float* sv_f32;            /* f32: [dim][num_sv] */

@@ -154,19 +154,23 @@ class SvmModel:
     """Host-side state of an SvmClassifier (RBF) + logistic (SvmClassifier.hpp:165-167)."""
 
     def __init__(self, support_vectors, coefficients, gamma, bias=0.0, threshold=0.0,
-                 logistic_a=0.00556, logistic_b=-2.95):
+                 logistic_a=0.00556, logistic_b=-2.95, kernel="rbf", alpha=1.0, constant=0.0, degree=2):
         sv = np.ascontiguousarray(support_vectors)
         assert sv.ndim == 2 and sv.dtype in (np.uint8, np.float32)
         self.sv = sv
         self.coef = np.ascontiguousarray(coefficients, np.float32)
         self.gamma = float(gamma)
+        self.kernel = {"rbf": capi.FDB_KERNEL_RBF, "polynomial": capi.FDB_KERNEL_POLYNOMIAL, "hik": capi.FDB_KERNEL_HIK,
+                       "linear": capi.FDB_KERNEL_LINEAR}[kernel]
+        self.alpha, self.constant, self.degree = float(alpha), float(constant), int(degree)
         self.bias, self.threshold = float(np.float32(bias)), float(np.float32(threshold))
         self.logistic_a, self.logistic_b = float(logistic_a), float(logistic_b)
 
     def desc(self):
         d = capi.SvmDesc()
-        d.kernel = capi.FDB_KERNEL_RBF
+        d.kernel = self.kernel
         d.gamma = self.gamma
+        d.poly_alpha, d.poly_constant, d.poly_degree = self.alpha, self.constant, self.degree
         d.num_sv, d.dim = self.sv.shape
         d.sv_type = capi.FDB_SV_U8 if self.sv.dtype == np.uint8 else capi.FDB_SV_F32
         d.support_vectors = self.sv.ctypes.data

@@ -41,7 +41,7 @@ extern "C" {
 #define FDB_API __attribute__((visibility("default")))
 #endif
 
-#define FDB_ABI_VERSION 1
+#define FDB_ABI_VERSION 2
 
 typedef enum fdb_status {
 	FDB_OK = 0,
@@ -96,7 +96,10 @@ typedef struct fdb_wvm_desc {
 } fdb_wvm_desc;
 
 typedef enum fdb_kernel_kind {
-	FDB_KERNEL_RBF = 0 /* classification::RbfKernel (RbfKernel.hpp:32-40) */
+	FDB_KERNEL_RBF = 0,        /* classification::RbfKernel (RbfKernel.hpp:32-40): exp(-gamma * sum (x - y)^2) */
+	FDB_KERNEL_POLYNOMIAL = 1, /* classification::PolynomialKernel (PolynomialKernel.hpp:38-40,62-70): powi(alpha * x.y + constant, degree) */
+	FDB_KERNEL_HIK = 2,        /* classification::HistogramIntersectionKernel (HistogramIntersectionKernel.hpp:31-39,59-83): sum min(x, y) */
+	FDB_KERNEL_LINEAR = 3      /* classification::LinearKernel (LinearKernel.hpp:27-29): x.y (cv::Mat::dot) */
 } fdb_kernel_kind;
 
 typedef enum fdb_sv_type {
@@ -120,6 +123,9 @@ typedef struct fdb_svm_desc {
 	float threshold;         /* VectorMachineClassifier::threshold */
 	double logistic_a;
 	double logistic_b;
+	double poly_alpha;       /* PolynomialKernel::alpha (ABI version 2) */
+	double poly_constant;    /* PolynomialKernel::constant */
+	int32_t poly_degree;     /* PolynomialKernel::degree */
 } fdb_svm_desc;
 
 /* Image pyramid + window extraction parameters.

@@ -413,6 +413,7 @@ double fdo_wvm_probability(const fdo_wvm* m, float fout) {
  * SVM (SvmClassifier.cpp:44-60; RbfKernel.hpp:32-40,78-108; ProbabilisticSvmClassifier.cpp:54-58)
  * ------------------------------------------------------------------------------------------- */
 struct fdo_svm {
+	int kernel; double poly_alpha, poly_constant; int poly_degree;
 	double gamma;
 	int num_sv, dim, sv_type;
 	void* sv;
@@ -423,6 +424,7 @@ struct fdo_svm {
 
 fdo_svm* fdo_svm_create(const fdb_svm_desc* d) {
 	fdo_svm* s = (fdo_svm*)calloc(1, sizeof(fdo_svm));
+	s->kernel = d->kernel; s->poly_alpha = d->poly_alpha; s->poly_constant = d->poly_constant; s->poly_degree = d->poly_degree;
 	s->gamma = d->gamma; s->num_sv = d->num_sv; s->dim = d->dim; s->sv_type = d->sv_type;
 	size_t es = d->sv_type == FDB_SV_U8 ? 1 : 4;
 	s->sv = dup_mem(d->support_vectors, es * (size_t)d->num_sv * d->dim);
@@ -437,25 +439,70 @@ void fdo_svm_free(fdo_svm* s) {
 	free(s->sv); free(s->coef); free(s);
 }
 
-double fdo_svm_distance(const fdo_svm* s, const void* x) {
-	double distance = -s->bias;                                             /* SvmClassifier.cpp:56 */
-	for (int i = 0; i < s->num_sv; ++i) {
+/* cv::Mat::dot (OpenCV 2.4.3 modules/core/src/matmul.cpp dotProd_): CV_8U sums integer products (exact); CV_32F is
+ * dotProd_<float, double>: float64 products, four added left to right, then to the running sum (CV_ENABLE_UNROLLED) */
+static double mat_dot(const void* a, const void* b, int n, int sv_type) {
+	if (sv_type == FDB_SV_U8) {
+		const uint8_t* l = (const uint8_t*)a; const uint8_t* r = (const uint8_t*)b;
+		long long sum = 0;
+		for (int k = 0; k < n; ++k) sum += (int)l[k] * (int)r[k];
+		return (double)sum;
+	}
+	const float* l = (const float*)a; const float* r = (const float*)b;
+	double result = 0;
+	int i = 0;
+	for (; i <= n - 4; i += 4)
+		result += (double)l[i] * r[i] + (double)l[i + 1] * r[i + 1] + (double)l[i + 2] * r[i + 2] + (double)l[i + 3] * r[i + 3];
+	for (; i < n; ++i) result += (double)l[i] * r[i];
+	return result;
+}
+
+/* Kernel::compute of the four kernels (RbfKernel.hpp:32-40,78-108; PolynomialKernel.hpp:38-40,62-70;
+ * HistogramIntersectionKernel.hpp:31-39,59-83; LinearKernel.hpp:27-29) */
+double fdo_kernel_value(int kernel, double gamma, double alpha, double constant, int degree, const void* x, const void* y, int dim, int sv_type) {
+	if (kernel == FDB_KERNEL_RBF) {
 		double ssd;
-		if (s->sv_type == FDB_SV_U8) {                                      /* RbfKernel.hpp:78-88 */
-			const uint8_t* l = (const uint8_t*)x;
-			const uint8_t* r = (const uint8_t*)s->sv + (size_t)i * s->dim;
+		if (sv_type == FDB_SV_U8) {                                         /* RbfKernel.hpp:78-88 */
+			const uint8_t* l = (const uint8_t*)x; const uint8_t* r = (const uint8_t*)y;
 			int sum = 0;
-			for (int k = 0; k < s->dim; ++k) { int diff = l[k] - r[k]; sum += diff * diff; }
+			for (int k = 0; k < dim; ++k) { int diff = l[k] - r[k]; sum += diff * diff; }
 			ssd = sum;
 		} else {                                                            /* RbfKernel.hpp:97-108 */
-			const float* l = (const float*)x;
-			const float* r = (const float*)s->sv + (size_t)i * s->dim;
+			const float* l = (const float*)x; const float* r = (const float*)y;
 			float sum = 0;
-			for (int k = 0; k < s->dim; ++k) { float diff = l[k] - r[k]; sum += diff * diff; }
+			for (int k = 0; k < dim; ++k) { float diff = l[k] - r[k]; sum += diff * diff; }
 			ssd = sum;
 		}
-		distance += s->coef[i] * exp(-s->gamma * ssd);                      /* SvmClassifier.cpp:58, RbfKernel.hpp:39 */
+		return exp(-gamma * ssd);                                           /* RbfKernel.hpp:39 */
 	}
+	if (kernel == FDB_KERNEL_HIK) {
+		if (sv_type == FDB_SV_U8) {                                         /* HistogramIntersectionKernel.hpp:59-67 */
+			const uint8_t* l = (const uint8_t*)x; const uint8_t* r = (const uint8_t*)y;
+			int sum = 0;
+			for (int k = 0; k < dim; ++k) sum += l[k] < r[k] ? l[k] : r[k];
+			return sum;
+		}
+		const float* l = (const float*)x; const float* r = (const float*)y; /* HistogramIntersectionKernel.hpp:72-80 */
+		float sum = 0;
+		for (int k = 0; k < dim; ++k) sum += r[k] < l[k] ? r[k] : l[k];     /* std::min(l, r) */
+		return sum;
+	}
+	const double dot = mat_dot(x, y, dim, sv_type);
+	if (kernel == FDB_KERNEL_LINEAR) return dot;                            /* LinearKernel.hpp:28 */
+	double tmp = alpha * dot + constant, ret = 1.0;                         /* PolynomialKernel.hpp:39,62-70 */
+	for (int t = degree; t > 0; t /= 2) {
+		if (t % 2 == 1) ret *= tmp;
+		tmp = tmp * tmp;
+	}
+	return ret;
+}
+
+double fdo_svm_distance(const fdo_svm* s, const void* x) {
+	double distance = -s->bias;                                             /* SvmClassifier.cpp:56 */
+	const size_t es = s->sv_type == FDB_SV_U8 ? 1 : 4;
+	for (int i = 0; i < s->num_sv; ++i)                                     /* SvmClassifier.cpp:58 */
+		distance += s->coef[i] * fdo_kernel_value(s->kernel, s->gamma, s->poly_alpha, s->poly_constant, s->poly_degree, x,
+				(const uint8_t*)s->sv + (size_t)i * s->dim * es, s->dim, s->sv_type);
 	return distance;
 }
 

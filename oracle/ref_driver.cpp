@@ -19,6 +19,9 @@
 #include "classification/SvmClassifier.hpp"
 #include "classification/ProbabilisticSvmClassifier.hpp"
 #include "classification/RbfKernel.hpp"
+#include "classification/PolynomialKernel.hpp"
+#include "classification/HistogramIntersectionKernel.hpp"
+#include "classification/LinearKernel.hpp"
 #include "imageprocessing/HistEq64Filter.hpp"
 #include "imageprocessing/Patch.hpp"
 #include "detection/ClassifiedPatch.hpp"
@@ -136,9 +139,16 @@ void ref_wvm_eval(void* p, const uint8_t* patch, int* level, float* fout, double
 	if (positive) *positive = pr.first ? 1 : 0;
 }
 
+static shared_ptr<classification::Kernel> ref_make_kernel(int kind, double gamma, double alpha, double constant, int degree) {
+	if (kind == FDB_KERNEL_POLYNOMIAL) return make_shared<classification::PolynomialKernel>(alpha, constant, degree);
+	if (kind == FDB_KERNEL_HIK) return make_shared<classification::HistogramIntersectionKernel>();
+	if (kind == FDB_KERNEL_LINEAR) return make_shared<classification::LinearKernel>();
+	return make_shared<classification::RbfKernel>(gamma);
+}
+
 void* ref_svm_create(const fdb_svm_desc* d) {
 	RefSvm* r = new RefSvm;
-	r->svm = make_shared<classification::SvmClassifier>(make_shared<classification::RbfKernel>(d->gamma));
+	r->svm = make_shared<classification::SvmClassifier>(ref_make_kernel(d->kernel, d->gamma, d->poly_alpha, d->poly_constant, d->poly_degree));
 	vector<Mat> svs;
 	for (int i = 0; i < d->num_sv; ++i) {
 		if (d->sv_type == FDB_SV_U8) {

@@ -175,7 +175,11 @@ public:
 		double r = 0;
 		size_t n = total() * channels();
 		if (depth() == CV_8U) { const uchar* a = ptr<uchar>(); const uchar* b = m.ptr<uchar>(); for (size_t i = 0; i < n; ++i) r += (double)a[i] * b[i]; }
-		else if (depth() == CV_32F) { const float* a = ptr<float>(); const float* b = m.ptr<float>(); for (size_t i = 0; i < n; ++i) r += (double)a[i] * b[i]; }
+		else if (depth() == CV_32F) { /* OpenCV 2.4.3 dotProd_<float, double> with CV_ENABLE_UNROLLED: four products at a time */
+			const float* a = ptr<float>(); const float* b = m.ptr<float>(); size_t i = 0;
+			for (; i + 4 <= n; i += 4) r += (double)a[i] * b[i] + (double)a[i + 1] * b[i + 1] + (double)a[i + 2] * b[i + 2] + (double)a[i + 3] * b[i + 3];
+			for (; i < n; ++i) r += (double)a[i] * b[i];
+		}
 		else if (depth() == CV_64F) { const double* a = ptr<double>(); const double* b = m.ptr<double>(); for (size_t i = 0; i < n; ++i) r += a[i] * b[i]; }
 		else throw std::runtime_error("shim Mat::dot: unsupported depth");
 		return r;

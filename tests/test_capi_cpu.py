@@ -20,7 +20,7 @@ def test_every_declared_symbol_is_exported(built):
     lib = capi.load_library()
     for name in declared:
         assert hasattr(lib, name)
-    assert lib.fdb_abi_version() == 1
+    assert lib.fdb_abi_version() == 2
 
 
 def _has_gpu():
