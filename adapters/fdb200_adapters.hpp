@@ -143,6 +143,48 @@ private:
 	int dim, type;
 };
 
+/* classification::ProbabilisticRvmClassifier replacement (ProbabilisticRvmClassifier.cpp:42-64 over RvmClassifier.cpp:50-112) */
+class B200ProbabilisticRvmClassifier : public classification::ProbabilisticClassifier {
+public:
+	B200ProbabilisticRvmClassifier(std::shared_ptr<Context> context, const fdb_rvm_desc& desc) :
+			context(context), handle(nullptr), dim(desc.dim), type(desc.sv_type) {
+		check(fdb_rvm_create(context->get(), &desc, &handle));
+	}
+	~B200ProbabilisticRvmClassifier() { fdb_rvm_destroy(handle); }
+
+	bool classify(const cv::Mat& featureVector) const { return evaluate(featureVector).positive; }
+	std::pair<bool, double> getConfidence(const cv::Mat& featureVector) const {
+		const Result r = evaluate(featureVector); /* RvmClassifier::getConfidence(pair), RvmClassifier.cpp:59-64 */
+		return std::make_pair(r.positive, r.positive ? r.distance : -r.distance);
+	}
+	std::pair<bool, double> getProbability(const cv::Mat& featureVector) const {
+		const Result r = evaluate(featureVector);
+		return std::make_pair(r.positive, r.probability);
+	}
+	/* RvmClassifier::computeHyperplaneDistance: (level reached, distance) */
+	std::pair<int, double> computeHyperplaneDistance(const cv::Mat& featureVector) const {
+		const Result r = evaluate(featureVector);
+		return std::make_pair(r.level, r.distance);
+	}
+	void setNumFiltersToUse(unsigned int numFilters) { check(fdb_rvm_set_num_filters_to_use(handle, (int32_t)numFilters)); }
+	fdb_rvm* get() const { return handle; }
+
+private:
+	struct Result { int level; double distance, probability; bool positive; };
+	Result evaluate(const cv::Mat& v) const {
+		const int want = type == FDB_SV_U8 ? CV_8U : CV_32F;
+		if (v.depth() != want || !v.isContinuous() || (int)(v.total() * v.channels()) != dim)
+			throw std::invalid_argument("fdb200: RVM feature vector has the wrong type or length");
+		int32_t level = 0; double d = 0, p = 0; uint8_t pos = 0;
+		check(fdb_rvm_get_probability(handle, v.ptr<uchar>(0), 1, &level, &d, &p, &pos));
+		Result r = {level, d, p, pos != 0};
+		return r;
+	}
+	std::shared_ptr<Context> context;
+	fdb_rvm* handle;
+	int dim, type;
+};
+
 /* detection::Detector replacement: FiveStageSlidingWindowDetector (stage = FDB_STAGE_NMS, svm != null)
  * or plain SlidingWindowDetector (stage = FDB_STAGE_WVM). It is also the PyramidFeatureExtractor of the
  * reference graph (ImagePyramid + GrayscaleFilter + DirectPyramidFeatureExtractor + HistEq64Filter). */

@@ -466,7 +466,7 @@ def _single_worker_run(frame_ids):
         _, layers = fo.pyramid(frame, kw["incremental_scale_factor"], kw["min_scale_factor"], kw["max_scale_factor"])
         raw, w0 = [], 0
         for _, _, img in layers:
-            wx, wy = img.shape[1] - 19, img.shape[0] - 19
+            wx, wy = img.shape[1] - 20, img.shape[0] - 20  # strict < loop bounds (DirectPyramidFeatureExtractor.cpp:101-103)
             for w in range((-w0) % SINGLE_STRIDE, wx * wy, SINGLE_STRIDE):
                 y, x = divmod(w, wx)
                 raw.append(img[y:y + 20, x:x + 20])

@@ -53,6 +53,20 @@ class SvmDesc(C.Structure):
     ]
 
 
+class RvmDesc(C.Structure):
+    _fields_ = [
+        ("kernel", C.c_int32), ("gamma", C.c_double),
+        ("poly_alpha", C.c_double), ("poly_constant", C.c_double), ("poly_degree", C.c_int32),
+        ("num_filters", C.c_int32), ("num_filters_to_use", C.c_int32),
+        ("dim", C.c_int32), ("sv_type", C.c_int32),
+        ("support_vectors", C.c_void_p),
+        ("coefficients", C.POINTER(C.c_float)),
+        ("hierarchical_thresholds", C.POINTER(C.c_float)),
+        ("bias", C.c_float),
+        ("logistic_a", C.c_double), ("logistic_b", C.c_double),
+    ]
+
+
 class DetectorDesc(C.Structure):
     _fields_ = [
         ("incremental_scale_factor", C.c_double),
@@ -131,6 +145,11 @@ SYMBOLS = [
     ("fdb_svm_set_threshold", C.c_int, [C.c_void_p, C.c_float]),
     ("fdb_svm_get_probability", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     ("fdb_svm_has_dense", C.c_int, [C.c_void_p]),
+    ("fdb_rvm_create", C.c_int, [C.c_void_p, _P(RvmDesc), _P(C.c_void_p)]),
+    ("fdb_rvm_destroy", None, [C.c_void_p]),
+    ("fdb_rvm_set_num_filters_to_use", C.c_int, [C.c_void_p, C.c_int32]),
+    ("fdb_rvm_get_probability", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("fdb_detector_create_rvm", C.c_int, [C.c_void_p, _P(DetectorDesc), C.c_void_p, _P(C.c_void_p)]),
     ("fdb_detector_create", C.c_int, [C.c_void_p, _P(DetectorDesc), C.c_void_p, C.c_void_p, _P(C.c_void_p)]),
     ("fdb_detector_destroy", None, [C.c_void_p]),
     ("fdb_detector_prepare", C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32]),

@@ -443,6 +443,96 @@ int fdb_svm_get_probability(fdb_svm* m, const void* vectors, int64_t n, double* 
 	return FDB_OK;
 }
 
+/* ---------------------------------------------------------------------------------------------
+ * RVM
+ * ------------------------------------------------------------------------------------------- */
+int fdb_rvm_create(fdb_ctx* ctx, const fdb_rvm_desc* d, fdb_rvm** out) {
+	int s = check_ctx(ctx); if (s) return s;
+	if (!d || !out) return fail(FDB_ERR_INVALID_ARGUMENT, "null argument");
+	*out = nullptr;
+	if (d->kernel < FDB_KERNEL_RBF || d->kernel > FDB_KERNEL_LINEAR) return fail(FDB_ERR_INVALID_ARGUMENT, "RVM: unknown kernel kind");
+	if (d->num_filters < 1 || d->dim < 1) return fail(FDB_ERR_INVALID_ARGUMENT, "RVM: empty model");
+	if (d->sv_type != FDB_SV_U8 && d->sv_type != FDB_SV_F32) return fail(FDB_ERR_INVALID_ARGUMENT, "RVM: bad sv_type");
+	if (!d->support_vectors || !d->coefficients || !d->hierarchical_thresholds) return fail(FDB_ERR_INVALID_ARGUMENT, "RVM: null array");
+	if ((size_t)d->dim * 4 > 96 * 1024) return fail(FDB_ERR_UNSUPPORTED, "RVM: feature vector too long");
+	/* the device form is the SVM's: support vectors transposed, one coefficient per vector (the diagonal c[l][l]) */
+	std::vector<float> diag((size_t)d->num_filters);
+	for (int l = 0; l < d->num_filters; ++l) diag[(size_t)l] = d->coefficients[(size_t)l * (l + 1) / 2 + l];
+	fdb_svm_desc sd = fdb_svm_desc();
+	sd.kernel = d->kernel; sd.gamma = d->gamma; sd.poly_alpha = d->poly_alpha; sd.poly_constant = d->poly_constant; sd.poly_degree = d->poly_degree;
+	sd.num_sv = d->num_filters; sd.dim = d->dim; sd.sv_type = d->sv_type; sd.support_vectors = d->support_vectors;
+	sd.coefficients = diag.data(); sd.bias = d->bias; sd.threshold = 0.f; sd.logistic_a = d->logistic_a; sd.logistic_b = d->logistic_b;
+	fdb_svm* base = nullptr;
+	s = fdb_svm_create(ctx, &sd, &base);
+	if (s) return s;
+	fdb_rvm* m = new fdb_rvm;
+	static_cast<fdb_svm&>(*m) = *base;  /* takes over the device allocations */
+	base->owned.clear();
+	delete base;
+	m->has_dense = false;
+	m->rvm_thresholds.assign(d->hierarchical_thresholds, d->hierarchical_thresholds + d->num_filters);
+	float* thr;
+	s = upload(m->rvm_thresholds.data(), m->rvm_thresholds.size(), &thr, m->owned);
+	if (s) { free_all(m->owned); delete m; return s; }
+	m->dev.rvm_thresholds = thr;
+	m->dev.rvm_filters = (d->num_filters_to_use <= 0 || d->num_filters_to_use > d->num_filters) ? d->num_filters : d->num_filters_to_use;
+	*out = m;
+	return FDB_OK;
+}
+
+void fdb_rvm_destroy(fdb_rvm* m) {
+	if (!m) return;
+	cudaSetDevice(m->ctx->device);
+	cudaStreamSynchronize(m->ctx->stream);
+	free_all(m->owned);
+	delete m;
+}
+
+int fdb_rvm_set_num_filters_to_use(fdb_rvm* m, int32_t n) { /* RvmClassifier.cpp:119-126 */
+	if (!m) return fail(FDB_ERR_INVALID_ARGUMENT, "null rvm");
+	m->dev.rvm_filters = (n <= 0 || n > m->dev.num_sv) ? m->dev.num_sv : n;
+	return FDB_OK;
+}
+
+int fdb_rvm_get_probability(fdb_rvm* m, const void* vectors, int64_t n, int32_t* level_out, double* dist_out, double* prob_out,
+		uint8_t* pos_out) {
+	if (!m) return fail(FDB_ERR_INVALID_ARGUMENT, "null rvm");
+	int s = check_ctx(m->ctx); if (s) return s;
+	if (n < 0 || (n > 0 && !vectors)) return fail(FDB_ERR_INVALID_ARGUMENT, "bad vector batch");
+	if (n == 0) return FDB_OK;
+	if (n > (1 << 30)) return fail(FDB_ERR_INVALID_ARGUMENT, "batch too large");
+	const size_t es = m->dev.sv_type == FDB_SV_U8 ? 1 : 4;
+	const size_t bytes = es * (size_t)m->dev.dim * (size_t)n;
+	std::vector<void*> tmp;
+	uint8_t* d_v; double* d_d; int* d_l;
+	s = dev_alloc(&d_v, bytes, tmp); if (s) { free_all(tmp); return s; }
+	s = dev_alloc(&d_d, (size_t)n, tmp); if (s) { free_all(tmp); return s; }
+	s = dev_alloc(&d_l, (size_t)n, tmp); if (s) { free_all(tmp); return s; }
+	cudaStream_t st = m->ctx->stream;
+	std::vector<double> host((size_t)n);
+	std::vector<int> lev((size_t)n);
+	cudaError_t e = cudaMemcpyAsync(d_v, vectors, bytes, cudaMemcpyHostToDevice, st);
+	if (e == cudaSuccess) {
+		launch_svm_vectors(st, m->dev, d_v, (int)n, d_d, d_l);
+		m->ctx->launches++;
+		e = cudaGetLastError();
+	}
+	if (e == cudaSuccess) e = cudaMemcpyAsync(host.data(), d_d, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, st);
+	if (e == cudaSuccess) e = cudaMemcpyAsync(lev.data(), d_l, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, st);
+	if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+	free_all(tmp);
+	if (e != cudaSuccess) return fail(FDB_ERR_CUDA, std::string("rvm_get_probability: ") + cudaGetErrorString(e));
+	for (int64_t i = 0; i < n; ++i) {
+		const double dd = host[(size_t)i];
+		const int l = lev[(size_t)i];
+		if (level_out) level_out[i] = l;
+		if (dist_out) dist_out[i] = dd;
+		if (prob_out) prob_out[i] = rvm_probability(m->logistic_a, m->logistic_b, dd);
+		if (pos_out) pos_out[i] = (l + 1 == m->dev.rvm_filters && dd >= (double)m->rvm_thresholds[(size_t)l]) ? 1 : 0;
+	}
+	return FDB_OK;
+}
+
 int fdb_plan_layers(const fdb_detector_desc* desc, int32_t width, int32_t height, int32_t roi_x, int32_t roi_y,
 		int32_t roi_w, int32_t roi_h, fdb_layer_info* out, int32_t cap, int32_t* n_layers, int64_t* n_windows) {
 	if (!desc) return fail(FDB_ERR_INVALID_ARGUMENT, "null descriptor");

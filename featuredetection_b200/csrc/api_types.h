@@ -42,7 +42,11 @@ struct fdb_svm {
 	fdb::DevSvmDense dense{};
 	std::vector<void*> owned;
 	double logistic_a = 0, logistic_b = 0;
+	std::vector<float> rvm_thresholds; /* host copy (RVM only) */
 };
+
+/* RvmClassifier + ProbabilisticRvmClassifier: the same device form as the SVM (support vectors, kernel) plus the cascade */
+struct fdb_rvm : fdb_svm {};
 
 namespace fdb {
 

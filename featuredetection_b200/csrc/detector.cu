@@ -99,6 +99,7 @@ struct fdb_detector {
 	int64_t farena_bytes = 0;         /* per frame */
 	SvmItem* d_all_items = nullptr;   /* every window of a frame as an SVM item (`single` detector without a WVM) */
 	double* d_all_dist = nullptr; double* h_all_dist = nullptr;
+	int* d_all_level = nullptr; int* h_all_level = nullptr; /* RVM (`single` prvm): level reached per window */
 	/* `single` detector on the tensor cores (svm_dense.cu): distances of a chunk, positives list */
 	double* d_sd_dist = nullptr; int* d_sd_count = nullptr; DensePositive* d_sd_pos = nullptr;
 	int* h_sd_count = nullptr; DensePositive* h_sd_pos = nullptr; int sd_pos_cap = 0;
@@ -214,11 +215,11 @@ const int STATUS_REDO = -1000;
 /* the second classifier on n work items of the slot's chunk: hq64 patches are rebuilt inside the SVM kernel;
  * any other feature space runs its layer filters once per chunk, then feature kernel + SVM in batches */
 void svm_stage(fdb_detector* det, Slot& sl, cudaStream_t st, const Plan& plan, const DevLayer* d_layers, const SvmItem* d_items,
-		int n, double* d_dist, bool filter_layers) {
+		int n, double* d_dist, bool filter_layers, int* d_level = nullptr) {
 	fdb_ctx* c = det->ctx;
 	if (!det->has_feature || det->feat.kind == FDB_FEATURE_HQ64) {
 		launch_svm_windows(st, det->svm->dev, det->desc.patch_width, det->desc.patch_height, sl.frames_dev, plan.width, plan.height,
-				sl.d_arena, plan.arena_bytes, d_layers, d_items, n, d_dist);
+				sl.d_arena, plan.arena_bytes, d_layers, d_items, n, d_dist, d_level);
 		c->launches++;
 		return;
 	}
@@ -231,7 +232,7 @@ void svm_stage(fdb_detector* det, Slot& sl, cudaStream_t st, const Plan& plan, c
 		const int m = std::min(FEAT_BATCH, n - off);
 		launch_feature_patches(st, det->feat, sl.frames_dev, plan.width, plan.height, sl.d_arena, plan.arena_bytes, d_layers,
 				sl.d_farena, det->farena_bytes, d_items + off, m, sl.d_feat);
-		launch_svm_vectors(st, det->svm->dev, sl.d_feat, m, d_dist + off);
+		launch_svm_vectors(st, det->svm->dev, sl.d_feat, m, d_dist + off, d_level ? d_level + off : nullptr);
 		c->launches += 2;
 	}
 }
@@ -390,23 +391,31 @@ int detect_single(fdb_detector* det, const uint8_t* frames, bool frames_on_devic
 		int s = enqueue_stage1(det, sl, st, sl.frames_dev, 1, plan, det->d_layers, 0, nullptr, nullptr, false);
 		if (s) return s;
 		if (nwin > 0) {
-			svm_stage(det, sl, st, plan, det->d_layers, det->d_all_items, nwin, det->d_all_dist, true);
+			const bool rvm_stage = det->svm->dev.rvm_filters > 0;
+			svm_stage(det, sl, st, plan, det->d_layers, det->d_all_items, nwin, det->d_all_dist, true, rvm_stage ? det->d_all_level : nullptr);
 			CUDA_TRY(cudaGetLastError());
 			CUDA_TRY(cudaMemcpyAsync(det->h_all_dist, det->d_all_dist, sizeof(double) * (size_t)nwin, cudaMemcpyDeviceToHost, st));
+			if (rvm_stage) CUDA_TRY(cudaMemcpyAsync(det->h_all_level, det->d_all_level, sizeof(int) * (size_t)nwin, cudaMemcpyDeviceToHost, st));
 		}
 		CUDA_TRY(cudaStreamSynchronize(st));
 		if (distance_out && nwin) std::memcpy(distance_out + (int64_t)k * nwin, det->h_all_dist, sizeof(double) * (size_t)nwin);
 		for (int w = 0; w < nwin; ++w) {
 			const double dist = det->h_all_dist[w];
-			if (!(dist >= det->svm->dev.threshold)) continue; /* SvmClassifier::classify (SvmClassifier.cpp:44-46) */
+			const bool is_rvm = det->svm->dev.rvm_filters > 0;
+			int level = -1;
+			if (is_rvm) { /* RvmClassifier::classify(pair) (RvmClassifier.cpp:66-73) */
+				level = det->h_all_level[w];
+				if (!(level + 1 == det->svm->dev.rvm_filters && dist >= (double)det->svm->rvm_thresholds[(size_t)level])) continue;
+			} else if (!(dist >= det->svm->dev.threshold)) continue; /* SvmClassifier::classify (SvmClassifier.cpp:44-46) */
 			fdb_detection d;
 			fill_detection(&d, plan, det->desc, k, w);
 			d.reserved = 0;
-			d.wvm_level = -1;
+			d.wvm_level = level;
 			d.wvm_fout = std::numeric_limits<float>::quiet_NaN();
 			d.wvm_probability = std::numeric_limits<double>::quiet_NaN();
 			d.svm_distance = dist;
-			d.svm_probability = svm_probability(det->svm->logistic_a, det->svm->logistic_b, dist);
+			d.svm_probability = is_rvm ? rvm_probability(det->svm->logistic_a, det->svm->logistic_b, dist)
+					: svm_probability(det->svm->logistic_a, det->svm->logistic_b, dist);
 			d.probability = d.svm_probability;
 			d.positive = 1;
 			dets.push_back(d);
@@ -737,6 +746,11 @@ int fdb_detector_create(fdb_ctx* ctx, const fdb_detector_desc* desc, fdb_wvm* wv
 	return FDB_OK;
 }
 
+int fdb_detector_create_rvm(fdb_ctx* ctx, const fdb_detector_desc* desc, fdb_rvm* rvm, fdb_detector** out) {
+	if (!rvm) return fail(FDB_ERR_INVALID_ARGUMENT, "null rvm");
+	return fdb_detector_create(ctx, desc, nullptr, static_cast<fdb_svm*>(rvm), out);
+}
+
 void fdb_detector_destroy(fdb_detector* det) {
 	if (!det) return;
 	cudaSetDevice(det->ctx->device);
@@ -931,7 +945,7 @@ int fdb_detector_prepare(fdb_detector* det, int32_t width, int32_t height, int32
 	}
 	det->n_strips = (int)strips.size();
 	s = upload(strips.data(), strips.size(), &det->d_strips, det->owned); if (s) return s;
-	det->d_all_items = nullptr; det->d_all_dist = nullptr; det->h_all_dist = nullptr;
+	det->d_all_items = nullptr; det->d_all_dist = nullptr; det->h_all_dist = nullptr; det->d_all_level = nullptr; det->h_all_level = nullptr;
 	if (!det->wvm) {
 		/* `single` detector: every window of a frame is an SVM work item, canonical order */
 		std::vector<SvmItem> all((size_t)plan.windows);
@@ -948,6 +962,8 @@ int fdb_detector_prepare(fdb_detector* det, int32_t width, int32_t height, int32
 		s = upload(all.data(), all.size(), &det->d_all_items, det->owned); if (s) return s;
 		s = dev_alloc(&det->d_all_dist, (size_t)std::max<int64_t>(plan.windows, 1), det->owned); if (s) return s;
 		s = host_alloc(&det->h_all_dist, (size_t)std::max<int64_t>(plan.windows, 1), det->owned_host); if (s) return s;
+		s = dev_alloc(&det->d_all_level, (size_t)std::max<int64_t>(plan.windows, 1), det->owned); if (s) return s;
+		s = host_alloc(&det->h_all_level, (size_t)std::max<int64_t>(plan.windows, 1), det->owned_host); if (s) return s;
 		det->d_sd_dist = nullptr;
 		if (det->svm->has_dense && plan.windows > 0) {
 			det->sd_pos_cap = (int)std::min<int64_t>(plan.windows * det->chunk, (int64_t)1 << 26); /* every window may be positive */

@@ -111,6 +111,7 @@ void overlap_eliminate(std::vector<fdb_detection>& v, float dist, float ratio);
 void five_stage_nms(std::vector<fdb_detection>& v, int width, int height);
 double wvm_probability(double logistic_a, double logistic_b, float fout);
 double svm_probability(double logistic_a, double logistic_b, double distance);
+double rvm_probability(double logistic_a, double logistic_b, double distance);
 
 } // namespace fdb
 

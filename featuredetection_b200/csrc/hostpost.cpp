@@ -28,6 +28,11 @@ double svm_probability(double a, double b, double distance) {
 	return fABp >= 0 ? std::exp(-fABp) / (1.0 + std::exp(-fABp)) : 1.0 / (1.0 + std::exp(fABp));
 }
 
+/* ProbabilisticRvmClassifier.cpp:62 */
+double rvm_probability(double a, double b, double distance) {
+	return 1.0f / (1.0f + std::exp(a + b * distance));
+}
+
 void stable_sort_desc(std::vector<fdb_detection>& v) {
 	std::stable_sort(v.begin(), v.end(), [](const fdb_detection& a, const fdb_detection& b) {
 		return a.probability > b.probability;

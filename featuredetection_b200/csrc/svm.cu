@@ -29,7 +29,7 @@ template <int MODE> /* 0: window of a frame (u8, hq64 built here), 1: given u8 v
 __global__ void __launch_bounds__(SVM_THREADS) svm_kernel(const DevSvm s, int patch_w, int patch_h,
 		const uint8_t* __restrict__ frames, int W, int H, const uint8_t* __restrict__ arena, int64_t arena_stride,
 		const DevLayer* __restrict__ layers, const SvmItem* __restrict__ items,
-		const void* __restrict__ vectors, double* __restrict__ distance_out) {
+		const void* __restrict__ vectors, double* __restrict__ distance_out, int* __restrict__ level_out) {
 	extern __shared__ __align__(16) unsigned char svm_smem[];
 	double* s_prod = reinterpret_cast<double*>(svm_smem);                    /* [SVM_CHUNK] */
 	uint32_t* s_x = reinterpret_cast<uint32_t*>(svm_smem + sizeof(double) * SVM_CHUNK); /* [nwords] or float[dim] */
@@ -81,9 +81,16 @@ __global__ void __launch_bounds__(SVM_THREADS) svm_kernel(const DevSvm s, int pa
 	}
 	__syncthreads();
 
-	double distance = -(double)s.bias; /* SvmClassifier.cpp:56: double distance = -bias */
-	for (int base = 0; base < s.num_sv; base += SVM_CHUNK) {
-		const int cnt = min(SVM_CHUNK, s.num_sv - base);
+	/* RvmClassifier (s.rvm_filters > 0): the same kernel values feed the cascade of RvmClassifier::computeHyperplaneDistance
+	 * (RvmClassifier.cpp:75-85) through computeHyperplaneDistanceCached (:94-112): level 0 is -bias + c[0][0] k_0, level l
+	 * adds c[l][l] k_l to the distance of level l - 1, until a level's distance falls below its threshold */
+	const bool rvm = s.rvm_filters > 0;
+	const int n_vec = rvm ? s.rvm_filters : s.num_sv;
+	double distance = -(double)s.bias; /* SvmClassifier.cpp:56 / RvmClassifier.cpp:104: double distance = -bias */
+	int level = -1;
+	bool done = false;
+	for (int base = 0; base < n_vec; base += SVM_CHUNK) {
+		const int cnt = min(SVM_CHUNK, n_vec - base);
 		for (int i = tid; i < cnt; i += SVM_THREADS) {
 			const int sv = base + i;
 			double kv;
@@ -142,14 +149,26 @@ __global__ void __launch_bounds__(SVM_THREADS) svm_kernel(const DevSvm s, int pa
 				}
 				kv = ret;
 			}
-			s_prod[i] = __dmul_rn((double)s.coef[sv], kv);                   /* SvmClassifier.cpp:58 */
+			s_prod[i] = __dmul_rn((double)s.coef[sv], kv);                   /* SvmClassifier.cpp:58 / RvmClassifier.cpp:98 (coef = c[l][l]) */
 		}
 		__syncthreads();
-		if (tid == 0)
-			for (int i = 0; i < cnt; ++i) distance = __dadd_rn(distance, s_prod[i]);
+		if (tid == 0) {
+			if (!rvm) {
+				for (int i = 0; i < cnt; ++i) distance = __dadd_rn(distance, s_prod[i]);
+			} else {
+				for (int i = 0; i < cnt && !done; ++i) {
+					distance = __dadd_rn(distance, s_prod[i]);
+					level = base + i;
+					done = !(distance >= (double)s.rvm_thresholds[level] && level + 1 < s.rvm_filters); /* RvmClassifier.cpp:84 */
+				}
+			}
+		}
 		__syncthreads();
 	}
-	if (tid == 0) distance_out[item] = distance;
+	if (tid == 0) {
+		distance_out[item] = distance;
+		if (rvm && level_out) level_out[item] = level;
+	}
 }
 
 /* HistEq64 patches (HistEq64Filter.cpp:32-125) of a list of windows -> [n][patch_w * patch_h] u8: the patch data of
@@ -210,20 +229,20 @@ int svm_configure() {
 
 void launch_svm_windows(cudaStream_t st, const DevSvm& s, int patch_w, int patch_h, const uint8_t* frames, int W, int H,
 		const uint8_t* arena, int64_t arena_stride, const DevLayer* layers, const SvmItem* items, int n_items,
-		double* distance_out) {
+		double* distance_out, int* level_out) {
 	if (n_items == 0) return;
 	svm_kernel<0><<<(unsigned)n_items, SVM_THREADS, svm_smem_bytes(s), st>>>(s, patch_w, patch_h, frames, W, H, arena,
-			arena_stride, layers, items, nullptr, distance_out);
+			arena_stride, layers, items, nullptr, distance_out, level_out);
 }
 
-void launch_svm_vectors(cudaStream_t st, const DevSvm& s, const void* vectors, int n, double* distance_out) {
+void launch_svm_vectors(cudaStream_t st, const DevSvm& s, const void* vectors, int n, double* distance_out, int* level_out) {
 	if (n == 0) return;
 	if (s.sv_type == FDB_SV_F32)
 		svm_kernel<2><<<(unsigned)n, SVM_THREADS, svm_smem_bytes(s), st>>>(s, 0, 0, nullptr, 0, 0, nullptr, 0, nullptr,
-				nullptr, vectors, distance_out);
+				nullptr, vectors, distance_out, level_out);
 	else
 		svm_kernel<1><<<(unsigned)n, SVM_THREADS, svm_smem_bytes(s), st>>>(s, 0, 0, nullptr, 0, 0, nullptr, 0, nullptr,
-				nullptr, vectors, distance_out);
+				nullptr, vectors, distance_out, level_out);
 }
 
 } // namespace fdb

@@ -81,7 +81,9 @@ struct DevSvm {
 	float bias, threshold;
 	const uint32_t* sv_words;       /* u8: [nwords][num_sv] packed 4 px per word */
 	const float* sv_f32;            /* f32: [dim][num_sv] */
-	const float* coef;              /* [num_sv] */
+	const float* coef;              /* [num_sv]; RVM: the diagonal coefficients c[l][l] */
+	int rvm_filters;                /* > 0: RvmClassifier cascade over the first rvm_filters vectors (numFiltersToUse) */
+	const float* rvm_thresholds;    /* [num_sv] hierarchicalThresholds */
 };
 
 /* tensor-core form of an u8 RBF SVM (svm_dense.cu): support vectors as UMMA core matrices, |sv|^2, float64
@@ -162,8 +164,8 @@ struct SvmItem {
 int svm_configure();
 void launch_svm_windows(cudaStream_t st, const DevSvm& s, int patch_w, int patch_h, const uint8_t* frames, int W, int H,
 		const uint8_t* arena, int64_t arena_stride, const DevLayer* layers, const SvmItem* items, int n_items,
-		double* distance_out);
-void launch_svm_vectors(cudaStream_t st, const DevSvm& s, const void* vectors, int n, double* distance_out);
+		double* distance_out, int* level_out = nullptr /* RVM: level reached */);
+void launch_svm_vectors(cudaStream_t st, const DevSvm& s, const void* vectors, int n, double* distance_out, int* level_out = nullptr);
 void launch_hq64_items(cudaStream_t st, int patch_w, int patch_h, const uint8_t* frames, int W, int H, const uint8_t* arena,
 		int64_t arena_stride, const DevLayer* layers, const SvmItem* items, int n_items, uint8_t* out);
 

@@ -144,19 +144,54 @@ class ProbabilisticSvmClassifier:
         return dist, prob, pos
 
 
+class ProbabilisticRvmClassifier:
+    """classification::ProbabilisticRvmClassifier over an RvmClassifier (fdb_rvm)."""
+
+    def __init__(self, ctx, model):
+        self.ctx, self.model = ctx, model
+        self._desc = model.desc()
+        self.h = None
+        h = C.c_void_p()
+        capi.check(ctx.lib, ctx.lib.fdb_rvm_create(ctx.h, C.byref(self._desc), C.byref(h)))
+        self.h = h
+
+    def __del__(self):
+        try:
+            if self.h and self.ctx.h:
+                self.ctx.lib.fdb_rvm_destroy(self.h)
+        except Exception:
+            pass
+
+    def set_num_filters_to_use(self, n):
+        capi.check(self.ctx.lib, self.ctx.lib.fdb_rvm_set_num_filters_to_use(self.h, n))
+
+    def get_probability(self, vectors):
+        """-> (level i32[n], distance f64[n], probability f64[n], positive u8[n])"""
+        v = np.ascontiguousarray(vectors, self.model.sv.dtype).reshape(-1, self.model.sv.shape[1])
+        n = v.shape[0]
+        level = np.empty(n, np.int32); dist = np.empty(n, np.float64); prob = np.empty(n, np.float64); pos = np.empty(n, np.uint8)
+        capi.check(self.ctx.lib, self.ctx.lib.fdb_rvm_get_probability(
+            self.h, v.ctypes.data, n, level.ctypes.data, dist.ctypes.data, prob.ctypes.data, pos.ctypes.data))
+        return level, dist, prob, pos
+
+
 class SlidingWindowCascade:
     """detection::FiveStageSlidingWindowDetector / SlidingWindowDetector over frame batches."""
 
-    def __init__(self, ctx, det_kwargs, wvm_model, svm_model=None, feature=None):
-        """wvm_model None + svm_model: the `single` psvm detector (every window through the SVM).
-        feature: capi.FeatureDesc - feature space of the SVM (default: the HistEq64 patch)."""
+    def __init__(self, ctx, det_kwargs, wvm_model, svm_model=None, feature=None, rvm_model=None):
+        """wvm_model None + svm_model: the `single` psvm detector (every window through the SVM); rvm_model alone: the
+        `single` prvm detector. feature: capi.FeatureDesc - feature space of the SVM (default: the HistEq64 patch)."""
         self.ctx = ctx
         self.wvm = ProbabilisticWvmClassifier(ctx, wvm_model) if wvm_model is not None else None
         self.svm = ProbabilisticSvmClassifier(ctx, svm_model) if svm_model is not None else None
+        self.rvm = ProbabilisticRvmClassifier(ctx, rvm_model) if rvm_model is not None else None
         self._desc = detector_desc(**det_kwargs)
         h = C.c_void_p()
-        capi.check(ctx.lib, ctx.lib.fdb_detector_create(ctx.h, C.byref(self._desc), self.wvm.h if self.wvm else None,
-                                                        self.svm.h if self.svm else None, C.byref(h)))
+        if self.rvm is not None:
+            capi.check(ctx.lib, ctx.lib.fdb_detector_create_rvm(ctx.h, C.byref(self._desc), self.rvm.h, C.byref(h)))
+        else:
+            capi.check(ctx.lib, ctx.lib.fdb_detector_create(ctx.h, C.byref(self._desc), self.wvm.h if self.wvm else None,
+                                                            self.svm.h if self.svm else None, C.byref(h)))
         self.h = h
         self.width = self.height = None
         self.patch = (self._desc.patch_width, self._desc.patch_height)

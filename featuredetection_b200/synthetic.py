@@ -220,6 +220,67 @@ def make_wvm(w, h, per_level, levels, rbf_r, seed, cntval=5, rects_per_value=4):
                     rec.reshape(-1, 4))
 
 
+class RvmModel:
+    """Host-side state of an RvmClassifier (RvmClassifier.hpp:120-124) + logistic (ProbabilisticRvmClassifier.hpp)."""
+
+    def __init__(self, support_vectors, coefficients, thresholds, gamma=7.689e-7, bias=0.0, num_filters_to_use=0,
+                 logistic_a=0.00556, logistic_b=-2.95, kernel="rbf", alpha=1.0, constant=0.0, degree=2):
+        sv = np.ascontiguousarray(support_vectors)
+        assert sv.ndim == 2 and sv.dtype in (np.uint8, np.float32)
+        n = sv.shape[0]
+        self.sv = sv
+        self.coef = np.ascontiguousarray(coefficients, np.float32)      # packed lower triangle, level l at l (l + 1) / 2
+        assert self.coef.shape == (n * (n + 1) // 2,)
+        self.thresholds = np.ascontiguousarray(thresholds, np.float32)
+        assert self.thresholds.shape == (n,)
+        self.gamma, self.bias, self.use = float(gamma), float(np.float32(bias)), int(num_filters_to_use)
+        self.kernel = {"rbf": capi.FDB_KERNEL_RBF, "polynomial": capi.FDB_KERNEL_POLYNOMIAL, "hik": capi.FDB_KERNEL_HIK,
+                       "linear": capi.FDB_KERNEL_LINEAR}[kernel]
+        self.alpha, self.constant, self.degree = float(alpha), float(constant), int(degree)
+        self.logistic_a, self.logistic_b = float(logistic_a), float(logistic_b)
+
+    @property
+    def filters_to_use(self):
+        n = self.sv.shape[0]
+        return n if self.use <= 0 or self.use > n else self.use
+
+    def desc(self):
+        d = capi.RvmDesc()
+        d.kernel, d.gamma = self.kernel, self.gamma
+        d.poly_alpha, d.poly_constant, d.poly_degree = self.alpha, self.constant, self.degree
+        d.num_filters, d.dim = self.sv.shape
+        d.num_filters_to_use = self.use
+        d.sv_type = capi.FDB_SV_U8 if self.sv.dtype == np.uint8 else capi.FDB_SV_F32
+        d.support_vectors = self.sv.ctypes.data
+        d.coefficients = self.coef.ctypes.data_as(C.POINTER(C.c_float))
+        d.hierarchical_thresholds = self.thresholds.ctypes.data_as(C.POINTER(C.c_float))
+        d.bias = self.bias
+        d.logistic_a, d.logistic_b = self.logistic_a, self.logistic_b
+        d._keepalive = self
+        return d
+
+
+def make_rvm(w, h, seed, num_filters=24, gamma=7.689e-7, survival=0.7):
+    """Synthetic u8 RBF RVM cascade: reduced set vectors from make_svm's crops, random coefficient rows, thresholds set so
+    that about `survival` of random equalised patches pass each level (calibrated here with numpy on the level sums the
+    reference's live code path uses: the diagonal coefficients)."""
+    rng = np.random.default_rng(int(seed) + 7)
+    svm = make_svm(w, h, seed, num_sv=num_filters, gamma=gamma)
+    coef = rng.normal(0, 1, num_filters * (num_filters + 1) // 2).astype(np.float32)
+    diag = np.array([coef[l * (l + 1) // 2 + l] for l in range(num_filters)], np.float64)
+    probe = svm.sv[rng.integers(0, num_filters, 256)].astype(np.int64)
+    probe = np.clip(probe + rng.integers(-40, 41, probe.shape), 0, 255)
+    ssd = ((probe[:, None, :] - svm.sv[None].astype(np.int64)) ** 2).sum(axis=2)
+    dist = np.cumsum(diag[None] * np.exp(-gamma * ssd), axis=1)
+    thr = np.empty(num_filters, np.float32)
+    alive = np.ones(len(probe), bool)
+    for l in range(num_filters):
+        v = dist[alive, l] if alive.sum() > 8 else dist[:, l]
+        thr[l] = np.float32(np.quantile(v, 1.0 - survival))
+        alive &= dist[:, l] >= thr[l]
+    return RvmModel(svm.sv, coef, thr, gamma=gamma)
+
+
 def make_svm(w, h, seed, num_sv=1024, gamma=7.689e-7):
     """Synthetic u8 RBF-SVM: support vectors are hq64-equalised crops of block-averaged frames
     1000..1003 (gamma from adaptiveTrackingApp/default.cfg:148)."""

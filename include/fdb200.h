@@ -56,6 +56,7 @@ typedef enum fdb_status {
 typedef struct fdb_ctx fdb_ctx;
 typedef struct fdb_wvm fdb_wvm;
 typedef struct fdb_svm fdb_svm;
+typedef struct fdb_rvm fdb_rvm;
 typedef struct fdb_detector fdb_detector;
 
 /* ------------------------------------------------------------------------------------------
@@ -127,6 +128,25 @@ typedef struct fdb_svm_desc {
 	double poly_constant;    /* PolynomialKernel::constant */
 	int32_t poly_degree;     /* PolynomialKernel::degree */
 } fdb_svm_desc;
+
+/* Reduced vector machine cascade + logistic.
+ * Replaces RvmClassifier (RvmClassifier.hpp:33-125: supportVectors, coefficients per level, hierarchicalThresholds,
+ * numFiltersToUse; the MATLAB loader RvmClassifier.cpp:131-319 is the only way the reference fills them) and
+ * ProbabilisticRvmClassifier's logistic (ProbabilisticRvmClassifier.cpp:56-64). */
+typedef struct fdb_rvm_desc {
+	int32_t kernel;              /* fdb_kernel_kind */
+	double gamma;                /* RbfKernel::gamma */
+	double poly_alpha, poly_constant; int32_t poly_degree;
+	int32_t num_filters;         /* reduced set vectors = cascade levels */
+	int32_t num_filters_to_use;  /* RvmClassifier::setNumFiltersToUse (RvmClassifier.cpp:119-126): 0 or > num_filters = all */
+	int32_t dim;
+	int32_t sv_type;             /* fdb_sv_type */
+	const void* support_vectors; /* [num_filters][dim] */
+	const float* coefficients;   /* RvmClassifier::coefficients packed: level l at l (l + 1) / 2, entries [l][0..l] */
+	const float* hierarchical_thresholds; /* [num_filters] */
+	float bias;
+	double logistic_a, logistic_b;
+} fdb_rvm_desc;
 
 /* Image pyramid + window extraction parameters.
  * Replaces ImagePyramid(double inc, double min, double max) (ImagePyramid.cpp:79-92),
@@ -299,6 +319,18 @@ FDB_API int fdb_svm_get_probability(fdb_svm* svm, const void* vectors_host, int6
  * Same loop as above (SvmClassifier.cpp:55-60, RbfKernel.hpp:32-40); distances agree with it to ~1e-13. */
 FDB_API int fdb_svm_has_dense(const fdb_svm* svm);
 
+/* RvmClassifier / ProbabilisticRvmClassifier. The cascade is evaluated the way the reference's live code path does
+ * (computeHyperplaneDistance -> computeHyperplaneDistanceCached, RvmClassifier.cpp:75-112): level 0 = -bias + c[0][0] k_0,
+ * level l = distance of level l - 1 + c[l][l] k_l (only the diagonal coefficients take part), stopping at the first level
+ * whose distance is below its threshold. */
+FDB_API int fdb_rvm_create(fdb_ctx* ctx, const fdb_rvm_desc* desc, fdb_rvm** out);
+FDB_API void fdb_rvm_destroy(fdb_rvm* rvm);
+FDB_API int fdb_rvm_set_num_filters_to_use(fdb_rvm* rvm, int32_t num_filters);
+/* ProbabilisticRvmClassifier::getProbability (ProbabilisticRvmClassifier.cpp:52-64) over n feature vectors: level reached,
+ * hyperplane distance, probability 1 / (1 + exp(A + B distance)), positive = RvmClassifier::classify (RvmClassifier.cpp:66-73) */
+FDB_API int fdb_rvm_get_probability(fdb_rvm* rvm, const void* vectors_host, int64_t n, int32_t* level_out,
+		double* distance_out, double* probability_out, uint8_t* positive_out);
+
 /* ------------------------------------------------------------------------------------------
  * Detector  (PyramidFeatureExtractor + Detector surface)
  * ---------------------------------------------------------------------------------------- */
@@ -306,6 +338,9 @@ FDB_API int fdb_svm_has_dense(const fdb_svm* svm);
  * given ("single" with psvm: see fdb_detect_single). */
 FDB_API int fdb_detector_create(fdb_ctx* ctx, const fdb_detector_desc* desc,
 		fdb_wvm* wvm, fdb_svm* svm, fdb_detector** out);
+/* `single` detector of ffpDetectApp.cpp:427-500 with classifier prvm: every window through the RVM cascade on its HistEq64
+ * patch. Use fdb_detect_single / fdb_detect_batch; detections carry wvm_level = level reached, svm_distance = distance. */
+FDB_API int fdb_detector_create_rvm(fdb_ctx* ctx, const fdb_detector_desc* desc, fdb_rvm* rvm, fdb_detector** out);
 FDB_API void fdb_detector_destroy(fdb_detector* det);
 
 /* Fix the frame geometry (ImagePyramid::update / createLayers sizing, ImagePyramid.cpp:170-198)

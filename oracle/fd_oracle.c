@@ -516,6 +516,75 @@ double fdo_svm_probability(const fdo_svm* s, double distance) {
 }
 
 /* ---------------------------------------------------------------------------------------------
+ * RVM cascade (RvmClassifier.cpp:66-112; ProbabilisticRvmClassifier.cpp:52-64)
+ * ------------------------------------------------------------------------------------------- */
+struct fdo_rvm {
+	int kernel; double gamma, poly_alpha, poly_constant; int poly_degree;
+	int num_filters, use, dim, sv_type;
+	void* sv;
+	float* coef;  /* packed lower triangle */
+	float* thr;
+	float bias;
+	double logistic_a, logistic_b;
+};
+
+fdo_rvm* fdo_rvm_create(const fdb_rvm_desc* d) {
+	fdo_rvm* r = (fdo_rvm*)calloc(1, sizeof(fdo_rvm));
+	r->kernel = d->kernel; r->gamma = d->gamma; r->poly_alpha = d->poly_alpha; r->poly_constant = d->poly_constant; r->poly_degree = d->poly_degree;
+	r->num_filters = d->num_filters; r->dim = d->dim; r->sv_type = d->sv_type;
+	r->use = (d->num_filters_to_use <= 0 || d->num_filters_to_use > d->num_filters) ? d->num_filters : d->num_filters_to_use; /* RvmClassifier.cpp:119-126 */
+	size_t es = d->sv_type == FDB_SV_U8 ? 1 : 4;
+	r->sv = dup_mem(d->support_vectors, es * (size_t)d->num_filters * d->dim);
+	r->coef = (float*)dup_mem(d->coefficients, sizeof(float) * (size_t)d->num_filters * (d->num_filters + 1) / 2);
+	r->thr = (float*)dup_mem(d->hierarchical_thresholds, sizeof(float) * d->num_filters);
+	r->bias = d->bias; r->logistic_a = d->logistic_a; r->logistic_b = d->logistic_b;
+	return r;
+}
+
+void fdo_rvm_free(fdo_rvm* r) {
+	if (!r) return;
+	free(r->sv); free(r->coef); free(r->thr); free(r);
+}
+
+/* RvmClassifier::computeHyperplaneDistance (RvmClassifier.cpp:75-85) with computeHyperplaneDistanceCached (:94-112) as the
+ * reference runs it: the cache vector is created with numFiltersToUse elements, so level 0 takes the full-sum branch
+ * (-bias + c[0][0] k_0) and leaves one element; every later level finds size == level and adds c[l][l] k_l to the previous
+ * distance. Returns the level, *distance the last distance. */
+int fdo_rvm_eval(const fdo_rvm* r, const void* x, double* distance) {
+	const size_t es = r->sv_type == FDB_SV_U8 ? 1 : 4;
+	int level = -1;
+	double d = 0;
+	size_t cache_size = (size_t)r->use;              /* vector<double> filterEvalCache(numFiltersToUse) */
+	double cache_back = 0;
+	do {
+		++level;
+		if (cache_size == (size_t)level && level != 0) {
+			d = cache_back;
+			d += r->coef[(size_t)level * (level + 1) / 2 + level] * fdo_kernel_value(r->kernel, r->gamma, r->poly_alpha, r->poly_constant,
+					r->poly_degree, x, (const uint8_t*)r->sv + (size_t)level * r->dim * es, r->dim, r->sv_type);
+			cache_size++;
+		} else {
+			d = -r->bias;
+			for (int i = 0; i <= level; ++i)
+				d += r->coef[(size_t)level * (level + 1) / 2 + i] * fdo_kernel_value(r->kernel, r->gamma, r->poly_alpha, r->poly_constant,
+						r->poly_degree, x, (const uint8_t*)r->sv + (size_t)i * r->dim * es, r->dim, r->sv_type);
+			cache_size = 1;
+		}
+		cache_back = d;
+	} while (d >= r->thr[level] && level + 1 < r->use);
+	*distance = d;
+	return level;
+}
+
+int fdo_rvm_classify(const fdo_rvm* r, int level, double distance) { /* RvmClassifier.cpp:66-73 */
+	return level + 1 == r->use && distance >= r->thr[level];
+}
+
+double fdo_rvm_probability(const fdo_rvm* r, double distance) { /* ProbabilisticRvmClassifier.cpp:62 */
+	return 1.0f / (1.0f + exp(r->logistic_a + r->logistic_b * distance));
+}
+
+/* ---------------------------------------------------------------------------------------------
  * Window enumeration (DirectPyramidFeatureExtractor.cpp:75-123; ImagePyramidLayer.hpp:65-67,98-100)
  * ------------------------------------------------------------------------------------------- */
 static void clamp_roi(int W, int H, int* rx, int* ry, int* rw, int* rh) {

@@ -328,6 +328,53 @@ class Svm:
         return dist, prob, pos
 
 
+class Rvm:
+    """RvmClassifier + ProbabilisticRvmClassifier: the C restatement (fdo_rvm_*) or - use_ref - the reference's own classes"""
+
+    def __init__(self, model, use_ref=False):
+        self.model, self.use_ref = model, use_ref
+        self._desc = model.desc()
+        if use_ref:
+            R = ref()
+            R.ref_rvm_create.restype = C.c_void_p; R.ref_rvm_create.argtypes = [C.POINTER(capi.RvmDesc)]
+            R.ref_rvm_free.restype = None; R.ref_rvm_free.argtypes = [C.c_void_p]
+            R.ref_rvm_eval.restype = C.c_int
+            R.ref_rvm_eval.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int)]
+            self.h = R.ref_rvm_create(C.byref(self._desc))
+        else:
+            L = lib()
+            L.fdo_rvm_create.restype = C.c_void_p; L.fdo_rvm_create.argtypes = [C.POINTER(capi.RvmDesc)]
+            L.fdo_rvm_free.restype = None; L.fdo_rvm_free.argtypes = [C.c_void_p]
+            L.fdo_rvm_eval.restype = C.c_int; L.fdo_rvm_eval.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_double)]
+            L.fdo_rvm_classify.restype = C.c_int; L.fdo_rvm_classify.argtypes = [C.c_void_p, C.c_int, C.c_double]
+            L.fdo_rvm_probability.restype = C.c_double; L.fdo_rvm_probability.argtypes = [C.c_void_p, C.c_double]
+            self.h = L.fdo_rvm_create(C.byref(self._desc))
+
+    def __del__(self):
+        try:
+            (ref().ref_rvm_free if self.use_ref else lib().fdo_rvm_free)(self.h)
+        except Exception:
+            pass
+
+    def eval(self, vectors):
+        """vectors [n, dim] -> (level i32[n], distance f64[n], probability f64[n], positive u8[n])"""
+        vectors = np.ascontiguousarray(vectors, self.model.sv.dtype).reshape(-1, self.model.sv.shape[1])
+        n = vectors.shape[0]
+        level = np.empty(n, np.int32); dist = np.empty(n, np.float64); prob = np.empty(n, np.float64); pos = np.empty(n, np.uint8)
+        d, p, q = C.c_double(), C.c_double(), C.c_int()
+        for i in range(n):
+            if self.use_ref:
+                level[i] = ref().ref_rvm_eval(self.h, vectors[i].ctypes.data, C.byref(d), C.byref(p), C.byref(q))
+                dist[i], prob[i], pos[i] = d.value, p.value, q.value
+            else:
+                L = lib()
+                level[i] = L.fdo_rvm_eval(self.h, vectors[i].ctypes.data, C.byref(d))
+                dist[i] = d.value
+                prob[i] = L.fdo_rvm_probability(self.h, d.value)
+                pos[i] = L.fdo_rvm_classify(self.h, int(level[i]), d.value)
+        return level, dist, prob, pos
+
+
 class Features:
     """A prepared feature space (fdo_features): layer filters + patch filter chain."""
 

@@ -14,6 +14,21 @@
  * Synthetic model state enters WvmClassifier through its protected members (a subclass), the way
  * WvmClassifier::loadFromMatlab (WvmClassifier.cpp:348-770) fills them.
  */
+/* RvmClassifier keeps its model private and fills it only from MATLAB files (RvmClassifier.cpp:131-319, needs libmat): the
+ * test driver reaches the members through the preprocessor; the class itself is compiled unmodified from the reference tree */
+#include <memory>
+#include <sstream>
+#include <string>
+#include <utility>
+#include <vector>
+#include "opencv2/core/core.hpp"
+#include "boost/property_tree/ptree.hpp"
+#define private public
+#define protected public
+#include "classification/RvmClassifier.hpp"
+#undef protected
+#undef private
+#include "classification/ProbabilisticRvmClassifier.hpp"
 #include "classification/WvmClassifier.hpp"
 #include "classification/ProbabilisticWvmClassifier.hpp"
 #include "classification/SvmClassifier.hpp"
@@ -144,6 +159,43 @@ static shared_ptr<classification::Kernel> ref_make_kernel(int kind, double gamma
 	if (kind == FDB_KERNEL_HIK) return make_shared<classification::HistogramIntersectionKernel>();
 	if (kind == FDB_KERNEL_LINEAR) return make_shared<classification::LinearKernel>();
 	return make_shared<classification::RbfKernel>(gamma);
+}
+
+struct RefRvm {
+	shared_ptr<classification::RvmClassifier> rvm;
+	shared_ptr<classification::ProbabilisticRvmClassifier> prvm;
+	int dim, type;
+};
+
+void* ref_rvm_create(const fdb_rvm_desc* d) {
+	RefRvm* r = new RefRvm;
+	r->rvm = make_shared<classification::RvmClassifier>(ref_make_kernel(d->kernel, d->gamma, d->poly_alpha, d->poly_constant, d->poly_degree));
+	for (int i = 0; i < d->num_filters; ++i) {
+		Mat sv(1, d->dim, d->sv_type == FDB_SV_U8 ? CV_8U : CV_32F);
+		const size_t bytes = (d->sv_type == FDB_SV_U8 ? 1 : 4) * (size_t)d->dim;
+		std::memcpy(sv.data, (const uint8_t*)d->support_vectors + (size_t)i * bytes, bytes);
+		r->rvm->supportVectors.push_back(sv);
+		r->rvm->coefficients.push_back(vector<float>(d->coefficients + (size_t)i * (i + 1) / 2, d->coefficients + (size_t)i * (i + 1) / 2 + i + 1));
+		r->rvm->hierarchicalThresholds.push_back(d->hierarchical_thresholds[i]);
+	}
+	r->rvm->bias = d->bias;
+	r->rvm->setNumFiltersToUse((unsigned int)(d->num_filters_to_use < 0 ? 0 : d->num_filters_to_use));
+	r->prvm = make_shared<classification::ProbabilisticRvmClassifier>(r->rvm, d->logistic_a, d->logistic_b);
+	r->dim = d->dim; r->type = d->sv_type;
+	return r;
+}
+void ref_rvm_free(void* p) { delete (RefRvm*)p; }
+
+/* RvmClassifier::computeHyperplaneDistance + ProbabilisticRvmClassifier::getProbability(pair) */
+int ref_rvm_eval(void* p, const void* x, double* distance, double* probability, int* positive) {
+	RefRvm* r = (RefRvm*)p;
+	Mat m(1, r->dim, r->type == FDB_SV_U8 ? CV_8U : CV_32F, (void*)x);
+	std::pair<int, double> ld = r->rvm->computeHyperplaneDistance(m);
+	*distance = ld.second;
+	std::pair<bool, double> pr = r->prvm->getProbability(ld);
+	if (probability) *probability = pr.second;
+	if (positive) *positive = pr.first ? 1 : 0;
+	return ld.first;
 }
 
 void* ref_svm_create(const fdb_svm_desc* d) {

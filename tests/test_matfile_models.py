@@ -108,9 +108,17 @@ def test_svm_mat_reader(built, tmp_path, compress):
     d = lib.fdb_svm_file_desc(f).contents
     assert (d.logistic_a, d.logistic_b) == (0.0, 0.0)
     lib.fdb_svm_file_free(f)
-    # polynomial kernel: parsed by the reference, not evaluated here
-    sio.savemat(path, {"param_nonlin1": np.array([[0.75, 1.0, 0.05, 2.0, 1.0]]), "support_nonlin1": sv, "weight_nonlin1": coef.reshape(1, -1)}, format="5")
-    assert lib.fdb_svm_mat_load(path.encode(), None, C.byref(f)) == 5
+    # polynomial kernel (SvmClassifier.cpp:270-272): PolynomialKernel(1 / divisor, basisParam / divisor, polyPower) in float arithmetic
+    sio.savemat(path, {"param_nonlin1": np.array([[0.75, 1.0, 0.05, 2.0, 4.0]]), "support_nonlin1": sv, "weight_nonlin1": coef.reshape(1, -1)}, format="5")
+    capi.check(lib, lib.fdb_svm_mat_load(path.encode(), None, C.byref(f)))
+    d = lib.fdb_svm_file_desc(f).contents
+    basis = np.float32(0.05 / 65025.0)
+    assert (d.kernel, d.poly_degree) == (capi.FDB_KERNEL_POLYNOMIAL, 2)
+    assert d.poly_alpha == float(np.float32(1) / np.float32(4)) and d.poly_constant == float(basis / np.float32(4))
+    lib.fdb_svm_file_free(f)
+    # any other kernel type: the reference throws
+    sio.savemat(path, {"param_nonlin1": np.array([[0.75, 3.0, 0.05, 2.0, 4.0]]), "support_nonlin1": sv, "weight_nonlin1": coef.reshape(1, -1)}, format="5")
+    assert lib.fdb_svm_mat_load(path.encode(), None, C.byref(f)) != 0
 
 
 def test_storage_types_and_small_elements(built, tmp_path):
