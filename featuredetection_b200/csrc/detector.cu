@@ -1248,6 +1248,28 @@ int fdb_extract_features(fdb_detector* det, const uint8_t* frame_host, int64_t p
 	return FDB_OK;
 }
 
+int fdb_detect_face_features(fdb_detector* face, fdb_detector* const* features, int32_t n_features, const uint8_t* frame_host,
+		int64_t pitch, fdb_detection* face_out, int64_t face_cap, int64_t* n_face, fdb_detection* feature_out,
+		int64_t feature_cap_each, int64_t* n_feature) {
+	if (!face || !n_face || (n_features > 0 && (!features || !n_feature))) return fail(FDB_ERR_INVALID_ARGUMENT, "null argument");
+	for (int i = 0; i < n_features; ++i) n_feature[i] = 0;
+	/* ffpDetectApp.cpp:555-557: facePatches = detector->detect(img) */
+	int s = fdb_detect_batch(face, frame_host, pitch, 1, face->svm ? FDB_STAGE_NMS : FDB_STAGE_WVM, nullptr, face_out, face_cap, n_face);
+	if (s) return s;
+	if (*n_face == 0) return FDB_OK; /* the reference indexes facePatches[0] unconditionally (ffpDetectApp.cpp:591): no face, no ROI */
+	/* Patch::getBounds() of the first (most probable) face: Rect(x - width / 2, y - height / 2, width, height) */
+	const fdb_detection& f = face_out[0];
+	const int rx = f.center_x - f.width / 2, ry = f.center_y - f.height / 2;
+	for (int i = 0; i < n_features; ++i) { /* ffpDetectApp.cpp:589-596: detector->detect(img, bounds) */
+		fdb_detector* d = features[i];
+		if (!d) return fail(FDB_ERR_INVALID_ARGUMENT, "null feature detector");
+		s = fdb_detect_roi(d, frame_host, pitch, rx, ry, f.width, f.height, d->svm ? FDB_STAGE_NMS : FDB_STAGE_WVM,
+				feature_out + (int64_t)i * feature_cap_each, feature_cap_each, &n_feature[i]);
+		if (s) return s;
+	}
+	return FDB_OK;
+}
+
 int fdb_evaluate_samples(fdb_detector* det, const uint8_t* frame_host, int64_t pitch, const int32_t* samples_xywh, int64_t n,
 		int32_t max_svm_patches, uint8_t* target_out, double* weight_out) {
 	if (!det || !det->prepared) return fail(FDB_ERR_INVALID_ARGUMENT, "detector not prepared (call fdb_detector_prepare)");

@@ -370,6 +370,21 @@ class SlidingWindowCascade:
         return list(c)
 
 
+def detect_face_features(face, features, frame, cap=4096):
+    """ffpDetectApp.cpp:553-596: face detector on the frame, then each feature detector inside the first face's bounds.
+    face / features: prepared SlidingWindowCascade objects. -> (face detections, [feature detections per detector])"""
+    frame = np.ascontiguousarray(frame, np.uint8)
+    lib = face.ctx.lib
+    fdets = np.zeros(cap, DETECTION_DTYPE)
+    out = np.zeros((max(len(features), 1), cap), DETECTION_DTYPE)
+    nf = C.c_int64()
+    counts = (C.c_int64 * max(len(features), 1))()
+    handles = (C.c_void_p * max(len(features), 1))(*[f.h for f in features])
+    capi.check(lib, lib.fdb_detect_face_features(face.h, handles, len(features), frame.ctypes.data, frame.shape[1], fdets.ctypes.data, cap,
+                                                 C.byref(nf), out.ctypes.data, cap, counts))
+    return fdets[:nf.value].copy(), [out[i, :counts[i]].copy() for i in range(len(features))]
+
+
 class SdmLandmarkModel:
     """fdb_sdm: superviseddescent::SdmLandmarkModel + SdmLandmarkModelFitting (SdmLandmarkModel.hpp:44-256) for batches of
     faces. `model` is a featuredetection_b200.synthetic.SdmModel; `path` a reference text model (SdmLandmarkModel::load)."""

@@ -482,6 +482,15 @@ FDB_API int fdb_detector_single_dense(fdb_detector* det);
  * and the number of launches (one per chunk of frames): the roofline numerator of bench.py --workload single-psvm */
 FDB_API int fdb_detector_single_dense_profile(fdb_detector* det, double* kernel_ms, int32_t* launches);
 
+/* The per-frame flow of ffpDetectApp (ffpDetectApp.cpp:553-596): the face detector on the whole frame, then every feature
+ * detector restricted to the bounds of the FIRST (most probable) face patch - Patch::getBounds() = {x - w / 2, y - h / 2, w, h}
+ * - through Detector::detect(img, roi). face_out receives the face detections; feature_out has feature_cap_each slots per
+ * feature detector, n_feature[i] their counts. Without a face nothing else runs (all n_feature = 0). All detectors must be
+ * prepared for the frame's size. */
+FDB_API int fdb_detect_face_features(fdb_detector* face, fdb_detector* const* features, int32_t n_features,
+		const uint8_t* frame_host, int64_t pitch, fdb_detection* face_out, int64_t face_cap, int64_t* n_face,
+		fdb_detection* feature_out, int64_t feature_cap_each, int64_t* n_feature);
+
 /* condensation::WvmSvmModel::evaluate(image, samples) (libCondensation/src/condensation/WvmSvmModel.cpp:74-119): the
  * tracker's sparse use of the two classifiers on one frame. samples_xywh[i] = {centre x, centre y, width, height} (Sample.hpp);
  * each sample's patch is DirectPyramidFeatureExtractor::extract(x, y, w, h) (DirectPyramidFeatureExtractor.cpp:67-73,133-147;

@@ -74,3 +74,38 @@ def test_evaluate_samples_edge_cases(ctx, face_models):
     single.prepare(640, 480, 1)
     with pytest.raises(capi.FdbError):
         single.evaluate_samples(frame, np.array([[320, 240, 200, 200]], np.int32))
+
+
+@pytest.mark.gpu
+def test_face_then_feature_detectors_in_the_face_box(ctx, face_models):
+    """ffpDetectApp.cpp:553-596: face detector, then the landmark detectors inside the bounds of the first face patch"""
+    from oracle import fdoracle as fo
+    from featuredetection_b200 import capi
+    from featuredetection_b200.detector import SlidingWindowCascade, detect_face_features
+    det_kw, wvm, svm = face_models
+    face = SlidingWindowCascade(ctx, det_kw, wvm, svm)
+    face.prepare(640, 480, 1)
+    names = ["RightEyeCenter", "NoseTip"]
+    models = [syn.landmark_models(n) for n in names]
+    feats = []
+    for kw, w, s in models:
+        c = SlidingWindowCascade(ctx, kw, w, s)
+        c.prepare(640, 480, 1)
+        feats.append(c)
+    checked = 0
+    for k in (0, 1, 2):
+        frame = syn.synthetic_frame(k)
+        fd, per = detect_face_features(face, feats, frame)
+        ref = fo.detect_frame(det_kw, fo.Wvm(wvm), fo.Svm(svm), frame, stage=capi.FDB_STAGE_NMS)["detections"]
+        assert list(fd["window"]) == list(ref["window"])
+        if len(ref) == 0:
+            assert all(len(p) == 0 for p in per)
+            continue
+        f = ref[0]
+        roi = (int(f["center_x"] - f["width"] // 2), int(f["center_y"] - f["height"] // 2), int(f["width"]), int(f["height"]))
+        for (kw, w, s), mine in zip(models, per):
+            r = fo.detect_frame(kw, fo.Wvm(w), fo.Svm(s), frame, stage=capi.FDB_STAGE_NMS, roi=roi)["detections"]
+            assert list(mine["window"]) == list(r["window"]) and np.array_equal(mine["center_x"], r["center_x"])
+            assert np.allclose(mine["probability"], r["probability"], rtol=0, atol=1e-9)
+            checked += 1
+    assert checked > 0

@@ -90,10 +90,20 @@ def test_single_prvm_detector(ctx, face_models):
     casc.prepare(320, 240, 2)
     dets, dist = casc.detect_single(frames)
     ro = fo.Rvm(model)
+    import ctypes as C
+    from featuredetection_b200 import capi
+    desc = syn.detector_desc(**kw)
     for k in range(2):
+        # the oracle's own window grid (fdo_enumerate: DirectPyramidFeatureExtractor.cpp:83-121, bounds from the theoretical scale)
+        L = fo.lib()
+        p = L.fdo_pyramid_build(frames[k].ctypes.data, 320, 240, 320, desc.incremental_scale_factor, desc.min_scale_factor, desc.max_scale_factor)
+        infos = (capi.LayerInfo * p.contents.n_layers)()
+        total = L.fdo_enumerate(p, 20, 20, 1, 1, 0, 0, 0, 0, infos, p.contents.n_layers)
+        L.fdo_pyramid_free(p)
         _, layers = fo.pyramid(frames[k], kw["incremental_scale_factor"], kw["min_scale_factor"], kw["max_scale_factor"])
-        patches = np.stack([fo.hq64(img[y:y + 20, x:x + 20]).ravel() for _, _, img in layers
-                            for y in range(img.shape[0] - 20) for x in range(img.shape[1] - 20)])  # strict < bounds (DirectPyramidFeatureExtractor.cpp:101-103)
+        patches = np.stack([fo.hq64(img[y:y + 20, x:x + 20]).ravel() for (_, _, img), info in zip(layers, infos)
+                            for y in range(info.windows_y) for x in range(info.windows_x)])
+        assert len(patches) == total
         rl, rd, rp, rq = ro.eval(patches)
         assert dist.shape[1] == len(patches)
         assert np.max(np.abs(dist[k] - rd)) <= 1e-9
