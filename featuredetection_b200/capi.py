@@ -172,6 +172,9 @@ SYMBOLS = [
     ("fdb_wvm_file_load", C.c_int, [C.c_char_p, C.c_char_p, _P(C.c_void_p)]),
     ("fdb_wvm_file_desc", _P(WvmDesc), [C.c_void_p]),
     ("fdb_wvm_file_free", None, [C.c_void_p]),
+    ("fdb_rvm_file_load", C.c_int, [C.c_char_p, C.c_char_p, _P(C.c_void_p)]),
+    ("fdb_rvm_file_desc", _P(RvmDesc), [C.c_void_p]),
+    ("fdb_rvm_file_free", None, [C.c_void_p]),
     ("fdb_svm_mat_load", C.c_int, [C.c_char_p, C.c_char_p, _P(C.c_void_p)]),
     ("fdb_gray_from_bgr", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     ("fdb_detect_batch_bgr", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, _P(C.c_int64)]),

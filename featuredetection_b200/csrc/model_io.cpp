@@ -225,6 +225,11 @@ struct fdb_wvm_file {
 	std::vector<fdb_rect4> area_rec;
 };
 
+struct fdb_rvm_file {
+	fdb_rvm_desc desc;
+	std::vector<float> support_vectors, coefficients, hierarchical_thresholds;
+};
+
 namespace {
 
 const MatArray* mat_var(const MatFile& f, const std::string& name) { return f.get(name); }
@@ -356,6 +361,87 @@ int fdb_wvm_file_load(const char* classifier_path, const char* thresholds_path, 
 
 const fdb_wvm_desc* fdb_wvm_file_desc(const fdb_wvm_file* f) { return f ? &f->desc : nullptr; }
 void fdb_wvm_file_free(fdb_wvm_file* f) { delete f; }
+
+/* RvmClassifier::loadFromMatlab (RvmClassifier.cpp:141-319) + ProbabilisticRvmClassifier::loadSigmoidParamsFromMatlab
+ * (ProbabilisticRvmClassifier.cpp:92-125): num_hk, param_nonlin1_rvm | param_nonlin1 {bias, kernel type, basis parameter
+ * (/ 65025), power, divisor}, support_hk%d as CV_32F vectors in row-major order (no grey-value scaling), weight_hk%d (i + 1
+ * coefficients of level i), hierar_thresh and posterior_wrvm = {B, A} from the thresholds file; setNumFiltersToUse(num_hk). */
+int fdb_rvm_file_load(const char* classifier_path, const char* thresholds_path, fdb_rvm_file** out) {
+	if (!classifier_path || !thresholds_path || !out) return fail(FDB_ERR_INVALID_ARGUMENT, "null argument");
+	*out = nullptr;
+	MatFile mf; std::string err;
+	if (!mat_read(classifier_path, &mf, &err)) return fail(FDB_ERR_INVALID_ARGUMENT, "RvmClassifier: Could not open the provided classifier filename: " + err);
+	const MatArray* a = mat_var(mf, "num_hk");
+	if (!a || a->real.empty()) return fail(FDB_ERR_RUNTIME, "RvmClassifier: There is a no num_hk in the classifier file.");
+	const int nfilter = (int)a->real[0];
+	if (nfilter < 1 || nfilter > 4096) return fail(FDB_ERR_RUNTIME, "RvmClassifier: bad num_hk");
+	a = mat_var(mf, "param_nonlin1_rvm");
+	if (!a) a = mat_var(mf, "param_nonlin1");
+	if (!a || a->real.size() < 5) return fail(FDB_ERR_RUNTIME, "RvmClassifier: Could not find kernel parameters and bias.");
+	std::unique_ptr<fdb_rvm_file> f(new fdb_rvm_file);
+	fdb_rvm_desc& d = f->desc;
+	d = fdb_rvm_desc();
+	d.bias = (float)a->real[0];
+	const int nonLinType = (int)a->real[1];
+	const float basisParam = (float)(a->real[2] / 65025.0);
+	const int polyPower = (int)a->real[3];
+	const float divisor = (float)a->real[4];
+	if (nonLinType == 1) { /* PolynomialKernel(1 / divisor, basisParam / divisor, polyPower), float arithmetic */
+		d.kernel = FDB_KERNEL_POLYNOMIAL;
+		d.poly_alpha = 1 / divisor; d.poly_constant = basisParam / divisor; d.poly_degree = polyPower;
+	} else if (nonLinType == 2) {
+		d.kernel = FDB_KERNEL_RBF;
+		d.gamma = basisParam;
+	} else return fail(FDB_ERR_RUNTIME, "RvmClassifier: Unsupported kernel type. Currently, only polynomial and RBF kernels are supported.");
+	a = mat_var(mf, "support_hk1");
+	if (!a) return fail(FDB_ERR_RUNTIME, "RvmClassifier: Unable to find the matrix 'support_hk1' in the classifier file.");
+	if (a->dims.size() != 2) return fail(FDB_ERR_RUNTIME, "RvmClassifier: The matrix 'support_hk1' in the classifier file should have 2 dimensions.");
+	const int h = dim0(*a), w = dim1(*a);
+	d.num_filters = nfilter; d.dim = w * h; d.sv_type = FDB_SV_F32;
+	f->support_vectors.assign((size_t)nfilter * w * h, 0.f);
+	f->coefficients.assign((size_t)nfilter * (nfilter + 1) / 2, 0.f);
+	int n_weights = 0;
+	for (int i = 0; i < nfilter; ++i) {
+		const std::string idx = std::to_string(i + 1);
+		a = mat_var(mf, "support_hk" + idx);
+		if (!a) return fail(FDB_ERR_RUNTIME, "RvmClassifier: Unable to find the matrix 'support_hk" + idx + "' in the classifier file.");
+		if (a->dims.size() != 2) return fail(FDB_ERR_RUNTIME, "RvmClassifier: The matrix 'support_hk" + idx + "' in the classifier file should have 2 dimensions.");
+		if (a->real.size() < (size_t)w * h) return fail(FDB_ERR_RUNTIME, "RvmClassifier: support_hk" + idx + " is smaller than support_hk1");
+		float* values = &f->support_vectors[(size_t)i * w * h];
+		size_t k = 0;
+		for (int x = 0; x < w; ++x)      /* column-major order (ML-convention), RvmClassifier.cpp:252-254 */
+			for (int y = 0; y < h; ++y) values[(size_t)y * w + x] = (float)a->real[k++];
+		a = mat_var(mf, "weight_hk" + idx);
+		if (a) { /* a missing weight_hk is skipped by the reference and caught by the size check at the end */
+			if (dim1(*a) != i + 1 && dim0(*a) != i + 1)
+				return fail(FDB_ERR_RUNTIME, "RvmClassifier: The matrix weight_hk" + idx + " in the classifier file should have a dimensions 1x" + idx + " or " + idx + "x1");
+			for (int j = 0; j <= i; ++j) f->coefficients[(size_t)i * (i + 1) / 2 + j] = (float)a->real[j];
+			++n_weights;
+		}
+	}
+	MatFile tf;
+	if (!mat_read(thresholds_path, &tf, &err)) return fail(FDB_ERR_RUNTIME, "RvmClassifier: Unable to open the thresholds file (wrong format?):" + err);
+	a = mat_var(tf, "hierar_thresh");
+	if (!a) return fail(FDB_ERR_RUNTIME, "RvmClassifier: Unable to find the matrix hierar_thresh in the thresholds file.");
+	for (int o = 0; o < dim1(*a) && (size_t)o < a->real.size(); ++o) f->hierarchical_thresholds.push_back((float)a->real[o]);
+	if ((int)f->hierarchical_thresholds.size() != n_weights || n_weights != nfilter)
+		return fail(FDB_ERR_RUNTIME, "RvmClassifier: Something seems to be wrong, hierarchicalThresholds.size() != coefficients.size(): "
+				+ std::to_string(f->hierarchical_thresholds.size()) + "!=" + std::to_string(n_weights));
+	a = mat_var(tf, "posterior_wrvm");
+	if (!a) return fail(FDB_ERR_RUNTIME, "ProbabilisticRvmClassifier: Unable to find the vector posterior_wrvm. If you don't want probabilistic output, don't use a probabilistic classifier.");
+	if (dim1(*a) != 2 || a->real.size() < 2) return fail(FDB_ERR_RUNTIME, "ProbabilisticRvmClassifier: Size of vector posterior_wrvm !=2. If you don't want probabilistic output, don't use a probabilistic classifier.");
+	d.logistic_b = a->real[0]; d.logistic_a = a->real[1];
+	d.num_filters_to_use = nfilter;
+	d.support_vectors = f->support_vectors.data();
+	d.coefficients = f->coefficients.data();
+	d.hierarchical_thresholds = f->hierarchical_thresholds.data();
+	*out = f.release();
+	return FDB_OK;
+}
+
+const fdb_rvm_desc* fdb_rvm_file_desc(const fdb_rvm_file* f) { return f ? &f->desc : nullptr; }
+
+void fdb_rvm_file_free(fdb_rvm_file* f) { delete f; }
 
 int fdb_svm_mat_load(const char* classifier_path, const char* logistic_path, fdb_svm_file** out) {
 	if (!classifier_path || !out) return fail(FDB_ERR_INVALID_ARGUMENT, "null argument");

@@ -442,6 +442,12 @@ typedef struct fdb_wvm_file fdb_wvm_file;
 FDB_API int fdb_wvm_file_load(const char* classifier_path, const char* thresholds_path, fdb_wvm_file** out);
 FDB_API const fdb_wvm_desc* fdb_wvm_file_desc(const fdb_wvm_file* file);
 FDB_API void fdb_wvm_file_free(fdb_wvm_file* file);
+/* RvmClassifier::loadFromMatlab (RvmClassifier.cpp:141-319) + the posterior_wrvm logistic (ProbabilisticRvmClassifier.cpp:92-125):
+ * float32 reduced set vectors, coefficient rows, hierar_thresh; the descriptor borrows the file object's arrays */
+typedef struct fdb_rvm_file fdb_rvm_file;
+FDB_API int fdb_rvm_file_load(const char* classifier_path, const char* thresholds_path, fdb_rvm_file** out);
+FDB_API const fdb_rvm_desc* fdb_rvm_file_desc(const fdb_rvm_file* file);
+FDB_API void fdb_rvm_file_free(fdb_rvm_file* file);
 FDB_API int fdb_svm_mat_load(const char* classifier_path, const char* logistic_path, fdb_svm_file** out);
 
 /* ------------------------------------------------------------------------------------------

@@ -139,3 +139,49 @@ def test_storage_types_and_small_elements(built, tmp_path):
     assert (d.num_lin_filters, d.num_filters_per_level, d.num_levels) == (2, 2, 1)
     assert np.array_equal(_arr(d.app_rsv_convol, 2, np.float64), written["app_rsv_convol"][0].astype(np.float64) * 65025.0)
     lib.fdb_wvm_file_free(f)
+
+
+@pytest.mark.parametrize("kernel_type", [2, 1])
+def test_rvm_mat_reader(built, tmp_path, kernel_type):
+    """RvmClassifier::loadFromMatlab (RvmClassifier.cpp:141-319) + posterior_wrvm: float32 vectors in row-major order (no
+    grey-value scaling), i + 1 coefficients for level i, thresholds, kernel parameters as the SVM loader computes them"""
+    lib = capi.load_library()
+    rng = np.random.default_rng(4)
+    n, h, w = 5, 6, 4
+    svs = [rng.uniform(0, 1, (h, w)) for _ in range(n)]
+    weights = [rng.normal(0, 1, i + 1) for i in range(n)]
+    thr = rng.normal(0, 1, n)
+    cpath, tpath = str(tmp_path / "rvm.mat"), str(tmp_path / "thr.mat")
+    d = {"num_hk": np.array([[float(n)]]), "param_nonlin1_rvm": np.array([[0.5, float(kernel_type), 0.04, 3.0, 2.0]])}
+    for i in range(n):
+        d["support_hk%d" % (i + 1)] = svs[i]
+        d["weight_hk%d" % (i + 1)] = weights[i].reshape(1, -1) if i % 2 else weights[i].reshape(-1, 1)
+    sio.savemat(cpath, d, format="5", do_compression=True)
+    sio.savemat(tpath, {"hierar_thresh": thr.reshape(1, -1), "posterior_wrvm": np.array([[-2.5, 0.25]])}, format="5")
+    f = C.c_void_p()
+    capi.check(lib, lib.fdb_rvm_file_load(cpath.encode(), tpath.encode(), C.byref(f)))
+    try:
+        r = lib.fdb_rvm_file_desc(f).contents
+        assert (r.num_filters, r.num_filters_to_use, r.dim, r.sv_type) == (n, n, w * h, capi.FDB_SV_F32)
+        basis = np.float32(0.04 / 65025.0)
+        if kernel_type == 2:
+            assert r.kernel == capi.FDB_KERNEL_RBF and r.gamma == float(basis)
+        else:
+            assert (r.kernel, r.poly_degree) == (capi.FDB_KERNEL_POLYNOMIAL, 3)
+            assert r.poly_alpha == float(np.float32(1) / np.float32(2)) and r.poly_constant == float(basis / np.float32(2))
+        assert r.bias == np.float32(0.5) and (r.logistic_a, r.logistic_b) == (0.25, -2.5)
+        got = np.ctypeslib.as_array(C.cast(r.support_vectors, C.POINTER(C.c_float)), shape=(n, h, w))
+        assert np.array_equal(got, np.stack(svs).astype(np.float32))
+        coef = _arr(r.coefficients, n * (n + 1) // 2, np.float32)
+        assert np.array_equal(coef, np.concatenate(weights).astype(np.float32))
+        assert np.array_equal(_arr(r.hierarchical_thresholds, n, np.float32), thr.astype(np.float32))
+    finally:
+        lib.fdb_rvm_file_free(f)
+    # error paths of the reference: missing thresholds / wrong count / missing kernel parameters
+    sio.savemat(tpath, {"hierar_thresh": thr[:3].reshape(1, -1), "posterior_wrvm": np.array([[-2.5, 0.25]])}, format="5")
+    assert lib.fdb_rvm_file_load(cpath.encode(), tpath.encode(), C.byref(f)) != 0
+    assert b"hierarchicalThresholds.size() != coefficients.size()" in lib.fdb_last_error()
+    d.pop("param_nonlin1_rvm")
+    sio.savemat(cpath, d, format="5")
+    assert lib.fdb_rvm_file_load(cpath.encode(), tpath.encode(), C.byref(f)) != 0
+    assert b"Could not find kernel parameters" in lib.fdb_last_error()
