@@ -880,9 +880,9 @@ def main():
         algo_bytes = (W * H + WINDOW_BYTES * nwin / len(cascs)) * frames_per_launch   # frame read once + dense records
         kernel_ms = ms_wvm / n_launch
         achieved = algo_bytes / (kernel_ms * 1e-3) / 1e9
-        # dram__bytes_read.sum + dram__bytes_write.sum of one wvm_strip_kernel launch (64 frames, FaceFrontal) from
-        # profiles/wvm_r1p_raw.txt (ncu --set full); the layers it reads were just written by pyrDown and sit in L2
-        traffic = 2585600 if args.workload == "facefrontal" and n == 256 else None
+        # dram__bytes_read.sum + dram__bytes_write.sum of one wvm_strip_mma_kernel launch (64 frames, FaceFrontal) from
+        # profiles/wvm_r1w_raw.txt (ncu --set full): 2.939 MB + 1 KB; the layers it reads were just written by pyrDown and sit in L2
+        traffic = 2940416 if args.workload == "facefrontal" and n == 256 else None
         cpu = None
         if not args.no_cpu_baseline:
             arm = CpuArm(args.profile, args.feature)
@@ -903,11 +903,11 @@ def main():
                     "d2h_bytes_per_step": int(len(dets_e2e) * DETECTION_DTYPE.itemsize + 4),
                     "ms_per_step": e2e_total / args.steps, "frames_per_s": e2e_value / nwin},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "wvm_strip_kernel (fused HistEq64 + first 8 WVM filters on every window; one launch per 64-frame chunk)",
+            "roofline": {"bound": "hbm", "kernel": "wvm_strip_mma_kernel (fused HistEq64 + the first 8 WVM filters of every window as an exact u8 IMMA product; one launch per 64-frame chunk)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": int(algo_bytes),
                          "kernel_ms": float(kernel_ms), "launches_per_step": int(n_launch),
-                         "note": "instruction/LSU bound by construction: ~5e3 scalar ops per window vs 27 B of compulsory traffic (SURVEY.md 8(d)); issue-slot utilisation 37 %, see profiles/"},
+                         "note": "instruction/LSU bound by construction: ~5e3 scalar ops per window vs 27 B of compulsory traffic (SURVEY.md 8(d)); issue-slot utilisation 50 % (profiles/wvm_r1w_raw.txt)"},
             "stage1_ms": {"resize": float(ms_resize), "pyrdown": float(ms_down), "window_kernel": float(ms_wvm), "deep_kernel": float(ms_deep), "total": float(ms_stage1)},
             "detections_per_step": int(len(dets)) * world,
             "cpu_baseline": cpu,
