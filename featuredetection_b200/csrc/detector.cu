@@ -103,6 +103,9 @@ struct fdb_detector {
 	/* `single` detector on the tensor cores (svm_dense.cu): distances of a chunk, positives list */
 	double* d_sd_dist = nullptr; int* d_sd_count = nullptr; DensePositive* d_sd_pos = nullptr;
 	int* h_sd_count = nullptr; DensePositive* h_sd_pos = nullptr; int sd_pos_cap = 0;
+	/* fdb_evaluate_samples scratch (grow-only; the tracker calls it every frame) */
+	std::vector<void*> es_owned; int es_cap = 0;
+	SvmItem* d_es_items = nullptr; uint8_t* d_es_patches = nullptr; fdb_window_score* d_es_scores = nullptr; double* d_es_dist = nullptr;
 	double sd_kernel_ms = 0; int sd_kernel_launches = 0; /* svm_dense_kernel time of the last call (CUDA events) */
 	int64_t counts[5] = {0, 0, 0, 0, 0};
 };
@@ -355,6 +358,7 @@ void release(fdb_detector* det) {
 	}
 	if (det->ev_begin) { cudaEventDestroy(det->ev_begin); det->ev_begin = nullptr; }
 	free_all(det->owned, &det->owned_host);
+	free_all(det->es_owned); det->es_cap = 0;
 	det->prepared = false;
 	det->d_patches = nullptr; det->d_patches_bytes = 0;
 	det->d_down.clear(); det->n_down.clear(); det->max_down_px.clear();
@@ -554,13 +558,20 @@ int evaluate_samples(fdb_detector* det, const uint8_t* frame_host, int64_t pitch
 	}
 	const int m = (int)items.size();
 	if (m == 0) return FDB_OK;
-	std::vector<void*> tmp;
-	SvmItem* d_items; uint8_t* d_patches; fdb_window_score* d_scores; double* d_dist;
-	int s = dev_alloc(&d_items, (size_t)m, tmp);
-	if (!s) s = dev_alloc(&d_patches, (size_t)m * npix, tmp);
-	if (!s) s = dev_alloc(&d_scores, (size_t)m, tmp);
-	if (!s) s = dev_alloc(&d_dist, (size_t)m, tmp);
-	if (s) { free_all(tmp); return s; }
+	int s = FDB_OK;
+	if (m > det->es_cap) {
+		free_all(det->es_owned);
+		det->es_cap = 0;
+		const size_t cap = (size_t)std::max(m, 1024) * 3 / 2;
+		s = dev_alloc(&det->d_es_items, cap, det->es_owned);
+		if (!s) s = dev_alloc(&det->d_es_patches, cap * npix, det->es_owned);
+		if (!s) s = dev_alloc(&det->d_es_scores, cap, det->es_owned);
+		if (!s) s = dev_alloc(&det->d_es_dist, cap, det->es_owned);
+		if (s) { free_all(det->es_owned); return s; }
+		det->es_cap = (int)cap;
+	}
+	SvmItem* d_items = det->d_es_items; uint8_t* d_patches = det->d_es_patches;
+	fdb_window_score* d_scores = det->d_es_scores; double* d_dist = det->d_es_dist;
 	std::vector<fdb_window_score> scores((size_t)m);
 	auto run = [&]() -> int {
 		CUDA_TRY(cudaMemcpy2DAsync(sl.d_frames, (size_t)plan.width, frame_host, (size_t)pitch, (size_t)plan.width, (size_t)plan.height,
@@ -579,7 +590,7 @@ int evaluate_samples(fdb_detector* det, const uint8_t* frame_host, int64_t pitch
 		return FDB_OK;
 	};
 	s = run();
-	if (s) { free_all(tmp); return s; }
+	if (s) return s;
 	/* WVM results per patch (ProbabilisticWvmClassifier::getProbability) */
 	std::vector<double> pwvm((size_t)m);
 	std::vector<int> remaining; /* WVM-positive patches in first-seen order */
@@ -590,7 +601,7 @@ int evaluate_samples(fdb_detector* det, const uint8_t* frame_host, int64_t pitch
 		if (r.level + 1 == wv->dev.num_lin && r.fout >= wv->thresholds[(size_t)r.level]) remaining.push_back(k);
 	}
 	for (int64_t i = 0; i < n; ++i) if (sample_patch[(size_t)i] >= 0) weight_out[i] = 0.5 * pwvm[(size_t)sample_patch[(size_t)i]];
-	if (remaining.empty() || !det->svm) { free_all(tmp); return FDB_OK; }
+	if (remaining.empty() || !det->svm) return FDB_OK;
 	if (max_svm_patches > 0 && (int)remaining.size() > max_svm_patches) {
 		std::stable_sort(remaining.begin(), remaining.end(), [&](int a, int b) { return pwvm[(size_t)a] > pwvm[(size_t)b]; });
 		remaining.resize((size_t)max_svm_patches);
@@ -611,7 +622,6 @@ int evaluate_samples(fdb_detector* det, const uint8_t* frame_host, int64_t pitch
 		return FDB_OK;
 	};
 	s = run2();
-	free_all(tmp);
 	if (s) return s;
 	std::vector<int> patch_rank((size_t)m, -1);
 	for (int k = 0; k < q; ++k) patch_rank[(size_t)remaining[(size_t)k]] = k;
