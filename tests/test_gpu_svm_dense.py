@@ -132,3 +132,23 @@ def test_single_detector_dense_full_size(ctx, face_models):
             wins.append(L["first_window"] + iy * L["windows_x"] + ix)
     rd, _, _ = so.eval(np.stack(patches))
     assert np.max(np.abs(dist[2][wins] - rd)) <= TOL
+
+
+def test_single_detector_dense_other_patch_size(ctx):
+    """16x24 patches (the ear detectors): the generic producer path of svm_dense_kernel against the per-window kernel and,
+    on a sample, the oracle"""
+    fo = _oracle()
+    det_kw, _, _ = syn.landmark_models("LeftEarCenter")
+    kw = dict(det_kw, min_scale_factor=0.3, max_scale_factor=0.5)
+    svm = syn.make_svm(16, 24, seed=8, num_sv=200)
+    frames = np.ascontiguousarray(syn.synthetic_frames(60, 2)[:, :240, :320])
+    casc = SlidingWindowCascade(ctx, kw, None, svm)
+    casc.prepare(320, 240, 2)
+    assert casc.single_dense
+    dets, dist = casc.detect_single(frames)
+    with _per_window_kernel():
+        d2, dist2 = casc.detect_single(frames)
+    assert np.max(np.abs(dist - dist2)) <= TOL, np.max(np.abs(dist - dist2))
+    assert list(d2["window"]) == list(dets["window"])
+    ref = fo.detect_frame(kw, None, fo.Svm(svm), frames[1], frame_index=1)
+    assert np.max(np.abs(dist[1] - ref["svm_dense"])) <= TOL
