@@ -295,7 +295,7 @@ def run_sdm(args, rank, world, local_rank):
         achieved = algo_bytes / (hog_ms * 1e-3) / 1e9
         gemm_flops = 2.0 * n * K * N
         cpu = None
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:  # the CPU baseline is a rank-0, N=1 datum
             arm = SdmCpuArm()
             arm.run(1)
             per_core = max(8, args.cpu_frames_per_core)
@@ -643,7 +643,7 @@ def run_single(args, rank, world, local_rank):
         bf16 = json.load(open(mp_path))["bf16_tflops"] if os.path.exists(mp_path) else 1638.6  # burst: the kernel is timed alone
         peak = 2.0 * bf16  # kind::i8 runs at twice the bf16 rate on sm_100a; no measured int8 figure exists on this pool
         cpu = None
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:  # the CPU baseline is a rank-0, N=1 datum
             arm = SingleCpuArm()
             arm.run(1)
             wcpu, wall = arm.run(8)
@@ -884,7 +884,7 @@ def main():
         # profiles/wvm_r1w_raw.txt (ncu --set full): 2.939 MB + 1 KB; the layers it reads were just written by pyrDown and sit in L2
         traffic = 2940416 if args.workload == "facefrontal" and n == 256 else None
         cpu = None
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:  # the CPU baseline is a rank-0, N=1 datum
             arm = CpuArm(args.profile, args.feature)
             arm.run(1)
             wcpu, wall = arm.run(args.cpu_frames_per_core)

@@ -89,8 +89,9 @@ __global__ void __launch_bounds__(RS_QX * RS_TY) resize_kernel(const uint8_t* __
 #define FDB_RS_PAIR(A0, A1, A2, T) __funnelshift_r(((T.w & 255) == 0 ? A0 : ((T.w & 255) == 1 ? A1 : A2)), \
 						((T.w & 255) == 0 ? A1 : A2), (unsigned)((T.w >> 8) & 31))
 #define FDB_RS_PIXW(T) { const uint32_t up = FDB_RS_PAIR(p0, p1, p2, T), lo = FDB_RS_PAIR(q0, q1, q2, T); \
-					const int h0 = (int)(up & 255u) * T.y + (int)((up >> 8) & 255u) * T.z; \
-					const int h1 = (int)(lo & 255u) * T.y + (int)((lo >> 8) & 255u) * T.z; \
+					const uint32_t cxy = (uint32_t)T.y | ((uint32_t)T.z << 16); /* a0, a1 <= 2048 as two u16 */ \
+					const int h0 = (int)__dp2a_lo(cxy, up, 0u); /* S[sx] * a0 + S[sx + 1] * a1: the two low bytes of `up` */ \
+					const int h1 = (int)__dp2a_lo(cxy, lo, 0u); \
 					v = (((ty.y * (h0 >> 4)) >> 16) + ((ty.z * (h1 >> 4)) >> 16) + 2) >> 2; }
 				int v;
 				FDB_RS_PIXW(t0) packed = (uint32_t)(v & 255);
