@@ -84,6 +84,7 @@ __global__ void __launch_bounds__(RS_QX * RS_TY) resize_kernel(const uint8_t* __
 				 * byte pairs (sx, sx+1) are cut out with funnel shifts. t.w = word select | bit shift << 8 | base word << 16 */
 				const uint32_t* __restrict__ r0 = reinterpret_cast<const uint32_t*>(s0);
 				const uint32_t* __restrict__ r1 = reinterpret_cast<const uint32_t*>(s1);
+				const int by0 = ty.y << 16, by1 = ty.z << 16; /* coefficients <= 2048: no overflow; all factors are non-negative */
 				const uint32_t p0 = __ldg(r0 + b0), p1 = __ldg(r0 + b1), p2 = __ldg(r0 + b2);
 				const uint32_t q0 = __ldg(r1 + b0), q1 = __ldg(r1 + b1), q2 = __ldg(r1 + b2);
 #define FDB_RS_PAIR(A0, A1, A2, T) __funnelshift_r(((T.w & 255) == 0 ? A0 : ((T.w & 255) == 1 ? A1 : A2)), \
@@ -92,7 +93,7 @@ __global__ void __launch_bounds__(RS_QX * RS_TY) resize_kernel(const uint8_t* __
 					const uint32_t cxy = (uint32_t)T.y | ((uint32_t)T.z << 16); /* a0, a1 <= 2048 as two u16 */ \
 					const int h0 = (int)__dp2a_lo(cxy, up, 0u); /* S[sx] * a0 + S[sx + 1] * a1: the two low bytes of `up` */ \
 					const int h1 = (int)__dp2a_lo(cxy, lo, 0u); \
-					v = (((ty.y * (h0 >> 4)) >> 16) + ((ty.z * (h1 >> 4)) >> 16) + 2) >> 2; }
+					v = (__mulhi(by0, h0 >> 4) + __mulhi(by1, h1 >> 4) + 2) >> 2; } /* (b * (h >> 4)) >> 16 as the high word of (b << 16) * (h >> 4) */
 				int v;
 				FDB_RS_PIXW(t0) packed = (uint32_t)(v & 255);
 				FDB_RS_PIXW(t1) packed |= (uint32_t)(v & 255) << 8;
@@ -122,8 +123,8 @@ __global__ void __launch_bounds__(RS_QX * RS_TY) resize_kernel(const uint8_t* __
 
 /* ---------------------------------------------------------------------------------------------
  * pyrDown: grid = (tiles, job, frame); a CTA of 256 threads = 32 x 8 threads, each thread
- * produces a 4 (x) x 2 (y) block of output pixels => a 128 x 16 output tile per CTA.
- * Interior threads read their 7 x 11 input footprint as aligned 32-bit words straight from global
+ * produces a 4 (x) x 4 (y) block of output pixels => a 128 x 32 output tile per CTA.
+ * Interior threads read their 11 x 11 input footprint as aligned 32-bit words straight from global
  * memory (L1 serves the overlap with the neighbours), realign with funnel shifts and evaluate the
  * horizontal [1 4 6 4 1] taps with dp4a on packed bytes; the vertical taps run on registers.
  * Threads whose footprint touches the image border (BORDER_REFLECT_101) take a byte-wise path.
@@ -132,7 +133,8 @@ __global__ void __launch_bounds__(RS_QX * RS_TY) resize_kernel(const uint8_t* __
 #define PD_BX 32
 #define PD_BY 8
 #define PD_TW (PD_BX * 4)
-#define PD_TH (PD_BY * 2)
+#define PD_RY 4              /* output rows per thread: 2 * PD_RY + 3 input rows feed PD_RY output rows */
+#define PD_TH (PD_BY * PD_RY)
 
 __device__ __forceinline__ void pd_hrow_fast(const uint8_t* __restrict__ rowp, int col, int* h) {
 	/* bytes col .. col+10 of the row as three words b[0..3], b[4..7], b[8..11] */
@@ -163,7 +165,7 @@ __global__ void __launch_bounds__(PD_BX * PD_BY) pyrdown_kernel(const uint8_t* _
 	if ((int)blockIdx.x >= tiles_x * tiles_y) return;
 	const int tile_y = (int)blockIdx.x / tiles_x;
 	const int x0 = (((int)blockIdx.x - tile_y * tiles_x) * PD_BX + ((int)threadIdx.x & 31)) * 4;
-	const int y0 = (tile_y * PD_BY + ((int)threadIdx.x >> 5)) * 2;
+	const int y0 = (tile_y * PD_BY + ((int)threadIdx.x >> 5)) * PD_RY;
 	if (x0 >= job.dst_w || y0 >= job.dst_h) return;
 	const uint8_t* __restrict__ src = job.src_offset < 0
 			? frames + (int64_t)blockIdx.z * W * H
@@ -172,21 +174,22 @@ __global__ void __launch_bounds__(PD_BX * PD_BY) pyrdown_kernel(const uint8_t* _
 	const int col = 2 * x0 - 2, row = 2 * y0 - 2;
 	/* fast path: footprint strictly inside the image and not on its last row (aligned word reads may
 	 * run a few bytes past the footprint) */
-	const bool interior = col >= 0 && row >= 0 && col + 16 <= job.src_w && row + 7 < job.src_h;
-	int h[7][4];
+	constexpr int NR = 2 * PD_RY + 3; /* input rows of a thread */
+	const bool interior = col >= 0 && row >= 0 && col + 16 <= job.src_w && row + NR < job.src_h;
+	int h[NR][4];
 	if (interior) {
 #pragma unroll
-		for (int r = 0; r < 7; ++r) pd_hrow_fast(src + (row + r) * job.src_pitch, col, h[r]);
+		for (int r = 0; r < NR; ++r) pd_hrow_fast(src + (row + r) * job.src_pitch, col, h[r]);
 	} else {
 		int cx[11];
 #pragma unroll
 		for (int i = 0; i < 11; ++i) cx[i] = reflect101(col + i, job.src_w);
 #pragma unroll
-		for (int r = 0; r < 7; ++r) pd_hrow_border(src + reflect101(row + r, job.src_h) * job.src_pitch, cx, h[r]);
+		for (int r = 0; r < NR; ++r) pd_hrow_border(src + reflect101(row + r, job.src_h) * job.src_pitch, cx, h[r]);
 	}
 	const int nx = min(4, job.dst_w - x0);
 #pragma unroll
-	for (int oy = 0; oy < 2; ++oy) {
+	for (int oy = 0; oy < PD_RY; ++oy) {
 		if (y0 + oy >= job.dst_h) break;
 		uint32_t packed = 0;
 #pragma unroll
