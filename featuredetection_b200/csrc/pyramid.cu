@@ -133,7 +133,9 @@ __global__ void __launch_bounds__(RS_QX * RS_TY) resize_kernel(const uint8_t* __
 #define PD_BX 32
 #define PD_BY 8
 #define PD_TW (PD_BX * 4)
+#ifndef PD_RY
 #define PD_RY 4              /* output rows per thread: 2 * PD_RY + 3 input rows feed PD_RY output rows */
+#endif
 #define PD_TH (PD_BY * PD_RY)
 
 __device__ __forceinline__ void pd_hrow_fast(const uint8_t* __restrict__ rowp, int col, int* h) {
