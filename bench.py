@@ -441,8 +441,8 @@ SINGLE_STRIDE = 16  # the CPU arm classifies every 16th window of its frames (21
 
 
 def _single_models():
-    """FaceFrontal geometry + its 1024-support-vector u8 RBF SVM; threshold = the 99.9 % quantile of the oracle-independent
-    distances of frame 0 (fixed: computed once from the model and committed here), so that ~0.1 % of the windows are positive"""
+    """FaceFrontal geometry + its 1024-support-vector u8 RBF SVM (threshold 0; run_single raises it to the 99.9 % quantile of
+    frame 0's distances so that ~0.1 % of the windows are positive - the CPU arm times classification, not thresholding)"""
     from featuredetection_b200 import synthetic as syn
     det_kw, _, svm = syn.landmark_models(CFG)
     return det_kw, svm
