@@ -165,6 +165,7 @@ SYMBOLS = [
     ("fdb_pyramid_layer", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int64]),
     ("fdb_plan_layers", C.c_int, [_P(DetectorDesc), C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P(LayerInfo), C.c_int32, _P(C.c_int32), _P(C.c_int64)]),
     ("fdb_overlap_eliminate", C.c_int, [C.c_void_p, C.c_int64, C.c_float, C.c_float, _P(C.c_int64)]),
+    ("fdb_non_maximum_suppression", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_double, C.c_int32, _P(C.c_int64)]),
     ("fdb_five_stage_nms", C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, _P(C.c_int64)]),
     ("fdb_svm_file_load", C.c_int, [C.c_char_p, _P(C.c_void_p)]),
     ("fdb_svm_file_desc", _P(SvmDesc), [C.c_void_p]),

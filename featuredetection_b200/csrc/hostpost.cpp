@@ -131,3 +131,63 @@ void five_stage_nms(std::vector<fdb_detection>& v, int width, int height) {
 }
 
 } // namespace fdb
+
+
+/* detection::NonMaximumSuppression::eliminateRedundantDetections (libDetection/src/detection/NonMaximumSuppression.cpp:27-112),
+ * the IoU suppression of the reference's newer detector family (AggregatedFeaturesDetector.cpp:104-112); host only.
+ * Candidates are sorted by ascending score (:35-39; std::sort - equal scores keep their input order here); the best
+ * remaining candidate opens a cluster and takes every candidate whose overlap with it exceeds the threshold (:48-58,
+ * intersection over union on integer rectangles :60-64); each cluster yields its best member, or the (score-weighted)
+ * mean box rounded half away from zero with the best score (:74-109). Output order: clusters by descending best score. */
+extern "C" int fdb_non_maximum_suppression(float* scores, int32_t* rects_xywh, int64_t n, double overlap_threshold,
+		int32_t maximum_type, int64_t* n_out) {
+	using fdb::fail;
+	if (n < 0 || (n > 0 && (!scores || !rects_xywh)) || !n_out) return fail(FDB_ERR_INVALID_ARGUMENT, "bad detection list");
+	if (maximum_type < FDB_NMS_MAX_SCORE || maximum_type > FDB_NMS_WEIGHTED_AVERAGE)
+		return fail(FDB_ERR_INVALID_ARGUMENT, "NonMaximumSuppression: unsupported maximum type");
+	*n_out = n;
+	if (overlap_threshold == 1.0 || n == 0) return FDB_OK; /* :28-29 */
+	struct Box { float score; int x, y, w, h; };
+	std::vector<Box> pending((size_t)n);
+	for (int64_t i = 0; i < n; ++i) {
+		Box b = {scores[i], rects_xywh[4 * i], rects_xywh[4 * i + 1], rects_xywh[4 * i + 2], rects_xywh[4 * i + 3]};
+		pending[(size_t)i] = b;
+	}
+	std::stable_sort(pending.begin(), pending.end(), [](const Box& a, const Box& b) { return a.score < b.score; });
+	auto iou = [](const Box& a, const Box& b) {
+		const int x1 = std::max(a.x, b.x), y1 = std::max(a.y, b.y);
+		const int iw = std::min(a.x + a.w, b.x + b.w) - x1, ih = std::min(a.y + a.h, b.y + b.h) - y1;
+		const double inter = (iw <= 0 || ih <= 0) ? 0.0 : (double)(iw * ih);     /* cv::Rect operator& and area() */
+		const double uni = (double)(a.w * a.h) + (double)(b.w * b.h) - inter;
+		return inter / uni;
+	};
+	int64_t out = 0;
+	std::vector<Box> members, rest;
+	while (!pending.empty()) {
+		const Box best = pending.back();
+		members.clear(); rest.clear();
+		for (const Box& c : pending) (iou(best, c) <= overlap_threshold ? rest : members).push_back(c);
+		std::reverse(members.begin(), members.end()); /* descending score: the best one first */
+		pending.swap(rest);
+		if (members.empty()) return fail(FDB_ERR_RUNTIME, "NonMaximumSuppression: a box does not overlap itself (empty rectangle)");
+		Box r = members.front();
+		if (maximum_type != FDB_NMS_MAX_SCORE) {
+			double ws = 0, xs = 0, ys = 0, wsum = 0, hs = 0;
+			for (const Box& m : members) {
+				const double wgt = maximum_type == FDB_NMS_AVERAGE ? 1.0 : (double)m.score;
+				ws += wgt;
+				if (maximum_type == FDB_NMS_AVERAGE) { xs += m.x; ys += m.y; wsum += m.w; hs += m.h; }
+				else { xs += wgt * m.x; ys += wgt * m.y; wsum += wgt * m.w; hs += wgt * m.h; }
+			}
+			const double den = maximum_type == FDB_NMS_AVERAGE ? (double)members.size() : ws;
+			r.x = (int)std::round(xs / den); r.y = (int)std::round(ys / den);
+			r.w = (int)std::round(wsum / den); r.h = (int)std::round(hs / den);
+		}
+		scores[out] = r.score;
+		rects_xywh[4 * out] = r.x; rects_xywh[4 * out + 1] = r.y; rects_xywh[4 * out + 2] = r.w; rects_xywh[4 * out + 3] = r.h;
+		++out;
+	}
+	*n_out = out;
+	return FDB_OK;
+}
+

@@ -418,6 +418,13 @@ FDB_API int fdb_overlap_eliminate(fdb_detection* dets, int64_t n, float dist, fl
  * (FiveStageSlidingWindowDetector.cpp:143-184,276-311) on the SVM-positive patches of ONE frame. */
 FDB_API int fdb_five_stage_nms(fdb_detection* dets, int64_t n, int32_t width, int32_t height, int64_t* n_out);
 
+/* detection::NonMaximumSuppression::eliminateRedundantDetections (libDetection/src/detection/NonMaximumSuppression.cpp:27-112;
+ * used by AggregatedFeaturesDetector.cpp:104-112): intersection-over-union suppression of n scored boxes {x, y, w, h}, in
+ * place; the first *n_out entries are the surviving boxes, best cluster first. maximum_type: fdb_nms_maximum_type. */
+typedef enum fdb_nms_maximum_type { FDB_NMS_MAX_SCORE = 0, FDB_NMS_AVERAGE = 1, FDB_NMS_WEIGHTED_AVERAGE = 2 } fdb_nms_maximum_type;
+FDB_API int fdb_non_maximum_suppression(float* scores, int32_t* rects_xywh, int64_t n, double overlap_threshold,
+		int32_t maximum_type, int64_t* n_out);
+
 /* The reference's SVM text container (SvmClassifier::store/load(std::ifstream&), SvmClassifier.cpp:68-158,
  * followed by ProbabilisticSvmClassifier's "Logistic a b" line, ProbabilisticSvmClassifier.cpp:65-78).
  * The returned descriptor points into the file object and stays valid until fdb_svm_file_free. */

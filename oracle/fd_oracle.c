@@ -944,3 +944,65 @@ void fdo_bgr_to_gray(const uint8_t* bgr, int width, int height, int pitch, uint8
 		for (int x = 0; x < width; ++x, s += 3) d[x] = (uint8_t)((s[0] * 1868 + s[1] * 9617 + s[2] * 4899 + (1 << 13)) >> 14);
 	}
 }
+
+/* ---------------------------------------------------------------------------------------------
+ * detection::NonMaximumSuppression (libDetection/src/detection/NonMaximumSuppression.cpp:27-112)
+ * ------------------------------------------------------------------------------------------- */
+typedef struct { float score; int x, y, w, h; long long order; } nms_box;
+
+static int nms_cmp(const void* a, const void* b) { /* ascending score (:36-38); ties by input order (std::sort leaves them open) */
+	const nms_box* p = (const nms_box*)a; const nms_box* q = (const nms_box*)b;
+	if (p->score < q->score) return -1;
+	if (p->score > q->score) return 1;
+	return p->order < q->order ? -1 : (p->order > q->order ? 1 : 0);
+}
+
+static double nms_overlap(const nms_box* a, const nms_box* b) { /* :60-64 with cv::Rect operator& / area() */
+	int x1 = a->x > b->x ? a->x : b->x, y1 = a->y > b->y ? a->y : b->y;
+	int x2 = a->x + a->w < b->x + b->w ? a->x + a->w : b->x + b->w, y2 = a->y + a->h < b->y + b->h ? a->y + a->h : b->y + b->h;
+	int iw = x2 - x1, ih = y2 - y1;
+	if (iw <= 0 || ih <= 0) { iw = 0; ih = 0; }
+	double intersectionArea = iw * ih;
+	double unionArea = a->w * a->h + b->w * b->h - intersectionArea;
+	return intersectionArea / unionArea;
+}
+
+int64_t fdo_non_maximum_suppression(float* scores, int32_t* rects, int64_t n, double overlap_threshold, int maximum_type) {
+	if (overlap_threshold == 1.0 || n <= 0) return n;                       /* :28-29 */
+	nms_box* cand = (nms_box*)malloc(sizeof(nms_box) * (size_t)n);
+	nms_box* cluster = (nms_box*)malloc(sizeof(nms_box) * (size_t)n);
+	for (int64_t i = 0; i < n; ++i) {
+		cand[i].score = scores[i]; cand[i].x = rects[4 * i]; cand[i].y = rects[4 * i + 1]; cand[i].w = rects[4 * i + 2]; cand[i].h = rects[4 * i + 3];
+		cand[i].order = i;
+	}
+	qsort(cand, (size_t)n, sizeof(nms_box), nms_cmp);                       /* sortByScore */
+	int64_t m = n, out = 0;
+	while (m > 0) {                                                        /* cluster(): :41-46 */
+		const nms_box detection = cand[m - 1];
+		int64_t keep = 0, nc = 0;
+		for (int64_t i = 0; i < m; ++i) {                                   /* stable_partition (:50-52) */
+			if (nms_overlap(&detection, &cand[i]) <= overlap_threshold) cand[keep++] = cand[i];
+			else cluster[nc++] = cand[i];
+		}
+		m = keep;
+		if (nc == 0) break;                                                 /* an empty box never overlaps itself: the reference would loop forever */
+		/* the cluster in reversed (descending score) order (:54): member k is cluster[nc - 1 - k] */
+		nms_box r = cluster[nc - 1];                                        /* MAX_SCORE: cluster.front() */
+		if (maximum_type == 1 || maximum_type == 2) {
+			double weightSum = 0, xSum = 0, ySum = 0, wSum = 0, hSum = 0;
+			for (int64_t k = 0; k < nc; ++k) {
+				const nms_box* e = &cluster[nc - 1 - k];
+				double weight = maximum_type == 1 ? 1.0 : e->score;
+				weightSum += weight;
+				if (maximum_type == 1) { xSum += e->x; ySum += e->y; wSum += e->w; hSum += e->h; }
+				else { xSum += weight * e->x; ySum += weight * e->y; wSum += weight * e->w; hSum += weight * e->h; }
+			}
+			double den = maximum_type == 1 ? (double)nc : weightSum;
+			r.x = (int)round(xSum / den); r.y = (int)round(ySum / den); r.w = (int)round(wSum / den); r.h = (int)round(hSum / den);
+		}
+		scores[out] = r.score; rects[4 * out] = r.x; rects[4 * out + 1] = r.y; rects[4 * out + 2] = r.w; rects[4 * out + 3] = r.h;
+		++out;
+	}
+	free(cand); free(cluster);
+	return out;
+}

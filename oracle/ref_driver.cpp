@@ -41,6 +41,7 @@
 #include "imageprocessing/Patch.hpp"
 #include "detection/ClassifiedPatch.hpp"
 #include "detection/OverlapElimination.hpp"
+#include "detection/NonMaximumSuppression.hpp"
 
 #include "fdb200.h"
 #include "fd_oracle.h"
@@ -196,6 +197,19 @@ int ref_rvm_eval(void* p, const void* x, double* distance, double* probability, 
 	if (probability) *probability = pr.second;
 	if (positive) *positive = pr.first ? 1 : 0;
 	return ld.first;
+}
+
+/* detection::NonMaximumSuppression (the reference's own NonMaximumSuppression.cpp) on n scored boxes, in place */
+int64_t ref_non_maximum_suppression(float* scores, int32_t* rects, int64_t n, double overlap_threshold, int maximum_type) {
+	vector<detection::Detection> c;
+	for (int64_t i = 0; i < n; ++i) c.push_back(detection::Detection{scores[i], cv::Rect(rects[4 * i], rects[4 * i + 1], rects[4 * i + 2], rects[4 * i + 3])});
+	detection::NonMaximumSuppression nms(overlap_threshold, (detection::NonMaximumSuppression::MaximumType)maximum_type);
+	vector<detection::Detection> r = nms.eliminateRedundantDetections(c);
+	for (size_t i = 0; i < r.size(); ++i) {
+		scores[i] = r[i].score;
+		rects[4 * i] = r[i].bounds.x; rects[4 * i + 1] = r[i].bounds.y; rects[4 * i + 2] = r[i].bounds.width; rects[4 * i + 3] = r[i].bounds.height;
+	}
+	return (int64_t)r.size();
 }
 
 void* ref_svm_create(const fdb_svm_desc* d) {

@@ -76,7 +76,15 @@ template<class T> struct Rect_ {
 	Point_<T> tl() const { return Point_<T>(x, y); }
 	Point_<T> br() const { return Point_<T>(x + width, y + height); }
 	Size_<T> size() const { return Size_<T>(width, height); }
+	T area() const { return width * height; }
 };
+/* intersection (OpenCV: operator&= clamps to an empty Rect_() when the rectangles do not overlap) */
+template<class T> inline Rect_<T> operator&(const Rect_<T>& a, const Rect_<T>& b) {
+	const T x1 = a.x > b.x ? a.x : b.x, y1 = a.y > b.y ? a.y : b.y;
+	const T w = (a.x + a.width < b.x + b.width ? a.x + a.width : b.x + b.width) - x1;
+	const T h = (a.y + a.height < b.y + b.height ? a.y + a.height : b.y + b.height) - y1;
+	return (w <= 0 || h <= 0) ? Rect_<T>() : Rect_<T>(x1, y1, w, h);
+}
 typedef Rect_<int> Rect;
 
 template<class T, int N> struct Vec {
