@@ -24,6 +24,8 @@ int main() {
 		std::shared_ptr<fdb200::B200ProbabilisticSvmClassifier> svm = std::make_shared<fdb200::B200ProbabilisticSvmClassifier>(ctx, sd);
 		fdb_rvm_desc rd = fdb_rvm_desc();
 		std::shared_ptr<classification::ProbabilisticClassifier> c3 = std::make_shared<fdb200::B200ProbabilisticRvmClassifier>(ctx, rd);
+		std::shared_ptr<detection::Detector> single1 = std::make_shared<fdb200::B200SingleDetector>(ctx, dd, svm);
+		std::shared_ptr<detection::Detector> single2 = std::make_shared<fdb200::B200SingleDetector>(ctx, dd, std::make_shared<fdb200::B200ProbabilisticRvmClassifier>(ctx, rd));
 		std::shared_ptr<classification::ProbabilisticClassifier> c1 = wvm, c2 = svm;
 		std::shared_ptr<fdb200::B200SlidingWindowDetector> det = std::make_shared<fdb200::B200SlidingWindowDetector>(ctx, dd, wvm, svm);
 		std::shared_ptr<detection::Detector> d = det;

@@ -363,5 +363,57 @@ private:
 	mutable std::vector<uint8_t> patches;
 };
 
+/* detection::Detector replacement for ffpDetectApp's `single` detectors (ffpDetectApp.cpp:427-500): a SlidingWindowDetector
+ * whose classifier is a ProbabilisticSvmClassifier (psvm) or ProbabilisticRvmClassifier (prvm) - every window is classified
+ * (SlidingWindowDetector.cpp:87-98). u8 RBF SVMs on 20x20 patches run on the tensor cores (csrc/svm_dense.cu). */
+class B200SingleDetector : public detection::Detector {
+public:
+	B200SingleDetector(std::shared_ptr<Context> context, const fdb_detector_desc& desc, std::shared_ptr<B200ProbabilisticSvmClassifier> svm) :
+			context(context), svm(svm), handle(nullptr), width(0), height(0) {
+		check(fdb_detector_create(context->get(), &desc, nullptr, svm->get(), &handle));
+	}
+	B200SingleDetector(std::shared_ptr<Context> context, const fdb_detector_desc& desc, std::shared_ptr<B200ProbabilisticRvmClassifier> rvm) :
+			context(context), rvm(rvm), handle(nullptr), width(0), height(0) {
+		check(fdb_detector_create_rvm(context->get(), &desc, rvm->get(), &handle));
+	}
+	~B200SingleDetector() { fdb_detector_destroy(handle); }
+	fdb_detector* get() const { return handle; }
+
+	std::vector<std::shared_ptr<detection::ClassifiedPatch>> detect(const cv::Mat& image) {
+		const cv::Mat gray = grayOf(context->get(), image);
+		if (gray.cols != width || gray.rows != height) {
+			check(fdb_detector_prepare(handle, gray.cols, gray.rows, 1));
+			width = gray.cols; height = gray.rows;
+		}
+		const int64_t cap = fdb_detector_windows_per_frame(handle);
+		std::vector<fdb_detection> dets((size_t)(cap > 0 ? cap : 1));
+		int64_t n = 0;
+		check(fdb_detect_single(handle, gray.ptr<uchar>(0), (int64_t)gray.step, 1, nullptr, &dets[0], (int64_t)dets.size(), &n));
+		std::vector<std::shared_ptr<detection::ClassifiedPatch>> out;
+		for (int64_t i = 0; i < n; ++i) {
+			const fdb_detection& d = dets[(size_t)i];
+			std::shared_ptr<imageprocessing::Patch> patch = std::make_shared<imageprocessing::Patch>(d.center_x, d.center_y, d.width, d.height, cv::Mat());
+			out.push_back(std::make_shared<detection::ClassifiedPatch>(patch, d.positive != 0, d.probability));
+		}
+		return out;
+	}
+	/* the whole-image scan filtered to the windows the ROI loop would visit is not implemented: the apps call the single
+	 * detectors on whole images (ffpDetectApp.cpp:557) */
+	std::vector<std::shared_ptr<detection::ClassifiedPatch>> detect(const cv::Mat& image, const cv::Rect& roi) {
+		if (roi.width != 0 || roi.height != 0) throw std::invalid_argument("fdb200: single detectors scan whole images");
+		return detect(image);
+	}
+	std::vector<std::shared_ptr<detection::ClassifiedPatch>> detect(std::shared_ptr<imageprocessing::VersionedImage> image) {
+		return detect(image->getData());
+	}
+
+private:
+	std::shared_ptr<Context> context;
+	std::shared_ptr<B200ProbabilisticSvmClassifier> svm;
+	std::shared_ptr<B200ProbabilisticRvmClassifier> rvm;
+	fdb_detector* handle;
+	int width, height;
+};
+
 } // namespace fdb200
 #endif
