@@ -42,6 +42,8 @@
 #include "detection/ClassifiedPatch.hpp"
 #include "detection/OverlapElimination.hpp"
 #include "detection/NonMaximumSuppression.hpp"
+#include "imageprocessing/filtering/FhogFilter.hpp"
+#include "imageprocessing/filtering/GradientHistogramFilter.hpp"
 
 #include "fdb200.h"
 #include "fd_oracle.h"
@@ -197,6 +199,25 @@ int ref_rvm_eval(void* p, const void* x, double* distance, double* probability, 
 	if (probability) *probability = pr.second;
 	if (positive) *positive = pr.first ? 1 : 0;
 	return ld.first;
+}
+
+/* drawing helper referenced by FhogAggregationFilter::visualizeUnsignedHistograms only (GradientHistogramFilter.cpp needs
+ * OpenCV's drawing API and is not compiled): never called by the oracle */
+cv::Mat imageprocessing::filtering::GradientHistogramFilter::visualizeUnsignedHistograms(const cv::Mat&, int, int, int) {
+	throw std::runtime_error("visualizeUnsignedHistograms is not part of the oracle");
+}
+
+/* imageprocessing::filtering::FhogFilter::applyTo (the reference's own FhogFilter.cpp / FhogAggregationFilter.cpp) */
+int64_t ref_fhog(const uint8_t* image, int cols, int rows, int channels, int cell, int unsigned_bins, int interpolate_bins,
+		int interpolate_cells, float alpha, float* out) {
+	Mat img(rows, cols, CV_MAKETYPE(CV_8U, channels));
+	std::memcpy(img.data, image, (size_t)rows * cols * channels);
+	imageprocessing::filtering::FhogFilter filter(cell, unsigned_bins, interpolate_bins != 0, interpolate_cells != 0, alpha);
+	Mat desc;
+	filter.applyTo(img, desc);
+	const size_t n = (size_t)desc.rows * desc.cols * desc.channels();
+	std::memcpy(out, desc.data, sizeof(float) * n);
+	return (int64_t)n;
 }
 
 /* detection::NonMaximumSuppression (the reference's own NonMaximumSuppression.cpp) on n scored boxes, in place */

@@ -86,6 +86,9 @@ template<class T> inline Rect_<T> operator&(const Rect_<T>& a, const Rect_<T>& b
 	return (w <= 0 || h <= 0) ? Rect_<T>() : Rect_<T>(x1, y1, w, h);
 }
 typedef Rect_<int> Rect;
+#ifndef CV_32FC2
+#define CV_32FC2 CV_MAKETYPE(CV_32F, 2)
+#endif
 
 template<class T, int N> struct Vec {
 	T val[N];
@@ -241,6 +244,9 @@ inline void sqrt(const Mat& src, Mat& dst) {
 	const int n = a.cols * a.channels();
 	for (int y = 0; y < a.rows; ++y) for (int i = 0; i < n; ++i) dst.ptr<float>(y)[i] = std::sqrt(a.ptr<float>(y)[i]);
 }
+
+/* only referenced by code paths the oracle never runs (GradientOrientationFilter::extractMagnitude) */
+inline void mixChannels(const std::vector<Mat>&, std::vector<Mat>, const std::vector<int>&) { throw std::runtime_error("shim: cv::mixChannels is not available"); }
 
 } // namespace cv
 

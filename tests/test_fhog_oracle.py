@@ -1,0 +1,58 @@
+"""Groundwork for SURVEY 8(f) rank 2: the FHOG layer filter of AggregatedFeaturesDetector's feature pyramid. The C
+restatement (oracle/fd_fhog.c) against the reference's own FhogFilter / FhogAggregationFilter compiled into oracle/_ref -
+bit for bit (float32, the reference's order of operations). No product kernel exists yet for this row."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from featuredetection_b200 import synthetic as syn
+
+ARGS = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p]
+
+
+def _fhog(fn, img, cell, bins, ib, ic, alpha):
+    img = np.ascontiguousarray(img, np.uint8)
+    rows, cols = img.shape[:2]
+    ch = 1 if img.ndim == 2 else img.shape[2]
+    D = 3 * bins + 4
+    out = np.full((rows // cell, cols // cell, D), np.nan, np.float32)
+    n = fn(img.ctypes.data, cols, rows, ch, cell, bins, int(ib), int(ic), alpha, out.ctypes.data)
+    assert n == out.size
+    return out
+
+
+@pytest.mark.parametrize("cell,bins,ib,ic,alpha", [(4, 9, True, True, 0.2), (8, 9, False, True, 0.2), (4, 6, True, False, 0.2),
+                                                   (5, 9, False, False, 0.5), (6, 8, True, True, 1.0)])
+def test_fhog_restatement_equals_the_compiled_reference(built, cell, bins, ib, ic, alpha):
+    from oracle import fdoracle as fo
+    if not fo.ref_available():
+        pytest.skip("oracle/_ref not built (no /root/reference)")
+    L, R = fo.lib(), fo.ref()
+    L.fdo_fhog.restype = C.c_int64; L.fdo_fhog.argtypes = ARGS
+    R.ref_fhog.restype = C.c_int64; R.ref_fhog.argtypes = ARGS
+    gray = syn.synthetic_frame(3)[:131, :203]                       # sizes that are not multiples of the cell
+    rng = np.random.default_rng(1)
+    bgr = np.stack([gray, np.roll(gray, 3, 1), rng.integers(0, 256, gray.shape, dtype=np.uint8)], axis=2)
+    flat = np.full((40, 48), 77, np.uint8)                           # zero gradients: the eps of the normalisers decides
+    for img in (gray, bgr, flat, gray[:cell, :cell * 2]):
+        a = _fhog(L.fdo_fhog, img, cell, bins, ib, ic, alpha)
+        b = _fhog(R.ref_fhog, img, cell, bins, ib, ic, alpha)
+        assert a.shape == b.shape and np.array_equal(a, b), float(np.nanmax(np.abs(a - b)))
+        assert np.isfinite(a).all() and a.min() >= 0 and a[..., :3 * bins].max() <= 2 * alpha + 1e-6
+
+
+def test_fhog_properties(built):
+    from oracle import fdoracle as fo
+    L = fo.lib()
+    L.fdo_fhog.restype = C.c_int64; L.fdo_fhog.argtypes = ARGS
+    img = syn.synthetic_frame(1)[:64, :96]
+    d = _fhog(L.fdo_fhog, img, 4, 9, True, True, 0.2)
+    assert d.shape == (16, 24, 31)
+    # contrast-insensitive bins are bounded by the clamp: 0.5 * 4 * alpha
+    assert d[..., 18:27].max() <= 0.4 + 1e-6
+    # inverting the image flips every gradient: signed bins rotate by half a turn, unsigned bins and energies stay
+    e = _fhog(L.fdo_fhog, 255 - img, 4, 9, True, True, 0.2)
+    assert np.allclose(e[..., 18:], d[..., 18:], atol=1e-5)
+    assert np.allclose(e[..., :9], d[..., 9:18], atol=2e-4) and np.allclose(e[..., 9:18], d[..., :9], atol=2e-4)
+    assert L.fdo_fhog(img.ctypes.data, 96, 64, 2, 4, 9, 1, 1, 0.2, d.ctypes.data) == -1
