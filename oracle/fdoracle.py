@@ -688,3 +688,94 @@ def evaluate_samples(det_kwargs, wvm, svm, frame, samples_xywh, max_svm_patches=
                 target[i] = res[sample_key[i]][0]
                 weight[i] = 2 * weight[i] * res[sample_key[i]][1]
     return target, weight
+
+
+def fhog(image, cell=4, unsigned_bins=9, interpolate_bins=False, interpolate_cells=True, alpha=0.2, use_ref=False):
+    """FhogFilter::applyTo (filtering/FhogFilter.cpp:59-67): u8 image [H, W] or [H, W, 3] -> float32 [H // cell, W // cell,
+    3 * unsigned_bins + 4]. use_ref: the reference's own classes (oracle/_ref)."""
+    img = np.ascontiguousarray(image, np.uint8)
+    rows, cols = img.shape[:2]
+    ch = 1 if img.ndim == 2 else img.shape[2]
+    args = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p]
+    if use_ref:
+        fn = ref().ref_fhog
+    else:
+        fn = lib().fdo_fhog
+    fn.restype = C.c_int64; fn.argtypes = args
+    out = np.zeros((rows // cell, cols // cell, 3 * unsigned_bins + 4), np.float32)
+    n = fn(img.ctypes.data, cols, rows, ch, cell, unsigned_bins, int(interpolate_bins), int(interpolate_cells), alpha, out.ctypes.data)
+    if n != out.size:
+        raise ValueError("fhog: invalid arguments")
+    return out
+
+
+def aggregated_features_detect(frame, weights, bias, threshold, cell=4, octave_layer_count=5, min_window_width=0,
+                               nms_threshold=0.3, nms_type=0, width_scale=1.0, height_scale=1.0, unsigned_bins=9,
+                               interpolate_bins=False, interpolate_cells=True, alpha=0.2, want_scores=False):
+    """detection::AggregatedFeaturesDetector::detectWithScores on a gray frame (SURVEY 8(f) rank 2), restated for the next
+    round's kernels - no product code exists for it yet:
+      AggregatedFeaturesExtractor ctor / update / getMinScaleFactor / getMaxScaleFactor / computeBoundsInImagePixels
+                                                             extraction/AggregatedFeaturesExtractor.cpp:22-131
+      ImagePyramid(size_t, double, double), createLayers(Mat)  ImagePyramid.cpp:60-76,170-198 (fdo_pyramid_build)
+      FhogFilter as the layer filter                           filtering/FhogFilter.cpp (fdo_fhog)
+      ConvolutionFilter::applyTo as the score layer filter     ConvolutionFilter.cpp:31-49: -bias + sum_c filter2D(channel_c, w_c),
+                                                               correlation, anchor (0, 0), zero border
+      getPositiveWindows / rescaleWindow                       AggregatedFeaturesDetector.cpp:92-118
+      NonMaximumSuppression                                    NonMaximumSuppression.cpp:27-112 (fdo_non_maximum_suppression)
+    weights [kh, kw, D] float32 = the support vector of the linear SVM. The score map is float32; cv::filter2D's own summation
+    order (and its DFT path for kernels of >= 50 elements) is OpenCV's: UNPINNED, compare at 1e-4.
+    Returns (rects [n, 4] int32 x y w h, scores [n] float32) after suppression (+ the per-layer score maps)."""
+    import math
+    frame = np.ascontiguousarray(frame, np.uint8)
+    H, W = frame.shape
+    weights = np.ascontiguousarray(weights, np.float32)
+    kh, kw, D = weights.shape
+    inc = math.pow(0.5, 1.0 / octave_layer_count)                      # ImagePyramid.cpp:75
+    patch_w, patch_h = kw * cell, kh * cell                            # patchSizeInPixels
+    max_scale = 1.0
+    if min_window_width > patch_w:                                     # AggregatedFeaturesExtractor.cpp:30-31,46-51
+        ms = float(patch_w) / min_window_width
+        max_scale = math.pow(inc, int(math.ceil(math.log(ms) / math.log(inc))))
+    aspect, image_aspect = float(patch_h) / float(patch_w), float(H) / float(W)   # getMaxWidth, :66-73
+    max_width = int(H / aspect) if aspect > image_aspect else W
+    mn = float(patch_w) / max_width                                    # getMinScaleFactor, :60-64
+    min_scale = math.pow(inc, int(math.log(mn) / math.log(inc)))
+    _, layers = pyramid(frame, inc, min_scale, max_scale)
+    scores_list, rects_list, maps = [], [], []
+    for index, scale, img in layers:
+        feat = fhog(img, cell, unsigned_bins, interpolate_bins, interpolate_cells, alpha)
+        rows, cols = feat.shape[:2]
+        vh, vw = rows - kh + 1, cols - kw + 1                          # AggregatedFeaturesDetector.cpp:95-96
+        if vh <= 0 or vw <= 0:
+            maps.append(np.zeros((max(vh, 0), max(vw, 0)), np.float32))
+            continue
+        score = np.full((vh, vw), np.float32(-bias), np.float32)       # filtered = delta
+        for c in range(D):                                             # filtered += filter2D(channel_c, w_c)
+            tmp = np.zeros((vh, vw), np.float32)
+            for i in range(kh):
+                for j in range(kw):
+                    tmp += feat[i:i + vh, j:j + vw, c] * weights[i, j, c]
+            score += tmp
+        maps.append(score)
+        scale_x, scale_y = float(img.shape[1]) / float(W), float(img.shape[0]) / float(H)   # ImagePyramid.cpp:178-179,187-188
+        ys, xs = np.nonzero(score > np.float32(threshold))
+        for y, x in zip(ys.tolist(), xs.tolist()):
+            # computeBoundsInImagePixels (:121-128): std::round = half away from zero
+            def rnd(v):
+                return int(math.floor(abs(v) + 0.5)) * (1 if v >= 0 else -1)
+            bx, by = rnd((x * cell) / scale_x), rnd((y * cell) / scale_y)
+            bw, bh = rnd((kw * cell) / scale_x), rnd((kh * cell) / scale_y)
+            cx, cy = bx + bw // 2, by + bh // 2                        # Patch::computeCenter (non-negative sizes)
+            rw, rh = int(np.float32(width_scale) * np.float32(bw)), int(np.float32(height_scale) * np.float32(bh))   # Size(float, float) -> int
+            rects_list.append((cx - rw // 2, cy - rh // 2, rw, rh))     # Patch::computeBounds
+            scores_list.append(score[y, x])
+    scores = np.array(scores_list, np.float32)
+    rects = np.array(rects_list, np.int32).reshape(-1, 4)
+    if len(scores):
+        L = lib()
+        L.fdo_non_maximum_suppression.restype = C.c_int64
+        L.fdo_non_maximum_suppression.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_double, C.c_int]
+        rects = np.ascontiguousarray(rects)
+        n = L.fdo_non_maximum_suppression(scores.ctypes.data, rects.ctypes.data, len(scores), nms_threshold, nms_type)
+        scores, rects = scores[:n].copy(), rects[:n].copy()
+    return (rects, scores, maps) if want_scores else (rects, scores)

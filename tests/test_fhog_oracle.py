@@ -56,3 +56,30 @@ def test_fhog_properties(built):
     assert np.allclose(e[..., 18:], d[..., 18:], atol=1e-5)
     assert np.allclose(e[..., :9], d[..., 9:18], atol=2e-4) and np.allclose(e[..., 9:18], d[..., :9], atol=2e-4)
     assert L.fdo_fhog(img.ctypes.data, 96, 64, 2, 4, 9, 1, 1, 0.2, d.ctypes.data) == -1
+
+
+def test_aggregated_features_detector_restatement_finds_a_planted_template(built):
+    """the whole rank-2 chain of the oracle (pyramid -> FHOG -> linear-SVM score map -> threshold -> bounds -> IoU NMS): a
+    template cut out of a frame's own FHOG map must be found where it was cut, at the scale it was cut from"""
+    from oracle import fdoracle as fo
+    frame = syn.synthetic_frame(4)[:240, :320].copy()
+    rng = np.random.default_rng(2)
+    frame[60:140, 100:180] = rng.integers(0, 256, (80, 80), dtype=np.uint8)      # a textured 80x80 object
+    cell, kh, kw = 4, 10, 10                                                       # 40x40 px window at scale 1
+    inc = 0.5 ** (1.0 / 5)
+    _, layers = fo.pyramid(frame, inc, 0.5, 1.0)
+    idx5 = [l for l in layers if l[0] == 5][0]                                     # scale 0.5: the object is 40x40 px there
+    feat = fo.fhog(idx5[2], cell)
+    y0, x0 = 30 // cell, 50 // cell
+    w = feat[y0:y0 + kh, x0:x0 + kw].copy()
+    w -= w.mean()
+    self_score = float((feat[y0:y0 + kh, x0:x0 + kw] * w).sum())
+    rects, scores, maps = fo.aggregated_features_detect(frame, w, bias=0.0, threshold=0.8 * self_score, cell=cell, octave_layer_count=5,
+                                                        nms_threshold=0.3, want_scores=True)
+    assert len(rects) >= 1 and scores[0] >= 0.99 * self_score * 0.8
+    x, y, bw, bh = rects[0]
+    assert abs(x - 2 * x0 * cell) <= 8 and abs(y - 2 * y0 * cell) <= 8 and abs(bw - 80) <= 2 and abs(bh - 80) <= 2
+    assert np.all(np.diff(scores) <= 0)
+    # min_window_width removes the layers whose windows would be smaller
+    r2, s2 = fo.aggregated_features_detect(frame, w, bias=0.0, threshold=0.8 * self_score, cell=cell, octave_layer_count=5, min_window_width=100)
+    assert all(r[2] >= 80 for r in r2)
