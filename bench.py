@@ -346,7 +346,27 @@ class ClockSampler:
     def __init__(self, index):
         self.index, self.samples, self.stop_flag, self.thread = index, [], False, None
 
+    def _loop_nvml(self):
+        """NVML polls in well under a millisecond, so even a 40 ms timed region gets several samples; any failure
+        (module missing, driver call refused) drops back to the nvidia-smi loop"""
+        import pynvml as nv
+        nv.nvmlInit()
+        h = nv.nvmlDeviceGetHandleByIndex(self.index)
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        bits = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
+        mx = str(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+        while not self.stop_flag:
+            sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+            r = int(get_reasons(h))
+            self.samples.append([str(sm), mx] + ["Active" if r & b else "Not Active" for _, b in bits])
+            time.sleep(0.005)
+
     def _loop(self):
+        try:
+            self._loop_nvml()
+            return
+        except Exception:
+            pass
         while not self.stop_flag:
             try:
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
