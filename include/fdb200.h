@@ -495,6 +495,14 @@ FDB_API int fdb_detector_single_dense(fdb_detector* det);
  * and the number of launches (one per chunk of frames): the roofline numerator of bench.py --workload single-psvm */
 FDB_API int fdb_detector_single_dense_profile(fdb_detector* det, double* kernel_ms, int32_t* launches);
 
+/* imageprocessing::filtering::FhogFilter::applyTo (libImageProcessing/src/imageprocessing/filtering/FhogFilter.cpp:59-67 with
+ * FhogAggregationFilter.cpp:43-150): the FHOG feature map of one 8-bit image (1 or 3 interleaved channels), the layer filter
+ * of detection::AggregatedFeaturesDetector's feature pyramid. out_host: (height / cell_size) x
+ * (width / cell_size) x (3 * unsigned_bins + 4) float32. EXPERIMENTAL in this round: the arithmetic is verified on the host
+ * against the pinned oracle, the kernels have not run on a B200 yet (see csrc/fhog.cu). */
+FDB_API int fdb_fhog(fdb_ctx* ctx, const uint8_t* image_host, int64_t pitch, int32_t width, int32_t height, int32_t channels,
+		int32_t cell_size, int32_t unsigned_bins, int32_t interpolate_bins, int32_t interpolate_cells, float alpha, float* out_host);
+
 /* The per-frame flow of ffpDetectApp (ffpDetectApp.cpp:553-596): the face detector on the whole frame, then every feature
  * detector restricted to the bounds of the FIRST (most probable) face patch - Patch::getBounds() = {x - w / 2, y - h / 2, w, h}
  * - through Detector::detect(img, roi). face_out receives the face detections; feature_out has feature_cap_each slots per

@@ -10,6 +10,7 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu on the GPU box)")
+    config.addinivalue_line("markers", "gpu_unverified: GPU tests of code that has not run on a B200 yet (FDB_RUN_UNVERIFIED=1 on a GPU box)")
 
 
 @pytest.fixture(scope="session")
