@@ -83,6 +83,16 @@ void fhog_build_lut(int unsigned_bins, int interpolate_bins, std::vector<FhogLut
 	}
 }
 
+/* thread = score-map position; weights are read through the read-only path (the same address across a warp's lanes) */
+__global__ void __launch_bounds__(128) aggdet_score_kernel(const float* __restrict__ feat, int rows, int cols, int D,
+		const float* __restrict__ weights, int kh, int kw, float bias, float* __restrict__ scores /* [rows - kh + 1][cols - kw + 1] */) {
+	const int vw = cols - kw + 1, vh = rows - kh + 1;
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= vw * vh) return;
+	const int y = i / vw, x = i - y * vw;
+	scores[i] = aggdet_score(feat, cols, D, weights, kh, kw, bias, y, x);
+}
+
 } // namespace fdb
 
 using namespace fdb;
@@ -124,5 +134,35 @@ extern "C" int fdb_fhog(fdb_ctx* ctx, const uint8_t* image_host, int64_t pitch, 
 	if (e == cudaSuccess) e = cudaStreamSynchronize(st);
 	free_all(tmp);
 	if (e != cudaSuccess) return fail(FDB_ERR_CUDA, std::string("fdb_fhog: ") + cudaGetErrorString(e));
+	return FDB_OK;
+}
+
+/* FHOG + linear-SVM score map of ONE pyramid layer (see fdb200.h) */
+extern "C" int fdb_fhog_score_map(fdb_ctx* ctx, const uint8_t* image_host, int64_t pitch, int32_t width, int32_t height, int32_t channels,
+		int32_t cell_size, int32_t unsigned_bins, int32_t interpolate_bins, int32_t interpolate_cells, float alpha,
+		const float* weights_host, int32_t kernel_rows, int32_t kernel_cols, float bias, float* scores_host) {
+	int s = check_ctx(ctx); if (s) return s;
+	if (!weights_host || !scores_host || kernel_rows < 1 || kernel_cols < 1) return fail(FDB_ERR_INVALID_ARGUMENT, "bad kernel");
+	if (cell_size < 1 || width < 1 || height < 1) return fail(FDB_ERR_INVALID_ARGUMENT, "bad image geometry");
+	const int crow = height / cell_size, ccol = width / cell_size, D = 3 * unsigned_bins + 4;
+	const int vh = crow - kernel_rows + 1, vw = ccol - kernel_cols + 1;
+	if (vh <= 0 || vw <= 0) return FDB_OK; /* no window fits this layer */
+	std::vector<float> feat((size_t)crow * ccol * D);
+	s = fdb_fhog(ctx, image_host, pitch, width, height, channels, cell_size, unsigned_bins, interpolate_bins, interpolate_cells, alpha, feat.data());
+	if (s) return s;
+	std::vector<void*> tmp;
+	float* d_feat; float* d_w; float* d_scores;
+	s = upload(feat.data(), feat.size(), &d_feat, tmp);
+	if (!s) s = upload(weights_host, (size_t)kernel_rows * kernel_cols * D, &d_w, tmp);
+	if (!s) s = dev_alloc(&d_scores, (size_t)vh * vw, tmp);
+	if (s) { free_all(tmp); return s; }
+	cudaStream_t st = ctx->stream;
+	aggdet_score_kernel<<<(unsigned)((vh * vw + 127) / 128), 128, 0, st>>>(d_feat, crow, ccol, D, d_w, kernel_rows, kernel_cols, bias, d_scores);
+	ctx->launches++;
+	cudaError_t e = cudaGetLastError();
+	if (e == cudaSuccess) e = cudaMemcpyAsync(scores_host, d_scores, sizeof(float) * (size_t)vh * vw, cudaMemcpyDeviceToHost, st);
+	if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+	free_all(tmp);
+	if (e != cudaSuccess) return fail(FDB_ERR_CUDA, std::string("fdb_fhog_score_map: ") + cudaGetErrorString(e));
 	return FDB_OK;
 }

@@ -170,4 +170,22 @@ FHOG_HD void fhog_descriptor(const float* hist, const float* energies, int crow,
 	out[signed_bins + unsigned_bins + 3] = (float)FHOG_DMUL(0.2357, (double)e3);
 }
 
+/* ConvolutionFilter::applyTo as AggregatedFeaturesDetector configures it (ConvolutionFilter.cpp:31-49,
+ * AggregatedFeaturesDetector.cpp:60-65): score(y, x) = -bias + sum over channels of the correlation of channel c with the
+ * kernel's channel c, anchor (0, 0). feat: [rows][cols][D] float32, weights: [kh][kw][D]. The order of the float32 sums is
+ * channel by channel, then kernel rows, then kernel columns (the order of the oracle's restatement; OpenCV's own order inside
+ * cv::filter2D is not reproducible - it uses a DFT for kernels of >= 50 elements - so parity with the reference is 1e-4). Only
+ * positions with the whole window inside the layer are scored (AggregatedFeaturesDetector.cpp:95-98). */
+FHOG_HD float aggdet_score(const float* feat, int cols, int D, const float* weights, int kh, int kw, float bias, int y, int x) {
+	float score = -bias;
+	for (int c = 0; c < D; ++c) {
+		float tmp = 0.f;
+		for (int i = 0; i < kh; ++i)
+			for (int j = 0; j < kw; ++j)
+				tmp = FHOG_ADD(tmp, FHOG_MUL(feat[((size_t)(y + i) * cols + (x + j)) * D + c], weights[((size_t)i * kw + j) * D + c]));
+		score = FHOG_ADD(score, tmp);
+	}
+	return score;
+}
+
 #endif

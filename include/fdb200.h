@@ -503,6 +503,15 @@ FDB_API int fdb_detector_single_dense_profile(fdb_detector* det, double* kernel_
 FDB_API int fdb_fhog(fdb_ctx* ctx, const uint8_t* image_host, int64_t pitch, int32_t width, int32_t height, int32_t channels,
 		int32_t cell_size, int32_t unsigned_bins, int32_t interpolate_bins, int32_t interpolate_cells, float alpha, float* out_host);
 
+/* The score map AggregatedFeaturesDetector computes for one pyramid layer (AggregatedFeaturesDetector.cpp:60-65,92-98;
+ * ConvolutionFilter.cpp:31-49): FHOG of the layer image, then -bias + the correlation with the linear SVM's support vector
+ * weights_host [kernel_rows][kernel_cols][3 * unsigned_bins + 4]. scores_host: (cells_y - kernel_rows + 1) x (cells_x -
+ * kernel_cols + 1) float32 (nothing is written when no window fits). EXPERIMENTAL like fdb_fhog: host-verified arithmetic,
+ * kernels not yet run on a B200; parity with cv::filter2D's own summation order is 1e-4 by design. */
+FDB_API int fdb_fhog_score_map(fdb_ctx* ctx, const uint8_t* image_host, int64_t pitch, int32_t width, int32_t height, int32_t channels,
+		int32_t cell_size, int32_t unsigned_bins, int32_t interpolate_bins, int32_t interpolate_cells, float alpha,
+		const float* weights_host, int32_t kernel_rows, int32_t kernel_cols, float bias, float* scores_host);
+
 /* The per-frame flow of ffpDetectApp (ffpDetectApp.cpp:553-596): the face detector on the whole frame, then every feature
  * detector restricted to the bounds of the FIRST (most probable) face patch - Patch::getBounds() = {x - w / 2, y - h / 2, w, h}
  * - through Detector::detect(img, roi). face_out receives the face detections; feature_out has feature_cap_each slots per

@@ -65,6 +65,11 @@ extern "C" long long emulate_fhog(const unsigned char* image, int cols, int rows
 		fhog_descriptor(&hist[(size_t)i * signed_bins], energies.data(), crow, ccol, i / ccol, i % ccol, unsigned_bins, alpha, out + (size_t)i * D);
 	return (long long)crow * ccol * D;
 }
+
+extern "C" void emulate_score_map(const float* feat, int rows, int cols, int D, const float* weights, int kh, int kw, float bias, float* scores) {
+	const int vh = rows - kh + 1, vw = cols - kw + 1;
+	for (int i = 0; i < vh * vw; ++i) scores[i] = aggdet_score(feat, cols, D, weights, kh, kw, bias, i / vw, i % vw); /* aggdet_score_kernel */
+}
 '''
 
 ARGS = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p]
@@ -82,6 +87,8 @@ def emu(tmp_path_factory, built):
     lib = C.CDLL(str(so))
     lib.emulate_fhog.restype = C.c_longlong
     lib.emulate_fhog.argtypes = ARGS
+    lib.emulate_score_map.restype = None
+    lib.emulate_score_map.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_void_p]
     return lib
 
 
@@ -104,6 +111,33 @@ def test_kernel_arithmetic_equals_the_pinned_oracle(emu, cell, bins, ib, ic, alp
         assert np.array_equal(got, want), (img.shape, float(np.nanmax(np.abs(got - want))))
 
 
+def test_score_map_arithmetic_equals_the_oracle_restatement(emu):
+    """aggdet_score (thread = score-map position) against the score maps of oracle/fdoracle.py:aggregated_features_detect"""
+    from oracle import fdoracle as fo
+    frame = np.ascontiguousarray(syn.synthetic_frame(6)[:160, :200])
+    rng = np.random.default_rng(4)
+    w = rng.normal(0, 0.1, (5, 6, 31)).astype(np.float32)
+    rects, scores, maps = fo.aggregated_features_detect(frame, w, bias=0.25, threshold=1e9, cell=4, octave_layer_count=3, want_scores=True)
+    inc = 0.5 ** (1.0 / 3)
+    checked = 0
+    # the same layers the restatement used (its scale limits are recomputed here through its own public pieces)
+    mn = (6 * 4) / float(int(160 / ((5 * 4) / (6 * 4.0))) if (5 * 4) / (6 * 4.0) > 160 / 200.0 else 200)
+    import math
+    min_scale = math.pow(inc, int(math.log(mn) / math.log(inc)))
+    _, layers = fo.pyramid(frame, inc, min_scale, 1.0)
+    assert len(layers) == len(maps)
+    for (_, _, img), want in zip(layers, maps):
+        feat = fo.fhog(img, 4)
+        rows, cols, D = feat.shape
+        if want.size == 0:
+            continue
+        got = np.full_like(want, np.nan)
+        emu.emulate_score_map(feat.ctypes.data, rows, cols, D, w.ctypes.data, 5, 6, 0.25, got.ctypes.data)
+        assert np.array_equal(got, want), float(np.nanmax(np.abs(got - want)))
+        checked += 1
+    assert checked >= 3
+
+
 @pytest.mark.gpu_unverified
 @pytest.mark.skipif(os.environ.get("FDB_RUN_UNVERIFIED") != "1", reason="fhog.cu has not run on a B200 yet: set FDB_RUN_UNVERIFIED=1 on a GPU box")
 @pytest.mark.parametrize("cell,bins,ib,ic,alpha", [(4, 9, True, True, 0.2), (8, 9, False, False, 0.2)])
@@ -122,3 +156,31 @@ def test_fdb_fhog_on_the_gpu(cell, bins, ib, ic, alpha):
         got = np.full_like(want, np.nan)
         capi.check(ctx.lib, ctx.lib.fdb_fhog(ctx.h, img.ctypes.data, cols * ch, cols, rows, ch, cell, bins, int(ib), int(ic), alpha, got.ctypes.data))
         assert np.array_equal(got, want)
+
+
+@pytest.mark.gpu_unverified
+@pytest.mark.skipif(os.environ.get("FDB_RUN_UNVERIFIED") != "1", reason="fhog.cu has not run on a B200 yet: set FDB_RUN_UNVERIFIED=1 on a GPU box")
+def test_fdb_fhog_score_map_on_the_gpu():
+    from oracle import fdoracle as fo
+    from featuredetection_b200 import capi
+    from featuredetection_b200.detector import Context
+    ctx = Context(0)
+    img = np.ascontiguousarray(syn.synthetic_frame(6)[:160, :200])
+    rng = np.random.default_rng(4)
+    w = rng.normal(0, 0.1, (5, 6, 31)).astype(np.float32)
+    feat = fo.fhog(img, 4)
+    rows, cols, D = feat.shape
+    want = np.zeros((rows - 4, cols - 5), np.float32)
+    for y in range(want.shape[0]):
+        for x in range(want.shape[1]):
+            s = np.float32(-0.25)
+            for c in range(D):
+                t = np.float32(0)
+                for i in range(5):
+                    for j in range(6):
+                        t = np.float32(t + np.float32(feat[y + i, x + j, c] * w[i, j, c]))
+                s = np.float32(s + t)
+            want[y, x] = s
+    got = np.full_like(want, np.nan)
+    capi.check(ctx.lib, ctx.lib.fdb_fhog_score_map(ctx.h, img.ctypes.data, 200, 200, 160, 1, 4, 9, 0, 1, 0.2, w.ctypes.data, 5, 6, 0.25, got.ctypes.data))
+    assert np.array_equal(got, want)
