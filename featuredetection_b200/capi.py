@@ -190,6 +190,8 @@ SYMBOLS = [
                           C.c_float, C.c_void_p]),
     ("fdb_fhog_score_map", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                     C.c_float, C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.c_void_p]),
+    ("fdb_aggdet_windows", C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_float,
+                                    C.c_float, C.c_void_p, C.c_void_p, C.c_int64, _P(C.c_int64)]),
     ("fdb_evaluate_samples", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]),
     ("fdb_detect_single_device", C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, _P(C.c_int64)]),
     ("fdb_detector_single_dense", C.c_int, [C.c_void_p]),

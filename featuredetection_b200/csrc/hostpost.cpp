@@ -191,3 +191,37 @@ extern "C" int fdb_non_maximum_suppression(float* scores, int32_t* rects_xywh, i
 	return FDB_OK;
 }
 
+/* AggregatedFeaturesDetector::getPositiveWindows for one layer (AggregatedFeaturesDetector.cpp:92-118) with
+ * AggregatedFeaturesExtractor::computeBoundsInImagePixels (AggregatedFeaturesExtractor.cpp:121-128) and rescaleWindow:
+ * every score-map position above the threshold becomes a box in image pixels. scale_x / scale_y = layer size / image size
+ * (ImagePyramid.cpp:178-179,187-188). Appends to scores_out / rects_out (capacity cap); *n_out = number found (may exceed cap:
+ * nothing past cap is written). Host only. */
+extern "C" int fdb_aggdet_windows(const float* score_map, int32_t valid_rows, int32_t valid_cols, float threshold, int32_t kernel_rows,
+		int32_t kernel_cols, int32_t cell_size, double scale_x, double scale_y, float width_scale, float height_scale,
+		float* scores_out, int32_t* rects_xywh_out, int64_t cap, int64_t* n_out) {
+	using fdb::fail;
+	if (!n_out || valid_rows < 0 || valid_cols < 0 || (valid_rows > 0 && valid_cols > 0 && !score_map) || cap < 0
+			|| (cap > 0 && (!scores_out || !rects_xywh_out)))
+		return fail(FDB_ERR_INVALID_ARGUMENT, "bad score map");
+	if (kernel_rows < 1 || kernel_cols < 1 || cell_size < 1 || !(scale_x > 0) || !(scale_y > 0)) return fail(FDB_ERR_INVALID_ARGUMENT, "bad geometry");
+	int64_t n = 0;
+	for (int y = 0; y < valid_rows; ++y)
+		for (int x = 0; x < valid_cols; ++x) {
+			const float score = score_map[(size_t)y * valid_cols + x];
+			if (!(score > threshold)) continue;
+			if (n < cap) {
+				/* bounds in layer cells (x, y, kernel) -> image pixels: round(value * cellSize / scale), half away from zero */
+				const int bx = (int)std::round((double)(x * cell_size) / scale_x), by = (int)std::round((double)(y * cell_size) / scale_y);
+				const int bw = (int)std::round((double)(kernel_cols * cell_size) / scale_x), bh = (int)std::round((double)(kernel_rows * cell_size) / scale_y);
+				const int cx = bx + bw / 2, cy = by + bh / 2;                       /* Patch::computeCenter */
+				const int rw = (int)(width_scale * bw), rh = (int)(height_scale * bh); /* Size(float, float) -> Size_<int> truncates */
+				scores_out[n] = score;
+				rects_xywh_out[4 * n] = cx - rw / 2; rects_xywh_out[4 * n + 1] = cy - rh / 2; /* Patch::computeBounds */
+				rects_xywh_out[4 * n + 2] = rw; rects_xywh_out[4 * n + 3] = rh;
+			}
+			++n;
+		}
+	*n_out = n;
+	return FDB_OK;
+}
+

@@ -512,6 +512,14 @@ FDB_API int fdb_fhog_score_map(fdb_ctx* ctx, const uint8_t* image_host, int64_t 
 		int32_t cell_size, int32_t unsigned_bins, int32_t interpolate_bins, int32_t interpolate_cells, float alpha,
 		const float* weights_host, int32_t kernel_rows, int32_t kernel_cols, float bias, float* scores_host);
 
+/* AggregatedFeaturesDetector::getPositiveWindows for ONE layer's score map (AggregatedFeaturesDetector.cpp:92-118;
+ * bounds: AggregatedFeaturesExtractor.cpp:121-128; rescaleWindow :114-118): positions with score > threshold become boxes in
+ * image pixels. scale_x / scale_y = layer size / image size. *n_out may exceed cap (only cap entries are written). Host only;
+ * feed the boxes of all layers to fdb_non_maximum_suppression. */
+FDB_API int fdb_aggdet_windows(const float* score_map, int32_t valid_rows, int32_t valid_cols, float threshold, int32_t kernel_rows,
+		int32_t kernel_cols, int32_t cell_size, double scale_x, double scale_y, float width_scale, float height_scale,
+		float* scores_out, int32_t* rects_xywh_out, int64_t cap, int64_t* n_out);
+
 /* The per-frame flow of ffpDetectApp (ffpDetectApp.cpp:553-596): the face detector on the whole frame, then every feature
  * detector restricted to the bounds of the FIRST (most probable) face patch - Patch::getBounds() = {x - w / 2, y - h / 2, w, h}
  * - through Detector::detect(img, roi). face_out receives the face detections; feature_out has feature_cap_each slots per

@@ -83,3 +83,40 @@ def test_aggregated_features_detector_restatement_finds_a_planted_template(built
     # min_window_width removes the layers whose windows would be smaller
     r2, s2 = fo.aggregated_features_detect(frame, w, bias=0.0, threshold=0.8 * self_score, cell=cell, octave_layer_count=5, min_window_width=100)
     assert all(r[2] >= 80 for r in r2)
+
+
+def test_host_chain_of_the_library_matches_the_restatement(built):
+    """the host-only product pieces of rank 2 - fdb_aggdet_windows (positives -> boxes) and fdb_non_maximum_suppression -
+    fed with the oracle's score maps reproduce aggregated_features_detect's detections exactly"""
+    import ctypes as C
+    from featuredetection_b200 import capi
+    from oracle import fdoracle as fo
+    lib = capi.load_library()
+    frame = np.ascontiguousarray(syn.synthetic_frame(8)[:200, :280])
+    rng = np.random.default_rng(6)
+    w = rng.normal(0, 0.15, (6, 5, 31)).astype(np.float32)
+    kw = dict(cell=4, octave_layer_count=4, nms_threshold=0.35, nms_type=2, width_scale=0.9, height_scale=1.1)
+    _, _, maps = fo.aggregated_features_detect(frame, w, bias=0.1, threshold=1e9, want_scores=True, **kw)
+    thr = float(np.quantile(np.concatenate([m.ravel() for m in maps if m.size]), 0.97))
+    rects, scores, maps = fo.aggregated_features_detect(frame, w, bias=0.1, threshold=thr, want_scores=True, **kw)
+    assert len(rects) > 3
+    import math
+    inc = 0.5 ** (1.0 / 4)
+    patch_w, patch_h = 5 * 4, 6 * 4
+    aspect, image_aspect = patch_h / patch_w, 200 / 280
+    max_width = int(200 / aspect) if aspect > image_aspect else 280
+    min_scale = math.pow(inc, int(math.log(patch_w / max_width) / math.log(inc)))
+    _, layers = fo.pyramid(frame, inc, min_scale, 1.0)
+    all_s, all_r = [], []
+    for (_, _, img), m in zip(layers, maps):
+        if m.size == 0:
+            continue
+        cap = m.size
+        s = np.zeros(cap, np.float32); r = np.zeros((cap, 4), np.int32); n = C.c_int64()
+        capi.check(lib, lib.fdb_aggdet_windows(np.ascontiguousarray(m).ctypes.data, m.shape[0], m.shape[1], thr, 6, 5, 4,
+                                               img.shape[1] / 280.0, img.shape[0] / 200.0, 0.9, 1.1, s.ctypes.data, r.ctypes.data, cap, C.byref(n)))
+        all_s.append(s[:n.value]); all_r.append(r[:n.value])
+    s = np.concatenate(all_s); r = np.ascontiguousarray(np.concatenate(all_r))
+    n = C.c_int64()
+    capi.check(lib, lib.fdb_non_maximum_suppression(s.ctypes.data, r.ctypes.data, len(s), 0.35, 2, C.byref(n)))
+    assert np.array_equal(r[:n.value], rects) and np.array_equal(s[:n.value], scores)
