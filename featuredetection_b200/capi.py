@@ -10,6 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("FDB_LIB") or os.path.join(_HERE, "csrc", "libfdb200.so")  # FDB_LIB: tuning builds only
 
 FDB_OK = 0
+FDB_ERR_INVALID_ARGUMENT, FDB_ERR_RUNTIME, FDB_ERR_CUDA, FDB_ERR_NO_DEVICE, FDB_ERR_UNSUPPORTED, FDB_ERR_OVERFLOW = 1, 2, 3, 4, 5, 6
 FDB_STAGE_WVM, FDB_STAGE_OE, FDB_STAGE_SVM, FDB_STAGE_NMS = 1, 2, 3, 4
 FDB_SV_U8, FDB_SV_F32 = 0, 1
 FDB_KERNEL_RBF, FDB_KERNEL_POLYNOMIAL, FDB_KERNEL_HIK, FDB_KERNEL_LINEAR = range(4)

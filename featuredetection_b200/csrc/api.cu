@@ -30,6 +30,14 @@ static thread_local std::string g_last_error;
 
 void set_error(const std::string& msg) { g_last_error = msg; }
 int fail(int status, const std::string& msg) { g_last_error = msg; return status; }
+int api_exception() noexcept {
+	try {
+		try { throw; }
+		catch (const std::bad_alloc&) { return fail(FDB_ERR_RUNTIME, "out of host memory"); }
+		catch (const std::exception& e) { return fail(FDB_ERR_RUNTIME, std::string("internal error: ") + e.what()); }
+		catch (...) { return fail(FDB_ERR_RUNTIME, "internal error: unknown exception"); }
+	} catch (...) { return FDB_ERR_RUNTIME; } /* the message itself could not be allocated */
+}
 
 } // namespace fdb
 
@@ -56,7 +64,7 @@ const char* fdb_status_string(int s) {
 	}
 }
 
-int fdb_ctx_create(int device, fdb_ctx** out) {
+int fdb_ctx_create(int device, fdb_ctx** out) try {
 	if (!out) return fail(FDB_ERR_INVALID_ARGUMENT, "out is null");
 	*out = nullptr;
 	int count = 0;
@@ -80,7 +88,7 @@ int fdb_ctx_create(int device, fdb_ctx** out) {
 	}
 	*out = c;
 	return FDB_OK;
-}
+} FDB_API_CATCH
 
 void fdb_ctx_destroy(fdb_ctx* c) {
 	if (!c) return;
@@ -93,19 +101,19 @@ void fdb_ctx_destroy(fdb_ctx* c) {
 
 void* fdb_ctx_stream(fdb_ctx* c) { return c ? (void*)c->stream : nullptr; }
 
-int fdb_ctx_synchronize(fdb_ctx* c) {
+int fdb_ctx_synchronize(fdb_ctx* c) try {
 	int s = check_ctx(c); if (s) return s;
 	CUDA_TRY(cudaStreamSynchronize(c->stream));
 	return FDB_OK;
-}
+} FDB_API_CATCH
 
-int fdb_ctx_timer_start(fdb_ctx* c) {
+int fdb_ctx_timer_start(fdb_ctx* c) try {
 	int s = check_ctx(c); if (s) return s;
 	CUDA_TRY(cudaEventRecord(c->ev[0], c->stream));
 	return FDB_OK;
-}
+} FDB_API_CATCH
 
-int fdb_ctx_timer_stop(fdb_ctx* c, double* elapsed_ms) {
+int fdb_ctx_timer_stop(fdb_ctx* c, double* elapsed_ms) try {
 	int s = check_ctx(c); if (s) return s;
 	CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));
 	CUDA_TRY(cudaEventSynchronize(c->ev[1]));
@@ -113,21 +121,21 @@ int fdb_ctx_timer_stop(fdb_ctx* c, double* elapsed_ms) {
 	CUDA_TRY(cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]));
 	if (elapsed_ms) *elapsed_ms = ms;
 	return FDB_OK;
-}
+} FDB_API_CATCH
 
 int64_t fdb_ctx_launch_count(fdb_ctx* c) { return c ? c->launches : 0; }
 
-int fdb_host_alloc(size_t bytes, void** out) {
+int fdb_host_alloc(size_t bytes, void** out) try {
 	if (!out) return fail(FDB_ERR_INVALID_ARGUMENT, "out is null");
 	CUDA_TRY(cudaMallocHost(out, std::max<size_t>(bytes, 16)));
 	return FDB_OK;
-}
+} FDB_API_CATCH
 void fdb_host_free(void* p) { if (p) cudaFreeHost(p); }
 
 /* ---------------------------------------------------------------------------------------------
  * WVM
  * ------------------------------------------------------------------------------------------- */
-int fdb_wvm_create(fdb_ctx* ctx, const fdb_wvm_desc* d, fdb_wvm** out) {
+int fdb_wvm_create(fdb_ctx* ctx, const fdb_wvm_desc* d, fdb_wvm** out) try {
 	int s = check_ctx(ctx); if (s) return s;
 	if (!d || !out) return fail(FDB_ERR_INVALID_ARGUMENT, "null argument");
 	*out = nullptr;
@@ -270,7 +278,7 @@ int fdb_wvm_create(fdb_ctx* ctx, const fdb_wvm_desc* d, fdb_wvm** out) {
 	if (s) { free_all(m->owned); delete m; return s; }
 	*out = m;
 	return FDB_OK;
-}
+} FDB_API_CATCH
 
 void fdb_wvm_destroy(fdb_wvm* m) {
 	if (!m) return;
@@ -280,7 +288,7 @@ void fdb_wvm_destroy(fdb_wvm* m) {
 	delete m;
 }
 
-int fdb_wvm_set_limit_reliability_filter(fdb_wvm* m, float value) {
+int fdb_wvm_set_limit_reliability_filter(fdb_wvm* m, float value) try {
 	if (!m) return fail(FDB_ERR_INVALID_ARGUMENT, "null wvm");
 	int s = check_ctx(m->ctx); if (s) return s;
 	/* WvmClassifier.cpp:165-181 */
@@ -291,10 +299,10 @@ int fdb_wvm_set_limit_reliability_filter(fdb_wvm* m, float value) {
 	CUDA_TRY(cudaStreamSynchronize(m->ctx->stream));
 	CUDA_TRY(cudaMemcpy(m->d_thresholds, m->thresholds.data(), sizeof(float) * m->thresholds.size(), cudaMemcpyHostToDevice));
 	return FDB_OK;
-}
+} FDB_API_CATCH
 
 int fdb_wvm_get_probability(fdb_wvm* m, const uint8_t* patches, int64_t n, int32_t* level_out, float* fout_out,
-		double* prob_out, uint8_t* pos_out) {
+		double* prob_out, uint8_t* pos_out) try {
 	if (!m) return fail(FDB_ERR_INVALID_ARGUMENT, "null wvm");
 	int s = check_ctx(m->ctx); if (s) return s;
 	if (n < 0 || (n > 0 && !patches)) return fail(FDB_ERR_INVALID_ARGUMENT, "bad patch batch");
@@ -325,12 +333,12 @@ int fdb_wvm_get_probability(fdb_wvm* m, const uint8_t* patches, int64_t n, int32
 		if (pos_out) pos_out[i] = (r.level + 1 == m->dev.num_lin && r.fout >= m->thresholds[(size_t)r.level]) ? 1 : 0;
 	}
 	return FDB_OK;
-}
+} FDB_API_CATCH
 
 /* ---------------------------------------------------------------------------------------------
  * SVM
  * ------------------------------------------------------------------------------------------- */
-int fdb_svm_create(fdb_ctx* ctx, const fdb_svm_desc* d, fdb_svm** out) {
+int fdb_svm_create(fdb_ctx* ctx, const fdb_svm_desc* d, fdb_svm** out) try {
 	int s = check_ctx(ctx); if (s) return s;
 	if (!d || !out) return fail(FDB_ERR_INVALID_ARGUMENT, "null argument");
 	*out = nullptr;
@@ -388,7 +396,7 @@ int fdb_svm_create(fdb_ctx* ctx, const fdb_svm_desc* d, fdb_svm** out) {
 	if (s) { free_all(m->owned); delete m; return s; }
 	*out = m;
 	return FDB_OK;
-}
+} FDB_API_CATCH
 
 void fdb_svm_destroy(fdb_svm* m) {
 	if (!m) return;
@@ -398,16 +406,16 @@ void fdb_svm_destroy(fdb_svm* m) {
 	delete m;
 }
 
-int fdb_svm_set_threshold(fdb_svm* m, float t) {
+int fdb_svm_set_threshold(fdb_svm* m, float t) try {
 	if (!m) return fail(FDB_ERR_INVALID_ARGUMENT, "null svm");
 	m->dev.threshold = t;
 	m->dense.threshold = t;
 	return FDB_OK;
-}
+} FDB_API_CATCH
 
 int fdb_svm_has_dense(const fdb_svm* m) { return m && m->has_dense && fdb::svm_dense_enabled() ? 1 : 0; }
 
-int fdb_svm_get_probability(fdb_svm* m, const void* vectors, int64_t n, double* dist_out, double* prob_out, uint8_t* pos_out) {
+int fdb_svm_get_probability(fdb_svm* m, const void* vectors, int64_t n, double* dist_out, double* prob_out, uint8_t* pos_out) try {
 	if (!m) return fail(FDB_ERR_INVALID_ARGUMENT, "null svm");
 	int s = check_ctx(m->ctx); if (s) return s;
 	if (n < 0 || (n > 0 && !vectors)) return fail(FDB_ERR_INVALID_ARGUMENT, "bad vector batch");
@@ -441,12 +449,12 @@ int fdb_svm_get_probability(fdb_svm* m, const void* vectors, int64_t n, double* 
 		if (pos_out) pos_out[i] = dd >= m->dev.threshold ? 1 : 0;
 	}
 	return FDB_OK;
-}
+} FDB_API_CATCH
 
 /* ---------------------------------------------------------------------------------------------
  * RVM
  * ------------------------------------------------------------------------------------------- */
-int fdb_rvm_create(fdb_ctx* ctx, const fdb_rvm_desc* d, fdb_rvm** out) {
+int fdb_rvm_create(fdb_ctx* ctx, const fdb_rvm_desc* d, fdb_rvm** out) try {
 	int s = check_ctx(ctx); if (s) return s;
 	if (!d || !out) return fail(FDB_ERR_INVALID_ARGUMENT, "null argument");
 	*out = nullptr;
@@ -478,7 +486,7 @@ int fdb_rvm_create(fdb_ctx* ctx, const fdb_rvm_desc* d, fdb_rvm** out) {
 	m->dev.rvm_filters = (d->num_filters_to_use <= 0 || d->num_filters_to_use > d->num_filters) ? d->num_filters : d->num_filters_to_use;
 	*out = m;
 	return FDB_OK;
-}
+} FDB_API_CATCH
 
 void fdb_rvm_destroy(fdb_rvm* m) {
 	if (!m) return;
@@ -495,7 +503,7 @@ int fdb_rvm_set_num_filters_to_use(fdb_rvm* m, int32_t n) { /* RvmClassifier.cpp
 }
 
 int fdb_rvm_get_probability(fdb_rvm* m, const void* vectors, int64_t n, int32_t* level_out, double* dist_out, double* prob_out,
-		uint8_t* pos_out) {
+		uint8_t* pos_out) try {
 	if (!m) return fail(FDB_ERR_INVALID_ARGUMENT, "null rvm");
 	int s = check_ctx(m->ctx); if (s) return s;
 	if (n < 0 || (n > 0 && !vectors)) return fail(FDB_ERR_INVALID_ARGUMENT, "bad vector batch");
@@ -531,10 +539,10 @@ int fdb_rvm_get_probability(fdb_rvm* m, const void* vectors, int64_t n, int32_t*
 		if (pos_out) pos_out[i] = (l + 1 == m->dev.rvm_filters && dd >= (double)m->rvm_thresholds[(size_t)l]) ? 1 : 0;
 	}
 	return FDB_OK;
-}
+} FDB_API_CATCH
 
 int fdb_plan_layers(const fdb_detector_desc* desc, int32_t width, int32_t height, int32_t roi_x, int32_t roi_y,
-		int32_t roi_w, int32_t roi_h, fdb_layer_info* out, int32_t cap, int32_t* n_layers, int64_t* n_windows) {
+		int32_t roi_w, int32_t roi_h, fdb_layer_info* out, int32_t cap, int32_t* n_layers, int64_t* n_windows) try {
 	if (!desc) return fail(FDB_ERR_INVALID_ARGUMENT, "null descriptor");
 	fdb_detector_desc d = *desc;
 	if (d.step_x == 0) d.step_x = 1;
@@ -555,24 +563,24 @@ int fdb_plan_layers(const fdb_detector_desc* desc, int32_t width, int32_t height
 		o.windows_x = L.windows_x; o.windows_y = L.windows_y; o.first_window = L.first_window;
 	}
 	return FDB_OK;
-}
+} FDB_API_CATCH
 
-int fdb_overlap_eliminate(fdb_detection* dets, int64_t n, float dist, float ratio, int64_t* n_out) {
+int fdb_overlap_eliminate(fdb_detection* dets, int64_t n, float dist, float ratio, int64_t* n_out) try {
 	if (n < 0 || (n > 0 && !dets)) return fail(FDB_ERR_INVALID_ARGUMENT, "bad detection list");
 	std::vector<fdb_detection> v(dets, dets + n);
 	overlap_eliminate(v, dist, ratio);
 	if (!v.empty()) std::memcpy(dets, v.data(), sizeof(fdb_detection) * v.size());
 	if (n_out) *n_out = (int64_t)v.size();
 	return FDB_OK;
-}
+} FDB_API_CATCH
 
-int fdb_five_stage_nms(fdb_detection* dets, int64_t n, int32_t width, int32_t height, int64_t* n_out) {
+int fdb_five_stage_nms(fdb_detection* dets, int64_t n, int32_t width, int32_t height, int64_t* n_out) try {
 	if (n < 0 || (n > 0 && !dets) || width < 1 || height < 1) return fail(FDB_ERR_INVALID_ARGUMENT, "bad detection list");
 	std::vector<fdb_detection> v(dets, dets + n);
 	five_stage_nms(v, width, height);
 	if (!v.empty()) std::memcpy(dets, v.data(), sizeof(fdb_detection) * v.size());
 	if (n_out) *n_out = (int64_t)v.size();
 	return FDB_OK;
-}
+} FDB_API_CATCH
 
 } // extern "C"

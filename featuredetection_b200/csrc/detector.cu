@@ -732,7 +732,7 @@ int detect_impl(fdb_detector* det, const uint8_t* frames, bool frames_on_device,
 
 extern "C" {
 
-int fdb_detector_create(fdb_ctx* ctx, const fdb_detector_desc* desc, fdb_wvm* wvm, fdb_svm* svm, fdb_detector** out) {
+int fdb_detector_create(fdb_ctx* ctx, const fdb_detector_desc* desc, fdb_wvm* wvm, fdb_svm* svm, fdb_detector** out) try {
 	int s = check_ctx(ctx); if (s) return s;
 	if (!desc || !out) return fail(FDB_ERR_INVALID_ARGUMENT, "null argument");
 	*out = nullptr;
@@ -754,12 +754,12 @@ int fdb_detector_create(fdb_ctx* ctx, const fdb_detector_desc* desc, fdb_wvm* wv
 	det->ctx = ctx; det->desc = d; det->wvm = wvm; det->svm = svm;
 	*out = det;
 	return FDB_OK;
-}
+} FDB_API_CATCH
 
-int fdb_detector_create_rvm(fdb_ctx* ctx, const fdb_detector_desc* desc, fdb_rvm* rvm, fdb_detector** out) {
+int fdb_detector_create_rvm(fdb_ctx* ctx, const fdb_detector_desc* desc, fdb_rvm* rvm, fdb_detector** out) try {
 	if (!rvm) return fail(FDB_ERR_INVALID_ARGUMENT, "null rvm");
 	return fdb_detector_create(ctx, desc, nullptr, static_cast<fdb_svm*>(rvm), out);
-}
+} FDB_API_CATCH
 
 void fdb_detector_destroy(fdb_detector* det) {
 	if (!det) return;
@@ -771,7 +771,7 @@ void fdb_detector_destroy(fdb_detector* det) {
 	delete det;
 }
 
-int fdb_detector_prepare(fdb_detector* det, int32_t width, int32_t height, int32_t max_batch) {
+int fdb_detector_prepare(fdb_detector* det, int32_t width, int32_t height, int32_t max_batch) try {
 	if (!det) return fail(FDB_ERR_INVALID_ARGUMENT, "null detector");
 	int s = check_ctx(det->ctx); if (s) return s;
 	if (max_batch < 1) return fail(FDB_ERR_INVALID_ARGUMENT, "max_batch must be positive");
@@ -986,9 +986,9 @@ int fdb_detector_prepare(fdb_detector* det, int32_t width, int32_t height, int32
 	}
 	det->prepared = true;
 	return FDB_OK;
-}
+} FDB_API_CATCH
 
-int fdb_detector_layers(fdb_detector* det, fdb_layer_info* out, int32_t cap, int32_t* n_layers) {
+int fdb_detector_layers(fdb_detector* det, fdb_layer_info* out, int32_t cap, int32_t* n_layers) try {
 	if (!det || !det->prepared) return fail(FDB_ERR_INVALID_ARGUMENT, "detector not prepared");
 	const Plan& p = det->plan;
 	if (n_layers) *n_layers = (int32_t)p.layers.size();
@@ -1000,7 +1000,7 @@ int fdb_detector_layers(fdb_detector* det, fdb_layer_info* out, int32_t cap, int
 		o.windows_x = L.windows_x; o.windows_y = L.windows_y; o.first_window = L.first_window;
 	}
 	return FDB_OK;
-}
+} FDB_API_CATCH
 
 int64_t fdb_detector_windows_per_frame(fdb_detector* det) { return det && det->prepared ? det->plan.windows : -1; }
 int64_t fdb_detector_pyramid_bytes(fdb_detector* det) {
@@ -1011,14 +1011,14 @@ int64_t fdb_detector_pyramid_bytes(fdb_detector* det) {
 }
 
 int fdb_detect_batch(fdb_detector* det, const uint8_t* frames_host, int64_t pitch, int32_t n_frames, int32_t stage,
-		fdb_window_score* dense_out, fdb_detection* detections_out, int64_t det_cap, int64_t* n_detections) {
+		fdb_window_score* dense_out, fdb_detection* detections_out, int64_t det_cap, int64_t* n_detections) try {
 	return detect_impl(det, frames_host, false, pitch, n_frames, stage, dense_out, false, detections_out, det_cap, n_detections);
-}
+} FDB_API_CATCH
 
 int fdb_detect_batch_device(fdb_detector* det, const uint8_t* frames_device, int32_t n_frames, int32_t stage,
-		fdb_window_score* dense_out_device, fdb_detection* detections_out, int64_t det_cap, int64_t* n_detections) {
+		fdb_window_score* dense_out_device, fdb_detection* detections_out, int64_t det_cap, int64_t* n_detections) try {
 	return detect_impl(det, frames_device, true, 0, n_frames, stage, dense_out_device, true, detections_out, det_cap, n_detections);
-}
+} FDB_API_CATCH
 
 /* GrayscaleFilter::applyTo on the device for n frames of interleaved 8-bit BGR in host memory -> d_gray (contiguous) */
 static int upload_bgr_as_gray(cudaStream_t st, const uint8_t* bgr_host, int64_t pitch, int W, int H, int n, uint8_t* d_bgr, uint8_t* d_gray) {
@@ -1029,7 +1029,7 @@ static int upload_bgr_as_gray(cudaStream_t st, const uint8_t* bgr_host, int64_t 
 	return FDB_OK;
 }
 
-int fdb_gray_from_bgr(fdb_ctx* ctx, const uint8_t* bgr_host, int64_t pitch, int32_t W, int32_t H, int32_t n_frames, uint8_t* gray_host) {
+int fdb_gray_from_bgr(fdb_ctx* ctx, const uint8_t* bgr_host, int64_t pitch, int32_t W, int32_t H, int32_t n_frames, uint8_t* gray_host) try {
 	int s = check_ctx(ctx); if (s) return s;
 	if (!bgr_host || !gray_host || W < 1 || H < 1 || n_frames < 0 || pitch < 3ll * W) return fail(FDB_ERR_INVALID_ARGUMENT, "bad BGR frame batch");
 	if (n_frames == 0) return FDB_OK;
@@ -1044,10 +1044,10 @@ int fdb_gray_from_bgr(fdb_ctx* ctx, const uint8_t* bgr_host, int64_t pitch, int3
 	if (s) return s;
 	if (e != cudaSuccess) return fail(FDB_ERR_CUDA, std::string("fdb_gray_from_bgr: ") + cudaGetErrorString(e));
 	return FDB_OK;
-}
+} FDB_API_CATCH
 
 int fdb_detect_batch_bgr(fdb_detector* det, const uint8_t* bgr_host, int64_t pitch, int32_t n_frames, int32_t stage,
-		fdb_window_score* dense_out, fdb_detection* detections_out, int64_t det_cap, int64_t* n_detections) {
+		fdb_window_score* dense_out, fdb_detection* detections_out, int64_t det_cap, int64_t* n_detections) try {
 	if (!det || !det->prepared) return fail(FDB_ERR_INVALID_ARGUMENT, "detector not prepared (call fdb_detector_prepare)");
 	int s = check_ctx(det->ctx); if (s) return s;
 	const int W = det->plan.width, H = det->plan.height;
@@ -1068,9 +1068,9 @@ int fdb_detect_batch_bgr(fdb_detector* det, const uint8_t* bgr_host, int64_t pit
 		CUDA_TRY(cudaStreamSynchronize(det->ctx->stream)); /* the pipeline slots run on their own streams */
 	}
 	return detect_impl(det, det->d_gray, true, 0, n_frames, stage, dense_out, false, detections_out, det_cap, n_detections);
-}
+} FDB_API_CATCH
 
-int fdb_detect_enqueue_device(fdb_detector* det, const uint8_t* frames_device, int32_t n_frames, fdb_window_score* dense_out_device) {
+int fdb_detect_enqueue_device(fdb_detector* det, const uint8_t* frames_device, int32_t n_frames, fdb_window_score* dense_out_device) try {
 	if (!det || !det->prepared) return fail(FDB_ERR_INVALID_ARGUMENT, "detector not prepared (call fdb_detector_prepare)");
 	int s = check_ctx(det->ctx); if (s) return s;
 	if (!det->wvm) return fail(FDB_ERR_INVALID_ARGUMENT, "this entry point needs a detector with a WVM first stage");
@@ -1083,9 +1083,9 @@ int fdb_detect_enqueue_device(fdb_detector* det, const uint8_t* frames_device, i
 		if (s) return s;
 	}
 	return FDB_OK;
-}
+} FDB_API_CATCH
 
-int fdb_detect_profile_device(fdb_detector* det, const uint8_t* frames_device, int32_t n_frames, double ms_out[6]) {
+int fdb_detect_profile_device(fdb_detector* det, const uint8_t* frames_device, int32_t n_frames, double ms_out[6]) try {
 	if (!det || !det->prepared) return fail(FDB_ERR_INVALID_ARGUMENT, "detector not prepared (call fdb_detector_prepare)");
 	int s = check_ctx(det->ctx); if (s) return s;
 	if (!det->wvm) return fail(FDB_ERR_INVALID_ARGUMENT, "this entry point needs a detector with a WVM first stage");
@@ -1108,10 +1108,10 @@ int fdb_detect_profile_device(fdb_detector* det, const uint8_t* frames_device, i
 		ms_out[0] += a; ms_out[1] += b; ms_out[2] += w; ms_out[3] += d; ms_out[4] += t; ms_out[5] += 1;
 	}
 	return FDB_OK;
-}
+} FDB_API_CATCH
 
 int fdb_detect_roi(fdb_detector* det, const uint8_t* frame_host, int64_t pitch, int32_t roi_x, int32_t roi_y, int32_t roi_w,
-		int32_t roi_h, int32_t stage, fdb_detection* detections_out, int64_t det_cap, int64_t* n_detections) {
+		int32_t roi_h, int32_t stage, fdb_detection* detections_out, int64_t det_cap, int64_t* n_detections) try {
 	if (!det || !det->prepared) return fail(FDB_ERR_INVALID_ARGUMENT, "detector not prepared (call fdb_detector_prepare)");
 	int s = check_ctx(det->ctx); if (s) return s;
 	if (!det->wvm) return fail(FDB_ERR_INVALID_ARGUMENT, "this entry point needs a detector with a WVM first stage");
@@ -1138,10 +1138,10 @@ int fdb_detect_roi(fdb_detector* det, const uint8_t* frame_host, int64_t pitch, 
 	s = phase_a(det, sl, st, plan, det->d_layers_roi, stage); if (s) return s;
 	s = phase_b(det, sl, plan, stage, is_roi, dets); if (s) return s;
 	return copy_out(dets, detections_out, det_cap, n_detections);
-}
+} FDB_API_CATCH
 
 int fdb_extract_patches(fdb_detector* det, const uint8_t* frame_host, int64_t pitch, uint8_t* patches_out, int64_t cap_windows,
-		int64_t* n_windows) {
+		int64_t* n_windows) try {
 	if (!det || !det->prepared) return fail(FDB_ERR_INVALID_ARGUMENT, "detector not prepared (call fdb_detector_prepare)");
 	int s = check_ctx(det->ctx); if (s) return s;
 	if (!det->wvm) return fail(FDB_ERR_INVALID_ARGUMENT, "this entry point needs a detector with a WVM first stage");
@@ -1164,9 +1164,9 @@ int fdb_extract_patches(fdb_detector* det, const uint8_t* frame_host, int64_t pi
 	if (bytes) CUDA_TRY(cudaMemcpyAsync(patches_out, det->d_patches, (size_t)bytes, cudaMemcpyDeviceToHost, st));
 	CUDA_TRY(cudaStreamSynchronize(st));
 	return FDB_OK;
-}
+} FDB_API_CATCH
 
-int fdb_pyramid_layer(fdb_detector* det, const uint8_t* frame_host, int64_t pitch, int32_t layer_index, uint8_t* out, int64_t cap) {
+int fdb_pyramid_layer(fdb_detector* det, const uint8_t* frame_host, int64_t pitch, int32_t layer_index, uint8_t* out, int64_t cap) try {
 	if (!det || !det->prepared) return fail(FDB_ERR_INVALID_ARGUMENT, "detector not prepared (call fdb_detector_prepare)");
 	int s = check_ctx(det->ctx); if (s) return s;
 	const Plan& plan = det->plan;
@@ -1187,18 +1187,18 @@ int fdb_pyramid_layer(fdb_detector* det, const uint8_t* frame_host, int64_t pitc
 	CUDA_TRY(cudaMemcpy2DAsync(out, (size_t)L->width, src, (size_t)im.pitch, (size_t)L->width, (size_t)L->height, cudaMemcpyDeviceToHost, st));
 	CUDA_TRY(cudaStreamSynchronize(st));
 	return FDB_OK;
-}
+} FDB_API_CATCH
 
-int fdb_feature_shape(const fdb_feature_desc* desc, int32_t patch_width, int32_t patch_height, int32_t* dim, int32_t* is_float) {
+int fdb_feature_shape(const fdb_feature_desc* desc, int32_t patch_width, int32_t patch_height, int32_t* dim, int32_t* is_float) try {
 	if (!desc) return fail(FDB_ERR_INVALID_ARGUMENT, "null feature descriptor");
 	FeatureShape sh;
 	int s = feature_shape(*desc, patch_width, patch_height, &sh); if (s) return s;
 	if (dim) *dim = sh.dim;
 	if (is_float) *is_float = sh.is_float;
 	return FDB_OK;
-}
+} FDB_API_CATCH
 
-int fdb_detector_set_feature(fdb_detector* det, const fdb_feature_desc* desc) {
+int fdb_detector_set_feature(fdb_detector* det, const fdb_feature_desc* desc) try {
 	if (!det || !desc) return fail(FDB_ERR_INVALID_ARGUMENT, "null argument");
 	int s = check_ctx(det->ctx); if (s) return s;
 	FeatureShape sh;
@@ -1208,9 +1208,9 @@ int fdb_detector_set_feature(fdb_detector* det, const fdb_feature_desc* desc) {
 	det->fdesc = *desc;
 	det->has_feature = true;
 	return FDB_OK;
-}
+} FDB_API_CATCH
 
-int fdb_extract_features(fdb_detector* det, const uint8_t* frame_host, int64_t pitch, const int32_t* layer_x_y, int64_t n, void* out) {
+int fdb_extract_features(fdb_detector* det, const uint8_t* frame_host, int64_t pitch, const int32_t* layer_x_y, int64_t n, void* out) try {
 	if (!det || !det->prepared) return fail(FDB_ERR_INVALID_ARGUMENT, "detector not prepared (call fdb_detector_prepare)");
 	int s = check_ctx(det->ctx); if (s) return s;
 	if (!frame_host || (n > 0 && (!layer_x_y || !out))) return fail(FDB_ERR_INVALID_ARGUMENT, "null buffer");
@@ -1256,11 +1256,11 @@ int fdb_extract_features(fdb_detector* det, const uint8_t* frame_host, int64_t p
 		CUDA_TRY(cudaStreamSynchronize(st));
 	}
 	return FDB_OK;
-}
+} FDB_API_CATCH
 
 int fdb_detect_face_features(fdb_detector* face, fdb_detector* const* features, int32_t n_features, const uint8_t* frame_host,
 		int64_t pitch, fdb_detection* face_out, int64_t face_cap, int64_t* n_face, fdb_detection* feature_out,
-		int64_t feature_cap_each, int64_t* n_feature) {
+		int64_t feature_cap_each, int64_t* n_feature) try {
 	if (!face || !n_face || (n_features > 0 && (!features || !n_feature))) return fail(FDB_ERR_INVALID_ARGUMENT, "null argument");
 	for (int i = 0; i < n_features; ++i) n_feature[i] = 0;
 	/* ffpDetectApp.cpp:555-557: facePatches = detector->detect(img) */
@@ -1278,10 +1278,10 @@ int fdb_detect_face_features(fdb_detector* face, fdb_detector* const* features, 
 		if (s) return s;
 	}
 	return FDB_OK;
-}
+} FDB_API_CATCH
 
 int fdb_evaluate_samples(fdb_detector* det, const uint8_t* frame_host, int64_t pitch, const int32_t* samples_xywh, int64_t n,
-		int32_t max_svm_patches, uint8_t* target_out, double* weight_out) {
+		int32_t max_svm_patches, uint8_t* target_out, double* weight_out) try {
 	if (!det || !det->prepared) return fail(FDB_ERR_INVALID_ARGUMENT, "detector not prepared (call fdb_detector_prepare)");
 	int s = check_ctx(det->ctx); if (s) return s;
 	if (!det->wvm) return fail(FDB_ERR_INVALID_ARGUMENT, "fdb_evaluate_samples needs a detector with a WVM");
@@ -1290,20 +1290,20 @@ int fdb_evaluate_samples(fdb_detector* det, const uint8_t* frame_host, int64_t p
 	if (n < 0 || !frame_host || (n > 0 && (!samples_xywh || !target_out || !weight_out))) return fail(FDB_ERR_INVALID_ARGUMENT, "null buffer");
 	if (pitch < det->plan.width) return fail(FDB_ERR_INVALID_ARGUMENT, "pitch smaller than the frame width");
 	return evaluate_samples(det, frame_host, pitch, samples_xywh, n, max_svm_patches, target_out, weight_out);
-}
+} FDB_API_CATCH
 
 int fdb_detect_single(fdb_detector* det, const uint8_t* frames_host, int64_t pitch, int32_t n_frames, double* distance_out,
-		fdb_detection* detections_out, int64_t det_cap, int64_t* n_detections) {
+		fdb_detection* detections_out, int64_t det_cap, int64_t* n_detections) try {
 	if (!det || !det->prepared) return fail(FDB_ERR_INVALID_ARGUMENT, "detector not prepared (call fdb_detector_prepare)");
 	int s = check_ctx(det->ctx); if (s) return s;
 	if (det->wvm || !det->svm) return fail(FDB_ERR_INVALID_ARGUMENT, "fdb_detect_single needs a detector created with an SVM only");
 	if (n_frames < 0 || (n_frames > 0 && !frames_host)) return fail(FDB_ERR_INVALID_ARGUMENT, "bad frame batch");
 	if (pitch < det->plan.width) return fail(FDB_ERR_INVALID_ARGUMENT, "pitch smaller than the frame width");
 	return detect_single(det, frames_host, false, pitch, n_frames, distance_out, detections_out, det_cap, n_detections);
-}
+} FDB_API_CATCH
 
 int fdb_detect_single_device(fdb_detector* det, const uint8_t* frames_device, int32_t n_frames, double* distance_device,
-		fdb_detection* detections_out, int64_t det_cap, int64_t* n_detections) {
+		fdb_detection* detections_out, int64_t det_cap, int64_t* n_detections) try {
 	if (!det || !det->prepared) return fail(FDB_ERR_INVALID_ARGUMENT, "detector not prepared (call fdb_detector_prepare)");
 	int s = check_ctx(det->ctx); if (s) return s;
 	if (det->wvm || !det->svm) return fail(FDB_ERR_INVALID_ARGUMENT, "fdb_detect_single_device needs a detector created with an SVM only");
@@ -1311,20 +1311,20 @@ int fdb_detect_single_device(fdb_detector* det, const uint8_t* frames_device, in
 	if (!single_dense_usable(det))
 		return fail(FDB_ERR_UNSUPPORTED, "fdb_detect_single_device: this SVM has no tensor-core form (u8 RBF on HistEq64 patches only)");
 	return detect_single_dense(det, frames_device, true, det->plan.width, n_frames, distance_device, true, detections_out, det_cap, n_detections);
-}
+} FDB_API_CATCH
 
 int fdb_detector_single_dense(fdb_detector* det) { return det && det->prepared && single_dense_usable(det) ? 1 : 0; }
 
-int fdb_detector_single_dense_profile(fdb_detector* det, double* kernel_ms, int32_t* launches) {
+int fdb_detector_single_dense_profile(fdb_detector* det, double* kernel_ms, int32_t* launches) try {
 	if (!det || !kernel_ms || !launches) return fail(FDB_ERR_INVALID_ARGUMENT, "null argument");
 	*kernel_ms = det->sd_kernel_ms; *launches = det->sd_kernel_launches;
 	return FDB_OK;
-}
+} FDB_API_CATCH
 
-int fdb_detector_last_counts(fdb_detector* det, int64_t counts[5]) {
+int fdb_detector_last_counts(fdb_detector* det, int64_t counts[5]) try {
 	if (!det || !counts) return fail(FDB_ERR_INVALID_ARGUMENT, "null argument");
 	std::memcpy(counts, det->counts, sizeof(det->counts));
 	return FDB_OK;
-}
+} FDB_API_CATCH
 
 } // extern "C"

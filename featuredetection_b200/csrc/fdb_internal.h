@@ -16,6 +16,9 @@ namespace fdb {
 /* ---- error plumbing -------------------------------------------------------------------- */
 void set_error(const std::string& msg);
 int fail(int status, const std::string& msg);
+/* status of the exception in flight (call inside a catch block): no C++ exception may cross the C ABI */
+int api_exception() noexcept;
+#define FDB_API_CATCH catch (...) { return fdb::api_exception(); }
 
 /* ---- pyramid plan (host) --------------------------------------------------------------- */
 enum ImageKind { IMG_FRAME = 0, IMG_RESIZE = 1, IMG_PYRDOWN = 2 };

@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(128) aggdet_score_kernel(const float* __restri
 using namespace fdb;
 
 extern "C" int fdb_fhog(fdb_ctx* ctx, const uint8_t* image_host, int64_t pitch, int32_t width, int32_t height, int32_t channels,
-		int32_t cell_size, int32_t unsigned_bins, int32_t interpolate_bins, int32_t interpolate_cells, float alpha, float* out_host) {
+		int32_t cell_size, int32_t unsigned_bins, int32_t interpolate_bins, int32_t interpolate_cells, float alpha, float* out_host) try {
 	int s = check_ctx(ctx); if (s) return s;
 	if (!image_host || !out_host) return fail(FDB_ERR_INVALID_ARGUMENT, "null buffer");
 	if (channels != 1 && channels != 3) return fail(FDB_ERR_INVALID_ARGUMENT, "FhogFilter: the image type must be CV_8UC1 or CV_8UC3");
@@ -135,15 +135,19 @@ extern "C" int fdb_fhog(fdb_ctx* ctx, const uint8_t* image_host, int64_t pitch, 
 	free_all(tmp);
 	if (e != cudaSuccess) return fail(FDB_ERR_CUDA, std::string("fdb_fhog: ") + cudaGetErrorString(e));
 	return FDB_OK;
-}
+} FDB_API_CATCH
 
 /* FHOG + linear-SVM score map of ONE pyramid layer (see fdb200.h) */
 extern "C" int fdb_fhog_score_map(fdb_ctx* ctx, const uint8_t* image_host, int64_t pitch, int32_t width, int32_t height, int32_t channels,
 		int32_t cell_size, int32_t unsigned_bins, int32_t interpolate_bins, int32_t interpolate_cells, float alpha,
-		const float* weights_host, int32_t kernel_rows, int32_t kernel_cols, float bias, float* scores_host) {
+		const float* weights_host, int32_t kernel_rows, int32_t kernel_cols, float bias, float* scores_host) try {
 	int s = check_ctx(ctx); if (s) return s;
 	if (!weights_host || !scores_host || kernel_rows < 1 || kernel_cols < 1) return fail(FDB_ERR_INVALID_ARGUMENT, "bad kernel");
-	if (cell_size < 1 || width < 1 || height < 1) return fail(FDB_ERR_INVALID_ARGUMENT, "bad image geometry");
+	if (!image_host) return fail(FDB_ERR_INVALID_ARGUMENT, "null buffer");
+	if (channels != 1 && channels != 3) return fail(FDB_ERR_INVALID_ARGUMENT, "FhogFilter: the image type must be CV_8UC1 or CV_8UC3");
+	if (unsigned_bins < 1 || unsigned_bins > 64) return fail(FDB_ERR_INVALID_ARGUMENT, "FhogFilter: unsignedBinCount must be bigger than zero");
+	if (!(alpha > 0)) return fail(FDB_ERR_INVALID_ARGUMENT, "FhogAggregationFilter: alpha must be bigger than zero");
+	if (cell_size < 1 || width < 1 || height < 1 || pitch < (int64_t)width * channels) return fail(FDB_ERR_INVALID_ARGUMENT, "bad image geometry");
 	const int crow = height / cell_size, ccol = width / cell_size, D = 3 * unsigned_bins + 4;
 	const int vh = crow - kernel_rows + 1, vw = ccol - kernel_cols + 1;
 	if (vh <= 0 || vw <= 0) return FDB_OK; /* no window fits this layer */
@@ -165,4 +169,4 @@ extern "C" int fdb_fhog_score_map(fdb_ctx* ctx, const uint8_t* image_host, int64
 	free_all(tmp);
 	if (e != cudaSuccess) return fail(FDB_ERR_CUDA, std::string("fdb_fhog_score_map: ") + cudaGetErrorString(e));
 	return FDB_OK;
-}
+} FDB_API_CATCH

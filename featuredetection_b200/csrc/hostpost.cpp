@@ -140,7 +140,7 @@ void five_stage_nms(std::vector<fdb_detection>& v, int width, int height) {
  * intersection over union on integer rectangles :60-64); each cluster yields its best member, or the (score-weighted)
  * mean box rounded half away from zero with the best score (:74-109). Output order: clusters by descending best score. */
 extern "C" int fdb_non_maximum_suppression(float* scores, int32_t* rects_xywh, int64_t n, double overlap_threshold,
-		int32_t maximum_type, int64_t* n_out) {
+		int32_t maximum_type, int64_t* n_out) try {
 	using fdb::fail;
 	if (n < 0 || (n > 0 && (!scores || !rects_xywh)) || !n_out) return fail(FDB_ERR_INVALID_ARGUMENT, "bad detection list");
 	if (maximum_type < FDB_NMS_MAX_SCORE || maximum_type > FDB_NMS_WEIGHTED_AVERAGE)
@@ -189,7 +189,7 @@ extern "C" int fdb_non_maximum_suppression(float* scores, int32_t* rects_xywh, i
 	}
 	*n_out = out;
 	return FDB_OK;
-}
+} FDB_API_CATCH
 
 /* AggregatedFeaturesDetector::getPositiveWindows for one layer (AggregatedFeaturesDetector.cpp:92-118) with
  * AggregatedFeaturesExtractor::computeBoundsInImagePixels (AggregatedFeaturesExtractor.cpp:121-128) and rescaleWindow:
@@ -198,7 +198,7 @@ extern "C" int fdb_non_maximum_suppression(float* scores, int32_t* rects_xywh, i
  * nothing past cap is written). Host only. */
 extern "C" int fdb_aggdet_windows(const float* score_map, int32_t valid_rows, int32_t valid_cols, float threshold, int32_t kernel_rows,
 		int32_t kernel_cols, int32_t cell_size, double scale_x, double scale_y, float width_scale, float height_scale,
-		float* scores_out, int32_t* rects_xywh_out, int64_t cap, int64_t* n_out) {
+		float* scores_out, int32_t* rects_xywh_out, int64_t cap, int64_t* n_out) try {
 	using fdb::fail;
 	if (!n_out || valid_rows < 0 || valid_cols < 0 || (valid_rows > 0 && valid_cols > 0 && !score_map) || cap < 0
 			|| (cap > 0 && (!scores_out || !rects_xywh_out)))
@@ -223,5 +223,5 @@ extern "C" int fdb_aggdet_windows(const float* score_map, int32_t valid_rows, in
 		}
 	*n_out = n;
 	return FDB_OK;
-}
+} FDB_API_CATCH
 

@@ -30,68 +30,66 @@ using namespace fdb;
 
 extern "C" {
 
-int fdb_svm_file_load(const char* path, fdb_svm_file** out) {
+int fdb_svm_file_load(const char* path, fdb_svm_file** out) try {
 	if (!path || !out) return fail(FDB_ERR_INVALID_ARGUMENT, "null argument");
 	*out = nullptr;
 	std::ifstream file(path);
 	if (!file) return fail(FDB_ERR_RUNTIME, "SvmClassifier: Cannot read from stream");
-	fdb_svm_file* f = new fdb_svm_file;
+	std::unique_ptr<fdb_svm_file> f(new fdb_svm_file);
 	fdb_svm_desc& d = f->desc;
 	d = fdb_svm_desc();
 	std::string tmp, kernelType;
 	file >> tmp >> kernelType; /* "Kernel" <type> */
-	bool supported = false;
 	if (kernelType == "RBF") {
 		file >> d.gamma;
 		d.kernel = FDB_KERNEL_RBF;
-		supported = true;
 	} else if (kernelType == "Polynomial") { /* SvmClassifier.cpp:76-77: degree, constant, alpha */
 		file >> d.poly_degree >> d.poly_constant >> d.poly_alpha;
 		d.kernel = FDB_KERNEL_POLYNOMIAL;
-		supported = true;
 	} else if (kernelType == "Linear") {
 		d.kernel = FDB_KERNEL_LINEAR;
-		supported = true;
 	} else if (kernelType == "HIK") {
 		d.kernel = FDB_KERNEL_HIK;
-		supported = true;
 	} else {
-		delete f;
 		return fail(FDB_ERR_RUNTIME, "SvmClassifier: Invalid kernel type: " + kernelType);
 	}
 	file >> tmp >> d.bias; /* "Bias" */
 	size_t count = 0;
 	file >> tmp >> count;   /* "Coefficients" */
-	if (!file || count == 0 || count > (1u << 24)) { delete f; return fail(FDB_ERR_RUNTIME, "SvmClassifier: Invalid classifier file"); }
+	if (!file || count == 0 || count > (1u << 24)) return fail(FDB_ERR_RUNTIME, "SvmClassifier: Invalid classifier file");
 	f->coefficients.resize(count);
 	for (size_t i = 0; i < count; ++i) file >> f->coefficients[i];
 	file >> tmp >> count >> f->rows >> f->cols >> f->channels >> f->depth; /* "SupportVectors" */
-	if (!file || count != f->coefficients.size() || f->rows < 1 || f->cols < 1 || f->channels < 1) {
-		delete f; return fail(FDB_ERR_RUNTIME, "SvmClassifier: Invalid classifier file");
-	}
+	if (!file || count != f->coefficients.size() || f->rows < 1 || f->cols < 1 || f->channels < 1)
+		return fail(FDB_ERR_RUNTIME, "SvmClassifier: Invalid classifier file");
+	/* the sizes come from the file: bound them before they size an allocation (fdb_svm_create's own limit on a vector is
+	 * 96 KB of float32 = 24 576 elements; the element count of all vectors must fit the stream that follows) */
+	const size_t max_dim = 96 * 1024 / 4;
+	if ((size_t)f->rows > max_dim || (size_t)f->cols > max_dim || (size_t)f->channels > max_dim ||
+			(size_t)f->rows * f->cols > max_dim || (size_t)f->rows * f->cols * f->channels > max_dim)
+		return fail(FDB_ERR_RUNTIME, "SvmClassifier: Invalid classifier file (support vector of more than 24576 elements)");
 	const size_t dim = (size_t)f->rows * f->cols * f->channels;
+	if (count > ((size_t)1 << 31) / dim) return fail(FDB_ERR_RUNTIME, "SvmClassifier: Invalid classifier file (support vectors exceed 2^31 elements)");
 	if (f->depth == 0) { /* CV_8U: raw characters */
 		f->sv_u8.resize(count * dim);
-		for (size_t i = 0; i < count * dim; ++i) { unsigned char c; file >> c; f->sv_u8[i] = c; }
+		for (size_t i = 0; i < count * dim && file; ++i) { unsigned char c; file >> c; f->sv_u8[i] = c; }
 		d.sv_type = FDB_SV_U8; d.support_vectors = f->sv_u8.data();
 	} else if (f->depth == 5) { /* CV_32F */
 		f->sv_f32.resize(count * dim);
-		for (size_t i = 0; i < count * dim; ++i) file >> f->sv_f32[i];
+		for (size_t i = 0; i < count * dim && file; ++i) file >> f->sv_f32[i];
 		d.sv_type = FDB_SV_F32; d.support_vectors = f->sv_f32.data();
 	} else {
-		delete f;
 		return fail(FDB_ERR_UNSUPPORTED, "SvmClassifier: only CV_8U and CV_32F support vectors are evaluated on the GPU");
 	}
-	if (!file) { delete f; return fail(FDB_ERR_RUNTIME, "SvmClassifier: Invalid classifier file"); }
+	if (!file) return fail(FDB_ERR_RUNTIME, "SvmClassifier: Invalid classifier file");
 	d.num_sv = (int32_t)count; d.dim = (int32_t)dim;
 	d.coefficients = f->coefficients.data();
 	d.threshold = 0.0f;                        /* VectorMachineClassifier default */
 	d.logistic_a = 0.00556; d.logistic_b = -2.95; /* ProbabilisticSvmClassifier.hpp:36 defaults */
 	if (file >> tmp && tmp == "Logistic") file >> d.logistic_a >> d.logistic_b;
-	if (!supported) { delete f; return fail(FDB_ERR_UNSUPPORTED, "SvmClassifier: kernel " + kernelType + " is not supported"); }
-	*out = f;
+	*out = f.release();
 	return FDB_OK;
-}
+} FDB_API_CATCH
 
 const fdb_svm_desc* fdb_svm_file_desc(const fdb_svm_file* f) { return f ? &f->desc : nullptr; }
 
@@ -131,7 +129,7 @@ std::vector<std::string> sdm_split(const std::string& line) { /* boost::split(..
 
 extern "C" {
 
-int fdb_sdm_file_load(const char* path, fdb_sdm_file** out) {
+int fdb_sdm_file_load(const char* path, fdb_sdm_file** out) try {
 	if (!path || !out) return fail(FDB_ERR_INVALID_ARGUMENT, "null argument");
 	*out = nullptr;
 	std::ifstream file(path);
@@ -197,7 +195,7 @@ int fdb_sdm_file_load(const char* path, fdb_sdm_file** out) {
 	}
 	*out = f;
 	return FDB_OK;
-}
+} FDB_API_CATCH
 
 const fdb_sdm_desc* fdb_sdm_file_desc(const fdb_sdm_file* f) { return f ? &f->desc : nullptr; }
 void fdb_sdm_file_free(fdb_sdm_file* f) { delete f; }
@@ -255,7 +253,7 @@ int load_posterior(const char* path, const char* var, bool required, double* A, 
 
 extern "C" {
 
-int fdb_wvm_file_load(const char* classifier_path, const char* thresholds_path, fdb_wvm_file** out) {
+int fdb_wvm_file_load(const char* classifier_path, const char* thresholds_path, fdb_wvm_file** out) try {
 	if (!classifier_path || !thresholds_path || !out) return fail(FDB_ERR_INVALID_ARGUMENT, "null argument");
 	*out = nullptr;
 	MatFile mf; std::string err;
@@ -283,6 +281,8 @@ int fdb_wvm_file_load(const char* classifier_path, const char* thresholds_path, 
 		if (!a) return fail(FDB_ERR_RUNTIME, "WvmClassifier: Unable to find the matrix 'weight_hk" + idx + "' (the reference would continue with uninitialised weights)");
 		if (dim1(*a) != i + 1 && dim0(*a) != i + 1)
 			return fail(FDB_ERR_RUNTIME, "WvmClassifier: The matrix weight_hk" + idx + " in the classifier file should have a dimensions 1x" + idx + " or " + idx + "x1");
+		if (a->real.size() < (size_t)i + 1) /* right dims, but a cell / struct / sparse / empty array: no numeric data to read */
+			return fail(FDB_ERR_RUNTIME, "WvmClassifier: The matrix weight_hk" + idx + " in the classifier file is not a numeric array of " + idx + " elements");
 		for (int j = 0; j <= i; ++j) f->hk_weights[(size_t)i * (i + 1) / 2 + j] = (float)a->real[j];
 	}
 	a = mat_var(mf, "param_nonlin1_rvm");
@@ -357,7 +357,7 @@ int fdb_wvm_file_load(const char* classifier_path, const char* thresholds_path, 
 	d.area_rec = f->area_rec.data();
 	*out = f.release();
 	return FDB_OK;
-}
+} FDB_API_CATCH
 
 const fdb_wvm_desc* fdb_wvm_file_desc(const fdb_wvm_file* f) { return f ? &f->desc : nullptr; }
 void fdb_wvm_file_free(fdb_wvm_file* f) { delete f; }
@@ -366,7 +366,7 @@ void fdb_wvm_file_free(fdb_wvm_file* f) { delete f; }
  * (ProbabilisticRvmClassifier.cpp:92-125): num_hk, param_nonlin1_rvm | param_nonlin1 {bias, kernel type, basis parameter
  * (/ 65025), power, divisor}, support_hk%d as CV_32F vectors in row-major order (no grey-value scaling), weight_hk%d (i + 1
  * coefficients of level i), hierar_thresh and posterior_wrvm = {B, A} from the thresholds file; setNumFiltersToUse(num_hk). */
-int fdb_rvm_file_load(const char* classifier_path, const char* thresholds_path, fdb_rvm_file** out) {
+int fdb_rvm_file_load(const char* classifier_path, const char* thresholds_path, fdb_rvm_file** out) try {
 	if (!classifier_path || !thresholds_path || !out) return fail(FDB_ERR_INVALID_ARGUMENT, "null argument");
 	*out = nullptr;
 	MatFile mf; std::string err;
@@ -415,6 +415,8 @@ int fdb_rvm_file_load(const char* classifier_path, const char* thresholds_path, 
 		if (a) { /* a missing weight_hk is skipped by the reference and caught by the size check at the end */
 			if (dim1(*a) != i + 1 && dim0(*a) != i + 1)
 				return fail(FDB_ERR_RUNTIME, "RvmClassifier: The matrix weight_hk" + idx + " in the classifier file should have a dimensions 1x" + idx + " or " + idx + "x1");
+			if (a->real.size() < (size_t)i + 1)
+				return fail(FDB_ERR_RUNTIME, "RvmClassifier: The matrix weight_hk" + idx + " in the classifier file is not a numeric array of " + idx + " elements");
 			for (int j = 0; j <= i; ++j) f->coefficients[(size_t)i * (i + 1) / 2 + j] = (float)a->real[j];
 			++n_weights;
 		}
@@ -437,13 +439,13 @@ int fdb_rvm_file_load(const char* classifier_path, const char* thresholds_path, 
 	d.hierarchical_thresholds = f->hierarchical_thresholds.data();
 	*out = f.release();
 	return FDB_OK;
-}
+} FDB_API_CATCH
 
 const fdb_rvm_desc* fdb_rvm_file_desc(const fdb_rvm_file* f) { return f ? &f->desc : nullptr; }
 
 void fdb_rvm_file_free(fdb_rvm_file* f) { delete f; }
 
-int fdb_svm_mat_load(const char* classifier_path, const char* logistic_path, fdb_svm_file** out) {
+int fdb_svm_mat_load(const char* classifier_path, const char* logistic_path, fdb_svm_file** out) try {
 	if (!classifier_path || !out) return fail(FDB_ERR_INVALID_ARGUMENT, "null argument");
 	*out = nullptr;
 	MatFile mf; std::string err;
@@ -469,6 +471,8 @@ int fdb_svm_mat_load(const char* classifier_path, const char* logistic_path, fdb
 	if (!a) return fail(FDB_ERR_RUNTIME, "SvmClassifier: There is a nonlinear SVM in the file, but the matrix support_nonlin1 is lacking.");
 	if (a->dims.size() != 3) return fail(FDB_ERR_RUNTIME, "SvmClassifier: The matrix support_nonlin1 in the file should have 3 dimensions.");
 	const int h = a->dims[0], w = a->dims[1], nsv = a->dims[2];
+	if (h < 1 || w < 1 || nsv < 1 || (int64_t)h * w > 96 * 1024 / 4 || a->real.size() / ((size_t)h * w) < (size_t)nsv)
+		return fail(FDB_ERR_RUNTIME, "SvmClassifier: The matrix support_nonlin1 is not a numeric h x w x n array (or a vector exceeds 24576 elements)");
 	f->sv_u8.resize((size_t)nsv * w * h);
 	size_t k = 0;
 	for (int sv = 0; sv < nsv; ++sv)
@@ -489,6 +493,6 @@ int fdb_svm_mat_load(const char* classifier_path, const char* logistic_path, fdb
 	}
 	*out = f.release();
 	return FDB_OK;
-}
+} FDB_API_CATCH
 
 } // extern "C"

@@ -715,7 +715,7 @@ int sdm_check_batch(const fdb_sdm* m, int W, int H, int n_frames, int64_t n_face
 
 extern "C" {
 
-int fdb_sdm_create(fdb_ctx* ctx, const fdb_sdm_desc* d, fdb_sdm** out) {
+int fdb_sdm_create(fdb_ctx* ctx, const fdb_sdm_desc* d, fdb_sdm** out) try {
 	if (!out) return fail(FDB_ERR_INVALID_ARGUMENT, "out is null");
 	*out = nullptr;
 	int s = check_ctx(ctx); if (s) return s;
@@ -739,7 +739,7 @@ int fdb_sdm_create(fdb_ctx* ctx, const fdb_sdm_desc* d, fdb_sdm** out) {
 	for (cudaStream_t& t : m->chunk_stream) if (cudaStreamCreateWithFlags(&t, cudaStreamNonBlocking) != cudaSuccess) { fdb_sdm_destroy(m); return fail(FDB_ERR_CUDA, "cudaStreamCreate"); }
 	*out = m;
 	return FDB_OK;
-}
+} FDB_API_CATCH
 
 void fdb_sdm_destroy(fdb_sdm* m) {
 	if (!m) return;
@@ -756,7 +756,7 @@ void fdb_sdm_destroy(fdb_sdm* m) {
 int32_t fdb_sdm_num_landmarks(const fdb_sdm* m) { return m ? m->dev.L : 0; }
 int32_t fdb_sdm_num_cascade_steps(const fdb_sdm* m) { return m ? m->dev.steps : 0; }
 
-int fdb_sdm_align_rigid(const fdb_sdm* m, const int32_t* boxes, int64_t n_faces, float* shapes_out) {
+int fdb_sdm_align_rigid(const fdb_sdm* m, const int32_t* boxes, int64_t n_faces, float* shapes_out) try {
 	if (!m || !boxes || !shapes_out) return fail(FDB_ERR_INVALID_ARGUMENT, "null argument");
 	const int L = m->dev.L;
 	/* SdmLandmarkModel.hpp:156-192 with modelShape = mean. The source line `(xCoords + 0.5f) * faceBox.width + faceBox.x` is a
@@ -773,10 +773,10 @@ int fdb_sdm_align_rigid(const fdb_sdm* m, const int32_t* boxes, int64_t n_faces,
 		}
 	}
 	return FDB_OK;
-}
+} FDB_API_CATCH
 
 int fdb_sdm_optimize_batch_device(fdb_sdm* m, const uint8_t* frames, int32_t W, int32_t H, int32_t n_frames, const int32_t* face_frame,
-		int64_t n_faces, float* shapes, int32_t* status) {
+		int64_t n_faces, float* shapes, int32_t* status) try {
 	int s = sdm_check_batch(m, W, H, n_frames, n_faces); if (s) return s;
 	if (!frames || !shapes) return fail(FDB_ERR_INVALID_ARGUMENT, "null argument");
 	if (!face_frame && n_faces > n_frames) return fail(FDB_ERR_INVALID_ARGUMENT, "face_frame is null but there are more faces than frames");
@@ -791,10 +791,10 @@ int fdb_sdm_optimize_batch_device(fdb_sdm* m, const uint8_t* frames, int32_t W, 
 		face_frame = m->d_face_frame;
 	}
 	return sdm_run(m, frames, W, H, face_frame, n_faces, shapes, status, nullptr, nullptr);
-}
+} FDB_API_CATCH
 
 int fdb_sdm_profile_device(fdb_sdm* m, const uint8_t* frames, int32_t W, int32_t H, int32_t n_frames, const int32_t* face_frame,
-		int64_t n_faces, float* shapes, int32_t* status, double ms_out[4]) {
+		int64_t n_faces, float* shapes, int32_t* status, double ms_out[4]) try {
 	int s = sdm_check_batch(m, W, H, n_frames, n_faces); if (s) return s;
 	if (!frames || !shapes || !face_frame || !ms_out) return fail(FDB_ERR_INVALID_ARGUMENT, "null argument");
 	s = check_ctx(m->ctx); if (s) return s;
@@ -809,10 +809,10 @@ int fdb_sdm_profile_device(fdb_sdm* m, const uint8_t* frames, int32_t W, int32_t
 			ms_out[j] += ms; ms_out[3] += ms;
 		}
 	return FDB_OK;
-}
+} FDB_API_CATCH
 
 int fdb_sdm_optimize_batch(fdb_sdm* m, const uint8_t* frames, int64_t pitch, int32_t W, int32_t H, int32_t n_frames, const int32_t* face_frame,
-		int64_t n_faces, float* shapes, int32_t* status_out, float* features_out) {
+		int64_t n_faces, float* shapes, int32_t* status_out, float* features_out) try {
 	int s = sdm_check_batch(m, W, H, n_frames, n_faces); if (s) return s;
 	if (!frames || !shapes || pitch < W) return fail(FDB_ERR_INVALID_ARGUMENT, "null argument or pitch < width");
 	if (!face_frame && n_faces > n_frames) return fail(FDB_ERR_INVALID_ARGUMENT, "face_frame is null but there are more faces than frames");
@@ -886,10 +886,10 @@ int fdb_sdm_optimize_batch(fdb_sdm* m, const uint8_t* frames, int64_t pitch, int
 		if (status_out) status_out[order[(size_t)k]] = hstatus[(size_t)k];
 	}
 	return FDB_OK;
-}
+} FDB_API_CATCH
 
 int fdb_sdm_descriptors(fdb_sdm* m, const uint8_t* frame, int64_t pitch, int32_t W, int32_t H, const float* pts, int32_t n_points,
-		int32_t window_half, float* out) {
+		int32_t window_half, float* out) try {
 	if (!m || !frame || !pts || !out || W < 1 || H < 1 || pitch < W || n_points < 0) return fail(FDB_ERR_INVALID_ARGUMENT, "bad argument");
 	int s = check_ctx(m->ctx); if (s) return s;
 	if (n_points == 0) return FDB_OK;
@@ -914,6 +914,6 @@ int fdb_sdm_descriptors(fdb_sdm* m, const uint8_t* frame, int64_t pitch, int32_t
 	CUDA_TRY(cudaGetLastError());
 	for (int v : status) if (v) return fail(FDB_ERR_RUNTIME, "VlHogDescriptorExtractor::getDescriptors: region of interest outside the image");
 	return FDB_OK;
-}
+} FDB_API_CATCH
 
 } // extern "C"

@@ -495,6 +495,9 @@ def load_svm_mat(classifier_path, logistic_path=None):
         d = lib.fdb_svm_file_desc(f).contents
         sv = np.ctypeslib.as_array(C.cast(d.support_vectors, C.POINTER(C.c_uint8)), shape=(d.num_sv, d.dim)).copy()
         coef = np.ctypeslib.as_array(d.coefficients, shape=(d.num_sv,)).copy()
-        return SvmModel(sv, coef, d.gamma, bias=d.bias, threshold=d.threshold, logistic_a=d.logistic_a, logistic_b=d.logistic_b)
+        kernel = {capi.FDB_KERNEL_RBF: "rbf", capi.FDB_KERNEL_POLYNOMIAL: "polynomial", capi.FDB_KERNEL_HIK: "hik",
+                  capi.FDB_KERNEL_LINEAR: "linear"}[d.kernel]
+        return SvmModel(sv, coef, d.gamma, bias=d.bias, threshold=d.threshold, logistic_a=d.logistic_a, logistic_b=d.logistic_b,
+                        kernel=kernel, alpha=d.poly_alpha, constant=d.poly_constant, degree=d.poly_degree)
     finally:
         lib.fdb_svm_file_free(f)

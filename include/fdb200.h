@@ -316,7 +316,12 @@ FDB_API int fdb_svm_get_probability(fdb_svm* svm, const void* vectors_host, int6
 /* 1 when the SVM has a tensor-core form (csrc/svm_dense.cu: u8 support vectors, RBF kernel, gamma and dimension within
  * the shared-memory budget): batches of >= 128 vectors in fdb_svm_get_probability and the `single` detector then
  * evaluate windows x support vectors as one exact u8 matrix product (tcgen05.mma kind::i8) with a float64 epilogue.
- * Same loop as above (SvmClassifier.cpp:55-60, RbfKernel.hpp:32-40); distances agree with it to ~1e-13. */
+ * Same loop as above (SvmClassifier.cpp:55-60, RbfKernel.hpp:32-40); distances agree with it to ~1e-13.
+ * CONSEQUENCE: the same feature vector may get distances ~1e-12 apart depending on the batch size (the tensor-core
+ * kernel sums the support vectors in a different order than the per-window kernel, which follows the reference's order),
+ * so a `distance >= threshold` result can differ for a distance within ~1e-12 of the threshold. Everything else in the
+ * library is bit-exact against the reference. Setting the environment variable FDB_SVM_DENSE=0 before the library is
+ * loaded forces the reference-order kernel everywhere. */
 FDB_API int fdb_svm_has_dense(const fdb_svm* svm);
 
 /* RvmClassifier / ProbabilisticRvmClassifier. The cascade is evaluated the way the reference's live code path does

@@ -138,11 +138,10 @@ def test_score_map_arithmetic_equals_the_oracle_restatement(emu):
     assert checked >= 3
 
 
-@pytest.mark.gpu_unverified
-@pytest.mark.skipif(os.environ.get("FDB_RUN_UNVERIFIED") != "1", reason="fhog.cu has not run on a B200 yet: set FDB_RUN_UNVERIFIED=1 on a GPU box")
+@pytest.mark.gpu
 @pytest.mark.parametrize("cell,bins,ib,ic,alpha", [(4, 9, True, True, 0.2), (8, 9, False, False, 0.2)])
 def test_fdb_fhog_on_the_gpu(cell, bins, ib, ic, alpha):
-    """first thing to run next round: fdb_fhog (the kernels) against the oracle, bit for bit"""
+    """fdb_fhog (the kernels) against the oracle, bit for bit (first run on a B200: round 2, gpurun_out/r2a_fhog.log)"""
     from oracle import fdoracle as fo
     from featuredetection_b200 import capi
     from featuredetection_b200.detector import Context
@@ -158,8 +157,7 @@ def test_fdb_fhog_on_the_gpu(cell, bins, ib, ic, alpha):
         assert np.array_equal(got, want)
 
 
-@pytest.mark.gpu_unverified
-@pytest.mark.skipif(os.environ.get("FDB_RUN_UNVERIFIED") != "1", reason="fhog.cu has not run on a B200 yet: set FDB_RUN_UNVERIFIED=1 on a GPU box")
+@pytest.mark.gpu
 def test_fdb_fhog_score_map_on_the_gpu():
     from oracle import fdoracle as fo
     from featuredetection_b200 import capi

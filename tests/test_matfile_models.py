@@ -185,3 +185,45 @@ def test_rvm_mat_reader(built, tmp_path, kernel_type):
     sio.savemat(cpath, d, format="5")
     assert lib.fdb_rvm_file_load(cpath.encode(), tpath.encode(), C.byref(f)) != 0
     assert b"Could not find kernel parameters" in lib.fdb_last_error()
+
+
+def test_malformed_files_fail_cleanly(built, tmp_path):
+    """variables with the expected DIMENSIONS but no numeric data (cell arrays), sizes from the file that would size a huge
+    allocation: every loader returns a status, nothing reads out of bounds and no C++ exception crosses the C ABI"""
+    lib = capi.load_library()
+    f = C.c_void_p()
+    m = syn.make_wvm(20, 20, 2, 2, 0.04, seed=8)
+    cpath, tpath = str(tmp_path / "wvm.mat"), str(tmp_path / "thr.mat")
+    written = write_wvm_mat(m, cpath, tpath, False)
+    cell = np.empty((1, 1), dtype=object)
+    cell[0, 0] = np.array([[1.0]])
+    bad = dict(written)
+    bad["weight_hk1"] = cell                       # 1x1 cell: right dims, real data empty
+    sio.savemat(cpath, bad, format="5")
+    assert lib.fdb_wvm_file_load(cpath.encode(), tpath.encode(), C.byref(f)) == capi.FDB_ERR_RUNTIME
+    assert b"weight_hk1" in lib.fdb_last_error()
+    # RVM: the same pattern
+    rng = np.random.default_rng(1)
+    d = {"num_hk": np.array([[2.0]]), "param_nonlin1_rvm": np.array([[0.5, 2.0, 0.04, 3.0, 2.0]]),
+         "support_hk1": rng.uniform(0, 1, (4, 4)), "support_hk2": rng.uniform(0, 1, (4, 4)),
+         "weight_hk1": cell, "weight_hk2": np.array([[1.0, 2.0]])}
+    rpath = str(tmp_path / "rvm.mat")
+    sio.savemat(rpath, d, format="5")
+    assert lib.fdb_rvm_file_load(rpath.encode(), tpath.encode(), C.byref(f)) == capi.FDB_ERR_RUNTIME
+    # SVM: a 3-D cell array as support_nonlin1
+    cell3 = np.empty((2, 2, 2), dtype=object)
+    for idx in np.ndindex(2, 2, 2):
+        cell3[idx] = np.array([[0.5]])
+    spath = str(tmp_path / "svm.mat")
+    sio.savemat(spath, {"param_nonlin1": np.array([[0.75, 2.0, 0.05, 0.0, 1.0]]), "support_nonlin1": cell3,
+                        "weight_nonlin1": np.array([[1.0, 2.0]])}, format="5")
+    assert lib.fdb_svm_mat_load(spath.encode(), None, C.byref(f)) == capi.FDB_ERR_RUNTIME
+    assert b"support_nonlin1" in lib.fdb_last_error()
+    # text container: sizes that would ask for 8e18 elements, and a truncated vector block
+    tpath2 = str(tmp_path / "svm.txt")
+    with open(tpath2, "w") as fh:
+        fh.write("Kernel RBF 0.5\nBias 0.1\nCoefficients 2 1.0 2.0\nSupportVectors 2 2000000000 2000000000 1 0\n")
+    assert lib.fdb_svm_file_load(tpath2.encode(), C.byref(f)) == capi.FDB_ERR_RUNTIME
+    with open(tpath2, "w") as fh:
+        fh.write("Kernel RBF 0.5\nBias 0.1\nCoefficients 2 1.0 2.0\nSupportVectors 2 1 4 1 5\n1 2 3 4 5 6\n")
+    assert lib.fdb_svm_file_load(tpath2.encode(), C.byref(f)) == capi.FDB_ERR_RUNTIME
