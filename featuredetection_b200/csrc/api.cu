@@ -23,6 +23,7 @@
 #include "wvm_device.h"
 #include "api_types.h"
 #include "features_device.h"
+#include "wvm_group.h"
 
 namespace fdb {
 
@@ -82,7 +83,7 @@ int fdb_ctx_create(int device, fdb_ctx** out) try {
 	c->device = device;
 	CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
 	for (cudaEvent_t& e : c->ev) CUDA_TRY(cudaEventCreate(&e));
-	if (wvm_configure() != 0 || svm_configure() != 0 || svm_dense_configure() != 0 || strip_configure_all() != 0 || strip_mma_configure_all() != 0 || feature_configure() != 0) {
+	if (wvm_configure() != 0 || svm_configure() != 0 || svm_dense_configure() != 0 || group_configure_all() != 0 || feature_configure() != 0) {
 		cudaStreamDestroy(c->stream); delete c;
 		return fail(FDB_ERR_CUDA, "cudaFuncSetAttribute failed: libfdb200 kernels not loadable on this device");
 	}
@@ -228,47 +229,43 @@ int fdb_wvm_create(fdb_ctx* ctx, const fdb_wvm_desc* d, fdb_wvm** out) try {
 		dv.rects = rp;
 		UP(roff.data(), n + 1, rect_off, ip);
 	}
-	{ /* weight rows padded to 16 bytes for the deep kernel's float4 loads */
-		std::vector<int> row4(n);
-		std::vector<float> w4;
-		size_t tri = 0;
-		for (int l = 0; l < n; ++l) {
-			row4[l] = (int)w4.size();
-			for (int p = 0; p <= l; ++p) w4.push_back(d->hk_weights[tri + p]);
-			while (w4.size() % 4) w4.push_back(0.f);
-			tri += (size_t)l + 1;
-		}
-		UP(w4.data(), w4.size(), hk_weights4, fp);
-		UP(row4.data(), n, hk_row4, ip);
-	}
-	dv.masks4 = nullptr;
 	dv.bfrag = nullptr;
-	if (max_nv <= 4) { /* padded copy for the strip / deep-warp kernels: [filter][word][4] */
-		std::vector<uint32_t> m4((size_t)n * nwords * 4, 0u);
-		for (int f = 0; f < n; ++f) {
-			const int nv = d->area_cntval[f] - 1;
-			for (int j = 0; j < nwords; ++j)
-				for (int v = 0; v < nv; ++v) m4[((size_t)f * nwords + j) * 4 + v] = masks[(size_t)mask_off[f] + (size_t)j * nv + v];
+	dv.hk_weights_t = nullptr; dv.hk_t_off = nullptr;
+	if (max_nv <= 4 && n > WVM_KA && group_supported(w, h)) {
+		/* rectangle coverage counts of the first WVM_KA filters in mma.m16n8k32 B-fragment order (wvm_group.cu): k-step s is
+		 * patch row s padded to 8 words (16-wide windows: rows 2 s and 2 s + 1); lane (g, t) holds, for n-tile nt, the words
+		 * 4 h + t of that row (16-wide: word t of row 2 s + h), h = 0, 1, of filter 2 nt + (g >> 2), grey value g & 3 */
+		const int wpr = w / 4, rpk = w <= 16 ? 2 : 1, ks = h / rpk;
+		std::vector<uint32_t> bf((size_t)ks * 32 * 8, 0u);
+		for (int s2 = 0; s2 < ks; ++s2)
+			for (int lane = 0; lane < 32; ++lane)
+				for (int nt = 0; nt < 4; ++nt)
+					for (int hh = 0; hh < 2; ++hh) {
+						const int g = lane >> 2, t = lane & 3;
+						const int f = 2 * nt + (g >> 2), v = g & 3;
+						const int row = rpk == 2 ? 2 * s2 + hh : s2, c4 = rpk == 2 ? t : 4 * hh + t;
+						const int nv = d->area_cntval[f] - 1;
+						if (c4 < wpr && v < nv)
+							bf[((size_t)s2 * 32 + lane) * 8 + nt * 2 + hh] = masks[(size_t)mask_off[f] + (size_t)(row * wpr + c4) * nv + v];
+					}
+		uint32_t* bp;
+		s = upload(bf.data(), bf.size(), &bp, m->owned); if (s) { free_all(m->owned); delete m; return s; }
+		dv.bfrag = reinterpret_cast<const uint4*>(bp);
+		/* weights of the deep kernel's rounds, transposed for coalesced loads; one zero group of padding per round (prefetch) */
+		std::vector<float> wt;
+		std::vector<int> toff;
+		for (int base = WVM_KA; base < n; base += 32) {
+			toff.push_back((int)(wt.size() / 4));
+			const int cnt = std::min(32, n - base), groups = (base + cnt + 3) / 4 + 1;
+			const size_t at = wt.size();
+			wt.resize(at + (size_t)groups * 32 * 4, 0.f);
+			for (int lane = 0; lane < cnt; ++lane) {
+				const int l = base + lane;
+				for (int p = 0; p <= l; ++p) wt[at + ((size_t)(p / 4) * 32 + lane) * 4 + (p & 3)] = d->hk_weights[(size_t)l * (l + 1) / 2 + p];
+			}
 		}
-		UP(m4.data(), m4.size(), masks4, up);
-		/* the same masks of the first WVM_KA filters in mma.m16n8k32 B-fragment order (wvm_strip_mma.cu): lane (g, t)
-		 * of k-step s holds, for n-tile nt, the words j = 8 s + t and j + 4 of filter 2 nt + (g >> 2), value g & 3 */
-		dv.bfrag = nullptr;
-		if (n >= WVM_KA) {
-			const int ks = (nwords + 7) / 8;
-			std::vector<uint32_t> bf((size_t)ks * 32 * 8, 0u);
-			for (int s2 = 0; s2 < ks; ++s2)
-				for (int lane = 0; lane < 32; ++lane)
-					for (int nt = 0; nt < 4; ++nt)
-						for (int h = 0; h < 2; ++h) {
-							const int g = lane >> 2, t = lane & 3;
-							const int f = 2 * nt + (g >> 2), v = g & 3, j = 8 * s2 + 4 * h + t;
-							if (j < nwords) bf[((size_t)s2 * 32 + lane) * 8 + nt * 2 + h] = m4[((size_t)f * nwords + j) * 4 + v];
-						}
-			uint32_t* bp;
-			s = upload(bf.data(), bf.size(), &bp, m->owned); if (s) { free_all(m->owned); delete m; return s; }
-			dv.bfrag = reinterpret_cast<const uint4*>(bp);
-		}
+		UP(wt.data(), wt.size(), hk_weights_t, fp);
+		UP(toff.data(), toff.size(), hk_t_off, ip);
 	}
 #undef UP
 	s = dev_alloc(&m->d_thresholds, (size_t)n, m->owned);

@@ -32,6 +32,7 @@
 #include "wvm_device.h"
 #include "api_types.h"
 #include "features_device.h"
+#include "wvm_group.h"
 
 using namespace fdb;
 
@@ -90,7 +91,8 @@ struct fdb_detector {
 	ResizeJob* d_resize = nullptr; int n_resize = 0; int max_quads = 0;
 	std::vector<DownJob*> d_down; std::vector<int> n_down; std::vector<int> max_down_px;
 	int4* d_xy_tab = nullptr; /* bilinear tables: {source offset, a0, a1, 0} */
-	Strip* d_strips = nullptr; int n_strips = 0;
+	GroupItem* d_gitems = nullptr; int n_gitems = 0; /* strips of the whole-image scan (group kernel work items, one model) */
+	GroupImage* d_gimages = nullptr;                 /* image table of the group kernels: entry li = image of layer li */
 	bool use_tma = false;             /* strip tiles staged by TMA (tensor maps encoded) */
 	bool use_strips = false;          /* fast path usable (and not yet overflowed) */
 	bool has_feature = false;         /* the SVM works in its own feature space (fdb_detector_set_feature) */
@@ -129,6 +131,34 @@ void linear_tables(int src, int dst, bool clamp_fraction, std::vector<int>& ofs,
 		c.x = (short)std::nearbyint((1.f - f) * 2048.f);
 		c.y = (short)std::nearbyint(f * 2048.f);
 		coef.push_back(c);
+	}
+}
+
+/* work items of the group kernel for one layer: strips of <= 32 window columns; narrow layers pack several row runs side
+ * by side (all 32 lanes busy), the runs share the tile's rows. Balanced run length: the same number of window rows for
+ * every lane of the layer. One item per strip and pack of <= GRP_MAX_PACK models. */
+void append_strip_items(const PlanLayer& L, int image, int patch_h, int n_models, const int* models, const int* first_windows,
+		std::vector<GroupItem>* out) {
+	if (L.windows_x <= 0 || L.windows_y <= 0) return;
+	const int budget = STRIP_TILE_ROWS - (patch_h - 1); /* window rows per tile */
+	for (int m0 = 0; m0 < n_models; m0 += GRP_MAX_PACK) {
+		const int nm = std::min(GRP_MAX_PACK, n_models - m0);
+		for (int ix0 = 0; ix0 < L.windows_x; ix0 += 32) {
+			const int cols = std::min(32, L.windows_x - ix0);
+			const int nsub = std::min(WVM_MAXSUB, 32 / cols);
+			const int run_cap = std::max(1, std::min(WVM_RUN, budget / nsub));
+			const int nruns = (L.windows_y + run_cap - 1) / run_cap;
+			const int run = (L.windows_y + nruns - 1) / nruns;
+			for (int iy0 = 0; iy0 < L.windows_y; iy0 += nsub * run) {
+				GroupItem it{};
+				it.image = image; it.begin_x = L.begin_x; it.begin_y = L.begin_y; it.windows_x = L.windows_x; it.windows_y = L.windows_y;
+				it.ix0 = ix0; it.iy0 = iy0; it.cols = cols; it.run = run;
+				it.nsub = std::min(nsub, (L.windows_y - iy0 + run - 1) / run);
+				it.nm = nm;
+				for (int k = 0; k < nm; ++k) { it.model[k] = models[m0 + k]; it.first_window[k] = first_windows[m0 + k]; }
+				out->push_back(it);
+			}
+		}
 	}
 }
 
@@ -174,9 +204,21 @@ int enqueue_stage1(fdb_detector* det, Slot& sl, cudaStream_t st, const uint8_t* 
 		DevWvm m = det->wvm->dev;
 		m.step_x = det->desc.step_x; m.step_y = det->desc.step_y;
 		if (det->use_strips && d_layers == det->d_layers && !d_patches) {
-			launch_wvm_strips(st, m, d_frames, W, H, n, sl.d_arena, plan.arena_bytes, d_layers, det->d_strips, det->n_strips,
-					(int)windows, d_dense, want_candidates ? sl.d_cand : nullptr, sl.d_counters, det->cand_cap, sl.deep,
-					marks ? c->ev[5] : nullptr, det->use_tma ? sl.d_tmaps : nullptr);
+			GroupModel gm{};
+			gm.m = m; gm.dense = d_dense; gm.windows_per_frame = (int)windows; gm.cand_cap = det->cand_cap;
+			gm.cand = want_candidates ? sl.d_cand : nullptr; gm.cand_count = sl.d_counters; gm.q = sl.deep;
+			GroupArgs ga{};
+			ga.items = det->d_gitems; ga.n_items = det->n_gitems; ga.n_frames = n;
+			ga.images = det->d_gimages; ga.tmaps = det->use_tma ? sl.d_tmaps : nullptr;
+			ga.frames = d_frames; ga.W = W; ga.H = H; ga.arena = sl.d_arena; ga.arena_stride = plan.arena_bytes;
+			ga.cursor = sl.d_counters + 3;
+			ga.models[0] = gm;
+			launch_wvm_group(st, det->desc.patch_width, det->desc.patch_height, 1, ga);
+			if (marks) CUDA_TRY(cudaEventRecord(c->ev[5], st)); /* profiling mark between the two kernels */
+			DeepArgs da{};
+			da.images = det->d_gimages; da.frames = d_frames; da.W = W; da.H = H; da.arena = sl.d_arena; da.arena_stride = plan.arena_bytes;
+			da.n_models = 1; da.models[0] = gm;
+			launch_wvm_deep_group(st, da);
 		} else {
 			if (marks) CUDA_TRY(cudaEventRecord(c->ev[5], st)); /* generic path: no separate deep mark */
 			launch_wvm_windows(st, m, d_frames, W, H, n, sl.d_arena, plan.arena_bytes, d_layers, (int)plan.layers.size(),
@@ -899,7 +941,7 @@ int fdb_detector_prepare(fdb_detector* det, int32_t width, int32_t height, int32
 		void* fn = nullptr;
 		cudaDriverEntryPointQueryResult qres = cudaDriverEntryPointSymbolNotFound;
 		const char* env = std::getenv("FDB_NO_TMA");
-		if (!(env && env[0] == '1') && strip_supported(det->desc.patch_width, det->desc.patch_height)
+		if (!(env && env[0] == '1') && group_supported(det->desc.patch_width, det->desc.patch_height)
 				&& cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess
 				&& qres == cudaDriverEntryPointSuccess && fn) {
 			bool ok = true;
@@ -912,7 +954,7 @@ int fdb_detector_prepare(fdb_detector* det, int32_t width, int32_t height, int32
 					if (im.offset < 0) continue; /* the frame itself: plain loads */
 					const cuuint64_t dims[3] = {(cuuint64_t)im.width, (cuuint64_t)im.height, (cuuint64_t)det->chunk};
 					const cuuint64_t strides[2] = {(cuuint64_t)im.pitch, (cuuint64_t)plan.arena_bytes};
-					const cuuint32_t box[3] = {(cuuint32_t)strip_tile_pitch(), (cuuint32_t)strip_tile_rows(det->desc.patch_height), 1};
+					const cuuint32_t box[3] = {STRIP_TILE_PITCH, STRIP_TILE_ROWS, 1};
 					const cuuint32_t estr[3] = {1, 1, 1};
 					ok = reinterpret_cast<EncodeFn>(fn)(&maps[li], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, sl.d_arena + im.offset,
 							dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
@@ -926,35 +968,25 @@ int fdb_detector_prepare(fdb_detector* det, int32_t width, int32_t height, int32
 	s = dev_alloc(&det->d_layers, FDB_MAX_LAYERS, det->owned); if (s) return s;
 	s = dev_alloc(&det->d_layers_roi, FDB_MAX_LAYERS, det->owned); if (s) return s;
 	s = upload_layers(det, plan, det->d_layers, det->ctx->stream); if (s) return s;
-	/* strip table of the fast path: whole-image scan, step 1, supported patch size, <= 4 grey values, <= 256 words */
-	det->use_strips = det->wvm && det->desc.step_x == 1 && det->desc.step_y == 1 && det->wvm->dev.masks4 != nullptr
-			&& strip_supported(det->desc.patch_width, det->desc.patch_height) && det->wvm->dev.num_lin > WVM_KA
+	/* work items of the fast path: whole-image scan, step 1, supported window size, <= 4 grey values per filter */
+	det->use_strips = det->wvm && det->desc.step_x == 1 && det->desc.step_y == 1 && det->wvm->dev.bfrag != nullptr
+			&& group_supported(det->desc.patch_width, det->desc.patch_height) && det->wvm->dev.num_lin > WVM_KA
 			&& det->wvm->dev.num_used > WVM_KA;
-	std::vector<Strip> strips;
-	if (det->use_strips) {
-		for (size_t li = 0; li < plan.layers.size(); ++li) {
-			const PlanLayer& L = plan.layers[li];
-			if (L.windows_x == 0) continue;
-			const int budget = strip_tile_rows(det->desc.patch_height) - (det->desc.patch_height - 1); /* window rows per tile */
-			for (int ix0 = 0; ix0 < L.windows_x; ix0 += 32) {
-				const int cols = std::min(32, L.windows_x - ix0);
-				/* narrow layers pack several row runs side by side (all 32 lanes busy); the runs share the tile's rows.
-				 * Balanced run length: the same number of window rows for every lane of the layer */
-				const int nsub = std::min(WVM_MAXSUB, 32 / cols);
-				const int run_cap = std::max(1, std::min(WVM_RUN, budget / nsub));
-				const int nruns = (L.windows_y + run_cap - 1) / run_cap;
-				const int run = (L.windows_y + nruns - 1) / nruns;
-				for (int iy0 = 0; iy0 < L.windows_y; iy0 += nsub * run) {
-					Strip st{};
-					st.layer = (int)li; st.ix0 = ix0; st.iy0 = iy0; st.cols = cols; st.run = run;
-					st.nsub = std::min(nsub, (L.windows_y - iy0 + run - 1) / run);
-					strips.push_back(st);
-				}
-			}
-		}
+	std::vector<GroupItem> items;
+	std::vector<GroupImage> gimages(plan.layers.size());
+	for (size_t li = 0; li < plan.layers.size(); ++li) {
+		const PyrImage& im = plan.images[plan.layers[li].image];
+		gimages[li].offset = im.offset; gimages[li].width = im.width; gimages[li].height = im.height; gimages[li].pitch = im.pitch;
+		gimages[li].tma_ok = det->use_tma && im.offset >= 0 ? 1 : 0;
 	}
-	det->n_strips = (int)strips.size();
-	s = upload(strips.data(), strips.size(), &det->d_strips, det->owned); if (s) return s;
+	if (det->use_strips)
+		for (size_t li = 0; li < plan.layers.size(); ++li) {
+			const int model0 = 0, first = (int)plan.layers[li].first_window;
+			append_strip_items(plan.layers[li], (int)li, det->desc.patch_height, 1, &model0, &first, &items);
+		}
+	det->n_gitems = (int)items.size();
+	s = upload(items.data(), items.size(), &det->d_gitems, det->owned); if (s) return s;
+	s = upload(gimages.data(), gimages.size(), &det->d_gimages, det->owned); if (s) return s;
 	det->d_all_items = nullptr; det->d_all_dist = nullptr; det->h_all_dist = nullptr; det->d_all_level = nullptr; det->h_all_level = nullptr;
 	if (!det->wvm) {
 		/* `single` detector: every window of a frame is an SVM work item, canonical order */

@@ -22,6 +22,7 @@ namespace fdb {
 /* a window that survived the first WVM_KA filters (state of WvmClassifier::computeHyperplaneDistance so far) */
 struct DeepRec {
 	int frame, window;
+	int image, x, y;   /* group path: pyramid image and window corner (the deep kernel re-equalises the window from the image) */
 	float total_f, sum_xx;
 	float hk[WVM_KA];
 	float u[WVM_KA];
@@ -50,27 +51,21 @@ struct DevWvm {
 	const double* val;              /* grey values */
 	const uint32_t* masks;          /* rectangle coverage counts, 4 pixels per word: filter f at mask_off[f], [nwords][cntval-1] */
 	const int* mask_off;            /* [num_lin] */
-	const uint4* bfrag;             /* masks of the first WVM_KA filters as mma.m16n8k32 B fragments: [k-step][lane][2] (wvm_strip_mma.cu); nullptr if unavailable */
-	const uint32_t* masks4;         /* same, padded to 4 values per word: [num_lin][nwords][4]; nullptr if a filter has > 4 */
-	const float* hk_weights4;       /* hkWeights rows padded to multiples of 4 floats (16-byte aligned rows) */
-	const int* hk_row4;             /* [num_lin] start of row l in hk_weights4 (floats) */
+	const uint4* bfrag;             /* masks of the first WVM_KA filters as mma.m16n8k32 B fragments: [k-step][lane][2], one k-step per
+	                                 * patch row padded to 32 bytes (two rows for 16-wide windows) - wvm_group.cu; nullptr if unavailable */
+	const float* hk_weights_t;      /* hkWeights of the deep kernel's rounds of 32 filters, transposed: round r at hk_t_off[r] (float4
+	                                 * units), [p / 4][lane][4] = w[WVM_KA + 32 r + lane][p .. p + 3] (0 beyond the triangle) */
+	const int* hk_t_off;
 	const uint2* rects;             /* rectangles of all filters: {x1 | y1 << 8 | x2 << 16 | y2 << 24, grey value index v - 1} */
 	const int* rect_off;            /* [num_lin + 1] first rectangle of filter l */
 };
 
-/* work item of wvm_strip_kernel: `cols` adjacent window columns x `nsub` runs of WVM_RUN window rows */
+/* strips of the window grid (wvm_group.cu): `cols` adjacent window columns x `nsub` runs of <= WVM_RUN window rows */
 #ifndef WVM_RUN
 #define WVM_RUN 12   /* longest run of window rows one lane walks down */
 #endif
 #define WVM_MAXSUB 4
-#define STRIP_TILE_ROWS 42 /* rows of a warp's bin tile: nsub * run + patch_h - 1 <= 42 (3 CTAs of 4 warps per SM) */
-struct Strip {
-	int layer;      /* index into the DevLayer table */
-	int ix0, iy0;   /* first window column / row of the strip */
-	int cols, nsub; /* cols * nsub <= 32 lanes */
-	int run;        /* window rows per lane (balanced over the layer, <= WVM_RUN) */
-	int pad[2];
-};
+#define STRIP_TILE_ROWS 42 /* rows of a warp's bin tile: nsub * run + patch_h - 1 <= 42 */
 
 /* SvmClassifier (RBF) state; support vectors transposed to [word][sv] for coalesced reads */
 struct DevSvm {
@@ -131,22 +126,8 @@ void launch_wvm_windows(cudaStream_t st, const DevWvm& m, const uint8_t* frames,
 		fdb_window_score* dense, uint8_t* patches_out, Candidate* cand, int* cand_count, int cand_cap, const DeepQueue& q);
 void launch_wvm_patches(cudaStream_t st, const DevWvm& m, const uint8_t* patches, int n, fdb_window_score* dense);
 
-/* fast path (wvm_strip.cu): whole-image scans with step 1 and one of the ffpDetectApp patch sizes */
-int strip_configure_all();
-int strip_mma_configure_all();
-int strip_mma_ksteps(int patch_w, int patch_h);
-bool launch_strip_mma(cudaStream_t st, const DevWvm& m, const uint8_t* frames, int W, int H, int n_frames,
-		const uint8_t* arena, int64_t arena_stride, const DevLayer* layers, const Strip* strips, int n_strips,
-		int windows_per_frame, fdb_window_score* dense, Candidate* cand, int* cand_count, int cand_cap, const DeepQueue& q,
-		const void* tmaps);
-bool strip_supported(int patch_w, int patch_h);
-void launch_wvm_strips(cudaStream_t st, const DevWvm& m, const uint8_t* frames, int W, int H, int n_frames,
-		const uint8_t* arena, int64_t arena_stride, const DevLayer* layers, const Strip* strips, int n_strips,
-		int windows_per_frame, fdb_window_score* dense, Candidate* cand, int* cand_count, int cand_cap, const DeepQueue& q,
-		cudaEvent_t ev_mid = nullptr, const void* tmaps = nullptr /* CUtensorMap[layer] of the slot's arena, or null */);
-int strip_tile_rows(int patch_h);
-int strip_tile_pitch();
-
+/* fast path (wvm_group.cu): whole-image scans with step 1 and one of the ffpDetectApp window sizes */
+#define STRIP_TILE_PITCH 64
 void launch_resize(cudaStream_t st, const uint8_t* frames, int W, int H, int n_frames, uint8_t* arena,
 		int64_t arena_stride, const ResizeJob* jobs_dev, int n_jobs, int max_tiles, const int4* xy_tab);
 int resize_tiles(int dst_w, int dst_h);
