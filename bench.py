@@ -558,7 +558,7 @@ def run_single(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
     from featuredetection_b200 import synthetic as syn, sharding
-    from featuredetection_b200.detector import Context, SlidingWindowCascade, DETECTION_DTYPE
+    from featuredetection_b200.detector import Context, SlidingWindowCascade, DetectorSet, DETECTION_DTYPE
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device - the B200 path has no CPU fallback (use --impl reference for the CPU arm)")
@@ -758,7 +758,7 @@ def main():
     import torch
     import torch.distributed as dist
     from featuredetection_b200 import capi, synthetic as syn, sharding
-    from featuredetection_b200.detector import Context, SlidingWindowCascade, DETECTION_DTYPE
+    from featuredetection_b200.detector import Context, SlidingWindowCascade, DetectorSet, DETECTION_DTYPE
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device - the B200 path has no CPU fallback (use --impl reference for the CPU arm)")
@@ -786,6 +786,10 @@ def main():
         c = SlidingWindowCascade(ctx, det_kw, wvm, svm, feature=fdesc)
         c.prepare(W, H, n)
         cascs.append(c)
+    dset = None
+    if len(cascs) > 1:  # all detectors of the application on every frame: one detector set (shared pyramids, shared equalisation)
+        dset = DetectorSet(ctx, cascs)
+        dset.prepare(W, H, n)
     nwin = sum(c.windows_per_frame for c in cascs)          # windows per frame over all detectors
     max_nwin = max(c.windows_per_frame for c in cascs)
     stage = capi.FDB_STAGE_NMS if args.profile == "realistic" else capi.FDB_STAGE_WVM
@@ -826,15 +830,24 @@ def main():
             finish_gather()
             pending[0] = ticket
 
+    dense_ptrs = None
+    if dset is not None:
+        dev_dense_all = [torch.empty((n, c.windows_per_frame, 2), dtype=torch.int32, device=device) for c in cascs]
+        dense_ptrs = [t.data_ptr() for t in dev_dense_all]
+
     def step_resident():
-        parts = [c.detect_device(dev_frames.data_ptr(), n, stage=stage, dense_ptr=dev_dense.data_ptr(), det_cap=det_cap) for c in cascs]
-        dets = np.concatenate(parts)
+        if dset is not None:
+            dets = dset.detect_device(dev_frames.data_ptr(), n, stage=stage, dense_ptrs=dense_ptrs, det_cap=det_cap * len(cascs))
+        else:
+            dets = cascs[0].detect_device(dev_frames.data_ptr(), n, stage=stage, dense_ptr=dev_dense.data_ptr(), det_cap=det_cap)
         exchange(dets)
         return dets
 
     def step_e2e():
-        parts = [c.detect(host_frames.numpy(), stage=stage, det_cap=det_cap) for c in cascs]
-        dets = np.concatenate(parts)
+        if dset is not None:
+            dets = dset.detect(host_frames.numpy(), stage=stage, det_cap=det_cap * len(cascs))
+        else:
+            dets = cascs[0].detect(host_frames.numpy(), stage=stage, det_cap=det_cap)
         exchange(dets)
         return dets
 
@@ -866,7 +879,8 @@ def main():
     prof = []
     for _ in range(max(args.steps, 5)):
         flush_l2()
-        prof.append(np.sum([c.profile_device(dev_frames.data_ptr(), n) for c in cascs], axis=0))
+        prof.append(np.array(dset.profile_device(dev_frames.data_ptr(), n)) if dset is not None
+                    else np.array(cascs[0].profile_device(dev_frames.data_ptr(), n)))
     prof = np.array(prof)
     ms_resize, ms_down, ms_wvm, ms_deep, ms_stage1, n_launch = prof.mean(axis=0)
 
@@ -919,7 +933,7 @@ def main():
             "config": workload_config(args, world),
             "frames_per_s": value / nwin,
             "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": "patches/s", "h2d_bytes_per_step": int(W * H * n * len(cascs)),
+            "e2e": {"value": e2e_value, "unit": "patches/s", "h2d_bytes_per_step": int(W * H * n * (1 if dset is not None else len(cascs))),
                     "d2h_bytes_per_step": int(len(dets_e2e) * DETECTION_DTYPE.itemsize + 4),
                     "ms_per_step": e2e_total / args.steps, "frames_per_s": e2e_value / nwin},
             "gpu_launches": int(launches),

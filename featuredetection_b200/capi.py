@@ -197,6 +197,16 @@ SYMBOLS = [
     ("fdb_detect_single_device", C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, _P(C.c_int64)]),
     ("fdb_detector_single_dense", C.c_int, [C.c_void_p]),
     ("fdb_detector_single_dense_profile", C.c_int, [C.c_void_p, _P(C.c_double), _P(C.c_int32)]),
+    ("fdb_detector_set_create", C.c_int, [C.c_void_p, _P(C.c_void_p), C.c_int32, _P(C.c_void_p)]),
+    ("fdb_detector_set_destroy", None, [C.c_void_p]),
+    ("fdb_detector_set_prepare", C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32]),
+    ("fdb_detector_set_windows_per_frame", C.c_int64, [C.c_void_p]),
+    ("fdb_detector_set_info", C.c_int, [C.c_void_p, _P(C.c_int32), _P(C.c_int64), _P(C.c_int32), _P(C.c_int32)]),
+    ("fdb_detector_set_detect_batch", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_int64,
+                                                _P(C.c_int64)]),
+    ("fdb_detector_set_detect_batch_device", C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, _P(C.c_void_p), C.c_void_p,
+                                                       C.c_int64, _P(C.c_int64)]),
+    ("fdb_detector_set_profile_device", C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, _P(C.c_double)]),
     ("fdb_sdm_create", C.c_int, [C.c_void_p, _P(SdmDesc), _P(C.c_void_p)]),
     ("fdb_sdm_destroy", None, [C.c_void_p]),
     ("fdb_sdm_num_landmarks", C.c_int32, [C.c_void_p]),

@@ -28,91 +28,11 @@
 #include <string>
 #include <vector>
 
-#include "fdb_internal.h"
-#include "wvm_device.h"
-#include "api_types.h"
-#include "features_device.h"
-#include "wvm_group.h"
+#include "detector_internal.h"
 
 using namespace fdb;
 
-#define PIPE_SLOTS 3
-#define OPT_CAND 4096 /* candidates fetched together with the counters (one D2H); more need a second copy */
-#define FEAT_BATCH 8192 /* feature vectors materialised at a time (feature-space SVM stage) */
-
-namespace {
-
-struct Slot {
-	cudaStream_t st = nullptr;
-	cudaEvent_t ev_stage1 = nullptr, ev_svm = nullptr;
-	uint8_t* d_frames = nullptr;
-	uint8_t* d_arena = nullptr;
-	CUtensorMap* d_tmaps = nullptr; /* one TMA descriptor per pyramid layer of this slot's arena (strip kernel) */
-	fdb_window_score* d_dense = nullptr;
-	int* d_counters = nullptr;     /* [0] candidates, [1] deep queue, [2] deep cursor; followed by the candidate list */
-	Candidate* d_cand = nullptr;   /* = (Candidate*)(d_counters + 4) */
-	DeepQueue deep{};
-	SvmItem* d_items = nullptr;
-	double* d_dist = nullptr;
-	uint8_t* d_farena = nullptr;   /* filtered pyramid layers of the chunk (feature spaces with layer filters) */
-	void* d_feat = nullptr;        /* FEAT_BATCH feature vectors */
-	int* h_counters = nullptr;     /* pinned mirror: 4 ints + OPT_CAND candidates */
-	Candidate* h_cand_big = nullptr; /* pinned, cand_cap entries (second copy when > OPT_CAND) */
-	SvmItem* h_items = nullptr;
-	double* h_dist = nullptr;
-	/* state of the chunk in flight */
-	int n = 0, base = 0;
-	const uint8_t* frames_dev = nullptr;
-	std::vector<std::vector<fdb_detection>> per_frame;
-	size_t svm_items = 0;
-	bool busy = false;
-};
-
-} // namespace
-
-struct fdb_detector {
-	fdb_ctx* ctx = nullptr;
-	fdb_detector_desc desc{};
-	fdb_wvm* wvm = nullptr;
-	fdb_svm* svm = nullptr;
-	Plan plan;
-	bool prepared = false;
-	uint8_t* d_bgr = nullptr;      /* fdb_detect_batch_bgr staging: interleaved frames and their gray conversion */
-	uint8_t* d_gray = nullptr;
-	int64_t bgr_cap_px = 0;
-	int max_batch = 0, chunk = 0, n_slots = 0;
-	int cand_cap = 0, items_cap = 0;
-	std::vector<void*> owned, owned_host;
-	Slot slots[PIPE_SLOTS];
-	cudaEvent_t ev_begin = nullptr;
-	uint8_t* d_patches = nullptr; int64_t d_patches_bytes = 0;
-	DevLayer* d_layers = nullptr;     /* whole-image scan */
-	DevLayer* d_layers_roi = nullptr; /* scratch table for ROI scans */
-	ResizeJob* d_resize = nullptr; int n_resize = 0; int max_quads = 0;
-	std::vector<DownJob*> d_down; std::vector<int> n_down; std::vector<int> max_down_px;
-	int4* d_xy_tab = nullptr; /* bilinear tables: {source offset, a0, a1, 0} */
-	GroupItem* d_gitems = nullptr; int n_gitems = 0; /* strips of the whole-image scan (group kernel work items, one model) */
-	GroupImage* d_gimages = nullptr;                 /* image table of the group kernels: entry li = image of layer li */
-	bool use_tma = false;             /* strip tiles staged by TMA (tensor maps encoded) */
-	bool use_strips = false;          /* fast path usable (and not yet overflowed) */
-	bool has_feature = false;         /* the SVM works in its own feature space (fdb_detector_set_feature) */
-	fdb_feature_desc fdesc{};
-	DevFeature feat{};
-	int64_t farena_bytes = 0;         /* per frame */
-	SvmItem* d_all_items = nullptr;   /* every window of a frame as an SVM item (`single` detector without a WVM) */
-	double* d_all_dist = nullptr; double* h_all_dist = nullptr;
-	int* d_all_level = nullptr; int* h_all_level = nullptr; /* RVM (`single` prvm): level reached per window */
-	/* `single` detector on the tensor cores (svm_dense.cu): distances of a chunk, positives list */
-	double* d_sd_dist = nullptr; int* d_sd_count = nullptr; DensePositive* d_sd_pos = nullptr;
-	int* h_sd_count = nullptr; DensePositive* h_sd_pos = nullptr; int sd_pos_cap = 0;
-	/* fdb_evaluate_samples scratch (grow-only; the tracker calls it every frame) */
-	std::vector<void*> es_owned; int es_cap = 0;
-	SvmItem* d_es_items = nullptr; uint8_t* d_es_patches = nullptr; fdb_window_score* d_es_scores = nullptr; double* d_es_dist = nullptr;
-	double sd_kernel_ms = 0; int sd_kernel_launches = 0; /* svm_dense_kernel time of the last call (CUDA events) */
-	int64_t counts[5] = {0, 0, 0, 0, 0};
-};
-
-namespace {
+namespace fdb {
 
 /* OpenCV bilinear coefficient tables for one axis (see pyramid.cu) */
 void linear_tables(int src, int dst, bool clamp_fraction, std::vector<int>& ofs, std::vector<short2>& coef) {
@@ -132,6 +52,100 @@ void linear_tables(int src, int dst, bool clamp_fraction, std::vector<int>& ofs,
 		c.y = (short)std::nearbyint(f * 2048.f);
 		coef.push_back(c);
 	}
+}
+
+int build_pyramid_jobs(const std::vector<PyrImage>& images, int max_down, int width, int height, PyramidJobs* out, std::vector<void*>& owned) {
+	*out = PyramidJobs();
+	std::vector<ResizeJob> rj;
+	std::vector<std::vector<DownJob>> dj((size_t)max_down + 1);
+	std::vector<int> ofs, winfo; std::vector<short2> coef;
+	for (const PyrImage& im : images) {
+		if (im.kind == IMG_RESIZE) {
+			ResizeJob j{};
+			j.dst_w = im.width; j.dst_h = im.height; j.dst_pitch = im.pitch; j.dst_offset = im.offset;
+			j.area2x = (width == 2 * im.width && height == 2 * im.height) ? 1 : 0;
+			j.xtab = (int)ofs.size();
+			linear_tables(width, im.width, true, ofs, coef);
+			/* word-path info per output column (see resize_kernel) */
+			j.words_ok = (width % 4 == 0) ? 1 : 0;
+			winfo.resize(ofs.size(), 0);
+			for (int dx0 = 0; dx0 < im.width; dx0 += 4) {
+				const int base = ofs[(size_t)j.xtab + dx0] & ~3;
+				for (int k = 0; k < 4 && dx0 + k < im.width; ++k) {
+					const int o = ofs[(size_t)j.xtab + dx0 + k] - base;
+					if (o < 0 || o > 10) j.words_ok = 0;
+					winfo[(size_t)j.xtab + dx0 + k] = (o >> 2) | (((o & 3) * 8) << 8) | ((base >> 2) << 16);
+				}
+			}
+			j.ytab = (int)ofs.size();
+			linear_tables(height, im.height, false, ofs, coef);
+			winfo.resize(ofs.size(), 0);
+			rj.push_back(j);
+			out->max_quads = std::max(out->max_quads, resize_tiles(im.width, im.height));
+		} else if (im.kind == IMG_PYRDOWN) {
+			const PyrImage& src = images[(size_t)im.src];
+			DownJob j{};
+			j.src_w = src.width; j.src_h = src.height; j.dst_w = im.width; j.dst_h = im.height;
+			j.src_pitch = src.pitch; j.dst_pitch = im.pitch;
+			j.src_offset = src.kind == IMG_FRAME ? -1 : src.offset; j.dst_offset = im.offset;
+			dj[(size_t)im.down].push_back(j);
+		}
+	}
+	out->n_resize = (int)rj.size();
+	int s = upload(rj.data(), rj.size(), &out->d_resize, owned); if (s) return s;
+	std::vector<int4> xy(ofs.size());
+	winfo.resize(ofs.size(), 0);
+	for (size_t k = 0; k < ofs.size(); ++k) { xy[k].x = ofs[k]; xy[k].y = coef[k].x; xy[k].z = coef[k].y; xy[k].w = winfo[k]; }
+	s = upload(xy.data(), xy.size(), &out->d_xy_tab, owned); if (s) return s;
+	for (size_t j = 1; j < dj.size(); ++j) {
+		DownJob* p = nullptr;
+		s = upload(dj[j].data(), dj[j].size(), &p, owned); if (s) return s;
+		int mx = 0;
+		for (const DownJob& q : dj[j]) mx = std::max(mx, pyrdown_tiles(q.dst_w, q.dst_h));
+		out->d_down.push_back(p); out->n_down.push_back((int)dj[j].size()); out->max_down_px.push_back(mx);
+	}
+	return FDB_OK;
+}
+
+int enqueue_pyramid(fdb_ctx* c, cudaStream_t st, const PyramidJobs& jobs, const uint8_t* d_frames, int W, int H, int n, uint8_t* d_arena,
+		int64_t arena_stride, cudaEvent_t ev_mid) {
+	if (jobs.n_resize) {
+		launch_resize(st, d_frames, W, H, n, d_arena, arena_stride, jobs.d_resize, jobs.n_resize, jobs.max_quads, jobs.d_xy_tab);
+		c->launches++;
+	}
+	if (ev_mid) CUDA_TRY(cudaEventRecord(ev_mid, st));
+	for (size_t j = 0; j < jobs.d_down.size(); ++j) {
+		if (!jobs.n_down[j]) continue;
+		launch_pyrdown(st, d_frames, W, H, n, d_arena, arena_stride, jobs.d_down[j], jobs.n_down[j], jobs.max_down_px[j]);
+		c->launches++;
+	}
+	return FDB_OK;
+}
+
+bool encode_tile_maps(const std::vector<PyrImage>& images, const std::vector<int>& which, uint8_t* arena, int64_t arena_stride, int frames,
+		std::vector<CUtensorMap>* out) {
+	/* encoded through the driver entry point (no link-time libcuda dependency) */
+	typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+			const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+			CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+	void* fn = nullptr;
+	cudaDriverEntryPointQueryResult qres = cudaDriverEntryPointSymbolNotFound;
+	if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess
+			|| qres != cudaDriverEntryPointSuccess || !fn) return false;
+	out->assign(which.size(), CUtensorMap());
+	std::memset(out->data(), 0, sizeof(CUtensorMap) * out->size());
+	for (size_t k = 0; k < which.size(); ++k) {
+		const PyrImage& im = images[(size_t)which[k]];
+		if (im.offset < 0) continue; /* the frame itself: plain loads */
+		const cuuint64_t dims[3] = {(cuuint64_t)im.width, (cuuint64_t)im.height, (cuuint64_t)frames};
+		const cuuint64_t strides[2] = {(cuuint64_t)im.pitch, (cuuint64_t)arena_stride};
+		const cuuint32_t box[3] = {STRIP_TILE_PITCH, STRIP_TILE_ROWS, 1};
+		const cuuint32_t estr[3] = {1, 1, 1};
+		if (reinterpret_cast<EncodeFn>(fn)(&(*out)[k], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, arena + im.offset, dims, strides, box, estr,
+				CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+				CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) return false;
+	}
+	return true;
 }
 
 /* work items of the group kernel for one layer: strips of <= 32 window columns; narrow layers pack several row runs side
@@ -186,19 +200,10 @@ int enqueue_stage1(fdb_detector* det, Slot& sl, cudaStream_t st, const uint8_t* 
 		bool marks = false) {
 	fdb_ctx* c = det->ctx;
 	const int W = plan.width, H = plan.height;
+	sl.arena = sl.d_arena; sl.arena_stride = plan.arena_bytes;
 	CUDA_TRY(cudaMemsetAsync(sl.d_counters, 0, 4 * sizeof(int), st));
 	if (marks) CUDA_TRY(cudaEventRecord(c->ev[1], st));
-	if (det->n_resize) {
-		launch_resize(st, d_frames, W, H, n, sl.d_arena, plan.arena_bytes, det->d_resize, det->n_resize,
-				det->max_quads, det->d_xy_tab);
-		c->launches++;
-	}
-	if (marks) CUDA_TRY(cudaEventRecord(c->ev[2], st));
-	for (size_t j = 0; j < det->d_down.size(); ++j) {
-		if (!det->n_down[j]) continue;
-		launch_pyrdown(st, d_frames, W, H, n, sl.d_arena, plan.arena_bytes, det->d_down[j], det->n_down[j], det->max_down_px[j]);
-		c->launches++;
-	}
+	{ const int r = enqueue_pyramid(c, st, det->jobs, d_frames, W, H, n, sl.d_arena, plan.arena_bytes, marks ? c->ev[2] : nullptr); if (r) return r; }
 	if (marks) CUDA_TRY(cudaEventRecord(c->ev[3], st));
 	if (windows > 0 && det->wvm) {
 		DevWvm m = det->wvm->dev;
@@ -255,7 +260,6 @@ int enqueue_fetch(fdb_detector* det, Slot& sl, cudaStream_t st) {
 	return FDB_OK;
 }
 
-const int STATUS_REDO = -1000;
 
 /* the second classifier on n work items of the slot's chunk: hq64 patches are rebuilt inside the SVM kernel;
  * any other feature space runs its layer filters once per chunk, then feature kernel + SVM in batches */
@@ -264,18 +268,18 @@ void svm_stage(fdb_detector* det, Slot& sl, cudaStream_t st, const Plan& plan, c
 	fdb_ctx* c = det->ctx;
 	if (!det->has_feature || det->feat.kind == FDB_FEATURE_HQ64) {
 		launch_svm_windows(st, det->svm->dev, det->desc.patch_width, det->desc.patch_height, sl.frames_dev, plan.width, plan.height,
-				sl.d_arena, plan.arena_bytes, d_layers, d_items, n, d_dist, d_level);
+				sl.arena, sl.arena_stride, d_layers, d_items, n, d_dist, d_level);
 		c->launches++;
 		return;
 	}
 	if (filter_layers && det->feat.layer_channels) {
-		launch_feature_layers(st, det->feat, sl.frames_dev, plan.width, plan.height, sl.n, sl.d_arena, plan.arena_bytes, d_layers,
+		launch_feature_layers(st, det->feat, sl.frames_dev, plan.width, plan.height, sl.n, sl.arena, sl.arena_stride, d_layers,
 				sl.d_farena, det->farena_bytes);
 		c->launches++;
 	}
 	for (int off = 0; off < n; off += FEAT_BATCH) {
 		const int m = std::min(FEAT_BATCH, n - off);
-		launch_feature_patches(st, det->feat, sl.frames_dev, plan.width, plan.height, sl.d_arena, plan.arena_bytes, d_layers,
+		launch_feature_patches(st, det->feat, sl.frames_dev, plan.width, plan.height, sl.arena, sl.arena_stride, d_layers,
 				sl.d_farena, det->farena_bytes, d_items + off, m, sl.d_feat);
 		launch_svm_vectors(st, det->svm->dev, sl.d_feat, m, d_dist + off, d_level ? d_level + off : nullptr);
 		c->launches += 2;
@@ -284,10 +288,11 @@ void svm_stage(fdb_detector* det, Slot& sl, cudaStream_t st, const Plan& plan, c
 
 /* phase A of the host post-processing: wait for stage 1 of the slot's chunk, build the per-frame
  * candidate lists, overlap elimination, launch the SVM on the survivors (async) */
-int phase_a(fdb_detector* det, Slot& sl, cudaStream_t st, const Plan& plan, const DevLayer* d_layers, int stage) {
+int phase_a(fdb_detector* det, Slot& sl, cudaStream_t st, const Plan& plan, const DevLayer* d_layers, int stage, int fast_path) {
 	fdb_ctx* c = det->ctx;
 	CUDA_TRY(cudaEventSynchronize(sl.ev_stage1));
-	if (det->use_strips && d_layers == det->d_layers && sl.h_counters[1] > sl.deep.cap) {
+	if (fast_path < 0) fast_path = det->use_strips && d_layers == det->d_layers;
+	if (fast_path && sl.h_counters[1] > sl.deep.cap) {
 		/* more survivors than the deep queue holds (a model with hardly any early exits): the strip
 		 * kernel cannot finish them inline, so this detector switches to the generic kernels for good */
 		det->use_strips = false;
@@ -403,7 +408,7 @@ void release(fdb_detector* det) {
 	free_all(det->es_owned); det->es_cap = 0;
 	det->prepared = false;
 	det->d_patches = nullptr; det->d_patches_bytes = 0;
-	det->d_down.clear(); det->n_down.clear(); det->max_down_px.clear();
+	det->jobs = PyramidJobs();
 }
 
 bool single_dense_usable(const fdb_detector* det);
@@ -770,7 +775,7 @@ int detect_impl(fdb_detector* det, const uint8_t* frames, bool frames_on_device,
 	return s;
 }
 
-} // namespace
+} // namespace fdb
 
 extern "C" {
 
@@ -847,56 +852,7 @@ int fdb_detector_prepare(fdb_detector* det, int32_t width, int32_t height, int32
 	det->cand_cap = (int)std::max<int64_t>(OPT_CAND, std::min<int64_t>(cap64, (int64_t)1 << 26));
 	det->items_cap = det->cand_cap;
 
-	/* job tables */
-	std::vector<ResizeJob> rj;
-	std::vector<std::vector<DownJob>> dj((size_t)plan.max_down + 1);
-	std::vector<int> ofs, winfo; std::vector<short2> coef;
-	det->max_quads = 0;
-	for (const PyrImage& im : plan.images) {
-		if (im.kind == IMG_RESIZE) {
-			ResizeJob j{};
-			j.dst_w = im.width; j.dst_h = im.height; j.dst_pitch = im.pitch; j.dst_offset = im.offset;
-			j.area2x = (width == 2 * im.width && height == 2 * im.height) ? 1 : 0;
-			j.xtab = (int)ofs.size();
-			linear_tables(width, im.width, true, ofs, coef);
-			/* word-path info per output column (see resize_kernel) */
-			j.words_ok = (width % 4 == 0) ? 1 : 0;
-			winfo.resize(ofs.size(), 0);
-			for (int dx0 = 0; dx0 < im.width; dx0 += 4) {
-				const int base = ofs[(size_t)j.xtab + dx0] & ~3;
-				for (int k = 0; k < 4 && dx0 + k < im.width; ++k) {
-					const int o = ofs[(size_t)j.xtab + dx0 + k] - base;
-					if (o < 0 || o > 10) j.words_ok = 0;
-					winfo[(size_t)j.xtab + dx0 + k] = (o >> 2) | (((o & 3) * 8) << 8) | ((base >> 2) << 16);
-				}
-			}
-			j.ytab = (int)ofs.size();
-			linear_tables(height, im.height, false, ofs, coef);
-			winfo.resize(ofs.size(), 0);
-			rj.push_back(j);
-			det->max_quads = std::max(det->max_quads, resize_tiles(im.width, im.height));
-		} else if (im.kind == IMG_PYRDOWN) {
-			const PyrImage& src = plan.images[(size_t)im.src];
-			DownJob j{};
-			j.src_w = src.width; j.src_h = src.height; j.dst_w = im.width; j.dst_h = im.height;
-			j.src_pitch = src.pitch; j.dst_pitch = im.pitch;
-			j.src_offset = src.kind == IMG_FRAME ? -1 : src.offset; j.dst_offset = im.offset;
-			dj[(size_t)im.down].push_back(j);
-		}
-	}
-	det->n_resize = (int)rj.size();
-	s = upload(rj.data(), rj.size(), &det->d_resize, det->owned); if (s) return s;
-	std::vector<int4> xy(ofs.size());
-	winfo.resize(ofs.size(), 0);
-	for (size_t k = 0; k < ofs.size(); ++k) { xy[k].x = ofs[k]; xy[k].y = coef[k].x; xy[k].z = coef[k].y; xy[k].w = winfo[k]; }
-	s = upload(xy.data(), xy.size(), &det->d_xy_tab, det->owned); if (s) return s;
-	for (size_t j = 1; j < dj.size(); ++j) {
-		DownJob* p = nullptr;
-		s = upload(dj[j].data(), dj[j].size(), &p, det->owned); if (s) return s;
-		int mx = 0;
-		for (const DownJob& q : dj[j]) mx = std::max(mx, pyrdown_tiles(q.dst_w, q.dst_h));
-		det->d_down.push_back(p); det->n_down.push_back((int)dj[j].size()); det->max_down_px.push_back(mx);
-	}
+	s = build_pyramid_jobs(plan.images, plan.max_down, width, height, &det->jobs, det->owned); if (s) return s;
 	CUDA_TRY(cudaEventCreateWithFlags(&det->ev_begin, cudaEventDisableTiming));
 	for (int i = 0; i < det->n_slots; ++i) {
 		Slot& sl = det->slots[i];
@@ -930,37 +886,20 @@ int fdb_detector_prepare(fdb_detector* det, int32_t width, int32_t height, int32
 		s = host_alloc(&sl.h_items, (size_t)det->items_cap, det->owned_host); if (s) return s;
 		s = host_alloc(&sl.h_dist, (size_t)det->items_cap, det->owned_host); if (s) return s;
 	}
-	/* TMA descriptors for the strip kernel's tiles: layer li of slot i is a 3-D u8 tensor {width, height, chunk}
-	 * with strides {pitch, arena_bytes}; the box is one warp tile. Encoded through the driver entry point
-	 * (no link-time libcuda dependency); when it is missing the kernel stages tiles with plain loads. */
+	/* TMA descriptors for the group kernel's tiles: layer li of slot i is a 3-D u8 tensor {width, height, chunk} with
+	 * strides {pitch, arena_bytes}; the box is one warp tile. When the driver entry point is missing the kernel stages
+	 * tiles with plain loads. */
 	det->use_tma = false;
 	{
-		typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-				const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-				CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-		void* fn = nullptr;
-		cudaDriverEntryPointQueryResult qres = cudaDriverEntryPointSymbolNotFound;
 		const char* env = std::getenv("FDB_NO_TMA");
-		if (!(env && env[0] == '1') && group_supported(det->desc.patch_width, det->desc.patch_height)
-				&& cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess
-				&& qres == cudaDriverEntryPointSuccess && fn) {
+		if (!(env && env[0] == '1') && group_supported(det->desc.patch_width, det->desc.patch_height)) {
+			std::vector<int> which;
+			for (const PlanLayer& L : plan.layers) which.push_back(L.image);
 			bool ok = true;
 			for (int i = 0; i < det->n_slots && ok; ++i) {
-				Slot& sl = det->slots[i];
-				std::vector<CUtensorMap> maps(plan.layers.size());
-				std::memset(maps.data(), 0, sizeof(CUtensorMap) * maps.size());
-				for (size_t li = 0; li < plan.layers.size() && ok; ++li) {
-					const PyrImage& im = plan.images[plan.layers[li].image];
-					if (im.offset < 0) continue; /* the frame itself: plain loads */
-					const cuuint64_t dims[3] = {(cuuint64_t)im.width, (cuuint64_t)im.height, (cuuint64_t)det->chunk};
-					const cuuint64_t strides[2] = {(cuuint64_t)im.pitch, (cuuint64_t)plan.arena_bytes};
-					const cuuint32_t box[3] = {STRIP_TILE_PITCH, STRIP_TILE_ROWS, 1};
-					const cuuint32_t estr[3] = {1, 1, 1};
-					ok = reinterpret_cast<EncodeFn>(fn)(&maps[li], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, sl.d_arena + im.offset,
-							dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-							CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-				}
-				if (ok) { s = upload(maps.data(), maps.size(), &sl.d_tmaps, det->owned); if (s) return s; }
+				std::vector<CUtensorMap> maps;
+				ok = encode_tile_maps(plan.images, which, det->slots[i].d_arena, plan.arena_bytes, det->chunk, &maps);
+				if (ok) { s = upload(maps.data(), maps.size(), &det->slots[i].d_tmaps, det->owned); if (s) return s; }
 			}
 			det->use_tma = ok;
 		}

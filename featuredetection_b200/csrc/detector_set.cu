@@ -1,0 +1,455 @@
+/*
+ * detector_set.cu - all detectors of an application over one frame batch.
+ *
+ * ffpDetectApp builds one detector per landmark cfg - each with its OWN ImagePyramid (ffpDetectApp.cpp:407,435) - and runs
+ * every one of them on every frame (ffpDetectApp.cpp:548-596). The 15 cfgs use 4 distinct pyramid parameter sets and 5
+ * window sizes; 12 of them scan the same four layers. A detector set gives the same results as running its members one
+ * after the other (tests/test_detector_set.py) while
+ *   - every distinct pyramid image is built once per frame (the union of the members' pyramid plans in one arena);
+ *   - windows of the same layer and size are equalised once for a pack of models (wvm_group.cu), one launch per window size;
+ *   - the survivors of all members finish their cascades in one launch of the deep kernel;
+ *   - host post-processing (overlap elimination, SVM stage, grid NMS) runs per member exactly as in detector.cu.
+ * Members that cannot take the group kernels (other window sizes or steps, models without early exits that overflow the
+ * deep queue) run through their own pipeline inside the same call.
+ */
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "detector_internal.h"
+
+using namespace fdb;
+
+namespace {
+
+struct SetSlot {
+	cudaStream_t st = nullptr;
+	uint8_t* d_frames = nullptr;
+	uint8_t* d_arena = nullptr;
+	CUtensorMap* d_tmaps = nullptr; /* one per union image */
+	int* d_cursors = nullptr;       /* work counters of the window launches */
+	int n = 0, base = 0;
+	const uint8_t* frames_dev = nullptr;
+	bool busy = false;
+};
+
+struct SetLaunch {  /* one wvm_group_kernel launch: all strips of one window size and pack width */
+	int pw = 0, ph = 0, pack = 1;
+	GroupItem* d_items = nullptr; int n_items = 0;
+};
+
+} // namespace
+
+struct fdb_detector_set {
+	fdb_ctx* ctx = nullptr;
+	std::vector<fdb_detector*> dets;
+	bool prepared = false;
+	int W = 0, H = 0, max_batch = 0, chunk = 0, n_slots = 0;
+	std::vector<PyrImage> images;       /* union of the members' pyramid images, dependency order */
+	std::vector<std::vector<int>> umap; /* member d, plan image k -> union image */
+	int64_t arena_bytes = 0;
+	int max_down = 0;
+	PyramidJobs jobs;
+	GroupImage* d_images = nullptr;
+	std::vector<DevLayer*> d_layers;    /* member d's layer table against the union arena */
+	std::vector<SetLaunch> launches;
+	std::vector<char> fast;             /* member d takes the group kernels */
+	bool use_tma = false;
+	SetSlot slots[PIPE_SLOTS];
+	cudaEvent_t ev_begin = nullptr;
+	std::vector<void*> owned, owned_host;
+	int64_t windows = 0;                /* per frame, all members */
+};
+
+namespace {
+
+void set_release(fdb_detector_set* s) {
+	for (SetSlot& sl : s->slots) {
+		if (sl.st) { cudaStreamSynchronize(sl.st); cudaStreamDestroy(sl.st); }
+		sl = SetSlot();
+	}
+	if (s->ev_begin) { cudaEventDestroy(s->ev_begin); s->ev_begin = nullptr; }
+	free_all(s->owned, &s->owned_host);
+	s->images.clear(); s->umap.clear(); s->d_layers.clear(); s->launches.clear(); s->fast.clear();
+	s->jobs = PyramidJobs();
+	s->prepared = false;
+}
+
+/* the members' plans merged: an image is identified by how it is made (the frame, a resize target, the pyrDown of an image) */
+void build_union(fdb_detector_set* s) {
+	std::map<std::tuple<int, int, int, int>, int> index; /* (kind, source union image, width, height) -> union image */
+	int64_t offset = 0;
+	auto align_up = [](int64_t v, int64_t a) { return (v + a - 1) / a * a; };
+	for (fdb_detector* det : s->dets) {
+		std::vector<int> m(det->plan.images.size(), -1);
+		for (size_t k = 0; k < det->plan.images.size(); ++k) {
+			const PyrImage& im = det->plan.images[k];
+			const int src = im.kind == IMG_PYRDOWN ? m[(size_t)im.src] : -1;
+			const auto key = std::make_tuple(im.kind, src, im.width, im.height);
+			auto it = index.find(key);
+			if (it == index.end()) {
+				PyrImage u = im;
+				u.src = src; u.kept = false; u.layer_index = -1;
+				if (u.kind != IMG_FRAME) {
+					u.offset = offset;
+					offset = align_up(offset + (int64_t)u.pitch * u.height, 128);
+				}
+				s->max_down = std::max(s->max_down, u.down);
+				s->images.push_back(u);
+				it = index.emplace(key, (int)s->images.size() - 1).first;
+			}
+			m[k] = it->second;
+		}
+		s->umap.push_back(m);
+	}
+	s->arena_bytes = std::max<int64_t>(align_up(offset, 128), 128);
+}
+
+GroupModel member_model(const fdb_detector_set* s, int d, const Slot& msl, fdb_window_score* dense) {
+	const fdb_detector* det = s->dets[(size_t)d];
+	GroupModel gm{};
+	gm.m = det->wvm->dev;
+	gm.m.step_x = gm.m.step_y = 1;
+	gm.dense = dense;
+	gm.windows_per_frame = (int)det->plan.windows;
+	gm.cand_cap = det->cand_cap;
+	gm.cand = msl.d_cand; gm.cand_count = msl.d_counters; gm.q = msl.deep;
+	return gm;
+}
+
+/* pyramid + stage 1 of every fast member for the chunk of slot si; ev (optional): marks after resize, pyrDown, window kernels */
+int set_enqueue(fdb_detector_set* s, int si, fdb_window_score* const* dense_dev, cudaEvent_t* marks) {
+	SetSlot& ss = s->slots[si];
+	fdb_ctx* c = s->ctx;
+	cudaStream_t st = ss.st;
+	const int nd = (int)s->dets.size();
+	if (!s->launches.empty()) CUDA_TRY(cudaMemsetAsync(ss.d_cursors, 0, sizeof(int) * s->launches.size(), st));
+	for (int d = 0; d < nd; ++d) if (s->fast[(size_t)d]) CUDA_TRY(cudaMemsetAsync(s->dets[(size_t)d]->slots[si].d_counters, 0, 4 * sizeof(int), st));
+	if (marks) CUDA_TRY(cudaEventRecord(marks[0], st));
+	{ const int r = enqueue_pyramid(c, st, s->jobs, ss.frames_dev, s->W, s->H, ss.n, ss.d_arena, s->arena_bytes, marks ? marks[1] : nullptr); if (r) return r; }
+	if (marks) CUDA_TRY(cudaEventRecord(marks[2], st));
+	GroupArgs ga{};
+	ga.n_frames = ss.n; ga.images = s->d_images; ga.tmaps = s->use_tma ? ss.d_tmaps : nullptr;
+	ga.frames = ss.frames_dev; ga.W = s->W; ga.H = s->H; ga.arena = ss.d_arena; ga.arena_stride = s->arena_bytes;
+	DeepArgs da{};
+	da.images = s->d_images; da.frames = ss.frames_dev; da.W = s->W; da.H = s->H; da.arena = ss.d_arena; da.arena_stride = s->arena_bytes;
+	std::vector<int> deep_of((size_t)nd, -1);
+	for (int d = 0; d < nd; ++d) {
+		if (!s->fast[(size_t)d]) continue;
+		fdb_detector* det = s->dets[(size_t)d];
+		fdb_window_score* dense = dense_dev && dense_dev[d] ? dense_dev[d] + (int64_t)ss.base * det->plan.windows : nullptr;
+		ga.models[d] = member_model(s, d, det->slots[si], dense);
+		da.models[da.n_models++] = ga.models[d];
+	}
+	for (size_t k = 0; k < s->launches.size(); ++k) {
+		const SetLaunch& L = s->launches[k];
+		ga.items = L.d_items; ga.n_items = L.n_items; ga.cursor = ss.d_cursors + k;
+		launch_wvm_group(st, L.pw, L.ph, L.pack, ga);
+		c->launches++;
+	}
+	if (marks) CUDA_TRY(cudaEventRecord(marks[3], st));
+	if (da.n_models) { launch_wvm_deep_group(st, da); c->launches++; }
+	if (marks) CUDA_TRY(cudaEventRecord(marks[4], st));
+	CUDA_TRY(cudaGetLastError());
+	return FDB_OK;
+}
+
+int set_pipeline(fdb_detector_set* s, const uint8_t* frames, bool frames_on_device, int64_t pitch, int32_t n_frames, int32_t stage,
+		fdb_window_score* const* dense_dev, std::vector<std::vector<fdb_detection>>& results) {
+	const int W = s->W, H = s->H, nd = (int)s->dets.size();
+	for (int d = 0; d < nd; ++d) {
+		fdb_detector* det = s->dets[(size_t)d];
+		std::fill(det->counts, det->counts + 5, 0);
+		det->counts[0] = det->plan.windows * n_frames;
+	}
+	CUDA_TRY(cudaEventRecord(s->ev_begin, s->ctx->stream));
+	for (int i = 0; i < s->n_slots; ++i) CUDA_TRY(cudaStreamWaitEvent(s->slots[i].st, s->ev_begin, 0));
+	const int n_chunks = (n_frames + s->chunk - 1) / s->chunk;
+	int enq = 0, a_done = 0, retired = 0;
+	auto do_a = [&]() -> int {
+		const int si = a_done % s->n_slots;
+		SetSlot& ss = s->slots[si];
+		for (int d = 0; d < nd; ++d) {
+			if (!s->fast[(size_t)d]) continue;
+			fdb_detector* det = s->dets[(size_t)d];
+			Slot& msl = det->slots[si];
+			msl.n = ss.n; msl.base = ss.base; msl.frames_dev = ss.frames_dev;
+			msl.arena = ss.d_arena; msl.arena_stride = s->arena_bytes;
+			const int r = phase_a(det, msl, ss.st, det->plan, s->d_layers[(size_t)d], stage, 1);
+			if (r) return r;
+		}
+		++a_done;
+		return FDB_OK;
+	};
+	auto do_b = [&]() -> int {
+		const int si = retired % s->n_slots;
+		for (int d = 0; d < nd; ++d) {
+			if (!s->fast[(size_t)d]) continue;
+			const int r = phase_b(s->dets[(size_t)d], s->dets[(size_t)d]->slots[si], s->dets[(size_t)d]->plan, stage, false, results[(size_t)d]);
+			if (r) return r;
+		}
+		s->slots[si].busy = false;
+		++retired;
+		return FDB_OK;
+	};
+	int r = FDB_OK;
+	while (enq < n_chunks) {
+		const int si = enq % s->n_slots;
+		SetSlot& ss = s->slots[si];
+		while (ss.busy) {
+			if (a_done == retired) { r = do_a(); if (r) return r; }
+			r = do_b(); if (r) return r;
+		}
+		ss.base = enq * s->chunk;
+		ss.n = std::min(s->chunk, n_frames - ss.base);
+		ss.busy = true;
+		if (frames_on_device) ss.frames_dev = frames + (int64_t)ss.base * W * H;
+		else {
+			if (pitch == W)
+				CUDA_TRY(cudaMemcpyAsync(ss.d_frames, frames + (int64_t)ss.base * W * H, (size_t)W * H * ss.n, cudaMemcpyHostToDevice, ss.st));
+			else
+				CUDA_TRY(cudaMemcpy2DAsync(ss.d_frames, (size_t)W, frames + (int64_t)ss.base * pitch * H, (size_t)pitch, (size_t)W,
+						(size_t)H * ss.n, cudaMemcpyHostToDevice, ss.st));
+			ss.frames_dev = ss.d_frames;
+		}
+		r = set_enqueue(s, si, dense_dev, nullptr); if (r) return r;
+		for (int d = 0; d < nd; ++d) {
+			if (!s->fast[(size_t)d]) continue;
+			Slot& msl = s->dets[(size_t)d]->slots[si];
+			CUDA_TRY(cudaMemcpyAsync(msl.h_counters, msl.d_counters, 4 * sizeof(int) + OPT_CAND * sizeof(Candidate), cudaMemcpyDeviceToHost, ss.st));
+			CUDA_TRY(cudaEventRecord(msl.ev_stage1, ss.st));
+		}
+		++enq;
+		while (a_done < enq - 1) { r = do_a(); if (r) return r; }
+		while (retired < a_done - 1) { r = do_b(); if (r) return r; }
+	}
+	while (a_done < n_chunks) {
+		r = do_a(); if (r) return r;
+		while (retired < a_done - 1) { r = do_b(); if (r) return r; }
+	}
+	while (retired < n_chunks) { r = do_b(); if (r) return r; }
+	for (int i = 0; i < s->n_slots; ++i) CUDA_TRY(cudaStreamSynchronize(s->slots[i].st));
+	return FDB_OK;
+}
+
+int set_detect(fdb_detector_set* s, const uint8_t* frames, bool frames_on_device, int64_t pitch, int32_t n_frames, int32_t stage,
+		fdb_window_score* const* dense_dev, fdb_detection* dets_out, int64_t det_cap, int64_t* n_dets) {
+	if (!s || !s->prepared) return fail(FDB_ERR_INVALID_ARGUMENT, "detector set not prepared (call fdb_detector_set_prepare)");
+	int r = check_ctx(s->ctx); if (r) return r;
+	if (n_frames < 0 || (n_frames > 0 && !frames)) return fail(FDB_ERR_INVALID_ARGUMENT, "bad frame batch");
+	if (stage < FDB_STAGE_WVM || stage > FDB_STAGE_NMS) return fail(FDB_ERR_INVALID_ARGUMENT, "bad stage");
+	if (!frames_on_device && pitch < s->W) return fail(FDB_ERR_INVALID_ARGUMENT, "pitch smaller than the frame width");
+	const int nd = (int)s->dets.size();
+	std::vector<std::vector<fdb_detection>> results((size_t)nd);
+	for (int attempt = 0; attempt < nd + 1; ++attempt) {
+		for (auto& v : results) v.clear();
+		r = set_pipeline(s, frames, frames_on_device, pitch, n_frames, stage, dense_dev, results);
+		for (int i = 0; i < s->n_slots; ++i) { cudaStreamSynchronize(s->slots[i].st); s->slots[i].busy = false; }
+		for (fdb_detector* det : s->dets) for (int i = 0; i < det->n_slots; ++i) det->slots[i].busy = false;
+		if (r != STATUS_REDO) break;
+		/* a member's deep queue overflowed (phase_a took it off the fast path): it runs alone from now on */
+		for (int d = 0; d < nd; ++d) if (s->fast[(size_t)d] && !s->dets[(size_t)d]->use_strips) s->fast[(size_t)d] = 0;
+	}
+	if (r) return r;
+	/* members outside the group kernels: their own pipeline (own pyramid), same results */
+	for (int d = 0; d < nd; ++d) {
+		if (s->fast[(size_t)d]) continue;
+		fdb_detector* det = s->dets[(size_t)d];
+		const int64_t cap = std::max<int64_t>((int64_t)det->desc.max_positives_per_frame * n_frames, 1);
+		std::vector<fdb_detection> tmp((size_t)cap);
+		int64_t got = 0;
+		fdb_window_score* dense = dense_dev ? dense_dev[d] : nullptr;
+		r = detect_impl(det, frames, frames_on_device, pitch, n_frames, stage, dense, true, tmp.data(), cap, &got);
+		if (r) return r;
+		results[(size_t)d].assign(tmp.begin(), tmp.begin() + got);
+	}
+	std::vector<fdb_detection> all;
+	for (int d = 0; d < nd; ++d)
+		for (fdb_detection& x : results[(size_t)d]) { x.reserved = d; all.push_back(x); }
+	return copy_out(all, dets_out, det_cap, n_dets);
+}
+
+} // namespace
+
+extern "C" {
+
+int fdb_detector_set_create(fdb_ctx* ctx, fdb_detector* const* detectors, int32_t n, fdb_detector_set** out) try {
+	int r = check_ctx(ctx); if (r) return r;
+	if (!detectors || !out || n < 1) return fail(FDB_ERR_INVALID_ARGUMENT, "a detector set needs at least one detector");
+	*out = nullptr;
+	if (n > GRP_MAX_MODELS) return fail(FDB_ERR_UNSUPPORTED, "more than 16 detectors in a set");
+	for (int i = 0; i < n; ++i) {
+		if (!detectors[i] || detectors[i]->ctx != ctx) return fail(FDB_ERR_INVALID_ARGUMENT, "detector of another context (or null) in the set");
+		if (!detectors[i]->wvm) return fail(FDB_ERR_INVALID_ARGUMENT, "a set holds cascade detectors (WVM first stage); `single` detectors run on their own");
+		for (int j = 0; j < i; ++j) if (detectors[j] == detectors[i]) return fail(FDB_ERR_INVALID_ARGUMENT, "the same detector twice in a set");
+	}
+	fdb_detector_set* s = new fdb_detector_set;
+	s->ctx = ctx;
+	s->dets.assign(detectors, detectors + n);
+	*out = s;
+	return FDB_OK;
+} FDB_API_CATCH
+
+void fdb_detector_set_destroy(fdb_detector_set* s) {
+	if (!s) return;
+	cudaSetDevice(s->ctx->device);
+	cudaStreamSynchronize(s->ctx->stream);
+	set_release(s);
+	delete s;
+}
+
+int fdb_detector_set_prepare(fdb_detector_set* s, int32_t width, int32_t height, int32_t max_batch) try {
+	if (!s) return fail(FDB_ERR_INVALID_ARGUMENT, "null detector set");
+	int r = check_ctx(s->ctx); if (r) return r;
+	if (max_batch < 1) return fail(FDB_ERR_INVALID_ARGUMENT, "max_batch must be positive");
+	CUDA_TRY(cudaStreamSynchronize(s->ctx->stream));
+	set_release(s);
+	const int nd = (int)s->dets.size();
+	for (fdb_detector* det : s->dets) { r = fdb_detector_prepare(det, width, height, max_batch); if (r) return r; }
+	s->W = width; s->H = height; s->max_batch = max_batch;
+	s->chunk = s->dets[0]->chunk; s->n_slots = s->dets[0]->n_slots;
+	s->windows = 0;
+	for (fdb_detector* det : s->dets) s->windows += det->plan.windows;
+	build_union(s);
+	r = build_pyramid_jobs(s->images, s->max_down, width, height, &s->jobs, s->owned); if (r) return r;
+	/* the set runs the fast members; a member prepared off the fast path (window size, step, model shape) runs alone */
+	s->fast.assign((size_t)nd, 0);
+	for (int d = 0; d < nd; ++d) s->fast[(size_t)d] = s->dets[(size_t)d]->use_strips ? 1 : 0;
+	CUDA_TRY(cudaEventCreateWithFlags(&s->ev_begin, cudaEventDisableTiming));
+	for (int i = 0; i < s->n_slots; ++i) {
+		SetSlot& sl = s->slots[i];
+		CUDA_TRY(cudaStreamCreateWithFlags(&sl.st, cudaStreamNonBlocking));
+		r = dev_alloc(&sl.d_frames, (size_t)s->chunk * width * height, s->owned); if (r) return r;
+		r = dev_alloc(&sl.d_arena, (size_t)s->chunk * (size_t)s->arena_bytes, s->owned); if (r) return r;
+		r = dev_alloc(&sl.d_cursors, 64, s->owned); if (r) return r;
+	}
+	s->use_tma = false;
+	{
+		const char* env = std::getenv("FDB_NO_TMA");
+		if (!(env && env[0] == '1')) {
+			std::vector<int> which(s->images.size());
+			for (size_t k = 0; k < which.size(); ++k) which[k] = (int)k;
+			bool ok = true;
+			for (int i = 0; i < s->n_slots && ok; ++i) {
+				std::vector<CUtensorMap> maps;
+				ok = encode_tile_maps(s->images, which, s->slots[i].d_arena, s->arena_bytes, s->chunk, &maps);
+				if (ok) { r = upload(maps.data(), maps.size(), &s->slots[i].d_tmaps, s->owned); if (r) return r; }
+			}
+			s->use_tma = ok;
+		}
+	}
+	std::vector<GroupImage> gim(s->images.size());
+	for (size_t k = 0; k < gim.size(); ++k) {
+		const PyrImage& im = s->images[k];
+		gim[k].offset = im.kind == IMG_FRAME ? -1 : im.offset; gim[k].width = im.width; gim[k].height = im.height; gim[k].pitch = im.pitch;
+		gim[k].tma_ok = s->use_tma && im.kind != IMG_FRAME ? 1 : 0;
+	}
+	r = upload(gim.data(), gim.size(), &s->d_images, s->owned); if (r) return r;
+	/* members' layer tables against the union arena (SVM stage, feature layers) */
+	s->d_layers.assign((size_t)nd, nullptr);
+	for (int d = 0; d < nd; ++d) {
+		const Plan& plan = s->dets[(size_t)d]->plan;
+		std::vector<DevLayer> L(std::max<size_t>(plan.layers.size(), 1));
+		for (size_t i = 0; i < plan.layers.size(); ++i) {
+			const PlanLayer& p = plan.layers[i];
+			const PyrImage& u = s->images[(size_t)s->umap[(size_t)d][(size_t)p.image]];
+			L[i].offset = u.kind == IMG_FRAME ? -1 : u.offset;
+			L[i].width = p.width; L[i].height = p.height; L[i].pitch = u.pitch;
+			L[i].begin_x = p.begin_x; L[i].begin_y = p.begin_y; L[i].windows_x = p.windows_x; L[i].windows_y = p.windows_y;
+			L[i].first_window = (int)p.first_window;
+			L[i].tma_ok = 0;
+		}
+		r = upload(L.data(), L.size(), &s->d_layers[(size_t)d], s->owned); if (r) return r;
+	}
+	/* work items: windows of the same image, size and grid are equalised once for all members that scan them */
+	typedef std::tuple<int, int, int, int, int, int, int> GridKey; /* patch w, h, union image, begin x, y, windows x, y */
+	std::map<GridKey, std::vector<std::pair<int, int>>> grids;     /* -> (member, layer) */
+	for (int d = 0; d < nd; ++d) {
+		if (!s->fast[(size_t)d]) continue;
+		const fdb_detector* det = s->dets[(size_t)d];
+		for (size_t li = 0; li < det->plan.layers.size(); ++li) {
+			const PlanLayer& p = det->plan.layers[li];
+			if (p.windows_x <= 0 || p.windows_y <= 0) continue;
+			grids[GridKey(det->desc.patch_width, det->desc.patch_height, s->umap[(size_t)d][(size_t)p.image], p.begin_x, p.begin_y,
+					p.windows_x, p.windows_y)].push_back(std::make_pair(d, (int)li));
+		}
+	}
+	std::map<std::tuple<int, int, int>, std::vector<GroupItem>> by_launch; /* (patch w, h, pack) -> items */
+	for (const auto& kv : grids) {
+		const int pw = std::get<0>(kv.first), ph = std::get<1>(kv.first), image = std::get<2>(kv.first);
+		std::vector<int> models, firsts;
+		for (const auto& ml : kv.second) {
+			models.push_back(ml.first);
+			firsts.push_back((int)s->dets[(size_t)ml.first]->plan.layers[(size_t)ml.second].first_window);
+		}
+		const PlanLayer& p = s->dets[(size_t)kv.second[0].first]->plan.layers[(size_t)kv.second[0].second];
+		std::vector<GroupItem> items;
+		append_strip_items(p, image, ph, (int)models.size(), models.data(), firsts.data(), &items);
+		for (const GroupItem& it : items) by_launch[std::make_tuple(pw, ph, it.nm > 1 ? 2 : 1)].push_back(it);
+	}
+	for (auto& kv : by_launch) {
+		SetLaunch L;
+		L.pw = std::get<0>(kv.first); L.ph = std::get<1>(kv.first); L.pack = std::get<2>(kv.first);
+		/* pack-major order: consecutive units share the models' fragment tables (L1) */
+		std::stable_sort(kv.second.begin(), kv.second.end(), [](const GroupItem& a, const GroupItem& b) { return a.model[0] < b.model[0]; });
+		L.n_items = (int)kv.second.size();
+		r = upload(kv.second.data(), kv.second.size(), &L.d_items, s->owned); if (r) return r;
+		s->launches.push_back(L);
+	}
+	if (s->launches.size() > 16) return fail(FDB_ERR_UNSUPPORTED, "more than 16 window-size classes in a detector set");
+	s->prepared = true;
+	return FDB_OK;
+} FDB_API_CATCH
+
+int64_t fdb_detector_set_windows_per_frame(fdb_detector_set* s) { return s && s->prepared ? s->windows : -1; }
+
+int fdb_detector_set_info(fdb_detector_set* s, int32_t* n_images, int64_t* pyramid_bytes, int32_t* n_window_launches, int32_t* n_fast) try {
+	if (!s || !s->prepared) return fail(FDB_ERR_INVALID_ARGUMENT, "detector set not prepared");
+	if (n_images) { int k = 0; for (const PyrImage& im : s->images) k += im.kind != IMG_FRAME; *n_images = k; }
+	if (pyramid_bytes) { int64_t b = 0; for (const PyrImage& im : s->images) if (im.kind != IMG_FRAME) b += (int64_t)im.pitch * im.height; *pyramid_bytes = b; }
+	if (n_window_launches) *n_window_launches = (int32_t)s->launches.size();
+	if (n_fast) { int k = 0; for (char f : s->fast) k += f; *n_fast = k; }
+	return FDB_OK;
+} FDB_API_CATCH
+
+int fdb_detector_set_detect_batch(fdb_detector_set* s, const uint8_t* frames_host, int64_t pitch, int32_t n_frames, int32_t stage,
+		fdb_detection* detections_out, int64_t det_cap, int64_t* n_detections) try {
+	return set_detect(s, frames_host, false, pitch, n_frames, stage, nullptr, detections_out, det_cap, n_detections);
+} FDB_API_CATCH
+
+int fdb_detector_set_detect_batch_device(fdb_detector_set* s, const uint8_t* frames_device, int32_t n_frames, int32_t stage,
+		fdb_window_score* const* dense_out_device, fdb_detection* detections_out, int64_t det_cap, int64_t* n_detections) try {
+	return set_detect(s, frames_device, true, 0, n_frames, stage, dense_out_device, detections_out, det_cap, n_detections);
+} FDB_API_CATCH
+
+int fdb_detector_set_profile_device(fdb_detector_set* s, const uint8_t* frames_device, int32_t n_frames, double ms_out[6]) try {
+	if (!s || !s->prepared) return fail(FDB_ERR_INVALID_ARGUMENT, "detector set not prepared");
+	int r = check_ctx(s->ctx); if (r) return r;
+	if (n_frames < 0 || n_frames > s->max_batch || !ms_out || !frames_device) return fail(FDB_ERR_INVALID_ARGUMENT, "bad arguments");
+	cudaEvent_t ev[5];
+	for (int k = 0; k < 5; ++k) CUDA_TRY(cudaEventCreate(&ev[k]));
+	for (int k = 0; k < 6; ++k) ms_out[k] = 0;
+	SetSlot& ss = s->slots[0];
+	for (int base = 0; base < n_frames && r == FDB_OK; base += s->chunk) {
+		ss.base = base; ss.n = std::min(s->chunk, n_frames - base);
+		ss.frames_dev = frames_device + (int64_t)base * s->W * s->H;
+		r = set_enqueue(s, 0, nullptr, ev);
+		if (r) break;
+		if (cudaEventSynchronize(ev[4]) != cudaSuccess) { r = fail(FDB_ERR_CUDA, "profile: event synchronize failed"); break; }
+		float a = 0, b = 0, w = 0, d = 0, t = 0;
+		cudaEventElapsedTime(&a, ev[0], ev[1]); cudaEventElapsedTime(&b, ev[1], ev[2]); cudaEventElapsedTime(&w, ev[2], ev[3]);
+		cudaEventElapsedTime(&d, ev[3], ev[4]); cudaEventElapsedTime(&t, ev[0], ev[4]);
+		ms_out[0] += a; ms_out[1] += b; ms_out[2] += w; ms_out[3] += d; ms_out[4] += t; ms_out[5] += (double)s->launches.size();
+	}
+	for (int k = 0; k < 5; ++k) cudaEventDestroy(ev[k]);
+	return r;
+} FDB_API_CATCH
+
+} // extern "C"

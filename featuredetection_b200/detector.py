@@ -370,6 +370,71 @@ class SlidingWindowCascade:
         return list(c)
 
 
+class DetectorSet:
+    """fdb_detector_set: every detector of an application on every frame (ffpDetectApp.cpp:548-596) over shared pyramids.
+    Results equal those of the members run one by one; `reserved` of a detection = member index."""
+
+    def __init__(self, ctx, cascades):
+        self.ctx, self.members = ctx, list(cascades)
+        arr = (C.c_void_p * len(self.members))(*[c.h for c in self.members])
+        h = C.c_void_p()
+        capi.check(ctx.lib, ctx.lib.fdb_detector_set_create(ctx.h, arr, len(self.members), C.byref(h)))
+        self.h = h
+
+    def __del__(self):
+        try:
+            if self.h and self.ctx.h:
+                self.ctx.lib.fdb_detector_set_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def prepare(self, width, height, max_batch):
+        capi.check(self.ctx.lib, self.ctx.lib.fdb_detector_set_prepare(self.h, width, height, max_batch))
+        self.width, self.height, self.max_batch = width, height, max_batch
+        for c in self.members:
+            c.width, c.height, c.max_batch = width, height, max_batch
+
+    @property
+    def windows_per_frame(self):
+        return int(self.ctx.lib.fdb_detector_set_windows_per_frame(self.h))
+
+    def info(self):
+        ni, nb, nl, nf = C.c_int32(), C.c_int64(), C.c_int32(), C.c_int32()
+        capi.check(self.ctx.lib, self.ctx.lib.fdb_detector_set_info(self.h, C.byref(ni), C.byref(nb), C.byref(nl), C.byref(nf)))
+        return {"pyramid_images": ni.value, "pyramid_bytes": nb.value, "window_launches": nl.value, "fast_members": nf.value}
+
+    def detect(self, frames, stage=capi.FDB_STAGE_NMS, det_cap=None):
+        frames = np.ascontiguousarray(frames, np.uint8)
+        if frames.ndim == 2:
+            frames = frames[None]
+        n, H, W = frames.shape
+        assert (W, H) == (self.width, self.height), "prepare() was called for another frame size"
+        det_cap = det_cap or max(1024, n * 4096 * len(self.members))
+        dets = np.zeros(det_cap, DETECTION_DTYPE)
+        cnt = C.c_int64()
+        capi.check(self.ctx.lib, self.ctx.lib.fdb_detector_set_detect_batch(
+            self.h, frames.ctypes.data, W, n, stage, dets.ctypes.data, det_cap, C.byref(cnt)))
+        return dets[:cnt.value].copy()
+
+    def detect_device(self, frames_ptr, n, stage=capi.FDB_STAGE_NMS, dense_ptrs=None, det_cap=None):
+        """frames in device memory; dense_ptrs: optional list (one device pointer or None per member)"""
+        det_cap = det_cap or max(1024, n * 4096 * len(self.members))
+        dets = np.zeros(det_cap, DETECTION_DTYPE)
+        cnt = C.c_int64()
+        arr = None
+        if dense_ptrs is not None:
+            arr = (C.c_void_p * len(self.members))(*[p if p else None for p in dense_ptrs])
+        capi.check(self.ctx.lib, self.ctx.lib.fdb_detector_set_detect_batch_device(
+            self.h, frames_ptr, n, stage, arr, dets.ctypes.data, det_cap, C.byref(cnt)))
+        return dets[:cnt.value].copy()
+
+    def profile_device(self, frames_ptr, n):
+        ms = (C.c_double * 6)()
+        capi.check(self.ctx.lib, self.ctx.lib.fdb_detector_set_profile_device(self.h, frames_ptr, n, ms))
+        return list(ms)
+
+
 def detect_face_features(face, features, frame, cap=4096):
     """ffpDetectApp.cpp:553-596: face detector on the frame, then each feature detector inside the first face's bounds.
     face / features: prepared SlidingWindowCascade objects. -> (face detections, [feature detections per detector])"""

@@ -58,6 +58,7 @@ typedef struct fdb_wvm fdb_wvm;
 typedef struct fdb_svm fdb_svm;
 typedef struct fdb_rvm fdb_rvm;
 typedef struct fdb_detector fdb_detector;
+typedef struct fdb_detector_set fdb_detector_set;
 
 /* ------------------------------------------------------------------------------------------
  * Model descriptors (host memory, copied during create)
@@ -254,7 +255,7 @@ typedef struct fdb_detection {
 	double svm_probability; /* ProbabilisticSvmClassifier::getProbability */
 	double probability;     /* ClassifiedPatch::getProbability as the reference returns it */
 	int32_t positive;
-	int32_t reserved;
+	int32_t reserved;       /* results of a detector set: index of the detector inside the set; 0 otherwise */
 } fdb_detection;
 
 typedef enum fdb_stage {
@@ -544,6 +545,35 @@ FDB_API int fdb_detect_face_features(fdb_detector* face, fdb_detector* const* fe
  * (the SVM may be NULL: no second stage) working on HistEq64 patches. */
 FDB_API int fdb_evaluate_samples(fdb_detector* det, const uint8_t* frame_host, int64_t pitch, const int32_t* samples_xywh,
 		int64_t n, int32_t max_svm_patches, uint8_t* target_out, double* weight_out);
+
+/* ------------------------------------------------------------------------------------------
+ * Detector set: every detector of an application on every frame
+ * ------------------------------------------------------------------------------------------
+ * ffpDetectApp creates one detector per landmark cfg, each with its own ImagePyramid (ffpDetectApp.cpp:391-500: loop over the
+ * "detectors" nodes; pyramids at :407 and :435), and runs all of them on every frame (ffpDetectApp.cpp:548-596). A set produces
+ * exactly the detections its members would produce one by one (fdb_detect_batch on each), but builds every distinct pyramid
+ * image once per frame and equalises windows of the same layer and size once for all members that scan them.
+ * Members: cascade detectors (WVM first stage) of the same context; the set does not own them (destroy the set first).
+ * Results are ordered by member, then frame, then as fdb_detect_batch orders them; fdb_detection.reserved = member index;
+ * per-member counters through fdb_detector_last_counts. */
+FDB_API int fdb_detector_set_create(fdb_ctx* ctx, fdb_detector* const* detectors, int32_t n_detectors, fdb_detector_set** out);
+FDB_API void fdb_detector_set_destroy(fdb_detector_set* set);
+/* prepares every member (fdb_detector_prepare) and the shared pyramid / work tables for frames of width x height */
+FDB_API int fdb_detector_set_prepare(fdb_detector_set* set, int32_t width, int32_t height, int32_t max_batch);
+FDB_API int64_t fdb_detector_set_windows_per_frame(fdb_detector_set* set); /* all members */
+/* shared pyramid: images built per frame and their bytes, window-kernel launches per chunk, members on the shared kernels */
+FDB_API int fdb_detector_set_info(fdb_detector_set* set, int32_t* n_images, int64_t* pyramid_bytes, int32_t* n_window_launches,
+		int32_t* n_fast_members);
+/* Detector::detect of every member on n_frames host frames (8-bit, 1 channel, row pitch `pitch`) */
+FDB_API int fdb_detector_set_detect_batch(fdb_detector_set* set, const uint8_t* frames_host, int64_t pitch, int32_t n_frames,
+		int32_t stage, fdb_detection* detections_out, int64_t det_cap, int64_t* n_detections);
+/* the same with frames resident in device memory (contiguous); dense_out_device: NULL or one pointer per member
+ * (NULL or device memory [n_frames][windows of that member]) receiving the stage-1 record of every window */
+FDB_API int fdb_detector_set_detect_batch_device(fdb_detector_set* set, const uint8_t* frames_device, int32_t n_frames, int32_t stage,
+		fdb_window_score* const* dense_out_device, fdb_detection* detections_out, int64_t det_cap, int64_t* n_detections);
+/* bench.py: stage-1 kernels of the set serialised between CUDA events, summed over the chunks: ms_out = {resize, pyrDown,
+ * window kernels, deep kernel, total, window-kernel launches} */
+FDB_API int fdb_detector_set_profile_device(fdb_detector_set* set, const uint8_t* frames_device, int32_t n_frames, double ms_out[6]);
 
 /* Per-stage counters of the last detect call (TOT/TACC-style counters, ffpDetectApp.cpp:650-657):
  * [0] windows, [1] wvm positives, [2] after OE, [3] svm positives, [4] after NMS. */
