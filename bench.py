@@ -1,22 +1,25 @@
 #!/usr/bin/env python
 """bench.py - headline benchmark of the sliding-window WVM->SVM landmark detector hot path.
 
-Workload (BASELINE.json configs[1]): a batch of 256 synthetic 640x480 1-channel frames per GPU
-through the FaceFrontal five-stage cascade (full pyramid, hq64 + WVM on all 16 185 windows of every
-frame, overlap elimination, RBF-SVM on the survivors, grid NMS).  One "step" = one pass over one
-such batch per GPU.  Metric: classified patches (windows) per second, whole job.
+Default workload (BASELINE.json north_star / configs[3]): a batch of 256 synthetic 640x480 1-channel frames per GPU through
+ALL 15 ffpDetectApp landmark detectors (WVM->SVM five-stage cascades, hq64 features, full pyramids, step 1): every frame is
+scanned by every detector, 4 302 040 classified windows per frame. One "step" = one pass over one such batch per GPU.
+Metric: classified patches (windows) per second, whole job. The line also carries a `facefrontal` block: BASELINE
+configs[1] (256 frames, FaceFrontal cascade alone, HOG SVM stage) measured in the same run, for round-over-round comparison.
 
   value   frames already resident in HBM; timed with CUDA events on the library's stream
-  e2e     the same through the C ABI call a user makes (fdb_detect_batch) with HOST (pinned)
-          frames: H2D copy of the frames and D2H of the results inside the timed region
-  roofline.achieved  algorithmic bytes (W*H + 8 B per window, per frame) of the
-          dominant kernel (fused hq64+WVM window kernel) / its CUDA-event duration
-  cpu_baseline       the CPU oracle port timed on this box's host cores on a bounded sample
+  e2e     the same through the C ABI call a user makes (fdb_detector_set_detect_batch) with HOST (pinned) frames: H2D copy
+          of the frames and D2H of the results inside the timed region
+  roofline.achieved  algorithmic bytes (W*H + 8 B per window, per frame) of the dominant kernel (the fused
+          hq64 + WVM window kernel, all its launches of a step) / its CUDA-event duration
+  cpu_baseline       the reference's own classes (oracle/_ref) timed on this box's host cores on a bounded sample
 
---impl reference times the reference's own CPU implementation (oracle/_ref when built, else the
-oracle port) on the same workload with all host cores.
-Multi-GPU (torchrun): frames are sharded over ranks (weak scaling: 256 frames per GPU), models are
-replicated, the only exchange is the final NCCL gather of the detection records.
+--impl reference times the reference's own CPU implementation (oracle/_ref when built, else the oracle port) on the same
+workload with all host cores: (frame, detector) pairs are spread over one process per core; pyramids come from cv2's SIMD
+cv::resize / cv::pyrDown (what the reference links), frames are generated outside the timed region.
+Multi-GPU (torchrun): frames are sharded over ranks (weak scaling: --frames per GPU; --frames-total T: strong scaling, T
+frames split over the ranks), models are replicated, the only exchange is ONE NCCL gather of the detection records at the
+end of the job.
 """
 import argparse
 import json
@@ -55,53 +58,87 @@ def feature_svm_model(syn, feature, det_kw, layers, extract):
     return syn.make_feature_svm(np.concatenate(vecs), seed=300, num_sv=1024, gamma=syn.FEATURE_GAMMA[feature], center=True)
 
 
-def _cpu_worker_init(kind, profile, feature="hq64"):
+def cascade_names(workload):
+    from featuredetection_b200 import synthetic as syn
+    return [CFG] if workload == "facefrontal" else [c[0] for c in syn.LANDMARK_CONFIGS]
+
+
+def _cpu_worker_init(kind, profile, feature, names):
+    """one process per host core (the reference objects are not thread-safe): every worker holds
+    the classifiers of every detector of the workload"""
     from featuredetection_b200 import synthetic as syn
     from oracle import fdoracle as fo
-    det_kw, wvm, svm = syn.landmark_models(CFG, profile)
+    try:
+        import cv2
+        cv2.setNumThreads(1)
+        have_cv2 = True
+    except Exception:
+        have_cv2 = False
     use_ref = kind == "reference"
-    feat = None
-    if feature != "hq64":
-        feat = fo.Features(syn.feature_desc(kind=feature), det_kw["patch_width"], det_kw["patch_height"])
-        r = fo.detect_frame(det_kw, fo.Wvm(wvm), None, syn.synthetic_frame(0), stage=1, want_dense=False)
-        svm = feature_svm_model(syn, feature, det_kw, r["layers"], lambda fr, lxy: feat.extract(det_kw, fr, lxy))
-    _worker_state.update(det_kw=det_kw, wvm=fo.Wvm(wvm, use_ref=use_ref), svm=fo.Svm(svm, use_ref=use_ref),
-                         use_ref=use_ref, fo=fo, syn=syn, feat=feat)
+    models = {}
+    for nm in names:
+        det_kw, wvm, svm = syn.landmark_models(nm, profile)
+        feat = None
+        if feature != "hq64":
+            feat = fo.Features(syn.feature_desc(kind=feature), det_kw["patch_width"], det_kw["patch_height"])
+            r = fo.detect_frame(det_kw, fo.Wvm(wvm), None, syn.synthetic_frame(0), stage=1, want_dense=False)
+            svm = feature_svm_model(syn, feature, det_kw, r["layers"], lambda fr, lxy: feat.extract(det_kw, fr, lxy))
+        models[nm] = (det_kw, fo.Wvm(wvm, use_ref=use_ref), fo.Svm(svm, use_ref=use_ref), feat)
+    _worker_state.update(models=models, use_ref=use_ref, fo=fo, pyramid_impl="cv2" if (use_ref and have_cv2) else "restated")
 
 
-def _cpu_worker_run(frame_ids):
+def _cpu_worker_item(item):
+    """one (frame, detector) pair: Detector::detect of that detector on that frame"""
+    frame, name = item
     st = _worker_state
-    fo, syn = st["fo"], st["syn"]
-    windows = 0
+    fo = st["fo"]
+    det_kw, wvm, svm, feat = st["models"][name]
     t0 = time.perf_counter()
-    for k in frame_ids:
-        frame = syn.synthetic_frame(k)
-        if st["use_ref"]:
-            r = fo.ref_detect_frame(st["det_kw"], st["wvm"], st["svm"], frame, want_dense=False, svm_features=st["feat"])
-        else:
-            r = fo.detect_frame(st["det_kw"], st["wvm"], st["svm"], frame, want_dense=False, svm_features=st["feat"])
-        windows += r["windows"]
-    return windows, time.perf_counter() - t0
+    if st["use_ref"]:
+        r = fo.ref_detect_frame(det_kw, wvm, svm, frame, want_dense=False, svm_features=feat, pyramid_impl=st["pyramid_impl"])
+        split = list(r["timing"])
+    else:
+        r = fo.detect_frame(det_kw, wvm, svm, frame, want_dense=False, svm_features=feat, timing=True)
+        split = list(r["timing"])[:5]
+    return r["windows"], time.perf_counter() - t0, split, st["pyramid_impl"]
 
 
 class CpuArm:
-    """The reference CPU path on all host cores (one process per core: the reference objects are
-    not thread-safe)."""
+    """The reference CPU path on all host cores: (frame, detector) pairs, longest first, over one process per core."""
 
-    def __init__(self, profile, feature="hq64"):
+    SPLIT = ("pyramid", "extract+hq64", "wvm", "overlap_elimination", "svm+nms")
+
+    def __init__(self, workload, profile, feature="hq64"):
         from oracle import fdoracle as fo
+        from featuredetection_b200 import synthetic as syn
         fo.build()
         self.kind = "reference" if fo.ref_available() else "port"
         self.cores = os.cpu_count() or 1
-        self.pool = mp.get_context("spawn").Pool(self.cores, initializer=_cpu_worker_init, initargs=(self.kind, profile, feature))
+        self.names = cascade_names(workload)
+        self.syn = syn
+        self.pool = mp.get_context("spawn").Pool(self.cores, initializer=_cpu_worker_init,
+                                                 initargs=(self.kind, profile, feature, self.names))
+        self.pyramid_impl = None
 
-    def run(self, frames_per_core, first_frame=0):
-        chunks = [list(range(first_frame + c * frames_per_core, first_frame + (c + 1) * frames_per_core))
-                  for c in range(self.cores)]
+    def frames(self, first, count):
+        """generated OUTSIDE the timed region (the GPU arm pre-generates its frames too)"""
+        return [self.syn.synthetic_frame(first + k) for k in range(count)]
+
+    def run(self, frames):
+        # longest first: windows per frame of each cfg at 640x480 (SURVEY.md section 8), only used to order the work
+        cost = {"FaceFrontal": 16, "FaceLeftProfile": 60, "FaceRightProfile": 60, "RightEyeCenter": 158}
+        items = [(f, nm) for f in frames for nm in self.names]
+        items.sort(key=lambda it: -cost.get(it[1], 365))
         t0 = time.perf_counter()
-        res = self.pool.map(_cpu_worker_run, chunks)
+        res = list(self.pool.imap_unordered(_cpu_worker_item, items, chunksize=1))
         wall = time.perf_counter() - t0
-        return sum(r[0] for r in res), wall
+        split = np.sum([r[2] for r in res], axis=0)
+        self.pyramid_impl = res[0][3]
+        return sum(r[0] for r in res), wall, {k: float(v) for k, v in zip(self.SPLIT, split)}
+
+    def describe(self):
+        return ("cv2 %s (SIMD cv::resize / cv::pyrDown, one pyramid per detector and frame as the reference builds them)" % __import__("cv2").__version__
+                if self.pyramid_impl == "cv2" else "scalar restatement (oracle/fd_oracle.c)")
 
     def close(self):
         self.pool.close()
@@ -404,51 +441,63 @@ def hbm_peak():
 
 
 # ------------------------------------------------------------------------------------------------
+WINDOWS_PER_FRAME = {"facefrontal": 16185, "landmarks15": 4302040}  # SURVEY.md section 8 (checked against the plan at run time)
+
+
 def run_reference(args, rank, world):
+    """the reference's own CPU implementation of the workload on all host cores of this box (rank 0 only)"""
     if rank != 0:
         return
-    arm = CpuArm(args.profile, args.feature)
-    per_core = args.ref_frames_per_core
-    for _ in range(args.warmup):
-        arm.run(1)
-    times, windows = [], 0
+    arm = CpuArm(args.workload, args.profile, args.feature)
+    nfr = args.ref_frames_per_step
+    warm = arm.frames(0, 1)
+    for _ in range(max(args.warmup, 1)):
+        arm.run(warm)
+    times, windows, split = [], 0, None
     for s in range(args.steps):
-        w, wall = arm.run(per_core, first_frame=s * per_core * arm.cores)
+        frames = arm.frames(100 + s * nfr, nfr)   # outside the timed region
+        w, wall, sp = arm.run(frames)
         windows += w
         times.append(wall)
+        split = sp if split is None else {k: split[k] + sp[k] for k in sp}
+    pyr = arm.describe()
     arm.close()
     total = sum(times)
     value = windows / total
-    sample = "%d frames per step (%d per core x %d processes), %d steps" % (per_core * arm.cores, per_core, arm.cores, args.steps)
+    wpf = WINDOWS_PER_FRAME[args.workload]
+    sample = "%d frames x %d detectors per step = %d (frame, detector) items over %d processes, %d steps" % (
+        nfr, len(arm.names), nfr * len(arm.names), arm.cores, args.steps)
     line = {
         "impl": "reference", "metric": "classified_patches_per_s", "value": value, "unit": "patches/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/f32/f64", "data": "synthetic",
-        "config": workload_config(args, world, sample),
-        "cpu_baseline": {"value": value, "unit": "patches/s", "cores": arm.cores, "kind": arm.kind, "sample": sample},
+        "higher_is_better": True, "scaling": "strong" if args.frames_total else "weak", "vs_baseline": None, "dtype": "u8/f32/f64", "data": "synthetic",
+        "config": workload_config(args, world),
+        "cpu_baseline": {"value": value, "unit": "patches/s", "cores": arm.cores, "kind": arm.kind, "sample": sample,
+                         "pyramid": pyr, "split_core_seconds": split},
         "e2e": {"value": value, "unit": "patches/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "frames_per_s": value / 16185.0,
+        "frames_per_s": value / wpf,
     }
     emit(line)
 
 
 def workload_config(args, world, extra=None):
+    frames = args.frames
     if args.workload == "facefrontal":
         fdesc = ("hq64 u8 features for both stages, as ffpDetectApp wires it" if args.feature == "hq64" else
                  "WVM on hq64 patches, RBF-SVM on %s features (adaptiveTrackingApp/default.cfg parameters: 9 unsigned bins, "
                  "interpolated binning, cell 5, block 1, l2norm -> 144-d float32)" % args.feature.upper() if args.feature == "hog" else
                  "WVM on hq64 patches, RBF-SVM on %s features" % args.feature.upper())
         wl = ("BASELINE configs[1]: %d-frame batch per GPU, 640x480 1-channel, FaceFrontal WVM->SVM five-stage cascade "
-              "(%s), full pyramid, step 1x1" % (args.frames, fdesc))
+              "(%s), full pyramid, step 1x1" % (frames, fdesc))
         wpf, pyr = 16185, 1931000
     else:
-        wl = ("BASELINE configs[3] shape: %d-frame batch per GPU, 640x480 1-channel, all 15 ffpDetectApp landmark detectors per frame "
-              "(WVM->SVM cascades, hq64 u8 features), one pyramid per detector as the reference builds them" % args.frames)
-        wpf, pyr = 4302040, 15 * 500000
-    cfg = {"workload": wl, "frames_per_gpu": args.frames, "global_frames": args.frames * world, "windows_per_frame": wpf,
+        wl = ("BASELINE north_star / configs[3]: %d-frame batch per GPU, 640x480 1-channel, all 15 ffpDetectApp landmark detectors on every "
+              "frame (WVM->SVM five-stage cascades, hq64 u8 features for both stages as ffpDetectApp wires them, full pyramids, step 1x1)" % frames)
+        wpf, pyr = 4302040, 1110000
+    cfg = {"workload": wl, "frames_per_gpu": frames, "global_frames": frames * world, "windows_per_frame": wpf,
            "threshold_profile": args.profile, "parallelism": "frame-sharded dp%d" % world,
            "l2": "per-step working set (frames + materialised pyramids + dense records = %.0f MB) exceeds the 126 MB L2; a 256 MB "
-                 "scratch write also flushes L2 between timed steps" % ((W * H + pyr + 8 * wpf) * args.frames / 1e6)}
+                 "scratch write also flushes L2 between timed steps" % ((W * H + pyr + 8 * wpf) * frames / 1e6)}
     if extra:
         cfg["sample"] = extra
     return cfg
@@ -711,6 +760,143 @@ def emit(line):
     _JSON_OUT.flush()
 
 
+def pin_rank_to_cores(local_rank, world):
+    """each rank's host threads (pipeline thread, CUDA driver threads) stay on their own share of the host cores"""
+    try:
+        cores = sorted(os.sched_getaffinity(0))
+        if world > 1 and len(cores) >= world:
+            per = len(cores) // world
+            os.sched_setaffinity(0, set(cores[local_rank * per:(local_rank + 1) * per]))
+            return per
+        return len(cores)
+    except Exception:
+        return None
+
+
+def measure_cascades(args, workload, feature, n, rank, world, device, ctx, dist, steps, warmup, sampler=None, gather=None, lo=0):
+    """value / e2e / stage-1 profile of one cascade workload (all ranks call this; collective-free except the max-reduce of
+    the timings and the final gather)."""
+    import torch
+    from featuredetection_b200 import capi, synthetic as syn
+    from featuredetection_b200.detector import SlidingWindowCascade, DetectorSet, DETECTION_DTYPE
+    names = cascade_names(workload)
+    cascs = []
+    for nm in names:
+        det_kw, wvm, svm = syn.landmark_models(nm, args.profile)
+        if args.profile == "no-exit":
+            det_kw = dict(det_kw, max_positives_per_frame=400000)
+        fdesc = None
+        if feature != "hq64":
+            fdesc = syn.feature_desc(kind=feature)
+            probe = SlidingWindowCascade(ctx, det_kw, wvm, None, feature=fdesc)  # the product's own extractor builds the SVM's support vectors
+            probe.prepare(W, H, 1)
+            svm = feature_svm_model(syn, feature, det_kw, probe.layers(), probe.extract_features)
+            del probe
+        cascs.append(SlidingWindowCascade(ctx, det_kw, wvm, svm, feature=fdesc))
+    dset = None
+    if len(cascs) > 1:  # all detectors of the application on every frame: one detector set
+        dset = DetectorSet(ctx, cascs)
+        dset.prepare(W, H, n)
+    else:
+        cascs[0].prepare(W, H, n)
+    nwin = sum(c.windows_per_frame for c in cascs)
+    assert nwin == WINDOWS_PER_FRAME[workload], (nwin, workload)
+    max_nwin = max(c.windows_per_frame for c in cascs)
+    stage = capi.FDB_STAGE_NMS if args.profile == "realistic" else capi.FDB_STAGE_WVM
+    det_cap = (64 * n if args.profile == "realistic" else max_nwin * n) * len(cascs)
+
+    # this rank's shard of the global batch: n frames starting at global frame lo, 8 distinct frames tiled
+    base = syn.synthetic_frames(lo % 97, min(8, n))
+    host_frames = torch.from_numpy(np.concatenate([base] * ((n + len(base) - 1) // len(base)))[:n]).pin_memory()
+    dev_frames = host_frames.to(device)
+    dev_dense = [torch.empty((n, c.windows_per_frame, 2), dtype=torch.int32, device=device) for c in cascs]
+    dense_ptrs = [t.data_ptr() for t in dev_dense]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ctx.synchronize()
+
+    def flush_l2():
+        flush.fill_(1)
+        torch.cuda.synchronize()
+
+    def step_resident():
+        if dset is not None:
+            return dset.detect_device(dev_frames.data_ptr(), n, stage=stage, dense_ptrs=dense_ptrs, det_cap=det_cap)
+        return cascs[0].detect_device(dev_frames.data_ptr(), n, stage=stage, dense_ptr=dense_ptrs[0], det_cap=det_cap)
+
+    def step_e2e():
+        if dset is not None:
+            return dset.detect(host_frames.numpy(), stage=stage, det_cap=det_cap)
+        return cascs[0].detect(host_frames.numpy(), stage=stage, det_cap=det_cap)
+
+    def final_gather(dets):
+        """one exchange at the end of the job - the positives block of every rank (NCCL over NVLink)"""
+        if gather is not None:
+            gather(dets[:gather.capacity], lo)
+
+    def timed(step_fn):
+        barrier()
+        launches0 = ctx.launch_count()
+        ms = []
+        dets = None
+        for k in range(steps):
+            flush_l2()
+            ctx.timer_start()
+            dets = step_fn()
+            if k == steps - 1:
+                final_gather(dets)   # inside the timed region of the last step
+            ms.append(ctx.timer_stop())
+        barrier()
+        tot = torch.tensor([sum(ms)], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(tot, op=dist.ReduceOp.MAX)
+        per_rank = None
+        if world > 1:
+            mine = torch.tensor([min(ms), float(np.median(ms)), max(ms)], dtype=torch.float64, device=device)
+            allr = [torch.empty_like(mine) for _ in range(world)]
+            dist.all_gather(allr, mine)
+            per_rank = [[round(float(x), 3) for x in t.cpu().tolist()] for t in allr]
+        return float(tot.item()), ms, dets, ctx.launch_count() - launches0, per_rank
+
+    for _ in range(warmup):
+        step_resident()
+    if sampler is not None and rank == 0:
+        sampler.start()
+    total_ms, step_ms, dets, launches, per_rank = timed(step_resident)
+    host_ms = dset.last_host_ms() if dset is not None else None
+
+    # dominant kernel: CUDA events around the stage-1 kernels (serialised)
+    prof = []
+    for _ in range(max(min(steps, 5), 3)):
+        flush_l2()
+        prof.append(np.array(dset.profile_device(dev_frames.data_ptr(), n)) if dset is not None
+                    else np.array(cascs[0].profile_device(dev_frames.data_ptr(), n)))
+    prof = np.array(prof).mean(axis=0)
+
+    for _ in range(2):
+        step_e2e()
+    e2e_total, e2e_ms, dets_e2e, _, e2e_per_rank = timed(step_e2e)
+    info = dset.info() if dset is not None else {"pyramid_images": None, "pyramid_bytes": cascs[0].pyramid_bytes,
+                                                  "window_launches": 1, "fast_members": 1}
+    return dict(nwin=nwin, n_detectors=len(cascs), total_ms=total_ms, step_ms=step_ms, e2e_total=e2e_total, e2e_ms=e2e_ms,
+                launches=int(launches), prof=prof, n_dets=int(len(dets)), d2h=int(len(dets_e2e) * DETECTION_DTYPE.itemsize + 8),
+                per_rank=per_rank, e2e_per_rank=e2e_per_rank, info=info, host_ms=host_ms)
+
+
+def measured_traffic(kernel):
+    """dram bytes per launch of a kernel from the committed ncu --set full capture (profiles/traffic.json names the capture)"""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(p):
+        return None, None
+    t = json.load(open(p)).get(kernel)
+    return (t["dram_bytes_per_launch"], t["source"]) if t else (None, None)
+
+
 def main():
     _claim_stdout()
     ap = argparse.ArgumentParser()
@@ -718,27 +904,39 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--frames", type=int, default=None, help="frames per GPU per step (default 256; 16 for landmarks15)")
-    ap.add_argument("--workload", default="facefrontal", choices=["facefrontal", "landmarks15", "sdm", "single-psvm"],
-                    help="sdm = BASELINE configs[4] (supervised-descent fit, 68 landmarks, 4096 faces per GPU); facefrontal = BASELINE configs[1] (headline); landmarks15 = all 15 ffpDetectApp landmark detectors per frame (configs[3] shape, hq64 features)")
+    ap.add_argument("--frames", type=int, default=None, help="frames per GPU per step (default 256; 4096 faces for sdm)")
+    ap.add_argument("--frames-total", type=int, default=None, help="strong scaling: this many frames per step split over the ranks (BASELINE configs[3]: 4096)")
+    ap.add_argument("--workload", default="landmarks15", choices=["landmarks15", "facefrontal", "sdm", "single-psvm"],
+                    help="landmarks15 (default, headline) = all 15 ffpDetectApp landmark detectors on every frame (BASELINE north_star / configs[3]); "
+                         "facefrontal = BASELINE configs[1]; sdm = BASELINE configs[4] (supervised-descent fit, 68 landmarks, 4096 faces per GPU); "
+                         "single-psvm = the `single` detector, every window through the RBF-SVM")
     ap.add_argument("--profile", default="realistic", choices=["realistic", "no-exit"])
     ap.add_argument("--feature", default=None, choices=["hq64", "hog", "whi", "lbp", "histeq", "ehog"],
                     help="feature space of the second-stage SVM (default: hog for facefrontal = BASELINE configs[1]; hq64 for landmarks15)")
-    ap.add_argument("--cpu-frames-per-core", type=int, default=32, help="cpu_baseline sample size per host core")
-    ap.add_argument("--ref-frames-per-core", type=int, default=2, help="--impl reference: frames per core per step")
+    ap.add_argument("--cpu-frames", type=int, default=None, help="cpu_baseline sample: frames (each through every detector of the workload)")
+    ap.add_argument("--ref-frames-per-step", type=int, default=None, help="--impl reference: frames per step (each through every detector)")
+    ap.add_argument("--cpu-frames-per-core", type=int, default=32, help="sdm / single-psvm: cpu_baseline sample size per host core")
+    ap.add_argument("--ref-frames-per-core", type=int, default=2, help="sdm / single-psvm, --impl reference: frames per core per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-facefrontal", action="store_true", help="landmarks15: skip the nested BASELINE configs[1] block")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.frames_total:
+        args.frames = max(1, args.frames_total // world)
     if args.frames is None:
-        args.frames = {"facefrontal": 256, "landmarks15": 16, "sdm": 4096, "single-psvm": 256}[args.workload]
+        args.frames = {"facefrontal": 256, "landmarks15": 256, "sdm": 4096, "single-psvm": 256}[args.workload]
     if args.feature is None:
         args.feature = "hog" if args.workload == "facefrontal" else "hq64"
     if args.workload == "landmarks15" and args.feature != "hq64":
         raise SystemExit("bench.py: --feature applies to the facefrontal workload")
+    if args.ref_frames_per_step is None:
+        args.ref_frames_per_step = 32 if args.workload == "facefrontal" else 2   # >= 16 work items per core (facefrontal) / 30 heavy items (15 detectors)
+    if args.cpu_frames is None:
+        args.cpu_frames = 512 if args.workload == "facefrontal" else 6
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.workload == "single-psvm":
         if args.impl == "reference":
             run_reference_single(args, rank, world)
@@ -757,195 +955,93 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from featuredetection_b200 import capi, synthetic as syn, sharding
-    from featuredetection_b200.detector import Context, SlidingWindowCascade, DetectorSet, DETECTION_DTYPE
+    from featuredetection_b200 import sharding
+    from featuredetection_b200.detector import Context
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device - the B200 path has no CPU fallback (use --impl reference for the CPU arm)")
+    host_cores = pin_rank_to_cores(local_rank, world)
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # NCCL writes its version banner / debug lines to stdout by default: keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=device)
 
-    names = [CFG] if args.workload == "facefrontal" else [c[0] for c in syn.LANDMARK_CONFIGS]
     ctx = Context(local_rank)
     n = args.frames
-    cascs = []
-    for nm in names:
-        det_kw, wvm, svm = syn.landmark_models(nm, args.profile)
-        if args.profile == "no-exit":
-            det_kw = dict(det_kw, max_positives_per_frame=400000)
-        fdesc = None
-        if args.feature != "hq64":
-            fdesc = syn.feature_desc(kind=args.feature)
-            probe = SlidingWindowCascade(ctx, det_kw, wvm, None, feature=fdesc)  # the product's own extractor builds the SVM's support vectors
-            probe.prepare(W, H, 1)
-            svm = feature_svm_model(syn, args.feature, det_kw, probe.layers(), probe.extract_features)
-            del probe
-        c = SlidingWindowCascade(ctx, det_kw, wvm, svm, feature=fdesc)
-        c.prepare(W, H, n)
-        cascs.append(c)
-    dset = None
-    if len(cascs) > 1:  # all detectors of the application on every frame: one detector set (shared pyramids, shared equalisation)
-        dset = DetectorSet(ctx, cascs)
-        dset.prepare(W, H, n)
-    nwin = sum(c.windows_per_frame for c in cascs)          # windows per frame over all detectors
-    max_nwin = max(c.windows_per_frame for c in cascs)
-    stage = capi.FDB_STAGE_NMS if args.profile == "realistic" else capi.FDB_STAGE_WVM
-    det_cap = 64 * n if args.profile == "realistic" else max_nwin * n
-
-    # this rank's shard of the global batch (weak scaling: n frames per rank), 8 distinct frames tiled
-    lo, hi = sharding.shard_range(n * world, rank, world)
-    base = syn.synthetic_frames(lo % 97, min(8, n))
-    host_frames = torch.from_numpy(np.concatenate([base] * ((n + len(base) - 1) // len(base)))[:n]).pin_memory()
-    dev_frames = host_frames.to(device)
-    dev_dense = torch.empty((n, max_nwin, 2), dtype=torch.int32, device=device)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
-    gather_cap = max(256, 8 * n) * len(cascs)  # fixed-size gather block per rank
-    gather = sharding.DetectionGather(gather_cap, dist, device) if world > 1 else None
-    torch.cuda.synchronize()
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        ctx.synchronize()
-
-    def flush_l2():
-        flush.fill_(1)
-        torch.cuda.synchronize()
-
-    pending = [None]
-
-    def finish_gather():
-        """wait for the outstanding result gather (it overlaps the next step's kernels)"""
-        if pending[0] is not None:
-            gather.collect(pending[0])
-            pending[0] = None
-
-    def exchange(dets):
-        if world > 1:
-            ticket = gather.submit(dets[:gather_cap], lo)
-            finish_gather()
-            pending[0] = ticket
-
-    dense_ptrs = None
-    if dset is not None:
-        dev_dense_all = [torch.empty((n, c.windows_per_frame, 2), dtype=torch.int32, device=device) for c in cascs]
-        dense_ptrs = [t.data_ptr() for t in dev_dense_all]
-
-    def step_resident():
-        if dset is not None:
-            dets = dset.detect_device(dev_frames.data_ptr(), n, stage=stage, dense_ptrs=dense_ptrs, det_cap=det_cap * len(cascs))
-        else:
-            dets = cascs[0].detect_device(dev_frames.data_ptr(), n, stage=stage, dense_ptr=dev_dense.data_ptr(), det_cap=det_cap)
-        exchange(dets)
-        return dets
-
-    def step_e2e():
-        if dset is not None:
-            dets = dset.detect(host_frames.numpy(), stage=stage, det_cap=det_cap * len(cascs))
-        else:
-            dets = cascs[0].detect(host_frames.numpy(), stage=stage, det_cap=det_cap)
-        exchange(dets)
-        return dets
-
-    # ---- value: HBM-resident ---------------------------------------------------------------
-    for _ in range(args.warmup):
-        step_resident()
-    finish_gather()
+    lo, _ = sharding.shard_range(n * world, rank, world)
+    n_det = len(cascade_names(args.workload))
+    gather = sharding.DetectionGather(max(256, 64 * n) * n_det, dist, device) if world > 1 else None
     sampler = ClockSampler(local_rank)
-    barrier()
-    launches0 = ctx.launch_count()
-    if rank == 0:
-        sampler.start()
-    step_ms = []
-    for _ in range(args.steps):
-        flush_l2()
-        ctx.timer_start()
-        dets = step_resident()
-        if _ == args.steps - 1:
-            finish_gather()  # the last step's gather completes inside the timed region
-        step_ms.append(ctx.timer_stop())
-    barrier()
-    launches = ctx.launch_count() - launches0
-    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=device)
-    if world > 1:
-        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
-    total_ms = float(total_ms.item())
-
-    # ---- dominant kernel: CUDA events around the fused window kernel ---------------------------
-    prof = []
-    for _ in range(max(args.steps, 5)):
-        flush_l2()
-        prof.append(np.array(dset.profile_device(dev_frames.data_ptr(), n)) if dset is not None
-                    else np.array(cascs[0].profile_device(dev_frames.data_ptr(), n)))
-    prof = np.array(prof)
-    ms_resize, ms_down, ms_wvm, ms_deep, ms_stage1, n_launch = prof.mean(axis=0)
-
-    # ---- e2e: host frames through the public call ---------------------------------------------
-    for _ in range(2):
-        step_e2e()
-    finish_gather()
-    barrier()
-    e2e_ms = []
-    for _ in range(args.steps):
-        flush_l2()
-        ctx.timer_start()
-        dets_e2e = step_e2e()
-        if _ == args.steps - 1:
-            finish_gather()
-        e2e_ms.append(ctx.timer_stop())
-    barrier()
+    m = measure_cascades(args, args.workload, args.feature, n, rank, world, device, ctx, dist, args.steps, args.warmup,
+                         sampler=sampler, gather=gather, lo=lo)
+    ff = None
+    if args.workload == "landmarks15" and not args.no_facefrontal:
+        ff = measure_cascades(args, "facefrontal", "hog", 256, rank, world, device, ctx, dist, max(args.steps, 10), 3, lo=256 * rank)
     clocks = sampler.stop() if rank == 0 else None
-    e2e_total = torch.tensor([sum(e2e_ms)], dtype=torch.float64, device=device)
-    if world > 1:
-        dist.all_reduce(e2e_total, op=dist.ReduceOp.MAX)
-    e2e_total = float(e2e_total.item())
 
     if rank == 0:
+        nwin = m["nwin"]
         windows_step = nwin * n * world
-        value = windows_step * args.steps / (total_ms * 1e-3)
-        e2e_value = windows_step * args.steps / (e2e_total * 1e-3)
+        value = windows_step * args.steps / (m["total_ms"] * 1e-3)
+        e2e_value = windows_step * args.steps / (m["e2e_total"] * 1e-3)
         peak, peak_src = hbm_peak()
-        # dominant kernel = wvm_strip_kernel; one launch covers one internal chunk of the batch
-        frames_per_launch = n * len(cascs) / n_launch
-        algo_bytes = (W * H + WINDOW_BYTES * nwin / len(cascs)) * frames_per_launch   # SURVEY 8(d): frame read once + dense records
-        kernel_ms = ms_wvm / n_launch
-        achieved = algo_bytes / (kernel_ms * 1e-3) / 1e9
-        # dram__bytes_read.sum + dram__bytes_write.sum of one wvm_strip_mma_kernel launch (64 frames, FaceFrontal) from
-        # profiles/wvm_r1w_raw.txt (ncu --set full): 2.939 MB + 1 KB; the layers it reads were just written by pyrDown and sit in L2
-        traffic = 2940416 if args.workload == "facefrontal" and n == 256 else None
+        ms_resize, ms_down, ms_wvm, ms_deep, ms_stage1, n_launch = m["prof"]
+        # dominant kernel = wvm_group_kernel (all its launches of a step together): SURVEY 8(d) bytes = frame read once + dense records
+        algo_bytes = (W * H + WINDOW_BYTES * nwin) * n
+        achieved = algo_bytes / (ms_wvm * 1e-3) / 1e9
+        kname = "wvm_group_kernel/landmarks15" if args.workload == "landmarks15" else "wvm_group_kernel/facefrontal"
+        traffic, traffic_src = measured_traffic(kname)
         cpu = None
         if not args.no_cpu_baseline and world == 1:  # the CPU baseline is a rank-0, N=1 datum
-            arm = CpuArm(args.profile, args.feature)
-            arm.run(1)
-            wcpu, wall = arm.run(args.cpu_frames_per_core)
-            arm.close()
+            arm = CpuArm(args.workload, args.profile, args.feature)
+            arm.run(arm.frames(0, 1))
+            per = args.ref_frames_per_step
+            wcpu, wall, split = 0, 0.0, None
+            for k in range(max(1, args.cpu_frames // per)):   # the same step size as --impl reference
+                w_, t_, sp = arm.run(arm.frames(100 + k * per, per))
+                wcpu += w_; wall += t_
+                split = sp if split is None else {q: split[q] + sp[q] for q in sp}
             cpu = {"value": wcpu / wall, "unit": "patches/s", "cores": arm.cores, "kind": arm.kind,
-                   "sample": "%d frames of the same workload (%d per core x %d processes), %.1f s wall" % (
-                       args.cpu_frames_per_core * arm.cores, args.cpu_frames_per_core, arm.cores, wall)}
+                   "sample": "%d frames x %d detectors of the same workload in steps of %d frames over %d processes, %.1f s wall" % (
+                       max(1, args.cpu_frames // per) * per, len(arm.names), per, arm.cores, wall),
+                   "pyramid": arm.describe(), "split_core_seconds": split}
+            arm.close()
         line = {
             "metric": "classified_patches_per_s", "value": value, "unit": "patches/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/f32/f64", "data": "synthetic",
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": m["total_ms"] / args.steps,
+            "higher_is_better": True, "scaling": "strong" if args.frames_total else "weak", "vs_baseline": None,
+            "dtype": "u8/f32/f64", "data": "synthetic",
             "config": workload_config(args, world),
             "frames_per_s": value / nwin,
             "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": "patches/s", "h2d_bytes_per_step": int(W * H * n * (1 if dset is not None else len(cascs))),
-                    "d2h_bytes_per_step": int(len(dets_e2e) * DETECTION_DTYPE.itemsize + 4),
-                    "ms_per_step": e2e_total / args.steps, "frames_per_s": e2e_value / nwin},
-            "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "wvm_strip_mma_kernel (fused HistEq64 + the first 8 WVM filters of every window as an exact u8 IMMA product; one launch per 64-frame chunk)",
+            "e2e": {"value": e2e_value, "unit": "patches/s", "h2d_bytes_per_step": int(W * H * n),
+                    "d2h_bytes_per_step": m["d2h"], "ms_per_step": m["e2e_total"] / args.steps, "frames_per_s": e2e_value / nwin},
+            "gpu_launches": m["launches"],
+            "roofline": {"bound": "hbm", "kernel": "wvm_group_kernel (fused HistEq64 + the first 8 WVM filters of every window of every detector as exact u8 "
+                                                   "IMMA products; %d launches per step, timed together)" % int(n_launch),
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                         "peak_source": peak_src, "algorithmic_bytes_per_launch": int(algo_bytes),
-                         "kernel_ms": float(kernel_ms), "launches_per_step": int(n_launch),
-                         "note": "instruction/LSU bound by construction: ~5e3 scalar ops per window vs 27 B of compulsory traffic (SURVEY.md 8(d)); issue-slot utilisation 50 % (profiles/wvm_r1w_raw.txt)"},
-            "stage1_ms": {"resize": float(ms_resize), "pyrdown": float(ms_down), "window_kernel": float(ms_wvm), "deep_kernel": float(ms_deep), "total": float(ms_stage1)},
-            "detections_per_step": int(len(dets)) * world,
+                         "traffic_source": traffic_src, "peak_source": peak_src, "algorithmic_bytes_per_step": int(algo_bytes),
+                         "kernel_ms_per_step": float(ms_wvm), "launches_per_step": int(n_launch),
+                         "note": "instruction-issue / shared-memory bound by construction: ~6e3 warp instructions per 32 windows vs 8 B of compulsory "
+                                 "traffic per window (SURVEY.md 8(d)); issue-slot utilisation and pipe shares in profiles/"},
+            "stage1_ms": {"resize": float(ms_resize), "pyrdown": float(ms_down), "window_kernels": float(ms_wvm), "deep_kernel": float(ms_deep),
+                          "total": float(ms_stage1)},
+            "detector_set": m["info"],
+            "host_ms_last_step": m["host_ms"],
+            "detections_per_step": m["n_dets"] * world,
+            "host_cores_per_rank": host_cores,
+            "step_ms_per_rank_min_median_max": m["per_rank"], "e2e_step_ms_per_rank_min_median_max": m["e2e_per_rank"],
             "cpu_baseline": cpu,
         }
+        if ff is not None:
+            ffw = ff["nwin"] * 256 * world
+            line["facefrontal"] = {
+                "workload": "BASELINE configs[1]: 256-frame batch per GPU, 640x480, FaceFrontal WVM->SVM cascade, HOG SVM stage (round-1 headline)",
+                "value": ffw * len(ff["step_ms"]) / (ff["total_ms"] * 1e-3), "ms_per_step": ff["total_ms"] / len(ff["step_ms"]),
+                "e2e_value": ffw * len(ff["e2e_ms"]) / (ff["e2e_total"] * 1e-3), "e2e_ms_per_step": ff["e2e_total"] / len(ff["e2e_ms"]),
+                "unit": "patches/s", "stage1_ms": {"resize": float(ff["prof"][0]), "pyrdown": float(ff["prof"][1]), "window_kernel": float(ff["prof"][2]),
+                                                   "deep_kernel": float(ff["prof"][3]), "total": float(ff["prof"][4])}}
         emit(line)
     if world > 1:
         dist.barrier()

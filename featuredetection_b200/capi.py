@@ -202,6 +202,7 @@ SYMBOLS = [
     ("fdb_detector_set_prepare", C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32]),
     ("fdb_detector_set_windows_per_frame", C.c_int64, [C.c_void_p]),
     ("fdb_detector_set_info", C.c_int, [C.c_void_p, _P(C.c_int32), _P(C.c_int64), _P(C.c_int32), _P(C.c_int32)]),
+    ("fdb_detector_set_last_host_ms", C.c_int, [C.c_void_p, _P(C.c_double)]),
     ("fdb_detector_set_detect_batch", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_int64,
                                                 _P(C.c_int64)]),
     ("fdb_detector_set_detect_batch_device", C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, _P(C.c_void_p), C.c_void_p,

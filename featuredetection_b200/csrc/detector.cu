@@ -303,8 +303,11 @@ int phase_a(fdb_detector* det, Slot& sl, cudaStream_t st, const Plan& plan, cons
 		return fail(FDB_ERR_OVERFLOW, "stage-1 candidate list overflow: raise max_positives_per_frame");
 	const Candidate* src = reinterpret_cast<const Candidate*>(sl.h_counters + 4);
 	if (ncand > OPT_CAND) {
-		CUDA_TRY(cudaMemcpyAsync(sl.h_cand_big, sl.d_cand, sizeof(Candidate) * (size_t)ncand, cudaMemcpyDeviceToHost, st));
-		CUDA_TRY(cudaStreamSynchronize(st));
+		/* the list is complete (stage 1 finished): fetch it on the copy stream - `st` may already hold other work of this chunk
+		 * (a detector set queues its members' SVM kernels there) and the host must not wait for that */
+		cudaStream_t cs = sl.st_copy ? sl.st_copy : st;
+		CUDA_TRY(cudaMemcpyAsync(sl.h_cand_big, sl.d_cand, sizeof(Candidate) * (size_t)ncand, cudaMemcpyDeviceToHost, cs));
+		CUDA_TRY(cudaStreamSynchronize(cs));
 		src = sl.h_cand_big;
 	}
 	/* canonical order: (frame, window) - SlidingWindowDetector::detect() pushes in extract order */
@@ -399,6 +402,7 @@ int copy_out(const std::vector<fdb_detection>& dets, fdb_detection* out, int64_t
 void release(fdb_detector* det) {
 	for (Slot& sl : det->slots) {
 		if (sl.st) { cudaStreamSynchronize(sl.st); cudaStreamDestroy(sl.st); }
+		if (sl.st_copy) { cudaStreamSynchronize(sl.st_copy); cudaStreamDestroy(sl.st_copy); }
 		if (sl.ev_stage1) cudaEventDestroy(sl.ev_stage1);
 		if (sl.ev_svm) cudaEventDestroy(sl.ev_svm);
 		sl = Slot();
@@ -857,6 +861,7 @@ int fdb_detector_prepare(fdb_detector* det, int32_t width, int32_t height, int32
 	for (int i = 0; i < det->n_slots; ++i) {
 		Slot& sl = det->slots[i];
 		CUDA_TRY(cudaStreamCreateWithFlags(&sl.st, cudaStreamNonBlocking));
+		CUDA_TRY(cudaStreamCreateWithFlags(&sl.st_copy, cudaStreamNonBlocking));
 		CUDA_TRY(cudaEventCreateWithFlags(&sl.ev_stage1, cudaEventDisableTiming));
 		CUDA_TRY(cudaEventCreateWithFlags(&sl.ev_svm, cudaEventDisableTiming));
 		s = dev_alloc(&sl.d_frames, (size_t)det->chunk * width * height, det->owned); if (s) return s;

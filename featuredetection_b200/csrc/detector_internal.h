@@ -24,6 +24,7 @@ namespace fdb {
 
 struct Slot {
 	cudaStream_t st = nullptr;
+	cudaStream_t st_copy = nullptr; /* late D2H of long candidate lists: must not queue behind SVM kernels on `st` */
 	cudaEvent_t ev_stage1 = nullptr, ev_svm = nullptr;
 	uint8_t* d_frames = nullptr;
 	uint8_t* d_arena = nullptr;

@@ -16,6 +16,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cstdlib>
 #include <cstring>
 #include <map>
@@ -38,6 +39,12 @@ struct SetSlot {
 	int n = 0, base = 0;
 	const uint8_t* frames_dev = nullptr;
 	bool busy = false;
+};
+
+struct HostTimer { /* adds the host wall clock of its scope to *dst (milliseconds) */
+	double* dst; std::chrono::steady_clock::time_point t0;
+	explicit HostTimer(double* d) : dst(d), t0(std::chrono::steady_clock::now()) {}
+	~HostTimer() { *dst += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); }
 };
 
 struct SetLaunch {  /* one wvm_group_kernel launch: all strips of one window size and pack width */
@@ -66,6 +73,7 @@ struct fdb_detector_set {
 	cudaEvent_t ev_begin = nullptr;
 	std::vector<void*> owned, owned_host;
 	int64_t windows = 0;                /* per frame, all members */
+	double host_ms[5] = {0, 0, 0, 0, 0}; /* last call, host wall clock: enqueue, phase A (overlap elimination, SVM launch), phase B, whole call, waiting for stage 1 */
 };
 
 namespace {
@@ -176,6 +184,11 @@ int set_pipeline(fdb_detector_set* s, const uint8_t* frames, bool frames_on_devi
 	auto do_a = [&]() -> int {
 		const int si = a_done % s->n_slots;
 		SetSlot& ss = s->slots[si];
+		{ /* stage 1 of the chunk: every member's records are complete after the last member's event */
+			HostTimer wait(&s->host_ms[4]);
+			for (int d = nd - 1; d >= 0; --d) if (s->fast[(size_t)d]) { CUDA_TRY(cudaEventSynchronize(s->dets[(size_t)d]->slots[si].ev_stage1)); break; }
+		}
+		HostTimer timer(&s->host_ms[1]);
 		for (int d = 0; d < nd; ++d) {
 			if (!s->fast[(size_t)d]) continue;
 			fdb_detector* det = s->dets[(size_t)d];
@@ -189,6 +202,7 @@ int set_pipeline(fdb_detector_set* s, const uint8_t* frames, bool frames_on_devi
 		return FDB_OK;
 	};
 	auto do_b = [&]() -> int {
+		HostTimer timer(&s->host_ms[2]);
 		const int si = retired % s->n_slots;
 		for (int d = 0; d < nd; ++d) {
 			if (!s->fast[(size_t)d]) continue;
@@ -207,6 +221,7 @@ int set_pipeline(fdb_detector_set* s, const uint8_t* frames, bool frames_on_devi
 			if (a_done == retired) { r = do_a(); if (r) return r; }
 			r = do_b(); if (r) return r;
 		}
+		HostTimer* timer = new HostTimer(&s->host_ms[0]);
 		ss.base = enq * s->chunk;
 		ss.n = std::min(s->chunk, n_frames - ss.base);
 		ss.busy = true;
@@ -227,6 +242,7 @@ int set_pipeline(fdb_detector_set* s, const uint8_t* frames, bool frames_on_devi
 			CUDA_TRY(cudaEventRecord(msl.ev_stage1, ss.st));
 		}
 		++enq;
+		delete timer;
 		while (a_done < enq - 1) { r = do_a(); if (r) return r; }
 		while (retired < a_done - 1) { r = do_b(); if (r) return r; }
 	}
@@ -248,6 +264,8 @@ int set_detect(fdb_detector_set* s, const uint8_t* frames, bool frames_on_device
 	if (!frames_on_device && pitch < s->W) return fail(FDB_ERR_INVALID_ARGUMENT, "pitch smaller than the frame width");
 	const int nd = (int)s->dets.size();
 	std::vector<std::vector<fdb_detection>> results((size_t)nd);
+	std::fill(s->host_ms, s->host_ms + 5, 0.0);
+	HostTimer whole(&s->host_ms[3]);
 	for (int attempt = 0; attempt < nd + 1; ++attempt) {
 		for (auto& v : results) v.clear();
 		r = set_pipeline(s, frames, frames_on_device, pitch, n_frames, stage, dense_dev, results);
@@ -416,6 +434,12 @@ int fdb_detector_set_info(fdb_detector_set* s, int32_t* n_images, int64_t* pyram
 	if (pyramid_bytes) { int64_t b = 0; for (const PyrImage& im : s->images) if (im.kind != IMG_FRAME) b += (int64_t)im.pitch * im.height; *pyramid_bytes = b; }
 	if (n_window_launches) *n_window_launches = (int32_t)s->launches.size();
 	if (n_fast) { int k = 0; for (char f : s->fast) k += f; *n_fast = k; }
+	return FDB_OK;
+} FDB_API_CATCH
+
+int fdb_detector_set_last_host_ms(fdb_detector_set* s, double ms_out[5]) try {
+	if (!s || !ms_out) return fail(FDB_ERR_INVALID_ARGUMENT, "null argument");
+	std::memcpy(ms_out, s->host_ms, sizeof(s->host_ms));
 	return FDB_OK;
 } FDB_API_CATCH
 

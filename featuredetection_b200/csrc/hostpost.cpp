@@ -43,20 +43,52 @@ void overlap_eliminate(std::vector<fdb_detection>& v, float dist, float ratio_in
 	if (v.empty()) return;
 	const float ratio = (ratio_in > 0.0f && ratio_in <= 1.0f) ? ratio_in : 0.0f;
 	stable_sort_desc(v);
-	std::vector<char> dead(v.size(), 0);
-	for (size_t acc = 0; acc < v.size(); ++acc) {
-		if (dead[acc]) continue;
-		for (size_t pro = acc + 1; pro < v.size(); ++pro) {
-			if (dead[pro]) continue;
-			const int wa = v[acc].width, wp = v[pro].width;
-			const float d = dist <= 1.0 ? dist * (float)std::max(wa, wp) : dist;
-			if (std::abs(v[acc].center_x - v[pro].center_x) < d && std::abs(v[acc].center_y - v[pro].center_y) < d
-					&& ((float)std::min(wa, wp) / (float)std::max(wa, wp)) > ratio)
-				dead[pro] = 1;
+	const size_t n = v.size();
+	std::vector<char> dead(n, 0);
+	auto kills = [&](size_t acc, size_t pro) {
+		const int wa = v[acc].width, wp = v[pro].width;
+		const float d = dist <= 1.0 ? dist * (float)std::max(wa, wp) : dist;
+		return std::abs(v[acc].center_x - v[pro].center_x) < d && std::abs(v[acc].center_y - v[pro].center_y) < d
+				&& ((float)std::min(wa, wp) / (float)std::max(wa, wp)) > ratio;
+	};
+	if (dist > 1.0f && n > 64) {
+		/* absolute distance (the cfg's dist 5.0): an accepted patch can only eliminate patches whose centre lies within
+		 * `dist` pixels, so each one looks at the 3 x 3 neighbourhood of a grid of dist-sized cells instead of at every
+		 * later candidate. Same pairs tested in the same greedy order as the reference's double loop => same survivors. */
+		const int cell = std::max(1, (int)std::ceil(dist));
+		int min_x = v[0].center_x, min_y = v[0].center_y, max_x = min_x, max_y = min_y;
+		for (const fdb_detection& d : v) {
+			min_x = std::min(min_x, d.center_x); max_x = std::max(max_x, d.center_x);
+			min_y = std::min(min_y, d.center_y); max_y = std::max(max_y, d.center_y);
+		}
+		const int gw = (max_x - min_x) / cell + 1, gh = (max_y - min_y) / cell + 1;
+		if ((int64_t)gw * gh <= (int64_t)1 << 22) {
+			std::vector<int> head((size_t)gw * gh, -1), next(n, -1);
+			for (size_t i = n; i-- > 0;) { /* lists in ascending candidate order */
+				const size_t c = (size_t)((v[i].center_y - min_y) / cell) * gw + (size_t)((v[i].center_x - min_x) / cell);
+				next[i] = head[c]; head[c] = (int)i;
+			}
+			for (size_t acc = 0; acc < n; ++acc) {
+				if (dead[acc]) continue;
+				const int cx = (v[acc].center_x - min_x) / cell, cy = (v[acc].center_y - min_y) / cell;
+				for (int gy = std::max(cy - 1, 0); gy <= std::min(cy + 1, gh - 1); ++gy)
+					for (int gx = std::max(cx - 1, 0); gx <= std::min(cx + 1, gw - 1); ++gx)
+						for (int pro = head[(size_t)gy * gw + gx]; pro >= 0; pro = next[(size_t)pro])
+							if ((size_t)pro > acc && !dead[(size_t)pro] && kills(acc, (size_t)pro)) dead[(size_t)pro] = 1;
+			}
+			size_t k = 0;
+			for (size_t i = 0; i < n; ++i) if (!dead[i]) v[k++] = v[i];
+			v.resize(k);
+			return;
 		}
 	}
+	for (size_t acc = 0; acc < n; ++acc) {
+		if (dead[acc]) continue;
+		for (size_t pro = acc + 1; pro < n; ++pro)
+			if (!dead[pro] && kills(acc, pro)) dead[pro] = 1;
+	}
 	size_t k = 0;
-	for (size_t i = 0; i < v.size(); ++i)
+	for (size_t i = 0; i < n; ++i)
 		if (!dead[i]) v[k++] = v[i];
 	v.resize(k);
 }

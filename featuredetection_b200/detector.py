@@ -434,6 +434,12 @@ class DetectorSet:
         capi.check(self.ctx.lib, self.ctx.lib.fdb_detector_set_profile_device(self.h, frames_ptr, n, ms))
         return list(ms)
 
+    def last_host_ms(self):
+        """host wall clock of the last detect call: enqueue, phase A (wait + overlap elimination + SVM launch), phase B, whole call"""
+        ms = (C.c_double * 5)()
+        capi.check(self.ctx.lib, self.ctx.lib.fdb_detector_set_last_host_ms(self.h, ms))
+        return dict(zip(("enqueue", "phase_a", "phase_b", "call", "wait_stage1"), ms))
+
 
 def detect_face_features(face, features, frame, cap=4096):
     """ffpDetectApp.cpp:553-596: face detector on the frame, then each feature detector inside the first face's bounds.

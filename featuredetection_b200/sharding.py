@@ -9,7 +9,7 @@ import numpy as np
 
 # columns of the gathered record (float64 keeps every field exactly: ints < 2^53)
 GATHER_FIELDS = ("frame", "window", "layer", "x", "y", "center_x", "center_y", "width", "height",
-                 "wvm_level", "wvm_fout", "wvm_probability", "svm_distance", "svm_probability", "probability", "positive")
+                 "wvm_level", "wvm_fout", "wvm_probability", "svm_distance", "svm_probability", "probability", "positive", "reserved")
 
 
 def shard_range(n_frames, rank, world):

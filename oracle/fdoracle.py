@@ -167,6 +167,9 @@ def ref():
         R.ref_detect_frame_ex.restype = C.c_int64
         R.ref_detect_frame_ex.argtypes = [C.POINTER(capi.DetectorDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                           C.c_int, C.c_void_p, C.POINTER(C.c_int64), C.c_void_p, C.c_int64, C.POINTER(C.c_double)]
+        R.ref_detect_layers_ex.restype = C.c_int64
+        R.ref_detect_layers_ex.argtypes = [C.POINTER(capi.DetectorDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                           C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_int64), C.c_void_p, C.c_int64, C.POINTER(C.c_double)]
         _bind_sdm(R)
         R.ref_vlhog_uoctti.restype = C.c_int
         R.ref_vlhog_uoctti.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
@@ -251,6 +254,37 @@ def pyramid(frame, inc, mn, mx):
         return p.contents.octave_layer_count, out
     finally:
         lib().fdo_pyramid_free(p)
+
+
+def cv2_pyramid(frame, inc, mn, mx):
+    """ImagePyramid::createLayers (ImagePyramid.cpp:170-198) with OpenCV's own cv::resize / cv::pyrDown (python cv2), in the
+    reference's loop order: for every octave layer i a resize of the frame, then pyrDown while the scale stays >= the minimum;
+    layers inside [min, max] are kept and sorted by index. Returns (octave_layer_count, [(index, scale, image), ...]) - the
+    same values as pyramid() (tests/test_oracle_golden.py pins the restatement to cv2 bit for bit). Used by the CPU
+    reference arm of bench.py so that the reference is timed with the SIMD pyramid it really links."""
+    import cv2
+    import math
+    frame = np.ascontiguousarray(frame, np.uint8)
+    H, W = frame.shape
+    olc = int(round(math.log(0.5) / math.log(inc)))
+    incr = math.pow(0.5, 1.0 / olc)
+    L = lib()
+    out = []
+    for i in range(olc):
+        sf = math.pow(incr, i)
+        w, h = L.fdo_cvround(W * sf), L.fdo_cvround(H * sf)
+        scaled = cv2.resize(frame, (w, h), interpolation=cv2.INTER_LINEAR)
+        if mn <= sf <= mx:
+            out.append((i, sf, scaled))
+        prev, sf, j = scaled, sf * 0.5, 1
+        while sf >= mn and prev.shape[1] > 1:
+            prev = cv2.pyrDown(prev)
+            if sf <= mx:
+                out.append((i + j * olc, sf, prev))
+            sf *= 0.5
+            j += 1
+    out.sort(key=lambda t: t[0])
+    return olc, out
 
 
 class Wvm:
@@ -612,9 +646,11 @@ def detect_frame(det_kwargs, wvm, svm, frame, stage=capi.FDB_STAGE_NMS, roi=(0, 
                 counts=list(counts), timing=list(tim), layers=layers, svm_dense=svm_dense)
 
 
-def ref_detect_frame(det_kwargs, wvm, svm, frame, stage=capi.FDB_STAGE_NMS, want_dense=True, det_cap=1 << 16, svm_features=None):
+def ref_detect_frame(det_kwargs, wvm, svm, frame, stage=capi.FDB_STAGE_NMS, want_dense=True, det_cap=1 << 16, svm_features=None,
+                     pyramid_impl="restated"):
     """One frame through the reference's own classes (oracle/_ref; see ref_driver.cpp:ref_detect_frame).
-    wvm / svm are Wvm / Svm objects created with use_ref=True. Returns a dict."""
+    wvm / svm are Wvm / Svm objects created with use_ref=True. pyramid_impl "cv2": the pyramid comes from cv2_pyramid()
+    (timing[0] = its wall time). Returns a dict."""
     from featuredetection_b200.synthetic import detector_desc
     desc = detector_desc(**det_kwargs)
     frame = np.ascontiguousarray(frame, np.uint8)
@@ -632,9 +668,26 @@ def ref_detect_frame(det_kwargs, wvm, svm, frame, stage=capi.FDB_STAGE_NMS, want
         total = lib().fdo_enumerate(p, desc.patch_width, desc.patch_height, max(desc.step_x, 1), max(desc.step_y, 1), 0, 0, 0, 0, infos, p.contents.n_layers)
         lib().fdo_pyramid_free(p)
         dense = np.zeros(total, SCORE_DTYPE)
-    n = ref().ref_detect_frame_ex(C.byref(desc), wvm.h, svm.h if svm is not None else None,
-                                  svm_features.h if svm_features is not None else None, frame.ctypes.data, W, H, stage,
-                                  dense.ctypes.data if dense is not None else None, C.byref(nwin), wins.ctypes.data, det_cap, tim)
+    if pyramid_impl == "cv2":
+        import time as _time
+        t0 = _time.perf_counter()
+        _, layers = cv2_pyramid(frame, desc.incremental_scale_factor, desc.min_scale_factor, desc.max_scale_factor)
+        arr = (_Layer * max(len(layers), 1))()
+        keep = []
+        for i, (idx, sc, img) in enumerate(layers):
+            img = np.ascontiguousarray(img)
+            keep.append(img)
+            arr[i].index, arr[i].scale, arr[i].width, arr[i].height = idx, sc, img.shape[1], img.shape[0]
+            arr[i].data = img.ctypes.data_as(C.POINTER(C.c_uint8))
+        t_pyr = _time.perf_counter() - t0
+        n = ref().ref_detect_layers_ex(C.byref(desc), wvm.h, svm.h if svm is not None else None,
+                                       svm_features.h if svm_features is not None else None, arr, len(layers), W, H, stage,
+                                       dense.ctypes.data if dense is not None else None, C.byref(nwin), wins.ctypes.data, det_cap, tim)
+        tim[0] = t_pyr
+    else:
+        n = ref().ref_detect_frame_ex(C.byref(desc), wvm.h, svm.h if svm is not None else None,
+                                      svm_features.h if svm_features is not None else None, frame.ctypes.data, W, H, stage,
+                                      dense.ctypes.data if dense is not None else None, C.byref(nwin), wins.ctypes.data, det_cap, tim)
     if n < 0:
         raise RuntimeError("ref_detect_frame failed (%d)" % n)
     return dict(windows=int(nwin.value), dense=dense, det_windows=wins[:n].copy(), timing=list(tim))

@@ -311,6 +311,10 @@ int64_t ref_detect_frame_ex(const fdb_detector_desc* desc, void* wvm_h, void* sv
 		int width, int height, int stage, fdb_window_score* dense_out, int64_t* windows_out, int64_t* det_windows_out,
 		int64_t det_cap, double* timing_out);
 
+static int64_t ref_detect_on_pyramid(const fdb_detector_desc* desc, void* wvm_h, void* svm_h, const fdo_features* feat, fdo_pyramid* pyr,
+		int width, int height, int stage, fdb_window_score* dense_out, int64_t* windows_out, int64_t* det_windows_out,
+		int64_t det_cap, double* timing_out);
+
 int64_t ref_detect_frame(const fdb_detector_desc* desc, void* wvm_h, void* svm_h, const uint8_t* frame, int width, int height,
 		int stage, fdb_window_score* dense_out, int64_t* windows_out, int64_t* det_windows_out, int64_t det_cap, double* timing_out) {
 	return ref_detect_frame_ex(desc, wvm_h, svm_h, nullptr, frame, width, height, stage, dense_out, windows_out, det_windows_out,
@@ -325,13 +329,45 @@ int64_t ref_detect_frame_ex(const fdb_detector_desc* desc, void* wvm_h, void* sv
 		int64_t det_cap, double* timing_out) {
 	typedef std::chrono::steady_clock clk;
 	auto secs = [](clk::time_point a, clk::time_point b) { return std::chrono::duration<double>(b - a).count(); };
-	RefWvm* rw = (RefWvm*)wvm_h;
-	RefSvm* rs = (RefSvm*)svm_h;
-	static imageprocessing::HistEq64Filter hq64;
 	auto t0 = clk::now();
 	fdo_pyramid* pyr = fdo_pyramid_build(frame, width, height, width, desc->incremental_scale_factor,
 			desc->min_scale_factor, desc->max_scale_factor);
 	if (!pyr) return -2;
+	auto t1 = clk::now();
+	const int64_t n = ref_detect_on_pyramid(desc, wvm_h, svm_h, feat, pyr, width, height, stage, dense_out, windows_out, det_windows_out,
+			det_cap, timing_out);
+	if (timing_out) timing_out[0] = secs(t0, t1);
+	fdo_pyramid_free(pyr);
+	return n;
+}
+
+/* the same on a pyramid the caller built (bench.py's reference arm builds it with cv2's resize / pyrDown - the SIMD code the real
+ * reference links, bit-identical to fdo_pyramid_build by tests/test_oracle_golden.py - in the loop order of
+ * ImagePyramid::createLayers, ImagePyramid.cpp:170-198). layers: n_layers kept layers sorted by index; not freed here. */
+int64_t ref_detect_layers_ex(const fdb_detector_desc* desc, void* wvm_h, void* svm_h, const fdo_features* feat, const fdo_layer* layers,
+		int n_layers, int width, int height, int stage, fdb_window_score* dense_out, int64_t* windows_out, int64_t* det_windows_out,
+		int64_t det_cap, double* timing_out) {
+	fdo_pyramid pyr;
+	std::memset(&pyr, 0, sizeof(pyr));
+	pyr.octave_layer_count = (int)(size_t)std::round(std::log(0.5) / std::log(desc->incremental_scale_factor));
+	pyr.incremental_scale_factor = std::pow(0.5, 1. / pyr.octave_layer_count);
+	pyr.min_scale_factor = desc->min_scale_factor; pyr.max_scale_factor = desc->max_scale_factor;
+	pyr.image_width = width; pyr.image_height = height;
+	pyr.n_layers = n_layers; pyr.layers = const_cast<fdo_layer*>(layers);
+	const int64_t n = ref_detect_on_pyramid(desc, wvm_h, svm_h, feat, &pyr, width, height, stage, dense_out, windows_out, det_windows_out,
+			det_cap, timing_out);
+	if (timing_out) timing_out[0] = 0.0;
+	return n;
+}
+
+static int64_t ref_detect_on_pyramid(const fdb_detector_desc* desc, void* wvm_h, void* svm_h, const fdo_features* feat, fdo_pyramid* pyr,
+		int width, int height, int stage, fdb_window_score* dense_out, int64_t* windows_out, int64_t* det_windows_out,
+		int64_t det_cap, double* timing_out) {
+	typedef std::chrono::steady_clock clk;
+	auto secs = [](clk::time_point a, clk::time_point b) { return std::chrono::duration<double>(b - a).count(); };
+	RefWvm* rw = (RefWvm*)wvm_h;
+	RefSvm* rs = (RefSvm*)svm_h;
+	static imageprocessing::HistEq64Filter hq64;
 	auto t1 = clk::now();
 	const int pw = desc->patch_width, ph = desc->patch_height;
 	const int sx = desc->step_x > 0 ? desc->step_x : 1, sy = desc->step_y > 0 ? desc->step_y : 1;
@@ -415,8 +451,7 @@ int64_t ref_detect_frame_ex(const fdb_detector_desc* desc, void* wvm_h, void* sv
 	auto t5 = clk::now();
 	if (n > det_cap) n = -1;
 	for (int64_t i = 0; i < n; ++i) det_windows_out[i] = dets[(size_t)i].window;
-	if (timing_out) { timing_out[0] = secs(t0, t1); timing_out[1] = secs(t1, t2); timing_out[2] = secs(t2, t3); timing_out[3] = secs(t3, t4); timing_out[4] = secs(t4, t5); }
-	fdo_pyramid_free(pyr);
+	if (timing_out) { timing_out[0] = 0.0; timing_out[1] = secs(t1, t2); timing_out[2] = secs(t2, t3); timing_out[3] = secs(t3, t4); timing_out[4] = secs(t4, t5); }
 	return n;
 }
 

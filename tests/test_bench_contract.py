@@ -9,10 +9,10 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("workload", ["facefrontal", "single-psvm"])
+@pytest.mark.parametrize("workload", ["landmarks15", "facefrontal", "single-psvm"])
 def test_reference_arm_prints_one_json_line(built, workload):
     cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", workload, "--steps", "1", "--warmup", "0",
-           "--ref-frames-per-core", "1"]
+           "--ref-frames-per-core", "1", "--ref-frames-per-step", "1"]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [l for l in r.stdout.splitlines() if l.strip()]
@@ -24,6 +24,9 @@ def test_reference_arm_prints_one_json_line(built, workload):
     cb = d["cpu_baseline"]
     assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == d["value"] and "sample" in cb
     assert "workload" in d["config"] and d["vs_baseline"] is None
+    if workload != "single-psvm":  # the cascade arms report where the CPU time goes (pyramid | extract+hq64 | wvm | oe | svm+nms)
+        assert set(cb["split_core_seconds"]) == {"pyramid", "extract+hq64", "wvm", "overlap_elimination", "svm+nms"}
+        assert "pyramid" in cb
 
 
 def test_b200_arm_refuses_to_run_without_a_gpu(built):

@@ -144,6 +144,29 @@ def test_overlap_elimination_vs_oracle_and_reference(built, seed):
         assert list(keep[:m]) == list(mine["window"])  # distinct probabilities: no tie ambiguity
 
 
+@pytest.mark.parametrize("seed", range(3))
+def test_overlap_elimination_grid_path_vs_reference(built, seed):
+    """hundreds to thousands of candidates per frame (the eye / lip / nose detectors): the product's grid-bucketed elimination
+    (absolute distance, n > 64) returns the survivors of the reference's own OverlapElimination class"""
+    from oracle import fdoracle as fo
+    lib = capi.load_library()
+    rng = np.random.default_rng(100 + seed)
+    n = [700, 3000, 5000][seed]
+    d = _random_dets(rng, n, 640, 480)
+    d["width"] = rng.choice([34, 38, 44, 48], n); d["height"] = d["width"]
+    d["probability"] = rng.permutation(n) / float(n)  # distinct: no tie ambiguity
+    dist, ratio = [(5.0, 0.0), (5.0, 0.85), (9.5, 0.0)][seed]
+    mine = d.copy(); cnt = C.c_int64()
+    capi.check(lib, lib.fdb_overlap_eliminate(mine.ctypes.data, n, dist, ratio, C.byref(cnt)))
+    mine = mine[:cnt.value]
+    assert 0 < cnt.value < n
+    if fo.ref_available():
+        keep = np.zeros(n, np.int32)
+        cx, cy, w, p = (np.ascontiguousarray(d[f]) for f in ("center_x", "center_y", "width", "probability"))
+        m = fo.ref().ref_overlap_eliminate(dist, ratio, n, cx.ctypes.data, cy.ctypes.data, w.ctypes.data, p.ctypes.data, keep.ctypes.data)
+        assert list(keep[:m]) == list(mine["window"])
+
+
 def test_host_nms_vs_oracle(built):
     """fdb_five_stage_nms (sparse, product) vs the oracle's dense-map restatement, incl. the
     all-0.5 probabilities the five-stage detector really produces and the no-maximum fallback."""

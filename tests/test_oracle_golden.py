@@ -193,3 +193,24 @@ def test_bgr_to_gray_formula(built):
     ref = cv2.cvtColor(bgr, cv2.COLOR_BGR2GRAY)
     diff = np.abs(got.astype(int) - ref.astype(int))
     assert diff.max() <= 1 and (diff != 0).mean() < 0.01
+
+
+def test_reference_arm_with_cv2_pyramid_equals_the_restated_pyramid(fo):
+    """bench.py's CPU reference arm builds its pyramids with cv2 (the SIMD cv::resize / cv::pyrDown the real reference links):
+    same layers, same stage-1 records and detections as with the restated pyramid"""
+    pytest.importorskip("cv2")
+    if not fo.ref_available():
+        pytest.skip("oracle/_ref not built")
+    for name in ("FaceFrontal", "RightEyeCenter"):
+        kw, wvm, svm = syn.landmark_models(name)
+        frame = syn.synthetic_frame(11)[:240, :320] if name != "FaceFrontal" else syn.synthetic_frame(11)
+        olc_a, a = fo.pyramid(frame, kw["incremental_scale_factor"], kw["min_scale_factor"], kw["max_scale_factor"])
+        olc_b, b = fo.cv2_pyramid(frame, kw["incremental_scale_factor"], kw["min_scale_factor"], kw["max_scale_factor"])
+        assert olc_a == olc_b and len(a) == len(b)
+        for (ia, sa, xa), (ib, sb, xb) in zip(a, b):
+            assert ia == ib and sa == sb and np.array_equal(xa, xb)
+        rw, rs = fo.Wvm(wvm, use_ref=True), fo.Svm(svm, use_ref=True)
+        r1 = fo.ref_detect_frame(kw, rw, rs, frame)
+        r2 = fo.ref_detect_frame(kw, rw, rs, frame, pyramid_impl="cv2")
+        assert r1["windows"] == r2["windows"] and np.array_equal(r1["dense"], r2["dense"])
+        assert np.array_equal(r1["det_windows"], r2["det_windows"])
