@@ -94,6 +94,16 @@ class SdmDesc(C.Structure):
                 ("mean_landmarks", C.POINTER(C.c_float)), ("regressors", C.POINTER(C.c_void_p))]
 
 
+class AggdetDesc(C.Structure):
+    _fields_ = [("cell_size", C.c_int32), ("window_cols", C.c_int32), ("window_rows", C.c_int32), ("octave_layer_count", C.c_int32),
+                ("min_window_width", C.c_int32), ("width_scale", C.c_float), ("height_scale", C.c_float), ("unsigned_bins", C.c_int32),
+                ("interpolate_bins", C.c_int32), ("interpolate_cells", C.c_int32), ("alpha", C.c_float), ("weights", C.POINTER(C.c_float)),
+                ("bias", C.c_float), ("threshold", C.c_float), ("nms_overlap_threshold", C.c_double), ("nms_type", C.c_int32)]
+
+
+FDB_NMS_MAX_SCORE, FDB_NMS_AVERAGE, FDB_NMS_WEIGHTED_AVERAGE = 0, 1, 2
+
+
 class WindowScore(C.Structure):
     _fields_ = [("fout", C.c_float), ("level", C.c_int32)]
 
@@ -208,6 +218,17 @@ SYMBOLS = [
     ("fdb_detector_set_detect_batch_device", C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, _P(C.c_void_p), C.c_void_p,
                                                        C.c_int64, _P(C.c_int64)]),
     ("fdb_detector_set_profile_device", C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, _P(C.c_double)]),
+    ("fdb_aggdet_create", C.c_int, [C.c_void_p, _P(AggdetDesc), _P(C.c_void_p)]),
+    ("fdb_aggdet_destroy", None, [C.c_void_p]),
+    ("fdb_aggdet_prepare", C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32]),
+    ("fdb_aggdet_layers", C.c_int, [C.c_void_p, _P(C.c_int32), C.c_void_p, C.c_int32]),
+    ("fdb_aggdet_positions_per_frame", C.c_int64, [C.c_void_p]),
+    ("fdb_aggdet_detect_batch", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                          _P(C.c_int64)]),
+    ("fdb_aggdet_detect_batch_device", C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                                 _P(C.c_int64)]),
+    ("fdb_aggdet_score_maps", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64]),
+    ("fdb_aggdet_profile_device", C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, _P(C.c_double)]),
     ("fdb_sdm_create", C.c_int, [C.c_void_p, _P(SdmDesc), _P(C.c_void_p)]),
     ("fdb_sdm_destroy", None, [C.c_void_p]),
     ("fdb_sdm_num_landmarks", C.c_int32, [C.c_void_p]),

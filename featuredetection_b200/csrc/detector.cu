@@ -286,10 +286,12 @@ void svm_stage(fdb_detector* det, Slot& sl, cudaStream_t st, const Plan& plan, c
 	}
 }
 
-/* phase A of the host post-processing: wait for stage 1 of the slot's chunk, build the per-frame
- * candidate lists, overlap elimination, launch the SVM on the survivors (async) */
-int phase_a(fdb_detector* det, Slot& sl, cudaStream_t st, const Plan& plan, const DevLayer* d_layers, int stage, int fast_path) {
-	fdb_ctx* c = det->ctx;
+/* phase A of the host post-processing, in three parts so that a detector set can run the middle one for all its members
+ * on several host threads:
+ *   fetch   wait for stage 1 of the slot's chunk, make the whole candidate list available on the host
+ *   host    (pure CPU, touches only det and sl) per-frame candidate lists in canonical order, overlap elimination, SVM work list
+ *   launch  SVM on the survivors (async) */
+int phase_a_fetch(fdb_detector* det, Slot& sl, cudaStream_t st, const DevLayer* d_layers, int fast_path) {
 	CUDA_TRY(cudaEventSynchronize(sl.ev_stage1));
 	if (fast_path < 0) fast_path = det->use_strips && d_layers == det->d_layers;
 	if (fast_path && sl.h_counters[1] > sl.deep.cap) {
@@ -301,17 +303,28 @@ int phase_a(fdb_detector* det, Slot& sl, cudaStream_t st, const Plan& plan, cons
 	const int ncand = sl.h_counters[0];
 	if (ncand > det->cand_cap)
 		return fail(FDB_ERR_OVERFLOW, "stage-1 candidate list overflow: raise max_positives_per_frame");
-	const Candidate* src = reinterpret_cast<const Candidate*>(sl.h_counters + 4);
+	sl.cand_src = reinterpret_cast<const Candidate*>(sl.h_counters + 4);
 	if (ncand > OPT_CAND) {
 		/* the list is complete (stage 1 finished): fetch it on the copy stream - `st` may already hold other work of this chunk
 		 * (a detector set queues its members' SVM kernels there) and the host must not wait for that */
 		cudaStream_t cs = sl.st_copy ? sl.st_copy : st;
 		CUDA_TRY(cudaMemcpyAsync(sl.h_cand_big, sl.d_cand, sizeof(Candidate) * (size_t)ncand, cudaMemcpyDeviceToHost, cs));
-		CUDA_TRY(cudaStreamSynchronize(cs));
-		src = sl.h_cand_big;
+		sl.cand_src = sl.h_cand_big;
+		sl.cand_pending = true;
 	}
+	return FDB_OK;
+}
+
+int phase_a_fetch_wait(Slot& sl, cudaStream_t st) {
+	if (sl.cand_pending) { CUDA_TRY(cudaStreamSynchronize(sl.st_copy ? sl.st_copy : st)); sl.cand_pending = false; }
+	return FDB_OK;
+}
+
+/* returns FDB_OK or FDB_ERR_OVERFLOW (no message: may run on a worker thread) */
+int phase_a_host(fdb_detector* det, Slot& sl, const Plan& plan, int stage) {
+	const int ncand = sl.h_counters[0];
 	/* canonical order: (frame, window) - SlidingWindowDetector::detect() pushes in extract order */
-	std::vector<Candidate> cand(src, src + ncand);
+	std::vector<Candidate> cand(sl.cand_src, sl.cand_src + ncand);
 	std::sort(cand.begin(), cand.end(), [](const Candidate& a, const Candidate& b) {
 		return a.frame != b.frame ? a.frame < b.frame : a.window < b.window; });
 	det->counts[1] += ncand;
@@ -333,8 +346,7 @@ int phase_a(fdb_detector* det, Slot& sl, cudaStream_t st, const Plan& plan, cons
 	if (stage >= FDB_STAGE_SVM && det->svm) {
 		size_t total = 0;
 		for (auto& v : sl.per_frame) total += v.size();
-		if ((int64_t)total > det->items_cap)
-			return fail(FDB_ERR_OVERFLOW, "SVM work list overflow");
+		if ((int64_t)total > det->items_cap) return FDB_ERR_OVERFLOW;
 		size_t k = 0;
 		for (int f = 0; f < sl.n; ++f)
 			for (const fdb_detection& d : sl.per_frame[(size_t)f]) {
@@ -342,20 +354,32 @@ int phase_a(fdb_detector* det, Slot& sl, cudaStream_t st, const Plan& plan, cons
 				sl.h_items[k++] = it;
 			}
 		sl.svm_items = total;
-		if (total) {
-			CUDA_TRY(cudaMemcpyAsync(sl.d_items, sl.h_items, sizeof(SvmItem) * total, cudaMemcpyHostToDevice, st));
-			svm_stage(det, sl, st, plan, d_layers, sl.d_items, (int)total, sl.d_dist, true);
-			CUDA_TRY(cudaGetLastError());
-			CUDA_TRY(cudaMemcpyAsync(sl.h_dist, sl.d_dist, sizeof(double) * total, cudaMemcpyDeviceToHost, st));
-		}
+	}
+	return FDB_OK;
+}
+
+int phase_a_launch(fdb_detector* det, Slot& sl, cudaStream_t st, const Plan& plan, const DevLayer* d_layers, int stage) {
+	const size_t total = sl.svm_items;
+	if (stage >= FDB_STAGE_SVM && det->svm && total) {
+		CUDA_TRY(cudaMemcpyAsync(sl.d_items, sl.h_items, sizeof(SvmItem) * total, cudaMemcpyHostToDevice, st));
+		svm_stage(det, sl, st, plan, d_layers, sl.d_items, (int)total, sl.d_dist, true);
+		CUDA_TRY(cudaGetLastError());
+		CUDA_TRY(cudaMemcpyAsync(sl.h_dist, sl.d_dist, sizeof(double) * total, cudaMemcpyDeviceToHost, st));
 	}
 	CUDA_TRY(cudaEventRecord(sl.ev_svm, st));
 	return FDB_OK;
 }
 
-/* phase B: SVM distances -> classify, grid NMS, append in frame order */
-int phase_b(fdb_detector* det, Slot& sl, const Plan& plan, int stage, bool is_roi, std::vector<fdb_detection>& out) {
-	CUDA_TRY(cudaEventSynchronize(sl.ev_svm));
+int phase_a(fdb_detector* det, Slot& sl, cudaStream_t st, const Plan& plan, const DevLayer* d_layers, int stage, int fast_path) {
+	int r = phase_a_fetch(det, sl, st, d_layers, fast_path); if (r) return r;
+	r = phase_a_fetch_wait(sl, st); if (r) return r;
+	r = phase_a_host(det, sl, plan, stage);
+	if (r) return fail(r, "SVM work list overflow");
+	return phase_a_launch(det, sl, st, plan, d_layers, stage);
+}
+
+/* phase B: SVM distances -> classify, grid NMS, append in frame order; phase_b_host is pure CPU (det, sl and out only) */
+void phase_b_host(fdb_detector* det, Slot& sl, const Plan& plan, int stage, bool is_roi, std::vector<fdb_detection>& out) {
 	if (stage >= FDB_STAGE_SVM && det->svm) {
 		size_t k = 0;
 		for (int f = 0; f < sl.n; ++f) {
@@ -379,6 +403,11 @@ int phase_b(fdb_detector* det, Slot& sl, const Plan& plan, int stage, bool is_ro
 	for (auto& v : sl.per_frame)
 		for (fdb_detection& d : v) { d.reserved = 0; out.push_back(d); }
 	sl.busy = false;
+}
+
+int phase_b(fdb_detector* det, Slot& sl, const Plan& plan, int stage, bool is_roi, std::vector<fdb_detection>& out) {
+	CUDA_TRY(cudaEventSynchronize(sl.ev_svm));
+	phase_b_host(det, sl, plan, stage, is_roi, out);
 	return FDB_OK;
 }
 

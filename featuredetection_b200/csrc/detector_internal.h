@@ -45,6 +45,8 @@ struct Slot {
 	double* h_dist = nullptr;
 	/* state of the chunk in flight */
 	int n = 0, base = 0;
+	const Candidate* cand_src = nullptr; /* host copy of the chunk's candidate list (valid after phase_a_fetch[_wait]) */
+	bool cand_pending = false;           /* a late copy of the list is in flight on st_copy */
 	const uint8_t* frames_dev = nullptr;
 	std::vector<std::vector<fdb_detection>> per_frame;
 	size_t svm_items = 0;
@@ -120,6 +122,11 @@ int copy_out(const std::vector<fdb_detection>& dets, fdb_detection* out, int64_t
  * elimination, SVM launch on the survivors (async); phase B: SVM distances -> classify, grid NMS, append in frame order */
 int phase_a(fdb_detector* det, Slot& sl, cudaStream_t st, const Plan& plan, const DevLayer* d_layers, int stage,
 		int fast_path = -1 /* 1: stage 1 ran on the group kernels (deep-queue overflow -> STATUS_REDO); -1: decide from d_layers */);
+int phase_a_fetch(fdb_detector* det, Slot& sl, cudaStream_t st, const DevLayer* d_layers, int fast_path);
+int phase_a_fetch_wait(Slot& sl, cudaStream_t st);
+int phase_a_host(fdb_detector* det, Slot& sl, const Plan& plan, int stage); /* pure CPU, thread-safe per (det, sl); FDB_OK or FDB_ERR_OVERFLOW */
+int phase_a_launch(fdb_detector* det, Slot& sl, cudaStream_t st, const Plan& plan, const DevLayer* d_layers, int stage);
+void phase_b_host(fdb_detector* det, Slot& sl, const Plan& plan, int stage, bool is_roi, std::vector<fdb_detection>& out); /* pure CPU */
 int detect_impl(fdb_detector* det, const uint8_t* frames, bool frames_on_device, int64_t pitch, int32_t n_frames,
 		int32_t stage, fdb_window_score* dense_out, bool dense_on_device, fdb_detection* dets_out, int64_t det_cap,
 		int64_t* n_dets);

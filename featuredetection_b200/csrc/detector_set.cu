@@ -16,7 +16,12 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
+#include <thread>
 #include <cstdlib>
 #include <cstring>
 #include <map>
@@ -25,6 +30,10 @@
 #include <vector>
 
 #include "detector_internal.h"
+
+#if defined(__linux__)
+#include <sched.h>
+#endif
 
 using namespace fdb;
 
@@ -46,6 +55,78 @@ struct HostTimer { /* adds the host wall clock of its scope to *dst (millisecond
 	explicit HostTimer(double* d) : dst(d), t0(std::chrono::steady_clock::now()) {}
 	~HostTimer() { *dst += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); }
 };
+
+/* host threads for the members' post-processing (overlap elimination, NMS): the pure-CPU parts of different members are
+ * independent. run(n, f) calls f(0..n-1) on the pool and the calling thread and returns when all are done. */
+class HostPool {
+public:
+	explicit HostPool(int threads) {
+		for (int i = 1; i < threads; ++i) workers_.emplace_back([this] { loop(); });
+	}
+	~HostPool() {
+		{ std::lock_guard<std::mutex> g(m_); stop_ = true; }
+		cv_.notify_all();
+		for (std::thread& t : workers_) t.join();
+	}
+	int threads() const { return (int)workers_.size() + 1; }
+	void run(int n, const std::function<void(int)>& f) {
+		if (n <= 0) return;
+		if (workers_.empty() || n == 1) { for (int i = 0; i < n; ++i) f(i); return; }
+		{
+			std::lock_guard<std::mutex> g(m_);
+			job_ = &f; n_ = n; next_ = 0; pending_ = n; ++generation_;
+		}
+		cv_.notify_all();
+		work();
+		std::unique_lock<std::mutex> g(m_);
+		done_.wait(g, [this] { return pending_ == 0; });
+		job_ = nullptr;
+	}
+private:
+	void work() {
+		for (;;) {
+			int i;
+			const std::function<void(int)>* f;
+			{
+				std::lock_guard<std::mutex> g(m_);
+				if (!job_ || next_ >= n_) return;
+				i = next_++; f = job_;
+			}
+			(*f)(i);
+			std::lock_guard<std::mutex> g(m_);
+			if (--pending_ == 0) done_.notify_all();
+		}
+	}
+	void loop() {
+		uint64_t seen = 0;
+		for (;;) {
+			{
+				std::unique_lock<std::mutex> g(m_);
+				cv_.wait(g, [&] { return stop_ || generation_ != seen; });
+				if (stop_) return;
+				seen = generation_;
+			}
+			work();
+		}
+	}
+	std::vector<std::thread> workers_;
+	std::mutex m_;
+	std::condition_variable cv_, done_;
+	const std::function<void(int)>* job_ = nullptr;
+	int n_ = 0, next_ = 0, pending_ = 0;
+	uint64_t generation_ = 0;
+	bool stop_ = false;
+};
+
+int host_thread_count() {
+	if (const char* e = std::getenv("FDB_HOST_THREADS")) { const int v = std::atoi(e); if (v > 0) return std::min(v, 64); }
+	int n = (int)std::thread::hardware_concurrency();
+#if defined(__linux__)
+	cpu_set_t set;
+	if (sched_getaffinity(0, sizeof(set), &set) == 0) n = CPU_COUNT(&set); /* a rank pinned to its share of the cores uses only those */
+#endif
+	return std::max(1, std::min(n, 8));
+}
 
 struct SetLaunch {  /* one wvm_group_kernel launch: all strips of one window size and pack width */
 	int pw = 0, ph = 0, pack = 1;
@@ -73,6 +154,7 @@ struct fdb_detector_set {
 	cudaEvent_t ev_begin = nullptr;
 	std::vector<void*> owned, owned_host;
 	int64_t windows = 0;                /* per frame, all members */
+	HostPool* pool = nullptr;           /* host threads of the members' post-processing */
 	double host_ms[5] = {0, 0, 0, 0, 0}; /* last call, host wall clock: enqueue, phase A (overlap elimination, SVM launch), phase B, whole call, waiting for stage 1 */
 };
 
@@ -84,6 +166,7 @@ void set_release(fdb_detector_set* s) {
 		sl = SetSlot();
 	}
 	if (s->ev_begin) { cudaEventDestroy(s->ev_begin); s->ev_begin = nullptr; }
+	delete s->pool; s->pool = nullptr;
 	free_all(s->owned, &s->owned_host);
 	s->images.clear(); s->umap.clear(); s->d_layers.clear(); s->launches.clear(); s->fast.clear();
 	s->jobs = PyramidJobs();
@@ -189,13 +272,27 @@ int set_pipeline(fdb_detector_set* s, const uint8_t* frames, bool frames_on_devi
 			for (int d = nd - 1; d >= 0; --d) if (s->fast[(size_t)d]) { CUDA_TRY(cudaEventSynchronize(s->dets[(size_t)d]->slots[si].ev_stage1)); break; }
 		}
 		HostTimer timer(&s->host_ms[1]);
+		std::vector<int> members;
 		for (int d = 0; d < nd; ++d) {
 			if (!s->fast[(size_t)d]) continue;
 			fdb_detector* det = s->dets[(size_t)d];
 			Slot& msl = det->slots[si];
 			msl.n = ss.n; msl.base = ss.base; msl.frames_dev = ss.frames_dev;
 			msl.arena = ss.d_arena; msl.arena_stride = s->arena_bytes;
-			const int r = phase_a(det, msl, ss.st, det->plan, s->d_layers[(size_t)d], stage, 1);
+			const int r = phase_a_fetch(det, msl, ss.st, s->d_layers[(size_t)d], 1);
+			if (r) return r;
+			members.push_back(d);
+		}
+		for (int d : members) { const int r = phase_a_fetch_wait(s->dets[(size_t)d]->slots[si], ss.st); if (r) return r; }
+		std::vector<int> status(members.size(), FDB_OK);
+		s->pool->run((int)members.size(), [&](int k) {
+			fdb_detector* det = s->dets[(size_t)members[(size_t)k]];
+			status[(size_t)k] = phase_a_host(det, det->slots[si], det->plan, stage);
+		});
+		for (size_t k = 0; k < members.size(); ++k) {
+			if (status[k]) return fail(status[k], "SVM work list overflow");
+			fdb_detector* det = s->dets[(size_t)members[k]];
+			const int r = phase_a_launch(det, det->slots[si], ss.st, det->plan, s->d_layers[(size_t)members[k]], stage);
 			if (r) return r;
 		}
 		++a_done;
@@ -204,11 +301,14 @@ int set_pipeline(fdb_detector_set* s, const uint8_t* frames, bool frames_on_devi
 	auto do_b = [&]() -> int {
 		HostTimer timer(&s->host_ms[2]);
 		const int si = retired % s->n_slots;
-		for (int d = 0; d < nd; ++d) {
-			if (!s->fast[(size_t)d]) continue;
-			const int r = phase_b(s->dets[(size_t)d], s->dets[(size_t)d]->slots[si], s->dets[(size_t)d]->plan, stage, false, results[(size_t)d]);
-			if (r) return r;
-		}
+		std::vector<int> members;
+		for (int d = 0; d < nd; ++d) if (s->fast[(size_t)d]) members.push_back(d);
+		/* the slot stream is in order: the last member's SVM results are the last to arrive */
+		if (!members.empty()) CUDA_TRY(cudaEventSynchronize(s->dets[(size_t)members.back()]->slots[si].ev_svm));
+		s->pool->run((int)members.size(), [&](int k) {
+			fdb_detector* det = s->dets[(size_t)members[(size_t)k]];
+			phase_b_host(det, det->slots[si], det->plan, stage, false, results[(size_t)members[(size_t)k]]);
+		});
 		s->slots[si].busy = false;
 		++retired;
 		return FDB_OK;
@@ -341,6 +441,7 @@ int fdb_detector_set_prepare(fdb_detector_set* s, int32_t width, int32_t height,
 	s->fast.assign((size_t)nd, 0);
 	for (int d = 0; d < nd; ++d) s->fast[(size_t)d] = s->dets[(size_t)d]->use_strips ? 1 : 0;
 	CUDA_TRY(cudaEventCreateWithFlags(&s->ev_begin, cudaEventDisableTiming));
+	s->pool = new HostPool(std::min(host_thread_count(), nd));
 	for (int i = 0; i < s->n_slots; ++i) {
 		SetSlot& sl = s->slots[i];
 		CUDA_TRY(cudaStreamCreateWithFlags(&sl.st, cudaStreamNonBlocking));

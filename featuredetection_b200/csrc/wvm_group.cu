@@ -71,8 +71,26 @@ __device__ __forceinline__ void grp_ldmatrix4(uint32_t (&r)[4], uint32_t saddr) 
 			: "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(saddr));
 }
 
-/* one step of the sequential cumulative histogram (HistEq64Filter.cpp:70-87,97) */
+/* one step of the sequential cumulative histogram (HistEq64Filter.cpp:70-87,97): cdf += count * stretch in float32, then
+ * (uchar)floor((double)cdf + 0.5). For 0 <= cdf < 256.5 that equals floor(cdf +f 0.5f) for EVERY float except the one just
+ * below 0.5 (0x1.fffffep-2: the float sum rounds up to 1.0) - checked exhaustively over all 1.13e9 floats of the range.
+ * A cumulative histogram below 0.5 is a single product count * stretch (stretch > 0.25 for windows of <= 1020 pixels), and
+ * grp_stretch_is_safe() verifies at compile time that no such product is that float for the window sizes built here. */
 __device__ __forceinline__ uint32_t grp_hq_step(float& cdf, uint32_t cnt, float stretch) {
+	cdf = __fadd_rn(cdf, __fmul_rn((float)cnt, stretch));
+	return (uint32_t)__float2int_rd(__fadd_rn(cdf, 0.5f));
+}
+
+__host__ __device__ constexpr bool grp_stretch_is_safe(int pixels) {
+	const float stretch = 255.0f / (float)pixels;
+	if (!(stretch > 0.25f)) return false;
+	for (int cnt = 1; (float)cnt * stretch < 0.5f; ++cnt)
+		if ((float)cnt * stretch > 0.4999999f) return false;
+	return true;
+}
+
+/* the deep kernel equalises windows of any size: same value, exception handled explicitly */
+__device__ __forceinline__ uint32_t grp_hq_step_any(float& cdf, uint32_t cnt, float stretch) {
 	cdf = __fadd_rn(cdf, __fmul_rn((float)cnt, stretch));
 	const float fl = floorf(cdf); /* (uchar)floor((double)cdf + 0.5) == floor(cdf) + (frac >= 0.5) */
 	return ((uint32_t)(int)fl + (__fsub_rn(cdf, fl) >= 0.5f ? 1u : 0u)) & 255u;
@@ -84,6 +102,7 @@ __global__ void __launch_bounds__(GRP_WARPS * 32, MSUB == 1 ? 4 : 3) wvm_group_k
 	constexpr int WPR = PW / 4;                 /* words per patch row */
 	constexpr int RPK = PW <= 16 ? 2 : 1;       /* patch rows per k-step (32 operand bytes) */
 	static_assert(PH % RPK == 0, "window height must split into k-steps");
+	static_assert(grp_stretch_is_safe(PW * PH), "grp_hq_step's shortcut does not hold for this window size");
 	constexpr int KS = PH / RPK;
 	extern __shared__ __align__(128) uint8_t smem8[];
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -218,6 +237,10 @@ __global__ void __launch_bounds__(GRP_WARPS * 32, MSUB == 1 ? 4 : 3) wvm_group_k
 			const uint32_t* const trow = reinterpret_cast<const uint32_t*>(s_tile + ((org + w * GRP_PITCH) & ~3));
 #pragma unroll 1
 			for (int s = 0; s < KS; ++s) {
+				/* the models' B fragments of this k-step: requested first, they arrive while the A rows are built */
+				uint4 bA[MSUB], bB[MSUB];
+#pragma unroll
+				for (int mi = 0; mi < MSUB; ++mi) { bA[mi] = __ldg(bf[mi] + s * 64); bB[mi] = __ldg(bf[mi] + s * 64 + 1); }
 				uint8_t* const arow = s_abuf + (s & 1) * GRP_ABUF_BYTES + lane * GRP_AROW;
 #pragma unroll
 				for (int pr = 0; pr < RPK; ++pr) {
@@ -231,9 +254,10 @@ __global__ void __launch_bounds__(GRP_WARPS * 32, MSUB == 1 ? 4 : 3) wvm_group_k
 					for (int c = 0; c < 8; ++c) {
 						if (c < WPR) {
 							const uint32_t b = __funnelshift_r(x[c], x[c + 1], sh); /* 4 bins of the lane's window */
-							const uint32_t e0 = s_lut[(b & 63u) * 32], e1 = s_lut[((b >> 8) & 63u) * 32];
-							const uint32_t e2 = s_lut[((b >> 16) & 63u) * 32], e3 = s_lut[(b >> 24) * 32];
-							wd[c] = e0 | (e1 << 8) | (e2 << 16) | (e3 << 24);
+							/* byte extraction as one PRMT each, table row = bin * 32 folded into the address (LEA): 3 instructions per pixel */
+							const uint32_t e0 = s_lut[__byte_perm(b, 0, 0x4440) * 32], e1 = s_lut[__byte_perm(b, 0, 0x4441) * 32];
+							const uint32_t e2 = s_lut[__byte_perm(b, 0, 0x4442) * 32], e3 = s_lut[__byte_perm(b, 0, 0x4443) * 32];
+							wd[c] = __byte_perm(__byte_perm(e0, e1, 0x0040), __byte_perm(e2, e3, 0x0040), 0x5410);
 							rowsq = __dp4a(wd[c], wd[c], rowsq);
 						} else wd[c] = 0u;
 					}
@@ -251,15 +275,14 @@ __global__ void __launch_bounds__(GRP_WARPS * 32, MSUB == 1 ? 4 : 3) wvm_group_k
 				grp_ldmatrix4(af[1], abuf_s + (s & 1) * GRP_ABUF_BYTES + 16 * GRP_AROW + ldm_off);
 #pragma unroll
 				for (int mi = 0; mi < MSUB; ++mi) {
-					const uint4 bA = __ldg(bf[mi] + s * 64), bB = __ldg(bf[mi] + s * 64 + 1);
-					grp_mma_u8(acc[mi][0][0], af[0], bA.x, bA.y);
-					grp_mma_u8(acc[mi][0][1], af[0], bA.z, bA.w);
-					grp_mma_u8(acc[mi][0][2], af[0], bB.x, bB.y);
-					grp_mma_u8(acc[mi][0][3], af[0], bB.z, bB.w);
-					grp_mma_u8(acc[mi][1][0], af[1], bA.x, bA.y);
-					grp_mma_u8(acc[mi][1][1], af[1], bA.z, bA.w);
-					grp_mma_u8(acc[mi][1][2], af[1], bB.x, bB.y);
-					grp_mma_u8(acc[mi][1][3], af[1], bB.z, bB.w);
+					grp_mma_u8(acc[mi][0][0], af[0], bA[mi].x, bA[mi].y);
+					grp_mma_u8(acc[mi][0][1], af[0], bA[mi].z, bA[mi].w);
+					grp_mma_u8(acc[mi][0][2], af[0], bB[mi].x, bB[mi].y);
+					grp_mma_u8(acc[mi][0][3], af[0], bB[mi].z, bB[mi].w);
+					grp_mma_u8(acc[mi][1][0], af[1], bA[mi].x, bA[mi].y);
+					grp_mma_u8(acc[mi][1][1], af[1], bA[mi].z, bA[mi].w);
+					grp_mma_u8(acc[mi][1][2], af[1], bB[mi].x, bB[mi].y);
+					grp_mma_u8(acc[mi][1][3], af[1], bB[mi].z, bB[mi].w);
 				}
 			}
 
@@ -377,7 +400,7 @@ __global__ void __launch_bounds__(GDEEP_WARPS * 32) wvm_deep_group_kernel(const 
 		__syncwarp();
 		if (lane == 0) {
 			float cdf = 0.f;
-			for (int k = 0; k < 64; ++k) lut[k] = (uint8_t)grp_hq_step(cdf, hist[k], stretch);
+			for (int k = 0; k < 64; ++k) lut[k] = (uint8_t)grp_hq_step_any(cdf, hist[k], stretch);
 		}
 		__syncwarp();
 		/* --- integral image with a zero first row and column: ii[(y+1)*pitch + x+1] = sum of x[0..y][0..x] --- */

@@ -441,6 +441,96 @@ class DetectorSet:
         return dict(zip(("enqueue", "phase_a", "phase_b", "call", "wait_stage1"), ms))
 
 
+class AggregatedFeaturesDetector:
+    """detection::AggregatedFeaturesDetector (AggregatedFeaturesDetector.cpp:37-118) with a GrayscaleFilter image filter and a
+    FhogFilter layer filter: weights [window_rows, window_cols, 3 * unsigned_bins + 4] float32 = the linear SVM's support vector."""
+
+    def __init__(self, ctx, weights, bias, threshold, cell=4, octave_layer_count=5, min_window_width=0, nms_threshold=0.3,
+                 nms_type=capi.FDB_NMS_MAX_SCORE, width_scale=1.0, height_scale=1.0, unsigned_bins=9, interpolate_bins=False,
+                 interpolate_cells=True, alpha=0.2):
+        self.ctx = ctx
+        w = np.ascontiguousarray(weights, np.float32)
+        assert w.ndim == 3 and w.shape[2] == 3 * unsigned_bins + 4
+        d = capi.AggdetDesc()
+        d.cell_size, d.window_rows, d.window_cols, d.octave_layer_count = cell, w.shape[0], w.shape[1], octave_layer_count
+        d.min_window_width, d.width_scale, d.height_scale = min_window_width, width_scale, height_scale
+        d.unsigned_bins, d.interpolate_bins, d.interpolate_cells, d.alpha = unsigned_bins, int(interpolate_bins), int(interpolate_cells), alpha
+        d.weights = w.ctypes.data_as(C.POINTER(C.c_float))
+        d.bias, d.threshold, d.nms_overlap_threshold, d.nms_type = bias, threshold, nms_threshold, nms_type
+        h = C.c_void_p()
+        capi.check(ctx.lib, ctx.lib.fdb_aggdet_create(ctx.h, C.byref(d), C.byref(h)))
+        self.h, self.dim = h, w.shape[2]
+
+    def __del__(self):
+        try:
+            if self.h and self.ctx.h:
+                self.ctx.lib.fdb_aggdet_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def prepare(self, width, height, max_batch):
+        capi.check(self.ctx.lib, self.ctx.lib.fdb_aggdet_prepare(self.h, width, height, max_batch))
+        self.width, self.height = width, height
+
+    def layers(self):
+        n = C.c_int32()
+        capi.check(self.ctx.lib, self.ctx.lib.fdb_aggdet_layers(self.h, C.byref(n), None, 0))
+        info = np.zeros((max(n.value, 1), 6), np.int32)
+        capi.check(self.ctx.lib, self.ctx.lib.fdb_aggdet_layers(self.h, C.byref(n), info.ctypes.data, n.value))
+        return [dict(zip(("index", "width", "height", "cells_x", "cells_y", "positions"), map(int, r))) for r in info[:n.value]]
+
+    @property
+    def positions_per_frame(self):
+        return int(self.ctx.lib.fdb_aggdet_positions_per_frame(self.h))
+
+    def detect(self, frames, cap=None):
+        """frames [n, H, W] u8 -> (rects [k, 4] x y w h, scores [k], frame [k])"""
+        frames = np.ascontiguousarray(frames, np.uint8)
+        if frames.ndim == 2:
+            frames = frames[None]
+        n, H, W = frames.shape
+        assert (W, H) == (self.width, self.height)
+        cap = cap or max(4096, 1024 * n)
+        scores, rects, fr = np.zeros(cap, np.float32), np.zeros((cap, 4), np.int32), np.zeros(cap, np.int32)
+        cnt = C.c_int64()
+        capi.check(self.ctx.lib, self.ctx.lib.fdb_aggdet_detect_batch(self.h, frames.ctypes.data, W, n, scores.ctypes.data, rects.ctypes.data,
+                                                                      fr.ctypes.data, cap, C.byref(cnt)))
+        k = cnt.value
+        return rects[:k].copy(), scores[:k].copy(), fr[:k].copy()
+
+    def detect_device(self, frames_ptr, n, cap=None):
+        cap = cap or max(4096, 1024 * n)
+        scores, rects, fr = np.zeros(cap, np.float32), np.zeros((cap, 4), np.int32), np.zeros(cap, np.int32)
+        cnt = C.c_int64()
+        capi.check(self.ctx.lib, self.ctx.lib.fdb_aggdet_detect_batch_device(self.h, frames_ptr, n, scores.ctypes.data, rects.ctypes.data,
+                                                                             fr.ctypes.data, cap, C.byref(cnt)))
+        k = cnt.value
+        return rects[:k].copy(), scores[:k].copy(), fr[:k].copy()
+
+    def score_maps(self, frame):
+        """per layer: (feature map [cells_y, cells_x, D], score map [valid rows, valid cols])"""
+        frame = np.ascontiguousarray(frame, np.uint8)
+        L = self.layers()
+        npos, ncell = sum(l["positions"] for l in L), sum(l["cells_x"] * l["cells_y"] for l in L)
+        sc, ft = np.zeros(max(npos, 1), np.float32), np.zeros(max(ncell * self.dim, 1), np.float32)
+        capi.check(self.ctx.lib, self.ctx.lib.fdb_aggdet_score_maps(self.h, frame.ctypes.data, frame.shape[1], sc.ctypes.data, sc.size,
+                                                                    ft.ctypes.data, ft.size))
+        out, so, fo_ = [], 0, 0
+        for l in L:
+            nc = l["cells_x"] * l["cells_y"]
+            feat = ft[fo_:fo_ + nc * self.dim].reshape(l["cells_y"], l["cells_x"], self.dim)
+            fo_ += nc * self.dim
+            out.append((l, feat, sc[so:so + l["positions"]]))
+            so += l["positions"]
+        return out
+
+    def profile_device(self, frames_ptr, n):
+        ms = (C.c_double * 6)()
+        capi.check(self.ctx.lib, self.ctx.lib.fdb_aggdet_profile_device(self.h, frames_ptr, n, ms))
+        return dict(zip(("pyramid", "histograms", "descriptors", "score_maps", "total", "chunks"), ms))
+
+
 def detect_face_features(face, features, frame, cap=4096):
     """ffpDetectApp.cpp:553-596: face detector on the frame, then each feature detector inside the first face's bounds.
     face / features: prepared SlidingWindowCascade objects. -> (face detections, [feature detections per detector])"""

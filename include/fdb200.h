@@ -59,6 +59,7 @@ typedef struct fdb_svm fdb_svm;
 typedef struct fdb_rvm fdb_rvm;
 typedef struct fdb_detector fdb_detector;
 typedef struct fdb_detector_set fdb_detector_set;
+typedef struct fdb_aggdet fdb_aggdet;
 
 /* ------------------------------------------------------------------------------------------
  * Model descriptors (host memory, copied during create)
@@ -504,8 +505,8 @@ FDB_API int fdb_detector_single_dense_profile(fdb_detector* det, double* kernel_
 /* imageprocessing::filtering::FhogFilter::applyTo (libImageProcessing/src/imageprocessing/filtering/FhogFilter.cpp:59-67 with
  * FhogAggregationFilter.cpp:43-150): the FHOG feature map of one 8-bit image (1 or 3 interleaved channels), the layer filter
  * of detection::AggregatedFeaturesDetector's feature pyramid. out_host: (height / cell_size) x
- * (width / cell_size) x (3 * unsigned_bins + 4) float32. EXPERIMENTAL in this round: the arithmetic is verified on the host
- * against the pinned oracle, the kernels have not run on a B200 yet (see csrc/fhog.cu). */
+ * (width / cell_size) x (3 * unsigned_bins + 4) float32, bit-identical to the reference's filter (GPU tests in
+ * tests/test_fhog_host_emulation.py). One image per call (simple kernels); the batched path is fdb_aggdet_*. */
 FDB_API int fdb_fhog(fdb_ctx* ctx, const uint8_t* image_host, int64_t pitch, int32_t width, int32_t height, int32_t channels,
 		int32_t cell_size, int32_t unsigned_bins, int32_t interpolate_bins, int32_t interpolate_cells, float alpha, float* out_host);
 
@@ -525,6 +526,50 @@ FDB_API int fdb_fhog_score_map(fdb_ctx* ctx, const uint8_t* image_host, int64_t 
 FDB_API int fdb_aggdet_windows(const float* score_map, int32_t valid_rows, int32_t valid_cols, float threshold, int32_t kernel_rows,
 		int32_t kernel_cols, int32_t cell_size, double scale_x, double scale_y, float width_scale, float height_scale,
 		float* scores_out, int32_t* rects_xywh_out, int64_t cap, int64_t* n_out);
+
+/* ------------------------------------------------------------------------------------------
+ * detection::AggregatedFeaturesDetector (the reference's newer detector family)
+ * ------------------------------------------------------------------------------------------
+ * AggregatedFeaturesDetector(imageFilter = GrayscaleFilter, layerFilter = FhogFilter, cellSize, windowSize, octaveLayerCount,
+ * svm (LinearKernel), nms, widthScale, heightScale, minWindowWidth) - AggregatedFeaturesDetector.cpp:37-66 - on batches of
+ * 8-bit 1-channel frames: image pyramid with one layer per octave step (AggregatedFeaturesExtractor.cpp:22-73: scale limits
+ * from the window and image size), FHOG of every layer, score map = -bias + correlation of the feature map with the SVM's
+ * support vector (ConvolutionFilter.cpp:31-49), windows with score > threshold -> boxes in image pixels
+ * (computeBoundsInImagePixels + rescaleWindow) -> NonMaximumSuppression per frame. Everything up to the candidate list runs on
+ * the GPU (csrc/aggdet.cu). Not covered: colour input to the layer filter, the approximated in-between layers of the FPDW
+ * variant (ImagePyramid.cpp:200-289) and the LUV / ACF channel filters. */
+typedef struct fdb_aggdet_desc {
+	int32_t cell_size;                /* cellSizeInPixels */
+	int32_t window_cols, window_rows; /* windowSize in cells = size of the SVM's support vector */
+	int32_t octave_layer_count;
+	int32_t min_window_width;         /* minWindowWidth in pixels; 0: none */
+	float width_scale, height_scale;  /* rescaleWindow */
+	int32_t unsigned_bins;            /* FhogFilter(cellSize, unsignedBinCount, interpolateBins, interpolateCells, alpha) */
+	int32_t interpolate_bins, interpolate_cells;
+	float alpha;
+	const float* weights;             /* [window_rows][window_cols][3 * unsigned_bins + 4] float32: svm->getSupportVectors()[0] */
+	float bias, threshold;            /* svm->getBias(), svm->getThreshold() */
+	double nms_overlap_threshold;     /* NonMaximumSuppression(overlapThreshold, maximumType) */
+	int32_t nms_type;                 /* fdb_nms_maximum_type */
+} fdb_aggdet_desc;
+FDB_API int fdb_aggdet_create(fdb_ctx* ctx, const fdb_aggdet_desc* desc, fdb_aggdet** out);
+FDB_API void fdb_aggdet_destroy(fdb_aggdet* det);
+FDB_API int fdb_aggdet_prepare(fdb_aggdet* det, int32_t width, int32_t height, int32_t max_batch);
+/* pyramid layers of the prepared size: info_out rows {layer index, width, height, cells x, cells y, score positions} */
+FDB_API int fdb_aggdet_layers(fdb_aggdet* det, int32_t* n_layers, int32_t* info_out, int32_t cap);
+FDB_API int64_t fdb_aggdet_positions_per_frame(fdb_aggdet* det); /* windows scored per frame (all layers) */
+/* AggregatedFeaturesDetector::detectWithScores on n_frames host frames: scores_out [cap], rects_xywh_out [cap][4] (image
+ * pixels), frame_out [cap] (may be NULL); per frame in the order NonMaximumSuppression returns them */
+FDB_API int fdb_aggdet_detect_batch(fdb_aggdet* det, const uint8_t* frames_host, int64_t pitch, int32_t n_frames, float* scores_out,
+		int32_t* rects_xywh_out, int32_t* frame_out, int64_t cap, int64_t* n_out);
+FDB_API int fdb_aggdet_detect_batch_device(fdb_aggdet* det, const uint8_t* frames_device, int32_t n_frames, float* scores_out,
+		int32_t* rects_xywh_out, int32_t* frame_out, int64_t cap, int64_t* n_out);
+/* parity / debugging: the valid score positions of every layer of one frame, concatenated in layer order (scores_out, may be
+ * NULL) and the FHOG feature maps [cells][3 * unsigned_bins + 4] of every layer, concatenated (features_out, may be NULL) */
+FDB_API int fdb_aggdet_score_maps(fdb_aggdet* det, const uint8_t* frame_host, int64_t pitch, float* scores_out, int64_t cap,
+		float* features_out, int64_t feat_cap);
+/* bench.py: kernels serialised between CUDA events: ms_out = {pyramid, histograms, descriptors, score maps, total, chunks} */
+FDB_API int fdb_aggdet_profile_device(fdb_aggdet* det, const uint8_t* frames_device, int32_t n_frames, double ms_out[6]);
 
 /* The per-frame flow of ffpDetectApp (ffpDetectApp.cpp:553-596): the face detector on the whole frame, then every feature
  * detector restricted to the bounds of the FIRST (most probable) face patch - Patch::getBounds() = {x - w / 2, y - h / 2, w, h}
