@@ -25,6 +25,7 @@
 
 #include "fdb200.h"
 
+#include <algorithm>
 #include <cmath>
 #include <memory>
 #include <stdexcept>
@@ -237,20 +238,52 @@ public:
 		if (stepX < 1) throw std::invalid_argument("DirectPyramidFeatureExtractor: stepX has to be greater than zero");
 		if (stepY < 1) throw std::invalid_argument("DirectPyramidFeatureExtractor: stepY has to be greater than zero");
 		if (stepLayer < 1) throw std::invalid_argument("DirectPyramidFeatureExtractor: stepLayer has to be greater than zero");
-		if (stepX != desc.step_x || stepY != desc.step_y || stepLayer != 1 || roi.width != 0 || roi.height != 0)
-			throw std::invalid_argument("fdb200: extract() supports the detector's own step over the whole image");
-		ensurePatches();
+		if (current.empty()) return std::vector<std::shared_ptr<imageprocessing::Patch>>();
 		std::vector<std::shared_ptr<imageprocessing::Patch>> out;
 		const int dim = desc.patch_width * desc.patch_height;
-		for (size_t li = 0; li < layers.size(); ++li) {
+		const bool whole = roi.x == 0 && roi.y == 0 && roi.width == 0 && roi.height == 0;
+		if (whole && stepX == desc.step_x && stepY == desc.step_y && stepLayer == 1) {
+			/* the detector's own scan: every patch in one call */
+			ensurePatches();
+			for (size_t li = 0; li < layers.size(); ++li) {
+				const fdb_layer_info& L = layers[li];
+				if ((firstLayer >= 0 && L.index < firstLayer) || (lastLayer >= 0 && L.index > lastLayer)) continue;
+				for (int iy = 0; iy < L.windows_y; ++iy)
+					for (int ix = 0; ix < L.windows_x; ++ix) {
+						const int64_t w = L.first_window + (int64_t)iy * L.windows_x + ix;
+						out.push_back(makePatch(L, ix * desc.step_x, iy * desc.step_y, &patches[(size_t)w * dim]));
+					}
+			}
+			return out;
+		}
+		/* any other step / region / layer stride: the window list of DirectPyramidFeatureExtractor.cpp:84-121, patches
+		 * from the device in one call */
+		cv::Rect r = roi;
+		if (whole) { r.x = 0; r.y = 0; r.width = width; r.height = height; }
+		else { /* :87-92 */
+			const int x0 = std::max(0, r.x), y0 = std::max(0, r.y);
+			r.width = std::min(width, r.width + x0) - x0; r.height = std::min(height, r.height + y0) - y0;
+			r.x = x0; r.y = y0;
+		}
+		std::vector<int32_t> lxy;
+		std::vector<const fdb_layer_info*> owner;
+		for (size_t li = 0; li < layers.size(); li += (size_t)stepLayer) { /* :99: the stride runs over the whole layer list */
 			const fdb_layer_info& L = layers[li];
 			if ((firstLayer >= 0 && L.index < firstLayer) || (lastLayer >= 0 && L.index > lastLayer)) continue;
-			for (int iy = 0; iy < L.windows_y; ++iy)
-				for (int ix = 0; ix < L.windows_x; ++ix) {
-					const int64_t w = L.first_window + (int64_t)iy * L.windows_x + ix;
-					out.push_back(makePatch(L, ix * desc.step_x, iy * desc.step_y, &patches[(size_t)w * dim]));
+			const int bx = cvRound(r.x * L.scale), by = cvRound(r.y * L.scale);             /* :110-111 */
+			const int ex = cvRound((r.x + r.width) * L.scale), ey = cvRound((r.y + r.height) * L.scale);
+			for (int y = by; y + desc.patch_height < ey; y += stepY)                         /* strict '<', :113-114 */
+				for (int x = bx; x + desc.patch_width < ex; x += stepX) {
+					lxy.push_back(L.index); lxy.push_back(x); lxy.push_back(y);
+					owner.push_back(&L);
 				}
 		}
+		const int64_t n = (int64_t)owner.size();
+		if (n == 0) return out;
+		std::vector<uint8_t> data((size_t)n * dim), valid((size_t)n);
+		check(fdb_extract_windows(handle, current.ptr<uchar>(0), (int64_t)current.step, &lxy[0], n, &data[0], &valid[0]));
+		for (int64_t i = 0; i < n; ++i)
+			if (valid[(size_t)i]) out.push_back(makePatch(*owner[(size_t)i], lxy[3 * i + 1], lxy[3 * i + 2], &data[(size_t)i * dim]));
 		return out;
 	}
 	std::shared_ptr<imageprocessing::Patch> extract(int layer, int x, int y) const {
@@ -320,15 +353,21 @@ private:
 		return std::make_shared<imageprocessing::Patch>(ox, oy, L.orig_patch_width, L.orig_patch_height, m);
 	}
 	std::shared_ptr<imageprocessing::Patch> extractAt(const fdb_layer_info& L, int x, int y) const {
-		/* DirectPyramidFeatureExtractor.cpp:133-143: out of the layer image => empty pointer.
-		 * Served from the step-1 window grid of the last update(); positions outside that grid
-		 * (the last row/column of a layer) are reported as out of bounds. */
-		if (desc.step_x != 1 || desc.step_y != 1) throw std::invalid_argument("fdb200: single extraction needs a step-1 detector");
-		if (x < 0 || y < 0 || x >= L.windows_x || y >= L.windows_y) return std::shared_ptr<imageprocessing::Patch>();
-		ensurePatches();
-		if (patches.empty()) return std::shared_ptr<imageprocessing::Patch>();
-		const int64_t w = L.first_window + (int64_t)y * L.windows_x + x;
-		return makePatch(L, x, y, &patches[(size_t)w * desc.patch_width * desc.patch_height]);
+		/* DirectPyramidFeatureExtractor.cpp:133-143: not inside the layer image => empty pointer */
+		if (x < 0 || y < 0 || x + desc.patch_width > L.width || y + desc.patch_height > L.height || current.empty())
+			return std::shared_ptr<imageprocessing::Patch>();
+		const int dim = desc.patch_width * desc.patch_height;
+		if (desc.step_x == 1 && desc.step_y == 1 && x < L.windows_x && y < L.windows_y) { /* inside the cached step-1 scan */
+			ensurePatches();
+			const int64_t w = L.first_window + (int64_t)y * L.windows_x + x;
+			return makePatch(L, x, y, &patches[(size_t)w * dim]);
+		}
+		/* the last rows / columns of a layer (the scan's strict '<' bound leaves them out) and coarser scans: one window */
+		const int32_t lxy[3] = {L.index, x, y};
+		std::vector<uint8_t> data((size_t)dim);
+		uint8_t valid = 0;
+		check(fdb_extract_windows(handle, current.ptr<uchar>(0), (int64_t)current.step, lxy, 1, &data[0], &valid));
+		return valid ? makePatch(L, x, y, &data[0]) : std::shared_ptr<imageprocessing::Patch>();
 	}
 	std::vector<std::shared_ptr<detection::ClassifiedPatch>> run(const cv::Mat& image, const cv::Rect& roi, bool useRoi) {
 		std::vector<fdb_detection> dets(4096);
@@ -341,11 +380,21 @@ private:
 			check(status);
 			break;
 		}
+		/* the reference hands the extractor's patch (the HistEq64 data) along with every ClassifiedPatch
+		 * (SlidingWindowDetector.cpp:93-96; read again by FiveStageSlidingWindowDetector.cpp:258-261 and the trackers):
+		 * the patches of the detections come back in one call */
+		const int dim = desc.patch_width * desc.patch_height;
+		std::vector<int32_t> lxy((size_t)n * 3);
+		for (int64_t i = 0; i < n; ++i) { lxy[3 * i] = dets[(size_t)i].layer; lxy[3 * i + 1] = dets[(size_t)i].x; lxy[3 * i + 2] = dets[(size_t)i].y; }
+		std::vector<uint8_t> data((size_t)n * dim), valid((size_t)n);
+		if (n) check(fdb_extract_windows(handle, image.ptr<uchar>(0), (int64_t)image.step, &lxy[0], n, &data[0], &valid[0]));
 		std::vector<std::shared_ptr<detection::ClassifiedPatch>> out;
 		for (int64_t i = 0; i < n; ++i) {
 			const fdb_detection& d = dets[(size_t)i];
-			/* the reference hands the hq64 patch along; fetch it only when a caller asks (empty Mat here) */
-			std::shared_ptr<imageprocessing::Patch> patch = std::make_shared<imageprocessing::Patch>(d.center_x, d.center_y, d.width, d.height, cv::Mat());
+			cv::Mat m(desc.patch_height, desc.patch_width, CV_8U);
+			for (int r = 0; r < desc.patch_height; ++r)
+				for (int c = 0; c < desc.patch_width; ++c) m.ptr<uchar>(r)[c] = data[(size_t)i * dim + r * desc.patch_width + c];
+			std::shared_ptr<imageprocessing::Patch> patch = std::make_shared<imageprocessing::Patch>(d.center_x, d.center_y, d.width, d.height, m);
 			out.push_back(std::make_shared<detection::ClassifiedPatch>(patch, d.positive != 0, d.probability));
 		}
 		return out;
@@ -397,11 +446,26 @@ public:
 		}
 		return out;
 	}
-	/* the whole-image scan filtered to the windows the ROI loop would visit is not implemented: the apps call the single
-	 * detectors on whole images (ffpDetectApp.cpp:557) */
+	/* SlidingWindowDetector::detect(image, roi) (SlidingWindowDetector.cpp:53-79): what ffpDetectApp.cpp:591 calls on every
+	 * feature detector with the bounds of the face */
 	std::vector<std::shared_ptr<detection::ClassifiedPatch>> detect(const cv::Mat& image, const cv::Rect& roi) {
-		if (roi.width != 0 || roi.height != 0) throw std::invalid_argument("fdb200: single detectors scan whole images");
-		return detect(image);
+		const cv::Mat gray = grayOf(context->get(), image);
+		if (gray.cols != width || gray.rows != height) {
+			check(fdb_detector_prepare(handle, gray.cols, gray.rows, 1));
+			width = gray.cols; height = gray.rows;
+		}
+		const int64_t cap = fdb_detector_windows_per_frame(handle);
+		std::vector<fdb_detection> dets((size_t)(cap > 0 ? cap : 1));
+		int64_t n = 0;
+		check(fdb_detect_single_roi(handle, gray.ptr<uchar>(0), (int64_t)gray.step, roi.x, roi.y, roi.width, roi.height, &dets[0],
+				(int64_t)dets.size(), &n));
+		std::vector<std::shared_ptr<detection::ClassifiedPatch>> out;
+		for (int64_t i = 0; i < n; ++i) {
+			const fdb_detection& d = dets[(size_t)i];
+			std::shared_ptr<imageprocessing::Patch> patch = std::make_shared<imageprocessing::Patch>(d.center_x, d.center_y, d.width, d.height, cv::Mat());
+			out.push_back(std::make_shared<detection::ClassifiedPatch>(patch, d.positive != 0, d.probability));
+		}
+		return out;
 	}
 	std::vector<std::shared_ptr<detection::ClassifiedPatch>> detect(std::shared_ptr<imageprocessing::VersionedImage> image) {
 		return detect(image->getData());

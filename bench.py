@@ -760,6 +760,157 @@ def emit(line):
     _JSON_OUT.flush()
 
 
+# ------------------------------------------------------------------------------------------------
+# detection::AggregatedFeaturesDetector: --workload aggdet
+# ------------------------------------------------------------------------------------------------
+AGG = dict(cell=4, window=(10, 10), octave_layer_count=5, unsigned_bins=9, bias=0.0, quantile=0.999)
+
+
+def _aggdet_model():
+    """linear SVM of a FHOG face-sized window (10 x 10 cells of 4 px, 31 features per cell), seeded; the threshold lets
+    0.1 % of the windows of frame 0 through (a detector at its operating point scores few windows above the threshold)"""
+    rng = np.random.default_rng(77)
+    kh, kw = AGG["window"]
+    return rng.normal(0, 0.05, (kh, kw, 3 * AGG["unsigned_bins"] + 4)).astype(np.float32)
+
+
+def _aggdet_cpu_init():
+    from oracle import fdoracle as fo
+    fo.build()
+    _worker_state.update(fo=fo, w=_aggdet_model())
+
+
+def _aggdet_cpu_item(item):
+    frame, thr = item
+    fo = _worker_state["fo"]
+    t0 = time.perf_counter()
+    _, _, maps = fo.aggregated_features_detect(frame, _worker_state["w"], AGG["bias"], thr, cell=AGG["cell"], octave_layer_count=AGG["octave_layer_count"],
+                                               want_scores=True)
+    return sum(m.size for m in maps), time.perf_counter() - t0
+
+
+def run_aggdet(args, rank, world, local_rank):
+    from featuredetection_b200 import synthetic as syn
+    n = args.frames
+    w = _aggdet_model()
+    cfg = {"workload": "detection::AggregatedFeaturesDetector (SURVEY 8(f) rank 2): %d-frame batch per GPU, 640x480 1-channel, GrayscaleFilter + FhogFilter "
+                       "(cell %d, 9 unsigned bins, interpolated cells), %dx%d-cell linear-SVM window, %d pyramid layers per octave, IoU suppression 0.3"
+                       % (n, AGG["cell"], AGG["window"][1], AGG["window"][0], AGG["octave_layer_count"]),
+           "frames_per_gpu": n, "global_frames": n * world, "parallelism": "frame-sharded dp%d" % world,
+           "l2": "a 256 MB scratch write flushes L2 between timed steps"}
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        from oracle import fdoracle as fo
+        fo.build()
+        cores = os.cpu_count() or 1
+        pool = mp.get_context("spawn").Pool(cores, initializer=_aggdet_cpu_init)
+        frames = [syn.synthetic_frame(100 + k) for k in range(cores * 2)]
+        pool.map(_aggdet_cpu_item, [(frames[0], 1e9)] * cores)
+        tot_w, tot_t = 0, 0.0
+        for _ in range(args.steps):
+            t0 = time.perf_counter()
+            res = pool.map(_aggdet_cpu_item, [(f, 1e9) for f in frames], chunksize=1)
+            tot_t += time.perf_counter() - t0
+            tot_w += sum(r[0] for r in res)
+        pool.close(); pool.join()
+        value = tot_w / tot_t
+        sample = "%d frames per step over %d processes (oracle restatement: C FHOG + numpy correlation), %d steps" % (len(frames), cores, args.steps)
+        emit({"impl": "reference", "metric": "scored_windows_per_s", "value": value, "unit": "windows/s", "n_gpus": args.gpus, "steps": args.steps,
+              "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+              "dtype": "u8/f32", "data": "synthetic", "config": cfg,
+              "cpu_baseline": {"value": value, "unit": "windows/s", "cores": cores, "kind": "port", "sample": sample},
+              "e2e": {"value": value, "unit": "windows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+        return
+    import torch
+    import torch.distributed as dist
+    from featuredetection_b200.detector import Context, AggregatedFeaturesDetector
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - the B200 path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        dist.init_process_group("nccl", device_id=device)
+    ctx = Context(local_rank)
+    base = syn.synthetic_frames((rank * n) % 97, min(8, n))
+    probe = AggregatedFeaturesDetector(ctx, w, AGG["bias"], 1e9, cell=AGG["cell"], octave_layer_count=AGG["octave_layer_count"])
+    probe.prepare(W, H, 1)
+    allsc = np.concatenate([sc for _, _, sc in probe.score_maps(base[0])])
+    thr = float(np.quantile(allsc, AGG["quantile"]))
+    det = AggregatedFeaturesDetector(ctx, w, AGG["bias"], thr, cell=AGG["cell"], octave_layer_count=AGG["octave_layer_count"])
+    det.prepare(W, H, n)
+    layers = det.layers()
+    npos = det.positions_per_frame
+    host_frames = torch.from_numpy(np.concatenate([base] * ((n + len(base) - 1) // len(base)))[:n]).pin_memory()
+    dev_frames = host_frames.to(device)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(); ctx.synchronize()
+
+    def timed(fn):
+        for _ in range(args.warmup):
+            fn()
+        barrier()
+        l0 = ctx.launch_count()
+        ms, out = [], None
+        for _ in range(args.steps):
+            flush.fill_(1); torch.cuda.synchronize()
+            ctx.timer_start()
+            out = fn()
+            ms.append(ctx.timer_stop())
+        barrier()
+        tot = torch.tensor([sum(ms)], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(tot, op=dist.ReduceOp.MAX)
+        return float(tot.item()), out, ctx.launch_count() - l0
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    tot, out, launches = timed(lambda: det.detect_device(dev_frames.data_ptr(), n))
+    prof = [det.profile_device(dev_frames.data_ptr(), n) for _ in range(3)]
+    e2e_tot, out_e2e, _ = timed(lambda: det.detect(host_frames.numpy()))
+    clocks = sampler.stop() if rank == 0 else None
+    if rank == 0:
+        value = npos * n * world * args.steps / (tot * 1e-3)
+        e2e = npos * n * world * args.steps / (e2e_tot * 1e-3)
+        pk = {k: float(np.mean([p[k] for p in prof])) for k in prof[0]}
+        peak, peak_src = hbm_peak()
+        # FHOG (histogram + descriptor kernels): every layer pixel read once, every feature written once (31 x 4 bytes per cell)
+        algo = (sum(l["width"] * l["height"] for l in layers) + sum(l["cells_x"] * l["cells_y"] for l in layers) * 31 * 4) * n
+        achieved = algo / ((pk["histograms"] + pk["descriptors"]) * 1e-3) / 1e9
+        traffic, traffic_src = measured_traffic("aggdet_hist_kernel")
+        cpu = None
+        if not args.no_cpu_baseline and world == 1:
+            cores = os.cpu_count() or 1
+            pool = mp.get_context("spawn").Pool(cores, initializer=_aggdet_cpu_init)
+            frames = [syn.synthetic_frame(100 + k) for k in range(cores * 2)]
+            pool.map(_aggdet_cpu_item, [(frames[0], 1e9)] * cores)
+            t0 = time.perf_counter()
+            res = pool.map(_aggdet_cpu_item, [(f, 1e9) for f in frames], chunksize=1)
+            wall = time.perf_counter() - t0
+            pool.close(); pool.join()
+            cpu = {"value": sum(r[0] for r in res) / wall, "unit": "windows/s", "cores": cores, "kind": "port",
+                   "sample": "%d frames over %d processes (oracle restatement: C FHOG + numpy correlation), %.1f s wall" % (len(frames), cores, wall)}
+        emit({"metric": "scored_windows_per_s", "value": value, "unit": "windows/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+              "ms_per_step": tot / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/f32", "data": "synthetic",
+              "config": dict(cfg, windows_per_frame=npos, pyramid_layers=len(layers)),
+              "frames_per_s": value / npos, "clocks": clocks,
+              "e2e": {"value": e2e, "unit": "windows/s", "h2d_bytes_per_step": int(W * H * n), "d2h_bytes_per_step": int(len(out_e2e[1]) * 24 + 4),
+                      "ms_per_step": e2e_tot / args.steps, "frames_per_s": e2e / npos},
+              "gpu_launches": int(launches),
+              "roofline": {"bound": "hbm", "kernel": "aggdet_hist_kernel + aggdet_desc_kernel (FHOG feature maps of every pyramid layer)", "achieved": achieved,
+                           "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                           "algorithmic_bytes_per_step": int(algo), "kernel_ms_per_step": pk["histograms"] + pk["descriptors"]},
+              "kernel_ms": pk, "detections_per_step": int(len(out[1])) * world, "cpu_baseline": cpu})
+    if world > 1:
+        dist.barrier(); dist.destroy_process_group()
+
+
 def pin_rank_to_cores(local_rank, world):
     """each rank's host threads (pipeline thread, CUDA driver threads) stay on their own share of the host cores"""
     try:
@@ -906,7 +1057,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--frames", type=int, default=None, help="frames per GPU per step (default 256; 4096 faces for sdm)")
     ap.add_argument("--frames-total", type=int, default=None, help="strong scaling: this many frames per step split over the ranks (BASELINE configs[3]: 4096)")
-    ap.add_argument("--workload", default="landmarks15", choices=["landmarks15", "facefrontal", "sdm", "single-psvm"],
+    ap.add_argument("--workload", default="landmarks15", choices=["landmarks15", "facefrontal", "sdm", "single-psvm", "aggdet"],
                     help="landmarks15 (default, headline) = all 15 ffpDetectApp landmark detectors on every frame (BASELINE north_star / configs[3]); "
                          "facefrontal = BASELINE configs[1]; sdm = BASELINE configs[4] (supervised-descent fit, 68 landmarks, 4096 faces per GPU); "
                          "single-psvm = the `single` detector, every window through the RBF-SVM")
@@ -927,7 +1078,7 @@ def main():
     if args.frames_total:
         args.frames = max(1, args.frames_total // world)
     if args.frames is None:
-        args.frames = {"facefrontal": 256, "landmarks15": 256, "sdm": 4096, "single-psvm": 256}[args.workload]
+        args.frames = {"facefrontal": 256, "landmarks15": 256, "sdm": 4096, "single-psvm": 256, "aggdet": 64}[args.workload]
     if args.feature is None:
         args.feature = "hog" if args.workload == "facefrontal" else "hq64"
     if args.workload == "landmarks15" and args.feature != "hq64":
@@ -942,6 +1093,9 @@ def main():
             run_reference_single(args, rank, world)
         else:
             run_single(args, rank, world, local_rank)
+        return
+    if args.workload == "aggdet":
+        run_aggdet(args, rank, world, local_rank)
         return
     if args.workload == "sdm":
         if args.impl == "reference":

@@ -207,6 +207,9 @@ SYMBOLS = [
     ("fdb_detect_single_device", C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, _P(C.c_int64)]),
     ("fdb_detector_single_dense", C.c_int, [C.c_void_p]),
     ("fdb_detector_single_dense_profile", C.c_int, [C.c_void_p, _P(C.c_double), _P(C.c_int32)]),
+    ("fdb_detect_single_roi", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int64,
+                                        _P(C.c_int64)]),
+    ("fdb_extract_windows", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     ("fdb_detector_set_create", C.c_int, [C.c_void_p, _P(C.c_void_p), C.c_int32, _P(C.c_void_p)]),
     ("fdb_detector_set_destroy", None, [C.c_void_p]),
     ("fdb_detector_set_prepare", C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32]),

@@ -1307,6 +1307,153 @@ int fdb_detect_single(fdb_detector* det, const uint8_t* frames_host, int64_t pit
 	return detect_single(det, frames_host, false, pitch, n_frames, distance_out, detections_out, det_cap, n_detections);
 } FDB_API_CATCH
 
+/* SlidingWindowDetector::detect(image, roi) (SlidingWindowDetector.cpp:53-79) of a `single` detector: the windows
+ * PyramidFeatureExtractor::extract(stepX, stepY, roi) visits (DirectPyramidFeatureExtractor.cpp:84-121), every one classified,
+ * positives in extract order - what ffpDetectApp.cpp:591 calls for every feature detector inside the face box */
+int fdb_detect_single_roi(fdb_detector* det, const uint8_t* frame_host, int64_t pitch, int32_t roi_x, int32_t roi_y, int32_t roi_w,
+		int32_t roi_h, fdb_detection* detections_out, int64_t det_cap, int64_t* n_detections) try {
+	if (!det || !det->prepared) return fail(FDB_ERR_INVALID_ARGUMENT, "detector not prepared (call fdb_detector_prepare)");
+	int s = check_ctx(det->ctx); if (s) return s;
+	if (det->wvm || !det->svm) return fail(FDB_ERR_INVALID_ARGUMENT, "fdb_detect_single_roi needs a detector created with an SVM or RVM only");
+	if (!frame_host) return fail(FDB_ERR_INVALID_ARGUMENT, "null frame");
+	Plan plan = det->plan;
+	const int W = plan.width, H = plan.height;
+	if (pitch < W) return fail(FDB_ERR_INVALID_ARGUMENT, "pitch smaller than the frame width");
+	const int64_t windows = enumerate_windows(&plan, det->desc.patch_width, det->desc.patch_height, det->desc.step_x, det->desc.step_y,
+			roi_x, roi_y, roi_w, roi_h);
+	plan.windows = windows;
+	std::fill(det->counts, det->counts + 5, 0);
+	det->counts[0] = windows;
+	std::vector<fdb_detection> dets;
+	if (windows > 0) {
+		cudaStream_t st = det->ctx->stream;
+		Slot& sl = det->slots[0];
+		std::vector<SvmItem> items((size_t)windows);
+		size_t k = 0;
+		for (size_t li = 0; li < plan.layers.size(); ++li) {
+			const PlanLayer& L = plan.layers[li];
+			for (int iy = 0; iy < L.windows_y; ++iy)
+				for (int ix = 0; ix < L.windows_x; ++ix) {
+					SvmItem it; it.frame = 0; it.layer = (int)li;
+					it.x = L.begin_x + ix * det->desc.step_x; it.y = L.begin_y + iy * det->desc.step_y;
+					items[k++] = it;
+				}
+		}
+		CUDA_TRY(cudaMemcpy2DAsync(sl.d_frames, (size_t)W, frame_host, (size_t)pitch, (size_t)W, (size_t)H, cudaMemcpyHostToDevice, st));
+		sl.frames_dev = sl.d_frames; sl.base = 0; sl.n = 1;
+		s = enqueue_stage1(det, sl, st, sl.d_frames, 1, det->plan, det->d_layers, 0, nullptr, nullptr, false);
+		if (s) return s;
+		const bool is_rvm = det->svm->dev.rvm_filters > 0;
+		/* d_all_items / d_all_dist hold a whole-image scan: a ROI never has more windows */
+		CUDA_TRY(cudaMemcpyAsync(det->d_all_items, items.data(), sizeof(SvmItem) * (size_t)windows, cudaMemcpyHostToDevice, st));
+		svm_stage(det, sl, st, det->plan, det->d_layers, det->d_all_items, (int)windows, det->d_all_dist, true, is_rvm ? det->d_all_level : nullptr);
+		CUDA_TRY(cudaGetLastError());
+		CUDA_TRY(cudaMemcpyAsync(det->h_all_dist, det->d_all_dist, sizeof(double) * (size_t)windows, cudaMemcpyDeviceToHost, st));
+		if (is_rvm) CUDA_TRY(cudaMemcpyAsync(det->h_all_level, det->d_all_level, sizeof(int) * (size_t)windows, cudaMemcpyDeviceToHost, st));
+		CUDA_TRY(cudaStreamSynchronize(st));
+		for (int64_t w = 0; w < windows; ++w) {
+			const double dist = det->h_all_dist[w];
+			int level = -1;
+			if (is_rvm) {
+				level = det->h_all_level[w];
+				if (!(level + 1 == det->svm->dev.rvm_filters && dist >= (double)det->svm->rvm_thresholds[(size_t)level])) continue;
+			} else if (!(dist >= det->svm->dev.threshold)) continue;
+			fdb_detection d;
+			fill_detection(&d, plan, det->desc, 0, w);
+			d.reserved = 0;
+			d.wvm_level = level;
+			d.wvm_fout = std::numeric_limits<float>::quiet_NaN();
+			d.wvm_probability = std::numeric_limits<double>::quiet_NaN();
+			d.svm_distance = dist;
+			d.svm_probability = is_rvm ? rvm_probability(det->svm->logistic_a, det->svm->logistic_b, dist)
+					: svm_probability(det->svm->logistic_a, det->svm->logistic_b, dist);
+			d.probability = d.svm_probability;
+			d.positive = 1;
+			dets.push_back(d);
+		}
+		/* the whole-image item table of fdb_detect_single lives in d_all_items: restore it */
+		std::vector<SvmItem> all((size_t)det->plan.windows);
+		size_t q = 0;
+		for (size_t li = 0; li < det->plan.layers.size(); ++li) {
+			const PlanLayer& L = det->plan.layers[li];
+			for (int iy = 0; iy < L.windows_y; ++iy)
+				for (int ix = 0; ix < L.windows_x; ++ix) {
+					SvmItem it; it.frame = 0; it.layer = (int)li;
+					it.x = L.begin_x + ix * det->desc.step_x; it.y = L.begin_y + iy * det->desc.step_y;
+					all[q++] = it;
+				}
+		}
+		if (!all.empty()) CUDA_TRY(cudaMemcpy(det->d_all_items, all.data(), sizeof(SvmItem) * all.size(), cudaMemcpyHostToDevice));
+	}
+	det->counts[1] = det->counts[2] = det->counts[3] = det->counts[4] = (int64_t)dets.size();
+	return copy_out(dets, detections_out, det_cap, n_detections);
+} FDB_API_CATCH
+
+/* PyramidFeatureExtractor::extract(layer, x, y) / extract(x, y, w, h) for a list of windows of one frame
+ * (DirectPyramidFeatureExtractor.cpp:125-143): layer_x_y = n triples {pyramid layer index, window corner x, y inside the layer};
+ * out = n vectors of the detector's patch filter (HistEq64 patches, or the feature space set with fdb_detector_set_feature);
+ * valid_out[i] = 0 where the reference returns an empty pointer (no such layer, window not inside the layer image) - such
+ * vectors are left untouched. */
+int fdb_extract_windows(fdb_detector* det, const uint8_t* frame_host, int64_t pitch, const int32_t* layer_x_y, int64_t n, void* out,
+		uint8_t* valid_out) try {
+	if (!det || !det->prepared) return fail(FDB_ERR_INVALID_ARGUMENT, "detector not prepared (call fdb_detector_prepare)");
+	int s = check_ctx(det->ctx); if (s) return s;
+	if (!frame_host || n < 0 || (n > 0 && (!layer_x_y || !out || !valid_out))) return fail(FDB_ERR_INVALID_ARGUMENT, "null buffer");
+	const Plan& plan = det->plan;
+	if (pitch < plan.width) return fail(FDB_ERR_INVALID_ARGUMENT, "pitch smaller than the frame width");
+	const int pw = det->desc.patch_width, ph = det->desc.patch_height;
+	const bool hq = !det->has_feature || det->feat.kind == FDB_FEATURE_HQ64;
+	const size_t vec_bytes = hq ? (size_t)pw * ph : (size_t)det->feat.dim * (det->feat.is_float ? 4 : 1);
+	std::vector<SvmItem> items;
+	std::vector<int64_t> where;
+	for (int64_t i = 0; i < n; ++i) {
+		valid_out[i] = 0;
+		int li = -1;
+		for (size_t k = 0; k < plan.layers.size(); ++k) if (plan.layers[k].index == layer_x_y[3 * i]) li = (int)k;
+		if (li < 0) continue;
+		const int x = layer_x_y[3 * i + 1], y = layer_x_y[3 * i + 2];
+		if (x < 0 || y < 0 || x + pw > plan.layers[(size_t)li].width || y + ph > plan.layers[(size_t)li].height) continue; /* :135-136 */
+		SvmItem it; it.frame = 0; it.layer = li; it.x = x; it.y = y;
+		items.push_back(it); where.push_back(i);
+		valid_out[i] = 1;
+	}
+	if (items.empty()) return FDB_OK;
+	cudaStream_t st = det->ctx->stream;
+	Slot& sl = det->slots[0];
+	CUDA_TRY(cudaMemcpy2DAsync(sl.d_frames, (size_t)plan.width, frame_host, (size_t)pitch, (size_t)plan.width, (size_t)plan.height,
+			cudaMemcpyHostToDevice, st));
+	sl.frames_dev = sl.d_frames; sl.base = 0; sl.n = 1;
+	s = enqueue_stage1(det, sl, st, sl.d_frames, 1, plan, det->d_layers, 0, nullptr, nullptr, false);
+	if (s) return s;
+	if (!hq && det->feat.layer_channels) {
+		launch_feature_layers(st, det->feat, sl.d_frames, plan.width, plan.height, 1, sl.d_arena, plan.arena_bytes, det->d_layers,
+				sl.d_farena, det->farena_bytes);
+		det->ctx->launches++;
+	}
+	const int batch = std::min<int>(hq ? 4096 : FEAT_BATCH, det->items_cap);
+	std::vector<void*> tmp;
+	uint8_t* d_vec = nullptr;
+	if (hq) { s = dev_alloc(&d_vec, (size_t)batch * vec_bytes, tmp); if (s) return s; }
+	std::vector<uint8_t> host((size_t)batch * vec_bytes);
+	for (size_t off = 0; off < items.size(); off += (size_t)batch) {
+		const int m = (int)std::min<size_t>((size_t)batch, items.size() - off);
+		cudaError_t e = cudaMemcpyAsync(sl.d_items, items.data() + off, sizeof(SvmItem) * (size_t)m, cudaMemcpyHostToDevice, st);
+		if (e == cudaSuccess) {
+			if (hq) launch_hq64_items(st, pw, ph, sl.d_frames, plan.width, plan.height, sl.d_arena, plan.arena_bytes, det->d_layers, sl.d_items, m, d_vec);
+			else launch_feature_patches(st, det->feat, sl.d_frames, plan.width, plan.height, sl.d_arena, plan.arena_bytes, det->d_layers,
+					sl.d_farena, det->farena_bytes, sl.d_items, m, sl.d_feat);
+			det->ctx->launches++;
+			e = cudaGetLastError();
+		}
+		if (e == cudaSuccess) e = cudaMemcpyAsync(host.data(), hq ? (const void*)d_vec : (const void*)sl.d_feat, vec_bytes * (size_t)m, cudaMemcpyDeviceToHost, st);
+		if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+		if (e != cudaSuccess) { free_all(tmp); return fail(FDB_ERR_CUDA, std::string("fdb_extract_windows: ") + cudaGetErrorString(e)); }
+		for (int k = 0; k < m; ++k) std::memcpy((uint8_t*)out + (size_t)where[off + (size_t)k] * vec_bytes, host.data() + (size_t)k * vec_bytes, vec_bytes);
+	}
+	free_all(tmp);
+	return FDB_OK;
+} FDB_API_CATCH
+
 int fdb_detect_single_device(fdb_detector* det, const uint8_t* frames_device, int32_t n_frames, double* distance_device,
 		fdb_detection* detections_out, int64_t det_cap, int64_t* n_detections) try {
 	if (!det || !det->prepared) return fail(FDB_ERR_INVALID_ARGUMENT, "detector not prepared (call fdb_detector_prepare)");

@@ -497,6 +497,18 @@ FDB_API int fdb_detect_single(fdb_detector* det, const uint8_t* frames_host, int
  * (fdb_detector_single_dense() == 1), FDB_ERR_UNSUPPORTED otherwise. */
 FDB_API int fdb_detect_single_device(fdb_detector* det, const uint8_t* frames_device, int32_t n_frames,
 		double* distance_device, fdb_detection* detections_out, int64_t det_cap, int64_t* n_detections);
+/* SlidingWindowDetector::detect(image, roi) (SlidingWindowDetector.cpp:53-79) of a `single` detector: the windows
+ * PyramidFeatureExtractor::extract(stepX, stepY, roi) visits inside the region of interest, all classified; positives in
+ * extract order. This is what ffpDetectApp.cpp:591 calls on every feature detector with the face box. */
+FDB_API int fdb_detect_single_roi(fdb_detector* det, const uint8_t* frame_host, int64_t pitch, int32_t roi_x, int32_t roi_y,
+		int32_t roi_w, int32_t roi_h, fdb_detection* detections_out, int64_t det_cap, int64_t* n_detections);
+/* PyramidFeatureExtractor::extract(layer, x, y) / extract(x, y, w, h) (DirectPyramidFeatureExtractor.cpp:67-73,125-143) for n
+ * windows of one frame: layer_x_y = n triples {pyramid layer index, window corner x, y inside the layer image}; out = n
+ * vectors of the detector's patch filter (HistEq64 patches of patch_width * patch_height bytes, or the feature space set with
+ * fdb_detector_set_feature); valid_out[i] = 0 where the reference returns an empty pointer (no such layer, window not inside
+ * the layer image; the vector is left untouched). */
+FDB_API int fdb_extract_windows(fdb_detector* det, const uint8_t* frame_host, int64_t pitch, const int32_t* layer_x_y, int64_t n,
+		void* out, uint8_t* valid_out);
 FDB_API int fdb_detector_single_dense(fdb_detector* det);
 /* time spent in svm_dense_kernel during the last fdb_detect_single[_device] call (CUDA events on the library stream)
  * and the number of launches (one per chunk of frames): the roofline numerator of bench.py --workload single-psvm */
