@@ -157,7 +157,7 @@ int fdb_wvm_create(fdb_ctx* ctx, const fdb_wvm_desc* d, fdb_wvm** out) try {
 		const int cntval = d->area_cntval[f];
 		max_nv = std::max(max_nv, cntval - 1);
 		if (cntval < 1) return fail(FDB_ERR_INVALID_ARGUMENT, "WVM: filter without grey values");
-		if (cntval - 1 > FDB_MAX_VALUES) return fail(FDB_ERR_UNSUPPORTED, "WVM: more than 8 rectangle grey values per filter");
+		if (cntval > 256) return fail(FDB_ERR_UNSUPPORTED, "WVM: more than 255 rectangle grey values per filter");
 		val_off[f] = slot;
 		mask_off[f] = (int)masks.size();
 		const int nv = cntval - 1;

@@ -201,7 +201,7 @@ int enqueue_stage1(fdb_detector* det, Slot& sl, cudaStream_t st, const uint8_t* 
 	fdb_ctx* c = det->ctx;
 	const int W = plan.width, H = plan.height;
 	sl.arena = sl.d_arena; sl.arena_stride = plan.arena_bytes;
-	CUDA_TRY(cudaMemsetAsync(sl.d_counters, 0, 4 * sizeof(int), st));
+	CUDA_TRY(cudaMemsetAsync(sl.d_counters, 0, FDB_NCOUNTERS * sizeof(int), st));
 	if (marks) CUDA_TRY(cudaEventRecord(c->ev[1], st));
 	{ const int r = enqueue_pyramid(c, st, det->jobs, d_frames, W, H, n, sl.d_arena, plan.arena_bytes, marks ? c->ev[2] : nullptr); if (r) return r; }
 	if (marks) CUDA_TRY(cudaEventRecord(c->ev[3], st));
@@ -255,7 +255,7 @@ void fill_detection(fdb_detection* d, const Plan& plan, const fdb_detector_desc&
 
 /* stage-1 results -> counters + candidates on their way to the host (async) */
 int enqueue_fetch(fdb_detector* det, Slot& sl, cudaStream_t st) {
-	CUDA_TRY(cudaMemcpyAsync(sl.h_counters, sl.d_counters, 4 * sizeof(int) + OPT_CAND * sizeof(Candidate), cudaMemcpyDeviceToHost, st));
+	CUDA_TRY(cudaMemcpyAsync(sl.h_counters, sl.d_counters, FDB_NCOUNTERS * sizeof(int) + OPT_CAND * sizeof(Candidate), cudaMemcpyDeviceToHost, st));
 	CUDA_TRY(cudaEventRecord(sl.ev_stage1, st));
 	return FDB_OK;
 }
@@ -303,7 +303,7 @@ int phase_a_fetch(fdb_detector* det, Slot& sl, cudaStream_t st, const DevLayer* 
 	const int ncand = sl.h_counters[0];
 	if (ncand > det->cand_cap)
 		return fail(FDB_ERR_OVERFLOW, "stage-1 candidate list overflow: raise max_positives_per_frame");
-	sl.cand_src = reinterpret_cast<const Candidate*>(sl.h_counters + 4);
+	sl.cand_src = reinterpret_cast<const Candidate*>(sl.h_counters + FDB_NCOUNTERS);
 	if (ncand > OPT_CAND) {
 		/* the list is complete (stage 1 finished): fetch it on the copy stream - `st` may already hold other work of this chunk
 		 * (a detector set queues its members' SVM kernels there) and the host must not wait for that */
@@ -896,14 +896,17 @@ int fdb_detector_prepare(fdb_detector* det, int32_t width, int32_t height, int32
 		s = dev_alloc(&sl.d_frames, (size_t)det->chunk * width * height, det->owned); if (s) return s;
 		s = dev_alloc(&sl.d_arena, (size_t)det->chunk * (size_t)plan.arena_bytes, det->owned); if (s) return s;
 		uint8_t* cbuf = nullptr;
-		s = dev_alloc(&cbuf, 4 * sizeof(int) + (size_t)det->cand_cap * sizeof(Candidate), det->owned); if (s) return s;
+		s = dev_alloc(&cbuf, FDB_NCOUNTERS * sizeof(int) + (size_t)det->cand_cap * sizeof(Candidate), det->owned); if (s) return s;
 		sl.d_counters = reinterpret_cast<int*>(cbuf);
-		sl.d_cand = reinterpret_cast<Candidate*>(cbuf + 4 * sizeof(int));
+		sl.d_cand = reinterpret_cast<Candidate*>(cbuf + FDB_NCOUNTERS * sizeof(int));
 		/* deep queue: room for 1/16 of the windows of a chunk (beyond that the detector leaves the fast path) */
 		sl.deep.count = sl.d_counters + 1;
 		sl.deep.next = sl.d_counters + 2;
+		sl.deep.count2 = sl.d_counters + 4;
+		sl.deep.next2 = sl.d_counters + 5;
 		sl.deep.cap = (int)std::max<int64_t>(1024, std::min<int64_t>(plan.windows * det->chunk / 16 + 1024, (int64_t)1 << 24));
 		s = dev_alloc(&sl.deep.rec, (size_t)sl.deep.cap, det->owned); if (s) return s;
+		s = dev_alloc(&sl.deep.order2, (size_t)sl.deep.cap, det->owned); if (s) return s;
 		s = dev_alloc(&sl.deep.patch, (size_t)sl.deep.cap * (size_t)(det->wvm ? det->wvm->dev.nwords : 1), det->owned); if (s) return s;
 		s = dev_alloc(&sl.d_items, (size_t)det->items_cap, det->owned); if (s) return s;
 		s = dev_alloc(&sl.d_dist, (size_t)det->items_cap, det->owned); if (s) return s;
@@ -914,7 +917,7 @@ int fdb_detector_prepare(fdb_detector* det, int32_t width, int32_t height, int32
 			sl.d_feat = fb;
 		}
 		uint8_t* hbuf = nullptr;
-		s = host_alloc(&hbuf, 4 * sizeof(int) + OPT_CAND * sizeof(Candidate), det->owned_host); if (s) return s;
+		s = host_alloc(&hbuf, FDB_NCOUNTERS * sizeof(int) + OPT_CAND * sizeof(Candidate), det->owned_host); if (s) return s;
 		sl.h_counters = reinterpret_cast<int*>(hbuf);
 		s = host_alloc(&sl.h_cand_big, (size_t)det->cand_cap, det->owned_host); if (s) return s;
 		s = host_alloc(&sl.h_items, (size_t)det->items_cap, det->owned_host); if (s) return s;

@@ -17,6 +17,7 @@
 #include "wvm_group.h"
 
 #define PIPE_SLOTS 3
+#define FDB_NCOUNTERS 8 /* per-slot device counters: [0] candidates, [1] deep queue, [2] deep cursor, [3] group-kernel cursor, [4] second deep queue, [5] its cursor */
 #define OPT_CAND 4096 /* candidates fetched together with the counters (one D2H); more need a second copy */
 #define FEAT_BATCH 8192 /* feature vectors materialised at a time (feature-space SVM stage) */
 
@@ -32,14 +33,14 @@ struct Slot {
 	int64_t arena_stride = 0;
 	CUtensorMap* d_tmaps = nullptr; /* one TMA descriptor per pyramid layer of this slot's arena (strip kernel) */
 	fdb_window_score* d_dense = nullptr;
-	int* d_counters = nullptr;     /* [0] candidates, [1] deep queue, [2] deep cursor; followed by the candidate list */
-	Candidate* d_cand = nullptr;   /* = (Candidate*)(d_counters + 4) */
+	int* d_counters = nullptr;     /* FDB_NCOUNTERS counters (see above), followed by the candidate list */
+	Candidate* d_cand = nullptr;   /* = (Candidate*)(d_counters + FDB_NCOUNTERS) */
 	DeepQueue deep{};
 	SvmItem* d_items = nullptr;
 	double* d_dist = nullptr;
 	uint8_t* d_farena = nullptr;   /* filtered pyramid layers of the chunk (feature spaces with layer filters) */
 	void* d_feat = nullptr;        /* FEAT_BATCH feature vectors */
-	int* h_counters = nullptr;     /* pinned mirror: 4 ints + OPT_CAND candidates */
+	int* h_counters = nullptr;     /* pinned mirror: the counters + OPT_CAND candidates */
 	Candidate* h_cand_big = nullptr; /* pinned, cand_cap entries (second copy when > OPT_CAND) */
 	SvmItem* h_items = nullptr;
 	double* h_dist = nullptr;

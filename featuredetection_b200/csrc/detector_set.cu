@@ -222,7 +222,7 @@ int set_enqueue(fdb_detector_set* s, int si, fdb_window_score* const* dense_dev,
 	cudaStream_t st = ss.st;
 	const int nd = (int)s->dets.size();
 	if (!s->launches.empty()) CUDA_TRY(cudaMemsetAsync(ss.d_cursors, 0, sizeof(int) * s->launches.size(), st));
-	for (int d = 0; d < nd; ++d) if (s->fast[(size_t)d]) CUDA_TRY(cudaMemsetAsync(s->dets[(size_t)d]->slots[si].d_counters, 0, 4 * sizeof(int), st));
+	for (int d = 0; d < nd; ++d) if (s->fast[(size_t)d]) CUDA_TRY(cudaMemsetAsync(s->dets[(size_t)d]->slots[si].d_counters, 0, FDB_NCOUNTERS * sizeof(int), st));
 	if (marks) CUDA_TRY(cudaEventRecord(marks[0], st));
 	{ const int r = enqueue_pyramid(c, st, s->jobs, ss.frames_dev, s->W, s->H, ss.n, ss.d_arena, s->arena_bytes, marks ? marks[1] : nullptr); if (r) return r; }
 	if (marks) CUDA_TRY(cudaEventRecord(marks[2], st));
@@ -338,7 +338,7 @@ int set_pipeline(fdb_detector_set* s, const uint8_t* frames, bool frames_on_devi
 		for (int d = 0; d < nd; ++d) {
 			if (!s->fast[(size_t)d]) continue;
 			Slot& msl = s->dets[(size_t)d]->slots[si];
-			CUDA_TRY(cudaMemcpyAsync(msl.h_counters, msl.d_counters, 4 * sizeof(int) + OPT_CAND * sizeof(Candidate), cudaMemcpyDeviceToHost, ss.st));
+			CUDA_TRY(cudaMemcpyAsync(msl.h_counters, msl.d_counters, FDB_NCOUNTERS * sizeof(int) + OPT_CAND * sizeof(Candidate), cudaMemcpyDeviceToHost, ss.st));
 			CUDA_TRY(cudaEventRecord(msl.ev_stage1, ss.st));
 		}
 		++enq;

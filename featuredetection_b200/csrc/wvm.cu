@@ -48,36 +48,41 @@ __device__ __forceinline__ float wvm_level(const DevWvm& m, int level, const X& 
 		float* un, float* hk, int static_level) {
 	const int nv = m.cntval[level] - 1;
 	const uint32_t* __restrict__ mk = m.masks + m.mask_off[level];
-	uint32_t acc[FDB_MAX_VALUES];
-#pragma unroll
-	for (int v = 0; v < FDB_MAX_VALUES; ++v) acc[v] = 0;
-	if (nv == 4) { /* common case: one 16-byte load brings the four masks of a word */
-		const uint4* __restrict__ mk4 = reinterpret_cast<const uint4*>(mk);
-#pragma unroll 4
-		for (int j = 0; j < m.nwords; ++j) {
-			const uint32_t xw = xs[j];
-			const uint4 k = __ldg(mk4 + j);
-			acc[0] = __dp4a(xw, k.x, acc[0]); acc[1] = __dp4a(xw, k.y, acc[1]);
-			acc[2] = __dp4a(xw, k.z, acc[2]); acc[3] = __dp4a(xw, k.w, acc[3]);
-		}
-	} else {
-		for (int j = 0; j < m.nwords; ++j) {
-			const uint32_t xw = xs[j];
-#pragma unroll
-			for (int v = 0; v < FDB_MAX_VALUES; ++v)
-				if (v < nv) acc[v] = __dp4a(xw, __ldg(mk + j * nv + v), acc[v]);
-		}
-	}
 	const double* __restrict__ val = m.val + m.val_off[level];
 	float sumv0 = total_f;
 	double sum_xp = 0.0;
+	/* any number of grey values per filter (WvmClassifier.hpp:107-124 sets no limit): FDB_MAX_VALUES at a time, each group one
+	 * pass over the patch words, folded into sumv0 / sum_xp in the reference's order v = 1, 2, ... (:277-309) */
+	for (int v0 = 0; v0 < nv; v0 += FDB_MAX_VALUES) {
+		const int nvc = min(FDB_MAX_VALUES, nv - v0);
+		uint32_t acc[FDB_MAX_VALUES];
 #pragma unroll
-	for (int v = 0; v < FDB_MAX_VALUES; ++v)
-		if (v < nv) {
-			const float sumv = (float)acc[v];                                 /* exact: < 2^24 */
-			sumv0 = __fsub_rn(sumv0, sumv);                                   /* :308 */
-			sum_xp = __dadd_rn(sum_xp, __dmul_rn((double)sumv, __ldg(val + v + 1))); /* :309 */
+		for (int v = 0; v < FDB_MAX_VALUES; ++v) acc[v] = 0;
+		if (nv == 4) { /* common case: one 16-byte load brings the four masks of a word */
+			const uint4* __restrict__ mk4 = reinterpret_cast<const uint4*>(mk);
+#pragma unroll 4
+			for (int j = 0; j < m.nwords; ++j) {
+				const uint32_t xw = xs[j];
+				const uint4 k = __ldg(mk4 + j);
+				acc[0] = __dp4a(xw, k.x, acc[0]); acc[1] = __dp4a(xw, k.y, acc[1]);
+				acc[2] = __dp4a(xw, k.z, acc[2]); acc[3] = __dp4a(xw, k.w, acc[3]);
+			}
+		} else {
+			for (int j = 0; j < m.nwords; ++j) {
+				const uint32_t xw = xs[j];
+#pragma unroll
+				for (int v = 0; v < FDB_MAX_VALUES; ++v)
+					if (v < nvc) acc[v] = __dp4a(xw, __ldg(mk + j * nv + v0 + v), acc[v]);
+			}
 		}
+#pragma unroll
+		for (int v = 0; v < FDB_MAX_VALUES; ++v)
+			if (v < nvc) {
+				const float sumv = (float)acc[v];                                 /* exact: < 2^24 */
+				sumv0 = __fsub_rn(sumv0, sumv);                                   /* :308 */
+				sum_xp = __dadd_rn(sum_xp, __dmul_rn((double)sumv, __ldg(val + v0 + v + 1))); /* :309 */
+			}
+	}
 	sum_xp = __dadd_rn(sum_xp, __dmul_rn((double)sumv0, __ldg(val)));         /* :312 */
 	sum_xp = __dadd_rn(sum_xp, (double)*un);                                  /* :313 */
 	*un = (float)sum_xp;                                                      /* :314 */

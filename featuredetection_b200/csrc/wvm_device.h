@@ -33,7 +33,10 @@ struct DeepQueue {
 	int* next;         /* work-distribution cursor of wvm_deep_warp_kernel */
 	int cap;
 	DeepRec* rec;      /* [cap]; nullptr disables the queue */
-	uint32_t* patch;   /* [nwords][cap] equalised patch words */
+	uint32_t* patch;   /* [nwords][cap] equalised patch words (generic kernels only) */
+	int* count2;       /* group path: windows that passed the deep kernel's first round of 32 filters ... */
+	int* next2;        /* ... and the work cursor of the batched kernel that finishes them */
+	int* order2;       /* [cap] their slots in rec */
 };
 
 /* WvmClassifier state in evaluator form; all pointers are device memory */

@@ -19,13 +19,14 @@ namespace fdb {
 /* acc[v] = exact integer sum over the rectangles of grey value v+1 (v < nv).
  * *un is u_kernel_eval[level % per_level] (read, then overwritten, :313-314).
  * Returns hk_kernel_eval[level] (:333). */
+template <int MAXV>
 __device__ __forceinline__ float wvm_kernel_value(const DevWvm& m, int level, const uint32_t* acc, int nv,
 		float total_f, float sum_xx, float* un) {
 	const double* __restrict__ val = m.val + __ldg(m.val_off + level);
 	float sumv0 = total_f;
 	double sum_xp = 0.0;
 #pragma unroll
-	for (int v = 0; v < FDB_MAX_VALUES; ++v)
+	for (int v = 0; v < MAXV; ++v)
 		if (v < nv) {
 			const float sumv = (float)acc[v];                                        /* exact: < 2^24 */
 			sumv0 = __fsub_rn(sumv0, sumv);                                          /* :308 */
@@ -42,11 +43,8 @@ __device__ __forceinline__ float wvm_kernel_value(const DevWvm& m, int level, co
 /* same with only four grey values and the sums passed by value (register friendly) */
 __device__ __forceinline__ float wvm_kernel_value4(const DevWvm& m, int level, uint32_t a0, uint32_t a1, uint32_t a2,
 		uint32_t a3, int nv, float total_f, float sum_xx, float* un) {
-	uint32_t acc[FDB_MAX_VALUES];
-#pragma unroll
-	for (int v = 0; v < FDB_MAX_VALUES; ++v) acc[v] = 0;
-	acc[0] = a0; acc[1] = a1; acc[2] = a2; acc[3] = a3;
-	return wvm_kernel_value(m, level, acc, nv, total_f, sum_xx, un);
+	const uint32_t acc[4] = {a0, a1, a2, a3};
+	return wvm_kernel_value<4>(m, level, acc, nv, total_f, sum_xx, un);
 }
 
 /* WvmClassifier::classify(pair) (WvmClassifier.cpp:91-98) + candidate append */

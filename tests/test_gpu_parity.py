@@ -278,6 +278,7 @@ def test_window_steps_generic_path(ctx, face_models, steps):
         assert np.array_equal(dense[k]["level"], ref["dense"]["level"])
         assert np.max(np.abs(dense[k]["fout"] - ref["dense"]["fout"])) <= TOL
         assert list(dets[dets["frame"] == k]["window"]) == list(ref["detections"]["window"])
+        assert len(np.unique(ref["dense"]["level"])) >= 4 and len(ref["detections"]) > 0
 
 
 def test_pitch_partial_batches_and_empty(ctx, face_models):
@@ -401,3 +402,34 @@ def test_bgr_frames(ctx, face_models):
     d2, dense2 = casc.detect(conv, want_dense=True)
     assert np.array_equal(dense1["level"], dense2["level"]) and np.array_equal(dense1["fout"], dense2["fout"])
     assert np.array_equal(d1["window"], d2["window"]) and np.array_equal(d1["svm_distance"], d2["svm_distance"])
+
+
+@pytest.mark.parametrize("cntval", [2, 7, 12])
+def test_any_number_of_grey_values_per_filter(ctx, cntval):
+    """WvmClassifier::Area holds any number of grey values per filter (WvmClassifier.hpp:107-124); the synthetic benchmark
+    models use 5. 2 (one rectangle value: the tensor-core strip path), 7 and 12 (more than the 4 columns per filter of the strip
+    path: the generic kernels, 8 values per pass) against the oracle: dense records and stage-1 positives."""
+    fo = _oracle()
+    frame = syn.synthetic_frame(17)
+    wvm = syn.make_wvm(20, 20, 6, 4, 0.04, seed=700 + cntval, cntval=cntval, rects_per_value=2 if cntval > 5 else 4)
+    kw = dict(incremental_scale_factor=float(np.float32(0.92)), min_scale_factor=float(np.float32(0.05)),
+              max_scale_factor=float(np.float32(0.16)), patch_width=20, patch_height=20, step_x=1, step_y=1,
+              max_positives_per_frame=400000)
+    # thresholds at the 35 % quantile of every third filter's output over the windows of another frame: exits at many levels
+    probe = fo.detect_frame({k: v for k, v in kw.items() if k != "max_positives_per_frame"}, fo.Wvm(wvm), None, syn.synthetic_frame(16),
+                            stage=capi.FDB_STAGE_WVM, want_patches=True, det_cap=400000)
+    per_level = fo.Wvm(wvm).eval_all_levels(probe["patches"][::7])
+    thr = np.full(24, -np.inf, np.float32)
+    thr[1::3] = np.quantile(per_level[:, 1::3], 0.35, axis=0).astype(np.float32)
+    wvm = wvm.with_thresholds(thr)
+    casc = SlidingWindowCascade(ctx, kw, wvm, None)
+    casc.prepare(640, 480, 2)
+    frames = np.stack([frame, syn.synthetic_frame(18)])
+    dets, dense = casc.detect(frames, stage=capi.FDB_STAGE_WVM, want_dense=True, det_cap=400000)
+    okw = {k: v for k, v in kw.items() if k != "max_positives_per_frame"}
+    for k in range(2):
+        ref = fo.detect_frame(okw, fo.Wvm(wvm), None, frames[k], stage=capi.FDB_STAGE_WVM, det_cap=400000, frame_index=k)
+        assert np.array_equal(dense[k]["level"], ref["dense"]["level"])
+        assert np.max(np.abs(dense[k]["fout"] - ref["dense"]["fout"])) <= TOL
+        assert list(dets[dets["frame"] == k]["window"]) == list(ref["detections"]["window"])
+        assert len(np.unique(ref["dense"]["level"])) >= 4 and len(ref["detections"]) > 0
