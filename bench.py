@@ -911,6 +911,155 @@ def run_aggdet(args, rank, world, local_rank):
         dist.barrier(); dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------------
+# `single` detector in a feature space (ffpDetectApp.cpp:445-454 -> FilteringPyramidFeatureExtractor: the patch filter chain runs
+# on EVERY window, then the psvm): --workload single-whi / single-hog (BASELINE configs[2] names WHI features)
+# ------------------------------------------------------------------------------------------------
+def _single_feature_models(feature):
+    from featuredetection_b200 import synthetic as syn
+    from oracle import fdoracle as fo
+    det_kw, wvm, _ = syn.landmark_models(CFG)
+    feat = fo.Features(syn.feature_desc(kind=feature), det_kw["patch_width"], det_kw["patch_height"])
+    r = fo.detect_frame(det_kw, fo.Wvm(wvm), None, syn.synthetic_frame(0), stage=1, want_dense=False)
+    svm = feature_svm_model(syn, feature, det_kw, r["layers"], lambda fr, lxy: feat.extract(det_kw, fr, lxy))
+    return det_kw, svm, feat
+
+
+def _single_feature_cpu_init(feature):
+    from oracle import fdoracle as fo
+    fo.build()
+    det_kw, svm, feat = _single_feature_models(feature)
+    _worker_state.update(fo=fo, kw=det_kw, svm=fo.Svm(svm), feat=feat)
+
+
+def _single_feature_cpu_item(crop):
+    st = _worker_state
+    t0 = time.perf_counter()
+    r = st["fo"].detect_frame(st["kw"], None, st["svm"], crop, want_dense=False, svm_features=st["feat"])
+    return r["windows"], time.perf_counter() - t0
+
+
+def _single_feature_cpu(feature, steps, frames_per_core=1):
+    """bounded sample: the top-left 320x240 quarter of frames (all pyramid layers of the quarter, every window classified)"""
+    from featuredetection_b200 import synthetic as syn
+    cores = os.cpu_count() or 1
+    pool = mp.get_context("spawn").Pool(cores, initializer=_single_feature_cpu_init, initargs=(feature,))
+    crops = [np.ascontiguousarray(syn.synthetic_frame(100 + k)[:240, :320]) for k in range(cores * frames_per_core)]
+    pool.map(_single_feature_cpu_item, crops[:cores])
+    tot_w, tot_t = 0, 0.0
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        res = pool.map(_single_feature_cpu_item, crops, chunksize=1)
+        tot_t += time.perf_counter() - t0
+        tot_w += sum(r[0] for r in res)
+    pool.close(); pool.join()
+    return tot_w, tot_t, cores, "%d quarter frames (320x240) per step over %d processes, every window through the %s chain + the SVM" % (
+        len(crops), cores, feature.upper())
+
+
+def run_single_feature(args, rank, world, local_rank):
+    from featuredetection_b200 import synthetic as syn
+    feature = args.workload.split("-")[1]
+    n = args.frames
+    cfg = {"workload": "ffpDetectApp `single` detector in a feature space (ffpDetectApp.cpp:445-454; BASELINE configs[2] names WHI): %d-frame batch per GPU, "
+                       "640x480 1-channel, FaceFrontal geometry, the %s patch-filter chain on EVERY window (16 185 per frame), then the RBF-SVM "
+                       "(1024 float32 support vectors)" % (n, feature.upper()),
+           "frames_per_gpu": n, "global_frames": n * world, "windows_per_frame": 16185, "parallelism": "frame-sharded dp%d" % world,
+           "l2": "a 256 MB scratch write flushes L2 between timed steps"}
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        w_, t_, cores, sample = _single_feature_cpu(feature, args.steps)
+        value = w_ / t_
+        emit({"impl": "reference", "metric": "classified_patches_per_s", "value": value, "unit": "patches/s", "n_gpus": args.gpus, "steps": args.steps,
+              "warmup": args.warmup, "ms_per_step": 1e3 * t_ / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+              "dtype": "u8/f32/f64", "data": "synthetic", "config": cfg,
+              "cpu_baseline": {"value": value, "unit": "patches/s", "cores": cores, "kind": "port", "sample": sample},
+              "e2e": {"value": value, "unit": "patches/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+        return
+    import torch
+    import torch.distributed as dist
+    from featuredetection_b200.detector import Context, SlidingWindowCascade
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - the B200 path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        dist.init_process_group("nccl", device_id=device)
+    ctx = Context(local_rank)
+    det_kw, wvm, _ = syn.landmark_models(CFG)
+    fdesc = syn.feature_desc(kind=feature)
+    probe = SlidingWindowCascade(ctx, det_kw, wvm, None, feature=fdesc)
+    probe.prepare(W, H, 1)
+    svm = feature_svm_model(syn, feature, det_kw, probe.layers(), probe.extract_features)
+    del probe
+    single = SlidingWindowCascade(ctx, det_kw, None, svm, feature=fdesc)
+    single.prepare(W, H, 1)
+    _, d0 = single.detect_single(syn.synthetic_frames(0, 1))
+    svm.threshold = float(np.float32(np.quantile(d0, 0.999)))   # ~0.1 % of the windows positive
+    del single
+    casc = SlidingWindowCascade(ctx, det_kw, None, svm, feature=fdesc)
+    casc.prepare(W, H, n)
+    wpf = casc.windows_per_frame
+    base = syn.synthetic_frames((rank * n) % 97, min(8, n))
+    host_frames = torch.from_numpy(np.concatenate([base] * ((n + len(base) - 1) // len(base)))[:n]).pin_memory()
+    dev_frames = host_frames.to(device)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(); ctx.synchronize()
+
+    def timed(fn):
+        for _ in range(args.warmup):
+            fn()
+        barrier()
+        l0 = ctx.launch_count()
+        ms, out = [], None
+        for _ in range(args.steps):
+            flush.fill_(1); torch.cuda.synchronize()
+            ctx.timer_start()
+            out = fn()
+            ms.append(ctx.timer_stop())
+        barrier()
+        tot = torch.tensor([sum(ms)], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(tot, op=dist.ReduceOp.MAX)
+        return float(tot.item()), out, ctx.launch_count() - l0
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    tot, out, launches = timed(lambda: casc.detect_single_device(dev_frames.data_ptr(), n, None, det_cap=64 * n))
+    e2e_tot, out_e2e, _ = timed(lambda: casc.detect_single(host_frames.numpy(), want_distances=False, det_cap=64 * n)[0])
+    clocks = sampler.stop() if rank == 0 else None
+    if rank == 0:
+        value = wpf * n * world * args.steps / (tot * 1e-3)
+        e2e = wpf * n * world * args.steps / (e2e_tot * 1e-3)
+        peak, peak_src = hbm_peak()
+        algo = (W * H + 8 * wpf) * n
+        cpu = None
+        if not args.no_cpu_baseline and world == 1:
+            w_, t_, cores, sample = _single_feature_cpu(feature, 1)
+            cpu = {"value": w_ / t_, "unit": "patches/s", "cores": cores, "kind": "port", "sample": sample}
+        emit({"metric": "classified_patches_per_s", "value": value, "unit": "patches/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+              "ms_per_step": tot / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/f32/f64", "data": "synthetic",
+              "config": cfg, "frames_per_s": value / wpf, "clocks": clocks,
+              "e2e": {"value": e2e, "unit": "patches/s", "h2d_bytes_per_step": int(W * H * n), "d2h_bytes_per_step": int(len(out_e2e) * 96 + 8),
+                      "ms_per_step": e2e_tot / args.steps},
+              "gpu_launches": int(launches),
+              "roofline": {"bound": "hbm", "kernel": "feature_patch_kernel + svm_kernel (whole step: the patch-filter chain and the SVM on every window)",
+                           "achieved": algo / (tot / args.steps * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                           "frac": algo / (tot / args.steps * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                           "algorithmic_bytes_per_step": int(algo),
+                           "note": "compute bound by construction: the exact float32 sequential SSD against 1024 support vectors is ~8e5 scalar operations per window"},
+              "detections_per_step": int(len(out)) * world, "cpu_baseline": cpu})
+    if world > 1:
+        dist.barrier(); dist.destroy_process_group()
+
+
 def pin_rank_to_cores(local_rank, world):
     """each rank's host threads (pipeline thread, CUDA driver threads) stay on their own share of the host cores"""
     try:
@@ -1057,7 +1206,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--frames", type=int, default=None, help="frames per GPU per step (default 256; 4096 faces for sdm)")
     ap.add_argument("--frames-total", type=int, default=None, help="strong scaling: this many frames per step split over the ranks (BASELINE configs[3]: 4096)")
-    ap.add_argument("--workload", default="landmarks15", choices=["landmarks15", "facefrontal", "sdm", "single-psvm", "aggdet"],
+    ap.add_argument("--workload", default="landmarks15", choices=["landmarks15", "facefrontal", "sdm", "single-psvm", "aggdet", "single-whi", "single-hog"],
                     help="landmarks15 (default, headline) = all 15 ffpDetectApp landmark detectors on every frame (BASELINE north_star / configs[3]); "
                          "facefrontal = BASELINE configs[1]; sdm = BASELINE configs[4] (supervised-descent fit, 68 landmarks, 4096 faces per GPU); "
                          "single-psvm = the `single` detector, every window through the RBF-SVM")
@@ -1078,7 +1227,7 @@ def main():
     if args.frames_total:
         args.frames = max(1, args.frames_total // world)
     if args.frames is None:
-        args.frames = {"facefrontal": 256, "landmarks15": 256, "sdm": 4096, "single-psvm": 256, "aggdet": 64}[args.workload]
+        args.frames = {"facefrontal": 256, "landmarks15": 256, "sdm": 4096, "single-psvm": 256, "aggdet": 64, "single-whi": 8, "single-hog": 8}[args.workload]
     if args.feature is None:
         args.feature = "hog" if args.workload == "facefrontal" else "hq64"
     if args.workload == "landmarks15" and args.feature != "hq64":
@@ -1096,6 +1245,9 @@ def main():
         return
     if args.workload == "aggdet":
         run_aggdet(args, rank, world, local_rank)
+        return
+    if args.workload in ("single-whi", "single-hog"):
+        run_single_feature(args, rank, world, local_rank)
         return
     if args.workload == "sdm":
         if args.impl == "reference":

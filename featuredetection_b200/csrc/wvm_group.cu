@@ -36,6 +36,7 @@
 #include <cuda_runtime.h>
 #include <algorithm>
 #include <cstdint>
+#include <cstdlib>
 
 #include "fdb_internal.h"
 #include "wvm_device.h"
@@ -696,7 +697,8 @@ void launch_wvm_deep_group(cudaStream_t st, const DeepArgs& args) {
 	}
 	const int hk_stride = (max_used + 4 + 3) / 4 * 4 + 4; /* + 4: rows of neighbouring windows start in different banks */
 	const size_t dyn = (size_t)GDEEP_WARPS * GDEEP_W * hk_stride * sizeof(float);
-	const bool batched = queues && max_used > WVM_KA + 32 && dyn <= 150 * 1024;
+	static const bool enabled = [] { const char* e = std::getenv("FDB_DEEP_BATCH"); return !(e && e[0] == '0'); }(); /* debugging: one kernel for the whole tail */
+	const bool batched = enabled && queues && max_used > WVM_KA + 32 && dyn <= 150 * 1024;
 	dim3 grid((unsigned)(grp_sm_count() * 8 / std::max(1, std::min(args.n_models, 8))), (unsigned)args.n_models);
 	wvm_deep_group_kernel<<<grid, GDEEP_WARPS * 32, 0, st>>>(args, batched ? 0 : 1);
 	if (batched) {
