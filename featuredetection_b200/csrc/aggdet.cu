@@ -74,7 +74,7 @@ struct AggParams {
 
 struct AggCandidate { int frame, layer, x, y; float score; };
 
-struct PixEntry { uint8_t i1, i2; uint16_t valid; float w1, w2; };
+typedef FhogPix PixEntry; /* fhog_core.h */
 
 __global__ void __launch_bounds__(128) aggdet_hist_kernel(const AggParams P, const AggLayer* __restrict__ layers, const int* __restrict__ tile_layer,
 		const FhogLutEntry* __restrict__ lut, const uint8_t* __restrict__ frames, int W, int H, const uint8_t* __restrict__ arena,
@@ -115,35 +115,7 @@ __global__ void __launch_bounds__(128) aggdet_hist_kernel(const AggParams P, con
 		const int cr = cr0 + lr, cc = cc0 + lc;
 		if (cr < L.crow && cc < L.ccol) {
 			float* const h = s_hist + threadIdx.x * P.hstride;
-			int r_lo = cr * cell - halo, r_hi = cr * cell + cell + halo, c_lo = cc * cell - halo, c_hi = cc * cell + cell + halo;
-			r_lo = max(r_lo, 0); c_lo = max(c_lo, 0); r_hi = min(r_hi, rows_used); c_hi = min(c_hi, cols_used);
-			for (int r = r_lo; r < r_hi; ++r) {
-				const FhogCoef R = fhog_pixel_coef(r, cell, L.crow, P.interp_cells);
-				const bool hit1 = R.index1 == cr, hit2 = P.interp_cells && R.index2 == cr;
-				if (!hit1 && !hit2) continue;
-				const PixEntry* const row = s_px + (r - pr0) * region - pc0;
-				for (int c = c_lo; c < c_hi; ++c) {
-					const FhogCoef Cc = fhog_pixel_coef(c, cell, L.ccol, P.interp_cells);
-					const bool chit1 = Cc.index1 == cc, chit2 = P.interp_cells && Cc.index2 == cc;
-					if (!chit1 && !chit2) continue;
-					const PixEntry e = row[c];
-#pragma unroll
-					for (int k = 0; k < 2; ++k) {
-						if (k == 1 && !P.interp_bins) break;
-						const int bin = k == 0 ? e.i1 : e.i2;
-						const float bw = k == 0 ? e.w1 : e.w2;
-						float acc = h[bin];
-						if (!P.interp_cells) acc = FHOG_ADD(acc, bw);
-						else { /* statement order of the reference for one pixel: (row1, col1), (row1, col2), (row2, col1), (row2, col2) */
-							if (hit1 && chit1) acc = FHOG_ADD(acc, FHOG_MUL(FHOG_MUL(bw, R.weight1), Cc.weight1));
-							if (hit1 && chit2) acc = FHOG_ADD(acc, FHOG_MUL(FHOG_MUL(bw, R.weight1), Cc.weight2));
-							if (hit2 && chit1) acc = FHOG_ADD(acc, FHOG_MUL(FHOG_MUL(bw, R.weight2), Cc.weight1));
-							if (hit2 && chit2) acc = FHOG_ADD(acc, FHOG_MUL(FHOG_MUL(bw, R.weight2), Cc.weight2));
-						}
-						h[bin] = acc;
-					}
-				}
-			}
+			fhog_cell_histogram(s_px, pr0, pc0, region, cell, L.crow, L.ccol, P.interp_bins, P.interp_cells, cr, cc, h);
 			const int64_t cellidx = (int64_t)cr * L.ccol + cc;
 			float* const out = hist + (int64_t)frame * hist_stride + L.hist_off + cellidx * sb;
 			for (int b = 0; b < sb; ++b) out[b] = h[b];

@@ -255,7 +255,7 @@ void fill_detection(fdb_detection* d, const Plan& plan, const fdb_detector_desc&
 
 /* stage-1 results -> counters + candidates on their way to the host (async) */
 int enqueue_fetch(fdb_detector* det, Slot& sl, cudaStream_t st) {
-	CUDA_TRY(cudaMemcpyAsync(sl.h_counters, sl.d_counters, FDB_NCOUNTERS * sizeof(int) + OPT_CAND * sizeof(Candidate), cudaMemcpyDeviceToHost, st));
+	CUDA_TRY(cudaMemcpyAsync(sl.h_counters, sl.d_counters, FDB_NCOUNTERS * sizeof(int) + (size_t)det->opt_cand * sizeof(Candidate), cudaMemcpyDeviceToHost, st));
 	CUDA_TRY(cudaEventRecord(sl.ev_stage1, st));
 	return FDB_OK;
 }
@@ -304,7 +304,7 @@ int phase_a_fetch(fdb_detector* det, Slot& sl, cudaStream_t st, const DevLayer* 
 	if (ncand > det->cand_cap)
 		return fail(FDB_ERR_OVERFLOW, "stage-1 candidate list overflow: raise max_positives_per_frame");
 	sl.cand_src = reinterpret_cast<const Candidate*>(sl.h_counters + FDB_NCOUNTERS);
-	if (ncand > OPT_CAND) {
+	if (ncand > det->opt_cand) {
 		/* the list is complete (stage 1 finished): fetch it on the copy stream - `st` may already hold other work of this chunk
 		 * (a detector set queues its members' SVM kernels there) and the host must not wait for that */
 		cudaStream_t cs = sl.st_copy ? sl.st_copy : st;
@@ -883,6 +883,9 @@ int fdb_detector_prepare(fdb_detector* det, int32_t width, int32_t height, int32
 	det->n_slots = std::min(PIPE_SLOTS, (max_batch + det->chunk - 1) / det->chunk);
 	const int64_t cap64 = (int64_t)det->desc.max_positives_per_frame * det->chunk;
 	det->cand_cap = (int)std::max<int64_t>(OPT_CAND, std::min<int64_t>(cap64, (int64_t)1 << 26));
+	/* a late copy of a long list queues behind whatever kernels the device is running for the next chunk (measured: the host
+	 * then waits for them) - so the copy that travels in stream order right behind stage 1 takes up to 64 K candidates (1 MB) */
+	det->opt_cand = std::min(det->cand_cap, 65536);
 	det->items_cap = det->cand_cap;
 
 	s = build_pyramid_jobs(plan.images, plan.max_down, width, height, &det->jobs, det->owned); if (s) return s;
@@ -902,11 +905,8 @@ int fdb_detector_prepare(fdb_detector* det, int32_t width, int32_t height, int32
 		/* deep queue: room for 1/16 of the windows of a chunk (beyond that the detector leaves the fast path) */
 		sl.deep.count = sl.d_counters + 1;
 		sl.deep.next = sl.d_counters + 2;
-		sl.deep.count2 = sl.d_counters + 4;
-		sl.deep.next2 = sl.d_counters + 5;
 		sl.deep.cap = (int)std::max<int64_t>(1024, std::min<int64_t>(plan.windows * det->chunk / 16 + 1024, (int64_t)1 << 24));
 		s = dev_alloc(&sl.deep.rec, (size_t)sl.deep.cap, det->owned); if (s) return s;
-		s = dev_alloc(&sl.deep.order2, (size_t)sl.deep.cap, det->owned); if (s) return s;
 		s = dev_alloc(&sl.deep.patch, (size_t)sl.deep.cap * (size_t)(det->wvm ? det->wvm->dev.nwords : 1), det->owned); if (s) return s;
 		s = dev_alloc(&sl.d_items, (size_t)det->items_cap, det->owned); if (s) return s;
 		s = dev_alloc(&sl.d_dist, (size_t)det->items_cap, det->owned); if (s) return s;
@@ -917,7 +917,7 @@ int fdb_detector_prepare(fdb_detector* det, int32_t width, int32_t height, int32
 			sl.d_feat = fb;
 		}
 		uint8_t* hbuf = nullptr;
-		s = host_alloc(&hbuf, FDB_NCOUNTERS * sizeof(int) + OPT_CAND * sizeof(Candidate), det->owned_host); if (s) return s;
+		s = host_alloc(&hbuf, FDB_NCOUNTERS * sizeof(int) + (size_t)det->opt_cand * sizeof(Candidate), det->owned_host); if (s) return s;
 		sl.h_counters = reinterpret_cast<int*>(hbuf);
 		s = host_alloc(&sl.h_cand_big, (size_t)det->cand_cap, det->owned_host); if (s) return s;
 		s = host_alloc(&sl.h_items, (size_t)det->items_cap, det->owned_host); if (s) return s;

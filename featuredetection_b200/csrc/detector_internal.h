@@ -17,8 +17,8 @@
 #include "wvm_group.h"
 
 #define PIPE_SLOTS 3
-#define FDB_NCOUNTERS 8 /* per-slot device counters: [0] candidates, [1] deep queue, [2] deep cursor, [3] group-kernel cursor, [4] second deep queue, [5] its cursor */
-#define OPT_CAND 4096 /* candidates fetched together with the counters (one D2H); more need a second copy */
+#define FDB_NCOUNTERS 8 /* per-slot device counters: [0] candidates, [1] deep queue, [2] deep cursor, [3] group-kernel cursor */
+#define OPT_CAND 4096 /* smallest candidate list capacity; det->opt_cand (<= 65536) candidates are fetched together with the counters (one D2H in stream order), more need a second copy */
 #define FEAT_BATCH 8192 /* feature vectors materialised at a time (feature-space SVM stage) */
 
 namespace fdb {
@@ -76,6 +76,7 @@ struct fdb_detector {
 	int64_t bgr_cap_px = 0;
 	int max_batch = 0, chunk = 0, n_slots = 0;
 	int cand_cap = 0, items_cap = 0;
+	int opt_cand = OPT_CAND;          /* candidates copied with the counters */
 	std::vector<void*> owned, owned_host;
 	Slot slots[PIPE_SLOTS];
 	cudaEvent_t ev_begin = nullptr;

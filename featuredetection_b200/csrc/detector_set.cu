@@ -22,6 +22,7 @@
 #include <functional>
 #include <mutex>
 #include <thread>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <map>
@@ -155,7 +156,7 @@ struct fdb_detector_set {
 	std::vector<void*> owned, owned_host;
 	int64_t windows = 0;                /* per frame, all members */
 	HostPool* pool = nullptr;           /* host threads of the members' post-processing */
-	double host_ms[5] = {0, 0, 0, 0, 0}; /* last call, host wall clock: enqueue, phase A (overlap elimination, SVM launch), phase B, whole call, waiting for stage 1 */
+	double host_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0}; /* last call, host wall clock: enqueue, phase A (overlap elimination, SVM launch), phase B, whole call, waiting for stage 1 */
 };
 
 namespace {
@@ -273,22 +274,29 @@ int set_pipeline(fdb_detector_set* s, const uint8_t* frames, bool frames_on_devi
 		}
 		HostTimer timer(&s->host_ms[1]);
 		std::vector<int> members;
-		for (int d = 0; d < nd; ++d) {
-			if (!s->fast[(size_t)d]) continue;
-			fdb_detector* det = s->dets[(size_t)d];
-			Slot& msl = det->slots[si];
-			msl.n = ss.n; msl.base = ss.base; msl.frames_dev = ss.frames_dev;
-			msl.arena = ss.d_arena; msl.arena_stride = s->arena_bytes;
-			const int r = phase_a_fetch(det, msl, ss.st, s->d_layers[(size_t)d], 1);
-			if (r) return r;
-			members.push_back(d);
+		{
+			HostTimer t5(&s->host_ms[5]);
+			for (int d = 0; d < nd; ++d) {
+				if (!s->fast[(size_t)d]) continue;
+				fdb_detector* det = s->dets[(size_t)d];
+				Slot& msl = det->slots[si];
+				msl.n = ss.n; msl.base = ss.base; msl.frames_dev = ss.frames_dev;
+				msl.arena = ss.d_arena; msl.arena_stride = s->arena_bytes;
+				const int r = phase_a_fetch(det, msl, ss.st, s->d_layers[(size_t)d], 1);
+				if (r) return r;
+				members.push_back(d);
+			}
+			for (int d : members) { const int r = phase_a_fetch_wait(s->dets[(size_t)d]->slots[si], ss.st); if (r) return r; }
 		}
-		for (int d : members) { const int r = phase_a_fetch_wait(s->dets[(size_t)d]->slots[si], ss.st); if (r) return r; }
 		std::vector<int> status(members.size(), FDB_OK);
-		s->pool->run((int)members.size(), [&](int k) {
-			fdb_detector* det = s->dets[(size_t)members[(size_t)k]];
-			status[(size_t)k] = phase_a_host(det, det->slots[si], det->plan, stage);
-		});
+		{
+			HostTimer t6(&s->host_ms[6]);
+			s->pool->run((int)members.size(), [&](int k) {
+				fdb_detector* det = s->dets[(size_t)members[(size_t)k]];
+				status[(size_t)k] = phase_a_host(det, det->slots[si], det->plan, stage);
+			});
+		}
+		HostTimer t7(&s->host_ms[7]);
 		for (size_t k = 0; k < members.size(); ++k) {
 			if (status[k]) return fail(status[k], "SVM work list overflow");
 			fdb_detector* det = s->dets[(size_t)members[k]];
@@ -338,7 +346,7 @@ int set_pipeline(fdb_detector_set* s, const uint8_t* frames, bool frames_on_devi
 		for (int d = 0; d < nd; ++d) {
 			if (!s->fast[(size_t)d]) continue;
 			Slot& msl = s->dets[(size_t)d]->slots[si];
-			CUDA_TRY(cudaMemcpyAsync(msl.h_counters, msl.d_counters, FDB_NCOUNTERS * sizeof(int) + OPT_CAND * sizeof(Candidate), cudaMemcpyDeviceToHost, ss.st));
+			CUDA_TRY(cudaMemcpyAsync(msl.h_counters, msl.d_counters, FDB_NCOUNTERS * sizeof(int) + (size_t)s->dets[(size_t)d]->opt_cand * sizeof(Candidate), cudaMemcpyDeviceToHost, ss.st));
 			CUDA_TRY(cudaEventRecord(msl.ev_stage1, ss.st));
 		}
 		++enq;
@@ -364,7 +372,7 @@ int set_detect(fdb_detector_set* s, const uint8_t* frames, bool frames_on_device
 	if (!frames_on_device && pitch < s->W) return fail(FDB_ERR_INVALID_ARGUMENT, "pitch smaller than the frame width");
 	const int nd = (int)s->dets.size();
 	std::vector<std::vector<fdb_detection>> results((size_t)nd);
-	std::fill(s->host_ms, s->host_ms + 5, 0.0);
+	std::fill(s->host_ms, s->host_ms + 8, 0.0);
 	HostTimer whole(&s->host_ms[3]);
 	for (int attempt = 0; attempt < nd + 1; ++attempt) {
 		for (auto& v : results) v.clear();
@@ -376,6 +384,9 @@ int set_detect(fdb_detector_set* s, const uint8_t* frames, bool frames_on_device
 		for (int d = 0; d < nd; ++d) if (s->fast[(size_t)d] && !s->dets[(size_t)d]->use_strips) s->fast[(size_t)d] = 0;
 	}
 	if (r) return r;
+	if (std::getenv("FDB_SET_TRACE"))
+		std::fprintf(stderr, "fdb_detector_set: enqueue %.1f wait %.1f phaseA %.1f (fetch %.1f host %.1f on %d threads, launch %.1f) phaseB %.1f ms\n", s->host_ms[0],
+				s->host_ms[4], s->host_ms[1], s->host_ms[5], s->host_ms[6], s->pool ? s->pool->threads() : 1, s->host_ms[7], s->host_ms[2]);
 	/* members outside the group kernels: their own pipeline (own pyramid), same results */
 	for (int d = 0; d < nd; ++d) {
 		if (s->fast[(size_t)d]) continue;
@@ -538,7 +549,7 @@ int fdb_detector_set_info(fdb_detector_set* s, int32_t* n_images, int64_t* pyram
 	return FDB_OK;
 } FDB_API_CATCH
 
-int fdb_detector_set_last_host_ms(fdb_detector_set* s, double ms_out[5]) try {
+int fdb_detector_set_last_host_ms(fdb_detector_set* s, double ms_out[8]) try {
 	if (!s || !ms_out) return fail(FDB_ERR_INVALID_ARGUMENT, "null argument");
 	std::memcpy(ms_out, s->host_ms, sizeof(s->host_ms));
 	return FDB_OK;

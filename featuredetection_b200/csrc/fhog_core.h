@@ -4,9 +4,8 @@
  *   - fhog.cu wraps them into CUDA kernels (thread = (cell, bin) for the histograms, thread = cell for the descriptors);
  *   - tests/test_fhog_host_emulation.py compiles the same functions with g++ and checks them bit for bit against the
  *     oracle (which is pinned against the reference's own FhogFilter / FhogAggregationFilter sources).
- * STATUS: the kernels of fhog.cu have NOT run on a B200 yet (the round's GPU budget was spent before they existed): the
- * arithmetic below is verified on the host, the launch geometry is not. No product entry point depends on them except
- * fdb_fhog().
+ *   - aggdet.cu (the batched detector path) stages the per-pixel LUT entries of a tile once and replays them per cell
+ *     (fhog_cell_histogram): also emulated on the host by that test, tile by tile as the kernel does.
  *
  * Reference: FhogFilter.cpp:20-122, FhogFilter.hpp:112-208 (signed histograms), FhogAggregationFilter.cpp:43-150
  * (energies, normalisers, descriptor). float32 additions are not associative: a histogram bin of a cell receives its
@@ -122,6 +121,54 @@ FHOG_HD float fhog_signed_bin(const FhogLutEntry* lut, const uint8_t* image, int
 		}
 	}
 	return acc;
+}
+
+/* the LUT entry of a pixel in the compact form the batched kernel (aggdet.cu) keeps in shared memory */
+struct FhogPix {
+	uint8_t i1, i2;
+	uint16_t valid;
+	float w1, w2;
+};
+
+/* ALL signed bins of cell (cr, cc) in one walk over the pixels that feed the cell, in raster order - the same additions, per
+ * bin in the same order, as fhog_signed_bin() performs bin by bin (addToSignedHistograms, FhogFilter.hpp:170-207).
+ * entries: the FhogPix of pixel (r, c) at entries[(r - r0) * stride + (c - c0)] for every pixel the walk touches;
+ * h: 2 * unsigned_bins floats, zeroed by the caller. */
+FHOG_HD void fhog_cell_histogram(const FhogPix* entries, int r0, int c0, int stride, int cell, int crow, int ccol,
+		int interpolate_bins, int interpolate_cells, int cr, int cc, float* h) {
+	const int rows_used = crow * cell, cols_used = ccol * cell;
+	const int halo = interpolate_cells ? cell : 0;
+	int r_lo = cr * cell - halo, r_hi = cr * cell + cell + halo, c_lo = cc * cell - halo, c_hi = cc * cell + cell + halo;
+	if (r_lo < 0) r_lo = 0;
+	if (c_lo < 0) c_lo = 0;
+	if (r_hi > rows_used) r_hi = rows_used;
+	if (c_hi > cols_used) c_hi = cols_used;
+	for (int r = r_lo; r < r_hi; ++r) {
+		const FhogCoef R = fhog_pixel_coef(r, cell, crow, interpolate_cells);
+		const int hit1 = R.index1 == cr, hit2 = interpolate_cells && R.index2 == cr;
+		if (!hit1 && !hit2) continue;
+		const FhogPix* row = entries + (r - r0) * stride - c0;
+		for (int c = c_lo; c < c_hi; ++c) {
+			const FhogCoef Cc = fhog_pixel_coef(c, cell, ccol, interpolate_cells);
+			const int chit1 = Cc.index1 == cc, chit2 = interpolate_cells && Cc.index2 == cc;
+			if (!chit1 && !chit2) continue;
+			const FhogPix e = row[c];
+			for (int k = 0; k < 2; ++k) {
+				if (k == 1 && !interpolate_bins) break;
+				const int bin = k == 0 ? e.i1 : e.i2;
+				const float bw = k == 0 ? e.w1 : e.w2;
+				float acc = h[bin];
+				if (!interpolate_cells) acc = FHOG_ADD(acc, bw);
+				else { /* statement order of the reference for one pixel: (row1, col1), (row1, col2), (row2, col1), (row2, col2) */
+					if (hit1 && chit1) acc = FHOG_ADD(acc, FHOG_MUL(FHOG_MUL(bw, R.weight1), Cc.weight1));
+					if (hit1 && chit2) acc = FHOG_ADD(acc, FHOG_MUL(FHOG_MUL(bw, R.weight1), Cc.weight2));
+					if (hit2 && chit1) acc = FHOG_ADD(acc, FHOG_MUL(FHOG_MUL(bw, R.weight2), Cc.weight1));
+					if (hit2 && chit2) acc = FHOG_ADD(acc, FHOG_MUL(FHOG_MUL(bw, R.weight2), Cc.weight2));
+				}
+				h[bin] = acc;
+			}
+		}
+	}
 }
 
 /* FhogAggregationFilter::computeGradientEnergy (FhogAggregationFilter.cpp:60-68) of one cell's signed histogram */

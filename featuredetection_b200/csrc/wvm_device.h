@@ -34,9 +34,6 @@ struct DeepQueue {
 	int cap;
 	DeepRec* rec;      /* [cap]; nullptr disables the queue */
 	uint32_t* patch;   /* [nwords][cap] equalised patch words (generic kernels only) */
-	int* count2;       /* group path: windows that passed the deep kernel's first round of 32 filters ... */
-	int* next2;        /* ... and the work cursor of the batched kernel that finishes them */
-	int* order2;       /* [cap] their slots in rec */
 };
 
 /* WvmClassifier state in evaluator form; all pointers are device memory */

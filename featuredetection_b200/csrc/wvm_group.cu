@@ -353,21 +353,15 @@ __global__ void __launch_bounds__(GRP_WARPS * 32, MSUB == 1 ? 4 : 3) wvm_group_k
 }
 
 /* ---------------------------------------------------------------------------------------------
- * deep kernels: the rest of the cascade for the survivors of the window kernel, all models of the table per launch
- *   wvm_deep_group_kernel   one warp per queued window: the next 32 filters. About half of the queued windows are rejected
- *                           there; the others (all_rounds = 0) are handed to the batched kernel.
- *   wvm_deep_batch_kernel   a warp finishes GDEEP_W windows of one model together: with realistic thresholds a window that
- *                           passes ~40 filters runs (nearly) all of them, and the float weighted sums of filter l need the
- *                           l + 1 weights of its row - 193 KB per window for 280 filters, L2 bandwidth bound when every
- *                           window streams them on its own. Kernel values of all remaining filters are computed per window
- *                           first (they do not depend on the cascade's outcome), then the weights of each round of 32
- *                           filters are loaded ONCE per warp and applied to the GDEEP_W windows (GDEEP_W independent
- *                           chains per lane). Results equal the sequential cascade: the first rejecting filter wins.
+ * deep kernel: the rest of the cascade for the survivors of the window kernel, all models of the table in one launch.
+ * One warp per queued window, 32 filters per round (lane = filter). A variant that finished 8 windows per warp together to
+ * load every round's weights once (the float weighted sums need 193 KB of weights per window for 280 filters) measured
+ * SLOWER on the B200 (90 vs 61 ms per 256-frame step): the weights of the one model a CTA works on stay L1 resident, so the
+ * kernel is bound by its ~9 000 warp instructions per full-depth window, not by the weight stream.
  * ------------------------------------------------------------------------------------------- */
 #define GDEEP_WARPS 4
 #define GDEEP_IIMG 1024   /* (w + 1) * (h + 1) <= 1024 ints per warp (32 x 24 -> 825) */
 #define GDEEP_PX 768      /* w * h <= 768 */
-#define GDEEP_W 8         /* windows per warp of the batched kernel */
 
 /* HistEq64 of the window straight from the pyramid image (HistEq64Filter.cpp:32-125), then its integral image with a zero
  * first row and column: ii[(y+1)*pitch + x+1] = sum of x[0..y][0..x] (exact integers < 2^24) */
@@ -438,7 +432,7 @@ __device__ __forceinline__ void gdeep_kernel_values(const DevWvm& m, const DeepR
 	}
 }
 
-__global__ void __launch_bounds__(GDEEP_WARPS * 32) wvm_deep_group_kernel(const __grid_constant__ DeepArgs a, const int all_rounds) {
+__global__ void __launch_bounds__(GDEEP_WARPS * 32) wvm_deep_group_kernel(const __grid_constant__ DeepArgs a) {
 	__shared__ __align__(16) float s_hk[GDEEP_WARPS][FDB_MAX_FILTERS + 4];
 	__shared__ float s_u[GDEEP_WARPS][FDB_MAX_PER_LEVEL];
 	__shared__ int s_ii[GDEEP_WARPS][GDEEP_IIMG];
@@ -470,13 +464,7 @@ __global__ void __launch_bounds__(GDEEP_WARPS * 32) wvm_deep_group_kernel(const 
 		int final_level = -1;
 		float final_fout = 0.f;
 		int round = 0;
-		bool handed_over = false;
 		for (int base = WVM_KA; base < m.num_used && final_level < 0; base += 32, ++round) {
-			if (round == 1 && !all_rounds) { /* passed 32 more filters: the batched kernel finishes this window */
-				if (lane == 0) { const int k = atomicAdd(q.count2, 1); q.order2[k] = slot; }
-				handed_over = true;
-				break;
-			}
 			const int cnt = min(32, m.num_used - base);
 			const int level = base + lane;
 			const bool owner = lane < cnt;
@@ -522,115 +510,8 @@ __global__ void __launch_bounds__(GDEEP_WARPS * 32) wvm_deep_group_kernel(const 
 			}
 			__syncwarp();
 		}
-		if (lane == 0 && !handed_over)
+		if (lane == 0)
 			wvm_emit(m, rec.frame, rec.window, gm.windows_per_frame, final_level, final_fout, gm.dense, gm.cand, gm.cand_count, gm.cand_cap);
-		__syncwarp();
-	}
-}
-
-__global__ void __launch_bounds__(GDEEP_WARPS * 32) wvm_deep_batch_kernel(const __grid_constant__ DeepArgs a, const int hk_stride) {
-	extern __shared__ __align__(16) float s_dyn[];                 /* [GDEEP_WARPS][GDEEP_W][hk_stride] kernel values */
-	__shared__ float s_u[GDEEP_WARPS][FDB_MAX_PER_LEVEL];
-	__shared__ int s_ii[GDEEP_WARPS][GDEEP_IIMG];
-	__shared__ uint8_t s_px[GDEEP_WARPS][GDEEP_PX];
-	__shared__ uint32_t s_hist[GDEEP_WARPS][64];
-	__shared__ uint8_t s_lut[GDEEP_WARPS][64];
-	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	float* const hk_all = s_dyn + (size_t)warp * GDEEP_W * hk_stride;
-	float* const us = s_u[warp];
-	int* const ii = s_ii[warp];
-	const GroupModel& gm = a.models[blockIdx.y];
-	const DevWvm& m = gm.m;
-	const DeepQueue& q = gm.q;
-	const int n = min(*q.count2, q.cap);
-	const int pw = m.fsx, ph = m.fsy, pitch = pw + 1;
-	const float stretch = __fdiv_rn(255.0f, (float)(pw * ph));
-	for (;;) {
-		int first = 0;
-		if (lane == 0) first = atomicAdd(q.next2, GDEEP_W);
-		first = __shfl_sync(0xffffffffu, first, 0);
-		if (first >= n) break;
-		const int nw = min(GDEEP_W, n - first);
-		/* --- kernel values of every remaining filter, window by window (one integral image at a time) --- */
-		int frame_w[GDEEP_W], window_w[GDEEP_W];
-#pragma unroll
-		for (int w = 0; w < GDEEP_W; ++w) {
-			frame_w[w] = 0; window_w[w] = 0;
-			if (w >= nw) continue;
-			const DeepRec rec = q.rec[q.order2[first + w]];
-			frame_w[w] = rec.frame; window_w[w] = rec.window;
-			float* const hk = hk_all + w * hk_stride;
-			gdeep_integral_image(a, rec, pw, ph, stretch, lane, s_hist[warp], s_lut[warp], s_px[warp], ii);
-			for (int i = lane; i < m.per_level; i += 32) us[i] = 0.f;
-			__syncwarp();
-			if (lane < WVM_KA) { hk[lane] = rec.hk[lane]; if (lane < m.per_level) us[lane] = rec.u[lane]; }
-			__syncwarp();
-			for (int base = WVM_KA; base < m.num_used; base += 32)
-				gdeep_kernel_values(m, rec, base, min(32, m.num_used - base), lane, ii, pitch, us, hk);
-		}
-		__syncwarp();
-		/* --- weighted sums, round by round, the round's weights loaded once for all windows of the warp --- */
-		int final_level[GDEEP_W];
-		float final_fout[GDEEP_W];
-#pragma unroll
-		for (int w = 0; w < GDEEP_W; ++w) { final_level[w] = w < nw ? -1 : 0; final_fout[w] = 0.f; }
-		int round = 0;
-		for (int base = WVM_KA; base < m.num_used; base += 32, ++round) {
-			bool open = false;
-#pragma unroll
-			for (int w = 0; w < GDEEP_W; ++w) open = open || final_level[w] < 0;
-			if (!open) break;
-			const int cnt = min(32, m.num_used - base);
-			const int level = base + lane;
-			const bool owner = lane < cnt;
-			const float4* __restrict__ w4 = reinterpret_cast<const float4*>(m.hk_weights_t) + __ldg(m.hk_t_off + round) + lane;
-			float res[GDEEP_W];
-			const float r0 = owner ? -__ldg(m.lin_thresholds + level) : 0.f;
-#pragma unroll
-			for (int w = 0; w < GDEEP_W; ++w) res[w] = r0;
-			const int full = base >> 2, groups = (base + cnt + 3) >> 2;
-			float4 wn = __ldg(w4);
-			int gq = 0;
-			for (; gq < full; ++gq) {
-				const float4 wc = wn;
-				wn = __ldg(w4 + (size_t)(gq + 1) * 32);
-#pragma unroll
-				for (int w = 0; w < GDEEP_W; ++w) {
-					const float4 hc = *reinterpret_cast<const float4*>(hk_all + w * hk_stride + 4 * gq);
-					res[w] = __fadd_rn(res[w], __fmul_rn(wc.x, hc.x)); res[w] = __fadd_rn(res[w], __fmul_rn(wc.y, hc.y));
-					res[w] = __fadd_rn(res[w], __fmul_rn(wc.z, hc.z)); res[w] = __fadd_rn(res[w], __fmul_rn(wc.w, hc.w));
-				}
-			}
-			for (; gq < groups; ++gq) {
-				const float4 wc = wn;
-				wn = __ldg(w4 + (size_t)(gq + 1) * 32);
-				const int p = 4 * gq;
-#pragma unroll
-				for (int w = 0; w < GDEEP_W; ++w) {
-					const float4 hc = *reinterpret_cast<const float4*>(hk_all + w * hk_stride + 4 * gq);
-					if (owner && p <= level) res[w] = __fadd_rn(res[w], __fmul_rn(wc.x, hc.x));
-					if (owner && p + 1 <= level) res[w] = __fadd_rn(res[w], __fmul_rn(wc.y, hc.y));
-					if (owner && p + 2 <= level) res[w] = __fadd_rn(res[w], __fmul_rn(wc.z, hc.z));
-					if (owner && p + 3 <= level) res[w] = __fadd_rn(res[w], __fmul_rn(wc.w, hc.w));
-				}
-			}
-			const float thr = owner ? __ldg(m.thresholds + level) : 0.f;
-#pragma unroll
-			for (int w = 0; w < GDEEP_W; ++w) {
-				const bool pass = !owner || (res[w] >= thr && level + 1 < m.num_used);
-				const unsigned fails = __ballot_sync(0xffffffffu, owner && !pass);
-				if (fails && final_level[w] < 0) { /* the first rejecting filter of the first rejecting round */
-					const int src = __ffs(fails) - 1;
-					final_level[w] = base + src;
-					final_fout[w] = __shfl_sync(0xffffffffu, res[w], src);
-				}
-			}
-		}
-		if (lane == 0) {
-#pragma unroll
-			for (int w = 0; w < GDEEP_W; ++w)
-				if (w < nw) wvm_emit(m, frame_w[w], window_w[w], gm.windows_per_frame, final_level[w], final_fout[w], gm.dense, gm.cand, gm.cand_count, gm.cand_cap);
-		}
 		__syncwarp();
 	}
 }
@@ -688,25 +569,8 @@ void launch_wvm_group(cudaStream_t st, int pw, int ph, int pack, const GroupArgs
 
 void launch_wvm_deep_group(cudaStream_t st, const DeepArgs& args) {
 	if (args.n_models == 0) return;
-	/* the batched second stage needs GDEEP_W kernel-value rows per warp in shared memory and a second queue */
-	int max_used = 0;
-	bool queues = true;
-	for (int k = 0; k < args.n_models; ++k) {
-		max_used = std::max(max_used, args.models[k].m.num_used);
-		queues = queues && args.models[k].q.order2 != nullptr && args.models[k].m.per_level <= FDB_MAX_PER_LEVEL;
-	}
-	const int hk_stride = (max_used + 4 + 3) / 4 * 4 + 4; /* + 4: rows of neighbouring windows start in different banks */
-	const size_t dyn = (size_t)GDEEP_WARPS * GDEEP_W * hk_stride * sizeof(float);
-	static const bool enabled = [] { const char* e = std::getenv("FDB_DEEP_BATCH"); return !(e && e[0] == '0'); }(); /* debugging: one kernel for the whole tail */
-	const bool batched = enabled && queues && max_used > WVM_KA + 32 && dyn <= 150 * 1024;
 	dim3 grid((unsigned)(grp_sm_count() * 8 / std::max(1, std::min(args.n_models, 8))), (unsigned)args.n_models);
-	wvm_deep_group_kernel<<<grid, GDEEP_WARPS * 32, 0, st>>>(args, batched ? 0 : 1);
-	if (batched) {
-		static size_t configured = 0;
-		if (dyn > configured) { cudaFuncSetAttribute(wvm_deep_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn); configured = dyn; }
-		dim3 grid2((unsigned)(grp_sm_count() * 4 / std::max(1, std::min(args.n_models, 4))), (unsigned)args.n_models);
-		wvm_deep_batch_kernel<<<grid2, GDEEP_WARPS * 32, dyn, st>>>(args, hk_stride);
-	}
+	wvm_deep_group_kernel<<<grid, GDEEP_WARPS * 32, 0, st>>>(args);
 }
 
 } // namespace fdb

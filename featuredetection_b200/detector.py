@@ -436,9 +436,9 @@ class DetectorSet:
 
     def last_host_ms(self):
         """host wall clock of the last detect call: enqueue, phase A (wait + overlap elimination + SVM launch), phase B, whole call"""
-        ms = (C.c_double * 5)()
+        ms = (C.c_double * 8)()
         capi.check(self.ctx.lib, self.ctx.lib.fdb_detector_set_last_host_ms(self.h, ms))
-        return dict(zip(("enqueue", "phase_a", "phase_b", "call", "wait_stage1"), ms))
+        return dict(zip(("enqueue", "phase_a", "phase_b", "call", "wait_stage1", "phase_a_fetch", "phase_a_cpu", "phase_a_launch"), ms))
 
 
 class AggregatedFeaturesDetector:

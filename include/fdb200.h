@@ -621,10 +621,10 @@ FDB_API int64_t fdb_detector_set_windows_per_frame(fdb_detector_set* set); /* al
 /* shared pyramid: images built per frame and their bytes, window-kernel launches per chunk, members on the shared kernels */
 FDB_API int fdb_detector_set_info(fdb_detector_set* set, int32_t* n_images, int64_t* pyramid_bytes, int32_t* n_window_launches,
 		int32_t* n_fast_members);
-/* host wall clock of the last detect call in milliseconds: {enqueueing the chunks, overlap elimination + SVM launch,
- * classification + NMS, whole call, waiting for stage 1} - where a batch spends its time outside the kernels (read after the
- * call returned; the whole-call entry is complete only then) */
-FDB_API int fdb_detector_set_last_host_ms(fdb_detector_set* set, double ms_out[5]);
+/* host wall clock of the last detect call in milliseconds: {enqueueing the chunks, phase A = candidate lists + overlap
+ * elimination + SVM launch, phase B = classification + NMS, whole call, waiting for stage 1, and phase A split into fetching
+ * long candidate lists, the members' CPU work (thread pool), launching} - where a batch spends its time outside the kernels */
+FDB_API int fdb_detector_set_last_host_ms(fdb_detector_set* set, double ms_out[8]);
 /* Detector::detect of every member on n_frames host frames (8-bit, 1 channel, row pitch `pitch`) */
 FDB_API int fdb_detector_set_detect_batch(fdb_detector_set* set, const uint8_t* frames_host, int64_t pitch, int32_t n_frames,
 		int32_t stage, fdb_detection* detections_out, int64_t det_cap, int64_t* n_detections);

@@ -66,6 +66,43 @@ extern "C" long long emulate_fhog(const unsigned char* image, int cols, int rows
 	return (long long)crow * ccol * D;
 }
 
+/* aggdet_hist_kernel (csrc/aggdet.cu), tile by tile: phase 1 = one FhogPix per pixel of the tile + halo, phase 2 = thread per cell
+ * (fhog_cell_histogram); then the energies and descriptors as aggdet_desc_kernel computes them */
+extern "C" long long emulate_fhog_tiled(const unsigned char* image, int cols, int rows, int cell, int unsigned_bins,
+		int interpolate_bins, int interpolate_cells, float alpha, int tc, float* out) {
+	std::vector<FhogLutEntry> lut;
+	build_lut(unsigned_bins, interpolate_bins, lut);
+	const int crow = rows / cell, ccol = cols / cell, sb = 2 * unsigned_bins, D = 3 * unsigned_bins + 4;
+	const int rows_used = crow * cell, cols_used = ccol * cell;
+	std::vector<float> hist((size_t)crow * ccol * sb), energies((size_t)crow * ccol);
+	const int halo = interpolate_cells ? cell : 0, region = tc * cell + 2 * halo;
+	std::vector<FhogPix> px((size_t)region * region);
+	for (int ty = 0; ty * tc < crow; ++ty)
+		for (int tx = 0; tx * tc < ccol; ++tx) {
+			const int cr0 = ty * tc, cc0 = tx * tc, pr0 = cr0 * cell - halo, pc0 = cc0 * cell - halo;
+			for (int i = 0; i < region * region; ++i) {
+				const int r = pr0 + i / region, c = pc0 + i % region;
+				FhogPix e; e.i1 = 0; e.i2 = 0; e.valid = 0; e.w1 = 0.f; e.w2 = 0.f;
+				if (r >= 0 && c >= 0 && r < rows_used && c < cols_used) {
+					const FhogLutEntry* q = fhog_pixel_entry(lut.data(), image, cols, rows, cols, 1, r, c);
+					e.i1 = (uint8_t)q->index1; e.i2 = (uint8_t)q->index2; e.w1 = q->weight1; e.w2 = q->weight2; e.valid = 1;
+				}
+				px[i] = e;
+			}
+			for (int t = 0; t < tc * tc; ++t) {
+				const int cr = cr0 + t / tc, cc = cc0 + t % tc;
+				if (cr >= crow || cc >= ccol) continue;
+				std::vector<float> h(sb + 1, 0.f);
+				fhog_cell_histogram(px.data(), pr0, pc0, region, cell, crow, ccol, interpolate_bins, interpolate_cells, cr, cc, h.data());
+				for (int b = 0; b < sb; ++b) hist[((size_t)cr * ccol + cc) * sb + b] = h[b];
+				energies[(size_t)cr * ccol + cc] = fhog_energy(h.data(), unsigned_bins);
+			}
+		}
+	for (int i = 0; i < crow * ccol; ++i)
+		fhog_descriptor(&hist[(size_t)i * sb], energies.data(), crow, ccol, i / ccol, i % ccol, unsigned_bins, alpha, out + (size_t)i * D);
+	return (long long)crow * ccol * D;
+}
+
 extern "C" void emulate_score_map(const float* feat, int rows, int cols, int D, const float* weights, int kh, int kw, float bias, float* scores) {
 	const int vh = rows - kh + 1, vw = cols - kw + 1;
 	for (int i = 0; i < vh * vw; ++i) scores[i] = aggdet_score(feat, cols, D, weights, kh, kw, bias, i / vw, i % vw); /* aggdet_score_kernel */
@@ -87,6 +124,8 @@ def emu(tmp_path_factory, built):
     lib = C.CDLL(str(so))
     lib.emulate_fhog.restype = C.c_longlong
     lib.emulate_fhog.argtypes = ARGS
+    lib.emulate_fhog_tiled.restype = C.c_longlong
+    lib.emulate_fhog_tiled.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_void_p]
     lib.emulate_score_map.restype = None
     lib.emulate_score_map.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_void_p]
     return lib
@@ -107,6 +146,23 @@ def test_kernel_arithmetic_equals_the_pinned_oracle(emu, cell, bins, ib, ic, alp
         want = fo.fhog(img, cell, bins, ib, ic, alpha)
         got = np.full_like(want, np.nan)
         n = emu.emulate_fhog(img.ctypes.data, cols, rows, ch, cell, bins, int(ib), int(ic), alpha, got.ctypes.data)
+        assert n == want.size
+        assert np.array_equal(got, want), (img.shape, float(np.nanmax(np.abs(got - want))))
+
+
+@pytest.mark.parametrize("cell,bins,ib,ic,tc", [(4, 9, False, True, 8), (8, 9, True, True, 6), (4, 6, True, False, 8), (5, 9, False, False, 3),
+                                                 (6, 8, True, True, 2), (3, 9, False, True, 1)])
+def test_batched_kernel_decomposition_equals_the_pinned_oracle(emu, cell, bins, ib, ic, tc):
+    """the tile + halo staging and the per-cell raster walk of aggdet_hist_kernel (fhog_cell_histogram), emulated on the host"""
+    from oracle import fdoracle as fo
+    gray = np.ascontiguousarray(syn.synthetic_frame(3)[:131, :203])
+    flat = np.full((40, 48), 77, np.uint8)
+    for img in (gray, flat, np.ascontiguousarray(gray[:cell, :cell * 2]), np.ascontiguousarray(gray[:2 * cell + 1, :cell])):
+        img = np.ascontiguousarray(img)
+        rows, cols = img.shape
+        want = fo.fhog(img, cell, bins, ib, ic, 0.2)
+        got = np.full_like(want, np.nan)
+        n = emu.emulate_fhog_tiled(img.ctypes.data, cols, rows, cell, bins, int(ib), int(ic), 0.2, tc, got.ctypes.data)
         assert n == want.size
         assert np.array_equal(got, want), (img.shape, float(np.nanmax(np.abs(got - want))))
 
