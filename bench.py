@@ -1188,13 +1188,17 @@ def measure_cascades(args, workload, feature, n, rank, world, device, ctx, dist,
                 per_rank=per_rank, e2e_per_rank=e2e_per_rank, info=info, host_ms=host_ms)
 
 
-def measured_traffic(kernel):
-    """dram bytes per launch of a kernel from the committed ncu --set full capture (profiles/traffic.json names the capture)"""
+def measured_traffic(kernel, frames=1):
+    """dram bytes of a kernel from the committed ncu --set full capture (profiles/traffic.json names the capture and the build)"""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     if not os.path.exists(p):
         return None, None
     t = json.load(open(p)).get(kernel)
-    return (t["dram_bytes_per_launch"], t["source"]) if t else (None, None)
+    if not t:
+        return None, None
+    if "dram_bytes_per_frame" in t:
+        return t["dram_bytes_per_frame"] * frames, t["source"]
+    return t["dram_bytes_per_launch"], t["source"]
 
 
 def main():
@@ -1297,7 +1301,7 @@ def main():
         algo_bytes = (W * H + WINDOW_BYTES * nwin) * n
         achieved = algo_bytes / (ms_wvm * 1e-3) / 1e9
         kname = "wvm_group_kernel/landmarks15" if args.workload == "landmarks15" else "wvm_group_kernel/facefrontal"
-        traffic, traffic_src = measured_traffic(kname)
+        traffic, traffic_src = measured_traffic(kname, n)
         cpu = None
         if not args.no_cpu_baseline and world == 1:  # the CPU baseline is a rank-0, N=1 datum
             arm = CpuArm(args.workload, args.profile, args.feature)

@@ -1463,8 +1463,10 @@ int fdb_detect_single_device(fdb_detector* det, const uint8_t* frames_device, in
 	int s = check_ctx(det->ctx); if (s) return s;
 	if (det->wvm || !det->svm) return fail(FDB_ERR_INVALID_ARGUMENT, "fdb_detect_single_device needs a detector created with an SVM only");
 	if (n_frames < 0 || (n_frames > 0 && !frames_device)) return fail(FDB_ERR_INVALID_ARGUMENT, "bad frame batch");
-	if (!single_dense_usable(det))
-		return fail(FDB_ERR_UNSUPPORTED, "fdb_detect_single_device: this SVM has no tensor-core form (u8 RBF on HistEq64 patches only)");
+	if (!single_dense_usable(det)) { /* any other classifier / feature space: the per-window kernels; distances only to host memory */
+		if (distance_device) return fail(FDB_ERR_UNSUPPORTED, "fdb_detect_single_device: distances stay on the device only for the tensor-core SVM (u8 RBF on HistEq64 patches)");
+		return detect_single(det, frames_device, true, det->plan.width, n_frames, nullptr, detections_out, det_cap, n_detections);
+	}
 	return detect_single_dense(det, frames_device, true, det->plan.width, n_frames, distance_device, true, detections_out, det_cap, n_detections);
 } FDB_API_CATCH
 

@@ -98,13 +98,17 @@ __device__ __forceinline__ uint32_t grp_hq_step_any(float& cdf, uint32_t cnt, fl
 }
 
 template <int PW, int PH, int MSUB>
-__global__ void __launch_bounds__(GRP_WARPS * 32, MSUB == 1 ? 4 : 3) wvm_group_kernel(const __grid_constant__ GroupArgs a) {
+__global__ void __launch_bounds__(GRP_WARPS * 32, MSUB == 1 ? 4 : (MSUB == 2 ? 3 : 2)) wvm_group_kernel(const __grid_constant__ GroupArgs a) {
 	static_assert(PW % 4 == 0 && PW >= 16 && PW <= 32, "window width: a multiple of 4 in 16..32");
 	constexpr int WPR = PW / 4;                 /* words per patch row */
 	constexpr int RPK = PW <= 16 ? 2 : 1;       /* patch rows per k-step (32 operand bytes) */
 	static_assert(PH % RPK == 0, "window height must split into k-steps");
 	static_assert(grp_stretch_is_safe(PW * PH), "grp_hq_step's shortcut does not hold for this window size");
 	constexpr int KS = PH / RPK;
+#ifndef GRP_KUNROLL
+#define GRP_KUNROLL 1
+#endif
+	constexpr int KUNROLL = GRP_KUNROLL; /* k-steps per loop iteration (tuning builds) */
 	extern __shared__ __align__(128) uint8_t smem8[];
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	uint8_t* const s_base = smem8 + warp * GRP_WARP_BYTES;
@@ -236,7 +240,7 @@ __global__ void __launch_bounds__(GRP_WARPS * 32, MSUB == 1 ? 4 : 3) wvm_group_k
 #pragma unroll
 			for (int mi = 0; mi < MSUB; ++mi) bf[mi] = a.models[it.model[mi < it.nm ? mi : 0]].m.bfrag + lane * 2;
 			const uint32_t* const trow = reinterpret_cast<const uint32_t*>(s_tile + ((org + w * GRP_PITCH) & ~3));
-#pragma unroll 1
+#pragma unroll KUNROLL
 			for (int s = 0; s < KS; ++s) {
 				/* the models' B fragments of this k-step: requested first, they arrive while the A rows are built */
 				uint4 bA[MSUB], bB[MSUB];
@@ -528,7 +532,12 @@ static cudaError_t grp_configure() {
 
 int group_configure_all() {
 	cudaError_t e = cudaSuccess;
+#if GRP_MAX_PACK > 2
+#define GRP_CFG(PW, PH) if (e == cudaSuccess) e = grp_configure<PW, PH, 1>(); if (e == cudaSuccess) e = grp_configure<PW, PH, 2>(); \
+	if (e == cudaSuccess) e = grp_configure<PW, PH, GRP_MAX_PACK>();
+#else
 #define GRP_CFG(PW, PH) if (e == cudaSuccess) e = grp_configure<PW, PH, 1>(); if (e == cudaSuccess) e = grp_configure<PW, PH, 2>();
+#endif
 	GRP_SIZES(GRP_CFG)
 #undef GRP_CFG
 	return (int)e;
@@ -555,14 +564,19 @@ static int grp_sm_count() {
 template <int PW, int PH, int MSUB>
 static void grp_launch(cudaStream_t st, const GroupArgs& args) {
 	const int64_t units = (int64_t)args.n_items * args.n_frames;
-	const int resident = grp_sm_count() * (MSUB == 1 ? 4 : 3); /* one persistent CTA per resident slot */
+	const int resident = grp_sm_count() * (MSUB == 1 ? 4 : (MSUB == 2 ? 3 : 2)); /* one persistent CTA per resident slot */
 	const int blocks = (int)std::min<int64_t>(resident, (units + GRP_WARPS - 1) / GRP_WARPS);
 	wvm_group_kernel<PW, PH, MSUB><<<blocks, GRP_WARPS * 32, GRP_SMEM, st>>>(args);
 }
 
 void launch_wvm_group(cudaStream_t st, int pw, int ph, int pack, const GroupArgs& args) {
 	if (args.n_items == 0 || args.n_frames == 0) return;
+#if GRP_MAX_PACK > 2
+#define GRP_CASE(PW, PH) if (pw == PW && ph == PH) { if (pack <= 1) grp_launch<PW, PH, 1>(st, args); else if (pack == 2) grp_launch<PW, PH, 2>(st, args); \
+	else grp_launch<PW, PH, GRP_MAX_PACK>(st, args); return; }
+#else
 #define GRP_CASE(PW, PH) if (pw == PW && ph == PH) { if (pack <= 1) grp_launch<PW, PH, 1>(st, args); else grp_launch<PW, PH, 2>(st, args); return; }
+#endif
 	GRP_SIZES(GRP_CASE)
 #undef GRP_CASE
 }

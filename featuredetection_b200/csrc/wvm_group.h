@@ -18,7 +18,9 @@
 namespace fdb {
 
 #define GRP_MAX_MODELS 16 /* detectors per launch (ffpDetectApp: 15) */
+#ifndef GRP_MAX_PACK
 #define GRP_MAX_PACK 2    /* models sharing one equalisation inside the window kernel (register accumulators: 32 per model) */
+#endif
 
 struct GroupModel {       /* one detector's stage-1 classifier and where its results go */
 	DevWvm m;
