@@ -19,10 +19,11 @@
  *                        exactly for every bin at once. Energy of the cell (FhogAggregationFilter.cpp:60-68) on the way out.
  *   aggdet_desc_kernel   thread = cell: 4 normalisers from the 3 x 3 energies, 3 B + 4 features (fhog_descriptor of fhog_core.h),
  *                        rows padded to a multiple of 4 floats.
- *   aggdet_score_kernel  a CTA owns 8 x 32 score positions of one layer: the feature tile (+ kernel halo) and the weights are
- *                        staged in shared memory, score = -bias + sum over channels of the correlation in the order of the
- *                        oracle's restatement (channel, kernel row, kernel column); positions above the threshold are appended
- *                        to the candidate list (atomic cursor), optionally the dense map is written.
+ *   aggdet_score_kernel  a CTA owns 8 x 32 score positions of one layer, a thread 4 adjacent ones: 8 channels at a time the
+ *                        feature tile (+ kernel halo) and the weights are staged in shared memory; per kernel tap one weight
+ *                        load and one new feature serve the thread's 4 positions; score = -bias + sum over channels of the
+ *                        correlation in the order of the oracle's restatement (channel, kernel row, kernel column); positions
+ *                        above the threshold are appended to the candidate list (atomic cursor), optionally the dense map.
  * Bound: HBM by construction (1 byte per pixel in, (3 B + 4) * 4 / cell^2 bytes per pixel out); the per-cell replay of phase 2
  * costs ~5 warp instructions per pixel, which keeps the kernel issue-bound below that roofline (measured: profiles/).
  * cv::filter2D's own summation order (and its DFT path for kernels of >= 50 elements) belongs to OpenCV: score parity is 1e-4.
@@ -143,7 +144,11 @@ __global__ void __launch_bounds__(128) aggdet_desc_kernel(const AggParams P, con
 	for (int k = P.D; k < P.Dp; ++k) dst[k] = 0.f;
 }
 
-__global__ void __launch_bounds__(AGG_SCORE_TY * AGG_SCORE_TX) aggdet_score_kernel(const AggParams P, const AggLayer* __restrict__ layers,
+#define AGG_SCORE_XB 4   /* adjacent score positions per thread: one weight load and a sliding feature window serve 4 positions */
+#define AGG_SCORE_CB 8   /* channels staged per pass */
+#define AGG_SCORE_THREADS (AGG_SCORE_TY * AGG_SCORE_TX / AGG_SCORE_XB)
+
+__global__ void __launch_bounds__(AGG_SCORE_THREADS) aggdet_score_kernel(const AggParams P, const AggLayer* __restrict__ layers,
 		const int* __restrict__ stile_layer, const float* __restrict__ feat, int64_t feat_stride, const float* __restrict__ weights,
 		float* __restrict__ scores /* nullable */, int64_t score_stride, AggCandidate* __restrict__ cand, int* __restrict__ cand_count, int cand_cap) {
 	extern __shared__ __align__(16) float sf[];
@@ -153,39 +158,67 @@ __global__ void __launch_bounds__(AGG_SCORE_TY * AGG_SCORE_TX) aggdet_score_kern
 	const int tile = blockIdx.x - L.first_stile;
 	const int ty0 = (tile / L.stiles_x) * AGG_SCORE_TY, tx0 = (tile % L.stiles_x) * AGG_SCORE_TX;
 	const int th = AGG_SCORE_TY + P.kh - 1, tw = AGG_SCORE_TX + P.kw - 1;
-	const int Ds = P.Dp + 1;                          /* odd row length in shared memory: neighbouring positions hit different banks */
-	float* const s_w = sf;                            /* [kh][kw][D] */
-	float* const s_f = sf + P.kh * P.kw * P.D;        /* [th][tw][Ds] */
-	for (int i = threadIdx.x; i < P.kh * P.kw * P.D; i += blockDim.x) s_w[i] = weights[i];
+	constexpr int CS = AGG_SCORE_CB + 1;              /* odd row length in shared memory: neighbouring positions hit different banks */
+	float* const s_w = sf;                            /* [kh][kw][CB] weights of the pass */
+	float* const s_f = sf + P.kh * P.kw * AGG_SCORE_CB; /* [th][tw][CS] features of the pass */
 	const float* __restrict__ f = feat + (int64_t)frame * feat_stride + L.feat_off;
-	const int quads = P.Dp / 4;
-	for (int i = threadIdx.x; i < th * tw * quads; i += blockDim.x) {
-		const int q = i % quads, cellidx = i / quads;
-		const int yy = cellidx / tw, xx = cellidx - yy * tw;
-		const int y = ty0 + yy, x = tx0 + xx;
-		float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-		if (y < L.crow && x < L.ccol) v = *reinterpret_cast<const float4*>(f + ((int64_t)y * L.ccol + x) * P.Dp + 4 * q);
-		float* d = s_f + (yy * tw + xx) * Ds + 4 * q;
-		d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
-	}
-	__syncthreads();
-	const int ly = threadIdx.x / AGG_SCORE_TX, lx = threadIdx.x % AGG_SCORE_TX;
-	const int y = ty0 + ly, x = tx0 + lx;
-	if (y >= L.vh || x >= L.vw) return;
+	const int ly = threadIdx.x / (AGG_SCORE_TX / AGG_SCORE_XB), lx = (threadIdx.x % (AGG_SCORE_TX / AGG_SCORE_XB)) * AGG_SCORE_XB;
 	/* ConvolutionFilter::applyTo as AggregatedFeaturesDetector configures it (ConvolutionFilter.cpp:31-49): delta = -bias, then
 	 * channel by channel the correlation with that channel's kernel, anchor (0, 0) */
-	float score = -P.bias;
-	for (int c = 0; c < P.D; ++c) {
-		float tmp = 0.f;
-		for (int i = 0; i < P.kh; ++i)
-			for (int j = 0; j < P.kw; ++j)
-				tmp = FHOG_ADD(tmp, FHOG_MUL(s_f[((ly + i) * tw + lx + j) * Ds + c], s_w[(i * P.kw + j) * P.D + c]));
-		score = FHOG_ADD(score, tmp);
+	float score[AGG_SCORE_XB];
+#pragma unroll
+	for (int k = 0; k < AGG_SCORE_XB; ++k) score[k] = -P.bias;
+	for (int c0 = 0; c0 < P.D; c0 += AGG_SCORE_CB) {
+		const int nc = min(AGG_SCORE_CB, P.D - c0);
+		__syncthreads(); /* the previous pass is consumed */
+		for (int i = threadIdx.x; i < P.kh * P.kw * AGG_SCORE_CB; i += blockDim.x) {
+			const int c = i % AGG_SCORE_CB, tap = i / AGG_SCORE_CB;
+			s_w[i] = c < nc ? weights[tap * P.D + c0 + c] : 0.f;
+		}
+		for (int i = threadIdx.x; i < th * tw * (AGG_SCORE_CB / 4); i += blockDim.x) {
+			const int q = i % (AGG_SCORE_CB / 4), cellidx = i / (AGG_SCORE_CB / 4);
+			const int yy = cellidx / tw, xx = cellidx - yy * tw;
+			const int y = ty0 + yy, x = tx0 + xx;
+			float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+			if (y < L.crow && x < L.ccol && c0 + 4 * q < P.Dp) v = *reinterpret_cast<const float4*>(f + ((int64_t)y * L.ccol + x) * P.Dp + c0 + 4 * q);
+			float* d = s_f + (yy * tw + xx) * CS + 4 * q;
+			d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+		}
+		__syncthreads();
+		for (int c = 0; c < nc; ++c) {
+			float tmp[AGG_SCORE_XB];
+#pragma unroll
+			for (int k = 0; k < AGG_SCORE_XB; ++k) tmp[k] = 0.f;
+			for (int i = 0; i < P.kh; ++i) {
+				const float* row = s_f + ((ly + i) * tw + lx) * CS + c;
+				const float* wrow = s_w + i * P.kw * AGG_SCORE_CB + c;
+				float win[AGG_SCORE_XB]; /* features under tap j of the 4 positions: a window sliding with j */
+#pragma unroll
+				for (int k = 0; k < AGG_SCORE_XB - 1; ++k) win[k + 1] = row[k * CS];
+				for (int j = 0; j < P.kw; ++j) {
+#pragma unroll
+					for (int k = 0; k < AGG_SCORE_XB - 1; ++k) win[k] = win[k + 1];
+					win[AGG_SCORE_XB - 1] = row[(j + AGG_SCORE_XB - 1) * CS];
+					const float w = wrow[j * AGG_SCORE_CB];
+#pragma unroll
+					for (int k = 0; k < AGG_SCORE_XB; ++k) tmp[k] = FHOG_ADD(tmp[k], FHOG_MUL(win[k], w));
+				}
+			}
+#pragma unroll
+			for (int k = 0; k < AGG_SCORE_XB; ++k) score[k] = FHOG_ADD(score[k], tmp[k]);
+		}
 	}
-	if (scores) scores[(int64_t)frame * score_stride + L.score_off + (int64_t)y * L.vw + x] = score;
-	if (score > P.threshold) { /* AggregatedFeaturesDetector.cpp:100 */
-		const int slot = atomicAdd(cand_count, 1);
-		if (slot < cand_cap) { AggCandidate k; k.frame = frame; k.layer = li; k.x = x; k.y = y; k.score = score; cand[slot] = k; }
+	const int y = ty0 + ly;
+	if (y >= L.vh) return;
+#pragma unroll
+	for (int k = 0; k < AGG_SCORE_XB; ++k) {
+		const int x = tx0 + lx + k;
+		if (x >= L.vw) continue;
+		if (scores) scores[(int64_t)frame * score_stride + L.score_off + (int64_t)y * L.vw + x] = score[k];
+		if (score[k] > P.threshold) { /* AggregatedFeaturesDetector.cpp:100 */
+			const int slot = atomicAdd(cand_count, 1);
+			if (slot < cand_cap) { AggCandidate q; q.frame = frame; q.layer = li; q.x = x; q.y = y; q.score = score[k]; cand[slot] = q; }
+		}
 	}
 }
 
@@ -260,7 +293,7 @@ int agg_enqueue(fdb_aggdet* d, const uint8_t* d_frames, int n, bool want_scores,
 	} else if (ev) CUDA_TRY(cudaEventRecord(ev[2], st));
 	if (ev) CUDA_TRY(cudaEventRecord(ev[3], st));
 	if (d->n_stiles) {
-		aggdet_score_kernel<<<dim3((unsigned)d->n_stiles, (unsigned)n), AGG_SCORE_TY * AGG_SCORE_TX, d->score_smem, st>>>(P, d->d_layers,
+		aggdet_score_kernel<<<dim3((unsigned)d->n_stiles, (unsigned)n), AGG_SCORE_THREADS, d->score_smem, st>>>(P, d->d_layers,
 				d->d_stile_layer, d->d_feat, d->feat_stride, d->d_weights, want_scores ? d->d_scores : nullptr, d->score_stride, d->d_cand,
 				d->d_count, d->cand_cap);
 		c->launches++;
@@ -401,7 +434,7 @@ int fdb_aggdet_prepare(fdb_aggdet* d, int32_t width, int32_t height, int32_t max
 	P.tc = std::max(1, std::min(8, (int)std::floor(std::sqrt(48.0 * 1024 / sizeof(PixEntry)) / a.cell_size) - 2));
 	const int region = P.tc * a.cell_size + 2 * a.cell_size;
 	d->hist_smem = (size_t)region * region * sizeof(PixEntry) + (size_t)P.tc * P.tc * P.hstride * sizeof(float);
-	d->score_smem = ((size_t)P.kh * P.kw * P.D + (size_t)(AGG_SCORE_TY + P.kh - 1) * (AGG_SCORE_TX + P.kw - 1) * (P.Dp + 1)) * sizeof(float);
+	d->score_smem = ((size_t)P.kh * P.kw * AGG_SCORE_CB + (size_t)(AGG_SCORE_TY + P.kh - 1) * (AGG_SCORE_TX + P.kw - 1) * (AGG_SCORE_CB + 1)) * sizeof(float);
 	if (d->hist_smem > 200 * 1024 || d->score_smem > 200 * 1024) return fail(FDB_ERR_UNSUPPORTED, "cell or window size too large for the shared-memory tiles");
 	CUDA_TRY(cudaFuncSetAttribute(aggdet_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->hist_smem));
 	CUDA_TRY(cudaFuncSetAttribute(aggdet_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->score_smem));

@@ -171,6 +171,58 @@ __global__ void __launch_bounds__(SVM_THREADS) svm_kernel(const DevSvm s, int pa
 	}
 }
 
+/* RBF SVM on float32 feature vectors, SVMB_W vectors per CTA: svm_kernel<2> streams the whole model (num_sv x dim floats,
+ * 1.6 MB for 1024 vectors of 400) from L2 once per classified vector, which bounds the `single` detector in a feature space
+ * (every window of every frame is classified) by L2 bandwidth. Here a thread owns one support vector of the chunk and keeps
+ * SVMB_W sums of squared differences, so every model element that arrives is used for SVMB_W windows. Arithmetic and order are
+ * those of svm_kernel<2>: float32 sequential SSD per (vector, support vector) pair (RbfKernel.hpp:97-108), exp in double,
+ * coefficient product, then the double sum over the support vectors in their order (SvmClassifier.cpp:55-60). */
+#define SVMB_W 8
+__global__ void __launch_bounds__(SVM_THREADS) svm_f32_rbf_block_kernel(const DevSvm s, const float* __restrict__ vectors, int n,
+		double* __restrict__ distance_out) {
+	extern __shared__ __align__(16) unsigned char svmb_smem[];
+	double* s_prod = reinterpret_cast<double*>(svmb_smem);                                   /* [SVMB_W][SVM_THREADS] */
+	float* s_x = reinterpret_cast<float*>(svmb_smem + sizeof(double) * SVMB_W * SVM_THREADS);  /* [dim][SVMB_W] */
+	const int tid = threadIdx.x;
+	const int v0 = blockIdx.x * SVMB_W;
+	const int nw = min(SVMB_W, n - v0);
+	for (int i = tid; i < s.dim * SVMB_W; i += SVM_THREADS) {
+		const int k = i / SVMB_W, w = i - k * SVMB_W;
+		s_x[i] = w < nw ? vectors[(int64_t)(v0 + w) * s.dim + k] : 0.f;
+	}
+	__syncthreads();
+	double distance = -(double)s.bias; /* thread w < nw: the hyperplane distance of vector v0 + w */
+	for (int base = 0; base < s.num_sv; base += SVM_THREADS) {
+		const int cnt = min(SVM_THREADS, s.num_sv - base);
+		if (tid < cnt) {
+			const int sv = base + tid;
+			const float* __restrict__ col = s.sv_f32 + sv;
+			float sum[SVMB_W];
+#pragma unroll
+			for (int w = 0; w < SVMB_W; ++w) sum[w] = 0.f;
+			for (int k = 0; k < s.dim; ++k) {
+				const float c = col[(size_t)k * s.num_sv];
+				const float4 xa = *reinterpret_cast<const float4*>(s_x + k * SVMB_W), xb = *reinterpret_cast<const float4*>(s_x + k * SVMB_W + 4);
+				const float x[SVMB_W] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+#pragma unroll
+				for (int w = 0; w < SVMB_W; ++w) {
+					const float diff = __fsub_rn(x[w], c);
+					sum[w] = __fadd_rn(sum[w], __fmul_rn(diff, diff));
+				}
+			}
+			const double coef = (double)s.coef[sv];
+#pragma unroll
+			for (int w = 0; w < SVMB_W; ++w) s_prod[w * SVM_THREADS + tid] = __dmul_rn(coef, exp(__dmul_rn(-s.gamma, (double)sum[w])));
+		}
+		__syncthreads();
+		if (tid < nw) for (int i = 0; i < cnt; ++i) distance = __dadd_rn(distance, s_prod[tid * SVM_THREADS + i]);
+		__syncthreads();
+	}
+	if (tid < nw) distance_out[v0 + tid] = distance;
+}
+
+static size_t svmb_smem_bytes(const DevSvm& s) { return sizeof(double) * SVMB_W * SVM_THREADS + sizeof(float) * (size_t)s.dim * SVMB_W; }
+
 /* HistEq64 patches (HistEq64Filter.cpp:32-125) of a list of windows -> [n][patch_w * patch_h] u8: the patch data of
  * DirectPyramidFeatureExtractor::extract(x, y, width, height) (DirectPyramidFeatureExtractor.cpp:67-73,133-147) for
  * sparse callers (condensation::WvmSvmModel). One CTA of 128 threads per window. */
@@ -224,6 +276,7 @@ int svm_configure() {
 	cudaError_t e = cudaFuncSetAttribute(svm_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
 	if (e == cudaSuccess) e = cudaFuncSetAttribute(svm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
 	if (e == cudaSuccess) e = cudaFuncSetAttribute(svm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
+	if (e == cudaSuccess) e = cudaFuncSetAttribute(svm_f32_rbf_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
 	return (int)e;
 }
 
@@ -237,6 +290,10 @@ void launch_svm_windows(cudaStream_t st, const DevSvm& s, int patch_w, int patch
 
 void launch_svm_vectors(cudaStream_t st, const DevSvm& s, const void* vectors, int n, double* distance_out, int* level_out) {
 	if (n == 0) return;
+	if (s.sv_type == FDB_SV_F32 && s.kernel == FDB_KERNEL_RBF && s.rvm_filters == 0 && n >= 2 * SVMB_W && svmb_smem_bytes(s) <= 128 * 1024) {
+		svm_f32_rbf_block_kernel<<<(unsigned)((n + SVMB_W - 1) / SVMB_W), SVM_THREADS, svmb_smem_bytes(s), st>>>(s, reinterpret_cast<const float*>(vectors), n, distance_out);
+		return;
+	}
 	if (s.sv_type == FDB_SV_F32)
 		svm_kernel<2><<<(unsigned)n, SVM_THREADS, svm_smem_bytes(s), st>>>(s, 0, 0, nullptr, 0, 0, nullptr, 0, nullptr,
 				nullptr, vectors, distance_out, level_out);
