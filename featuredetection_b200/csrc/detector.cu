@@ -875,7 +875,7 @@ int fdb_detector_prepare(fdb_detector* det, int32_t width, int32_t height, int32
 		if (det->has_feature) { s = feature_build(fd, det->desc.patch_width, det->desc.patch_height, plan, &det->feat, &det->farena_bytes, det->owned); if (s) return s; }
 	}
 	/* chunking: big batches flow through the slots in quarters so that copies, kernels and host work overlap */
-	det->chunk = max_batch >= 16 ? (max_batch + 3) / 4 : max_batch;
+	det->chunk = max_batch >= 16 ? std::min((max_batch + 3) / 4, 64) : max_batch; /* at most 64 frames: candidate lists stay within the in-order copy */
 	if (const char* e = std::getenv("FDB_CHUNK_FRAMES")) { /* tuning knob: frames per pipeline chunk */
 		const int v = std::atoi(e);
 		if (v > 0) det->chunk = std::min(v, (int)max_batch);
