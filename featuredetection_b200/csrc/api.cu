@@ -229,7 +229,7 @@ int fdb_wvm_create(fdb_ctx* ctx, const fdb_wvm_desc* d, fdb_wvm** out) try {
 		dv.rects = rp;
 		UP(roff.data(), n + 1, rect_off, ip);
 	}
-	dv.bfrag = nullptr;
+	dv.bfrag = nullptr; dv.btc = nullptr;
 	dv.hk_weights_t = nullptr; dv.hk_t_off = nullptr;
 	if (max_nv <= 4 && n > WVM_KA && group_supported(w, h)) {
 		/* rectangle coverage counts of the first WVM_KA filters in mma.m16n8k32 B-fragment order (wvm_group.cu): k-step s is
@@ -251,6 +251,22 @@ int fdb_wvm_create(fdb_ctx* ctx, const fdb_wvm_desc* d, fdb_wvm** out) try {
 		uint32_t* bp;
 		s = upload(bf.data(), bf.size(), &bp, m->owned); if (s) { free_all(m->owned); delete m; return s; }
 		dv.bfrag = reinterpret_cast<const uint4*>(bp);
+		/* the same counts as the B operand of tcgen05.mma (wvm_group_tc.cu): per k-step 32 columns (4 * filter + grey value) x 32
+		 * operand bytes as UMMA core matrices, K-major without swizzle: byte (n, k) at (n / 8) * 256 + (k / 16) * 128 + (n % 8) * 16 + k % 16 */
+		std::vector<uint32_t> bt((size_t)ks * 256, 0u);
+		for (int s2 = 0; s2 < ks; ++s2)
+			for (int col = 0; col < 32; ++col)
+				for (int c = 0; c < 8; ++c) { /* word c of the k-step's 32 operand bytes */
+					const int f = col >> 2, v = col & 3;
+					const int row = rpk == 2 ? 2 * s2 + (c >> 2) : s2, c4 = rpk == 2 ? (c & 3) : c;
+					const int nv = d->area_cntval[f] - 1;
+					if (c4 < wpr && v < nv)
+						bt[(size_t)s2 * 256 + (size_t)((col >> 3) * 256 + (c >> 2) * 128 + (col & 7) * 16 + (c & 3) * 4) / 4] =
+								masks[(size_t)mask_off[f] + (size_t)(row * wpr + c4) * nv + v];
+				}
+		uint32_t* btp;
+		s = upload(bt.data(), bt.size(), &btp, m->owned); if (s) { free_all(m->owned); delete m; return s; }
+		dv.btc = reinterpret_cast<const uint8_t*>(btp);
 		/* weights of the deep kernel's rounds, transposed for coalesced loads; one zero group of padding per round (prefetch) */
 		std::vector<float> wt;
 		std::vector<int> toff;

@@ -150,13 +150,15 @@ bool encode_tile_maps(const std::vector<PyrImage>& images, const std::vector<int
 
 /* work items of the group kernel for one layer: strips of <= 32 window columns; narrow layers pack several row runs side
  * by side (all 32 lanes busy), the runs share the tile's rows. Balanced run length: the same number of window rows for
- * every lane of the layer. One item per strip and pack of <= GRP_MAX_PACK models. */
+ * every lane of the layer. One item per strip and pack of <= group_max_pack() models. */
 void append_strip_items(const PlanLayer& L, int image, int patch_h, int n_models, const int* models, const int* first_windows,
 		std::vector<GroupItem>* out) {
 	if (L.windows_x <= 0 || L.windows_y <= 0) return;
 	const int budget = STRIP_TILE_ROWS - (patch_h - 1); /* window rows per tile */
-	for (int m0 = 0; m0 < n_models; m0 += GRP_MAX_PACK) {
-		const int nm = std::min(GRP_MAX_PACK, n_models - m0);
+	/* balanced packs: 7 models -> 4 + 3, 5 -> 3 + 2 */
+	const int cap = group_max_pack(), npacks = (n_models + cap - 1) / cap;
+	for (int pk = 0, m0 = 0; pk < npacks; ++pk) {
+		const int nm = n_models / npacks + (pk < n_models % npacks ? 1 : 0);
 		for (int ix0 = 0; ix0 < L.windows_x; ix0 += 32) {
 			const int cols = std::min(32, L.windows_x - ix0);
 			const int nsub = std::min(WVM_MAXSUB, 32 / cols);
@@ -173,6 +175,7 @@ void append_strip_items(const PlanLayer& L, int image, int patch_h, int n_models
 				out->push_back(it);
 			}
 		}
+		m0 += nm;
 	}
 }
 

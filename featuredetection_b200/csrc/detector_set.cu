@@ -522,7 +522,7 @@ int fdb_detector_set_prepare(fdb_detector_set* s, int32_t width, int32_t height,
 		const PlanLayer& p = s->dets[(size_t)kv.second[0].first]->plan.layers[(size_t)kv.second[0].second];
 		std::vector<GroupItem> items;
 		append_strip_items(p, image, ph, (int)models.size(), models.data(), firsts.data(), &items);
-		for (const GroupItem& it : items) by_launch[std::make_tuple(pw, ph, it.nm > 2 ? GRP_MAX_PACK : it.nm)].push_back(it);
+		for (const GroupItem& it : items) by_launch[std::make_tuple(pw, ph, it.nm > 2 ? GRP_MAX_PACK : it.nm /* kernel instances exist for packs of 1, 2 and GRP_MAX_PACK */)].push_back(it);
 	}
 	for (auto& kv : by_launch) {
 		SetLaunch L;

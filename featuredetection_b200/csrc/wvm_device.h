@@ -53,6 +53,8 @@ struct DevWvm {
 	const int* mask_off;            /* [num_lin] */
 	const uint4* bfrag;             /* masks of the first WVM_KA filters as mma.m16n8k32 B fragments: [k-step][lane][2], one k-step per
 	                                 * patch row padded to 32 bytes (two rows for 16-wide windows) - wvm_group.cu; nullptr if unavailable */
+	const uint8_t* btc;             /* the same coverage counts as UMMA core matrices for wvm_group_tc.cu: [k-step][1 KB] = [4 groups of 8 columns]
+	                                 * [2 chunks of 16 operand bytes][8 columns][16 bytes], column = 4 * filter + grey value */
 	const float* hk_weights_t;      /* hkWeights of the deep kernel's rounds of 32 filters, transposed: round r at hk_t_off[r] (float4
 	                                 * units), [p / 4][lane][4] = w[WVM_KA + 32 r + lane][p .. p + 3] (0 beyond the triangle) */
 	const int* hk_t_off;

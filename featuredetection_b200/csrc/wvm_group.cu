@@ -41,26 +41,10 @@
 #include "fdb_internal.h"
 #include "wvm_device.h"
 #include "wvm_group.h"
+#include "wvm_group_dev.cuh"
 #include "wvm_math.cuh"
 
 namespace fdb {
-
-#define GRP_WARPS 4
-#define GRP_PITCH 64                    /* bytes per tile row: 32 columns + PW - 1 <= 63 */
-#define GRP_TILE_BYTES (STRIP_TILE_ROWS * GRP_PITCH)
-#define GRP_HIST_BYTES (64 * 32 * 2)    /* u16 [bin][lane] */
-#define GRP_LUT_BYTES (64 * 32)         /* u8 [bin][lane] */
-#define GRP_AROW 48                     /* bytes between windows in an A buffer: 32 used; 3 x 16 keeps ldmatrix and the 16-byte stores conflict free */
-#define GRP_ABUF_BYTES (32 * GRP_AROW)
-#define GRP_STAGE 40                    /* ints per window row of the D staging area */
-#define GRP_R_BYTES (GRP_LUT_BYTES + 2 * GRP_ABUF_BYTES) /* table + two A buffers = the staging area */
-#define GRP_HKU_BYTES (2 * WVM_KA * 32 * 4)
-#define GRP_WARP_BYTES (GRP_TILE_BYTES + GRP_HIST_BYTES + GRP_R_BYTES + GRP_HKU_BYTES)
-#define GRP_SMEM (GRP_WARPS * GRP_WARP_BYTES + GRP_WARPS * 8)
-
-static_assert(WVM_KA == 8, "the fragment table holds 8 filters x 4 grey values = 32 columns");
-static_assert(GRP_R_BYTES == 32 * GRP_STAGE * 4, "the staging area overlays the table and the A buffers exactly");
-static_assert(GRP_WARP_BYTES % 128 == 0, "TMA destinations are 128-byte aligned");
 
 __device__ __forceinline__ void grp_mma_u8(int (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
 	asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
@@ -70,31 +54,6 @@ __device__ __forceinline__ void grp_mma_u8(int (&d)[4], const uint32_t (&a)[4], 
 __device__ __forceinline__ void grp_ldmatrix4(uint32_t (&r)[4], uint32_t saddr) {
 	asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
 			: "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(saddr));
-}
-
-/* one step of the sequential cumulative histogram (HistEq64Filter.cpp:70-87,97): cdf += count * stretch in float32, then
- * (uchar)floor((double)cdf + 0.5). For 0 <= cdf < 256.5 that equals floor(cdf +f 0.5f) for EVERY float except the one just
- * below 0.5 (0x1.fffffep-2: the float sum rounds up to 1.0) - checked exhaustively over all 1.13e9 floats of the range.
- * A cumulative histogram below 0.5 is a single product count * stretch (stretch > 0.25 for windows of <= 1020 pixels), and
- * grp_stretch_is_safe() verifies at compile time that no such product is that float for the window sizes built here. */
-__device__ __forceinline__ uint32_t grp_hq_step(float& cdf, uint32_t cnt, float stretch) {
-	cdf = __fadd_rn(cdf, __fmul_rn((float)cnt, stretch));
-	return (uint32_t)__float2int_rd(__fadd_rn(cdf, 0.5f));
-}
-
-__host__ __device__ constexpr bool grp_stretch_is_safe(int pixels) {
-	const float stretch = 255.0f / (float)pixels;
-	if (!(stretch > 0.25f)) return false;
-	for (int cnt = 1; (float)cnt * stretch < 0.5f; ++cnt)
-		if ((float)cnt * stretch > 0.4999999f) return false;
-	return true;
-}
-
-/* the deep kernel equalises windows of any size: same value, exception handled explicitly */
-__device__ __forceinline__ uint32_t grp_hq_step_any(float& cdf, uint32_t cnt, float stretch) {
-	cdf = __fadd_rn(cdf, __fmul_rn((float)cnt, stretch));
-	const float fl = floorf(cdf); /* (uchar)floor((double)cdf + 0.5) == floor(cdf) + (frac >= 0.5) */
-	return ((uint32_t)(int)fl + (__fsub_rn(cdf, fl) >= 0.5f ? 1u : 0u)) & 255u;
 }
 
 template <int PW, int PH, int MSUB>
@@ -116,7 +75,8 @@ __global__ void __launch_bounds__(GRP_WARPS * 32, MSUB == 1 ? 4 : (MSUB == 2 ? 3
 	uint32_t* const s_histw = reinterpret_cast<uint32_t*>(s_base + GRP_TILE_BYTES);       /* word of bin b: [b * 16 + lane / 2] */
 	const uint16_t* const s_hist = reinterpret_cast<const uint16_t*>(s_histw) + lane;      /* count of bin b: [b * 32] */
 	uint8_t* const s_R = s_base + GRP_TILE_BYTES + GRP_HIST_BYTES;
-	uint8_t* const s_lut = s_R + lane;                                                    /* entry of bin b: [b * 32] */
+	uint32_t* const s_lutw = reinterpret_cast<uint32_t*>(s_R) + lane;                     /* word of bins 4q..4q+3: [q * 32] */
+	const uint8_t* const s_lutb = s_R + lane * 4;                                         /* the same column, as bytes */
 	uint8_t* const s_abuf = s_R + GRP_LUT_BYTES;
 	int* const s_stage = reinterpret_cast<int*>(s_R);                                     /* [32][GRP_STAGE] */
 	float* const s_hk = reinterpret_cast<float*>(s_R + GRP_R_BYTES) + lane;               /* hk_kernel_eval[i]: [i * 32] */
@@ -213,16 +173,7 @@ __global__ void __launch_bounds__(GRP_WARPS * 32, MSUB == 1 ? 4 : (MSUB == 2 ? 3
 			}
 			__syncwarp(); /* both lanes of a histogram word are done with it; the previous row's staging area is consumed */
 			/* --- equalisation table: sequential float32 cumulative histogram, one byte column per lane --- */
-			if (active) {
-				float cdf = 0.f;
-#pragma unroll 4
-				for (int k = 0; k < 64; ++k) {
-					const uint32_t cnt = s_hist[k * 32];
-					const uint32_t e = grp_hq_step(cdf, cnt, stretch);
-					s_lut[k * 32] = (uint8_t)e;
-					total += cnt * e;
-				}
-			}
+			if (active) total = grp_build_table(s_hist, s_lutw, stretch);
 			const float total_f = (float)total;
 
 			/* --- per k-step: this lane's window row(s) -> A buffer; all models of the pack multiply the same fragments --- */
@@ -250,22 +201,8 @@ __global__ void __launch_bounds__(GRP_WARPS * 32, MSUB == 1 ? 4 : (MSUB == 2 ? 3
 #pragma unroll
 				for (int pr = 0; pr < RPK; ++pr) {
 					const uint32_t* const src = trow + (s * RPK + pr) * (GRP_PITCH / 4);
-					uint32_t x[WPR + 1];
-#pragma unroll
-					for (int c = 0; c <= WPR; ++c) x[c] = src[c];
 					uint32_t wd[8];
-					uint32_t rowsq = 0;
-#pragma unroll
-					for (int c = 0; c < 8; ++c) {
-						if (c < WPR) {
-							const uint32_t b = __funnelshift_r(x[c], x[c + 1], sh); /* 4 bins of the lane's window */
-							/* byte extraction as one PRMT each, table row = bin * 32 folded into the address (LEA): 3 instructions per pixel */
-							const uint32_t e0 = s_lut[__byte_perm(b, 0, 0x4440) * 32], e1 = s_lut[__byte_perm(b, 0, 0x4441) * 32];
-							const uint32_t e2 = s_lut[__byte_perm(b, 0, 0x4442) * 32], e3 = s_lut[__byte_perm(b, 0, 0x4443) * 32];
-							wd[c] = __byte_perm(__byte_perm(e0, e1, 0x0040), __byte_perm(e2, e3, 0x0040), 0x5410);
-							rowsq = __dp4a(wd[c], wd[c], rowsq);
-						} else wd[c] = 0u;
-					}
+					const uint32_t rowsq = grp_equalise_row<WPR>(src, sh, s_lutb, wd);
 					sum_xx = (s == 0 && pr == 0) ? (float)rowsq : __fadd_rn(sum_xx, (float)rowsq);
 					if (RPK == 2) {
 						*reinterpret_cast<uint4*>(arow + pr * 16) = make_uint4(wd[0], wd[1], wd[2], wd[3]);
@@ -523,6 +460,10 @@ __global__ void __launch_bounds__(GDEEP_WARPS * 32) wvm_deep_group_kernel(const 
 /* ---------------------------------------------------------------------------------------------
  * launchers
  * ------------------------------------------------------------------------------------------- */
+#ifndef GRP_MMA_PACK
+#define GRP_MMA_PACK 2 /* register accumulators (32 per model) limit the mma.sync kernel to packs of two */
+#endif
+
 template <int PW, int PH, int MSUB>
 static cudaError_t grp_configure() {
 	return cudaFuncSetAttribute(wvm_group_kernel<PW, PH, MSUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GRP_SMEM);
@@ -532,14 +473,15 @@ static cudaError_t grp_configure() {
 
 int group_configure_all() {
 	cudaError_t e = cudaSuccess;
-#if GRP_MAX_PACK > 2
+#if GRP_MMA_PACK > 2
 #define GRP_CFG(PW, PH) if (e == cudaSuccess) e = grp_configure<PW, PH, 1>(); if (e == cudaSuccess) e = grp_configure<PW, PH, 2>(); \
-	if (e == cudaSuccess) e = grp_configure<PW, PH, GRP_MAX_PACK>();
+	if (e == cudaSuccess) e = grp_configure<PW, PH, GRP_MMA_PACK>();
 #else
 #define GRP_CFG(PW, PH) if (e == cudaSuccess) e = grp_configure<PW, PH, 1>(); if (e == cudaSuccess) e = grp_configure<PW, PH, 2>();
 #endif
 	GRP_SIZES(GRP_CFG)
 #undef GRP_CFG
+	if (e == cudaSuccess) return group_tc_configure_all();
 	return (int)e;
 }
 
@@ -569,16 +511,36 @@ static void grp_launch(cudaStream_t st, const GroupArgs& args) {
 	wvm_group_kernel<PW, PH, MSUB><<<blocks, GRP_WARPS * 32, GRP_SMEM, st>>>(args);
 }
 
-void launch_wvm_group(cudaStream_t st, int pw, int ph, int pack, const GroupArgs& args) {
+void launch_wvm_group_mma(cudaStream_t st, int pw, int ph, int pack, const GroupArgs& args) {
 	if (args.n_items == 0 || args.n_frames == 0) return;
-#if GRP_MAX_PACK > 2
+#if GRP_MMA_PACK > 2
 #define GRP_CASE(PW, PH) if (pw == PW && ph == PH) { if (pack <= 1) grp_launch<PW, PH, 1>(st, args); else if (pack == 2) grp_launch<PW, PH, 2>(st, args); \
-	else grp_launch<PW, PH, GRP_MAX_PACK>(st, args); return; }
+	else grp_launch<PW, PH, GRP_MMA_PACK>(st, args); return; }
 #else
 #define GRP_CASE(PW, PH) if (pw == PW && ph == PH) { if (pack <= 1) grp_launch<PW, PH, 1>(st, args); else grp_launch<PW, PH, 2>(st, args); return; }
 #endif
 	GRP_SIZES(GRP_CASE)
 #undef GRP_CASE
+}
+
+/* which window kernel runs a pack: measured on the B200 (profiles/), the mma.sync kernel wins for packs of one and two models
+ * (16 independent warps per SM hide the table look-up latency best), the tcgen05 kernel for packs of three and four (one
+ * equalisation and one A operand for up to four models; accumulators in tensor memory). FDB_WINDOW_KERNEL=mma | tc forces one. */
+static int group_kernel_choice() { /* 0: by pack size, 1: mma.sync only, 2: tcgen05 only */
+	static int choice = -1;
+	if (choice < 0) {
+		const char* e = std::getenv("FDB_WINDOW_KERNEL");
+		choice = !e ? 0 : (e[0] == 'm' ? 1 : (e[0] == 't' ? 2 : 0));
+	}
+	return choice;
+}
+
+int group_max_pack() { return group_kernel_choice() == 1 ? GRP_MMA_PACK : GRP_MAX_PACK; }
+
+void launch_wvm_group(cudaStream_t st, int pw, int ph, int pack, const GroupArgs& args) {
+	const int choice = group_kernel_choice();
+	if (choice == 2 || (choice == 0 && pack > GRP_MMA_PACK)) launch_wvm_group_tc(st, pw, ph, pack, args);
+	else launch_wvm_group_mma(st, pw, ph, pack, args);
 }
 
 void launch_wvm_deep_group(cudaStream_t st, const DeepArgs& args) {

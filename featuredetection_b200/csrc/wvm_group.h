@@ -19,7 +19,7 @@ namespace fdb {
 
 #define GRP_MAX_MODELS 16 /* detectors per launch (ffpDetectApp: 15) */
 #ifndef GRP_MAX_PACK
-#define GRP_MAX_PACK 2    /* models sharing one equalisation inside the window kernel (register accumulators: 32 per model) */
+#define GRP_MAX_PACK 4    /* models sharing one equalisation inside the window kernel (accumulators in tensor memory: 32 columns per model) */
 #endif
 
 struct GroupModel {       /* one detector's stage-1 classifier and where its results go */
@@ -68,9 +68,14 @@ struct DeepArgs {
 };
 
 int group_configure_all();
+int group_tc_configure_all();
+/* models per pack: GRP_MAX_PACK, or 2 when FDB_WINDOW_KERNEL=mma rules the tcgen05 kernel out */
+int group_max_pack();
 bool group_supported(int patch_w, int patch_h);
 /* window kernel over args.items (all of one window size, packs of at most `pack` models) */
 void launch_wvm_group(cudaStream_t st, int patch_w, int patch_h, int pack, const GroupArgs& args);
+void launch_wvm_group_mma(cudaStream_t st, int patch_w, int patch_h, int pack, const GroupArgs& args);
+void launch_wvm_group_tc(cudaStream_t st, int patch_w, int patch_h, int pack, const GroupArgs& args);
 /* the rest of the cascade for every queued survivor of every model of the table: one launch */
 void launch_wvm_deep_group(cudaStream_t st, const DeepArgs& args);
 
