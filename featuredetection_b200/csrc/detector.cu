@@ -150,13 +150,13 @@ bool encode_tile_maps(const std::vector<PyrImage>& images, const std::vector<int
 
 /* work items of the group kernel for one layer: strips of <= 32 window columns; narrow layers pack several row runs side
  * by side (all 32 lanes busy), the runs share the tile's rows. Balanced run length: the same number of window rows for
- * every lane of the layer. One item per strip and pack of <= group_max_pack() models. */
+ * every lane of the layer. One item per strip and pack of <= max_pack models. */
 void append_strip_items(const PlanLayer& L, int image, int patch_h, int n_models, const int* models, const int* first_windows,
-		std::vector<GroupItem>* out) {
+		int max_pack, std::vector<GroupItem>* out) {
 	if (L.windows_x <= 0 || L.windows_y <= 0) return;
 	const int budget = STRIP_TILE_ROWS - (patch_h - 1); /* window rows per tile */
 	/* balanced packs: 7 models -> 4 + 3, 5 -> 3 + 2 */
-	const int cap = group_max_pack(), npacks = (n_models + cap - 1) / cap;
+	const int cap = std::max(1, std::min(max_pack, GRP_MAX_PACK)), npacks = (n_models + cap - 1) / cap;
 	for (int pk = 0, m0 = 0; pk < npacks; ++pk) {
 		const int nm = n_models / npacks + (pk < n_models % npacks ? 1 : 0);
 		for (int ix0 = 0; ix0 < L.windows_x; ix0 += 32) {
@@ -221,7 +221,7 @@ int enqueue_stage1(fdb_detector* det, Slot& sl, cudaStream_t st, const uint8_t* 
 			ga.frames = d_frames; ga.W = W; ga.H = H; ga.arena = sl.d_arena; ga.arena_stride = plan.arena_bytes;
 			ga.cursor = sl.d_counters + 3;
 			ga.models[0] = gm;
-			launch_wvm_group(st, det->desc.patch_width, det->desc.patch_height, 1, ga);
+			launch_wvm_group(st, det->desc.patch_width, det->desc.patch_height, 1, ga, m.btc != nullptr);
 			if (marks) CUDA_TRY(cudaEventRecord(c->ev[5], st)); /* profiling mark between the two kernels */
 			DeepArgs da{};
 			da.images = det->d_gimages; da.frames = d_frames; da.W = W; da.H = H; da.arena = sl.d_arena; da.arena_stride = plan.arena_bytes;
@@ -961,7 +961,7 @@ int fdb_detector_prepare(fdb_detector* det, int32_t width, int32_t height, int32
 	if (det->use_strips)
 		for (size_t li = 0; li < plan.layers.size(); ++li) {
 			const int model0 = 0, first = (int)plan.layers[li].first_window;
-			append_strip_items(plan.layers[li], (int)li, det->desc.patch_height, 1, &model0, &first, &items);
+			append_strip_items(plan.layers[li], (int)li, det->desc.patch_height, 1, &model0, &first, 1, &items);
 		}
 	det->n_gitems = (int)items.size();
 	s = upload(items.data(), items.size(), &det->d_gitems, det->owned); if (s) return s;

@@ -115,7 +115,7 @@ int enqueue_pyramid(fdb_ctx* c, cudaStream_t st, const PyramidJobs& jobs, const 
  * arena_stride}); entries of the frame itself stay zero. false: the driver entry point is missing */
 bool encode_tile_maps(const std::vector<PyrImage>& images, const std::vector<int>& which, uint8_t* arena, int64_t arena_stride, int frames,
 		std::vector<CUtensorMap>* out);
-void append_strip_items(const PlanLayer& L, int image, int patch_h, int n_models, const int* models, const int* first_windows,
+void append_strip_items(const PlanLayer& L, int image, int patch_h, int n_models, const int* models, const int* first_windows, int max_pack,
 		std::vector<GroupItem>* out);
 void fill_detection(fdb_detection* d, const Plan& plan, const fdb_detector_desc& desc, int frame, int64_t window);
 int copy_out(const std::vector<fdb_detection>& dets, fdb_detection* out, int64_t cap, int64_t* n_out);

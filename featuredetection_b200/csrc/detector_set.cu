@@ -131,6 +131,7 @@ int host_thread_count() {
 
 struct SetLaunch {  /* one wvm_group_kernel launch: all strips of one window size and pack width */
 	int pw = 0, ph = 0, pack = 1;
+	bool tc_ok = false;   /* every model of the launch has the tcgen05 operand */
 	GroupItem* d_items = nullptr; int n_items = 0;
 };
 
@@ -243,7 +244,7 @@ int set_enqueue(fdb_detector_set* s, int si, fdb_window_score* const* dense_dev,
 	for (size_t k = 0; k < s->launches.size(); ++k) {
 		const SetLaunch& L = s->launches[k];
 		ga.items = L.d_items; ga.n_items = L.n_items; ga.cursor = ss.d_cursors + k;
-		launch_wvm_group(st, L.pw, L.ph, L.pack, ga);
+		launch_wvm_group(st, L.pw, L.ph, L.pack, ga, L.tc_ok);
 		c->launches++;
 	}
 	if (marks) CUDA_TRY(cudaEventRecord(marks[3], st));
@@ -263,7 +264,19 @@ int set_pipeline(fdb_detector_set* s, const uint8_t* frames, bool frames_on_devi
 	}
 	CUDA_TRY(cudaEventRecord(s->ev_begin, s->ctx->stream));
 	for (int i = 0; i < s->n_slots; ++i) CUDA_TRY(cudaStreamWaitEvent(s->slots[i].st, s->ev_begin, 0));
-	const int n_chunks = (n_frames + s->chunk - 1) / s->chunk;
+	/* chunk schedule: full chunks, the last one split into 1/2 + 1/4 + 1/4 - what follows the last chunk's stage 1 (its host
+	 * phases and the SVM kernels) overlaps nothing, so it should be short */
+	std::vector<std::pair<int, int>> chunks; /* (first frame, frames) */
+	for (int base = 0; base < n_frames; base += s->chunk) chunks.push_back(std::make_pair(base, std::min(s->chunk, n_frames - base)));
+	if (chunks.size() >= 2 && chunks.back().second >= 16) {
+		const std::pair<int, int> last = chunks.back();
+		chunks.pop_back();
+		const int half = last.second / 2, quarter = (last.second - half) / 2;
+		chunks.push_back(std::make_pair(last.first, half));
+		chunks.push_back(std::make_pair(last.first + half, quarter));
+		chunks.push_back(std::make_pair(last.first + half + quarter, last.second - half - quarter));
+	}
+	const int n_chunks = (int)chunks.size();
 	int enq = 0, a_done = 0, retired = 0;
 	auto do_a = [&]() -> int {
 		const int si = a_done % s->n_slots;
@@ -330,8 +343,8 @@ int set_pipeline(fdb_detector_set* s, const uint8_t* frames, bool frames_on_devi
 			r = do_b(); if (r) return r;
 		}
 		HostTimer* timer = new HostTimer(&s->host_ms[0]);
-		ss.base = enq * s->chunk;
-		ss.n = std::min(s->chunk, n_frames - ss.base);
+		ss.base = chunks[(size_t)enq].first;
+		ss.n = chunks[(size_t)enq].second;
 		ss.busy = true;
 		if (frames_on_device) ss.frames_dev = frames + (int64_t)ss.base * W * H;
 		else {
@@ -511,22 +524,27 @@ int fdb_detector_set_prepare(fdb_detector_set* s, int32_t width, int32_t height,
 					p.windows_x, p.windows_y)].push_back(std::make_pair(d, (int)li));
 		}
 	}
-	std::map<std::tuple<int, int, int>, std::vector<GroupItem>> by_launch; /* (patch w, h, pack) -> items */
+	std::map<std::tuple<int, int, int, int>, std::vector<GroupItem>> by_launch; /* (patch w, h, pack, tcgen05 operand present) -> items */
 	for (const auto& kv : grids) {
 		const int pw = std::get<0>(kv.first), ph = std::get<1>(kv.first), image = std::get<2>(kv.first);
-		std::vector<int> models, firsts;
-		for (const auto& ml : kv.second) {
-			models.push_back(ml.first);
-			firsts.push_back((int)s->dets[(size_t)ml.first]->plan.layers[(size_t)ml.second].first_window);
-		}
 		const PlanLayer& p = s->dets[(size_t)kv.second[0].first]->plan.layers[(size_t)kv.second[0].second];
-		std::vector<GroupItem> items;
-		append_strip_items(p, image, ph, (int)models.size(), models.data(), firsts.data(), &items);
-		for (const GroupItem& it : items) by_launch[std::make_tuple(pw, ph, it.nm > 2 ? GRP_MAX_PACK : it.nm /* kernel instances exist for packs of 1, 2 and GRP_MAX_PACK */)].push_back(it);
+		for (int tc = 1; tc >= 0; --tc) { /* models with the tcgen05 operand pack by four, the others by two */
+			std::vector<int> models, firsts;
+			for (const auto& ml : kv.second) {
+				if ((s->dets[(size_t)ml.first]->wvm->dev.btc != nullptr) != (tc == 1)) continue;
+				models.push_back(ml.first);
+				firsts.push_back((int)s->dets[(size_t)ml.first]->plan.layers[(size_t)ml.second].first_window);
+			}
+			if (models.empty()) continue;
+			std::vector<GroupItem> items;
+			append_strip_items(p, image, ph, (int)models.size(), models.data(), firsts.data(), group_max_pack(tc == 1), &items);
+			/* kernel instances exist for packs of 1, 2 and GRP_MAX_PACK */
+			for (const GroupItem& it : items) by_launch[std::make_tuple(pw, ph, it.nm > 2 ? GRP_MAX_PACK : it.nm, tc)].push_back(it);
+		}
 	}
 	for (auto& kv : by_launch) {
 		SetLaunch L;
-		L.pw = std::get<0>(kv.first); L.ph = std::get<1>(kv.first); L.pack = std::get<2>(kv.first);
+		L.pw = std::get<0>(kv.first); L.ph = std::get<1>(kv.first); L.pack = std::get<2>(kv.first); L.tc_ok = std::get<3>(kv.first) != 0;
 		/* pack-major order: consecutive units share the models' fragment tables (L1) */
 		std::stable_sort(kv.second.begin(), kv.second.end(), [](const GroupItem& a, const GroupItem& b) { return a.model[0] < b.model[0]; });
 		L.n_items = (int)kv.second.size();

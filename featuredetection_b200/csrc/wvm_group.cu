@@ -384,7 +384,10 @@ __global__ void __launch_bounds__(GDEEP_WARPS * 32) wvm_deep_group_kernel(const 
 	float* const hk = s_hk[warp];
 	float* const us = s_u[warp];
 	int* const ii = s_ii[warp];
-	const GroupModel& gm = a.models[blockIdx.y];
+	/* every CTA works through the queues of all models in turn: the queues differ in length by orders of magnitude (a face detector
+	 * scans a few small layers, a landmark detector three large ones), so a grid split by model would leave most CTAs idle */
+	for (int mi = 0; mi < a.n_models; ++mi) {
+	const GroupModel& gm = a.models[mi];
 	const DevWvm& m = gm.m;
 	const DeepQueue& q = gm.q;
 	const int n = min(*q.count, q.cap);
@@ -454,6 +457,7 @@ __global__ void __launch_bounds__(GDEEP_WARPS * 32) wvm_deep_group_kernel(const 
 		if (lane == 0)
 			wvm_emit(m, rec.frame, rec.window, gm.windows_per_frame, final_level, final_fout, gm.dense, gm.cand, gm.cand_count, gm.cand_cap);
 		__syncwarp();
+	}
 	}
 }
 
@@ -535,18 +539,17 @@ static int group_kernel_choice() { /* 0: by pack size, 1: mma.sync only, 2: tcge
 	return choice;
 }
 
-int group_max_pack() { return group_kernel_choice() == 1 ? GRP_MMA_PACK : GRP_MAX_PACK; }
+int group_max_pack(bool tc_ok) { return group_kernel_choice() == 1 || !tc_ok ? GRP_MMA_PACK : GRP_MAX_PACK; }
 
-void launch_wvm_group(cudaStream_t st, int pw, int ph, int pack, const GroupArgs& args) {
+void launch_wvm_group(cudaStream_t st, int pw, int ph, int pack, const GroupArgs& args, bool tc_ok) {
 	const int choice = group_kernel_choice();
-	if (choice == 2 || (choice == 0 && pack > GRP_MMA_PACK)) launch_wvm_group_tc(st, pw, ph, pack, args);
+	if (tc_ok && (choice == 2 || (choice == 0 && pack > GRP_MMA_PACK))) launch_wvm_group_tc(st, pw, ph, pack, args);
 	else launch_wvm_group_mma(st, pw, ph, pack, args);
 }
 
 void launch_wvm_deep_group(cudaStream_t st, const DeepArgs& args) {
 	if (args.n_models == 0) return;
-	dim3 grid((unsigned)(grp_sm_count() * 8 / std::max(1, std::min(args.n_models, 8))), (unsigned)args.n_models);
-	wvm_deep_group_kernel<<<grid, GDEEP_WARPS * 32, 0, st>>>(args);
+	wvm_deep_group_kernel<<<grp_sm_count() * 8, GDEEP_WARPS * 32, 0, st>>>(args);
 }
 
 } // namespace fdb

@@ -69,11 +69,12 @@ struct DeepArgs {
 
 int group_configure_all();
 int group_tc_configure_all();
-/* models per pack: GRP_MAX_PACK, or 2 when FDB_WINDOW_KERNEL=mma rules the tcgen05 kernel out */
-int group_max_pack();
+/* models per pack: GRP_MAX_PACK if every model has the tcgen05 operand (DevWvm::btc), or 2 - also when FDB_WINDOW_KERNEL=mma
+ * rules the tcgen05 kernel out */
+int group_max_pack(bool tc_ok);
 bool group_supported(int patch_w, int patch_h);
-/* window kernel over args.items (all of one window size, packs of at most `pack` models) */
-void launch_wvm_group(cudaStream_t st, int patch_w, int patch_h, int pack, const GroupArgs& args);
+/* window kernel over args.items (all of one window size, packs of at most `pack` models); tc_ok: every model has DevWvm::btc */
+void launch_wvm_group(cudaStream_t st, int patch_w, int patch_h, int pack, const GroupArgs& args, bool tc_ok);
 void launch_wvm_group_mma(cudaStream_t st, int patch_w, int patch_h, int pack, const GroupArgs& args);
 void launch_wvm_group_tc(cudaStream_t st, int patch_w, int patch_h, int pack, const GroupArgs& args);
 /* the rest of the cascade for every queued survivor of every model of the table: one launch */

@@ -17,11 +17,9 @@
 namespace fdb {
 
 /* acc[v] = exact integer sum over the rectangles of grey value v+1 (v < nv).
- * *un is u_kernel_eval[level % per_level] (read, then overwritten, :313-314).
- * Returns hk_kernel_eval[level] (:333). */
+ * Returns sum_xp after :313 (the value u_kernel_eval[level % per_level] takes at :314, as a double). */
 template <int MAXV>
-__device__ __forceinline__ float wvm_kernel_value(const DevWvm& m, int level, const uint32_t* acc, int nv,
-		float total_f, float sum_xx, float* un) {
+__device__ __forceinline__ double wvm_sum_xp(const DevWvm& m, int level, const uint32_t* acc, int nv, float total_f, float un) {
 	const double* __restrict__ val = m.val + __ldg(m.val_off + level);
 	float sumv0 = total_f;
 	double sum_xp = 0.0;
@@ -33,7 +31,15 @@ __device__ __forceinline__ float wvm_kernel_value(const DevWvm& m, int level, co
 			sum_xp = __dadd_rn(sum_xp, __dmul_rn((double)sumv, __ldg(val + v + 1))); /* :309 */
 		}
 	sum_xp = __dadd_rn(sum_xp, __dmul_rn((double)sumv0, __ldg(val)));                /* :312 */
-	sum_xp = __dadd_rn(sum_xp, (double)*un);                                         /* :313 */
+	return __dadd_rn(sum_xp, (double)un);                                            /* :313 */
+}
+
+/* *un is u_kernel_eval[level % per_level] (read, then overwritten, :313-314).
+ * Returns hk_kernel_eval[level] (:333). */
+template <int MAXV>
+__device__ __forceinline__ float wvm_kernel_value(const DevWvm& m, int level, const uint32_t* acc, int nv,
+		float total_f, float sum_xx, float* un) {
+	const double sum_xp = wvm_sum_xp<MAXV>(m, level, acc, nv, total_f, *un);
 	*un = (float)sum_xp;                                                             /* :314 */
 	double norm = __dsub_rn((double)sum_xx, __dmul_rn(2.0, sum_xp));                 /* :316 */
 	norm = __dadd_rn(norm, __ldg(m.app_rsv_convol + level));                         /* :322 */

@@ -1,0 +1,7 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_detector_set.py tests/test_gpu_parity.py -x -q -m gpu 2>&1 | tail -3
+timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/r2z_bench.json 2> gpurun_out/r2z_bench.err; tail -2 gpurun_out/r2z_bench.err
+python -c "
+import json; d=json.load(open('gpurun_out/r2z_bench.json')); print('bench', '%.4g' % d['value'], '%.4g' % d['e2e']['value'], d['ms_per_step'], d['e2e']['ms_per_step'], d['stage1_ms'], d['host_ms_last_step'], d.get('facefrontal'))"
+nvidia-smi --query-gpu=memory.used --format=csv
