@@ -1328,13 +1328,15 @@ def main():
             "e2e": {"value": e2e_value, "unit": "patches/s", "h2d_bytes_per_step": int(W * H * n),
                     "d2h_bytes_per_step": m["d2h"], "ms_per_step": m["e2e_total"] / args.steps, "frames_per_s": e2e_value / nwin},
             "gpu_launches": m["launches"],
-            "roofline": {"bound": "hbm", "kernel": "wvm_group_kernel (fused HistEq64 + the first 8 WVM filters of every window of every detector as exact u8 "
-                                                   "IMMA products; %d launches per step, timed together)" % int(n_launch),
+            "roofline": {"bound": "hbm", "kernel": "window kernels: wvm_group_tc_kernel (tcgen05.mma kind::i8, packs of 3-4 detectors) + wvm_group_kernel "
+                                                   "(mma.sync u8, packs of 1-2): fused HistEq64 + the first 8 WVM filters of every window of every detector "
+                                                   "as exact u8 matrix products; %d launches per step, timed together" % int(n_launch),
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "traffic_source": traffic_src, "peak_source": peak_src, "algorithmic_bytes_per_step": int(algo_bytes),
                          "kernel_ms_per_step": float(ms_wvm), "launches_per_step": int(n_launch),
-                         "note": "instruction-issue / shared-memory bound by construction: ~6e3 warp instructions per 32 windows vs 8 B of compulsory "
-                                 "traffic per window (SURVEY.md 8(d)); issue-slot utilisation and pipe shares in profiles/"},
+                         "note": "instruction-issue / shared-memory bound by construction: ~4e3 warp instructions per 32 windows (shared by the "
+                                 "detectors of a pack) + ~1e3 per detector vs 8 B of compulsory traffic per window (SURVEY.md 8(d)); issue-slot "
+                                 "utilisation, load/store-pipe wavefronts and pipe shares in profiles/"},
             "stage1_ms": {"resize": float(ms_resize), "pyrdown": float(ms_down), "window_kernels": float(ms_wvm), "deep_kernel": float(ms_deep),
                           "total": float(ms_stage1)},
             "detector_set": m["info"],

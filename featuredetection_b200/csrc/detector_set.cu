@@ -40,8 +40,11 @@ using namespace fdb;
 
 namespace {
 
+#define SET_SIDE_STREAMS 2
 struct SetSlot {
 	cudaStream_t st = nullptr;
+	cudaStream_t side[SET_SIDE_STREAMS] = {nullptr, nullptr}; /* the window launches of a chunk are independent: run side by side, one */
+	cudaEvent_t ev_fork = nullptr, ev_join[SET_SIDE_STREAMS] = {nullptr, nullptr}; /* kernel's CTAs fill the SMs another one drains */
 	uint8_t* d_frames = nullptr;
 	uint8_t* d_arena = nullptr;
 	CUtensorMap* d_tmaps = nullptr; /* one per union image */
@@ -165,6 +168,11 @@ namespace {
 void set_release(fdb_detector_set* s) {
 	for (SetSlot& sl : s->slots) {
 		if (sl.st) { cudaStreamSynchronize(sl.st); cudaStreamDestroy(sl.st); }
+		for (int k = 0; k < SET_SIDE_STREAMS; ++k) {
+			if (sl.side[k]) { cudaStreamSynchronize(sl.side[k]); cudaStreamDestroy(sl.side[k]); sl.side[k] = nullptr; }
+			if (sl.ev_join[k]) { cudaEventDestroy(sl.ev_join[k]); sl.ev_join[k] = nullptr; }
+		}
+		if (sl.ev_fork) { cudaEventDestroy(sl.ev_fork); sl.ev_fork = nullptr; }
 		sl = SetSlot();
 	}
 	if (s->ev_begin) { cudaEventDestroy(s->ev_begin); s->ev_begin = nullptr; }
@@ -217,6 +225,58 @@ GroupModel member_model(const fdb_detector_set* s, int d, const Slot& msl, fdb_w
 	return gm;
 }
 
+/* work items of the window kernels for the members on the group path (s->fast): windows of the same image, size and grid are
+ * equalised once for all members that scan them. Called at prepare and again when a member leaves the group path. */
+int set_build_launches(fdb_detector_set* s) {
+	const int nd = (int)s->dets.size();
+	int r = FDB_OK;
+	s->launches.clear();
+	typedef std::tuple<int, int, int, int, int, int, int> GridKey; /* patch w, h, union image, begin x, y, windows x, y */
+	std::map<GridKey, std::vector<std::pair<int, int>>> grids;     /* -> (member, layer) */
+	for (int d = 0; d < nd; ++d) {
+		if (!s->fast[(size_t)d]) continue;
+		const fdb_detector* det = s->dets[(size_t)d];
+		for (size_t li = 0; li < det->plan.layers.size(); ++li) {
+			const PlanLayer& p = det->plan.layers[li];
+			if (p.windows_x <= 0 || p.windows_y <= 0) continue;
+			grids[GridKey(det->desc.patch_width, det->desc.patch_height, s->umap[(size_t)d][(size_t)p.image], p.begin_x, p.begin_y,
+					p.windows_x, p.windows_y)].push_back(std::make_pair(d, (int)li));
+		}
+	}
+	std::map<std::tuple<int, int, int, int>, std::vector<GroupItem>> by_launch; /* (patch w, h, pack, tcgen05 operand present) -> items */
+	for (const auto& kv : grids) {
+		const int pw = std::get<0>(kv.first), ph = std::get<1>(kv.first), image = std::get<2>(kv.first);
+		const PlanLayer& p = s->dets[(size_t)kv.second[0].first]->plan.layers[(size_t)kv.second[0].second];
+		for (int tc = 1; tc >= 0; --tc) { /* models with the tcgen05 operand pack by four, the others by two */
+			std::vector<int> models, firsts;
+			for (const auto& ml : kv.second) {
+				if ((s->dets[(size_t)ml.first]->wvm->dev.btc != nullptr) != (tc == 1)) continue;
+				models.push_back(ml.first);
+				firsts.push_back((int)s->dets[(size_t)ml.first]->plan.layers[(size_t)ml.second].first_window);
+			}
+			if (models.empty()) continue;
+			std::vector<GroupItem> items;
+			append_strip_items(p, image, ph, (int)models.size(), models.data(), firsts.data(), group_max_pack(tc == 1), &items);
+			/* kernel instances exist for packs of 1, 2 and GRP_MAX_PACK */
+			for (const GroupItem& it : items) by_launch[std::make_tuple(pw, ph, it.nm > 2 ? GRP_MAX_PACK : it.nm, tc)].push_back(it);
+		}
+	}
+	for (auto& kv : by_launch) {
+		SetLaunch L;
+		L.pw = std::get<0>(kv.first); L.ph = std::get<1>(kv.first); L.pack = std::get<2>(kv.first); L.tc_ok = std::get<3>(kv.first) != 0;
+		/* pack-major order: consecutive units share the models' fragment tables (L1) */
+		std::stable_sort(kv.second.begin(), kv.second.end(), [](const GroupItem& a, const GroupItem& b) { return a.model[0] < b.model[0]; });
+		L.n_items = (int)kv.second.size();
+		r = upload(kv.second.data(), kv.second.size(), &L.d_items, s->owned); if (r) return r;
+		s->launches.push_back(L);
+	}
+	if (s->launches.size() > 16) return fail(FDB_ERR_UNSUPPORTED, "more than 16 window-size classes in a detector set");
+	/* longest first: the launches run on a few streams side by side, the short ones fill the SMs the long ones drain */
+	std::stable_sort(s->launches.begin(), s->launches.end(), [](const SetLaunch& a, const SetLaunch& b) {
+		return (int64_t)a.n_items * a.ph * a.pack > (int64_t)b.n_items * b.ph * b.pack; });
+	return FDB_OK;
+}
+
 /* pyramid + stage 1 of every fast member for the chunk of slot si; ev (optional): marks after resize, pyrDown, window kernels */
 int set_enqueue(fdb_detector_set* s, int si, fdb_window_score* const* dense_dev, cudaEvent_t* marks) {
 	SetSlot& ss = s->slots[si];
@@ -241,12 +301,24 @@ int set_enqueue(fdb_detector_set* s, int si, fdb_window_score* const* dense_dev,
 		ga.models[d] = member_model(s, d, det->slots[si], dense);
 		da.models[da.n_models++] = ga.models[d];
 	}
+	/* the window launches only share atomic counters: launch k goes to stream k mod (1 + SET_SIDE_STREAMS), joined before the deep kernel */
+	const bool fork = !marks && s->launches.size() > 1;
+	if (fork) {
+		CUDA_TRY(cudaEventRecord(ss.ev_fork, st));
+		for (int k = 0; k < SET_SIDE_STREAMS; ++k) CUDA_TRY(cudaStreamWaitEvent(ss.side[k], ss.ev_fork, 0));
+	}
 	for (size_t k = 0; k < s->launches.size(); ++k) {
 		const SetLaunch& L = s->launches[k];
 		ga.items = L.d_items; ga.n_items = L.n_items; ga.cursor = ss.d_cursors + k;
-		launch_wvm_group(st, L.pw, L.ph, L.pack, ga, L.tc_ok);
+		const int lane = fork ? (int)(k % (1 + SET_SIDE_STREAMS)) : 0;
+		launch_wvm_group(lane == 0 ? st : ss.side[lane - 1], L.pw, L.ph, L.pack, ga, L.tc_ok);
 		c->launches++;
 	}
+	if (fork)
+		for (int k = 0; k < SET_SIDE_STREAMS; ++k) {
+			CUDA_TRY(cudaEventRecord(ss.ev_join[k], ss.side[k]));
+			CUDA_TRY(cudaStreamWaitEvent(st, ss.ev_join[k], 0));
+		}
 	if (marks) CUDA_TRY(cudaEventRecord(marks[3], st));
 	if (da.n_models) { launch_wvm_deep_group(st, da); c->launches++; }
 	if (marks) CUDA_TRY(cudaEventRecord(marks[4], st));
@@ -395,6 +467,7 @@ int set_detect(fdb_detector_set* s, const uint8_t* frames, bool frames_on_device
 		if (r != STATUS_REDO) break;
 		/* a member's deep queue overflowed (phase_a took it off the fast path): it runs alone from now on */
 		for (int d = 0; d < nd; ++d) if (s->fast[(size_t)d] && !s->dets[(size_t)d]->use_strips) s->fast[(size_t)d] = 0;
+		r = set_build_launches(s); if (r) return r; /* the packs must not name a member that left */
 	}
 	if (r) return r;
 	if (std::getenv("FDB_SET_TRACE"))
@@ -469,6 +542,11 @@ int fdb_detector_set_prepare(fdb_detector_set* s, int32_t width, int32_t height,
 	for (int i = 0; i < s->n_slots; ++i) {
 		SetSlot& sl = s->slots[i];
 		CUDA_TRY(cudaStreamCreateWithFlags(&sl.st, cudaStreamNonBlocking));
+		CUDA_TRY(cudaEventCreateWithFlags(&sl.ev_fork, cudaEventDisableTiming));
+		for (int k = 0; k < SET_SIDE_STREAMS; ++k) {
+			CUDA_TRY(cudaStreamCreateWithFlags(&sl.side[k], cudaStreamNonBlocking));
+			CUDA_TRY(cudaEventCreateWithFlags(&sl.ev_join[k], cudaEventDisableTiming));
+		}
 		r = dev_alloc(&sl.d_frames, (size_t)s->chunk * width * height, s->owned); if (r) return r;
 		r = dev_alloc(&sl.d_arena, (size_t)s->chunk * (size_t)s->arena_bytes, s->owned); if (r) return r;
 		r = dev_alloc(&sl.d_cursors, 64, s->owned); if (r) return r;
@@ -511,47 +589,7 @@ int fdb_detector_set_prepare(fdb_detector_set* s, int32_t width, int32_t height,
 		}
 		r = upload(L.data(), L.size(), &s->d_layers[(size_t)d], s->owned); if (r) return r;
 	}
-	/* work items: windows of the same image, size and grid are equalised once for all members that scan them */
-	typedef std::tuple<int, int, int, int, int, int, int> GridKey; /* patch w, h, union image, begin x, y, windows x, y */
-	std::map<GridKey, std::vector<std::pair<int, int>>> grids;     /* -> (member, layer) */
-	for (int d = 0; d < nd; ++d) {
-		if (!s->fast[(size_t)d]) continue;
-		const fdb_detector* det = s->dets[(size_t)d];
-		for (size_t li = 0; li < det->plan.layers.size(); ++li) {
-			const PlanLayer& p = det->plan.layers[li];
-			if (p.windows_x <= 0 || p.windows_y <= 0) continue;
-			grids[GridKey(det->desc.patch_width, det->desc.patch_height, s->umap[(size_t)d][(size_t)p.image], p.begin_x, p.begin_y,
-					p.windows_x, p.windows_y)].push_back(std::make_pair(d, (int)li));
-		}
-	}
-	std::map<std::tuple<int, int, int, int>, std::vector<GroupItem>> by_launch; /* (patch w, h, pack, tcgen05 operand present) -> items */
-	for (const auto& kv : grids) {
-		const int pw = std::get<0>(kv.first), ph = std::get<1>(kv.first), image = std::get<2>(kv.first);
-		const PlanLayer& p = s->dets[(size_t)kv.second[0].first]->plan.layers[(size_t)kv.second[0].second];
-		for (int tc = 1; tc >= 0; --tc) { /* models with the tcgen05 operand pack by four, the others by two */
-			std::vector<int> models, firsts;
-			for (const auto& ml : kv.second) {
-				if ((s->dets[(size_t)ml.first]->wvm->dev.btc != nullptr) != (tc == 1)) continue;
-				models.push_back(ml.first);
-				firsts.push_back((int)s->dets[(size_t)ml.first]->plan.layers[(size_t)ml.second].first_window);
-			}
-			if (models.empty()) continue;
-			std::vector<GroupItem> items;
-			append_strip_items(p, image, ph, (int)models.size(), models.data(), firsts.data(), group_max_pack(tc == 1), &items);
-			/* kernel instances exist for packs of 1, 2 and GRP_MAX_PACK */
-			for (const GroupItem& it : items) by_launch[std::make_tuple(pw, ph, it.nm > 2 ? GRP_MAX_PACK : it.nm, tc)].push_back(it);
-		}
-	}
-	for (auto& kv : by_launch) {
-		SetLaunch L;
-		L.pw = std::get<0>(kv.first); L.ph = std::get<1>(kv.first); L.pack = std::get<2>(kv.first); L.tc_ok = std::get<3>(kv.first) != 0;
-		/* pack-major order: consecutive units share the models' fragment tables (L1) */
-		std::stable_sort(kv.second.begin(), kv.second.end(), [](const GroupItem& a, const GroupItem& b) { return a.model[0] < b.model[0]; });
-		L.n_items = (int)kv.second.size();
-		r = upload(kv.second.data(), kv.second.size(), &L.d_items, s->owned); if (r) return r;
-		s->launches.push_back(L);
-	}
-	if (s->launches.size() > 16) return fail(FDB_ERR_UNSUPPORTED, "more than 16 window-size classes in a detector set");
+	r = set_build_launches(s); if (r) return r;
 	s->prepared = true;
 	return FDB_OK;
 } FDB_API_CATCH

@@ -530,13 +530,9 @@ void launch_wvm_group_mma(cudaStream_t st, int pw, int ph, int pack, const Group
 /* which window kernel runs a pack: measured on the B200 (profiles/), the mma.sync kernel wins for packs of one and two models
  * (16 independent warps per SM hide the table look-up latency best), the tcgen05 kernel for packs of three and four (one
  * equalisation and one A operand for up to four models; accumulators in tensor memory). FDB_WINDOW_KERNEL=mma | tc forces one. */
-static int group_kernel_choice() { /* 0: by pack size, 1: mma.sync only, 2: tcgen05 only */
-	static int choice = -1;
-	if (choice < 0) {
-		const char* e = std::getenv("FDB_WINDOW_KERNEL");
-		choice = !e ? 0 : (e[0] == 'm' ? 1 : (e[0] == 't' ? 2 : 0));
-	}
-	return choice;
+static int group_kernel_choice() { /* 0: by pack size, 1: mma.sync only, 2: tcgen05 only; read at every call (tests switch it) */
+	const char* e = std::getenv("FDB_WINDOW_KERNEL");
+	return !e ? 0 : (e[0] == 'm' ? 1 : (e[0] == 't' ? 2 : 0));
 }
 
 int group_max_pack(bool tc_ok) { return group_kernel_choice() == 1 || !tc_ok ? GRP_MMA_PACK : GRP_MAX_PACK; }

@@ -155,3 +155,55 @@ def test_set_argument_errors(ctx):
     dset.width, dset.height = 640, 480  # not prepared: the library refuses
     with pytest.raises(capi.FdbError):
         dset.detect(np.zeros((1, 480, 640), np.uint8))
+
+
+@pytest.mark.gpu
+def test_both_window_kernels_return_the_same_records(ctx, fifteen, monkeypatch):
+    """wvm_group_tc.cu (tcgen05, packs of up to four models) and wvm_group.cu (mma.sync, packs of two) are two schedules of the same
+    arithmetic: dense stage-1 records (float bits and levels) and detections must be identical, also for a frame count that
+    leaves the last group of four frames incomplete. FDB_WINDOW_KERNEL is read at prepare (packing) and at every launch."""
+    import torch
+    models, cascs, dset = fifteen
+    frames = syn.synthetic_frames(90, 5)
+    dev = torch.from_numpy(frames).cuda()
+    got = {}
+    for choice in ("mma", "tc", None):
+        if choice is None:
+            monkeypatch.delenv("FDB_WINDOW_KERNEL", raising=False)
+        else:
+            monkeypatch.setenv("FDB_WINDOW_KERNEL", choice)
+        dset.prepare(640, 480, 5)
+        dense, ptrs = _dense_buffers(cascs, 5)
+        dets = dset.detect_device(dev.data_ptr(), 5, stage=capi.FDB_STAGE_NMS, dense_ptrs=ptrs)
+        torch.cuda.synchronize()
+        got[choice] = (dets, [b.cpu().numpy() for b in dense])
+    for choice in ("tc", None):
+        assert np.array_equal(got[choice][0], got["mma"][0]), choice
+        for d in range(len(cascs)):
+            assert np.array_equal(got[choice][1][d], got["mma"][1][d]), (choice, NAMES[d])
+
+
+@pytest.mark.gpu
+def test_packs_of_three_without_early_exit(ctx, monkeypatch):
+    """three models of one geometry whose cascades never reject (every window reaches the deep kernel's queue, which overflows and
+    sends the members down the generic path): the set still equals its members, on either window kernel"""
+    names = ("LeftLipCorner", "RightLipCorner", "LeftNoseCorner")
+    models = [syn.landmark_models(nm, profile="no-exit") for nm in names]
+    frames = syn.synthetic_frames(95, 2)[:, :120, :160].copy()
+    ref = None
+    for choice in ("mma", "tc"):
+        monkeypatch.setenv("FDB_WINDOW_KERNEL", choice)
+        cascs = [SlidingWindowCascade(ctx, dict(kw, min_scale_factor=0.5, max_scale_factor=1.0, max_positives_per_frame=65536), wvm, svm)
+                 for kw, wvm, svm in models]
+        dset = DetectorSet(ctx, cascs)
+        dset.prepare(160, 120, 2)
+        dets = dset.detect(frames, stage=capi.FDB_STAGE_WVM, det_cap=1 << 20)
+        for d, c in enumerate(cascs):
+            own = c.detect(frames, stage=capi.FDB_STAGE_WVM, det_cap=1 << 20)
+            mine = dets[dets["reserved"] == d].copy()
+            mine["reserved"] = 0
+            assert mine.tobytes() == own.tobytes(), (choice, names[d])  # bytes: stage-1 records carry NaN for the SVM fields
+        if ref is None:
+            ref = dets
+        else:
+            assert dets.tobytes() == ref.tobytes()
