@@ -336,17 +336,19 @@ int set_pipeline(fdb_detector_set* s, const uint8_t* frames, bool frames_on_devi
 	}
 	CUDA_TRY(cudaEventRecord(s->ev_begin, s->ctx->stream));
 	for (int i = 0; i < s->n_slots; ++i) CUDA_TRY(cudaStreamWaitEvent(s->slots[i].st, s->ev_begin, 0));
-	/* chunk schedule: full chunks, the last one split into 1/2 + 1/4 + 1/4 - what follows the last chunk's stage 1 (its host
+	/* chunk schedule: full chunks, the last one split into 1/2 + 1/4 + 1/8 + 1/8 - what follows the last chunk's stage 1 (its host
 	 * phases and the SVM kernels) overlaps nothing, so it should be short */
 	std::vector<std::pair<int, int>> chunks; /* (first frame, frames) */
 	for (int base = 0; base < n_frames; base += s->chunk) chunks.push_back(std::make_pair(base, std::min(s->chunk, n_frames - base)));
 	if (chunks.size() >= 2 && chunks.back().second >= 16) {
-		const std::pair<int, int> last = chunks.back();
+		std::pair<int, int> rest = chunks.back();
 		chunks.pop_back();
-		const int half = last.second / 2, quarter = (last.second - half) / 2;
-		chunks.push_back(std::make_pair(last.first, half));
-		chunks.push_back(std::make_pair(last.first + half, quarter));
-		chunks.push_back(std::make_pair(last.first + half + quarter, last.second - half - quarter));
+		while (rest.second >= 16) { /* pieces of at least 8 frames: two groups of four for the tcgen05 kernel */
+			const int half = rest.second / 2;
+			chunks.push_back(std::make_pair(rest.first, half));
+			rest = std::make_pair(rest.first + half, rest.second - half);
+		}
+		chunks.push_back(rest);
 	}
 	const int n_chunks = (int)chunks.size();
 	int enq = 0, a_done = 0, retired = 0;
