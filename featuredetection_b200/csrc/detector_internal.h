@@ -16,7 +16,7 @@
 #include "features_device.h"
 #include "wvm_group.h"
 
-#define PIPE_SLOTS 3
+#define PIPE_SLOTS 4
 #define FDB_NCOUNTERS 8 /* per-slot device counters: [0] candidates, [1] deep queue, [2] deep cursor, [3] group-kernel cursor */
 #define OPT_CAND 4096 /* smallest candidate list capacity; det->opt_cand (<= 65536) candidates are fetched together with the counters (one D2H in stream order), more need a second copy */
 #define FEAT_BATCH 8192 /* feature vectors materialised at a time (feature-space SVM stage) */

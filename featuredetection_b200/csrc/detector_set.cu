@@ -45,6 +45,7 @@ struct SetSlot {
 	cudaStream_t st = nullptr;
 	cudaStream_t side[SET_SIDE_STREAMS] = {nullptr, nullptr}; /* the window launches of a chunk are independent: run side by side, one */
 	cudaEvent_t ev_fork = nullptr, ev_join[SET_SIDE_STREAMS] = {nullptr, nullptr}; /* kernel's CTAs fill the SMs another one drains */
+	cudaEvent_t ev_s1_end = nullptr; /* the chunk's deep kernel is done: the next chunk's stage 1 may start */
 	uint8_t* d_frames = nullptr;
 	uint8_t* d_arena = nullptr;
 	CUtensorMap* d_tmaps = nullptr; /* one per union image */
@@ -129,7 +130,7 @@ int host_thread_count() {
 	cpu_set_t set;
 	if (sched_getaffinity(0, sizeof(set), &set) == 0) n = CPU_COUNT(&set); /* a rank pinned to its share of the cores uses only those */
 #endif
-	return std::max(1, std::min(n, 8));
+	return std::max(1, std::min(n, 16));
 }
 
 struct SetLaunch {  /* one wvm_group_kernel launch: all strips of one window size and pack width */
@@ -157,6 +158,8 @@ struct fdb_detector_set {
 	bool use_tma = false;
 	SetSlot slots[PIPE_SLOTS];
 	cudaEvent_t ev_begin = nullptr;
+	std::vector<cudaEvent_t> trace_ev;   /* FDB_SET_TRACE: begin / end of stage 1 per chunk, timing enabled */
+	bool trace = false;
 	std::vector<void*> owned, owned_host;
 	int64_t windows = 0;                /* per frame, all members */
 	HostPool* pool = nullptr;           /* host threads of the members' post-processing */
@@ -173,6 +176,7 @@ void set_release(fdb_detector_set* s) {
 			if (sl.ev_join[k]) { cudaEventDestroy(sl.ev_join[k]); sl.ev_join[k] = nullptr; }
 		}
 		if (sl.ev_fork) { cudaEventDestroy(sl.ev_fork); sl.ev_fork = nullptr; }
+		if (sl.ev_s1_end) { cudaEventDestroy(sl.ev_s1_end); sl.ev_s1_end = nullptr; }
 		sl = SetSlot();
 	}
 	if (s->ev_begin) { cudaEventDestroy(s->ev_begin); s->ev_begin = nullptr; }
@@ -286,6 +290,12 @@ int set_enqueue(fdb_detector_set* s, int si, fdb_window_score* const* dense_dev,
 	if (!s->launches.empty()) CUDA_TRY(cudaMemsetAsync(ss.d_cursors, 0, sizeof(int) * s->launches.size(), st));
 	for (int d = 0; d < nd; ++d) if (s->fast[(size_t)d]) CUDA_TRY(cudaMemsetAsync(s->dets[(size_t)d]->slots[si].d_counters, 0, FDB_NCOUNTERS * sizeof(int), st));
 	if (marks) CUDA_TRY(cudaEventRecord(marks[0], st));
+	if (s->trace && !marks) {
+		cudaEvent_t e0, e1;
+		CUDA_TRY(cudaEventCreate(&e0)); CUDA_TRY(cudaEventCreate(&e1));
+		s->trace_ev.push_back(e0); s->trace_ev.push_back(e1);
+		CUDA_TRY(cudaEventRecord(e0, st));
+	}
 	{ const int r = enqueue_pyramid(c, st, s->jobs, ss.frames_dev, s->W, s->H, ss.n, ss.d_arena, s->arena_bytes, marks ? marks[1] : nullptr); if (r) return r; }
 	if (marks) CUDA_TRY(cudaEventRecord(marks[2], st));
 	GroupArgs ga{};
@@ -322,6 +332,7 @@ int set_enqueue(fdb_detector_set* s, int si, fdb_window_score* const* dense_dev,
 	if (marks) CUDA_TRY(cudaEventRecord(marks[3], st));
 	if (da.n_models) { launch_wvm_deep_group(st, da); c->launches++; }
 	if (marks) CUDA_TRY(cudaEventRecord(marks[4], st));
+	if (s->trace && !marks) CUDA_TRY(cudaEventRecord(s->trace_ev.back(), st));
 	CUDA_TRY(cudaGetLastError());
 	return FDB_OK;
 }
@@ -409,14 +420,10 @@ int set_pipeline(fdb_detector_set* s, const uint8_t* frames, bool frames_on_devi
 		return FDB_OK;
 	};
 	int r = FDB_OK;
-	while (enq < n_chunks) {
+	auto enqueue_next = [&]() -> int {
+		HostTimer timer(&s->host_ms[0]);
 		const int si = enq % s->n_slots;
 		SetSlot& ss = s->slots[si];
-		while (ss.busy) {
-			if (a_done == retired) { r = do_a(); if (r) return r; }
-			r = do_b(); if (r) return r;
-		}
-		HostTimer* timer = new HostTimer(&s->host_ms[0]);
 		ss.base = chunks[(size_t)enq].first;
 		ss.n = chunks[(size_t)enq].second;
 		ss.busy = true;
@@ -429,7 +436,11 @@ int set_pipeline(fdb_detector_set* s, const uint8_t* frames, bool frames_on_devi
 						(size_t)H * ss.n, cudaMemcpyHostToDevice, ss.st));
 			ss.frames_dev = ss.d_frames;
 		}
-		r = set_enqueue(s, si, dense_dev, nullptr); if (r) return r;
+		/* stage 1 of consecutive chunks runs in order (the copy above does not wait): chunks are enqueued as far ahead as there are
+		 * slots, and two chunks sharing the SMs would both finish late - the host phases of the first would start late */
+		if (enq > 0) CUDA_TRY(cudaStreamWaitEvent(ss.st, s->slots[(enq - 1) % s->n_slots].ev_s1_end, 0));
+		const int r2 = set_enqueue(s, si, dense_dev, nullptr); if (r2) return r2;
+		CUDA_TRY(cudaEventRecord(ss.ev_s1_end, ss.st));
 		for (int d = 0; d < nd; ++d) {
 			if (!s->fast[(size_t)d]) continue;
 			Slot& msl = s->dets[(size_t)d]->slots[si];
@@ -437,15 +448,18 @@ int set_pipeline(fdb_detector_set* s, const uint8_t* frames, bool frames_on_devi
 			CUDA_TRY(cudaEventRecord(msl.ev_stage1, ss.st));
 		}
 		++enq;
-		delete timer;
-		while (a_done < enq - 1) { r = do_a(); if (r) return r; }
-		while (retired < a_done - 1) { r = do_b(); if (r) return r; }
+		return FDB_OK;
+	};
+	for (;;) {
+		/* the GPU first: every free slot gets the next chunk before the host turns to its own phases */
+		while (enq < n_chunks && !s->slots[enq % s->n_slots].busy) { r = enqueue_next(); if (r) return r; }
+		if (a_done < enq) {
+			r = do_a(); if (r) return r;
+			if (retired < a_done - 1) { r = do_b(); if (r) return r; } /* phase B of the chunk before: its SVM kernels have had a chunk's time */
+		} else if (retired < a_done) {
+			r = do_b(); if (r) return r;
+		} else break;
 	}
-	while (a_done < n_chunks) {
-		r = do_a(); if (r) return r;
-		while (retired < a_done - 1) { r = do_b(); if (r) return r; }
-	}
-	while (retired < n_chunks) { r = do_b(); if (r) return r; }
 	for (int i = 0; i < s->n_slots; ++i) CUDA_TRY(cudaStreamSynchronize(s->slots[i].st));
 	return FDB_OK;
 }
@@ -460,6 +474,7 @@ int set_detect(fdb_detector_set* s, const uint8_t* frames, bool frames_on_device
 	const int nd = (int)s->dets.size();
 	std::vector<std::vector<fdb_detection>> results((size_t)nd);
 	std::fill(s->host_ms, s->host_ms + 8, 0.0);
+	s->trace = std::getenv("FDB_SET_TRACE") != nullptr;
 	HostTimer whole(&s->host_ms[3]);
 	for (int attempt = 0; attempt < nd + 1; ++attempt) {
 		for (auto& v : results) v.clear();
@@ -472,6 +487,19 @@ int set_detect(fdb_detector_set* s, const uint8_t* frames, bool frames_on_device
 		r = set_build_launches(s); if (r) return r; /* the packs must not name a member that left */
 	}
 	if (r) return r;
+	if (s->trace && s->trace_ev.size() >= 2) { /* stage-1 intervals of the chunks on the device clock: gaps = the GPU waiting for the host */
+		cudaEventSynchronize(s->trace_ev.back());
+		std::fprintf(stderr, "fdb_detector_set: stage 1 per chunk [begin, end] ms:");
+		for (size_t k = 0; k + 1 < s->trace_ev.size(); k += 2) {
+			float b = 0.f, e = 0.f;
+			cudaEventElapsedTime(&b, s->trace_ev[0], s->trace_ev[k]);
+			cudaEventElapsedTime(&e, s->trace_ev[0], s->trace_ev[k + 1]);
+			std::fprintf(stderr, " [%.1f, %.1f]", b, e);
+		}
+		std::fprintf(stderr, "\n");
+	}
+	for (cudaEvent_t e : s->trace_ev) cudaEventDestroy(e);
+	s->trace_ev.clear();
 	if (std::getenv("FDB_SET_TRACE"))
 		std::fprintf(stderr, "fdb_detector_set: enqueue %.1f wait %.1f phaseA %.1f (fetch %.1f host %.1f on %d threads, launch %.1f) phaseB %.1f ms\n", s->host_ms[0],
 				s->host_ms[4], s->host_ms[1], s->host_ms[5], s->host_ms[6], s->pool ? s->pool->threads() : 1, s->host_ms[7], s->host_ms[2]);
@@ -545,6 +573,7 @@ int fdb_detector_set_prepare(fdb_detector_set* s, int32_t width, int32_t height,
 		SetSlot& sl = s->slots[i];
 		CUDA_TRY(cudaStreamCreateWithFlags(&sl.st, cudaStreamNonBlocking));
 		CUDA_TRY(cudaEventCreateWithFlags(&sl.ev_fork, cudaEventDisableTiming));
+		CUDA_TRY(cudaEventCreateWithFlags(&sl.ev_s1_end, cudaEventDisableTiming));
 		for (int k = 0; k < SET_SIDE_STREAMS; ++k) {
 			CUDA_TRY(cudaStreamCreateWithFlags(&sl.side[k], cudaStreamNonBlocking));
 			CUDA_TRY(cudaEventCreateWithFlags(&sl.ev_join[k], cudaEventDisableTiming));

@@ -80,7 +80,7 @@ def test_fifteen_models_640x480_against_the_oracle(ctx, fifteen):
 
 @pytest.mark.gpu
 def test_set_equals_its_members_over_a_chunked_batch(ctx, fifteen):
-    """7 frames through the 3-slot pipeline (chunks of 2): the set's detections = each member's own fdb_detect_batch"""
+    """7 frames through the slot pipeline (chunks of 2): the set's detections = each member's own fdb_detect_batch"""
     models, cascs, dset = fifteen
     dset.prepare(640, 480, 7)
     frames = syn.synthetic_frames(70, 7)
