@@ -59,6 +59,25 @@ __global__ void __launch_bounds__(RS_QX * RS_TY) resize_kernel(const uint8_t* __
 	if (fast) { t0 = __ldg(xt); t1 = __ldg(xt + 1); t2 = __ldg(xt + 2); t3 = __ldg(xt + 3); }
 	const int wlast = (W >> 2) - 1;
 	const int b0 = (int)((uint32_t)t0.w >> 16), b1 = min(b0 + 1, wlast), b2 = min(b0 + 2, wlast);
+	/* word path: the 8 source bytes of a row that 4 adjacent outputs need lie within 12 bytes of a 4-aligned base (scale < 2):
+	 * three aligned 32-bit loads per row; the byte pairs (sx, sx + 1) of two outputs are gathered by two PRMT - one over the first
+	 * two words, one over its result and the third word - whose selectors depend on the column only (computed once per thread).
+	 * t.w = word select | bit shift << 8 | base word << 16, so the byte offset of sx in the 12 bytes is 4 * select + shift / 8 */
+	uint32_t sel1[2] = {0u, 0u}, sel2[2] = {0u, 0u};
+	if (fast) {
+		const int off[4] = {(t0.w & 255) * 4 + ((t0.w >> 8) & 31) / 8, (t1.w & 255) * 4 + ((t1.w >> 8) & 31) / 8,
+				(t2.w & 255) * 4 + ((t2.w >> 8) & 31) / 8, (t3.w & 255) * 4 + ((t3.w >> 8) & 31) / 8};
+#pragma unroll
+		for (int pr = 0; pr < 2; ++pr)
+#pragma unroll
+			for (int i = 0; i < 4; ++i) {
+				const int j = off[2 * pr + (i >> 1)] + (i & 1); /* source byte of output byte i of the pair: 0 .. 11 */
+				sel1[pr] |= (uint32_t)(j < 8 ? j : 0) << (4 * i);
+				sel2[pr] |= (uint32_t)(j < 8 ? i : j - 4) << (4 * i);
+			}
+	}
+	const uint32_t cxy0 = (uint32_t)t0.y | ((uint32_t)t0.z << 16), cxy1 = (uint32_t)t1.y | ((uint32_t)t1.z << 16); /* a0, a1 <= 2048 as two u16 */
+	const uint32_t cxy2 = (uint32_t)t2.y | ((uint32_t)t2.z << 16), cxy3 = (uint32_t)t3.y | ((uint32_t)t3.z << 16);
 #pragma unroll
 	for (int i = 0; i < RS_ROWS; ++i) {
 		const int dy = tile_y * (RS_TY * RS_ROWS) + i * RS_TY + ((int)threadIdx.x >> 5);
@@ -79,29 +98,23 @@ __global__ void __launch_bounds__(RS_QX * RS_TY) resize_kernel(const uint8_t* __
 			const uint8_t* __restrict__ s0 = src + y0 * W;
 			const uint8_t* __restrict__ s1 = src + y1 * W;
 			if (fast) {
-				/* word path: the 8 source bytes of a row that 4 adjacent outputs need lie within 12 bytes of a
-				 * 4-aligned base (scale < 2); three aligned 32-bit loads per row replace 8 byte gathers and the
-				 * byte pairs (sx, sx+1) are cut out with funnel shifts. t.w = word select | bit shift << 8 | base word << 16 */
 				const uint32_t* __restrict__ r0 = reinterpret_cast<const uint32_t*>(s0);
 				const uint32_t* __restrict__ r1 = reinterpret_cast<const uint32_t*>(s1);
 				const int by0 = ty.y << 16, by1 = ty.z << 16; /* coefficients <= 2048: no overflow; all factors are non-negative */
 				const uint32_t p0 = __ldg(r0 + b0), p1 = __ldg(r0 + b1), p2 = __ldg(r0 + b2);
 				const uint32_t q0 = __ldg(r1 + b0), q1 = __ldg(r1 + b1), q2 = __ldg(r1 + b2);
-#define FDB_RS_PAIR(A0, A1, A2, T) __funnelshift_r(((T.w & 255) == 0 ? A0 : ((T.w & 255) == 1 ? A1 : A2)), \
-						((T.w & 255) == 0 ? A1 : A2), (unsigned)((T.w >> 8) & 31))
-#define FDB_RS_PIXW(T) { const uint32_t up = FDB_RS_PAIR(p0, p1, p2, T), lo = FDB_RS_PAIR(q0, q1, q2, T); \
-					const uint32_t cxy = (uint32_t)T.y | ((uint32_t)T.z << 16); /* a0, a1 <= 2048 as two u16 */ \
-					const int h0 = (int)__dp2a_lo(cxy, up, 0u); /* S[sx] * a0 + S[sx + 1] * a1: the two low bytes of `up` */ \
-					const int h1 = (int)__dp2a_lo(cxy, lo, 0u); \
-					v = (__mulhi(by0, h0 >> 4) + __mulhi(by1, h1 >> 4) + 2) >> 2; } /* (b * (h >> 4)) >> 16 as the high word of (b << 16) * (h >> 4) */
-				int v;
-				FDB_RS_PIXW(t0) packed = (uint32_t)(v & 255);
-				FDB_RS_PIXW(t1) packed |= (uint32_t)(v & 255) << 8;
-				FDB_RS_PIXW(t2) packed |= (uint32_t)(v & 255) << 16;
-				FDB_RS_PIXW(t3) packed |= (uint32_t)(v & 255) << 24;
-#undef FDB_RS_PIXW
-#undef FDB_RS_PAIR
-			} else {
+				/* {S[sx_a], S[sx_a + 1], S[sx_b], S[sx_b + 1]} of the upper and the lower source row, outputs (0, 1) and (2, 3) */
+				const uint32_t up01 = __byte_perm(__byte_perm(p0, p1, sel1[0]), p2, sel2[0]), lo01 = __byte_perm(__byte_perm(q0, q1, sel1[0]), q2, sel2[0]);
+				const uint32_t up23 = __byte_perm(__byte_perm(p0, p1, sel1[1]), p2, sel2[1]), lo23 = __byte_perm(__byte_perm(q0, q1, sel1[1]), q2, sel2[1]);
+				/* S[sx] * a0 + S[sx + 1] * a1 (dp2a on the low / high byte pair), then (b * (h >> 4)) >> 16 as the high word of (b << 16) * (h >> 4) */
+#define FDB_RS_OUT(H0, H1) ((__mulhi(by0, (int)(H0) >> 4) + __mulhi(by1, (int)(H1) >> 4) + 2) >> 2)
+				const int v0 = FDB_RS_OUT(__dp2a_lo(cxy0, up01, 0u), __dp2a_lo(cxy0, lo01, 0u));
+				const int v1 = FDB_RS_OUT(__dp2a_hi(cxy1, up01, 0u), __dp2a_hi(cxy1, lo01, 0u));
+				const int v2 = FDB_RS_OUT(__dp2a_lo(cxy2, up23, 0u), __dp2a_lo(cxy2, lo23, 0u));
+				const int v3 = FDB_RS_OUT(__dp2a_hi(cxy3, up23, 0u), __dp2a_hi(cxy3, lo23, 0u));
+#undef FDB_RS_OUT
+				packed = (uint32_t)(v0 & 255) | ((uint32_t)(v1 & 255) << 8) | ((uint32_t)(v2 & 255) << 16) | ((uint32_t)(v3 & 255) << 24);
+		} else {
 				for (int k = 0; k < nvalid; ++k) {
 					const int4 tx = __ldg(xt + k);
 					const int sx = tx.x, sx1 = min(sx + 1, W - 1);

@@ -612,7 +612,11 @@ FDB_API int fdb_evaluate_samples(fdb_detector* det, const uint8_t* frame_host, i
  * image once per frame and equalises windows of the same layer and size once for all members that scan them.
  * Members: cascade detectors (WVM first stage) of the same context; the set does not own them (destroy the set first).
  * Results are ordered by member, then frame, then as fdb_detect_batch orders them; fdb_detection.reserved = member index;
- * per-member counters through fdb_detector_last_counts. */
+ * per-member counters through fdb_detector_last_counts.
+ * Environment (diagnostics, never needed): FDB_WINDOW_KERNEL=mma|tc forces one of the two window kernels (default: the tcgen05
+ * kernel for packs of three and four detectors of one window geometry, the mma.sync kernel otherwise - same results);
+ * FDB_HOST_THREADS=n sizes the post-processing pool (default: the affinity mask, at most 16); FDB_SET_TRACE=1 prints the host
+ * phases and the stage-1 intervals of every chunk on the device clock to stderr. */
 FDB_API int fdb_detector_set_create(fdb_ctx* ctx, fdb_detector* const* detectors, int32_t n_detectors, fdb_detector_set** out);
 FDB_API void fdb_detector_set_destroy(fdb_detector_set* set);
 /* prepares every member (fdb_detector_prepare) and the shared pyramid / work tables for frames of width x height */
