@@ -1266,7 +1266,7 @@ def main():
     import torch
     import torch.distributed as dist
     from featuredetection_b200 import sharding
-    from featuredetection_b200.detector import Context
+    from featuredetection_b200.detector import Context, DETECTION_DTYPE
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device - the B200 path has no CPU fallback (use --impl reference for the CPU arm)")
@@ -1282,6 +1282,8 @@ def main():
     lo, _ = sharding.shard_range(n * world, rank, world)
     n_det = len(cascade_names(args.workload))
     gather = sharding.DetectionGather(max(256, 64 * n) * n_det, dist, device) if world > 1 else None
+    if gather is not None:  # set-up, like loading the models: NCCL connects the ranks for a collective when it is first used
+        gather(np.zeros(0, DETECTION_DTYPE), lo)
     sampler = ClockSampler(local_rank)
     m = measure_cascades(args, args.workload, args.feature, n, rank, world, device, ctx, dist, args.steps, args.warmup,
                          sampler=sampler, gather=gather, lo=lo)

@@ -19,10 +19,10 @@ def shard_range(n_frames, rank, world):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
-def pack_detections(dets, frame_offset, capacity):
-    """structured detections -> [capacity + 1, len(GATHER_FIELDS)] float64 block; row 0 holds the
-    count (and an overflow flag); frame indices become global."""
-    block = np.zeros((capacity + 1, len(GATHER_FIELDS)), np.float64)
+def pack_detections(dets, frame_offset, capacity, rows=None):
+    """structured detections -> [capacity + 1, len(GATHER_FIELDS)] float64 block (or its first `rows` rows, rows > number
+    of detections kept); row 0 holds the count (and an overflow flag); frame indices become global."""
+    block = np.zeros((capacity + 1 if rows is None else rows, len(GATHER_FIELDS)), np.float64)
     n = min(len(dets), capacity)
     block[0, 0] = len(dets)
     block[0, 1] = 1.0 if len(dets) > capacity else 0.0
@@ -66,13 +66,16 @@ def gather_detections(dets, frame_offset, capacity, dist, device=None, dst=0):
 class DetectionGather:
     """Reusable gather with preallocated buffers (pinned host + device), double-buffered so that the gather of
     step k overlaps the computation of step k+1: submit() enqueues H2D + all_gather + D2H on a side stream and
-    returns a ticket, collect(ticket) waits for it and unpacks on the destination rank."""
+    returns a ticket, collect(ticket) waits for it and unpacks on the destination rank.
+    Blocks travel padded to the largest rank's count, not to the capacity (a first, 8-byte all_gather tells every rank
+    that count), and only the destination rank copies the gathered blocks to the host."""
 
     def __init__(self, capacity, dist, device=None):
         import torch
         self.torch, self.dist, self.device, self.capacity = torch, dist, device, int(capacity)
         self.world = dist.get_world_size()
-        shape = (self.capacity + 1, len(GATHER_FIELDS))
+        self.fields = len(GATHER_FIELDS)
+        shape = (self.capacity + 1, self.fields)
         pin = device is not None
         self.bufs = []
         for _ in range(2):
@@ -82,22 +85,31 @@ class DetectionGather:
                 b["d_in"] = torch.zeros(shape, dtype=torch.float64, device=device)
                 b["d_out"] = torch.zeros((self.world,) + shape, dtype=torch.float64, device=device)
             self.bufs.append(b)
+        self.count_in = torch.zeros(1, dtype=torch.int64, device=device)
+        self.count_out = torch.zeros(self.world, dtype=torch.int64, device=device)
         self.stream = torch.cuda.Stream(device) if device is not None else None
         self.turn = 0
 
-    def submit(self, dets, frame_offset):
+    def submit(self, dets, frame_offset, dst=0):
         torch = self.torch
         b = self.bufs[self.turn]
         self.turn ^= 1
-        b["h_in"].numpy()[...] = pack_detections(dets, frame_offset, self.capacity)
-        b["dtype"] = dets.dtype
+        n = min(len(dets), self.capacity)
+        self.count_in.fill_(n)
+        self.dist.all_gather_into_tensor(self.count_out, self.count_in)
+        rows = int(self.count_out.max().item()) + 1  # row 0 of a block: count and overflow flag
+        b["rows"], b["dtype"] = rows, dets.dtype
+        used = rows * self.fields
+        b["h_in"].numpy()[:rows] = pack_detections(dets, frame_offset, self.capacity, rows)
         if self.device is None:
-            self.dist.all_gather_into_tensor(b["h_out"].view(-1), b["h_in"].view(-1))
+            self.dist.all_gather_into_tensor(b["h_out"].view(-1)[:self.world * used], b["h_in"].view(-1)[:used])
         else:
+            self.stream.wait_stream(torch.cuda.current_stream(self.device))
             with torch.cuda.stream(self.stream):
-                b["d_in"].copy_(b["h_in"], non_blocking=True)
-                self.dist.all_gather_into_tensor(b["d_out"].view(-1), b["d_in"].view(-1))
-                b["h_out"].copy_(b["d_out"], non_blocking=True)
+                b["d_in"].view(-1)[:used].copy_(b["h_in"].view(-1)[:used], non_blocking=True)
+                self.dist.all_gather_into_tensor(b["d_out"].view(-1)[:self.world * used], b["d_in"].view(-1)[:used])
+                if self.dist.get_rank() == dst:
+                    b["h_out"].view(-1)[:self.world * used].copy_(b["d_out"].view(-1)[:self.world * used], non_blocking=True)
                 b["event"] = torch.cuda.Event()
                 b["event"].record(self.stream)
         return b
@@ -107,7 +119,9 @@ class DetectionGather:
             ticket["event"].synchronize()
         if self.dist.get_rank() != dst:
             return None
-        return unpack_detections(list(ticket["h_out"].numpy()), ticket["dtype"])
+        rows = ticket["rows"]
+        blocks = ticket["h_out"].view(-1)[:self.world * rows * self.fields].view(self.world, rows, self.fields)
+        return unpack_detections(list(blocks.numpy()), ticket["dtype"])
 
     def __call__(self, dets, frame_offset, dst=0):
-        return self.collect(self.submit(dets, frame_offset), dst)
+        return self.collect(self.submit(dets, frame_offset, dst), dst)
