@@ -12,7 +12,8 @@
  *   6-bit histogram bins; lane = window throughout:
  *     - sliding 64-bin histogram down the lane's column (one pixel row leaves, one enters: 2 PW fire-and-forget shared
  *       atomics), u16 counts packed two lanes per word, column layout (conflict free);
- *     - sequential float32 cumulative histogram -> the window's equalisation table, one byte column per lane;
+ *     - sequential float32 cumulative histogram -> the window's equalisation table, one column of words per lane (a bank
+ *       per lane: look-ups never conflict; wvm_group_dev.cuh);
  *     - per patch row: equalised pixels of the lane's window (aligned word loads + funnel shift, 4 table look-ups per
  *       word) -> 32 bytes of the window's row of the A operand in shared memory; sum(x^2) accumulates per patch row in
  *       the reference's float32 order (IImg.cpp:33-47) from dp4a row sums;
@@ -20,9 +21,10 @@
  *       B[pixel][filter, value] (rectangle coverage counts, fragment order prepared on the host) for every model of the
  *       pack from the SAME A fragments - the equalisation is shared by the models of a pack. Exact: sums < 2^24.
  *       K runs over patch rows padded to 32 bytes (one k-step per patch row; two rows per k-step for 16-wide windows),
- *       so no index arithmetic separates the window from the operand.  The contraction stays on the legacy mma.sync
- *       path on purpose: K <= 768, N = 32 per model and the A operand is produced by the consuming warp, which leaves
- *       nothing for a tcgen05 + TMEM pipeline to amortise (the tensor pipe is < 15 % busy).
+ *       so no index arithmetic separates the window from the operand.  This kernel serves packs of one and two models
+ *       (32 accumulator registers per model); packs of three and four run on wvm_group_tc.cu (tcgen05.mma, accumulators in
+ *       tensor memory). For small packs mma.sync measures faster on the B200: its warps are independent (16 per SM), while the
+ *       four warps of a UMMA tile walk in step and wait for the slowest one - launch_wvm_group picks by pack size.
  *     - D goes through shared memory (over the table and the A buffers, which are dead by then) and the scalar cascade
  *       tail runs per lane and model; survivors of all WVM_KA filters are queued for the deep kernel.
  *

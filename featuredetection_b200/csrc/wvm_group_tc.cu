@@ -20,6 +20,14 @@
  *     window, 4 columns = the grey-value sums of one filter) and run the scalar cascade tail per model as before
  *     (WvmClassifier.cpp:129-138,191-346); survivors of all WVM_KA filters are queued for the deep kernel.
  *
+ * Measured on the B200 (profiles/NOTES_r2.md): packs of 4 + 3 detectors of one 24 x 24 grid take 6.8 ms per 16-frame chunk
+ * against 9.2 ms as 2 + 2 + 2 + 1 on the mma.sync kernel; for packs of 1-2 the mma.sync kernel is faster, so launch_wvm_group
+ * sends only packs of 3-4 here. 4 CTAs per SM (55.8 KB shared memory, 96 registers, 128 tensor-memory columns each) beat 3 by
+ * 16 %; deeper slab / B rings changed nothing - a producer's waiting time is the tile's slowest warp, whose cascade tail is
+ * longer. Two rewrites of the tail that looked better on paper measured slower and were dropped: compacting the surviving
+ * (window, model) pairs of a row into full passes (45 % fewer filter evaluations, but gathering sums and state across lanes
+ * lengthens the dependency chain of each pass), and interleaving two models' cascades in straight-line code.
+ *
  * Exactness: u8 x u8 -> s32 with sums < 2^24, identical to the integral-image rectangle sums of the reference.
  */
 #include <cuda.h>
