@@ -221,6 +221,90 @@ __global__ void __launch_bounds__(SVM_THREADS) svm_f32_rbf_block_kernel(const De
 	if (tid < nw) distance_out[v0 + tid] = distance;
 }
 
+/* RBF SVM on HistEq64 windows of frames, SVMU_W windows per CTA: svm_kernel<0> streams the whole model (num_sv x nwords words,
+ * 590 KB for 1024 vectors of 24 x 24) from L2 once per stage-1 survivor - 177 GB per 256-frame step of the 15 landmark detectors.
+ * Here warp w equalises window w of the block (HistEq64Filter.cpp:32-125, the sequential float32 cumulative histogram on its lane
+ * 0), then a thread owns one support vector of the chunk and keeps SVMU_W integer sums of squared differences, so every model
+ * word that arrives is used for SVMU_W windows. Arithmetic and order are those of svm_kernel<0>: exact integer SSD
+ * (RbfKernel.hpp:39,78-88), exp in double, coefficient product, the double sum over the support vectors in their order
+ * (SvmClassifier.cpp:55-60) - the distances are bit-identical. */
+#define SVMU_W 8
+static_assert(SVMU_W * 32 == SVM_THREADS, "one warp per window of the block");
+__global__ void __launch_bounds__(SVM_THREADS) svm_u8_rbf_block_kernel(const DevSvm s, int patch_w, int patch_h,
+		const uint8_t* __restrict__ frames, int W, int H, const uint8_t* __restrict__ arena, int64_t arena_stride,
+		const DevLayer* __restrict__ layers, const SvmItem* __restrict__ items, int n_items, double* __restrict__ distance_out) {
+	extern __shared__ __align__(16) unsigned char svmu_smem[];
+	double* s_prod = reinterpret_cast<double*>(svmu_smem);                                        /* [SVMU_W][SVM_THREADS] */
+	uint32_t* s_x = reinterpret_cast<uint32_t*>(svmu_smem + sizeof(double) * SVMU_W * SVM_THREADS); /* [nwords][SVMU_W] */
+	__shared__ uint32_t s_hist[SVMU_W][64];
+	__shared__ uint8_t s_eq[SVMU_W][64];
+	const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+	const int v0 = blockIdx.x * SVMU_W;
+	const int nw = min(SVMU_W, n_items - v0);
+	for (int i = tid; i < s.nwords * SVMU_W; i += SVM_THREADS) s_x[i] = 0;
+	s_hist[w][lane] = 0; s_hist[w][lane + 32] = 0;
+	__syncthreads();
+	if (w < nw) { /* warp w: window v0 + w */
+		const SvmItem it = items[v0 + w];
+		const DevLayer L = layers[it.layer];
+		const uint8_t* img = (L.offset < 0 ? frames + (int64_t)it.frame * W * H
+				: arena + (int64_t)it.frame * arena_stride + L.offset) + (int64_t)it.y * L.pitch + it.x;
+		const int npix = patch_w * patch_h;
+		for (int i = lane; i < npix; i += 32) {
+			const int r = i / patch_w, c = i - r * patch_w;
+			atomicAdd(&s_hist[w][img[(int64_t)r * L.pitch + c] >> 2], 1u);
+		}
+		__syncwarp();
+		if (lane == 0) { /* sequential float cumsum, HistEq64Filter.cpp:70-87,97 */
+			const float stretch = __fdiv_rn(255.0f, (float)npix);
+			float cdf = 0.f;
+			for (int b = 0; b < 64; ++b) {
+				cdf = __fadd_rn(cdf, __fmul_rn((float)s_hist[w][b], stretch));
+				const float fl = floorf(cdf);
+				s_eq[w][b] = (uint8_t)((int)fl + (__fsub_rn(cdf, fl) >= 0.5f ? 1 : 0));
+			}
+		}
+		__syncwarp();
+		for (int i = lane; i < npix; i += 32) {
+			const int r = i / patch_w, c = i - r * patch_w;
+			const uint32_t e = s_eq[w][img[(int64_t)r * L.pitch + c] >> 2];
+			atomicOr(&s_x[(i >> 2) * SVMU_W + w], e << (8 * (i & 3)));
+		}
+	}
+	__syncthreads();
+	double distance = -(double)s.bias; /* thread t < nw: the hyperplane distance of window v0 + t (SvmClassifier.cpp:56) */
+	for (int base = 0; base < s.num_sv; base += SVM_THREADS) {
+		const int cnt = min(SVM_THREADS, s.num_sv - base);
+		if (tid < cnt) {
+			const int sv = base + tid;
+			const uint32_t* __restrict__ col = s.sv_words + sv;
+			uint32_t acc[SVMU_W];
+#pragma unroll
+			for (int k = 0; k < SVMU_W; ++k) acc[k] = 0;
+			for (int j = 0; j < s.nwords; ++j) {
+				const uint32_t c = col[(size_t)j * s.num_sv];
+				const uint4 xa = *reinterpret_cast<const uint4*>(s_x + j * SVMU_W), xb = *reinterpret_cast<const uint4*>(s_x + j * SVMU_W + 4);
+				const uint32_t x[SVMU_W] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+#pragma unroll
+				for (int k = 0; k < SVMU_W; ++k) {
+					const uint32_t d = __vabsdiffu4(x[k], c);
+					acc[k] = __dp4a(d, d, acc[k]);
+				}
+			}
+			const double coef = (double)s.coef[sv];
+#pragma unroll
+			for (int k = 0; k < SVMU_W; ++k)
+				s_prod[k * SVM_THREADS + tid] = __dmul_rn(coef, exp(__dmul_rn(-s.gamma, (double)(int)acc[k])));      /* SvmClassifier.cpp:58 */
+		}
+		__syncthreads();
+		if (tid < nw) for (int i = 0; i < cnt; ++i) distance = __dadd_rn(distance, s_prod[tid * SVM_THREADS + i]);
+		__syncthreads();
+	}
+	if (tid < nw) distance_out[v0 + tid] = distance;
+}
+
+static size_t svmu_smem_bytes(const DevSvm& s) { return sizeof(double) * SVMU_W * SVM_THREADS + sizeof(uint32_t) * (size_t)s.nwords * SVMU_W; }
+
 static size_t svmb_smem_bytes(const DevSvm& s) { return sizeof(double) * SVMB_W * SVM_THREADS + sizeof(float) * (size_t)s.dim * SVMB_W; }
 
 /* HistEq64 patches (HistEq64Filter.cpp:32-125) of a list of windows -> [n][patch_w * patch_h] u8: the patch data of
@@ -277,6 +361,7 @@ int svm_configure() {
 	if (e == cudaSuccess) e = cudaFuncSetAttribute(svm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
 	if (e == cudaSuccess) e = cudaFuncSetAttribute(svm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
 	if (e == cudaSuccess) e = cudaFuncSetAttribute(svm_f32_rbf_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
+	if (e == cudaSuccess) e = cudaFuncSetAttribute(svm_u8_rbf_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
 	return (int)e;
 }
 
@@ -284,6 +369,12 @@ void launch_svm_windows(cudaStream_t st, const DevSvm& s, int patch_w, int patch
 		const uint8_t* arena, int64_t arena_stride, const DevLayer* layers, const SvmItem* items, int n_items,
 		double* distance_out, int* level_out) {
 	if (n_items == 0) return;
+	if (s.sv_type != FDB_SV_F32 && s.kernel == FDB_KERNEL_RBF && s.rvm_filters == 0 && !level_out && n_items >= 2 * SVMU_W
+			&& svmu_smem_bytes(s) <= 128 * 1024) {
+		svm_u8_rbf_block_kernel<<<(unsigned)((n_items + SVMU_W - 1) / SVMU_W), SVM_THREADS, svmu_smem_bytes(s), st>>>(s, patch_w, patch_h,
+				frames, W, H, arena, arena_stride, layers, items, n_items, distance_out);
+		return;
+	}
 	svm_kernel<0><<<(unsigned)n_items, SVM_THREADS, svm_smem_bytes(s), st>>>(s, patch_w, patch_h, frames, W, H, arena,
 			arena_stride, layers, items, nullptr, distance_out, level_out);
 }
